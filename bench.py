@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py - headline measurement of the hot path (BASELINE.json: env-steps/sec; TD3 updates/sec rides along).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at every N (weak scaling, per GPU): BASELINE.json configs[1] - a batched dynamics rollout of 4096 envs,
+random actions U(-7.5, 7.5), 1000 steps.  One bench "step" = one such rollout = ONE launch of env_rollout_kernel.
+Inputs rotate through enough distinct action/trajectory buffers that the footprint exceeds the 126 MB L2.
+Prints ONE JSON line on rank 0 (see the task contract); `--impl reference` times the CPU oracle port instead.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS = 4096          # configs[1]
+T_STEPS = 1000       # configs[1]
+ACTION_RANGE = 7.5
+SEED = 1707366464
+ROLL_BYTES_PER_ENV_STEP = 16   # 8 B action read + 8 B state written; state stays in registers
+STEP_BYTES_PER_ENV_STEP = 24   # single-step kernel: state in 8 + action in 8 + state out 8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.in_region = False
+        self._stop = threading.Event()
+        self.ok = False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.in_region:
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """Scalar oracle port: the reference's own per-env Python loop (environment.py:122-127) on this worker's envs."""
+    lo, hi, t_steps, seed = args
+    from oracle import env_oracle as eo
+    speed, angle = eo.synthetic_maps(0)
+    rs = np.random.RandomState(seed)
+    n = hi - lo
+    states = rs.uniform(0, 98.9999, (n, 2))
+    actions = rs.uniform(-ACTION_RANGE, ACTION_RANGE, (t_steps, n, 2))
+    t0 = time.perf_counter()
+    for i in range(n):
+        s = states[i]
+        for t in range(t_steps):
+            s = eo.step_scalar(speed, angle, s, actions[t, i])
+    return time.perf_counter() - t0, n * t_steps
+
+
+def cpu_env_steps(envs, t_steps, procs, pool=None):
+    """env-steps/s of the oracle port over `procs` worker processes (each one GIL-bound core)."""
+    bounds = np.linspace(0, envs, procs + 1).astype(int)
+    jobs = [(int(bounds[k]), int(bounds[k + 1]), t_steps, 100 + k) for k in range(procs) if bounds[k + 1] > bounds[k]]
+    t0 = time.perf_counter()
+    if pool is None:
+        res = [_cpu_worker(j) for j in jobs]
+    else:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[1] for r in res)
+    return total / wall, wall, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    t_sample = 8                                       # 4096 envs x 8 steps per bench step (bounded sample)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        for _ in range(args.warmup):
+            cpu_env_steps(ENVS, t_sample, procs, pool)
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(args.steps):
+            _, _, n = cpu_env_steps(ENVS, t_sample, procs, pool)
+            total += n
+        wall = time.perf_counter() - t0
+    value = total / wall
+    sample = "%d envs x %d of the %d rollout steps per bench step, scalar oracle port (oracle/env_oracle.py step_scalar), %d processes" % (
+        ENVS, t_sample, T_STEPS, procs)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched dynamics rollout: %d envs x %d steps, random actions (configs[1])" % (ENVS, T_STEPS)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import rtd3_b200 as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, _, peak_kind = load_peaks()
+
+    n, T = args.envs, args.T
+    speed, angle = rt.synthetic_maps(0)
+    env = rt.Environment(num_envs=n, seed=SEED + rank * n, maps=(speed, angle), device=dev)   # env shard of this rank
+    env.reset()
+    start = env.robot_state.clone()
+
+    # rotating inputs: R action buffers + R trajectory buffers, footprint > L2 (126 MB)
+    per_buf = T * 2 * n * 4
+    R = max(2, int(np.ceil(160e6 / per_buf)) + 1)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts = [(torch.rand((T, 2, n), device=dev, generator=gen) * (2 * ACTION_RANGE) - ACTION_RANGE) for _ in range(R)]
+    L = rt._lib.lib()
+    trajs = [torch.empty((T, 2, n), dtype=torch.float32, device=dev) for _ in range(R)]
+    stream = torch.cuda.current_stream(dev)
+    sp = rt._lib.stream_ptr(dev)
+
+    def one_step(k):
+        rt._lib.check(L.rtd3_env_rollout(env._handle, rt._lib.ptr(env._state[0]), rt._lib.ptr(env._state[1]),
+                                         rt._lib.ptr(acts[k % R]), rt._lib.ptr(trajs[k % R]), n, T, sp))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    for k in range(args.warmup):
+        one_step(k)
+    barrier()
+    rt._lib.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.in_region = True
+    e0.record(stream)
+    for k in range(args.steps):
+        one_step(args.warmup + k)
+    e1.record(stream)
+    barrier()
+    launches = rt._lib.launch_count()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    env_steps_total = float(n) * T * args.steps * world
+    value = env_steps_total / (ms * 1e-3)
+
+    # ---- e2e: host action buffers -> public API -> host trajectory, copies inside the timed region
+    h_act = [torch.empty((T, 2, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for b in h_act:
+        b.uniform_(-ACTION_RANGE, ACTION_RANGE)
+    h_traj = [torch.empty((T, 2, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step(k):
+        d_act = h_act[k % 2].to(dev, non_blocking=True)
+        traj = env.rollout(d_act, record=True)                         # public API ([T,2,N] planes in, [T,N,2] view out)
+        h_traj[k % 2].copy_(traj.permute(0, 2, 1), non_blocking=True)
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    e0.record(stream)
+    for k in range(e2e_steps):
+        e2e_step(k)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = float(n) * T * e2e_steps * world / (e2e_ms * 1e-3)
+
+    # ---- side measurements on rank 0: single-step kernel at HBM-sized batches (24 B/env-step), both table paths
+    extra = {}
+    if rank == 0 and not args.no_sweep:
+        sweep = []
+        for big in (1 << 20, 1 << 24):
+            bx = [torch.rand((2, big), device=dev) * 98 for _ in range(3)]          # 3 rotating sets: > L2 at 16M
+            ba = [torch.rand((2, big), device=dev) * 15 - 7.5 for _ in range(3)]
+            for variant, name in ((1, "smem"), (2, "ldg")):
+                def go(k):
+                    rt._lib.check(L.rtd3_env_step(env._handle, rt._lib.ptr(bx[k % 3][0]), rt._lib.ptr(bx[k % 3][1]),
+                                                  rt._lib.ptr(ba[k % 3][0]), rt._lib.ptr(ba[k % 3][1]), big, variant, sp))
+                for k in range(3):
+                    go(k)
+                torch.cuda.synchronize(dev)
+                reps = 30
+                e0.record(stream)
+                for k in range(reps):
+                    go(k)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                us = e0.elapsed_time(e1) * 1e3 / reps
+                gbs = big * STEP_BYTES_PER_ENV_STEP / (us * 1e-6) / 1e9
+                sweep.append({"kernel": "env_step_kernel/" + name, "envs": big, "us": round(us, 2),
+                              "env_steps_per_sec": big / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
+            del bx, ba
+        extra["step_kernel_sweep"] = sweep
+    sampler.in_region = False
+    sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1 only): scalar oracle port on all host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            cpu_env_steps(procs * 4, 8, procs, pool)                                   # warm the workers
+            t_sample = 16
+            v_all, wall, total = cpu_env_steps(ENVS, t_sample, procs, pool)
+        v_one, _, _ = cpu_env_steps(64, 16, 1, None)
+        cpu = {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
+               "sample": "%d envs x %d steps (%.1f s wall) of the rollout, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
+                         % (ENVS, t_sample, wall, procs, v_one)}
+
+    if rank == 0:
+        us_per_launch = ms * 1e3 / args.steps
+        alg_bytes = float(n) * T * ROLL_BYTES_PER_ENV_STEP
+        achieved = alg_bytes / (us_per_launch * 1e-6) / 1e9
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batched dynamics rollout: %d envs x %d steps per GPU, random actions U(-7.5,7.5) (configs[1])" % (n, T),
+                       "envs_per_gpu": n, "rollout_steps": T, "kernel": "env_rollout_kernel<traj>",
+                       "l2": "inputs rotate over %d action + %d trajectory buffers (%.0f MB > 126 MB L2)" % (R, R, 2 * R * per_buf / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind,
+                         "note": "%d B per env-step (action in 8 B, state out 8 B; state lives in registers) x %d env-steps per launch; "
+                                 "4096 envs = 128 warps on 148 SMs, so this config is latency-bound (see step_kernel_sweep for HBM-sized batches)"
+                                 % (ROLL_BYTES_PER_ENV_STEP, n * T)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": per_buf, "d2h_bytes_per_step": per_buf,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS)
+    ap.add_argument("--T", type=int, default=T_STEPS)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""ctypes binding of csrc/librtd3.so (the C ABI declared in include/rtd3.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_uint32, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librtd3.so")
+
+
+class Rtd3Error(RuntimeError):
+    pass
+
+
+class MtBankStruct(Structure):
+    _fields_ = [("mt", c_void_p), ("pos", c_void_p), ("has_gauss", c_void_p), ("gauss", c_void_p), ("n", c_int64)]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "rtd3_version": (c_int32, []),
+    "rtd3_last_error": (c_char_p, []),
+    "rtd3_launch_count": (c_int64, []),
+    "rtd3_launch_count_reset": (None, []),
+    "rtd3_env_create": (c_int32, [POINTER(c_void_p), c_int32]),
+    "rtd3_env_destroy": (c_int32, [_P]),
+    "rtd3_env_set_map": (c_int32, [_P, _P, _P, _P]),
+    "rtd3_env_step": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int32, _P]),
+    "rtd3_env_dynamics": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rtd3_env_rollout": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
+    "rtd3_mt_seed": (c_int32, [POINTER(MtBankStruct), _P, _P]),
+    "rtd3_mt_draw_u32": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
+    "rtd3_mt_draw_gauss": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
+    "rtd3_env_init_goal_region": (c_int32, [POINTER(MtBankStruct), _P, _P, _P]),
+    "rtd3_env_reset": (c_int32, [POINTER(MtBankStruct), _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every symbol include/rtd3.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "librtd3.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C residual-td3-robot-navigation_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the .so is stale: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().rtd3_last_error().decode("utf-8", "replace")
+        raise Rtd3Error("librtd3 call failed (%d) %s: %s" % (code, what, msg))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def launch_count():
+    return int(lib().rtd3_launch_count())
+
+
+def launch_count_reset():
+    lib().rtd3_launch_count_reset()

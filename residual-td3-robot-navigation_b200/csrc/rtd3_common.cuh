@@ -1,0 +1,86 @@
+// Shared host/device helpers for librtd3 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rtd3.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "librtd3 targets sm_100a (B200) only"
+#endif
+
+namespace rtd3 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define RTD3_CHECK_ARG(cond, msg)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      ::rtd3::set_error("%s: %s", __func__, msg);                   \
+      return RTD3_ERR_ARG;                                          \
+    }                                                               \
+  } while (0)
+
+#define RTD3_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::rtd3::set_error("%s: %s -> %s", __func__, #expr, cudaGetErrorString(_e));         \
+      return (int32_t)_e;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+// Every launch goes through this so gpu_launches in bench.py is a count, not a guess.
+#define RTD3_LAUNCHED()                     \
+  do {                                      \
+    ::rtd3::count_launch();                 \
+    RTD3_CUDA(cudaGetLastError());          \
+  } while (0)
+
+constexpr float kMaxAction = 5.0f;                 // constants.py:34
+constexpr float kClipHi = 98.9999f;                // float32(WORLD_SIZE - 1.0001), environment.py:117
+constexpr int kWorld = RTD3_WORLD_SIZE;
+constexpr int kCells = RTD3_MAP_CELLS;
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// np.clip semantics: NaN passes through (fminf/fmaxf would swallow it).
+__device__ __forceinline__ float clip_keep_nan(float v, float lo, float hi) {
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// ---- mbarrier + bulk-async (TMA) copy primitives, sm_90+/sm_100a PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace rtd3

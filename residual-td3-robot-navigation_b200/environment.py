@@ -1,0 +1,220 @@
+"""`Environment`: the reference's world (environment.py:14-183) batched over `num_envs` independent envs on one B200.
+
+Call surface kept from the reference:
+    attrs   robot_state, goal_state, robot_init_region ([left,right,bottom,top]), dynamics_speed, dynamics_angle
+    methods step(action) -> state, reset() -> state, dynamics(state, action) -> next_state (pure),
+            compute_reward(path), get_random_robot_init_state(), set_init_and_goal(), set_dynamics()
+With `num_envs == 1` (the default) calls take / return numpy `[2]` float64 arrays like the reference and, unless a
+seed is given, draw from numpy's *global* legacy MT19937 stream exactly as the reference does.  With
+`num_envs > 1` they take / return CUDA tensors `[N,2]` (views of plane-major `[2,N]` storage, so no copies).
+
+All arithmetic happens in csrc/librtd3.so (hand-written sm_100a kernels); there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _lib, configuration, constants
+from .rng import MtBank
+
+STEP_AUTO, STEP_SMEM, STEP_LDG = 0, 1, 2
+
+
+def synthetic_maps(seed=0):
+    """Benchmark maps: low-pass filtered uniform noise `u`, speed = sigmoid(10*(u-0.5))
+    (the reference's stretch, environment.py:81-83), angle = u; float32 `[100,100]` indexed `[x][y]`.
+    The reference's own Perlin generator is an unpinned third-party package; maps are inputs here."""
+    W = constants.WORLD_SIZE
+    u = np.random.RandomState(seed).rand(W, W)
+    for _ in range(3):
+        p = np.pad(u, 1, mode="edge")
+        u = (p[1:-1, 1:-1] + p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:]) / 5.0
+    u = ((u - u.min()) / (u.max() - u.min())).astype(np.float32)
+    speed = (1 / (1 + np.exp(-10 * (u - 0.5)))).astype(np.float32)
+    return speed, u.copy()
+
+
+def _planes(t, n, name):
+    """[N,2] (any strides) or [2,N] CUDA float32 -> contiguous [2,N] planes; zero-copy when already plane-backed."""
+    if t.dim() != 2:
+        raise ValueError("%s must be 2-D" % name)
+    if t.shape == (n, 2):          # documented layout; for n == 2 a [2,2] tensor is read as [N,2]
+        t = t.t()
+    elif t.shape != (2, n):
+        raise ValueError("%s must have shape [%d,2]" % (name, n))
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Environment:
+    def __init__(self, num_envs=1, device=None, seed=None, maps=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("Environment needs a CUDA device (B200); there is no CPU path")
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        n = self.num_envs
+        self._handle = _lib.c_void_p()
+        _lib.check(_lib.lib().rtd3_env_create(_lib.ctypes.byref(self._handle), self.device.index or 0), "env_create")
+        self._state = torch.zeros((2, n), dtype=torch.float32, device=self.device)        # x plane, y plane
+        self._state64 = torch.zeros((2, n), dtype=torch.float64, device=self.device)      # last reset draw (float64)
+        self._goal = torch.zeros((2, n), dtype=torch.float64, device=self.device)
+        self._region = torch.zeros((4, n), dtype=torch.float64, device=self.device)       # left,right,bottom,top
+        self._bank = MtBank(n, self.device)
+        # single env + no seed: mirror numpy's global stream like the reference (robot-learning.py:19-22)
+        self._numpy_global = (n == 1 and seed is None)
+        if not self._numpy_global:
+            self._bank.seed(configuration.RANDOM_SEED if seed is None else seed)
+        self.step_variant = STEP_AUTO
+        self.set_init_and_goal()
+        if maps is None:
+            self.set_dynamics()
+        else:
+            self.set_maps(*maps)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().rtd3_env_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ---- RNG plumbing -------------------------------------------------------------------------------
+    def _rng_in(self):
+        if self._numpy_global:
+            self._bank.sync_from_numpy()
+
+    def _rng_out(self):
+        if self._numpy_global:
+            self._bank.sync_to_numpy()
+
+    # ---- reference attributes -----------------------------------------------------------------------
+    @property
+    def robot_state(self):
+        if self.num_envs == 1:
+            return self._state[:, 0].double().cpu().numpy()
+        return self._state.t()
+
+    @robot_state.setter
+    def robot_state(self, value):
+        if self.num_envs == 1 and not isinstance(value, torch.Tensor):
+            value = torch.as_tensor(np.asarray(value, dtype=np.float32).reshape(1, 2))
+        self._state.copy_(_planes(value.to(self.device), self.num_envs, "robot_state"))
+
+    @property
+    def goal_state(self):
+        if self.num_envs == 1:
+            return self._goal[:, 0].cpu().numpy()
+        return self._goal.t()
+
+    @property
+    def robot_init_region(self):
+        if self.num_envs == 1:
+            return self._region[:, 0].cpu().numpy()
+        return self._region.t()
+
+    # ---- environment.py:28-56 -----------------------------------------------------------------------
+    def set_init_and_goal(self):
+        self._rng_in()
+        _lib.check(_lib.lib().rtd3_env_init_goal_region(self._bank.ref, _lib.ptr(self._goal), _lib.ptr(self._region),
+                                                        _lib.stream_ptr(self.device)), "env_init_goal_region")
+        self._rng_out()
+
+    # ---- environment.py:59-95 (map contents are inputs; generator parity is unpinned) ------------------
+    def set_dynamics(self):
+        self.set_maps(*synthetic_maps(0))
+
+    def set_maps(self, speed, angle):
+        W = constants.WORLD_SIZE
+        speed = torch.as_tensor(np.asarray(speed.cpu() if isinstance(speed, torch.Tensor) else speed, dtype=np.float32))
+        angle = torch.as_tensor(np.asarray(angle.cpu() if isinstance(angle, torch.Tensor) else angle, dtype=np.float32))
+        if speed.shape != (W, W) or angle.shape != (W, W):
+            raise ValueError("maps must be [%d,%d]" % (W, W))
+        self.dynamics_speed = speed.numpy().copy()
+        self.dynamics_angle = angle.numpy().copy()
+        self._speed_dev = speed.contiguous().to(self.device)
+        self._angle_dev = angle.contiguous().to(self.device)
+        _lib.check(_lib.lib().rtd3_env_set_map(self._handle, _lib.ptr(self._speed_dev), _lib.ptr(self._angle_dev),
+                                               _lib.stream_ptr(self.device)), "env_set_map")
+
+    # ---- environment.py:98-119 ----------------------------------------------------------------------
+    def dynamics(self, state, action):
+        single = not isinstance(state, torch.Tensor)
+        if single:
+            s = torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(1, 2)).to(self.device)
+            a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 2)).to(self.device)
+        else:
+            s, a = state, action
+        n = s.shape[0]
+        sp, ap = _planes(s, n, "state"), _planes(a, n, "action")
+        out = torch.empty((2, n), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().rtd3_env_dynamics(self._handle, _lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(ap[0]),
+                                                _lib.ptr(ap[1]), _lib.ptr(out[0]), _lib.ptr(out[1]), n,
+                                                _lib.stream_ptr(self.device)), "env_dynamics")
+        if single:
+            return out[:, 0].double().cpu().numpy()
+        return out.t()
+
+    # ---- environment.py:122-127 ---------------------------------------------------------------------
+    def step(self, action):
+        n = self.num_envs
+        if not isinstance(action, torch.Tensor):
+            action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(n, 2)).to(self.device)
+        ap = _planes(action, n, "action")
+        _lib.check(_lib.lib().rtd3_env_step(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
+                                            _lib.ptr(ap[0]), _lib.ptr(ap[1]), n, self.step_variant,
+                                            _lib.stream_ptr(self.device)), "env_step")
+        return self.robot_state
+
+    def rollout(self, actions, record=True):
+        """T calls of `step` in one launch.  `actions`: CUDA float32 `[T,N,2]` backed by `[T,2,N]` planes
+        (e.g. `planes.permute(0,2,1)`) or a contiguous `[T,2,N]` tensor.  Returns the trajectory `[T,N,2]`
+        (a view of `[T,2,N]` planes) if `record`, else None; `robot_state` ends at the final state."""
+        n = self.num_envs
+        if actions.dim() != 3:
+            raise ValueError("actions must be [T,N,2] or [T,2,N]")
+        if actions.shape[1:] == (n, 2):
+            planes = actions.permute(0, 2, 1)
+        else:
+            planes = actions
+        if planes.shape[1:] != (2, n):
+            raise ValueError("actions must be [T,%d,2] or [T,2,%d]" % (n, n))
+        if planes.dtype != torch.float32:
+            planes = planes.float()
+        planes = planes if planes.is_contiguous() else planes.contiguous()
+        T = planes.shape[0]
+        traj = torch.empty((T, 2, n), dtype=torch.float32, device=self.device) if record else None
+        _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
+                                               _lib.ptr(planes), _lib.ptr(traj), n, T,
+                                               _lib.stream_ptr(self.device)), "env_rollout")
+        return traj.permute(0, 2, 1) if record else None
+
+    # ---- environment.py:130-137 ---------------------------------------------------------------------
+    def reset(self, mask=None):
+        """Redraw the start state inside the fixed init region (all envs, or those where `mask` is set)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._rng_in()
+        _lib.check(_lib.lib().rtd3_env_reset(self._bank.ref, _lib.ptr(self._region), _lib.ptr(m), _lib.ptr(self._state[0]),
+                                             _lib.ptr(self._state[1]), _lib.ptr(self._state64),
+                                             _lib.stream_ptr(self.device)), "env_reset")
+        self._rng_out()
+        if self.num_envs == 1:
+            return self._state64[:, 0].cpu().numpy()      # the reference returns the float64 draw itself
+        return self.robot_state
+
+    def get_random_robot_init_state(self):
+        """environment.py:135-137: a draw that does not move the robot."""
+        keep = self._state.clone()
+        out = self.reset()
+        out = out.copy() if self.num_envs == 1 else out.clone()
+        self._state.copy_(keep)
+        return out
+
+    # ---- environment.py:182-183 ---------------------------------------------------------------------
+    def compute_reward(self, path):
+        if self.num_envs == 1 and not isinstance(path, torch.Tensor):
+            return -np.linalg.norm(np.asarray(path)[-1] - self.goal_state)
+        last = path[-1].to(torch.float64)                      # [N,2]
+        return -torch.linalg.norm(last - self._goal.t(), dim=1)

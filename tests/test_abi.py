@@ -1,0 +1,64 @@
+"""The C-ABI library loads and exports every symbol include/rtd3.h declares (no compute calls: runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rtd3.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtd3_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_something():
+    syms = declared_symbols()
+    assert "rtd3_env_step" in syms and "rtd3_version" in syms
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    path = pkg._lib.LIB_PATH
+    assert os.path.isfile(path), "librtd3.so not built: run __graft_entry__.build()"
+    L = ctypes.CDLL(path)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header(pkg):
+    assert pkg._lib.exported_symbols() == declared_symbols()
+
+
+def test_version_and_error_string(pkg):
+    L = pkg._lib.lib()
+    assert L.rtd3_version() == 100
+    assert isinstance(L.rtd3_last_error(), bytes)
+
+
+def test_argument_errors_are_reported_without_a_gpu(pkg):
+    L = pkg._lib.lib()
+    rc = L.rtd3_env_step(None, None, None, None, None, 4, 0, None)
+    assert rc == -1
+    assert b"rtd3_env_step" in L.rtd3_last_error() or b"launch_step" in L.rtd3_last_error()
+    with pytest.raises(pkg._lib.Rtd3Error):
+        pkg._lib.check(rc, "env_step")
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        pkg.Environment()
+
+
+def test_product_does_not_import_oracle():
+    pkg_dir = os.path.join(ROOT, "residual-td3-robot-navigation_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
