@@ -248,7 +248,7 @@ def run_b200(args):
     extra = {}
     if rank == 0 and not args.no_sweep:
         sweep = []
-        for big in (1 << 20, 1 << 24):
+        for big in (1 << 20, 1 << 22, 1 << 24):
             bx = [torch.rand((2, big), device=dev) * 98 for _ in range(3)]          # 3 rotating sets: > L2 at 16M
             ba = [torch.rand((2, big), device=dev) * 15 - 7.5 for _ in range(3)]
             for variant, name in ((1, "smem"), (2, "ldg")):

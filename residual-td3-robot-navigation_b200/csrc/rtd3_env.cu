@@ -26,26 +26,58 @@ __global__ void build_table_kernel(const float* __restrict__ speed, const float*
   double s, c;
   sincos((double)rot, &s, &c);
   double sp = (double)speed[i];
-  table[i] = make_float2((float)(sp * c), (float)(sp * s));
+  float tc = (float)(sp * c), ts = (float)(sp * s);
+  // A non-finite map cell would make the reference raise (int(nan)); here it becomes a dead cell so that the
+  // state recurrence below can never leave [0, 100) and index out of the table.
+  if (!isfinite(tc) || !isfinite(ts)) { tc = 0.0f; ts = 0.0f; }
+  table[i] = make_float2(tc, ts);
 }
 
-// One env: the rotation form of environment.py:100-117 (no atan2):
+// One env-step, the rotation form of environment.py:100-117 (no atan2):
 //   s' = clip(s + speed*(ax*cos(rot) - ay*sin(rot), ax*sin(rot) + ay*cos(rot)), 0, 98.9999)
-template <typename TableT>
-__device__ __forceinline__ void dynamics_one(const TableT& table, float x, float y, float ax, float ay, float& nx,
-                                             float& ny) {
+// split into the part that does not depend on the state (StepIn, off the dependent chain of a rollout) and the
+// state recurrence itself, which is FADD.RZ -> IMAD -> IMAD -> LDS.64 -> FFMA -> FFMA -> FMNMX -> FMNMX.
+struct StepIn {
+  float ax, ay;   // clipped action (np.clip keeps NaN), zeroed when NaN
+  float lo, hi;   // clip bounds: [0, 98.9999], or [-inf, +inf] when the action is NaN so that the state is kept
+  bool bad;       // NaN action: environment.py:125 rejects the (NaN) next state and keeps robot_state
+};
+
+__device__ __forceinline__ StepIn prep_action(float ax, float ay) {
+  StepIn in;
   ax = clip_keep_nan(ax, -kMaxAction, kMaxAction);
   ay = clip_keep_nan(ay, -kMaxAction, kMaxAction);
-  int cx = min(max(__float2int_rz(x), 0), kWorld - 1);   // int(state[0]); clamped only for memory safety
-  int cy = min(max(__float2int_rz(y), 0), kWorld - 1);
-  float2 cs = table[cx * kWorld + cy];
-  nx = clip_keep_nan(x + fmaf(ax, cs.x, -ay * cs.y), 0.0f, kClipHi);
-  ny = clip_keep_nan(y + fmaf(ax, cs.y, ay * cs.x), 0.0f, kClipHi);
+  in.bad = (ax != ax) || (ay != ay);
+  in.ax = in.bad ? 0.0f : ax;
+  in.ay = in.bad ? 0.0f : ay;
+  in.lo = in.bad ? -INFINITY : 0.0f;
+  in.hi = in.bad ? INFINITY : kClipHi;
+  return in;
 }
 
-// environment.py:125 - accept unless NaN (the clip already bounds everything else)
-__device__ __forceinline__ bool in_world(float nx, float ny) {
-  return nx >= 0.0f && nx < (float)kWorld && ny >= 0.0f && ny < (float)kWorld;
+// s' from (s, table entry). Two dependent FFMAs per axis; the only roundings are at the magnitude of the state.
+__device__ __forceinline__ void advance(float2 cs, const StepIn& in, float& x, float& y) {
+  const float nx = fmaf(in.ax, cs.x, fmaf(-in.ay, cs.y, x));
+  const float ny = fmaf(in.ax, cs.y, fmaf(in.ay, cs.x, y));
+  x = fminf(fmaxf(nx, in.lo), in.hi);
+  y = fminf(fmaxf(ny, in.lo), in.hi);
+}
+
+// int(state) -> cell, clamped so that any input stays inside the table (used by the single-step kernels)
+__device__ __forceinline__ int cell_index(float x, float y) {
+  const int cx = min(max(__float2int_rz(x), 0), kWorld - 1);
+  const int cy = min(max(__float2int_rz(y), 0), kWorld - 1);
+  return cx * kWorld + cy;
+}
+
+template <bool kKeepOnNan, typename TableT>
+__device__ __forceinline__ void step_one(const TableT& table, float x, float y, float ax, float ay, float& ox, float& oy) {
+  const StepIn in = prep_action(ax, ay);
+  const float2 cs = table[cell_index(x, y)];
+  advance(cs, in, x, y);
+  if (!kKeepOnNan && in.bad) { x = NAN; y = NAN; }   // pure dynamics(): the NaN propagates
+  ox = x;
+  oy = y;
 }
 
 struct LdgTable {
@@ -78,15 +110,6 @@ __device__ __forceinline__ void stage_table(float2* s_table, uint64_t* bar, cons
 // ---- single step over n envs ------------------------------------------------------------------
 // Each thread owns 4 consecutive envs per iteration: four 16 B loads (x,y,ax,ay) and two 16 B stores,
 // all coalesced (a warp covers 512 B contiguous per plane).  kKeepOnNan=false gives pure dynamics().
-template <bool kKeepOnNan, typename TableT>
-__device__ __forceinline__ void step_one(const TableT& table, float x, float y, float ax, float ay, float& ox, float& oy) {
-  float nx, ny;
-  dynamics_one(table, x, y, ax, ay, nx, ny);
-  const bool keep = kKeepOnNan && !in_world(nx, ny);
-  ox = keep ? x : nx;
-  oy = keep ? y : ny;
-}
-
 template <bool kSmem, bool kKeepOnNan>
 __global__ void __launch_bounds__(kSmem ? 512 : 256, kSmem ? 2 : 4)
 env_step_kernel(const float2* __restrict__ g_table, const float* __restrict__ x, const float* __restrict__ y,
@@ -144,59 +167,100 @@ env_step_kernel(const float2* __restrict__ g_table, const float* __restrict__ x,
 
 // ---- T-step rollout: state stays in registers, table in smem, actions prefetched kU steps ahead ----
 constexpr int kU = 16;
+constexpr int kDeep = 8;      // chunks in flight per thread, latency-bound launches (128 steps of lead)
+constexpr int kShallow = 2;   // chunks in flight per thread, occupancy-bound launches
 
-template <bool kTraj>
+// The dependent chain of one rollout step.  trunc(x) comes from a round-toward-zero add of 2^23 (the low mantissa
+// bits of x + 2^23 are floor(x) for 0 <= x < 2^23), so the shared-memory byte address is two IMADs away from the state:
+//   addr = bits(x+2^23)*800 + bits(y+2^23)*8 + (table_base - 0x4B000000*808)
+__device__ __forceinline__ void rollout_step(uint32_t addr_bias, const StepIn& in, float& x, float& y) {
+  const uint32_t bx = __float_as_uint(__fadd_rz(x, 8388608.0f));
+  const uint32_t by = __float_as_uint(__fadd_rz(y, 8388608.0f));
+  const uint32_t addr = bx * 800u + (by * 8u + addr_bias);
+  float2 cs;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cs.x), "=f"(cs.y) : "r"(addr));
+  advance(cs, in, x, y);
+}
+
+// Actions reach the SM through a per-thread cp.async ring in shared memory: kStages chunks of kU steps are in
+// flight, so the HBM latency (~1 us) is hidden even when a CTA is a single warp (4096 envs on 148 SMs); every
+// thread reads back only the words it copied itself, so cp.async.wait_group is the only synchronisation.
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const float* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kN>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
+
+template <bool kTraj, int kStages>
 __global__ void __launch_bounds__(256)
 env_rollout_kernel(const float2* __restrict__ g_table, float* __restrict__ x, float* __restrict__ y,
                    const float* __restrict__ actions, float* __restrict__ traj, int64_t n, int64_t T) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* s_table = reinterpret_cast<float2*>(smem_raw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes);
-  stage_table(s_table, bar, g_table);
+  float* ring = reinterpret_cast<float*>(smem_raw + kTableBytes + 16);   // [kStages][kU][2][blockDim]
+  stage_table(s_table, bar, g_table);   // contains the only __syncthreads of the kernel
 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const int64_t ii = live ? i : 0;
-  float sx = x[ii], sy = y[ii];
-  const float* a = actions + ii;          // ax(t) = a[(2t)*n], ay(t) = a[(2t+1)*n]
-  float* tr = traj + ii;
+  if (i >= n) return;                   // thread 0 of every launched CTA is live, so the bulk copy always has an owner
+  // Sanitise once: inside [0, 100) the recurrence can never leave the table (finite table, clamped or kept state).
+  // States outside the world are invalid input for the reference as well (IndexError at environment.py:107).
+  float sx = fminf(fmaxf(x[i], 0.0f), 99.99999f);
+  float sy = fminf(fmaxf(y[i], 0.0f), 99.99999f);
   const int64_t n2 = 2 * n;
+  const float* pa = actions + i;        // ax(t) = pa[0], ay(t) = pa[n]; advances by 2n per step
+  float* pt = traj + i;
+  const uint32_t addr_bias = smem_u32(s_table) - 0x4B000000u * 808u;
+  const uint32_t bd = blockDim.x;
+  const uint32_t my_ring = smem_u32(ring) + threadIdx.x * 4u;
+  const uint32_t stage_bytes = kU * 2u * bd * 4u;
 
-  float bax[kU], bay[kU];
-  auto load_chunk = [&](int64_t t0) {
+  const int64_t full = T / kU;          // chunks of kU steps without per-step bounds checks
+  auto issue_chunk = [&](int64_t c) {   // chunk c -> ring slot c % kStages
+    if (c < full) {
+      const float* src = pa + c * (kU * n2);
+      const uint32_t dst = my_ring + (uint32_t)(c % kStages) * stage_bytes;
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t t = t0 + u;
-      if (t < T) {
-        bax[u] = __ldcs(a + t * n2);
-        bay[u] = __ldcs(a + t * n2 + n);
+      for (int u = 0; u < kU; ++u) {
+        cp_async4(dst + (2 * u) * bd * 4u, src + u * n2);
+        cp_async4(dst + (2 * u + 1) * bd * 4u, src + u * n2 + n);
       }
     }
+    cp_async_commit();                  // always commit, so that group counting stays uniform
   };
-  load_chunk(0);
-  mbar_wait(bar, 0);
-  SmemTable table{s_table};
-
-  for (int64_t t0 = 0; t0 < T; t0 += kU) {
-    float cax[kU], cay[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) { cax[u] = bax[u]; cay[u] = bay[u]; }
-    if (t0 + kU < T) load_chunk(t0 + kU);
+  for (int sgi = 0; sgi < kStages; ++sgi) issue_chunk(sgi);
+  mbar_wait(bar, 0);
+
+  for (int64_t c = 0; c < full; ++c) {
+    cp_async_wait<kStages - 1>();       // chunk c has landed
+    StepIn in[kU];
+    const uint32_t src = my_ring + (uint32_t)(c % kStages) * stage_bytes;
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t t = t0 + u;
-      if (t < T) {
-        float nx, ny;
-        dynamics_one(table, sx, sy, cax[u], cay[u], nx, ny);
-        if (in_world(nx, ny)) { sx = nx; sy = ny; }
-        if (kTraj && live) {
-          __stcs(tr + t * n2, sx);
-          __stcs(tr + t * n2 + n, sy);
-        }
-      }
+      float ax, ay;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ax) : "r"(src + (2 * u) * bd * 4u));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ay) : "r"(src + (2 * u + 1) * bd * 4u));
+      in[u] = prep_action(ax, ay);
+    }
+    issue_chunk(c + kStages);           // refill the slot just drained (its values are in registers now)
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      rollout_step(addr_bias, in[u], sx, sy);
+      if (kTraj) { __stcs(pt, sx); __stcs(pt + n, sy); pt += n2; }
     }
   }
-  if (live) { x[i] = sx; y[i] = sy; }
+  pa += full * (kU * n2);
+  for (int64_t t = full * kU; t < T; ++t) {   // ragged tail, T % kU steps
+    const StepIn in = prep_action(__ldcs(pa), __ldcs(pa + n));
+    pa += n2;
+    rollout_step(addr_bias, in, sx, sy);
+    if (kTraj) { __stcs(pt, sx); __stcs(pt + n, sy); pt += n2; }
+  }
+  cp_async_wait<0>();
+  x[i] = sx;
+  y[i] = sy;
 }
 
 // ---- seeded init / reset on per-env legacy MT19937 streams ------------------------------------
@@ -266,7 +330,8 @@ __global__ void env_reset_kernel(rtd3_mt_bank b, const double* __restrict__ regi
   MtStream s{b.mt + i, n, b.pos[i]};
   const double sx = s.uniform(region[i], region[n + i]);           // x in [left, right)
   const double sy = s.uniform(region[2 * n + i], region[3 * n + i]);   // y in [bottom, top)
-  x[i] = (float)sx; y[i] = (float)sy;
+  // float32 rounding must not reach 100.0 (the cell index would leave the map): cap at the largest float below it
+  x[i] = fminf((float)sx, 99.99999f); y[i] = fminf((float)sy, 99.99999f);
   if (state64) { state64[i] = sx; state64[n + i] = sy; }
   b.pos[i] = s.pos;
 }
@@ -297,8 +362,11 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   const int smem = kTableBytes + 16;
   RTD3_CUDA(cudaFuncSetAttribute(env_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   RTD3_CUDA(cudaFuncSetAttribute(env_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem_roll = 200 * 1024;
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;
@@ -362,13 +430,23 @@ int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, 
   RTD3_CHECK_ARG(n >= 0 && T >= 0, "negative n or T");
   if (n == 0 || T == 0) return 0;
   RTD3_CHECK_ARG(x && y && actions, "null state/action pointer");
-  // spread small batches over all SMs (latency-bound: one dependent chain per env), cap CTA size at 256
-  int64_t per_sm = ceil_div(n, (int64_t)h->num_sms);
-  int block = (int)std::min<int64_t>(256, std::max<int64_t>(32, ceil_div(per_sm, 32) * 32));
+  // Small batches are latency-bound (one dependent chain per env): spread them over all SMs in CTAs as small as a
+  // warp and keep kDeep chunks of actions in flight per thread.  Large batches hide latency with occupancy instead:
+  // 128-thread CTAs, kShallow chunks in flight, up to 2 CTAs per SM next to the 80 KB table.
+  const int64_t per_sm = ceil_div(n, (int64_t)h->num_sms);
+  const bool deep = per_sm <= 64;
+  const int block = deep ? (int)std::max<int64_t>(32, ceil_div(per_sm, 32) * 32) : 128;
   const int grid = (int)ceil_div(n, block);
-  const int smem = kTableBytes + 16;
-  if (traj) env_rollout_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(h->table, x, y, actions, traj, n, T);
-  else env_rollout_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(h->table, x, y, actions, nullptr, n, T);
+  const int stages = deep ? kDeep : kShallow;
+  const int smem = kTableBytes + 16 + stages * kU * 2 * block * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (deep) {
+    if (traj) env_rollout_kernel<true, kDeep><<<grid, block, smem, st>>>(h->table, x, y, actions, traj, n, T);
+    else env_rollout_kernel<false, kDeep><<<grid, block, smem, st>>>(h->table, x, y, actions, nullptr, n, T);
+  } else {
+    if (traj) env_rollout_kernel<true, kShallow><<<grid, block, smem, st>>>(h->table, x, y, actions, traj, n, T);
+    else env_rollout_kernel<false, kShallow><<<grid, block, smem, st>>>(h->table, x, y, actions, nullptr, n, T);
+  }
   RTD3_LAUNCHED();
   return 0;
 }
