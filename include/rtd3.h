@@ -104,6 +104,75 @@ int32_t rtd3_env_init_goal_region(const rtd3_mt_bank* bank, double* goal, double
 int32_t rtd3_env_reset(const rtd3_mt_bank* bank, const double* region, const uint8_t* mask, float* x, float* y,
                        double* state64, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Replay ring + minibatch sampling           (robot.py:58-124)
+ * Device layout (36 B per row): s [cap][2], a [cap][2], r [cap], s2 [cap][2], notdone [cap]  float32.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ReplayBuffer.push (robot.py:79-96) for n transitions given as env planes; rows go to
+ * (position + i) % capacity; the caller advances position/size.  done: uint8 [n]. */
+int32_t rtd3_replay_push(float* s, float* a, float* r, float* s2, float* notdone, int64_t capacity, int64_t position,
+                         const float* sx, const float* sy, const float* ax, const float* ay, const float* reward,
+                         const float* nx, const float* ny, const uint8_t* done, int64_t n, void* stream);
+
+/* The gather half of ReplayBuffer.sample (robot.py:113-115): rows idx[b] -> dense minibatch arrays. */
+int32_t rtd3_replay_gather(const float* s, const float* a, const float* r, const float* s2, const float* notdone,
+                           const int32_t* idx, int32_t batch, float* out_s, float* out_a, float* out_r, float* out_s2,
+                           float* out_notdone, void* stream);
+
+/* The index half of ReplayBuffer.sample (robot.py:111): `count` consecutive draws of
+ * np.random.choice(n, batch, replace=False) from stream `stream_id` of the bank, bit-exact with numpy's
+ * legacy shuffle.  out: int32 [count][batch].  scratch: int32 [n], only needed when n > 48000. */
+int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t stream_id, int32_t n, int32_t batch, int32_t count,
+                                    int32_t* out, int32_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Residual-TD3 learner                        (robot.py:128-206 networks, :209-398 TD3)
+ * Networks: actor 2->H->..->H->2, critic 4->H->..->H->1 with `layers` hidden layers (reference: H=200, 3).
+ * Parameters live in ONE float32 arena owned by the caller:
+ *   [actor | critic1 | critic2 | target actor | target critic1 | target critic2]
+ * every slot in torch's parameters() order (W1 [H][in], b1, W2 [H][H], b2, ..., Wout [out][H], bout) and
+ * padded to a multiple of 4 floats.  grads / adam_m / adam_v cover the first three slots.
+ * steps: int32 [2] on the device = Adam step counters {actor optimiser, critic optimisers}.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rtd3_td3 rtd3_td3;
+
+int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t layers);
+int32_t rtd3_td3_destroy(rtd3_td3* h);
+/* net: 0 actor, 1 critic1, 2 critic2, 3 target actor, 4 target critic1, 5 target critic2 */
+int64_t rtd3_td3_param_count(const rtd3_td3* h, int32_t net);
+int64_t rtd3_td3_param_offset(const rtd3_td3* h, int32_t net);
+int64_t rtd3_td3_arena_floats(const rtd3_td3* h);
+
+/* TD3.train_critic minus the optimiser steps (robot.py:326-357/361): gathers rows idx[batch] from the
+ * replay ring, target-policy smoothing with the supplied unit-normal noise [batch][2] (robot.py:338-339),
+ * clipped double-Q target (robot.py:342-345), both critic forward passes, both MSE losses (added into
+ * loss2[0..1], which the caller zeroes) and both backward passes (gradients ADDED into grads, which the
+ * caller keeps zeroed between steps - rtd3_td3_adam_polyak re-zeroes what it consumes).
+ * q_out (nullable) [2][batch] receives Q1,Q2(s,a) before the update, y_out (nullable) [batch] the targets.
+ * Increments steps[1]. */
+int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const float* rp_a,
+                             const float* rp_r, const float* rp_s2, const float* rp_notdone, const int32_t* idx,
+                             const float* noise, int32_t batch, float gamma, float policy_noise, float noise_clip,
+                             float max_action, float* loss2, float* q_out, float* y_out, int32_t* steps, void* stream);
+
+/* TD3.train_actor minus the optimiser step (robot.py:382-394): loss = -mean(Q1(s, pi(s))) added into
+ * loss1[0]; gradient w.r.t. the actor parameters only, ADDED into grads.  Increments steps[0]. */
+int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const int32_t* idx,
+                            int32_t batch, float* loss1, int32_t* steps, void* stream);
+
+/* torch.optim.Adam step (lr, betas 0.9/0.999, eps 1e-8; robot.py:237-239, 356-363, 393-395) on the nets
+ * selected by `nets` (bit 0 actor, bit 1 critic1, bit 2 critic2) using grads*grad_scale (grad_scale = 1/world
+ * after a gradient all-reduce), zeroing the consumed gradients; then TD3.soft_update (robot.py:293-310)
+ * on the target nets selected by `polyak` (same bit layout) with the freshly updated online parameters. */
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const int32_t* steps,
+                             int32_t nets, float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau,
+                             void* stream);
+
+/* Forward of one network of the arena (robot.py:153-159 / 193-200): x [batch][in] -> y [batch][out]. */
+int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* x, float* y, int64_t batch,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,406 @@
+"""Replay ring and residual-TD3 learner of the reference (robot.py:58-398) on one B200.
+
+Same names and call surface as the reference:
+    ReplayBuffer(capacity).push / sample / __len__                                   robot.py:58-124
+    Residual_Actor_Network(), Residual_Critic_Network()  (.layer_1 ... .output_layer) robot.py:128-206
+    TD3(actor, critic1, critic2, ...).td3_update / train_critic / train_actor / soft_update
+                                                                                     robot.py:209-398
+All arithmetic runs in csrc/librtd3.so; torch tensors only own the memory.  The replay rows live in a
+device-side SoA ring; a TD3 update draws its 150 minibatch index sets with the numpy-legacy MT19937
+protocol on the device (bit-exact with `np.random.choice(len, B, replace=False)`).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, constants
+from .rng import MtBank
+
+# robot.py:36, 46-54
+BUFFER_SIZE = 10000
+ACTOR_LR = 0.00001
+CRITIC_LR = 0.00001
+POLICY_UPDATE_DELAY = 2
+TARGET_POLICY_NOISE = 0.2
+NOISE_CLIP = 0.5
+TD3_EPOCHS = 100
+TD3_BATCH_SIZE = 100
+GAMMA = 0.99
+TAU = 0.001
+
+HIDDEN = 200     # robot.py:145-148
+LAYERS = 3
+
+NET_ACTOR, NET_CRITIC1, NET_CRITIC2, NET_T_ACTOR, NET_T_CRITIC1, NET_T_CRITIC2 = range(6)
+
+
+def _device(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("the learner needs a CUDA device (B200); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+# ------------------------------------------------------------------------------------------------ replay ring
+class ReplayBuffer:
+    """robot.py:58-124 as a device ring: s,a,s2 `[cap,2]`, r, notdone `[cap]` float32 (36 B per row)."""
+
+    def __init__(self, capacity, device=None, seed=None):
+        self.capacity = int(capacity)
+        self.device = _device(device)
+        c = self.capacity
+        self.s = torch.zeros((c, 2), dtype=torch.float32, device=self.device)
+        self.a = torch.zeros((c, 2), dtype=torch.float32, device=self.device)
+        self.r = torch.zeros((c,), dtype=torch.float32, device=self.device)
+        self.s2 = torch.zeros((c, 2), dtype=torch.float32, device=self.device)
+        self.notdone = torch.ones((c,), dtype=torch.float32, device=self.device)
+        self.position = 0
+        self.size = 0
+        # index draws come from numpy's global legacy stream (like the reference) unless a seed is given
+        self._bank = MtBank(1, self.device)
+        self._numpy_global = seed is None
+        if seed is not None:
+            self._bank.seed(seed)
+        self._scratch = None
+
+    def __len__(self):
+        return self.size
+
+    def _advance(self, n):
+        self.position = (self.position + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def push(self, state, action, reward, next_state, done):
+        """One transition (numpy / python scalars, like the reference) or n transitions (`[n,2]` / `[n]` CUDA tensors)."""
+        if isinstance(state, torch.Tensor) and state.dim() == 2:
+            n = state.shape[0]
+            s, a, s2 = state.t().contiguous().float(), action.t().contiguous().float(), next_state.t().contiguous().float()
+            return self.push_planes(s[0], s[1], a[0], a[1], reward.float().contiguous(), s2[0], s2[1],
+                                    done.to(torch.uint8).contiguous(), n)
+        row = np.concatenate([np.asarray(state, np.float32).reshape(2), np.asarray(action, np.float32).reshape(2),
+                              np.asarray([reward], np.float32), np.asarray(next_state, np.float32).reshape(2)])
+        t = torch.from_numpy(row).to(self.device)
+        d = torch.tensor([1 if done else 0], dtype=torch.uint8, device=self.device)
+        self.push_planes(t[0:1], t[1:2], t[2:3], t[3:4], t[4:5], t[5:6], t[6:7], d, 1)
+
+    def push_planes(self, sx, sy, ax, ay, reward, nx, ny, done, n):
+        """n transitions given as env planes (the layout the env / transition kernels produce)."""
+        if n > self.capacity:
+            raise ValueError("cannot push more rows than the ring holds in one call")
+        _lib.check(_lib.lib().rtd3_replay_push(_lib.ptr(self.s), _lib.ptr(self.a), _lib.ptr(self.r), _lib.ptr(self.s2),
+                                               _lib.ptr(self.notdone), self.capacity, self.position, _lib.ptr(sx), _lib.ptr(sy),
+                                               _lib.ptr(ax), _lib.ptr(ay), _lib.ptr(reward), _lib.ptr(nx), _lib.ptr(ny),
+                                               _lib.ptr(done), n, _lib.stream_ptr(self.device)), "replay_push")
+        self._advance(n)
+
+    def sample_indices(self, batch_size, count=1):
+        """`count` consecutive `np.random.choice(len, batch_size, replace=False)` draws -> int32 `[count, B]` (device)."""
+        if self.size < batch_size:
+            return None
+        out = torch.empty((count, batch_size), dtype=torch.int32, device=self.device)
+        scratch = None
+        if self.size > 48000:
+            if self._scratch is None or self._scratch.numel() < self.size:
+                self._scratch = torch.empty((self.capacity,), dtype=torch.int32, device=self.device)
+            scratch = self._scratch
+        if self._numpy_global:
+            self._bank.sync_from_numpy()
+        _lib.check(_lib.lib().rtd3_sample_indices_mt19937(self._bank.ref, 0, self.size, batch_size, count, _lib.ptr(out),
+                                                          _lib.ptr(scratch), _lib.stream_ptr(self.device)), "sample_indices")
+        if self._numpy_global:
+            self._bank.sync_to_numpy()
+        return out
+
+    def gather(self, idx):
+        B = idx.numel()
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        os_, oa, os2 = (torch.empty((B, 2), dtype=torch.float32, device=self.device) for _ in range(3))
+        orw, ond = (torch.empty((B,), dtype=torch.float32, device=self.device) for _ in range(2))
+        _lib.check(_lib.lib().rtd3_replay_gather(_lib.ptr(self.s), _lib.ptr(self.a), _lib.ptr(self.r), _lib.ptr(self.s2),
+                                                 _lib.ptr(self.notdone), _lib.ptr(idx), B, _lib.ptr(os_), _lib.ptr(oa),
+                                                 _lib.ptr(orw), _lib.ptr(os2), _lib.ptr(ond), _lib.stream_ptr(self.device)),
+                   "replay_gather")
+        return os_, oa, orw, os2, ond
+
+    def sample(self, batch_size, as_torch=False):
+        """robot.py:98-115: None when under-filled, else (states, actions, rewards, next_states, dones)."""
+        idx = self.sample_indices(batch_size, 1)
+        if idx is None:
+            return None
+        s, a, r, s2, nd = self.gather(idx[0])
+        dones = nd < 0.5
+        if as_torch:
+            return s, a, r, s2, dones
+        return tuple(t.cpu().numpy() for t in (s, a, r, s2, dones))
+
+
+# ------------------------------------------------------------------------------------------------ network objects
+def _layer_dims(in_dim, hidden, layers, out_dim):
+    dims = [in_dim] + [hidden] * layers + [out_dim]
+    return list(zip(dims[:-1], dims[1:]))
+
+
+class _LayerView:
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+
+class _Network:
+    """A network whose parameters are either its own CPU init (before TD3 adopts it) or views of the TD3 arena."""
+    in_dim = out_dim = None
+
+    def __init__(self, hidden=HIDDEN, layers=LAYERS):
+        self.hidden, self.layers = int(hidden), int(layers)
+        # Same torch RNG consumption as the reference constructor: nn.Linear's own init for every layer, then
+        # kaiming_uniform_(fan_in, relu) on every weight and zero biases (robot.py:145-151, 161-165).
+        lin = [torch.nn.Linear(i, o) for i, o in _layer_dims(self.in_dim, self.hidden, self.layers, self.out_dim)]
+        with torch.no_grad():
+            for m in lin:
+                torch.nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+                torch.nn.init.constant_(m.bias, 0)
+        self._flat = torch.cat([torch.cat([m.weight.detach().reshape(-1), m.bias.detach().reshape(-1)]) for m in lin])
+        self._td3 = None
+        self._net = None
+        self._bind_views()
+
+    def count(self):
+        return sum(i * o + o for i, o in _layer_dims(self.in_dim, self.hidden, self.layers, self.out_dim))
+
+    def _bind_views(self):
+        self._layers = []
+        off = 0
+        for i, o in _layer_dims(self.in_dim, self.hidden, self.layers, self.out_dim):
+            w = self._flat[off:off + i * o].view(o, i)
+            off += i * o
+            b = self._flat[off:off + o]
+            off += o
+            self._layers.append(_LayerView(w, b))
+        for k, lv in enumerate(self._layers[:-1]):
+            setattr(self, "layer_%d" % (k + 1), lv)
+        self.output_layer = self._layers[-1]
+
+    def _adopt(self, td3, net):
+        """Move into slot `net` of `td3`'s arena; afterwards all attributes are views of device memory."""
+        view = td3.flat(net)
+        view.copy_(self._flat.to(view.device))
+        self._flat, self._td3, self._net = view, td3, net
+        self._bind_views()
+
+    @classmethod
+    def _view_of(cls, td3, net, hidden, layers):
+        obj = cls.__new__(cls)
+        obj.hidden, obj.layers = hidden, layers
+        obj._flat, obj._td3, obj._net = td3.flat(net), td3, net
+        obj._bind_views()
+        return obj
+
+    def parameters(self):
+        for lv in self._layers:
+            yield lv.weight
+            yield lv.bias
+
+    def flat_parameters(self):
+        return self._flat
+
+    def load_flat(self, values):
+        self._flat.copy_(torch.as_tensor(np.asarray(values, dtype=np.float32)).to(self._flat.device))
+
+    def eval(self):
+        return self
+
+    def train(self, mode=True):
+        return self
+
+
+class Residual_Actor_Network(_Network):
+    """robot.py:128-165: 2 -> H -> H -> H -> 2, ReLU, linear head."""
+    in_dim, out_dim = 2, 2
+
+    def forward(self, input):
+        return self._td3.forward(self._net, input)
+
+    __call__ = forward
+
+
+class Residual_Critic_Network(_Network):
+    """robot.py:168-206: cat(state, action) 4 -> H -> H -> H -> 1."""
+    in_dim, out_dim = 4, 1
+
+    def forward(self, state, action):
+        return self._td3.forward(self._net, torch.cat([state, action], dim=1))
+
+    __call__ = forward
+
+
+# ------------------------------------------------------------------------------------------------ TD3
+class TD3:
+    """robot.py:209-398.  `process_group` (torch.distributed, NCCL) makes the learner data-parallel: every rank steps on
+    its own replay shard and the flat gradient buffer is all-reduced once per optimiser step."""
+
+    def __init__(self, actor_network, critic_network_1, critic_network_2, actor_lr=ACTOR_LR, critic_lr=CRITIC_LR, gamma=GAMMA,
+                 tau=TAU, policy_noise=TARGET_POLICY_NOISE, noise_clip=NOISE_CLIP, policy_update_delay=POLICY_UPDATE_DELAY,
+                 num_epochs=TD3_EPOCHS, batch_size=TD3_BATCH_SIZE, device=None, process_group=None):
+        self.device = _device(device)
+        self.hidden, self.layers = actor_network.hidden, actor_network.layers
+        for net in (critic_network_1, critic_network_2):
+            if (net.hidden, net.layers) != (self.hidden, self.layers):
+                raise ValueError("actor and critics must share hidden width and depth")
+        self._handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().rtd3_td3_create(ctypes.byref(self._handle), self.device.index or 0, self.hidden, self.layers), "td3_create")
+        L = _lib.lib()
+        self._off = [int(L.rtd3_td3_param_offset(self._handle, k)) for k in range(6)]
+        self._cnt = [int(L.rtd3_td3_param_count(self._handle, k)) for k in range(6)]
+        total = int(L.rtd3_td3_arena_floats(self._handle))
+        self.params = torch.zeros((total,), dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros((total // 2,), dtype=torch.float32, device=self.device)
+        self.adam_m = torch.zeros_like(self.grads)
+        self.adam_v = torch.zeros_like(self.grads)
+        self.steps = torch.zeros((2,), dtype=torch.int32, device=self.device)       # Adam step counters {actor, critics}
+
+        # online networks adopt arena slots 0..2; targets are copies (copy.deepcopy, robot.py:232-234)
+        self.actor_network, self.critic_network_1, self.critic_network_2 = actor_network, critic_network_1, critic_network_2
+        actor_network._adopt(self, NET_ACTOR)
+        critic_network_1._adopt(self, NET_CRITIC1)
+        critic_network_2._adopt(self, NET_CRITIC2)
+        half = total // 2
+        self.params[half:].copy_(self.params[:half])
+        self.target_actor = Residual_Actor_Network._view_of(self, NET_T_ACTOR, self.hidden, self.layers)
+        self.target_critic_network_1 = Residual_Critic_Network._view_of(self, NET_T_CRITIC1, self.hidden, self.layers)
+        self.target_critic_network_2 = Residual_Critic_Network._view_of(self, NET_T_CRITIC2, self.hidden, self.layers)
+
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
+        self.gamma, self.tau = gamma, tau
+        self.policy_noise, self.noise_clip = policy_noise, noise_clip
+        self.policy_update_delay = policy_update_delay
+        self.max_action = constants.ROBOT_MAX_ACTION
+        self.num_epochs, self.batch_size = num_epochs, batch_size
+        self.actor_losses, self.critic_losses = [], []
+        self.process_group = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.last_losses = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().rtd3_td3_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ---- arena access ---------------------------------------------------------------------------------
+    def flat(self, net):
+        return self.params[self._off[net]:self._off[net] + self._cnt[net]]
+
+    def flat_grad(self, net):
+        return self.grads[self._off[net]:self._off[net] + self._cnt[net]]
+
+    def forward(self, net, x):
+        """Forward of arena network `net` on `x` `[B,in]` (CUDA float32) -> `[B,out]`."""
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        out_dim = 2 if net in (NET_ACTOR, NET_T_ACTOR) else 1
+        y = torch.empty((x.shape[0], out_dim), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().rtd3_mlp_forward(self._handle, net, _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y), x.shape[0],
+                                               _lib.stream_ptr(self.device)), "mlp_forward")
+        return y
+
+    # ---- the three device steps -------------------------------------------------------------------------
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=self.process_group)
+
+    def _critic_step(self, rb, idx, noise, loss2, q_out=None, y_out=None):
+        B = idx.numel()
+        _lib.check(_lib.lib().rtd3_td3_critic_step(
+            self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(rb.s), _lib.ptr(rb.a), _lib.ptr(rb.r), _lib.ptr(rb.s2),
+            _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise, self.noise_clip, float(self.max_action),
+            _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps), _lib.stream_ptr(self.device)), "td3_critic_step")
+        self._allreduce()
+        self._adam(nets=0b110, polyak=0)
+
+    def _actor_step(self, rb, idx, loss1):
+        B = idx.numel()
+        _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(rb.s),
+                                                  _lib.ptr(idx), B, _lib.ptr(loss1), _lib.ptr(self.steps),
+                                                  _lib.stream_ptr(self.device)), "td3_actor_step")
+        self._allreduce()
+
+    def _adam(self, nets, polyak):
+        _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+                                                   _lib.ptr(self.adam_v), _lib.ptr(self.steps), nets, self.actor_lr, self.critic_lr,
+                                                   1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
+
+    def _noise(self, shape):
+        return torch.randn(shape, dtype=torch.float32, device=self.device)      # torch.randn_like, robot.py:338 (unseeded there)
+
+    # ---- reference methods --------------------------------------------------------------------------------
+    def train_critic(self, replay_buffer, noise=None, idx=None, q_out=None, y_out=None):
+        """robot.py:312-366.  `noise` (unit normal `[B,2]`) and `idx` can be injected for parity tests."""
+        if idx is None:
+            idx = replay_buffer.sample_indices(self.batch_size, 1)
+            if idx is None:
+                raise TypeError("cannot unpack non-iterable NoneType object")     # what the reference raises when under-filled
+            idx = idx[0]
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        noise = self._noise((idx.numel(), 2)) if noise is None else noise.to(self.device, torch.float32).contiguous()
+        loss2 = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        self._critic_step(replay_buffer, idx, noise, loss2, q_out, y_out)
+        l = loss2.cpu()
+        return float(l[0]), float(l[1])
+
+    def train_actor(self, replay_buffer, idx=None):
+        """robot.py:369-398 (the Adam step included; the Polyak updates are td3_update's / soft_update's job)."""
+        if idx is None:
+            idx = replay_buffer.sample_indices(self.batch_size, 1)
+            if idx is None:
+                raise TypeError("cannot unpack non-iterable NoneType object")
+            idx = idx[0]
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        loss1 = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        self._actor_step(replay_buffer, idx, loss1)
+        self._adam(nets=0b001, polyak=0)
+        return float(loss1.cpu()[0])
+
+    def soft_update(self, target, source, tau):
+        """robot.py:293-310 for one (target, source) pair of this agent's networks."""
+        pairs = {NET_T_ACTOR: NET_ACTOR, NET_T_CRITIC1: NET_CRITIC1, NET_T_CRITIC2: NET_CRITIC2}
+        if getattr(target, "_td3", None) is not self or pairs.get(target._net) != getattr(source, "_net", None):
+            raise ValueError("soft_update expects a (target, online) pair of this TD3 agent")
+        old_tau, self.tau = self.tau, tau
+        try:
+            self._adam(nets=0, polyak=1 << (target._net - 3))
+        finally:
+            self.tau = old_tau
+
+    def td3_update(self, replay_buffer, noise=None, idx=None):
+        """robot.py:258-285: `num_epochs` critic steps, an actor step + the three Polyak updates every
+        `policy_update_delay`-th epoch.  Returns (critic_losses `[E,2]`, actor_losses `[E_actor]`) as CPU tensors -
+        the values the reference collects at robot.py:274-280."""
+        E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
+        actor_epochs = [e for e in range(E) if e % delay == 0]
+        count = E + len(actor_epochs)
+        if idx is None:
+            idx = replay_buffer.sample_indices(B, count)            # in the order the reference draws them
+            if idx is None:
+                raise TypeError("cannot unpack non-iterable NoneType object")
+        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
+        noise = self._noise((E, B, 2)) if noise is None else noise.to(self.device, torch.float32).contiguous()
+        closs = torch.zeros((E, 2), dtype=torch.float32, device=self.device)
+        aloss = torch.zeros((max(1, len(actor_epochs)),), dtype=torch.float32, device=self.device)
+        k = 0
+        ka = 0
+        for e in range(E):
+            self._critic_step(replay_buffer, idx[k], noise[e], closs[e])
+            k += 1
+            if e % delay == 0:
+                self._actor_step(replay_buffer, idx[k], aloss[ka:ka + 1])
+                k += 1
+                ka += 1
+                self._adam(nets=0b001, polyak=0b111)
+        self.last_losses = (closs, aloss[:len(actor_epochs)])
+        return self.last_losses
