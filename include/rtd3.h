@@ -133,7 +133,10 @@ int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t stream_id,
  *   [actor | critic1 | critic2 | target actor | target critic1 | target critic2]
  * every slot in torch's parameters() order (W1 [H][in], b1, W2 [H][H], b2, ..., Wout [out][H], bout) and
  * padded to a multiple of 4 floats.  grads / adam_m / adam_v cover the first three slots.
- * steps: int32 [2] on the device = Adam step counters {actor optimiser, critic optimisers}.
+ * steps: int32 [2] on the device = Adam step counters {actor optimiser, critic optimisers};
+ * beta_pows: float64 [4] on the device = {0.9^t, 0.999^t} per optimiser (initialise to 1.0), advanced together
+ * with `steps` by the step calls and read by rtd3_td3_adam_polyak for the bias corrections.
+ * scratch: rtd3_td3_scratch_floats(batch) floats of device memory, contents are transient.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rtd3_td3 rtd3_td3;
 
@@ -143,29 +146,35 @@ int32_t rtd3_td3_destroy(rtd3_td3* h);
 int64_t rtd3_td3_param_count(const rtd3_td3* h, int32_t net);
 int64_t rtd3_td3_param_offset(const rtd3_td3* h, int32_t net);
 int64_t rtd3_td3_arena_floats(const rtd3_td3* h);
+/* floats of row scratch a critic/actor step needs for `batch` rows (layer inputs and pre-activation
+ * gradients of the trained networks, from which the weight gradients are reduced). */
+int64_t rtd3_td3_scratch_floats(const rtd3_td3* h, int32_t batch);
 
 /* TD3.train_critic minus the optimiser steps (robot.py:326-357/361): gathers rows idx[batch] from the
  * replay ring, target-policy smoothing with the supplied unit-normal noise [batch][2] (robot.py:338-339),
  * clipped double-Q target (robot.py:342-345), both critic forward passes, both MSE losses (added into
- * loss2[0..1], which the caller zeroes) and both backward passes (gradients ADDED into grads, which the
- * caller keeps zeroed between steps - rtd3_td3_adam_polyak re-zeroes what it consumes).
+ * loss2[0..1], which the caller zeroes) and both backward passes; the parameter gradients of both critics
+ * are written to grads (for batch > 512 they are accumulated, so grads must be zero on entry -
+ * rtd3_td3_adam_polyak re-zeroes what it consumes).
  * q_out (nullable) [2][batch] receives Q1,Q2(s,a) before the update, y_out (nullable) [batch] the targets.
  * Increments steps[1]. */
-int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const float* rp_a,
-                             const float* rp_r, const float* rp_s2, const float* rp_notdone, const int32_t* idx,
-                             const float* noise, int32_t batch, float gamma, float policy_noise, float noise_clip,
-                             float max_action, float* loss2, float* q_out, float* y_out, int32_t* steps, void* stream);
+int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s,
+                             const float* rp_a, const float* rp_r, const float* rp_s2, const float* rp_notdone,
+                             const int32_t* idx, const float* noise, int32_t batch, float gamma, float policy_noise,
+                             float noise_clip, float max_action, float* loss2, float* q_out, float* y_out, int32_t* steps,
+                             double* beta_pows, void* stream);
 
 /* TD3.train_actor minus the optimiser step (robot.py:382-394): loss = -mean(Q1(s, pi(s))) added into
- * loss1[0]; gradient w.r.t. the actor parameters only, ADDED into grads.  Increments steps[0]. */
-int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const int32_t* idx,
-                            int32_t batch, float* loss1, int32_t* steps, void* stream);
+ * loss1[0]; gradient w.r.t. the actor parameters only, written to grads (same zero-on-entry rule).
+ * Increments steps[0]. */
+int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s,
+                            const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream);
 
 /* torch.optim.Adam step (lr, betas 0.9/0.999, eps 1e-8; robot.py:237-239, 356-363, 393-395) on the nets
  * selected by `nets` (bit 0 actor, bit 1 critic1, bit 2 critic2) using grads*grad_scale (grad_scale = 1/world
  * after a gradient all-reduce), zeroing the consumed gradients; then TD3.soft_update (robot.py:293-310)
  * on the target nets selected by `polyak` (same bit layout) with the freshly updated online parameters. */
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const int32_t* steps,
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const double* beta_pows,
                              int32_t nets, float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau,
                              void* stream);
 

@@ -37,23 +37,36 @@ struct Arena {
   __host__ __device__ int64_t total() const { return 2 * online_total(); }
 };
 
+// Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
+// beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
+__device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {
+  steps[o] += 1;
+  beta_pows[2 * o] *= 0.9;
+  beta_pows[2 * o + 1] *= 0.999;
+}
+
 // ---- critic phase: robot.py:312-366 up to (not including) the optimiser steps ------------------------------------
 //   y = r + gamma * min(Q1', Q2')(s2, clip(pi'(s2) + clip(noise*sigma, +-c), +-5)) * notdone
-//   L_i = mean((Q_i(s,a) - y)^2);  gradients of L_1, L_2 accumulated (RED.ADD) into grads[critic1], grads[critic2]
-// One CTA = R batch rows through the whole chain; steps[1] (the critics' Adam step counter) is advanced by block 0.
+//   L_i = mean((Q_i(s,a) - y)^2); forward + backward of both critics; per-row layer inputs / pre-activation gradients
+//   go to the row scratch (slot c = critic c), from which wgrad_kernel forms the parameter gradients.
+// One CTA = R batch rows through the whole chain: five network passes driven by ONE loop so that the layer code is
+// instantiated once (the fully inlined five-call version was 143 KB of SASS and stalled on instruction fetch).
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1)
-td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ grads, ReplayView rp, const int32_t* __restrict__ idx,
+__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
+td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
                   const float* __restrict__ noise /*[B][2] unit normal*/, int B, Td3Hyper hp, float* __restrict__ loss /*[2]*/,
-                  float* __restrict__ q_out /*nullable [2][B]*/, float* __restrict__ y_out /*nullable [B]*/, int32_t* __restrict__ steps) {
-  extern __shared__ __align__(16) float smem_f[];
+                  float* __restrict__ q_out /*nullable [2][B]*/, float* __restrict__ y_out /*nullable [B]*/, int32_t* __restrict__ steps,
+                  double* __restrict__ beta_pows) {
   MlpSmem<R> sm;
-  sm.carve(smem_f, ar.critic.hid, ar.critic.layers);
+  sm.carve(0, ar.critic.hid, ar.critic.layers);
   const int r0 = blockIdx.x * R;
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) steps[1] += 1;
+  if (blockIdx.x == 0 && t == 0) advance_adam_clock(steps, beta_pows, 1);
 
-  float* S = sm.scratch;   // [R][8]: 0 s.x 1 s.y 2 a.x 3 a.y 4 reward 5 notdone 6 y 7 valid
+  float* S = smem_f + sm.scratch;   // [R][8]: 0 s.x 1 s.y 2 a.x 3 a.y 4 reward 5 notdone 6 y 7 valid
+  float* in0 = smem_f + sm.in0;
+  float* out = smem_f + sm.out;
+  float* dout = smem_f + sm.dout;
   if (t < R) {
     const int row = r0 + t;
     const bool valid = row < B;
@@ -61,82 +74,77 @@ td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict_
     const float2 s = rp.s[j], a = rp.a[j], s2 = rp.s2[j];
     S[t * 8 + 0] = s.x; S[t * 8 + 1] = s.y; S[t * 8 + 2] = a.x; S[t * 8 + 3] = a.y;
     S[t * 8 + 4] = rp.r[j]; S[t * 8 + 5] = rp.notdone[j]; S[t * 8 + 7] = valid ? 1.f : 0.f;
-    sm.in0[t * 4 + 0] = s2.x; sm.in0[t * 4 + 1] = s2.y; sm.in0[t * 4 + 2] = 0.f; sm.in0[t * 4 + 3] = 0.f;
+    in0[t * 4 + 0] = s2.x; in0[t * 4 + 1] = s2.y; in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;
   }
   __syncthreads();
 
-  // target actor on s2, then smoothing noise and clip (robot.py:338-339)
-  mlp_forward<R>(params + ar.off(3), ar.actor, sm, false);
-  if (t < R) {
-    const int row = min(r0 + t, B - 1);
-    float a2[2];
-#pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      float e = noise[row * 2 + o] * hp.policy_noise;
-      e = fminf(fmaxf(e, -hp.noise_clip), hp.noise_clip);
-      a2[o] = fminf(fmaxf(sm.out[t * 2 + o] + e, -hp.max_action), hp.max_action);
-    }
-    sm.in0[t * 4 + 2] = a2[0];
-    sm.in0[t * 4 + 3] = a2[1];
-  }
-  __syncthreads();
-  // target critics on (s2, a') and the clipped double-Q target (robot.py:342-345)
-  mlp_forward<R>(params + ar.off(4), ar.critic, sm, false);
-  if (t < R) S[t * 8 + 6] = sm.out[t * 2];
-  __syncthreads();
-  mlp_forward<R>(params + ar.off(5), ar.critic, sm, false);
-  if (t < R) {
-    const float qmin = fminf(S[t * 8 + 6], sm.out[t * 2]);
-    const float y = S[t * 8 + 4] + hp.gamma * qmin * S[t * 8 + 5];
-    S[t * 8 + 6] = y;
-    if (y_out && r0 + t < B) y_out[r0 + t] = y;
-    sm.in0[t * 4 + 0] = S[t * 8 + 0]; sm.in0[t * 4 + 1] = S[t * 8 + 1];
-    sm.in0[t * 4 + 2] = S[t * 8 + 2]; sm.in0[t * 4 + 3] = S[t * 8 + 3];
-  }
-  __syncthreads();
-
-  // both critics: forward (activations kept), MSE loss, backward (robot.py:348-363)
-  for (int c = 0; c < 2; ++c) {
-    const float* P = params + ar.off(1 + c);
-    float* G = grads + ar.off(1 + c);
-    mlp_forward<R>(P, ar.critic, sm, true);
+  // pass 0: target actor(s2); 1, 2: target critics(s2, a'); 3, 4: critics(s, a) forward + backward
+  for (int pass = 0; pass < 5; ++pass) {
+    const int net = pass == 0 ? 3 : (pass == 1 ? 4 : (pass == 2 ? 5 : pass - 2));
+    const NetShape shape = pass == 0 ? ar.actor : ar.critic;
+    const bool train = pass >= 3;
+    const float* P = params + ar.off(net);
+    RowScratch rs{scratch + (train ? (pass - 3) : 0) * RowScratch::floats(B, ar.critic.hid, ar.critic.layers), B, ar.critic.hid,
+                  ar.critic.layers};
+    mlp_forward<R>(P, shape, sm, train, train ? &rs : nullptr, r0);
     if (t < R) {
-      const float valid = S[t * 8 + 7];
-      const float q = sm.out[t * 2];
-      const float diff = (q - S[t * 8 + 6]) * valid;
-      sm.dout[t * 2] = 2.0f * diff / (float)B;
-      sm.dout[t * 2 + 1] = 0.f;
-      if (q_out && valid != 0.f) q_out[c * B + r0 + t] = q;
-      float l = diff * diff / (float)B;                 // this row's share of the mean
+      if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
+        const int row = min(r0 + t, B - 1);
 #pragma unroll
-      for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
-      if (t == 0) atomicAdd(loss + c, l);
+        for (int o = 0; o < 2; ++o) {
+          float e = noise[row * 2 + o] * hp.policy_noise;
+          e = fminf(fmaxf(e, -hp.noise_clip), hp.noise_clip);
+          in0[t * 4 + 2 + o] = fminf(fmaxf(out[t * 2 + o] + e, -hp.max_action), hp.max_action);
+        }
+      } else if (pass == 1) {
+        S[t * 8 + 6] = out[t * 2];
+      } else if (pass == 2) {                            // clipped double-Q target (robot.py:342-345)
+        const float qmin = fminf(S[t * 8 + 6], out[t * 2]);
+        const float y = S[t * 8 + 4] + hp.gamma * qmin * S[t * 8 + 5];
+        S[t * 8 + 6] = y;
+        if (y_out && r0 + t < B) y_out[r0 + t] = y;
+        in0[t * 4 + 0] = S[t * 8 + 0]; in0[t * 4 + 1] = S[t * 8 + 1];
+        in0[t * 4 + 2] = S[t * 8 + 2]; in0[t * 4 + 3] = S[t * 8 + 3];
+      } else {                                           // MSE loss and its gradient (robot.py:348-353)
+        const int c = pass - 3;
+        const float valid = S[t * 8 + 7];
+        const float q = out[t * 2];
+        const float diff = (q - S[t * 8 + 6]) * valid;
+        dout[t * 2] = 2.0f * diff / (float)B;
+        dout[t * 2 + 1] = 0.f;
+        if (q_out && valid != 0.f) q_out[c * B + r0 + t] = q;
+        float l = diff * diff / (float)B;                // this row's share of the mean
+#pragma unroll
+        for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
+        if (t == 0) atomicAdd(loss + c, l);
+      }
     }
     __syncthreads();
-    mlp_backward<R>(P, G, ar.critic, sm, false);
-    __syncthreads();
+    if (train) {
+      mlp_backward<R>(P, shape, sm, &rs, r0, false);
+      __syncthreads();
+    }
   }
 }
 
 // ---- actor phase: robot.py:369-398 up to the optimiser step ---------------------------------------------------------
 //   L = -mean(Q1(s, pi(s)));  gradient w.r.t. the actor only (critic-1 parameter gradients are discarded by the reference)
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1)
-td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ grads, ReplayView rp, const int32_t* __restrict__ idx,
-                 int B, float* __restrict__ loss /*[1]*/, int32_t* __restrict__ steps) {
-  extern __shared__ __align__(16) float smem_f[];
-  MlpSmem<R> sm;                      // critic pass (activations kept, backward for dQ/da)
-  sm.carve(smem_f, ar.critic.hid, ar.critic.layers);
-  MlpSmem<R> sa;                      // actor pass: own activation buffers behind the critic's working set
-  float* actor_base = smem_f + MlpSmem<R>::bytes(ar.critic.hid, ar.critic.layers) / sizeof(float);
+__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
+td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
+                 int B, float* __restrict__ loss /*[1]*/, int32_t* __restrict__ steps, double* __restrict__ beta_pows) {
+  MlpSmem<R> sc;                      // critic pass (activations kept, backward for dQ/da)
+  sc.carve(0, ar.critic.hid, ar.critic.layers);
+  // the actor pass shares the weight-tile ring and small buffers; only its kept activations and its input are separate
+  MlpSmem<R> sa = sc;
+  sa.act0 = (int)MlpSmem<R>::floats(ar.critic.hid, ar.critic.layers);
+  sa.in0 = sa.act0 + ar.actor.layers * R * sc.ld;
   const int r0 = blockIdx.x * R;
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) steps[0] += 1;
-  // the actor working set shares the weight-tile ring and scratch with `sm`; only its kept activations are separate
-  sa = sm;
-  for (int l = 0; l < ar.actor.layers; ++l) sa.act[l] = actor_base + l * R * sm.ld;
-  float* actor_in = actor_base + ar.actor.layers * R * sm.ld;   // [R][4]
-  float* S = sm.scratch;
+  if (blockIdx.x == 0 && t == 0) advance_adam_clock(steps, beta_pows, 0);
+  float* S = smem_f + sc.scratch;
+  float* actor_in = smem_f + sa.in0;
+  RowScratch rs{scratch, B, ar.actor.hid, ar.actor.layers};
 
   if (t < R) {
     const int row = r0 + t;
@@ -146,31 +154,171 @@ td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__
     S[t * 8 + 7] = valid ? 1.f : 0.f;
   }
   __syncthreads();
-  sa.in0 = actor_in;
-  mlp_forward<R>(params + ar.off(0), ar.actor, sa, true);        // a = pi(s), fed the raw replay state (robot.py:386)
-  if (t < R) {
-    sm.in0[t * 4 + 0] = actor_in[t * 4 + 0]; sm.in0[t * 4 + 1] = actor_in[t * 4 + 1];
-    sm.in0[t * 4 + 2] = sa.out[t * 2]; sm.in0[t * 4 + 3] = sa.out[t * 2 + 1];
-  }
-  __syncthreads();
-  mlp_forward<R>(params + ar.off(1), ar.critic, sm, true);       // Q1(s, a)
-  if (t < R) {
-    const float valid = S[t * 8 + 7];
-    sm.dout[t * 2] = -valid / (float)B;
-    sm.dout[t * 2 + 1] = 0.f;
-    float l = -sm.out[t * 2] * valid / (float)B;
+  // forward: pass 0 a = pi(s) (fed the raw replay state, robot.py:386), pass 1 Q1(s, a)
+  for (int pass = 0; pass < 2; ++pass) {
+    const MlpSmem<R> sm = pass == 0 ? sa : sc;
+    mlp_forward<R>(params + ar.off(pass), pass == 0 ? ar.actor : ar.critic, sm, true, pass == 0 ? &rs : nullptr, r0);
+    if (t < R) {
+      if (pass == 0) {
+        float* cin = smem_f + sc.in0;
+        cin[t * 4 + 0] = actor_in[t * 4 + 0]; cin[t * 4 + 1] = actor_in[t * 4 + 1];
+        cin[t * 4 + 2] = smem_f[sa.out + t * 2]; cin[t * 4 + 3] = smem_f[sa.out + t * 2 + 1];
+      } else {
+        const float valid = S[t * 8 + 7];
+        smem_f[sc.dout + t * 2] = -valid / (float)B;
+        smem_f[sc.dout + t * 2 + 1] = 0.f;
+        float l = -smem_f[sc.out + t * 2] * valid / (float)B;
 #pragma unroll
-    for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
-    if (t == 0) atomicAdd(loss, l);
+        for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
+        if (t == 0) atomicAdd(loss, l);
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  mlp_backward<R>(params + ar.off(1), nullptr, ar.critic, sm, true);   // only dQ/d(input) is needed
-  if (t < R) {
-    sa.dout[t * 2] = sm.din[t * 4 + 2];
-    sa.dout[t * 2 + 1] = sm.din[t * 4 + 3];
+  // backward: pass 0 through critic 1 (only dQ/d(input) is needed), pass 1 through the actor
+  for (int pass = 0; pass < 2; ++pass) {
+    const MlpSmem<R> sm = pass == 0 ? sc : sa;
+    mlp_backward<R>(params + ar.off(1 - pass), pass == 0 ? ar.critic : ar.actor, sm, pass == 0 ? nullptr : &rs, r0, pass == 0);
+    if (pass == 0 && t < R) {
+      smem_f[sa.dout + t * 2] = smem_f[sc.din + t * 4 + 2];
+      smem_f[sa.dout + t * 2 + 1] = smem_f[sc.din + t * 4 + 3];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  mlp_backward<R>(params + ar.off(0), grads + ar.off(0), ar.actor, sa, false);
+}
+
+// ---- weight gradients from the row scratch, reduced over the batch without atomics -----------------------------------
+//   hidden layer l (1..L-1):  gW_l[n][k] = sum_b dz_l[b][n] * h_{l-1}[b][k]      32x32 output tiles
+//   every hidden layer l:     gb_l[n]    = sum_b dz_l[b][n];   l = 0 also gW_0[n][j] = sum_b dz_0[b][n] * in0[b][j]
+//   output layer:             gW_L[o][k] = sum_b dout[b][o] * h_{L-1}[b][k];  gb_L[o] = sum_b dout[b][o]
+// blockIdx.x = job, blockIdx.y = network slot, blockIdx.z = batch split (>1 only for large batches: atomicAdd into
+// gradients that the optimiser pass left zeroed).  Each of the 8 warps reduces every 8th row; the partial tiles meet in smem.
+struct WgradSlots {
+  int64_t grad_off[2];      // offset of the slot's network in the gradient arena
+  int64_t scratch_off[2];   // offset of the slot's row scratch
+};
+
+__global__ void __launch_bounds__(kThreads)
+wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split) {
+  __shared__ __align__(16) float red[8][32 * 32];
+  const int H = s.hid, L = s.layers;
+  const int nch = (H + 31) / 32;
+  const int nT = (L - 1) * nch * nch, nS = L * nch;
+  const int job = blockIdx.x;
+  const int slot = blockIdx.y;
+  const RowScratch rs{const_cast<float*>(scratch) + slots.scratch_off[slot], B, H, L};
+  float* G = grads + slots.grad_off[slot];
+  const bool atomic = gridDim.z > 1;
+  const int b_lo = blockIdx.z * rows_per_split, b_hi = min(B, b_lo + rows_per_split);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (job < nT) {
+    const int l = 1 + job / (nch * nch);
+    const int tile = job % (nch * nch);
+    const int n0 = (tile / nch) * 32, k0 = (tile % nch) * 32;
+    const float* dz = rs.dz(l);
+    const float* x = rs.h(l - 1);
+    const int ty = lane >> 2, tx = lane & 3;
+    const int n = n0 + ty * 4, k = k0 + tx * 8;
+    const bool n_ok = n < H, k_ok0 = k < H, k_ok1 = k + 4 < H;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int b = b_lo + warp; b < b_hi; b += 8) {
+      const float4 z = n_ok ? __ldg(reinterpret_cast<const float4*>(dz + (int64_t)b * H + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 x0 = k_ok0 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 x1 = k_ok1 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * H + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+      const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(zz[i], xx[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* dst = &red[warp][(ty * 4 + i) * 32 + tx * 8];
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __syncthreads();
+    const int o = threadIdx.x * 4;            // 4 consecutive outputs of the 32x32 tile
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 p = *reinterpret_cast<const float4*>(&red[w][o]);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    const int gn = n0 + (o >> 5), gk = k0 + (o & 31);
+    if (gn < H && gk < H) {
+      float* dst = G + net_w_off(s, l) + (int64_t)gn * H + gk;
+      if (atomic) { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
+      else *reinterpret_cast<float4*>(dst) = v;
+    }
+  } else if (job < nT + nS) {
+    const int l = (job - nT) / nch, n = ((job - nT) % nch) * 32 + lane;
+    const float* dz = rs.dz(l);
+    const float* in0 = rs.in0();
+    float ab = 0.f, aw[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < H) {
+      for (int b = b_lo + warp; b < b_hi; b += 8) {
+        const float d = __ldg(dz + (int64_t)b * H + n);
+        ab += d;
+        if (l == 0) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(in0 + (int64_t)b * 4));
+          aw[0] = fmaf(d, x.x, aw[0]); aw[1] = fmaf(d, x.y, aw[1]); aw[2] = fmaf(d, x.z, aw[2]); aw[3] = fmaf(d, x.w, aw[3]);
+        }
+      }
+    }
+    float* r = &red[warp][lane * 5];
+    r[0] = ab; r[1] = aw[0]; r[2] = aw[1]; r[3] = aw[2]; r[4] = aw[3];
+    __syncthreads();
+    if (warp == 0 && n < H) {
+      float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < 8; ++w)
+        for (int q = 0; q < 5; ++q) v[q] += red[w][lane * 5 + q];
+      float* gb = G + net_b_off(s, l) + n;
+      if (atomic) atomicAdd(gb, v[0]); else *gb = v[0];
+      if (l == 0) {
+        for (int j = 0; j < s.in; ++j) {
+          float* gw = G + net_w_off(s, 0) + n * s.in + j;
+          if (atomic) atomicAdd(gw, v[1 + j]); else *gw = v[1 + j];
+        }
+      }
+    }
+  } else {
+    const int chunk = job - nT - nS, k = chunk * 32 + lane;
+    const float* hl = rs.h(L - 1);
+    const float* dout = rs.dout();
+    float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+    for (int b = b_lo + warp; b < b_hi; b += 8) {
+      const float2 d = __ldg(reinterpret_cast<const float2*>(dout + (int64_t)b * 2));
+      const float h = k < H ? __ldg(hl + (int64_t)b * H + k) : 0.f;
+      a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1);
+      s0 += d.x; s1 += d.y;
+    }
+    float* r = &red[warp][lane * 4];
+    r[0] = a0; r[1] = a1; r[2] = s0; r[3] = s1;
+    __syncthreads();
+    if (warp == 0) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < 8; ++w)
+        for (int q = 0; q < 4; ++q) v[q] += red[w][lane * 4 + q];
+      if (k < H) {
+        for (int o = 0; o < s.out; ++o) {
+          float* gw = G + net_w_off(s, L) + (int64_t)o * H + k;
+          if (atomic) atomicAdd(gw, v[o]); else *gw = v[o];
+        }
+      }
+      if (chunk == 0 && lane < s.out) {
+        float* gb = G + net_b_off(s, L) + lane;
+        if (atomic) atomicAdd(gb, v[2 + lane]); else *gb = v[2 + lane];
+      }
+    }
+  }
 }
 
 // ---- Adam (torch.optim.Adam defaults, robot.py:237-239) + optional Polyak (robot.py:293-310), one pass --------------
@@ -178,12 +326,11 @@ td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__
 // polyak: same bit layout; afterwards the selected target slots are blended with their (updated) online net:
 // t = t*(1-tau) + p*tau.
 __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m,
-                                       float* __restrict__ v, const int32_t* __restrict__ steps, int nets, float lr_actor, float lr_critic,
-                                       float grad_scale, int polyak, float tau) {
+                                       float* __restrict__ v, const double* __restrict__ beta_pows, int nets, float lr_actor,
+                                       float lr_critic, float grad_scale, int polyak, float tau) {
   __shared__ float s_step[2], s_bc2[2];
-  if (threadIdx.x < 2) {
-    const double tt = (double)steps[threadIdx.x];                     // 0: actor optimiser, 1: both critic optimisers
-    const double bc1 = 1.0 - pow(0.9, tt), bc2 = 1.0 - pow(0.999, tt);
+  if (threadIdx.x < 2) {                                              // 0: actor optimiser, 1: both critic optimisers
+    const double bc1 = 1.0 - beta_pows[2 * threadIdx.x], bc2 = 1.0 - beta_pows[2 * threadIdx.x + 1];
     const double lr = threadIdx.x == 0 ? (double)lr_actor : (double)lr_critic;
     s_step[threadIdx.x] = (float)(lr / bc1);
     s_bc2[threadIdx.x] = (float)sqrt(bc2);
@@ -216,22 +363,21 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
 
 // ---- plain forward of one network over B rows (actor inference for get_next_action, parity checks of Q-values) ------
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
 mlp_forward_kernel(NetShape s, const float* __restrict__ P, const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/,
                    int B) {
-  extern __shared__ __align__(16) float smem_f[];
   MlpSmem<R> sm;
-  sm.carve(smem_f, s.hid, 0);
+  sm.carve(0, s.hid, 0);
   const int r0 = blockIdx.x * R, t = threadIdx.x;
   if (t < R * 4) {
     const int r = t >> 2, j = t & 3, row = r0 + r;
-    sm.in0[t] = (row < B && j < s.in) ? x[(int64_t)row * s.in + j] : 0.f;
+    smem_f[sm.in0 + t] = (row < B && j < s.in) ? x[(int64_t)row * s.in + j] : 0.f;
   }
   __syncthreads();
-  mlp_forward<R>(P, s, sm, false);
+  mlp_forward<R>(P, s, sm, false, nullptr, r0);
   if (t < R * s.out) {
     const int r = t / s.out, o = t - r * s.out;
-    if (r0 + r < B) y[(int64_t)(r0 + r) * s.out + o] = sm.out[r * 2 + o];
+    if (r0 + r < B) y[(int64_t)(r0 + r) * s.out + o] = smem_f[sm.out + r * 2 + o];
   }
 }
 
@@ -260,27 +406,50 @@ __global__ void replay_gather_kernel(ReplayView rp, const int32_t* __restrict__ 
 }
 
 static bool shape_ok(const NetShape& s) {
-  return s.in >= 1 && s.in <= 4 && s.out >= 1 && s.out <= 2 && s.layers >= 1 && s.layers <= 4 && s.hid >= 4 && s.hid <= kMaxHidden &&
-         s.hid % 4 == 0;
+  return s.in >= 1 && s.in <= 4 && s.out >= 1 && s.out <= 2 && s.layers >= 1 && s.layers <= kMaxLayers && s.hid >= 4 &&
+         s.hid <= kMaxHidden && s.hid % 4 == 0;
 }
 
 }  // namespace rtd3
 
 using namespace rtd3;
 
+constexpr int kNumTiles = 3;
+static const int kRowTiles[kNumTiles] = {4, 8, 16};
+
 struct rtd3_td3 {
   Arena ar;
   int device;
   int num_sms;
-  size_t smem_critic[2], smem_actor[2], smem_fwd[2];   // per row-tile size: [0] R=8, [1] R=16
+  size_t smem_critic[kNumTiles], smem_actor[kNumTiles], smem_fwd[kNumTiles];
 };
 
-static const int kRowTiles[2] = {8, 16};
-
-static inline int pick_tile(int B, int num_sms) { return (B > 8 * num_sms * 2) ? 1 : 0; }
+// Rows per CTA: few rows while the batch cannot fill the SMs (latency-bound), more rows once it can (every CTA
+// re-streams all weights from L2, so larger tiles cut that traffic).
+static inline int pick_tile(int64_t B, int num_sms) {
+  if (B <= 4 * (int64_t)num_sms) return 0;
+  if (B <= 16 * (int64_t)num_sms) return 1;
+  return 2;
+}
 
 static size_t actor_phase_smem(const Arena& ar, int R) {
   return mlp_smem_bytes(R, ar.critic.hid, ar.critic.layers) + ((size_t)ar.actor.layers * R * (ar.critic.hid + 4) + R * 4) * sizeof(float);
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int32_t launch_wgrad(rtd3_td3* h, const NetShape& s, const float* scratch, float* grads, const WgradSlots& slots, int nslots, int B,
+                            cudaStream_t st) {
+  const int nch = (s.hid + 31) / 32;
+  const int jobs = (s.layers - 1) * nch * nch + s.layers * nch + nch;
+  const int rows_per_split = 512;
+  const int bsplit = (B + rows_per_split - 1) / rows_per_split;
+  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, 0, st>>>(s, scratch, grads, slots, B, rows_per_split);
+  RTD3_LAUNCHED();
+  return 0;
 }
 
 extern "C" {
@@ -292,7 +461,7 @@ int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t 
   h->ar.critic = NetShape{4, hidden, layers, 1};
   if (!shape_ok(h->ar.actor)) {
     delete h;
-    rtd3::set_error("rtd3_td3_create: hidden must be a multiple of 4 in [4,%d], layers in [1,4]", kMaxHidden);
+    rtd3::set_error("rtd3_td3_create: hidden must be a multiple of 4 in [4,%d], layers in [1,%d]", kMaxHidden, kMaxLayers);
     return RTD3_ERR_ARG;
   }
   h->device = device;
@@ -300,18 +469,21 @@ int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t 
   RTD3_CUDA(cudaGetDevice(&prev));
   RTD3_CUDA(cudaSetDevice(device));
   RTD3_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kNumTiles; ++i) {
     const int R = kRowTiles[i];
     h->smem_critic[i] = mlp_smem_bytes(R, hidden, layers);
     h->smem_actor[i] = actor_phase_smem(h->ar, R);
     h->smem_fwd[i] = mlp_smem_bytes(R, hidden, 0);
   }
-  RTD3_CUDA(cudaFuncSetAttribute(td3_critic_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_critic[0]));
-  RTD3_CUDA(cudaFuncSetAttribute(td3_critic_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_critic[1]));
-  RTD3_CUDA(cudaFuncSetAttribute(td3_actor_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_actor[0]));
-  RTD3_CUDA(cudaFuncSetAttribute(td3_actor_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_actor[1]));
-  RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fwd[0]));
-  RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fwd[1]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<4>, h->smem_critic[0]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<8>, h->smem_critic[1]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<16>, h->smem_critic[2]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<4>, h->smem_actor[0]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<8>, h->smem_actor[1]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<16>, h->smem_actor[2]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<4>, h->smem_fwd[0]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<8>, h->smem_fwd[1]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<16>, h->smem_fwd[2]));
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;
@@ -328,12 +500,16 @@ int64_t rtd3_td3_param_count(const rtd3_td3* h, int32_t net) {
 }
 int64_t rtd3_td3_param_offset(const rtd3_td3* h, int32_t net) { return h ? h->ar.off(net) : -1; }
 int64_t rtd3_td3_arena_floats(const rtd3_td3* h) { return h ? h->ar.total() : -1; }
+int64_t rtd3_td3_scratch_floats(const rtd3_td3* h, int32_t batch) {
+  return h ? 2 * RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers) : -1;
+}
 
-int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const float* rp_a, const float* rp_r,
-                             const float* rp_s2, const float* rp_notdone, const int32_t* idx, const float* noise, int32_t batch,
-                             float gamma, float policy_noise, float noise_clip, float max_action, float* loss2, float* q_out, float* y_out,
-                             int32_t* steps, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && rp_s && rp_a && rp_r && rp_s2 && rp_notdone && idx && noise && loss2 && steps, "null argument");
+int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s, const float* rp_a,
+                             const float* rp_r, const float* rp_s2, const float* rp_notdone, const int32_t* idx, const float* noise,
+                             int32_t batch, float gamma, float policy_noise, float noise_clip, float max_action, float* loss2, float* q_out,
+                             float* y_out, int32_t* steps, double* beta_pows, void* stream) {
+  RTD3_CHECK_ARG(h && params && grads && scratch && rp_s && rp_a && rp_r && rp_s2 && rp_notdone && idx && noise && loss2 && steps && beta_pows,
+                 "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, (const float2*)rp_a, rp_r, (const float2*)rp_s2, rp_notdone};
   Td3Hyper hp{gamma, policy_noise, noise_clip, max_action};
@@ -341,37 +517,45 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, con
   const int R = kRowTiles[ti];
   const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ti == 0)
-    td3_critic_kernel<8><<<grid, kThreads, h->smem_critic[0], st>>>(h->ar, params, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps);
-  else
-    td3_critic_kernel<16><<<grid, kThreads, h->smem_critic[1], st>>>(h->ar, params, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps);
+#define RTD3_CRITIC(RR) \
+  td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
+  if (ti == 0) RTD3_CRITIC(4); else if (ti == 1) RTD3_CRITIC(8); else RTD3_CRITIC(16);
+#undef RTD3_CRITIC
   RTD3_LAUNCHED();
-  return 0;
+  WgradSlots slots;
+  const int64_t per = RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers);
+  slots.grad_off[0] = h->ar.off(1); slots.grad_off[1] = h->ar.off(2);
+  slots.scratch_off[0] = 0; slots.scratch_off[1] = per;
+  return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st);
 }
 
-int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, const float* rp_s, const int32_t* idx, int32_t batch,
-                            float* loss1, int32_t* steps, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && rp_s && idx && loss1 && steps, "null argument");
+int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
+                            int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {
+  RTD3_CHECK_ARG(h && params && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
   const int ti = pick_tile(batch, h->num_sms);
   const int R = kRowTiles[ti];
   const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
-  if (ti == 0) td3_actor_kernel<8><<<grid, kThreads, h->smem_actor[0], st>>>(h->ar, params, grads, rp, idx, batch, loss1, steps);
-  else td3_actor_kernel<16><<<grid, kThreads, h->smem_actor[1], st>>>(h->ar, params, grads, rp, idx, batch, loss1, steps);
+#define RTD3_ACTOR(RR) td3_actor_kernel<RR><<<grid, kThreads, h->smem_actor[ti], st>>>(h->ar, params, scratch, rp, idx, batch, loss1, steps, beta_pows)
+  if (ti == 0) RTD3_ACTOR(4); else if (ti == 1) RTD3_ACTOR(8); else RTD3_ACTOR(16);
+#undef RTD3_ACTOR
   RTD3_LAUNCHED();
-  return 0;
+  WgradSlots slots;
+  slots.grad_off[0] = h->ar.off(0); slots.grad_off[1] = 0;
+  slots.scratch_off[0] = 0; slots.scratch_off[1] = 0;
+  return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st);
 }
 
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const int32_t* steps, int32_t nets,
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
                              float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && adam_m && adam_v && steps, "null argument");
+  RTD3_CHECK_ARG(h && params && grads && adam_m && adam_v && beta_pows, "null argument");
   const int64_t n = h->ar.online_total();
   const int block = 256;
-  const int grid = (int)std::min<int64_t>(ceil_div(n, block), (int64_t)h->num_sms * 4);
-  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, grads, adam_m, adam_v, steps, nets, lr_actor, lr_critic,
-                                                                    grad_scale, polyak, tau);
+  const int grid = (int)std::min<int64_t>(ceil_div(n, block), (int64_t)h->num_sms * 8);
+  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
+                                                                    lr_critic, grad_scale, polyak, tau);
   RTD3_LAUNCHED();
   return 0;
 }
@@ -382,12 +566,13 @@ int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const fl
   RTD3_CHECK_ARG(batch >= 0 && batch < (1ll << 31), "bad batch");
   if (batch == 0) return 0;
   const NetShape s = (net == 0 || net == 3) ? h->ar.actor : h->ar.critic;
-  const int ti = pick_tile((int)batch, h->num_sms);
+  const int ti = pick_tile(batch, h->num_sms);
   const int R = kRowTiles[ti];
   const int grid = (int)((batch + R - 1) / R);
   cudaStream_t st = (cudaStream_t)stream;
-  if (ti == 0) mlp_forward_kernel<8><<<grid, kThreads, h->smem_fwd[0], st>>>(s, params + h->ar.off(net), x, y, (int)batch);
-  else mlp_forward_kernel<16><<<grid, kThreads, h->smem_fwd[1], st>>>(s, params + h->ar.off(net), x, y, (int)batch);
+#define RTD3_FWD(RR) mlp_forward_kernel<RR><<<grid, kThreads, h->smem_fwd[ti], st>>>(s, params + h->ar.off(net), x, y, (int)batch)
+  if (ti == 0) RTD3_FWD(4); else if (ti == 1) RTD3_FWD(8); else RTD3_FWD(16);
+#undef RTD3_FWD
   RTD3_LAUNCHED();
   return 0;
 }

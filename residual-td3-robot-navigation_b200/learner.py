@@ -258,6 +258,8 @@ class TD3:
         self.adam_m = torch.zeros_like(self.grads)
         self.adam_v = torch.zeros_like(self.grads)
         self.steps = torch.zeros((2,), dtype=torch.int32, device=self.device)       # Adam step counters {actor, critics}
+        self.beta_pows = torch.ones((4,), dtype=torch.float64, device=self.device)  # {0.9^t, 0.999^t} per optimiser
+        self._scratch = None
 
         # online networks adopt arena slots 0..2; targets are copies (copy.deepcopy, robot.py:232-234)
         self.actor_network, self.critic_network_1, self.critic_network_2 = actor_network, critic_network_1, critic_network_2
@@ -283,6 +285,11 @@ class TD3:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.last_losses = None
+        self._graphs = {}
+        if self.world > 1:                  # initialise the communicator outside of any graph capture
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=process_group)
+            self.grads.zero_()
 
     def __del__(self):
         try:
@@ -314,25 +321,33 @@ class TD3:
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=self.process_group)
 
+    def _row_scratch(self, B):
+        need = int(_lib.lib().rtd3_td3_scratch_floats(self._handle, B))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty((need,), dtype=torch.float32, device=self.device)
+        return self._scratch
+
     def _critic_step(self, rb, idx, noise, loss2, q_out=None, y_out=None):
         B = idx.numel()
         _lib.check(_lib.lib().rtd3_td3_critic_step(
-            self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(rb.s), _lib.ptr(rb.a), _lib.ptr(rb.r), _lib.ptr(rb.s2),
-            _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise, self.noise_clip, float(self.max_action),
-            _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps), _lib.stream_ptr(self.device)), "td3_critic_step")
+            self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(rb.a),
+            _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise,
+            self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
+            _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step")
         self._allreduce()
         self._adam(nets=0b110, polyak=0)
 
     def _actor_step(self, rb, idx, loss1):
         B = idx.numel()
-        _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(rb.s),
-                                                  _lib.ptr(idx), B, _lib.ptr(loss1), _lib.ptr(self.steps),
-                                                  _lib.stream_ptr(self.device)), "td3_actor_step")
+        _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads),
+                                                  _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1),
+                                                  _lib.ptr(self.steps), _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)),
+                   "td3_actor_step")
         self._allreduce()
 
     def _adam(self, nets, polyak):
         _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
-                                                   _lib.ptr(self.adam_v), _lib.ptr(self.steps), nets, self.actor_lr, self.critic_lr,
+                                                   _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
 
     def _noise(self, shape):
@@ -377,30 +392,57 @@ class TD3:
         finally:
             self.tau = old_tau
 
-    def td3_update(self, replay_buffer, noise=None, idx=None):
+    def _run_epochs(self, rb, idx, noise, closs, aloss):
+        """The epoch loop of robot.py:272-285 as a stream of kernel launches (capturable in a CUDA graph)."""
+        k = ka = 0
+        for e in range(self.num_epochs):
+            self._critic_step(rb, idx[k], noise[e], closs[e])
+            k += 1
+            if e % self.policy_update_delay == 0:
+                self._actor_step(rb, idx[k], aloss[ka:ka + 1])
+                k += 1
+                ka += 1
+                self._adam(nets=0b001, polyak=0b111)
+
+    def td3_update(self, replay_buffer, noise=None, idx=None, use_graph=True):
         """robot.py:258-285: `num_epochs` critic steps, an actor step + the three Polyak updates every
-        `policy_update_delay`-th epoch.  Returns (critic_losses `[E,2]`, actor_losses `[E_actor]`) as CPU tensors -
-        the values the reference collects at robot.py:274-280."""
+        `policy_update_delay`-th epoch.  Returns (critic_losses `[E,2]`, actor_losses `[E_actor]`) as device tensors -
+        the values the reference collects at robot.py:274-280.  The whole loop is one CUDA graph (captured on first use per
+        replay buffer / shape), so an update is a single host call: index draw, noise draw, graph launch."""
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
-        actor_epochs = [e for e in range(E) if e % delay == 0]
-        count = E + len(actor_epochs)
+        n_actor = len([e for e in range(E) if e % delay == 0])
+        count = E + n_actor
         if idx is None:
             idx = replay_buffer.sample_indices(B, count)            # in the order the reference draws them
             if idx is None:
                 raise TypeError("cannot unpack non-iterable NoneType object")
-        idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
-        noise = self._noise((E, B, 2)) if noise is None else noise.to(self.device, torch.float32).contiguous()
-        closs = torch.zeros((E, 2), dtype=torch.float32, device=self.device)
-        aloss = torch.zeros((max(1, len(actor_epochs)),), dtype=torch.float32, device=self.device)
-        k = 0
-        ka = 0
-        for e in range(E):
-            self._critic_step(replay_buffer, idx[k], noise[e], closs[e])
-            k += 1
-            if e % delay == 0:
-                self._actor_step(replay_buffer, idx[k], aloss[ka:ka + 1])
-                k += 1
-                ka += 1
-                self._adam(nets=0b001, polyak=0b111)
-        self.last_losses = (closs, aloss[:len(actor_epochs)])
+        B = idx.shape[1]
+        key = (id(replay_buffer), E, B, delay)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"idx": torch.zeros((count, B), dtype=torch.int32, device=self.device),
+                  "noise": torch.zeros((E, B, 2), dtype=torch.float32, device=self.device),
+                  "closs": torch.zeros((E, 2), dtype=torch.float32, device=self.device),
+                  "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None}
+            self._row_scratch(B)
+            self._graphs[key] = st
+        st["idx"].copy_(idx)
+        if noise is None:
+            st["noise"].normal_()                                     # torch.randn_like, robot.py:338 (unseeded there)
+        else:
+            st["noise"].copy_(noise)
+        if use_graph:
+            if st["graph"] is None:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    st["closs"].zero_()
+                    st["aloss"].zero_()
+                    self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+                st["graph"] = graph
+            st["graph"].replay()
+        else:
+            st["closs"].zero_()
+            st["aloss"].zero_()
+            self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+        self.last_losses = (st["closs"], st["aloss"][:n_actor])
         return self.last_losses
