@@ -122,7 +122,8 @@ int32_t rtd3_replay_gather(const float* s, const float* a, const float* r, const
 
 /* The index half of ReplayBuffer.sample (robot.py:111): `count` consecutive draws of
  * np.random.choice(n, batch, replace=False) from stream `stream_id` of the bank, bit-exact with numpy's
- * legacy shuffle.  out: int32 [count][batch].  scratch: int32 [n], only needed when n > 48000. */
+ * legacy shuffle.  out: int32 [count][batch].  scratch: int32 [count][n] (the swap lists; transient).
+ * n <= 56000. */
 int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t stream_id, int32_t n, int32_t batch, int32_t count,
                                     int32_t* out, int32_t* scratch, void* stream);
 

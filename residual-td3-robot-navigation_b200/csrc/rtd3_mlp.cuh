@@ -142,57 +142,66 @@ __device__ __forceinline__ void fwd_first(const float* __restrict__ W, const flo
   __syncthreads();
 }
 
-// stage rows [0,N) x cols [k0,k0+kc) of a row-major [N][K] matrix into smem_f[wst..] as [N][kLdW]; kc in {4,8,12,16}
-__device__ __forceinline__ void stage_rowpat(int wst, const float* __restrict__ W, int N, int K, int k0, int kc) {
-  if (kc == kKC) {
-    for (int idx = threadIdx.x; idx < N * (kKC / 4); idx += kThreads) {
-      const int row = idx >> 2, j = idx & 3;
-      cp_async16(smem_f + wst + row * kLdW + 4 * j, W + row * K + k0 + 4 * j);
-    }
-  } else {
-    const int q = kc >> 2;
-    for (int idx = threadIdx.x; idx < N * q; idx += kThreads) {
-      const int row = idx / q, j = idx - row * q;
-      cp_async16(smem_f + wst + row * kLdW + 4 * j, W + row * K + k0 + 4 * j);
-    }
-  }
-}
-// stage rows [n0,n0+nc) x all K cols of a row-major [N][K] matrix into smem_f[wst..] as [nc][K] (a contiguous block)
-__device__ __forceinline__ void stage_colpat(int wst, const float* __restrict__ W, int K, int n0, int nc) {
-  const float* src = W + n0 * K;
-  for (int idx = threadIdx.x; idx < (nc * K) >> 2; idx += kThreads) cp_async16(smem_f + wst + 4 * idx, src + 4 * idx);
-}
-
 // ---- hidden layer forward: Y[r][c] = relu(b[c] + sum_k X[r][k] * W[c][k]) -------------------------------------
+// Weight tile of a stage: rows [0,N) x cols [k0,k0+kc) of the row-major [N][K] matrix, laid out [N][kLdW].
+// Thread t copies quarter (t&3) of rows (t>>2) + 64*i: four 16 B cp.async per stage, sources advance by kKC floats.
 template <int R>
 __device__ __forceinline__ void fwd_hidden(const float* __restrict__ W, const float* __restrict__ b, int X, int Y, int ld, int N, int K, int wst) {
   const int c = threadIdx.x;
-  float acc[R];
+  const int srow = c >> 2, sq = c & 3;
+  const float* src = W + srow * K + 4 * sq;
+  float* dst = smem_f + wst + srow * kLdW + 4 * sq;
+  const int rowstep = 64 * K;
+  auto stage = [&](int ch) {
+    const int k0 = ch * kKC;
+    if (4 * sq < K - k0) {
+      float* d = dst + (ch % kStages) * kStageFloats;
+      const float* g = src + k0;
+#pragma unroll
+      for (int i = 0; i < kMaxHidden / 64; ++i)
+        if (srow + 64 * i < N) cp_async16(d + i * 64 * kLdW, g + i * rowstep);
+    }
+  };
+  float acc0[R], acc1[R];
   const float bias = (c < N) ? __ldg(b + c) : 0.f;
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = bias;
+  for (int r = 0; r < R; ++r) { acc0[r] = bias; acc1[r] = 0.f; }
   const int nchunks = (K + kKC - 1) / kKC;
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    if (s < nchunks) stage_rowpat(wst + s * kStageFloats, W, N, K, s * kKC, min(kKC, K - s * kKC));
+    if (s < nchunks) stage(s);
     cp_commit();
   }
+  const float* xbase = smem_f + X;
   for (int ch = 0; ch < nchunks; ++ch) {
     cp_wait<kStages - 2>();            // chunk ch has landed (this thread's copies) ...
     __syncthreads();                   // ... and everyone's; everyone is also done reading chunk ch-1's slot
-    const int nx = ch + kStages - 1;
-    if (nx < nchunks) stage_rowpat(wst + (nx % kStages) * kStageFloats, W, N, K, nx * kKC, min(kKC, K - nx * kKC));
+    if (ch + kStages - 1 < nchunks) stage(ch + kStages - 1);
     cp_commit();
-    const int k0 = ch * kKC, kc = min(kKC, K - k0);
+    const int k0 = ch * kKC;
     if (c < N) {
-      const int wrow = wst + (ch % kStages) * kStageFloats + c * kLdW;
-      for (int kk = 0; kk < kc; kk += 4) {
-        const float4 w = lds4(wrow + kk);
+      const float* wrow = smem_f + wst + (ch % kStages) * kStageFloats + c * kLdW;
+      const float* xr = xbase + k0;
+      if (K - k0 >= kKC) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 x = lds4(X + r * ld + k0 + kk);   // warp-broadcast
-          acc[r] = fmaf(x.x, w.x, acc[r]); acc[r] = fmaf(x.y, w.y, acc[r]);
-          acc[r] = fmaf(x.z, w.z, acc[r]); acc[r] = fmaf(x.w, w.w, acc[r]);
+        for (int kk = 0; kk < kKC; kk += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + kk);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(xr + r * ld + kk);   // warp-broadcast
+            acc0[r] = fmaf(x.x, w.x, acc0[r]); acc1[r] = fmaf(x.y, w.y, acc1[r]);
+            acc0[r] = fmaf(x.z, w.z, acc0[r]); acc1[r] = fmaf(x.w, w.w, acc1[r]);
+          }
+        }
+      } else {
+        for (int kk = 0; kk < K - k0; kk += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + kk);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 x = *reinterpret_cast<const float4*>(xr + r * ld + kk);
+            acc0[r] = fmaf(x.x, w.x, acc0[r]); acc1[r] = fmaf(x.y, w.y, acc1[r]);
+            acc0[r] = fmaf(x.z, w.z, acc0[r]); acc1[r] = fmaf(x.w, w.w, acc1[r]);
+          }
         }
       }
     }
@@ -200,7 +209,7 @@ __device__ __forceinline__ void fwd_hidden(const float* __restrict__ W, const fl
   cp_wait<0>();
   if (c < N) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) smem_f[Y + r * ld + c] = fmaxf(acc[r], 0.f);
+    for (int r = 0; r < R; ++r) smem_f[Y + r * ld + c] = fmaxf(acc0[r] + acc1[r], 0.f);
   }
   __syncthreads();
 }
@@ -254,35 +263,55 @@ __device__ __forceinline__ void bwd_out(const float* __restrict__ W, int H, int 
 }
 
 // Input gradient of a hidden layer: dzp[r][k] = relu'(Hprev[r][k]) * sum_n dz[r][n] * W[n][k]
+// Weight tile of a stage: rows [n0,n0+nc) x all K cols = a contiguous block, laid out [nc][K]; thread k reads column k.
 template <int R>
 __device__ __forceinline__ void bwd_input(const float* __restrict__ W, int dz, int Hprev, int dzp, int ld, int N, int K, int wst) {
   const int k = threadIdx.x;
-  float acc[R];
+  auto stage = [&](int ch) {
+    const int n0 = ch * kKC, nc = min(kKC, N - n0);
+    const float* g = W + n0 * K;
+    float* d = smem_f + wst + (ch % kStages) * kStageFloats;
+    for (int idx = k; idx < (nc * K) >> 2; idx += kThreads) cp_async16(d + 4 * idx, g + 4 * idx);
+  };
+  float acc0[R], acc1[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  for (int r = 0; r < R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
   const int nchunks = (N + kKC - 1) / kKC;
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    if (s < nchunks) stage_colpat(wst + s * kStageFloats, W, K, s * kKC, min(kKC, N - s * kKC));
+    if (s < nchunks) stage(s);
     cp_commit();
   }
+  const float* dbase = smem_f + dz;
   for (int ch = 0; ch < nchunks; ++ch) {
     cp_wait<kStages - 2>();
     __syncthreads();
-    const int nx = ch + kStages - 1;
-    if (nx < nchunks) stage_colpat(wst + (nx % kStages) * kStageFloats, W, K, nx * kKC, min(kKC, N - nx * kKC));
+    if (ch + kStages - 1 < nchunks) stage(ch + kStages - 1);
     cp_commit();
-    const int n0 = ch * kKC, nc = min(kKC, N - n0);
+    const int n0 = ch * kKC;
     if (k < K) {
-      const int cur = wst + (ch % kStages) * kStageFloats + k;
-      for (int nn = 0; nn < nc; nn += 4) {
-        const float w0 = smem_f[cur + (nn + 0) * K], w1 = smem_f[cur + (nn + 1) * K], w2 = smem_f[cur + (nn + 2) * K],
-                    w3 = smem_f[cur + (nn + 3) * K];
+      const float* wp = smem_f + wst + (ch % kStages) * kStageFloats + k;
+      const float* dr = dbase + n0;
+      if (N - n0 >= kKC) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 d = lds4(dz + r * ld + n0 + nn);   // warp-broadcast
-          acc[r] = fmaf(d.x, w0, acc[r]); acc[r] = fmaf(d.y, w1, acc[r]);
-          acc[r] = fmaf(d.z, w2, acc[r]); acc[r] = fmaf(d.w, w3, acc[r]);
+        for (int nn = 0; nn < kKC; nn += 4) {
+          const float w0 = wp[(nn + 0) * K], w1 = wp[(nn + 1) * K], w2 = wp[(nn + 2) * K], w3 = wp[(nn + 3) * K];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 d = *reinterpret_cast<const float4*>(dr + r * ld + nn);   // warp-broadcast
+            acc0[r] = fmaf(d.x, w0, acc0[r]); acc1[r] = fmaf(d.y, w1, acc1[r]);
+            acc0[r] = fmaf(d.z, w2, acc0[r]); acc1[r] = fmaf(d.w, w3, acc1[r]);
+          }
+        }
+      } else {
+        for (int nn = 0; nn < N - n0; nn += 4) {
+          const float w0 = wp[(nn + 0) * K], w1 = wp[(nn + 1) * K], w2 = wp[(nn + 2) * K], w3 = wp[(nn + 3) * K];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 d = *reinterpret_cast<const float4*>(dr + r * ld + nn);
+            acc0[r] = fmaf(d.x, w0, acc0[r]); acc1[r] = fmaf(d.y, w1, acc1[r]);
+            acc0[r] = fmaf(d.z, w2, acc0[r]); acc1[r] = fmaf(d.w, w3, acc1[r]);
+          }
         }
       }
     }
@@ -290,7 +319,7 @@ __device__ __forceinline__ void bwd_input(const float* __restrict__ W, int dz, i
   cp_wait<0>();
   if (k < K) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) smem_f[dzp + r * ld + k] = smem_f[Hprev + r * ld + k] > 0.f ? acc[r] : 0.f;
+    for (int r = 0; r < R; ++r) smem_f[dzp + r * ld + k] = smem_f[Hprev + r * ld + k] > 0.f ? acc0[r] + acc1[r] : 0.f;
   }
   __syncthreads();
 }

@@ -99,11 +99,10 @@ class ReplayBuffer:
         if self.size < batch_size:
             return None
         out = torch.empty((count, batch_size), dtype=torch.int32, device=self.device)
-        scratch = None
-        if self.size > 48000:
-            if self._scratch is None or self._scratch.numel() < self.size:
-                self._scratch = torch.empty((self.capacity,), dtype=torch.int32, device=self.device)
-            scratch = self._scratch
+        need = count * self.size
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty((need,), dtype=torch.int32, device=self.device)
+        scratch = self._scratch
         if self._numpy_global:
             self._bank.sync_from_numpy()
         _lib.check(_lib.lib().rtd3_sample_indices_mt19937(self._bank.ref, 0, self.size, batch_size, count, _lib.ptr(out),
