@@ -183,6 +183,43 @@ int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* ad
 int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* x, float* y, int64_t batch,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Robot per-step hooks                         (robot.py:443-675, 727-762)
+ * Per-env robot state lives in caller-owned device arrays: goal [2][n] float64; stuck history ring
+ * hist [5][2][n] float32 with hist_count/hist_head int32 [n]; goal_reached / stuck_flag / demo_flag uint8 [n];
+ * plan_index / path_length / num_episodes int32 [n]; noise_scale float64 [n].
+ * ---------------------------------------------------------------------------------------------- */
+
+/* baseline_action = state - goal as float32 [n][2] (robot.py:556/586, :612) - the actor's input. */
+int32_t rtd3_robot_baseline(const float* x, const float* y, const double* goal, float* base, int64_t n, void* stream);
+
+/* get_next_action_training / _testing after the actor forward (robot.py:560-567 / 590-593):
+ * action = clip(baseline + residual [n][2] + unit_noise * noise_scale * 5, +-5) evaluated in float64;
+ * unit_noise [2][n] float64 standard normals (NULL = testing, no noise; robot.py:640 otherwise).
+ * ax, ay receive float32 actions, action64 (nullable) [2][n] the float64 values. */
+int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* goal, const float* residual,
+                                  const double* unit_noise, const double* noise_scale, float* ax, float* ay,
+                                  double* action64, int64_t n, void* stream);
+
+/* Robot.process_transition (robot.py:645-675) for n envs: compute_reward (robot.py:727-762: goal radius,
+ * distance to goal, 10 x distance to the nearest of the num_demo demonstration states demo [num_demo][2]
+ * float64 shared by all envs, applied where demo_flag is set), check_if_stuck on the pre-step state
+ * (robot.py:509-538, -50 penalty), done = plan_index == path_length - 1, and the replay push of the n rows at
+ * (position + i) % capacity (rp_s == NULL skips the push).  reward float32 [n] (reward64 nullable float64). */
+int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
+                              uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index,
+                              const int32_t* path_length, const float* sx, const float* sy, const float* ax, const float* ay,
+                              const float* nx, const float* ny, const double* demo, int64_t num_demo, float* reward,
+                              double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2,
+                              float* rp_notdone, int64_t capacity, int64_t position, int64_t n, void* stream);
+
+/* Robot.get_next_action_type + Robot.reset (robot.py:443-506) for n envs.  type_out int8 [n]: 0 'step',
+ * 1 'demo', 2 'reset'; update_out uint8 [n] marks envs whose episode ended (where the reference calls
+ * td3_update, robot.py:480-483); any_update int32 [1] (zeroed by the caller) is set if any env did. */
+int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, int32_t* plan_index, int32_t* path_length,
+                                    uint8_t* goal_reached, uint8_t* stuck_flag, double* noise_scale, int8_t* type_out,
+                                    uint8_t* update_out, int32_t* any_update, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

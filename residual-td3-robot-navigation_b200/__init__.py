@@ -7,6 +7,7 @@ from . import _lib, configuration, constants  # noqa: F401
 from .environment import Environment, synthetic_maps  # noqa: F401
 from .rng import MtBank  # noqa: F401
 from .learner import ReplayBuffer, Residual_Actor_Network, Residual_Critic_Network, TD3  # noqa: F401
+from .robot import Robot  # noqa: F401
 
 __all__ = ["Environment", "MtBank", "synthetic_maps", "constants", "configuration", "ReplayBuffer", "Residual_Actor_Network",
-           "Residual_Critic_Network", "TD3"]
+           "Residual_Critic_Network", "TD3", "Robot"]

@@ -52,6 +52,10 @@ _SIGNATURES = {
     "rtd3_td3_actor_step": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, _P]),
     "rtd3_td3_adam_polyak": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_float, c_int32, c_float, _P]),
     "rtd3_mlp_forward": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, _P]),
+    "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
+    "rtd3_robot_compose_action": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rtd3_robot_transition": (c_int32, [_P] * 16 + [c_int64] + [_P] * 8 + [c_int64] * 3 + [_P]),
+    "rtd3_robot_next_action_type": (c_int32, [_P] * 10 + [c_int64, _P]),
 }
 
 _lib = None

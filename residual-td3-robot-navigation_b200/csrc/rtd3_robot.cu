@@ -1,0 +1,236 @@
+// Robot per-step hooks batched over n envs.  Reference behaviour: /root/reference/robot.py
+//   get_next_action_training / testing, residual_action, generate_noise      robot.py:541-642
+//   process_transition, compute_reward, check_if_stuck                      robot.py:645-675, 727-762, 509-538
+//   get_next_action_type, reset                                             robot.py:443-506
+// The actor forward inside the act hook is rtd3_mlp_forward (rtd3_td3.cu); the kernels here are the glue around it.
+// Threshold compares (goal radius 5, stuck radius 2) are evaluated in float64 from the float32 states and the
+// float64 goal with numpy's norm rounding (rtd3_mt.cuh: norm2_np), so the flags match the reference bit for bit.
+#include "rtd3_common.cuh"
+#include "rtd3_mt.cuh"
+
+namespace rtd3 {
+
+constexpr int kStuckSteps = 5;          // robot.py:40
+constexpr double kStuckThreshold = 2.0; // robot.py:39
+constexpr double kStuckPenalty = 50.0;  // robot.py:41
+constexpr double kGoalReward = 50.0;    // robot.py:42
+constexpr double kGoalRadius = 5.0;     // constants.py:50
+constexpr int kNumDemo = 3;             // robot.py:22
+
+// baseline_action = state - goal (robot.py:556 / 586), cast to float32 as torch.FloatTensor does (robot.py:612)
+__global__ void robot_baseline_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ goal,
+                                      float* __restrict__ base /*[n][2]*/, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  reinterpret_cast<float2*>(base)[i] = make_float2((float)((double)x[i] - goal[i]), (float)((double)y[i] - goal[n + i]));
+}
+
+// action = clip(baseline + residual + noise, +-5)   (robot.py:560-567 / 590-593); noise = unit_normal * noise_scale * 5 (robot.py:640)
+__global__ void robot_compose_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ goal,
+                                     const float* __restrict__ residual /*[n][2]*/, const double* __restrict__ unit_noise /*nullable [2][n]*/,
+                                     const double* __restrict__ noise_scale /*[n]*/, float* __restrict__ ax, float* __restrict__ ay,
+                                     double* __restrict__ action64 /*nullable [2][n]*/, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 res = reinterpret_cast<const float2*>(residual)[i];
+  double cx = __dadd_rn(__dsub_rn((double)x[i], goal[i]), (double)res.x);
+  double cy = __dadd_rn(__dsub_rn((double)y[i], goal[n + i]), (double)res.y);
+  if (unit_noise) {
+    const double sc = __dmul_rn(noise_scale[i], 5.0);
+    cx = __dadd_rn(cx, __dmul_rn(sc, unit_noise[i]));
+    cy = __dadd_rn(cy, __dmul_rn(sc, unit_noise[n + i]));
+  }
+  cx = cx < -5.0 ? -5.0 : (cx > 5.0 ? 5.0 : cx);
+  cy = cy < -5.0 ? -5.0 : (cy > 5.0 ? 5.0 : cy);
+  ax[i] = (float)cx;
+  ay[i] = (float)cy;
+  if (action64) { action64[i] = cx; action64[n + i] = cy; }
+}
+
+struct RobotState {
+  const double* goal;       // [2][n]
+  float* hist;              // [5][2][n] ring of pre-step states (robot.py:425, 509-538)
+  int32_t* hist_count;      // [n]
+  int32_t* hist_head;       // [n] slot of the oldest entry
+  uint8_t* goal_reached;    // [n]
+  uint8_t* stuck_flag;      // [n]
+  const uint8_t* demo_flag; // [n]
+  const int32_t* plan_index;
+  const int32_t* path_length;
+};
+
+struct ReplayRing {
+  float2* s; float2* a; float* r; float2* s2; float* notdone;
+  int64_t capacity, position;
+};
+
+// process_transition for n envs; demo points ([m][2] float64, shared by all envs) are swept from shared memory.
+__global__ void __launch_bounds__(256)
+robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ ax,
+                        const float* __restrict__ ay, const float* __restrict__ nx, const float* __restrict__ ny,
+                        const double* __restrict__ demo, int64_t m, float* __restrict__ reward_out, double* __restrict__ reward64,
+                        uint8_t* __restrict__ done_out, ReplayRing ring, int64_t n) {
+  __shared__ double2 tile[512];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const int64_t ii = live ? i : 0;
+  const double px = (double)nx[ii], py = (double)ny[ii];
+  // compute_reward([next_state])  robot.py:741-762
+  const double gd = norm2_np(__dsub_rn(px, st.goal[ii]), __dsub_rn(py, st.goal[n + ii]));
+  const bool reached = (-gd >= -kGoalRadius);
+  // nearest demonstration state (only needed when the goal was not reached and there are demos): min over m points
+  double best = INFINITY;
+  if (m > 0) {
+    for (int64_t base = 0; base < m; base += 512) {
+      const int cnt = (int)min((int64_t)512, m - base);
+      __syncthreads();
+      for (int k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = reinterpret_cast<const double2*>(demo)[base + k];
+      __syncthreads();
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const double dx = px - tile[k].x, dy = py - tile[k].y;
+        best = fmin(best, fma(dy, dy, dx * dx));     // squared distance; sqrt once at the end (monotone)
+      }
+    }
+  }
+  if (!live) return;
+  double reward;
+  if (reached) {
+    st.goal_reached[i] = 1;
+    reward = kGoalReward;
+  } else if (m == 0) {
+    reward = -gd;
+  } else {
+    const double prox = st.demo_flag[i] ? -sqrt(best) : 0.0;
+    reward = __dadd_rn(-gd, __dmul_rn(10.0, prox));   // DEMO_PROXIMITY_FACTOR, robot.py:43, 760
+  }
+  // check_if_stuck(state)  robot.py:509-538, on the pre-step state
+  const double cxs = (double)sx[i], cys = (double)sy[i];
+  int cnt = st.hist_count[i], head = st.hist_head[i];
+  bool stuck = false;
+  if (cnt >= kStuckSteps) {
+    stuck = true;
+    for (int k = 0; k < kStuckSteps; ++k) {
+      const double hx = (double)st.hist[(int64_t)(2 * k) * n + i], hy = (double)st.hist[(int64_t)(2 * k + 1) * n + i];
+      if (!(norm2_np(__dsub_rn(cxs, hx), __dsub_rn(cys, hy)) < kStuckThreshold)) stuck = false;
+    }
+    if (stuck) { cnt = 0; head = 0; }                 // previous_states.clear()
+    else { head = (head + 1) % kStuckSteps; cnt -= 1; }   // pop(0)
+  }
+  const int slot = (head + cnt) % kStuckSteps;        // append(state)
+  st.hist[(int64_t)(2 * slot) * n + i] = sx[i];
+  st.hist[(int64_t)(2 * slot + 1) * n + i] = sy[i];
+  st.hist_count[i] = cnt + 1;
+  st.hist_head[i] = head;
+  if (stuck) {
+    st.stuck_flag[i] = 1;
+    reward = __dsub_rn(reward, kStuckPenalty);
+  }
+  const bool done = st.plan_index[i] == st.path_length[i] - 1;   // robot.py:672: time-out only
+  reward_out[i] = (float)reward;
+  if (reward64) reward64[i] = reward;
+  done_out[i] = done ? 1 : 0;
+  if (ring.s) {                                       // memory.push  robot.py:675
+    const int64_t p = (ring.position + i) % ring.capacity;
+    ring.s[p] = make_float2(sx[i], sy[i]);
+    ring.a[p] = make_float2(ax[i], ay[i]);
+    ring.r[p] = (float)reward;
+    ring.s2[p] = make_float2(nx[i], ny[i]);
+    ring.notdone[p] = done ? 0.f : 1.f;
+  }
+}
+
+// get_next_action_type + reset  (robot.py:443-506).  type: 0 'step', 1 'demo', 2 'reset'; update[i] = 1 where the
+// reference would call td3_update (robot.py:480-483).
+__global__ void robot_action_type_kernel(int32_t* __restrict__ num_episodes, uint8_t* __restrict__ demo_flag, int32_t* __restrict__ plan_index,
+                                         int32_t* __restrict__ path_length, uint8_t* __restrict__ goal_reached, uint8_t* __restrict__ stuck_flag,
+                                         double* __restrict__ noise_scale, int8_t* __restrict__ type_out, uint8_t* __restrict__ update_out,
+                                         int32_t* __restrict__ any_update, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool upd = false;
+  if (i < n) {
+    int ne = num_episodes[i];
+    bool df = demo_flag[i] != 0;
+    int type = 0;
+    if (ne <= kNumDemo && !df) { ne += 1; type = 1; }
+    if (ne > kNumDemo && !df) { df = true; ne += 1; type = 2; }
+    if (plan_index[i] == path_length[i] - 1 || goal_reached[i] || stuck_flag[i]) {
+      ne += 1;                                        // Robot.reset  robot.py:492-506
+      plan_index[i] = 0;
+      goal_reached[i] = 0;
+      stuck_flag[i] = 0;
+      noise_scale[i] = __dmul_rn(noise_scale[i], 0.75);
+      path_length[i] += 20;
+      type = 2;
+      upd = true;
+    } else {
+      plan_index[i] += 1;
+    }
+    num_episodes[i] = ne;
+    demo_flag[i] = df ? 1 : 0;
+    type_out[i] = (int8_t)type;
+    update_out[i] = upd ? 1 : 0;
+  }
+  if (__any_sync(0xffffffffu, upd) && (threadIdx.x & 31) == 0) atomicOr(any_update, 1);   // one flag per warp that needs it
+}
+
+}  // namespace rtd3
+
+using namespace rtd3;
+
+extern "C" {
+
+int32_t rtd3_robot_baseline(const float* x, const float* y, const double* goal, float* base, int64_t n, void* stream) {
+  RTD3_CHECK_ARG(x && y && goal && base && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  robot_baseline_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, goal, base, n);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* goal, const float* residual, const double* unit_noise,
+                                  const double* noise_scale, float* ax, float* ay, double* action64, int64_t n, void* stream) {
+  RTD3_CHECK_ARG(x && y && goal && residual && ax && ay && n >= 0, "bad argument");
+  RTD3_CHECK_ARG(!unit_noise || noise_scale, "noise needs noise_scale");
+  if (n == 0) return 0;
+  robot_compose_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, goal, residual, unit_noise, noise_scale, ax, ay, action64, n);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
+                              uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index, const int32_t* path_length,
+                              const float* sx, const float* sy, const float* ax, const float* ay, const float* nx, const float* ny,
+                              const double* demo, int64_t num_demo, float* reward, double* reward64, uint8_t* done, float* rp_s, float* rp_a,
+                              float* rp_r, float* rp_s2, float* rp_notdone, int64_t capacity, int64_t position, int64_t n, void* stream) {
+  RTD3_CHECK_ARG(goal && hist && hist_count && hist_head && goal_reached && stuck_flag && demo_flag && plan_index && path_length,
+                 "null robot state");
+  RTD3_CHECK_ARG(sx && sy && ax && ay && nx && ny && reward && done, "null transition array");
+  RTD3_CHECK_ARG(num_demo == 0 || demo, "demo set missing");
+  RTD3_CHECK_ARG(n >= 0, "negative n");
+  RTD3_CHECK_ARG(!rp_s || (rp_a && rp_r && rp_s2 && rp_notdone && capacity > 0 && position >= 0 && position < capacity && n <= capacity),
+                 "bad replay ring");
+  if (n == 0) return 0;
+  RobotState st{goal, hist, hist_count, hist_head, goal_reached, stuck_flag, demo_flag, plan_index, path_length};
+  ReplayRing ring{(float2*)rp_s, (float2*)rp_a, rp_r, (float2*)rp_s2, rp_notdone, capacity, position};
+  robot_transition_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(st, sx, sy, ax, ay, nx, ny, demo, num_demo, reward, reward64,
+                                                                                  done, ring, n);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, int32_t* plan_index, int32_t* path_length,
+                                    uint8_t* goal_reached, uint8_t* stuck_flag, double* noise_scale, int8_t* type_out, uint8_t* update_out,
+                                    int32_t* any_update, int64_t n, void* stream) {
+  RTD3_CHECK_ARG(num_episodes && demo_flag && plan_index && path_length && goal_reached && stuck_flag && noise_scale && type_out &&
+                     update_out && any_update && n >= 0,
+                 "bad argument");
+  if (n == 0) return 0;
+  robot_action_type_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(num_episodes, demo_flag, plan_index, path_length,
+                                                                                   goal_reached, stuck_flag, noise_scale, type_out, update_out,
+                                                                                   any_update, n);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -212,6 +212,43 @@ class Environment:
         self._state.copy_(keep)
         return out
 
+    # ---- environment.py:140-179 (the 80 000 serial dynamics calls become 4 rollouts of 100 paths) ----
+    def get_demonstration(self):
+        """Cross-entropy-method planner of the reference.  Random draws (start state, iteration-0 action signs, later
+        Gaussian action samples) come from numpy's stream in the reference's order; the 100 x 200-step path rollouts of
+        every iteration run as one launch of the rollout kernel (float32 state, so paths agree with the float64
+        reference to the per-step tolerance, not bit for bit)."""
+        if self.num_envs != 1:
+            raise NotImplementedError("get_demonstration is defined for the single-env form")
+        c = constants
+        I, P, T, E = c.DEMOS_CEM_NUM_ITERATIONS, c.DEMOS_CEM_NUM_PATHS, c.DEMOS_CEM_PATH_LENGTH, c.DEMOS_CEM_NUM_ELITES
+        planning_actions = np.zeros([I, P, T, 2], dtype=np.float32)
+        planning_paths = np.zeros([I, P, T + 1, 2], dtype=np.float32)
+        planning_path_rewards = np.zeros([I, P])
+        start = self.get_random_robot_init_state()
+        goal = self.goal_state
+        mean = std = None
+        for it in range(I):
+            if it == 0:
+                acts = np.random.choice([-c.ROBOT_MAX_ACTION, c.ROBOT_MAX_ACTION], (P, T, 2))
+            else:
+                acts = np.random.normal(mean[None], std[None], (P, T, 2))
+            planning_actions[it] = acts
+            x = torch.full((P,), float(np.float32(start[0])), dtype=torch.float32, device=self.device)
+            y = torch.full((P,), float(np.float32(start[1])), dtype=torch.float32, device=self.device)
+            planes = torch.from_numpy(np.ascontiguousarray(planning_actions[it].transpose(1, 2, 0))).to(self.device)   # [T,2,P]
+            traj = torch.empty((T, 2, P), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(planes), _lib.ptr(traj), P, T,
+                                                   _lib.stream_ptr(self.device)), "env_rollout")
+            planning_paths[it, :, 0] = start
+            planning_paths[it, :, 1:] = traj.permute(2, 0, 1).cpu().numpy()
+            planning_path_rewards[it] = -np.sqrt(((planning_paths[it, :, -1].astype(np.float64) - goal) ** 2).sum(axis=1))
+            elites = np.argsort(planning_path_rewards[it].copy())[-E:]
+            mean = np.mean(planning_actions[it, elites], axis=0)
+            std = np.std(planning_actions[it, elites], axis=0)
+        best = np.argmax(planning_path_rewards[-1])
+        return planning_paths[-1, best, 0:T], planning_actions[-1, best]
+
     # ---- environment.py:182-183 ---------------------------------------------------------------------
     def compute_reward(self, path):
         if self.num_envs == 1 and not isinstance(path, torch.Tensor):

@@ -1,0 +1,158 @@
+"""Parity of the CUDA Robot hooks (act / transition / episode state machine) with the reference golden trace and the oracle.
+
+Flags (done, goal reached, stuck) and action types bit-exact; actions and rewards to float32 round-off of float64 references.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.mt19937 import LegacyMT19937
+from oracle.robot_oracle import RobotOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_act_training_and_testing_vs_reference(pkg, robot_golden):
+    g = robot_golden
+    robot = pkg.Robot(g["goal"])
+    robot.td3_agent.actor_network.load_flat(g["actor_w"])
+    robot._noise_scale.fill_(0.75)
+    np.random.seed(99)                                     # the single-env robot draws from numpy's global stream (robot.py:640)
+    train = np.array([robot.get_next_action_training(s, 100.0) for s in g["act_states"]])
+    test = np.array([robot.get_next_action_testing(s) for s in g["act_states"]])
+    np.testing.assert_allclose(train, g["act_train"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(test, g["act_test"], rtol=0, atol=5e-5)
+    assert ((np.abs(g["act_train"]) == 5) == (np.abs(train) == 5)).all()
+    assert train.dtype == np.float64 and train.shape == (64, 2)
+    # numpy's stream advanced by exactly the draws the reference makes
+    m = LegacyMT19937(99)
+    for _ in range(64 * 2):
+        m.gauss()
+    assert np.random.normal() == m.gauss()
+    res = robot.residual_action(g["act_states"][0] - g["goal"])
+    np.testing.assert_allclose(res, g["act_residual"][0], rtol=1e-4, atol=1e-4)
+
+
+def test_act_batched_matches_oracle(pkg, robot_golden):
+    g = robot_golden
+    n = 3000
+    rs = np.random.RandomState(1)
+    goals = rs.uniform(5, 95, (n, 2))
+    states = rs.uniform(0, 98.9999, (n, 2)).astype(np.float32)
+    robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=11)
+    robot.td3_agent.actor_network.load_flat(g["actor_w"])
+    z = rs.normal(size=(2, n))
+    act = robot.get_next_action_training(torch.from_numpy(states).cuda(), None, noise=torch.from_numpy(z).cuda()).cpu().numpy()
+    for i in range(0, n, 37):
+        o = RobotOracle(goals[i], g["actor_w"])
+        ref = o.act(states[i].astype(np.float64), z[:, i])
+        np.testing.assert_allclose(act[i], ref, rtol=0, atol=5e-5)
+    # default noise path: per-env legacy streams seeded seed+i
+    a2 = robot.get_next_action_training(torch.from_numpy(states).cuda(), None).cpu().numpy()
+    for i in (0, 5, 2999):
+        m = LegacyMT19937(11 + i)
+        o = RobotOracle(goals[i], g["actor_w"])
+        np.testing.assert_allclose(a2[i], o.act(states[i].astype(np.float64), [m.gauss(), m.gauss()]), rtol=0, atol=5e-5)
+
+
+def test_transition_trace_vs_reference(pkg, robot_golden):
+    g = robot_golden
+    robot = pkg.Robot(g["goal"], seed=0)
+    robot.set_demonstration_states(g["demo_states"])
+    robot._demo_flag.fill_(1)
+    robot._path_length.fill_(int(g["trace_path_length"]))
+    T = g["trace_s"].shape[0]
+    for t in range(T):
+        assert robot.plan_index == g["trace_plan"][t]
+        robot.process_transition(g["trace_s"][t], g["trace_a"][t], g["trace_s2"][t], 100.0)
+        # the kernel sees float32 states; the reference float64 ones: rewards agree to float32 round-off of ~100-unit distances
+        np.testing.assert_allclose(float(robot._reward64[0]), g["trace_reward"][t], rtol=0, atol=2e-4)
+        assert bool(robot._done[0]) == g["trace_done"][t]
+        assert robot.stuck_flag == g["trace_stuck"][t] and robot.goal_reached == g["trace_reached"][t]
+        if robot.plan_index == robot.path_length - 1 or robot.goal_reached or robot.stuck_flag:
+            robot._plan_index.zero_(); robot._goal_reached.zero_(); robot._stuck_flag.zero_()
+        else:
+            robot._plan_index += 1
+    rb = robot.memory
+    assert len(rb) == T and rb.position == T
+    np.testing.assert_allclose(rb.r[:T].cpu().numpy(), g["trace_reward"], rtol=0, atol=2e-4)
+    assert ((rb.notdone[:T].cpu().numpy() < 0.5) == g["trace_done"]).all()
+    assert (rb.s[:T].cpu().numpy() == g["trace_s"].astype(np.float32)).all()
+    assert (rb.s2[:T].cpu().numpy() == g["trace_s2"].astype(np.float32)).all()
+
+
+def test_transition_batched_flags_bit_exact_vs_oracle(pkg):
+    """Many envs, float32-representable inputs so that the float64 oracle sees exactly what the kernel sees."""
+    n, T = 512, 24
+    rs = np.random.RandomState(3)
+    goals = rs.uniform(5, 95, (n, 2))
+    demos = rs.uniform(0, 99, (700, 2))
+    robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=20000)
+    robot.set_demonstration_states(demos)
+    robot._demo_flag.fill_(1)
+    robot._path_length.fill_(9)
+    orcs = []
+    for i in range(n):
+        o = RobotOracle(goals[i])
+        o.demonstration_states, o.demo_flag, o.path_length = list(demos), True, 9
+        orcs.append(o)
+    cur = rs.uniform(10, 90, (n, 2)).astype(np.float32)
+    for t in range(T):
+        step = (rs.uniform(-5, 5, (n, 2)) * np.where(rs.rand(n, 1) < 0.5, 0.1, 1.0)).astype(np.float32)
+        nxt = np.clip(cur + step, 0, 98.9999).astype(np.float32)
+        near = rs.rand(n) < 0.05                           # some envs land inside / on the edge of the goal radius
+        nxt[near] = (goals[near] + rs.uniform(-3.6, 3.6, (near.sum(), 2))).astype(np.float32)
+        robot.process_transition(torch.from_numpy(cur).cuda(), torch.from_numpy(step).cuda(), torch.from_numpy(nxt).cuda(), None)
+        rew = robot._reward64.cpu().numpy(); done = robot._done.cpu().numpy().astype(bool)
+        stuck = robot._stuck_flag.cpu().numpy().astype(bool); reached = robot._goal_reached.cpu().numpy().astype(bool)
+        for i in range(n):
+            o = orcs[i]
+            r_ref, d_ref = o.process_transition(cur[i].astype(np.float64), step[i].astype(np.float64), nxt[i].astype(np.float64))
+            assert done[i] == d_ref and stuck[i] == o.stuck_flag and reached[i] == o.goal_reached, (t, i)
+            np.testing.assert_allclose(rew[i], r_ref, rtol=1e-12, atol=1e-9)
+        # episode bookkeeping on both sides through the real state machine (td3_update is not the subject here)
+        robot.td3_agent.td3_update = lambda mem: None
+        types = robot.get_next_action_type(None, None).cpu().numpy()
+        for i in range(n):
+            assert ("step", "demo", "reset")[types[i]] == orcs[i].get_next_action_type(), (t, i)
+        cur = nxt
+    assert len(robot.memory) == n * T
+
+
+def test_state_machine_vs_reference(pkg, robot_golden):
+    g = robot_golden
+    robot = pkg.Robot(g["goal"], seed=0)
+    calls = []
+    robot.td3_agent.td3_update = lambda mem: calls.append(1)
+    code = {"step": 0, "demo": 1, "reset": 2}
+    for t in range(400):
+        if t in (200, 300):
+            robot._stuck_flag.fill_(1)
+        if t == 250:
+            robot._goal_reached.fill_(1)
+        ty = robot.get_next_action_type(np.zeros(2), 100.0)
+        assert code[ty] == g["sm_types"][t], t
+        assert robot.num_episodes == g["sm_episodes"][t] and robot.path_length == g["sm_path_len"][t]
+        assert robot.current_noise_scale == g["sm_noise"][t]
+    assert len(calls) == int(g["sm_updates"])
+
+
+def test_demonstration_pipeline_single_env(pkg, env_golden):
+    """get_demonstration -> process_demonstration: shapes, counts and RNG consumption as in the reference (SURVEY a-8, 3.4)."""
+    g = env_golden
+    np.random.seed(1707366464)
+    env = pkg.Environment(maps=(g["speed"], g["angle"]))
+    state = env.reset()
+    robot = pkg.Robot(env.goal_state)
+    demo_s, demo_a = env.get_demonstration()
+    assert demo_s.shape == (200, 2) and demo_a.shape == (200, 2) and demo_s.dtype == np.float32 and demo_a.dtype == np.float32
+    # the planner's end point is close to the goal compared with where it started
+    d0 = np.linalg.norm(demo_s[0] - env.goal_state)
+    last = env.dynamics(demo_s[-1], demo_a[-1])
+    assert np.linalg.norm(last - env.goal_state) < 0.5 * d0
+    robot.process_demonstration(demo_s, demo_a, 100.0)
+    assert len(robot.memory) == 199
+    assert len(robot.demonstration_states) == 200 + 3 * (199 * 6 + 1)      # 3 785 per demo (SURVEY: 11 355 after 3 demos)
+    assert len(robot.paths_to_draw) == 4
+    assert not robot.goal_reached
+    assert (env.robot_state == state.astype(np.float32).astype(np.float64)).all()   # planning did not move the robot
