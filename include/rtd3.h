@@ -127,6 +127,11 @@ int32_t rtd3_replay_gather(const float* s, const float* a, const float* r, const
 int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t stream_id, int32_t n, int32_t batch, int32_t count,
                                     int32_t* out, int32_t* scratch, void* stream);
 
+/* Throughput-mode index draw (NOT the reference's stream): count x batch indices uniform in [0, n) WITH
+ * replacement from Philox4x32-10(seed, offset).  For replay shards too large for the exact sampler. */
+int32_t rtd3_sample_indices_philox(uint64_t seed, uint64_t offset, int64_t n, int32_t batch, int32_t count, int32_t* out,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Residual-TD3 learner                        (robot.py:128-206 networks, :209-398 TD3)
  * Networks: actor 2->H->..->H->2, critic 4->H->..->H->1 with `layers` hidden layers (reference: H=200, 3).
@@ -196,22 +201,27 @@ int32_t rtd3_robot_baseline(const float* x, const float* y, const double* goal, 
 /* get_next_action_training / _testing after the actor forward (robot.py:560-567 / 590-593):
  * action = clip(baseline + residual [n][2] + unit_noise * noise_scale * 5, +-5) evaluated in float64;
  * unit_noise [2][n] float64 standard normals (NULL = testing, no noise; robot.py:640 otherwise).
- * ax, ay receive float32 actions, action64 (nullable) [2][n] the float64 values. */
+ * type (nullable int8 [n], the output of rtd3_robot_next_action_type): envs whose type is not 0 ('step') get a
+ * null action.  ax, ay receive float32 actions, action64 (nullable) [2][n] the float64 values. */
 int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* goal, const float* residual,
-                                  const double* unit_noise, const double* noise_scale, float* ax, float* ay,
-                                  double* action64, int64_t n, void* stream);
+                                  const double* unit_noise, const double* noise_scale, const int8_t* type, float* ax,
+                                  float* ay, double* action64, int64_t n, void* stream);
 
 /* Robot.process_transition (robot.py:645-675) for n envs: compute_reward (robot.py:727-762: goal radius,
  * distance to goal, 10 x distance to the nearest of the num_demo demonstration states demo [num_demo][2]
  * float64 shared by all envs, applied where demo_flag is set), check_if_stuck on the pre-step state
  * (robot.py:509-538, -50 penalty), done = plan_index == path_length - 1, and the replay push of the n rows at
- * (position + i) % capacity (rp_s == NULL skips the push).  reward float32 [n] (reward64 nullable float64). */
+ * (position + i) % capacity (rp_s == NULL skips the push).  reward float32 [n] (reward64 nullable float64).
+ * type (nullable int8 [n]): only envs of type 0 ('step') are processed; their rows are then compacted behind the
+ * ring's device row counter rp_total (uint64 [1], rows ever pushed; required with type, optional otherwise -
+ * when given it is advanced by n). */
 int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index,
                               const int32_t* path_length, const float* sx, const float* sy, const float* ax, const float* ay,
                               const float* nx, const float* ny, const double* demo, int64_t num_demo, float* reward,
                               double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2,
-                              float* rp_notdone, int64_t capacity, int64_t position, int64_t n, void* stream);
+                              float* rp_notdone, int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type,
+                              int64_t n, void* stream);
 
 /* Robot.get_next_action_type + Robot.reset (robot.py:443-506) for n envs.  type_out int8 [n]: 0 'step',
  * 1 'demo', 2 'reset'; update_out uint8 [n] marks envs whose episode ended (where the reference calls

@@ -4,7 +4,7 @@ There is no fallback: if the shared library is missing or a call fails, this rai
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 import torch
 
@@ -41,6 +41,7 @@ _SIGNATURES = {
     "rtd3_replay_push": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rtd3_replay_gather": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P]),
     "rtd3_sample_indices_mt19937": (c_int32, [POINTER(MtBankStruct), c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "rtd3_sample_indices_philox": (c_int32, [c_uint64, c_uint64, c_int64, c_int32, c_int32, _P, _P]),
     "rtd3_td3_create": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32]),
     "rtd3_td3_destroy": (c_int32, [_P]),
     "rtd3_td3_param_count": (c_int64, [_P, c_int32]),
@@ -53,8 +54,8 @@ _SIGNATURES = {
     "rtd3_td3_adam_polyak": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_float, c_float, c_int32, c_float, _P]),
     "rtd3_mlp_forward": (c_int32, [_P, c_int32, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
-    "rtd3_robot_compose_action": (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
-    "rtd3_robot_transition": (c_int32, [_P] * 16 + [c_int64] + [_P] * 8 + [c_int64] * 3 + [_P]),
+    "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
+    "rtd3_robot_transition": (c_int32, [_P] * 16 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
     "rtd3_robot_next_action_type": (c_int32, [_P] * 10 + [c_int64, _P]),
 }
 

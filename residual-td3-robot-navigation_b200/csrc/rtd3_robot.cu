@@ -28,10 +28,16 @@ __global__ void robot_baseline_kernel(const float* __restrict__ x, const float* 
 // action = clip(baseline + residual + noise, +-5)   (robot.py:560-567 / 590-593); noise = unit_normal * noise_scale * 5 (robot.py:640)
 __global__ void robot_compose_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ goal,
                                      const float* __restrict__ residual /*[n][2]*/, const double* __restrict__ unit_noise /*nullable [2][n]*/,
-                                     const double* __restrict__ noise_scale /*[n]*/, float* __restrict__ ax, float* __restrict__ ay,
-                                     double* __restrict__ action64 /*nullable [2][n]*/, int64_t n) {
+                                     const double* __restrict__ noise_scale /*[n]*/, const int8_t* __restrict__ type /*nullable [n]*/,
+                                     float* __restrict__ ax, float* __restrict__ ay, double* __restrict__ action64 /*nullable [2][n]*/,
+                                     int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (type && type[i] != 0) {            // this env does not step in this tick (robot-learning.py:82-95): a null action
+    ax[i] = 0.f; ay[i] = 0.f;
+    if (action64) { action64[i] = 0.0; action64[n + i] = 0.0; }
+    return;
+  }
   const float2 res = reinterpret_cast<const float2*>(residual)[i];
   double cx = __dadd_rn(__dsub_rn((double)x[i], goal[i]), (double)res.x);
   double cy = __dadd_rn(__dsub_rn((double)y[i], goal[n + i]), (double)res.y);
@@ -62,6 +68,7 @@ struct RobotState {
 struct ReplayRing {
   float2* s; float2* a; float* r; float2* s2; float* notdone;
   int64_t capacity, position;
+  unsigned long long* total;   // device counter of rows ever pushed (nullable); authoritative for masked pushes
 };
 
 // process_transition for n envs; demo points ([m][2] float64, shared by all envs) are swept from shared memory.
@@ -69,10 +76,11 @@ __global__ void __launch_bounds__(256)
 robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ ax,
                         const float* __restrict__ ay, const float* __restrict__ nx, const float* __restrict__ ny,
                         const double* __restrict__ demo, int64_t m, float* __restrict__ reward_out, double* __restrict__ reward64,
-                        uint8_t* __restrict__ done_out, ReplayRing ring, int64_t n) {
+                        uint8_t* __restrict__ done_out, ReplayRing ring, const int8_t* __restrict__ type /*nullable: only type 0 steps*/,
+                        int64_t n) {
   __shared__ double2 tile[512];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
+  const bool live = i < n && (!type || type[i] == 0);
   const int64_t ii = live ? i : 0;
   const double px = (double)nx[ii], py = (double)ny[ii];
   // compute_reward([next_state])  robot.py:741-762
@@ -93,50 +101,66 @@ robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float
       }
     }
   }
-  if (!live) return;
-  double reward;
-  if (reached) {
-    st.goal_reached[i] = 1;
-    reward = kGoalReward;
-  } else if (m == 0) {
-    reward = -gd;
-  } else {
-    const double prox = st.demo_flag[i] ? -sqrt(best) : 0.0;
-    reward = __dadd_rn(-gd, __dmul_rn(10.0, prox));   // DEMO_PROXIMITY_FACTOR, robot.py:43, 760
-  }
-  // check_if_stuck(state)  robot.py:509-538, on the pre-step state
-  const double cxs = (double)sx[i], cys = (double)sy[i];
-  int cnt = st.hist_count[i], head = st.hist_head[i];
-  bool stuck = false;
-  if (cnt >= kStuckSteps) {
-    stuck = true;
-    for (int k = 0; k < kStuckSteps; ++k) {
-      const double hx = (double)st.hist[(int64_t)(2 * k) * n + i], hy = (double)st.hist[(int64_t)(2 * k + 1) * n + i];
-      if (!(norm2_np(__dsub_rn(cxs, hx), __dsub_rn(cys, hy)) < kStuckThreshold)) stuck = false;
+  double reward = 0.0;
+  bool done = false;
+  if (live) {
+    if (reached) {
+      st.goal_reached[i] = 1;
+      reward = kGoalReward;
+    } else if (m == 0) {
+      reward = -gd;
+    } else {
+      const double prox = st.demo_flag[i] ? -sqrt(best) : 0.0;
+      reward = __dadd_rn(-gd, __dmul_rn(10.0, prox));   // DEMO_PROXIMITY_FACTOR, robot.py:43, 760
     }
-    if (stuck) { cnt = 0; head = 0; }                 // previous_states.clear()
-    else { head = (head + 1) % kStuckSteps; cnt -= 1; }   // pop(0)
+    // check_if_stuck(state)  robot.py:509-538, on the pre-step state
+    const double cxs = (double)sx[i], cys = (double)sy[i];
+    int cnt = st.hist_count[i], head = st.hist_head[i];
+    bool stuck = false;
+    if (cnt >= kStuckSteps) {
+      stuck = true;
+      for (int k = 0; k < kStuckSteps; ++k) {
+        const double hx = (double)st.hist[(int64_t)(2 * k) * n + i], hy = (double)st.hist[(int64_t)(2 * k + 1) * n + i];
+        if (!(norm2_np(__dsub_rn(cxs, hx), __dsub_rn(cys, hy)) < kStuckThreshold)) stuck = false;
+      }
+      if (stuck) { cnt = 0; head = 0; }                 // previous_states.clear()
+      else { head = (head + 1) % kStuckSteps; cnt -= 1; }   // pop(0)
+    }
+    const int slot = (head + cnt) % kStuckSteps;        // append(state)
+    st.hist[(int64_t)(2 * slot) * n + i] = sx[i];
+    st.hist[(int64_t)(2 * slot + 1) * n + i] = sy[i];
+    st.hist_count[i] = cnt + 1;
+    st.hist_head[i] = head;
+    if (stuck) {
+      st.stuck_flag[i] = 1;
+      reward = __dsub_rn(reward, kStuckPenalty);
+    }
+    done = st.plan_index[i] == st.path_length[i] - 1;   // robot.py:672: time-out only
+    reward_out[i] = (float)reward;
+    if (reward64) reward64[i] = reward;
+    done_out[i] = done ? 1 : 0;
   }
-  const int slot = (head + cnt) % kStuckSteps;        // append(state)
-  st.hist[(int64_t)(2 * slot) * n + i] = sx[i];
-  st.hist[(int64_t)(2 * slot + 1) * n + i] = sy[i];
-  st.hist_count[i] = cnt + 1;
-  st.hist_head[i] = head;
-  if (stuck) {
-    st.stuck_flag[i] = 1;
-    reward = __dsub_rn(reward, kStuckPenalty);
-  }
-  const bool done = st.plan_index[i] == st.path_length[i] - 1;   // robot.py:672: time-out only
-  reward_out[i] = (float)reward;
-  if (reward64) reward64[i] = reward;
-  done_out[i] = done ? 1 : 0;
-  if (ring.s) {                                       // memory.push  robot.py:675
-    const int64_t p = (ring.position + i) % ring.capacity;
-    ring.s[p] = make_float2(sx[i], sy[i]);
-    ring.a[p] = make_float2(ax[i], ay[i]);
-    ring.r[p] = (float)reward;
-    ring.s2[p] = make_float2(nx[i], ny[i]);
-    ring.notdone[p] = done ? 0.f : 1.f;
+  if (ring.s) {                                         // memory.push  robot.py:675
+    int64_t p;
+    if (type) {
+      // only some envs push: compact them with a warp ballot, one atomic per warp on the ring's row counter
+      const uint32_t act = __ballot_sync(0xffffffffu, live);
+      const int lane = threadIdx.x & 31;
+      unsigned long long base = 0;
+      if (lane == 0 && act) base = atomicAdd(ring.total, (unsigned long long)__popc(act));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      p = (int64_t)((base + __popc(act & ((1u << lane) - 1u))) % (unsigned long long)ring.capacity);
+    } else {
+      p = (ring.position + i) % ring.capacity;
+      if (i == 0 && ring.total) atomicAdd(ring.total, (unsigned long long)n);
+    }
+    if (live) {
+      ring.s[p] = make_float2(sx[i], sy[i]);
+      ring.a[p] = make_float2(ax[i], ay[i]);
+      ring.r[p] = (float)reward;
+      ring.s2[p] = make_float2(nx[i], ny[i]);
+      ring.notdone[p] = done ? 0.f : 1.f;
+    }
   }
 }
 
@@ -189,11 +213,12 @@ int32_t rtd3_robot_baseline(const float* x, const float* y, const double* goal, 
 }
 
 int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* goal, const float* residual, const double* unit_noise,
-                                  const double* noise_scale, float* ax, float* ay, double* action64, int64_t n, void* stream) {
+                                  const double* noise_scale, const int8_t* type, float* ax, float* ay, double* action64, int64_t n,
+                                  void* stream) {
   RTD3_CHECK_ARG(x && y && goal && residual && ax && ay && n >= 0, "bad argument");
   RTD3_CHECK_ARG(!unit_noise || noise_scale, "noise needs noise_scale");
   if (n == 0) return 0;
-  robot_compose_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, goal, residual, unit_noise, noise_scale, ax, ay, action64, n);
+  robot_compose_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, goal, residual, unit_noise, noise_scale, type, ax, ay, action64, n);
   RTD3_LAUNCHED();
   return 0;
 }
@@ -202,7 +227,8 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index, const int32_t* path_length,
                               const float* sx, const float* sy, const float* ax, const float* ay, const float* nx, const float* ny,
                               const double* demo, int64_t num_demo, float* reward, double* reward64, uint8_t* done, float* rp_s, float* rp_a,
-                              float* rp_r, float* rp_s2, float* rp_notdone, int64_t capacity, int64_t position, int64_t n, void* stream) {
+                              float* rp_r, float* rp_s2, float* rp_notdone, int64_t capacity, int64_t position, uint64_t* rp_total,
+                              const int8_t* type, int64_t n, void* stream) {
   RTD3_CHECK_ARG(goal && hist && hist_count && hist_head && goal_reached && stuck_flag && demo_flag && plan_index && path_length,
                  "null robot state");
   RTD3_CHECK_ARG(sx && sy && ax && ay && nx && ny && reward && done, "null transition array");
@@ -212,9 +238,10 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
                  "bad replay ring");
   if (n == 0) return 0;
   RobotState st{goal, hist, hist_count, hist_head, goal_reached, stuck_flag, demo_flag, plan_index, path_length};
-  ReplayRing ring{(float2*)rp_s, (float2*)rp_a, rp_r, (float2*)rp_s2, rp_notdone, capacity, position};
+  RTD3_CHECK_ARG(!(type && rp_s) || rp_total, "a masked push needs the ring's device row counter");
+  ReplayRing ring{(float2*)rp_s, (float2*)rp_a, rp_r, (float2*)rp_s2, rp_notdone, capacity, position, (unsigned long long*)rp_total};
   robot_transition_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(st, sx, sy, ax, ay, nx, ny, demo, num_demo, reward, reward64,
-                                                                                  done, ring, n);
+                                                                                  done, ring, type, n);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -134,9 +134,44 @@ sample_trace_kernel(const int32_t* __restrict__ J, int32_t n, int32_t batch, int
   }
 }
 
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator used for the non-parity index draw.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__global__ void sample_philox_kernel(uint64_t seed, uint64_t offset, uint32_t n, int64_t total, int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (4 * t >= total) return;
+  const uint64_t c = offset + (uint64_t)t;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (4 * t + k < total) out[4 * t + k] = (int32_t)__umulhi(v[k], n);   // multiply-shift map to [0, n)
+}
+
 }  // namespace rtd3
 
 using namespace rtd3;
+
+extern "C" int32_t rtd3_sample_indices_philox(uint64_t seed, uint64_t offset, int64_t n, int32_t batch, int32_t count, int32_t* out,
+                                              void* stream) {
+  RTD3_CHECK_ARG(out && n >= 1 && n < (1ll << 31) && batch >= 1 && count >= 0, "bad argument");
+  const int64_t total = (int64_t)batch * count;
+  if (total == 0) return 0;
+  sample_philox_kernel<<<(int)ceil_div(ceil_div(total, 4), 256), 256, 0, (cudaStream_t)stream>>>(seed, offset, (uint32_t)n, total, out);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
 
 extern "C" int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t stream_id, int32_t n, int32_t batch, int32_t count,
                                                int32_t* out, int32_t* scratch, void* stream) {

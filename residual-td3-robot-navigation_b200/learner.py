@@ -55,8 +55,14 @@ class ReplayBuffer:
         self.r = torch.zeros((c,), dtype=torch.float32, device=self.device)
         self.s2 = torch.zeros((c, 2), dtype=torch.float32, device=self.device)
         self.notdone = torch.ones((c,), dtype=torch.float32, device=self.device)
-        self.position = 0
-        self.size = 0
+        # rows ever pushed: host mirror + device counter (the device one is authoritative after masked pushes, see
+        # Robot.process_transition(types=...): the number of rows those add is only known on the device)
+        self._total_host = 0
+        self._total_dev = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._host_stale = False
+        self.sampler = "mt19937"      # "mt19937": numpy-exact index draws; "philox": throughput mode (with replacement)
+        self._philox_seed = 0x5eed if seed is None else int(seed)
+        self._philox_offset = 0
         # index draws come from numpy's global legacy stream (like the reference) unless a seed is given
         self._bank = MtBank(1, self.device)
         self._numpy_global = seed is None
@@ -64,12 +70,31 @@ class ReplayBuffer:
             self._bank.seed(seed)
         self._scratch = None
 
+    def _total(self):
+        if self._host_stale:
+            self._total_host = int(self._total_dev.item())
+            self._host_stale = False
+        return self._total_host
+
+    @property
+    def position(self):
+        return self._total() % self.capacity
+
+    @property
+    def size(self):
+        return min(self.capacity, self._total())
+
     def __len__(self):
         return self.size
 
-    def _advance(self, n):
-        self.position = (self.position + n) % self.capacity
-        self.size = min(self.capacity, self.size + n)
+    def _advance(self, n, device_counted=False):
+        """n rows were pushed at `position`; device_counted: the kernel already advanced the device counter."""
+        self._total_host = self._total() + n
+        if not device_counted:
+            self._total_dev += n
+
+    def _mark_device_advanced(self):
+        self._host_stale = True
 
     def push(self, state, action, reward, next_state, done):
         """One transition (numpy / python scalars, like the reference) or n transitions (`[n,2]` / `[n]` CUDA tensors)."""
@@ -99,6 +124,11 @@ class ReplayBuffer:
         if self.size < batch_size:
             return None
         out = torch.empty((count, batch_size), dtype=torch.int32, device=self.device)
+        if self.sampler == "philox":
+            _lib.check(_lib.lib().rtd3_sample_indices_philox(self._philox_seed, self._philox_offset, self.size, batch_size, count,
+                                                             _lib.ptr(out), _lib.stream_ptr(self.device)), "sample_indices_philox")
+            self._philox_offset += (count * batch_size + 3) // 4
+            return out
         need = count * self.size
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty((need,), dtype=torch.int32, device=self.device)

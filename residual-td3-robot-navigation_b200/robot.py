@@ -151,7 +151,7 @@ class Robot:
         self._path_length += PATH_INCREASE
 
     # ---- robot.py:541-642 ------------------------------------------------------------------------------------------
-    def _act(self, state, noise):
+    def _act(self, state, noise, types=None):
         n = self.num_envs
         sp = self._state_planes(state)
         L = _lib.lib()
@@ -159,7 +159,7 @@ class Robot:
         _lib.check(L.rtd3_robot_baseline(_lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(self._goal), _lib.ptr(self._base), n, sptr), "robot_baseline")
         residual = self.td3_agent.forward(NET_ACTOR, self._base)                  # residual_action, robot.py:598-624
         _lib.check(L.rtd3_robot_compose_action(_lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(self._goal), _lib.ptr(residual),
-                                               _lib.ptr(noise), _lib.ptr(self._noise_scale), _lib.ptr(self._action[0]),
+                                               _lib.ptr(noise), _lib.ptr(self._noise_scale), _lib.ptr(types), _lib.ptr(self._action[0]),
                                                _lib.ptr(self._action[1]), _lib.ptr(self._action64), n, sptr), "robot_compose_action")
         if self.batched:
             return self._action.t()
@@ -174,10 +174,12 @@ class Robot:
             self._bank.sync_to_numpy()
         return z
 
-    def get_next_action_training(self, state, money_remaining, noise=None):
-        """`noise`: optional injected unit normals `[2,N]` float64 (tests); default draws them from the MT19937 streams."""
+    def get_next_action_training(self, state, money_remaining, noise=None, types=None):
+        """`noise`: optional injected unit normals `[2,N]` float64 (tests / throughput mode); default draws them from the
+        MT19937 streams.  `types` (batched): the tensor get_next_action_type returned - envs that are not stepping in
+        this tick get a null action."""
         z = self.generate_noise() if noise is None else noise.to(self.device, torch.float64).contiguous()
-        return self._act(state, z)
+        return self._act(state, z, types)
 
     def get_next_action_testing(self, state):
         return self._act(state, None)
@@ -188,7 +190,7 @@ class Robot:
         return out if self.batched else out[0].cpu().numpy()
 
     # ---- robot.py:645-675 ------------------------------------------------------------------------------------------
-    def process_transition(self, state, action, next_state, money_remaining, push=True):
+    def process_transition(self, state, action, next_state, money_remaining, push=True, types=None):
         n = self.num_envs
         sp, ap, npl = self._state_planes(state), self._state_planes(action), self._state_planes(next_state)
         m = 0 if self._demo_dev is None else self._demo_dev.shape[0]
@@ -201,9 +203,13 @@ class Robot:
             _lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(ap[0]), _lib.ptr(ap[1]), _lib.ptr(npl[0]), _lib.ptr(npl[1]),
             _lib.ptr(self._demo_dev), m, _lib.ptr(self._reward), _lib.ptr(self._reward64), _lib.ptr(self._done),
             _lib.ptr(rb.s if push else None), _lib.ptr(rb.a), _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), rb.capacity,
-            rb.position, n, _lib.stream_ptr(self.device)), "robot_transition")
+            0 if types is not None else rb.position, _lib.ptr(rb._total_dev), _lib.ptr(types), n, _lib.stream_ptr(self.device)),
+            "robot_transition")
         if push:
-            rb._advance(n)
+            if types is None:
+                rb._advance(n, device_counted=True)
+            else:
+                rb._mark_device_advanced()              # how many envs stepped is only known on the device
 
     # ---- robot.py:727-762 (host form, used by process_demonstration; the per-step form lives in the transition kernel) ----
     def compute_reward(self, path):

@@ -1,0 +1,61 @@
+"""Batched restatement of the training branch of the reference's `update(dt)` (robot-learning.py:66-101), plus the
+env-range sharding used for multi-GPU runs.
+
+One tick = what the reference does for one env per call of `update`, applied to all N envs of this rank:
+    types = robot.get_next_action_type(state, money)          robot-learning.py:68   (runs td3_update when an episode ended)
+    type 'reset' -> state = environment.reset()               robot-learning.py:82-85
+    type 'step'  -> action = robot.get_next_action_training(state); next = environment.step(action);
+                    robot.process_transition(state, action, next); state = next     robot-learning.py:95-101
+    type 'demo'  -> batched mode has no per-env planner call yet: the tick is a no-op for that env (demonstration
+                    states are installed up front with Robot.set_demonstration_states)
+Money accounting keeps the reference's counters per env (demos / resets / steps bought); the wall-clock term
+(robot-learning.py:47) is replaced by a fixed per-tick charge so that runs are deterministic.
+"""
+import torch
+
+from . import constants
+
+
+def shard_range(num_envs, rank, world):
+    """Contiguous env-index range of `rank`: envs are independent, so sharding is a partition with no data-path collective."""
+    if num_envs % world != 0:
+        raise ValueError("num_envs must divide evenly over the ranks (equal shards keep mean-of-means == global mean)")
+    per = num_envs // world
+    return rank * per, (rank + 1) * per
+
+
+class BatchedTrainer:
+    def __init__(self, environment, robot, noise="mt19937"):
+        if environment.num_envs != robot.num_envs:
+            raise ValueError("environment and robot must hold the same envs")
+        self.env, self.robot = environment, robot
+        self.n = environment.num_envs
+        self.device = environment.device
+        self.env.reset()
+        self.noise = noise                    # "mt19937": per-env numpy-legacy streams; "randn": torch's Philox (throughput mode)
+        self.steps_bought = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        self.resets_bought = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+        self.ticks = 0
+        self._prev = torch.empty((2, self.n), dtype=torch.float32, device=self.device)
+
+    def money_remaining(self, tick_charge=0.0):
+        c = constants
+        return (c.STARTING_MONEY - self.resets_bought * c.COST_PER_RESET - self.steps_bought * c.COST_PER_STEP - self.ticks * tick_charge)
+
+    def tick(self):
+        env, robot = self.env, self.robot
+        types = robot.get_next_action_type(None, None)                        # int8 [N]; td3_update inside when due
+        stepping = types == 0
+        z = None
+        if self.noise == "randn":
+            z = torch.randn((2, self.n), dtype=torch.float64, device=self.device)
+        self._prev.copy_(env._state)
+        state = self._prev.t()
+        action = robot.get_next_action_training(state, None, noise=z, types=types)
+        next_state = env.step(action)                                         # null action where the env is not stepping
+        robot.process_transition(state, action, next_state, None, types=types)
+        env.reset(mask=types == 2)
+        self.steps_bought += stepping
+        self.resets_bought += (types == 2)
+        self.ticks += 1
+        return types

@@ -156,3 +156,44 @@ def test_demonstration_pipeline_single_env(pkg, env_golden):
     assert len(robot.paths_to_draw) == 4
     assert not robot.goal_reached
     assert (env.robot_state == state.astype(np.float32).astype(np.float64)).all()   # planning did not move the robot
+
+
+def test_batched_trainer_loop_and_masked_push(pkg, env_golden):
+    """The lock-step loop of robot-learning.py:66-101 over 300 envs: per-env counters follow the reference's state machine,
+    only stepping envs push replay rows, and an update runs when episodes end."""
+    g = env_golden
+    n = 300
+    env = pkg.Environment(num_envs=n, seed=21, maps=(g["speed"], g["angle"]))
+    robot = pkg.Robot(env.goal_state, hidden=64, layers=2, seed=3, buffer_size=40000)
+    robot.td3_agent.num_epochs = 4
+    robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (300, 2)))
+    tr = pkg.BatchedTrainer(env, robot)
+    orcs = [RobotOracle(np.zeros(2)) for _ in range(3)]
+    pushed = 0
+    for t in range(60):
+        types = tr.tick().cpu().numpy()
+        pushed += int((types == 0).sum())
+        assert len(robot.memory) == min(pushed, robot.memory.capacity)
+    # first four ticks: demo, demo, demo, reset for every env (SURVEY a-11), then stepping
+    assert pushed > 0 and robot.num_updates >= 1
+    assert int(tr.resets_bought.min()) >= 2                 # the leaving-demo reset and the first time-out (path length 50)
+    st = env.robot_state
+    assert float(st.min()) >= 0 and float(st.max()) < 100
+    rows = robot.memory.s[:len(robot.memory)]
+    assert torch.isfinite(rows).all() and torch.isfinite(robot.memory.r[:len(robot.memory)]).all()
+    assert torch.isfinite(robot.td3_agent.params).all()
+
+
+def test_philox_sampler_range_and_determinism(pkg):
+    rb = pkg.ReplayBuffer(100000, seed=9)
+    k = torch.arange(70000, dtype=torch.float32, device="cuda")
+    rb.push(torch.stack([k, k], 1), torch.stack([k, k], 1), k, torch.stack([k, k], 1), torch.zeros(70000, dtype=torch.bool, device="cuda"))
+    rb.sampler = "philox"
+    a = rb.sample_indices(8192, 6)
+    assert a.shape == (6, 8192) and int(a.min()) >= 0 and int(a.max()) < 70000
+    assert float(a.float().mean()) == pytest.approx(35000, rel=0.02)
+    rb2 = pkg.ReplayBuffer(100000, seed=9)
+    rb2.push(torch.stack([k, k], 1), torch.stack([k, k], 1), k, torch.stack([k, k], 1), torch.zeros(70000, dtype=torch.bool, device="cuda"))
+    rb2.sampler = "philox"
+    assert torch.equal(a, rb2.sample_indices(8192, 6))
+    assert not torch.equal(a, rb.sample_indices(8192, 6))   # the counter advances
