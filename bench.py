@@ -153,6 +153,131 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------ TD3 legs
+TD3_SHAPES = [  # (label, batch, hidden, layers, epochs): configs[2] benchmark shape, the reference's own shape, configs[4] large batch
+    ("B256_2x256", 256, 256, 2, 100),
+    ("B100_3x200_reference_shape", 100, 200, 3, 100),
+    ("B8192_2x256", 8192, 256, 2, 20),
+]
+FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+
+
+def td3_flops_per_epoch(B, H, L):
+    """Algorithmic FLOPs (2*MAC) of one epoch = critic step + 1/2 actor step (fwd + bwd incl. targets)."""
+    actor = 2 * H + (L - 1) * H * H + H * 2
+    critic = 4 * H + (L - 1) * H * H + H * 1
+    critic_step = actor + 2 * critic + 2 * 3 * critic          # target actor, 2 target critics, 2 x (fwd + bwd(dX + dW))
+    actor_step = 3 * actor + critic + critic                   # actor fwd + bwd(dX+dW), critic-1 fwd, critic-1 bwd (dX only)
+    return 2.0 * B * (critic_step + 0.5 * actor_step)
+
+
+def cpu_td3_epochs_per_sec(B, H, L, epochs):
+    """The oracle port (numpy float32, BLAS threads as configured) of TD3.td3_update on a synthetic replay."""
+    from oracle import td3_oracle as to
+    rs = np.random.RandomState(0)
+    w = [to.kaiming_uniform_params(rs, 2, H, L, 2), to.kaiming_uniform_params(rs, 4, H, L, 1), to.kaiming_uniform_params(rs, 4, H, L, 1)]
+    orc = to.TD3Oracle(w[0], w[1], w[2], hidden=H, layers=L)
+    n = 10000
+    rb = to.ReplayOracle(n)
+    rb.s[:] = rs.uniform(0, 98.9999, (n, 2)); rb.a[:] = rs.uniform(-5, 5, (n, 2)); rb.s2[:] = np.clip(rb.s + rb.a, 0, 98.9999)
+    rb.r[:] = -np.linalg.norm(rb.s2 - np.array([80, 20], np.float32), axis=1); rb.size = n
+    # index draws through numpy's own C implementation of the legacy shuffle, as the reference does (robot.py:111)
+    t0 = time.perf_counter()
+    for e in range(epochs):
+        idx = rs.choice(n, B, replace=False) if B <= n else rs.randint(0, n, B)
+        orc.train_critic(*rb.gather(idx), rs.normal(size=(B, 2)).astype(np.float32))
+        if e % 2 == 0:
+            idx = rs.choice(n, B, replace=False) if B <= n else rs.randint(0, n, B)
+            orc.train_actor(rb.gather(idx)[0])
+            orc.polyak_all()
+    return epochs / (time.perf_counter() - t0)
+
+
+def bench_td3(rt, torch, dev, world, rank, cpu):
+    import torch.distributed as dist
+    out = []
+    pg = dist.group.WORLD if world > 1 else None
+    for label, B, H, L, epochs in TD3_SHAPES:
+        torch.manual_seed(0)
+        agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L),
+                       batch_size=B, num_epochs=epochs, device=dev, process_group=pg)
+        n = 10000
+        rb = rt.ReplayBuffer(n, device=dev, seed=rank)
+        g = torch.Generator(device=dev).manual_seed(rank)
+        s = torch.rand((n, 2), device=dev, generator=g) * 98.9999
+        a = torch.rand((n, 2), device=dev, generator=g) * 10 - 5
+        s2 = (s + a).clamp(0, 98.9999)
+        r = -torch.linalg.norm(s2 - torch.tensor([80., 20.], device=dev), dim=1)
+        rb.push(s, a, r, s2, (torch.arange(n, device=dev) % 50) == 49)
+        if B > n:
+            rb.sampler = "philox"                         # with replacement: the exact sampler needs batch <= rows
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reps, ms_s, ms_u = 4, [], []
+        for rep in range(reps):                           # rep 0 captures the graph / warms up
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            ev[0].record()
+            idx = rb.sample_indices(B, epochs + (epochs + 1) // 2)
+            ev[1].record()
+            agent.td3_update(rb, idx=idx)
+            ev[2].record()
+            torch.cuda.synchronize(dev)
+            if rep > 0:
+                ms_s.append(ev[0].elapsed_time(ev[1])); ms_u.append(ev[1].elapsed_time(ev[2]))
+        t = torch.tensor([float(np.median(ms_s)), float(np.median(ms_u))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_sample, ms_update = float(t[0]), float(t[1])
+        flops = td3_flops_per_epoch(B * world, H, L) * epochs
+        row = {"shape": label, "global_batch": B * world, "epochs": epochs, "sampler": rb.sampler,
+               "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
+               "updates_per_sec": epochs / ((ms_update + ms_sample) * 1e-3), "updates_per_sec_update_only": epochs / (ms_update * 1e-3),
+               "tflops_fp32": flops / (ms_update * 1e-3) / 1e12,
+               "frac_of_nominal_fp32_peak": flops / (ms_update * 1e-3) / 1e12 / (FP32_FFMA_PEAK_TFLOPS * world)}
+        if cpu and rank == 0 and world == 1:
+            e_cpu = 40 if B <= 256 else 4
+            row["cpu_port_updates_per_sec"] = cpu_td3_epochs_per_sec(B, H, L, e_cpu)
+        out.append(row)
+        del agent, rb
+    return out
+
+
+def bench_full_loop(rt, torch, dev, world, rank):
+    """configs[3]: the act -> step -> transition -> (episode end: TD3 update) loop, 8192 envs per GPU, gradients all-reduced."""
+    import torch.distributed as dist
+    pg = dist.group.WORLD if world > 1 else None
+    n = 8192
+    env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
+    robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=50000)
+    robot.td3_agent.batch_size = 256
+    robot.td3_agent.num_epochs = 20
+    robot.memory.sampler = "philox"
+    robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
+    tr = rt.BatchedTrainer(env, robot, noise="randn")
+    for _ in range(8):
+        tr.tick()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ticks, upd0, steps0 = 120, robot.num_updates, int(tr.steps_bought.sum())
+    e0.record()
+    for _ in range(ticks):
+        tr.tick()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    st = torch.tensor([float(int(tr.steps_bought.sum()) - steps0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st)
+    ms = float(t[0])
+    return {"envs_total": n * world, "ticks": ticks, "ms_per_tick": ms / ticks, "env_steps_per_sec": float(st[0]) / (ms * 1e-3),
+            "td3_updates_in_window": (robot.num_updates - upd0), "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
+            "note": "host-driven tick loop (5 launches + 1 flag read per tick); exploration noise torch.randn, replay sampling philox"}
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -270,6 +395,8 @@ def run_b200(args):
                               "env_steps_per_sec": big / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
             del bx, ba
         extra["step_kernel_sweep"] = sweep
+    td3_rows = None if args.no_td3 else bench_td3(rt, torch, dev, world, rank, cpu=not args.no_cpu)
+    loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
     sampler.in_region = False
     sampler.stop()
 
@@ -310,6 +437,10 @@ def run_b200(args):
             "clocks": sampler.summary(),
         }
         line.update(extra)
+        if td3_rows is not None:
+            line["td3"] = td3_rows
+        if loop_row is not None:
+            line["full_loop"] = loop_row
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -325,6 +456,8 @@ def main():
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-td3", action="store_true")
+    ap.add_argument("--no-loop", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

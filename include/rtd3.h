@@ -40,6 +40,8 @@ const char* rtd3_last_error(void);
 /* Number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches). */
 int64_t rtd3_launch_count(void);
 void rtd3_launch_count_reset(void);
+/* Replaying a captured CUDA graph launches kernels without passing through the library: the owner of the graph adds them here. */
+void rtd3_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Environment: dynamics / step / rollout        (environment.py:98-127)

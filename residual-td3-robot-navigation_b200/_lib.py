@@ -27,6 +27,7 @@ _SIGNATURES = {
     "rtd3_last_error": (c_char_p, []),
     "rtd3_launch_count": (c_int64, []),
     "rtd3_launch_count_reset": (None, []),
+    "rtd3_launch_count_add": (None, [c_int64]),
     "rtd3_env_create": (c_int32, [POINTER(c_void_p), c_int32]),
     "rtd3_env_destroy": (c_int32, [_P]),
     "rtd3_env_set_map": (c_int32, [_P, _P, _P, _P]),

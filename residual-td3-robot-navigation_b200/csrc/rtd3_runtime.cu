@@ -23,4 +23,5 @@ int32_t rtd3_version(void) { return RTD3_VERSION; }
 const char* rtd3_last_error(void) { return rtd3::g_err; }
 int64_t rtd3_launch_count(void) { return rtd3::g_launches.load(); }
 void rtd3_launch_count_reset(void) { rtd3::g_launches.store(0); }
+void rtd3_launch_count_add(int64_t n) { rtd3::g_launches.fetch_add(n); }
 }

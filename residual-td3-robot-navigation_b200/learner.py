@@ -347,8 +347,8 @@ class TD3:
     # ---- the three device steps -------------------------------------------------------------------------
     def _allreduce(self):
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.grads, group=self.process_group)
+            from .trainer import allreduce_grads_
+            allreduce_grads_(self.grads, self.process_group)
 
     def _row_scratch(self, B):
         need = int(_lib.lib().rtd3_td3_scratch_floats(self._handle, B))
@@ -460,15 +460,20 @@ class TD3:
             st["noise"].normal_()                                     # torch.randn_like, robot.py:338 (unseeded there)
         else:
             st["noise"].copy_(noise)
-        if use_graph:
+        # NCCL collectives are issued eagerly between the kernels: the data-parallel loop is not graph-captured
+        if use_graph and self.world == 1:
             if st["graph"] is None:
                 graph = torch.cuda.CUDAGraph()
+                before = _lib.launch_count()
                 with torch.cuda.graph(graph):
                     st["closs"].zero_()
                     st["aloss"].zero_()
                     self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
                 st["graph"] = graph
+                st["launches"] = _lib.launch_count() - before      # kernels inside the graph (capture itself ran none)
+                _lib.lib().rtd3_launch_count_add(-st["launches"])
             st["graph"].replay()
+            _lib.lib().rtd3_launch_count_add(st["launches"])
         else:
             st["closs"].zero_()
             st["aloss"].zero_()

@@ -24,6 +24,18 @@ def shard_range(num_envs, rank, world):
     return rank * per, (rank + 1) * per
 
 
+def allreduce_grads_(flat_grads, group=None):
+    """The one collective of the data-parallel learner: SUM all-reduce of the flat gradient buffer over the ranks
+    (NCCL over NVLink on the GPUs; the optimiser kernel then applies the 1/world scale).  Returns the world size."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return world
+
+
 class BatchedTrainer:
     def __init__(self, environment, robot, noise="mt19937"):
         if environment.num_envs != robot.num_envs:
