@@ -280,6 +280,20 @@ def bench_full_loop(rt, torch, dev, world, rank):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
+    # ---- CPU baseline (rank 0, N=1 only): scalar oracle port on all host cores, bounded sample
+    cpu = None
+    if int(os.environ.get("RANK", "0")) == 0 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            cpu_env_steps(procs * 4, 8, procs, pool)                                   # warm the workers
+            t_sample = 200                                                             # ~13 core-seconds of the reference loop
+            v_all, wall, total = cpu_env_steps(ENVS, t_sample, procs, pool)
+        v_one, _, _ = cpu_env_steps(64, 16, 1, None)
+        cpu = {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
+               "sample": "%d envs x %d steps (%.1f s wall) of the rollout, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
+                         % (ENVS, t_sample, wall, procs, v_one)}
+
     import torch
     import torch.distributed as dist
     import rtd3_b200 as rt
@@ -399,20 +413,6 @@ def run_b200(args):
     loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
     sampler.in_region = False
     sampler.stop()
-
-    # ---- CPU baseline (rank 0, N=1 only): scalar oracle port on all host cores, bounded sample
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        procs = os.cpu_count() or 1
-        ctx = mp.get_context("fork")
-        with ctx.Pool(procs) as pool:
-            cpu_env_steps(procs * 4, 8, procs, pool)                                   # warm the workers
-            t_sample = 16
-            v_all, wall, total = cpu_env_steps(ENVS, t_sample, procs, pool)
-        v_one, _, _ = cpu_env_steps(64, 16, 1, None)
-        cpu = {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
-               "sample": "%d envs x %d steps (%.1f s wall) of the rollout, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
-                         % (ENVS, t_sample, wall, procs, v_one)}
 
     if rank == 0:
         us_per_launch = ms * 1e3 / args.steps

@@ -227,7 +227,7 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
 
 /* Robot.get_next_action_type + Robot.reset (robot.py:443-506) for n envs.  type_out int8 [n]: 0 'step',
  * 1 'demo', 2 'reset'; update_out uint8 [n] marks envs whose episode ended (where the reference calls
- * td3_update, robot.py:480-483); any_update int32 [1] (zeroed by the caller) is set if any env did. */
+ * td3_update, robot.py:480-483); any_update int32 [1] (zeroed by the caller) receives how many envs did. */
 int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, int32_t* plan_index, int32_t* path_length,
                                     uint8_t* goal_reached, uint8_t* stuck_flag, double* noise_scale, int8_t* type_out,
                                     uint8_t* update_out, int32_t* any_update, int64_t n, void* stream);

@@ -165,7 +165,7 @@ robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float
 }
 
 // get_next_action_type + reset  (robot.py:443-506).  type: 0 'step', 1 'demo', 2 'reset'; update[i] = 1 where the
-// reference would call td3_update (robot.py:480-483).
+// reference would call td3_update (robot.py:480-483); any_update accumulates how many envs did.
 __global__ void robot_action_type_kernel(int32_t* __restrict__ num_episodes, uint8_t* __restrict__ demo_flag, int32_t* __restrict__ plan_index,
                                          int32_t* __restrict__ path_length, uint8_t* __restrict__ goal_reached, uint8_t* __restrict__ stuck_flag,
                                          double* __restrict__ noise_scale, int8_t* __restrict__ type_out, uint8_t* __restrict__ update_out,
@@ -195,7 +195,8 @@ __global__ void robot_action_type_kernel(int32_t* __restrict__ num_episodes, uin
     type_out[i] = (int8_t)type;
     update_out[i] = upd ? 1 : 0;
   }
-  if (__any_sync(0xffffffffu, upd) && (threadIdx.x & 31) == 0) atomicOr(any_update, 1);   // one flag per warp that needs it
+  const uint32_t ended = __ballot_sync(0xffffffffu, upd);                                   // warp-ballot of the episode-end flags
+  if (ended && (threadIdx.x & 31) == 0) atomicAdd(any_update, __popc(ended));               // one atomic per warp that needs it
 }
 
 }  // namespace rtd3

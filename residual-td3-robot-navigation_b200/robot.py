@@ -8,8 +8,8 @@ Call surface kept from the reference:
 `Robot(goal_state)` with a numpy `[2]` goal is the single-env drop-in: numpy in / numpy out, exploration noise and
 replay indices drawn from numpy's global legacy stream exactly where the reference draws them.  `Robot(goal_state)`
 with a CUDA `[N,2]` goal tensor is the batched form: one shared replay ring and one TD3 agent serve N envs, calls
-take / return CUDA tensors, `get_next_action_type` returns an int8 tensor (0 step, 1 demo, 2 reset) and runs ONE
-`td3_update` when any env finished an episode (the reference has no multi-env semantics to copy here).
+take / return CUDA tensors, `get_next_action_type` returns an int8 tensor (0 step, 1 demo, 2 reset) and runs one
+`td3_update` per `episodes_per_update` finished env-episodes (default N; the reference has no multi-env semantics to copy).
 """
 import numpy as np
 import torch
@@ -108,6 +108,11 @@ class Robot:
         self.td3_agent = TD3(actor_network=Residual_Actor_Network(**kw), critic_network_1=Residual_Critic_Network(**kw),
                              critic_network_2=Residual_Critic_Network(**kw), device=dev, process_group=process_group)
         self.num_updates = 0
+        # One shared learner serves all envs: an update runs once `episodes_per_update` env-episodes have ended since the last
+        # one.  The default N keeps the reference's rhythm (every env finishes about one episode between updates) and is
+        # exactly the reference for the single-env drop-in (robot.py:480-483).
+        self.episodes_per_update = self.num_envs
+        self._episodes_since_update = 0
 
     # ---- reference attributes (single-env views of the device state) --------------------------------------------
     def _scalar(self, t):
@@ -134,7 +139,9 @@ class Robot:
             _lib.ptr(self._num_episodes), _lib.ptr(self._demo_flag), _lib.ptr(self._plan_index), _lib.ptr(self._path_length),
             _lib.ptr(self._goal_reached), _lib.ptr(self._stuck_flag), _lib.ptr(self._noise_scale), _lib.ptr(self._type),
             _lib.ptr(self._update), _lib.ptr(self._any_update), n, _lib.stream_ptr(self.device)), "robot_next_action_type")
-        if int(self._any_update.item()):                        # robot.py:480-483: reset() then td3_update(memory)
+        self._episodes_since_update += int(self._any_update.item())
+        if self._episodes_since_update >= self.episodes_per_update:   # robot.py:480-483: reset() then td3_update(memory)
+            self._episodes_since_update = 0
             self.td3_agent.td3_update(self.memory)
             self.num_updates += 1
         if self.batched:
