@@ -1,5 +1,7 @@
 // Environment hot path: dynamics / step / T-step rollout / seeded init + reset.
 // Reference behaviour: /root/reference/environment.py:28-56, 98-137 (see include/rtd3.h per entry point).
+#include <cuda.h>
+
 #include "rtd3_common.cuh"
 #include "rtd3_mt.cuh"
 
@@ -263,6 +265,121 @@ env_rollout_kernel(const float2* __restrict__ g_table, float* __restrict__ x, fl
   y[i] = sy;
 }
 
+// ---- T-step rollout, TMA variant (n % 4 == 0): one warp = 32 envs = one independent pipeline -------------------------
+// Actions [T][2][n] and trajectories are 2-D tensors (inner dim n, outer dim 2T) described by CUtensorMaps; a warp moves
+// its [kU steps x 2][32 envs] tile (32 rows of 128 B) with ONE cp.async.bulk.tensor.2d (SASS UTMALDG / UTMASTG) per
+// chunk and direction: loads complete on a per-stage mbarrier, stores are tracked by the bulk async-group.  This removes
+// the per-step LDGSTS/STG and their 64-bit address arithmetic from the single warp that has to issue everything
+// (ncu r1: 47 instr/step at IPC 0.38 bounded the cp.async version; 32 row-wise 128 B bulk copies per chunk were tried
+// first and were 2.6x SLOWER - the TMA unit is op-bound, not byte-bound, at that size).  Out-of-range rows / envs of
+// edge tiles are zero-filled on load and clipped on store by the TMA unit itself.
+constexpr int kTileFloats = kU * 2 * 32;          // 1024 floats = 4 KB per warp per stage
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+template <bool kTraj, int kStages>
+__global__ void __launch_bounds__(256)
+env_rollout_tma_kernel(const float2* __restrict__ g_table, float* __restrict__ x, float* __restrict__ y,
+                       const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_traj, int64_t n, int64_t T) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_table = reinterpret_cast<float2*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes);            // table barrier
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes + 16) + warp * kStages;     // [nwarps][kStages]
+  // tiles start on a 128 B boundary behind the barriers
+  float* tiles = reinterpret_cast<float*>(smem_raw + ((kTableBytes + 16 + nwarps * kStages * 8 + 127) & ~127u));
+  float* my_in = tiles + (size_t)warp * kStages * kTileFloats;                                     // action ring of this warp
+  float* my_out = tiles + (size_t)nwarps * kStages * kTileFloats + (size_t)warp * 2 * kTileFloats; // 2 trajectory staging tiles
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+    fence_mbar_init();
+  }
+  stage_table(s_table, bar, g_table);   // init + fence + __syncthreads, then the table's bulk copies
+
+  const int64_t i0 = ((int64_t)blockIdx.x * nwarps + warp) * 32;                  // first env of this warp
+  if (i0 >= n) return;
+  const int64_t i = i0 + lane;
+  const bool live = i < n;
+  float sx = live ? fminf(fmaxf(x[i], 0.0f), 99.99999f) : 0.0f;
+  float sy = live ? fminf(fmaxf(y[i], 0.0f), 99.99999f) : 0.0f;
+  const uint32_t addr_bias = smem_u32(s_table) - 0x4B000000u * 808u;
+  const int64_t chunks = (T + kU - 1) / kU;
+
+  auto issue_chunk = [&](int64_t c) {
+    if (c < chunks && lane == 0) {
+      const int s = (int)(c % kStages);
+      mbar_arrive_expect_tx(full + s, kTileFloats * 4);
+      tma_load_2d(my_in + s * kTileFloats, &tm_act, (int)i0, (int)(c * (2 * kU)), full + s);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kStages; ++s) issue_chunk(s);
+  mbar_wait(bar, 0);
+
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int s = (int)(c % kStages);
+    mbar_wait(full + s, (uint32_t)((c / kStages) & 1));
+    float cax[kU], cay[kU];
+    float nanacc = 0.0f;
+    const float* tin = my_in + s * kTileFloats + lane;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      cax[u] = tin[(2 * u) * 32];
+      cay[u] = tin[(2 * u + 1) * 32];
+      nanacc = fmaf(cax[u], 0.0f, nanacc);      // stays 0 unless an action is NaN or inf
+      nanacc = fmaf(cay[u], 0.0f, nanacc);
+    }
+    __syncwarp();                               // every lane holds its values: the slot can be refilled
+    issue_chunk(c + kStages);
+    float* tout = my_out + (c & 1) * kTileFloats + lane;
+    if (kTraj && lane == 0) bulk_wait_read<1>();   // the staging tile used two chunks ago has been read by its store
+    __syncwarp();
+    const int steps = (int)min((int64_t)kU, T - c * kU);
+    const bool careful = __any_sync(0xffffffffu, nanacc != 0.0f) || steps < kU;
+    if (!careful) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        StepIn in;
+        in.ax = fminf(fmaxf(cax[u], -kMaxAction), kMaxAction);
+        in.ay = fminf(fmaxf(cay[u], -kMaxAction), kMaxAction);
+        in.lo = 0.0f; in.hi = kClipHi; in.bad = false;
+        rollout_step(addr_bias, in, sx, sy);
+        if (kTraj) { tout[(2 * u) * 32] = sx; tout[(2 * u + 1) * 32] = sy; }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (u < steps) {
+          const StepIn in = prep_action(cax[u], cay[u]);
+          rollout_step(addr_bias, in, sx, sy);
+        }
+        if (kTraj) { tout[(2 * u) * 32] = sx; tout[(2 * u + 1) * 32] = sy; }
+      }
+    }
+    if (kTraj) {
+      fence_proxy_async();                      // generic-proxy writes of the tile -> visible to the TMA (async proxy) read
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_traj, (int)i0, (int)(c * (2 * kU)), my_out + (c & 1) * kTileFloats);
+        bulk_commit();
+      }
+    }
+  }
+  if (live) { x[i] = sx; y[i] = sy; }
+  if (kTraj && lane == 0) bulk_wait<0>();       // the stores must have left shared memory before the CTA exits
+}
+
 // ---- seeded init / reset on per-env legacy MT19937 streams ------------------------------------
 __global__ void mt_seed_kernel(rtd3_mt_bank b, const uint32_t* __restrict__ seeds) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,7 +463,40 @@ static int32_t check_bank(const rtd3_mt_bank* b) {
 
 using namespace rtd3;
 
+static bool g_force_plain_rollout = false;
+
+// cuTensorMapEncodeTiled comes from the driver (libcuda); it is looked up at run time so that librtd3.so links against
+// the runtime only.  If the lookup fails the rollout falls back to the cp.async kernel.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+static void load_encode_tiled() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    g_encode_tiled = (EncodeTiledFn)fn;
+}
+
+// [T][2][n] float32 planes as a 2-D tensor: inner dim n, outer dim 2T, box = 32 envs x 2*kU rows
+static int32_t make_plane_map(CUtensorMap* tm, const float* base, int64_t n, int64_t T) {
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)(2 * T)};
+  const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
+  const cuuint32_t box[2] = {32, 2 * kU};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rtd3::set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RTD3_ERR_STATE;
+  }
+  return 0;
+}   // test hook: exercise the cp.async variant on aligned sizes too
+
 extern "C" {
+
+void rtd3_env_force_plain_rollout(int32_t on) { g_force_plain_rollout = on != 0; }
 
 int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   RTD3_CHECK_ARG(out, "out is null");
@@ -359,14 +509,19 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   h->table = nullptr;
   RTD3_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   RTD3_CUDA(cudaMalloc(&h->table, kTableBytes));
+  if (!g_encode_tiled) load_encode_tiled();
   const int smem = kTableBytes + 16;
   RTD3_CUDA(cudaFuncSetAttribute(env_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   RTD3_CUDA(cudaFuncSetAttribute(env_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int smem_roll = 200 * 1024;
+  const int smem_roll = 227 * 1024;
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;
@@ -440,6 +595,26 @@ int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, 
   const int stages = deep ? kDeep : kShallow;
   const int smem = kTableBytes + 16 + stages * kU * 2 * block * 4;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tma_ok = (n % 4 == 0) && (n < (1ll << 31)) && (2 * T < (1ll << 31)) && ((uintptr_t)actions % 16 == 0) &&
+                      (!traj || (uintptr_t)traj % 16 == 0) && !g_force_plain_rollout && g_encode_tiled;
+  CUtensorMap tm_act, tm_traj;
+  // an encode failure (unexpected shape limits) is not an error: the cp.async kernel below handles every shape
+  if (tma_ok && make_plane_map(&tm_act, actions, n, T) == 0 && make_plane_map(&tm_traj, traj ? traj : actions, n, T) == 0) {
+    // one warp per 32 envs; few warps per CTA while the batch cannot fill the SMs, 8 once it can
+    const int64_t warps_total = ceil_div(n, 32);
+    const int wpc = deep ? (int)std::max<int64_t>(1, std::min<int64_t>(8, ceil_div(warps_total, (int64_t)h->num_sms))) : 8;
+    const int bgrid = (int)ceil_div(warps_total, wpc);
+    const int bsmem = ((kTableBytes + 16 + wpc * stages * 8 + 127) & ~127) + wpc * (stages + 2) * kTileFloats * 4;
+    if (deep) {
+      if (traj) env_rollout_tma_kernel<true, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+      else env_rollout_tma_kernel<false, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+    } else {
+      if (traj) env_rollout_tma_kernel<true, kShallow><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+      else env_rollout_tma_kernel<false, kShallow><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+    }
+    RTD3_LAUNCHED();
+    return 0;
+  }
   if (deep) {
     if (traj) env_rollout_kernel<true, kDeep><<<grid, block, smem, st>>>(h->table, x, y, actions, traj, n, T);
     else env_rollout_kernel<false, kDeep><<<grid, block, smem, st>>>(h->table, x, y, actions, nullptr, n, T);

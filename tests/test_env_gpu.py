@@ -164,16 +164,36 @@ def test_rollout_teacher_forced_vs_golden_trajectory(pkg, env_golden):
         assert_state_close(out, ref)
 
 
-@pytest.mark.parametrize("n,T", [(8, 32), (4096, 50), (1000, 17), (70000, 33)])
-def test_rollout_equals_repeated_steps(pkg, env_golden, n, T):
+@pytest.mark.parametrize("plain", [False, True])
+@pytest.mark.parametrize("n,T", [(8, 32), (4096, 50), (1000, 17), (70000, 33), (65536, 40), (4096, 1000), (32, 16), (64, 15)])
+def test_rollout_equals_repeated_steps(pkg, env_golden, n, T, plain):
+    """Both rollout kernels (bulk-async tiles for n % 32 == 0, per-thread cp.async otherwise / when forced)."""
     g = env_golden
+    if T == 1000 and plain:
+        pytest.skip("long case once")
+    pkg._lib.lib().rtd3_env_force_plain_rollout(1 if plain else 0)
+    try:
+        _rollout_vs_steps(pkg, g, n, T)
+    finally:
+        pkg._lib.lib().rtd3_env_force_plain_rollout(0)
+
+
+def _rollout_vs_steps(pkg, g, n, T):
     env_a = pkg.Environment(num_envs=n, seed=3, maps=(g["speed"], g["angle"]))
     env_b = pkg.Environment(num_envs=n, seed=3, maps=(g["speed"], g["angle"]))
     env_a.reset(); env_b.reset()
     gen = torch.Generator(device="cuda").manual_seed(0)
     planes = (torch.rand((T, 2, n), device="cuda", generator=gen) * 15 - 7.5)
+    if T >= 17:                                            # NaN / inf actions inside a chunk: the careful path
+        planes[5, 0, n // 2] = float("nan")
+        planes[16, 1, 0] = float("inf")
+        planes[3, 1, n - 1] = float("nan")
     traj = env_a.rollout(planes.permute(0, 2, 1))
+    step_every = 1 if T <= 60 else 37
     for t in range(T):
+        if T > 60 and t % step_every != 0:
+            env_b.step(planes[t].t())
+            continue
         st = env_b.step(planes[t].t())
         assert torch.equal(traj[t], st), t               # same kernel arithmetic: bit-identical
     assert torch.equal(env_a.robot_state, env_b.robot_state)
