@@ -168,7 +168,11 @@ int64_t rtd3_td3_scratch_floats(const rtd3_td3* h, int32_t batch);
  * rtd3_td3_adam_polyak re-zeroes what it consumes).
  * q_out (nullable) [2][batch] receives Q1,Q2(s,a) before the update, y_out (nullable) [batch] the targets.
  * Increments steps[1]. */
-int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s,
+/* params_t: a second arena of the same size holding the hidden-layer weights transposed ([in][out], what the forward
+ * kernels read).  rtd3_td3_adam_polyak keeps it in step; call this after writing weights into `params` directly. */
+int32_t rtd3_td3_sync_transposed(rtd3_td3* h, const float* params, float* params_t, void* stream);
+
+int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
                              const float* rp_a, const float* rp_r, const float* rp_s2, const float* rp_notdone,
                              const int32_t* idx, const float* noise, int32_t batch, float gamma, float policy_noise,
                              float noise_clip, float max_action, float* loss2, float* q_out, float* y_out, int32_t* steps,
@@ -177,20 +181,20 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, flo
 /* TD3.train_actor minus the optimiser step (robot.py:382-394): loss = -mean(Q1(s, pi(s))) added into
  * loss1[0]; gradient w.r.t. the actor parameters only, written to grads (same zero-on-entry rule).
  * Increments steps[0]. */
-int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s,
+int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
                             const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream);
 
 /* torch.optim.Adam step (lr, betas 0.9/0.999, eps 1e-8; robot.py:237-239, 356-363, 393-395) on the nets
  * selected by `nets` (bit 0 actor, bit 1 critic1, bit 2 critic2) using grads*grad_scale (grad_scale = 1/world
  * after a gradient all-reduce), zeroing the consumed gradients; then TD3.soft_update (robot.py:293-310)
  * on the target nets selected by `polyak` (same bit layout) with the freshly updated online parameters. */
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const double* beta_pows,
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* grads, float* adam_m, float* adam_v, const double* beta_pows,
                              int32_t nets, float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau,
                              void* stream);
 
 /* Forward of one network of the arena (robot.py:153-159 / 193-200): x [batch][in] -> y [batch][out]. */
-int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* x, float* y, int64_t batch,
-                         void* stream);
+int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* params_t, const float* x, float* y,
+                         int64_t batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Robot per-step hooks                         (robot.py:443-675, 727-762)

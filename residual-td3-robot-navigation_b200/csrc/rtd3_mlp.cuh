@@ -1,9 +1,12 @@
 // CTA-level fp32 building blocks for the residual-TD3 networks (robot.py:128-206):
 //   actor  2 -> H -> ... -> H -> 2      critic  4 -> H -> ... -> H -> 1      (L hidden layers, ReLU, linear head)
 // A CTA of kThreads threads owns R consecutive batch rows and walks the whole layer chain for them; activations
-// stay in shared memory, weights ([out][in] row-major, torch layout) stream from L2 through a kStages-deep
-// cp.async tile ring.  Thread t owns output column t of every hidden layer (H <= kThreads) and keeps R
-// accumulators in registers.  Weight gradients are NOT formed here: forward/backward store the per-row layer
+// stay in shared memory.  Hidden-layer products are out[r][c] = sum_j X[r][j] * M[j][c] with M row-major and c
+// contiguous: the forward pass reads the TRANSPOSED weight copy Wt [in][out] (kept next to the torch-layout
+// parameters by the optimiser kernel), the backward pass reads the torch layout W [out][in] itself.  A thread owns 4
+// consecutive columns (one coalesced 16 B load per weight row, straight from L2 - no shared-memory staging, which
+// made LDGSTS + LDS traffic the bottleneck of the first version) and a quarter of the j range; the four partial
+// sums meet in shared memory once per layer.  Weight gradients are NOT formed here: forward/backward store the per-row layer
 // inputs and pre-activation gradients to an L2-resident scratch, and wgrad_kernel (rtd3_td3.cu) reduces them over
 // the batch tile by tile without atomics.
 #pragma once
@@ -14,10 +17,8 @@ namespace rtd3 {
 constexpr int kThreads = 256;
 constexpr int kMaxHidden = 256;
 constexpr int kMaxLayers = 4;
-constexpr int kKC = 16;              // reduction chunk per pipeline stage
-constexpr int kStages = 4;           // cp.async stages in flight
-constexpr int kLdW = kKC + 4;        // padded row stride (floats) of a row-pattern weight tile: conflict-free LDS.128
-constexpr int kStageFloats = kMaxHidden * kLdW;   // 5120 floats = 20 KB per stage (>= kKC * kMaxHidden for the column pattern)
+constexpr int kGroups = 4;           // thread groups splitting the reduction range of a hidden layer
+constexpr int kColThreads = kThreads / kGroups;   // 64 column groups x 4 columns = 256 columns
 
 struct NetShape {
   int in, hid, layers, out;          // layers = number of hidden layers L (>= 1)
@@ -72,7 +73,7 @@ extern __shared__ __align__(16) float smem_f[];
 
 template <int R>
 struct MlpSmem {
-  int wst;        // [kStages][kStageFloats] weight tile ring
+  int wst;        // [kGroups][R][kMaxHidden] partial sums of the reduction groups
   int act0;       // act(l) = act0 + l*R*ld: output of hidden layer l (R x ld), kept for backward
   int dz0, dz1;   // gradient w.r.t. pre-activations / forward ping-pong (R x ld)
   int in0;        // [R][4] network input
@@ -84,12 +85,12 @@ struct MlpSmem {
 
   __host__ __device__ static size_t floats(int hid, int keep_layers) {
     const int ld = hid + 4;
-    return (size_t)kStages * kStageFloats + (size_t)keep_layers * R * ld + 2 * (size_t)R * ld + R * 4 + R * 2 + R * 2 + R * 4 + R * 8;
+    return (size_t)kGroups * R * kMaxHidden + (size_t)keep_layers * R * ld + 2 * (size_t)R * ld + R * 4 + R * 2 + R * 2 + R * 4 + R * 8;
   }
   __device__ __forceinline__ void carve(int base, int hid, int keep_layers) {
     ld = hid + 4;
     int p = base;
-    wst = p; p += kStages * kStageFloats;
+    wst = p; p += kGroups * R * kMaxHidden;
     act0 = p; p += keep_layers * R * ld;
     dz0 = p; p += R * ld;
     dz1 = p; p += R * ld;
@@ -105,7 +106,7 @@ struct MlpSmem {
 
 __host__ inline size_t mlp_smem_bytes(int R, int hid, int keep_layers) {
   const int ld = hid + 4;
-  size_t f = (size_t)kStages * kStageFloats + (size_t)keep_layers * R * ld + 2 * (size_t)R * ld + R * 4 + R * 2 + R * 2 + R * 4 + R * 8;
+  size_t f = (size_t)kGroups * R * kMaxHidden + (size_t)keep_layers * R * ld + 2 * (size_t)R * ld + R * 4 + R * 2 + R * 2 + R * 4 + R * 8;
   return f * sizeof(float);
 }
 
@@ -142,74 +143,69 @@ __device__ __forceinline__ void fwd_first(const float* __restrict__ W, const flo
   __syncthreads();
 }
 
-// ---- hidden layer forward: Y[r][c] = relu(b[c] + sum_k X[r][k] * W[c][k]) -------------------------------------
-// Weight tile of a stage: rows [0,N) x cols [k0,k0+kc) of the row-major [N][K] matrix, laid out [N][kLdW].
-// Thread t copies quarter (t&3) of rows (t>>2) + 64*i: four 16 B cp.async per stage, sources advance by kKC floats.
+// ---- hidden-layer product: part[g][r][c] = sum_{j in range(g)} X[r][j] * M[j][c],  M row-major [J][C] in global ----
+// Thread t: column group cg = t % 64 (columns 4cg..4cg+3), reduction group g = t / 64 (a contiguous quarter of j, in
+// multiples of 4).  Per 4 j's: four coalesced 16 B weight loads (software-pipelined one iteration ahead), R broadcast
+// LDS.128 of X, 16*R FFMA.  Partials are left in smem_f[red + (g*R + r)*kMaxHidden + c].
 template <int R>
-__device__ __forceinline__ void fwd_hidden(const float* __restrict__ W, const float* __restrict__ b, int X, int Y, int ld, int N, int K, int wst) {
-  const int c = threadIdx.x;
-  const int srow = c >> 2, sq = c & 3;
-  const float* src = W + srow * K + 4 * sq;
-  float* dst = smem_f + wst + srow * kLdW + 4 * sq;
-  const int rowstep = 64 * K;
-  auto stage = [&](int ch) {
-    const int k0 = ch * kKC;
-    if (4 * sq < K - k0) {
-      float* d = dst + (ch % kStages) * kStageFloats;
-      const float* g = src + k0;
+__device__ __forceinline__ void rows_times_matrix(const float* __restrict__ M, int X, int ld, int J, int C, int red) {
+  const int cg = threadIdx.x & (kColThreads - 1), g = threadIdx.x / kColThreads;
+  const int c0 = cg * 4;
+  const int part = ((J + 4 * kGroups - 1) / (4 * kGroups)) * 4;
+  const int jlo = g * part, jhi = min(J, jlo + part);
+  float acc[R][4];
 #pragma unroll
-      for (int i = 0; i < kMaxHidden / 64; ++i)
-        if (srow + 64 * i < N) cp_async16(d + i * 64 * kLdW, g + i * rowstep);
-    }
-  };
-  float acc0[R], acc1[R];
-  const float bias = (c < N) ? __ldg(b + c) : 0.f;
+  for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+  if (c0 < C && jlo < jhi) {
+    const float4* mp = reinterpret_cast<const float4*>(M + jlo * C + c0);
+    const int stride4 = C >> 2;                       // float4 per weight row
+    float4 w[4], wn[4];
 #pragma unroll
-  for (int r = 0; r < R; ++r) { acc0[r] = bias; acc1[r] = 0.f; }
-  const int nchunks = (K + kKC - 1) / kKC;
+    for (int i = 0; i < 4; ++i) w[i] = __ldg(mp + i * stride4);
+    for (int j = jlo; j < jhi; j += 4) {
+      if (j + 4 < jhi) {
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
-    if (s < nchunks) stage(s);
-    cp_commit();
-  }
-  const float* xbase = smem_f + X;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    cp_wait<kStages - 2>();            // chunk ch has landed (this thread's copies) ...
-    __syncthreads();                   // ... and everyone's; everyone is also done reading chunk ch-1's slot
-    if (ch + kStages - 1 < nchunks) stage(ch + kStages - 1);
-    cp_commit();
-    const int k0 = ch * kKC;
-    if (c < N) {
-      const float* wrow = smem_f + wst + (ch % kStages) * kStageFloats + c * kLdW;
-      const float* xr = xbase + k0;
-      if (K - k0 >= kKC) {
-#pragma unroll
-        for (int kk = 0; kk < kKC; kk += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(wrow + kk);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 x = *reinterpret_cast<const float4*>(xr + r * ld + kk);   // warp-broadcast
-            acc0[r] = fmaf(x.x, w.x, acc0[r]); acc1[r] = fmaf(x.y, w.y, acc1[r]);
-            acc0[r] = fmaf(x.z, w.z, acc0[r]); acc1[r] = fmaf(x.w, w.w, acc1[r]);
-          }
-        }
-      } else {
-        for (int kk = 0; kk < K - k0; kk += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(wrow + kk);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 x = *reinterpret_cast<const float4*>(xr + r * ld + kk);
-            acc0[r] = fmaf(x.x, w.x, acc0[r]); acc1[r] = fmaf(x.y, w.y, acc1[r]);
-            acc0[r] = fmaf(x.z, w.z, acc0[r]); acc1[r] = fmaf(x.w, w.w, acc1[r]);
-          }
-        }
+        for (int i = 0; i < 4; ++i) wn[i] = __ldg(mp + (4 + i) * stride4);
       }
+      mp += 4 * stride4;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 x = lds4(X + r * ld + j);        // warp-broadcast
+        acc[r][0] = fmaf(x.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[0].y, acc[r][1]);
+        acc[r][2] = fmaf(x.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[0].w, acc[r][3]);
+        acc[r][0] = fmaf(x.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[1].y, acc[r][1]);
+        acc[r][2] = fmaf(x.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[1].w, acc[r][3]);
+        acc[r][0] = fmaf(x.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[2].y, acc[r][1]);
+        acc[r][2] = fmaf(x.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[2].w, acc[r][3]);
+        acc[r][0] = fmaf(x.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[3].y, acc[r][1]);
+        acc[r][2] = fmaf(x.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[3].w, acc[r][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = wn[i];
     }
   }
-  cp_wait<0>();
-  if (c < N) {
+  if (c0 < C) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) smem_f[Y + r * ld + c] = fmaxf(acc0[r] + acc1[r], 0.f);
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4*>(smem_f + red + (g * R + r) * kMaxHidden + c0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+  __syncthreads();
+}
+
+// ---- hidden layer forward: Y[r][c] = relu(b[c] + sum_k X[r][k] * Wt[k][c]) ------------------------------------
+template <int R>
+__device__ __forceinline__ void fwd_hidden(const float* __restrict__ Wt, const float* __restrict__ b, int X, int Y, int ld, int N, int K, int red) {
+  rows_times_matrix<R>(Wt, X, ld, K, N, red);
+  const int c = threadIdx.x;
+  if (c < N) {
+    const float bias = __ldg(b + c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v = bias;
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) v += smem_f[red + (g * R + r) * kMaxHidden + c];
+      smem_f[Y + r * ld + c] = fmaxf(v, 0.f);
+    }
   }
   __syncthreads();
 }
@@ -231,15 +227,15 @@ __device__ __forceinline__ void fwd_out(const float* __restrict__ W, const float
 // Whole-network forward for the CTA's R rows.  keep=true stores hidden layer l in sm.act(l) (needed by backward) and,
 // when `rs` is given, also in the global row scratch; keep=false ping-pongs between sm.dz0 / sm.dz1.
 template <int R>
-__device__ __forceinline__ void mlp_forward(const float* __restrict__ P, const NetShape& s, const MlpSmem<R>& sm, bool keep,
-                                            const RowScratch* rs, int r0) {
+__device__ __forceinline__ void mlp_forward(const float* __restrict__ P, const float* __restrict__ Pt, const NetShape& s, const MlpSmem<R>& sm,
+                                            bool keep, const RowScratch* rs, int r0) {
   const int y0 = keep ? sm.act(0) : sm.dz0;
   fwd_first<R>(P + net_w_off(s, 0), P + net_b_off(s, 0), sm.in0, s.in, y0, sm.ld, s.hid);
   if (rs) store_rows<R>(rs->h(0), y0, sm.ld, s.hid, r0, rs->B);
   int x = y0;
   for (int l = 1; l < s.layers; ++l) {
     const int y = keep ? sm.act(l) : sm.dz(l & 1);
-    fwd_hidden<R>(P + net_w_off(s, l), P + net_b_off(s, l), x, y, sm.ld, s.hid, s.hid, sm.wst);
+    fwd_hidden<R>(Pt + net_w_off(s, l), P + net_b_off(s, l), x, y, sm.ld, s.hid, s.hid, sm.wst);
     if (rs) store_rows<R>(rs->h(l), y, sm.ld, s.hid, r0, rs->B);
     x = y;
   }
@@ -262,64 +258,19 @@ __device__ __forceinline__ void bwd_out(const float* __restrict__ W, int H, int 
   __syncthreads();
 }
 
-// Input gradient of a hidden layer: dzp[r][k] = relu'(Hprev[r][k]) * sum_n dz[r][n] * W[n][k]
-// Weight tile of a stage: rows [n0,n0+nc) x all K cols = a contiguous block, laid out [nc][K]; thread k reads column k.
+// Input gradient of a hidden layer: dzp[r][k] = relu'(Hprev[r][k]) * sum_n dz[r][n] * W[n][k]   (torch layout W [N][K])
 template <int R>
-__device__ __forceinline__ void bwd_input(const float* __restrict__ W, int dz, int Hprev, int dzp, int ld, int N, int K, int wst) {
+__device__ __forceinline__ void bwd_input(const float* __restrict__ W, int dz, int Hprev, int dzp, int ld, int N, int K, int red) {
+  rows_times_matrix<R>(W, dz, ld, N, K, red);
   const int k = threadIdx.x;
-  auto stage = [&](int ch) {
-    const int n0 = ch * kKC, nc = min(kKC, N - n0);
-    const float* g = W + n0 * K;
-    float* d = smem_f + wst + (ch % kStages) * kStageFloats;
-    for (int idx = k; idx < (nc * K) >> 2; idx += kThreads) cp_async16(d + 4 * idx, g + 4 * idx);
-  };
-  float acc0[R], acc1[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-  const int nchunks = (N + kKC - 1) / kKC;
-#pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
-    if (s < nchunks) stage(s);
-    cp_commit();
-  }
-  const float* dbase = smem_f + dz;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    cp_wait<kStages - 2>();
-    __syncthreads();
-    if (ch + kStages - 1 < nchunks) stage(ch + kStages - 1);
-    cp_commit();
-    const int n0 = ch * kKC;
-    if (k < K) {
-      const float* wp = smem_f + wst + (ch % kStages) * kStageFloats + k;
-      const float* dr = dbase + n0;
-      if (N - n0 >= kKC) {
-#pragma unroll
-        for (int nn = 0; nn < kKC; nn += 4) {
-          const float w0 = wp[(nn + 0) * K], w1 = wp[(nn + 1) * K], w2 = wp[(nn + 2) * K], w3 = wp[(nn + 3) * K];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 d = *reinterpret_cast<const float4*>(dr + r * ld + nn);   // warp-broadcast
-            acc0[r] = fmaf(d.x, w0, acc0[r]); acc1[r] = fmaf(d.y, w1, acc1[r]);
-            acc0[r] = fmaf(d.z, w2, acc0[r]); acc1[r] = fmaf(d.w, w3, acc1[r]);
-          }
-        }
-      } else {
-        for (int nn = 0; nn < N - n0; nn += 4) {
-          const float w0 = wp[(nn + 0) * K], w1 = wp[(nn + 1) * K], w2 = wp[(nn + 2) * K], w3 = wp[(nn + 3) * K];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 d = *reinterpret_cast<const float4*>(dr + r * ld + nn);
-            acc0[r] = fmaf(d.x, w0, acc0[r]); acc1[r] = fmaf(d.y, w1, acc1[r]);
-            acc0[r] = fmaf(d.z, w2, acc0[r]); acc1[r] = fmaf(d.w, w3, acc1[r]);
-          }
-        }
-      }
-    }
-  }
-  cp_wait<0>();
   if (k < K) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) smem_f[dzp + r * ld + k] = smem_f[Hprev + r * ld + k] > 0.f ? acc0[r] + acc1[r] : 0.f;
+    for (int r = 0; r < R; ++r) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) v += smem_f[red + (g * R + r) * kMaxHidden + k];
+      smem_f[dzp + r * ld + k] = smem_f[Hprev + r * ld + k] > 0.f ? v : 0.f;
+    }
   }
   __syncthreads();
 }

@@ -53,7 +53,7 @@ __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_
 // instantiated once (the fully inlined five-call version was 143 KB of SASS and stalled on instruction fetch).
 template <int R>
 __global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
-td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
+td3_critic_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
                   const float* __restrict__ noise /*[B][2] unit normal*/, int B, Td3Hyper hp, float* __restrict__ loss /*[2]*/,
                   float* __restrict__ q_out /*nullable [2][B]*/, float* __restrict__ y_out /*nullable [B]*/, int32_t* __restrict__ steps,
                   double* __restrict__ beta_pows) {
@@ -86,7 +86,7 @@ td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict_
     const float* P = params + ar.off(net);
     RowScratch rs{scratch + (train ? (pass - 3) : 0) * RowScratch::floats(B, ar.critic.hid, ar.critic.layers), B, ar.critic.hid,
                   ar.critic.layers};
-    mlp_forward<R>(P, shape, sm, train, train ? &rs : nullptr, r0);
+    mlp_forward<R>(P, params_t + ar.off(net), shape, sm, train, train ? &rs : nullptr, r0);
     if (t < R) {
       if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
         const int row = min(r0 + t, B - 1);
@@ -131,7 +131,7 @@ td3_critic_kernel(Arena ar, const float* __restrict__ params, float* __restrict_
 //   L = -mean(Q1(s, pi(s)));  gradient w.r.t. the actor only (critic-1 parameter gradients are discarded by the reference)
 template <int R>
 __global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
-td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
+td3_actor_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
                  int B, float* __restrict__ loss /*[1]*/, int32_t* __restrict__ steps, double* __restrict__ beta_pows) {
   MlpSmem<R> sc;                      // critic pass (activations kept, backward for dQ/da)
   sc.carve(0, ar.critic.hid, ar.critic.layers);
@@ -157,7 +157,7 @@ td3_actor_kernel(Arena ar, const float* __restrict__ params, float* __restrict__
   // forward: pass 0 a = pi(s) (fed the raw replay state, robot.py:386), pass 1 Q1(s, a)
   for (int pass = 0; pass < 2; ++pass) {
     const MlpSmem<R> sm = pass == 0 ? sa : sc;
-    mlp_forward<R>(params + ar.off(pass), pass == 0 ? ar.actor : ar.critic, sm, true, pass == 0 ? &rs : nullptr, r0);
+    mlp_forward<R>(params + ar.off(pass), params_t + ar.off(pass), pass == 0 ? ar.actor : ar.critic, sm, true, pass == 0 ? &rs : nullptr, r0);
     if (t < R) {
       if (pass == 0) {
         float* cin = smem_f + sc.in0;
@@ -325,7 +325,31 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
 // nets: bit 0 actor, bit 1 critic1, bit 2 critic2 get an Adam step from `grads` (then the gradients are zeroed);
 // polyak: same bit layout; afterwards the selected target slots are blended with their (updated) online net:
 // t = t*(1-tau) + p*tau.
-__global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ grads, float* __restrict__ m,
+// Index of parameter i (arena index inside slot `net_off`) in the transposed arena: hidden-layer weights W_l [H][H]
+// (l = 1..L-1) are stored as Wt_l [in][out] at the same offset; everything else keeps its place.
+__device__ __forceinline__ int64_t transposed_index(const NetShape& s, int64_t net_off, int64_t i) {
+  const int64_t o = i - net_off;
+  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
+  if (o < first) return i;
+  const int64_t o2 = o - first;
+  const int64_t l = o2 / blk, rem = o2 - l * blk;
+  if (l >= s.layers - 1 || rem >= (int64_t)s.hid * s.hid) return i;
+  const int64_t n = rem / s.hid, k = rem - n * s.hid;
+  return net_off + first + l * blk + k * s.hid + n;
+}
+
+// Rebuild the whole transposed arena from the parameters (after weights were written from outside the optimiser).
+__global__ void td3_sync_transposed_kernel(Arena ar, const float* __restrict__ params, float* __restrict__ params_t) {
+  const int64_t total = ar.total(), n_online = ar.online_total();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i < n_online ? i : i - n_online;
+    const int net = j < ar.off(1) ? 0 : (j < ar.off(2) ? 1 : 2);
+    const int64_t base = (i < n_online ? 0 : n_online) + ar.off(net);
+    params_t[transposed_index(net == 0 ? ar.actor : ar.critic, base, i)] = params[i];
+  }
+}
+
+__global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ grads, float* __restrict__ m,
                                        float* __restrict__ v, const double* __restrict__ beta_pows, int nets, float lr_actor,
                                        float lr_critic, float grad_scale, int polyak, float tau) {
   __shared__ float s_step[2], s_bc2[2];
@@ -352,11 +376,14 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
       const float denom = sqrtf(vi) / s_bc2[o] + 1e-8f;
       p = p - s_step[o] * (mi / denom);
       params[i] = p;
+      params_t[transposed_index(net == 0 ? ar.actor : ar.critic, ar.off(net), i)] = p;
     }
     if ((polyak >> net) & 1) {
       const int64_t ti = n_online + i;                                // target slots mirror the online layout
       // torch evaluates target*(1-tau) + source*tau as three separately rounded float32 ops (robot.py:309): no fma here
-      params[ti] = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
+      const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
+      params[ti] = tv;
+      params_t[transposed_index(net == 0 ? ar.actor : ar.critic, n_online + ar.off(net), ti)] = tv;
     }
   }
 }
@@ -364,7 +391,7 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
 // ---- plain forward of one network over B rows (actor inference for get_next_action, parity checks of Q-values) ------
 template <int R>
 __global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
-mlp_forward_kernel(NetShape s, const float* __restrict__ P, const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/,
+mlp_forward_kernel(NetShape s, const float* __restrict__ P, const float* __restrict__ Pt, const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/,
                    int B) {
   MlpSmem<R> sm;
   sm.carve(0, s.hid, 0);
@@ -374,7 +401,7 @@ mlp_forward_kernel(NetShape s, const float* __restrict__ P, const float* __restr
     smem_f[sm.in0 + t] = (row < B && j < s.in) ? x[(int64_t)row * s.in + j] : 0.f;
   }
   __syncthreads();
-  mlp_forward<R>(P, s, sm, false, nullptr, r0);
+  mlp_forward<R>(P, Pt, s, sm, false, nullptr, r0);
   if (t < R * s.out) {
     const int r = t / s.out, o = t - r * s.out;
     if (r0 + r < B) y[(int64_t)(r0 + r) * s.out + o] = smem_f[sm.out + r * 2 + o];
@@ -504,11 +531,18 @@ int64_t rtd3_td3_scratch_floats(const rtd3_td3* h, int32_t batch) {
   return h ? 2 * RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers) : -1;
 }
 
-int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s, const float* rp_a,
+int32_t rtd3_td3_sync_transposed(rtd3_td3* h, const float* params, float* params_t, void* stream) {
+  RTD3_CHECK_ARG(h && params && params_t, "null argument");
+  td3_sync_transposed_kernel<<<h->num_sms * 2, 256, 0, (cudaStream_t)stream>>>(h->ar, params, params_t);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s, const float* rp_a,
                              const float* rp_r, const float* rp_s2, const float* rp_notdone, const int32_t* idx, const float* noise,
                              int32_t batch, float gamma, float policy_noise, float noise_clip, float max_action, float* loss2, float* q_out,
                              float* y_out, int32_t* steps, double* beta_pows, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && scratch && rp_s && rp_a && rp_r && rp_s2 && rp_notdone && idx && noise && loss2 && steps && beta_pows,
+  RTD3_CHECK_ARG(h && params && params_t && grads && scratch && rp_s && rp_a && rp_r && rp_s2 && rp_notdone && idx && noise && loss2 && steps && beta_pows,
                  "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, (const float2*)rp_a, rp_r, (const float2*)rp_s2, rp_notdone};
@@ -518,7 +552,7 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, flo
   const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
 #define RTD3_CRITIC(RR) \
-  td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
+  td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
   if (ti == 0) RTD3_CRITIC(4); else if (ti == 1) RTD3_CRITIC(8); else RTD3_CRITIC(16);
 #undef RTD3_CRITIC
   RTD3_LAUNCHED();
@@ -529,16 +563,16 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, float* grads, flo
   return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st);
 }
 
-int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
+int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
                             int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
+  RTD3_CHECK_ARG(h && params && params_t && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
   const int ti = pick_tile(batch, h->num_sms);
   const int R = kRowTiles[ti];
   const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
-#define RTD3_ACTOR(RR) td3_actor_kernel<RR><<<grid, kThreads, h->smem_actor[ti], st>>>(h->ar, params, scratch, rp, idx, batch, loss1, steps, beta_pows)
+#define RTD3_ACTOR(RR) td3_actor_kernel<RR><<<grid, kThreads, h->smem_actor[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows)
   if (ti == 0) RTD3_ACTOR(4); else if (ti == 1) RTD3_ACTOR(8); else RTD3_ACTOR(16);
 #undef RTD3_ACTOR
   RTD3_LAUNCHED();
@@ -548,20 +582,21 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, float* grads, floa
   return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st);
 }
 
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
                              float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau, void* stream) {
-  RTD3_CHECK_ARG(h && params && grads && adam_m && adam_v && beta_pows, "null argument");
+  RTD3_CHECK_ARG(h && params && params_t && grads && adam_m && adam_v && beta_pows, "null argument");
   const int64_t n = h->ar.online_total();
   const int block = 256;
   const int grid = (int)std::min<int64_t>(ceil_div(n, block), (int64_t)h->num_sms * 8);
-  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
+  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, params_t, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
                                                                     lr_critic, grad_scale, polyak, tau);
   RTD3_LAUNCHED();
   return 0;
 }
 
-int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* x, float* y, int64_t batch, void* stream) {
-  RTD3_CHECK_ARG(h && params && x && y, "null argument");
+int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* params_t, const float* x, float* y, int64_t batch,
+                         void* stream) {
+  RTD3_CHECK_ARG(h && params && params_t && x && y, "null argument");
   RTD3_CHECK_ARG(net >= 0 && net < 6, "net index out of range");
   RTD3_CHECK_ARG(batch >= 0 && batch < (1ll << 31), "bad batch");
   if (batch == 0) return 0;
@@ -570,7 +605,7 @@ int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const fl
   const int R = kRowTiles[ti];
   const int grid = (int)((batch + R - 1) / R);
   cudaStream_t st = (cudaStream_t)stream;
-#define RTD3_FWD(RR) mlp_forward_kernel<RR><<<grid, kThreads, h->smem_fwd[ti], st>>>(s, params + h->ar.off(net), x, y, (int)batch)
+#define RTD3_FWD(RR) mlp_forward_kernel<RR><<<grid, kThreads, h->smem_fwd[ti], st>>>(s, params + h->ar.off(net), params_t + h->ar.off(net), x, y, (int)batch)
   if (ti == 0) RTD3_FWD(4); else if (ti == 1) RTD3_FWD(8); else RTD3_FWD(16);
 #undef RTD3_FWD
   RTD3_LAUNCHED();

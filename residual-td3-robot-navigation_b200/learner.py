@@ -235,6 +235,8 @@ class _Network:
 
     def load_flat(self, values):
         self._flat.copy_(torch.as_tensor(np.asarray(values, dtype=np.float32)).to(self._flat.device))
+        if self._td3 is not None:
+            self._td3._t_stale = True
 
     def eval(self):
         return self
@@ -283,6 +285,8 @@ class TD3:
         self._cnt = [int(L.rtd3_td3_param_count(self._handle, k)) for k in range(6)]
         total = int(L.rtd3_td3_arena_floats(self._handle))
         self.params = torch.zeros((total,), dtype=torch.float32, device=self.device)
+        self.params_t = torch.zeros((total,), dtype=torch.float32, device=self.device)   # hidden weights transposed (forward layout)
+        self._t_stale = True
         self.grads = torch.zeros((total // 2,), dtype=torch.float32, device=self.device)
         self.adam_m = torch.zeros_like(self.grads)
         self.adam_v = torch.zeros_like(self.grads)
@@ -330,7 +334,16 @@ class TD3:
 
     # ---- arena access ---------------------------------------------------------------------------------
     def flat(self, net):
+        """Flat torch-order view of network `net`'s parameters.  Handing it out marks the transposed copy stale (it may be
+        written through); edits through previously obtained views need an explicit `sync_transposed()`."""
+        self._t_stale = True
         return self.params[self._off[net]:self._off[net] + self._cnt[net]]
+
+    def sync_transposed(self, force=True):
+        if force or self._t_stale:
+            _lib.check(_lib.lib().rtd3_td3_sync_transposed(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t),
+                                                           _lib.stream_ptr(self.device)), "td3_sync_transposed")
+            self._t_stale = False
 
     def flat_grad(self, net):
         return self.grads[self._off[net]:self._off[net] + self._cnt[net]]
@@ -340,7 +353,8 @@ class TD3:
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         out_dim = 2 if net in (NET_ACTOR, NET_T_ACTOR) else 1
         y = torch.empty((x.shape[0], out_dim), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().rtd3_mlp_forward(self._handle, net, _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y), x.shape[0],
+        self.sync_transposed(force=False)
+        _lib.check(_lib.lib().rtd3_mlp_forward(self._handle, net, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(x), _lib.ptr(y), x.shape[0],
                                                _lib.stream_ptr(self.device)), "mlp_forward")
         return y
 
@@ -359,7 +373,7 @@ class TD3:
     def _critic_step(self, rb, idx, noise, loss2, q_out=None, y_out=None):
         B = idx.numel()
         _lib.check(_lib.lib().rtd3_td3_critic_step(
-            self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(rb.a),
+            self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads), _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(rb.a),
             _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise,
             self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
             _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step")
@@ -368,14 +382,14 @@ class TD3:
 
     def _actor_step(self, rb, idx, loss1):
         B = idx.numel()
-        _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads),
+        _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads),
                                                   _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1),
                                                   _lib.ptr(self.steps), _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)),
                    "td3_actor_step")
         self._allreduce()
 
     def _adam(self, nets, polyak):
-        _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+        _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
 
@@ -393,6 +407,7 @@ class TD3:
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
         noise = self._noise((idx.numel(), 2)) if noise is None else noise.to(self.device, torch.float32).contiguous()
         loss2 = torch.zeros((2,), dtype=torch.float32, device=self.device)
+        self.sync_transposed(force=False)
         self._critic_step(replay_buffer, idx, noise, loss2, q_out, y_out)
         l = loss2.cpu()
         return float(l[0]), float(l[1])
@@ -406,6 +421,7 @@ class TD3:
             idx = idx[0]
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
         loss1 = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        self.sync_transposed(force=False)
         self._actor_step(replay_buffer, idx, loss1)
         self._adam(nets=0b001, polyak=0)
         return float(loss1.cpu()[0])
@@ -415,6 +431,7 @@ class TD3:
         pairs = {NET_T_ACTOR: NET_ACTOR, NET_T_CRITIC1: NET_CRITIC1, NET_T_CRITIC2: NET_CRITIC2}
         if getattr(target, "_td3", None) is not self or pairs.get(target._net) != getattr(source, "_net", None):
             raise ValueError("soft_update expects a (target, online) pair of this TD3 agent")
+        self.sync_transposed(force=False)
         old_tau, self.tau = self.tau, tau
         try:
             self._adam(nets=0, polyak=1 << (target._net - 3))
@@ -455,6 +472,7 @@ class TD3:
                   "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None}
             self._row_scratch(B)
             self._graphs[key] = st
+        self.sync_transposed(force=False)
         st["idx"].copy_(idx)
         if noise is None:
             st["noise"].normal_()                                     # torch.randn_like, robot.py:338 (unseeded there)
