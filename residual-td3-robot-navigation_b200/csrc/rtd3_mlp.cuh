@@ -147,8 +147,41 @@ __device__ __forceinline__ void fwd_first(const float* __restrict__ W, const flo
 // Thread t: column group cg = t % 64 (columns 4cg..4cg+3), reduction group g = t / 64 (a contiguous quarter of j, in
 // multiples of 4).  Per 4 j's: four coalesced 16 B weight loads (software-pipelined one iteration ahead), R broadcast
 // LDS.128 of X, 16*R FFMA.  Partials are left in smem_f[red + (g*R + r)*kMaxHidden + c].
+// kJ = weight rows per register buffer (8 for row tiles R <= 8, 4 for R = 16 where the accumulators need the registers): two buffers alternate, so 8 coalesced 16 B loads (one per row)
+                         // are in flight per thread while the previous 8 rows are consumed - with 2 warps per scheduler a
+                         // one-iteration (4-row) pipeline left the loop 52 % stalled on these loads (ncu r1c)
+
+template <int R, int kJ>
+__device__ __forceinline__ void consume_rows(const float4 (&w)[kJ], int X, int ld, int j, int cnt, float (&acc)[R][4]) {
+#pragma unroll
+  for (int jj = 0; jj < kJ; jj += 4) {
+    if (jj < cnt) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 x = lds4(X + r * ld + j + jj);        // warp-broadcast
+        acc[r][0] = fmaf(x.x, w[jj].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[jj].y, acc[r][1]);
+        acc[r][2] = fmaf(x.x, w[jj].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[jj].w, acc[r][3]);
+        acc[r][0] = fmaf(x.y, w[jj + 1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[jj + 1].y, acc[r][1]);
+        acc[r][2] = fmaf(x.y, w[jj + 1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[jj + 1].w, acc[r][3]);
+        acc[r][0] = fmaf(x.z, w[jj + 2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[jj + 2].y, acc[r][1]);
+        acc[r][2] = fmaf(x.z, w[jj + 2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[jj + 2].w, acc[r][3]);
+        acc[r][0] = fmaf(x.w, w[jj + 3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[jj + 3].y, acc[r][1]);
+        acc[r][2] = fmaf(x.w, w[jj + 3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[jj + 3].w, acc[r][3]);
+      }
+    }
+  }
+}
+
+template <int kJ>
+__device__ __forceinline__ void load_rows(float4 (&w)[kJ], const float4* __restrict__ mp, int stride4, int cnt) {
+#pragma unroll
+  for (int i = 0; i < kJ; ++i)
+    if (i < cnt) w[i] = __ldg(mp + i * stride4);
+}
+
 template <int R>
 __device__ __forceinline__ void rows_times_matrix(const float* __restrict__ M, int X, int ld, int J, int C, int red) {
+  constexpr int kJ = (R >= 16) ? 4 : 8;
   const int cg = threadIdx.x & (kColThreads - 1), g = threadIdx.x / kColThreads;
   const int c0 = cg * 4;
   const int part = ((J + 4 * kGroups - 1) / (4 * kGroups)) * 4;
@@ -159,29 +192,14 @@ __device__ __forceinline__ void rows_times_matrix(const float* __restrict__ M, i
   if (c0 < C && jlo < jhi) {
     const float4* mp = reinterpret_cast<const float4*>(M + jlo * C + c0);
     const int stride4 = C >> 2;                       // float4 per weight row
-    float4 w[4], wn[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] = __ldg(mp + i * stride4);
-    for (int j = jlo; j < jhi; j += 4) {
-      if (j + 4 < jhi) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wn[i] = __ldg(mp + (4 + i) * stride4);
-      }
-      mp += 4 * stride4;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4 x = lds4(X + r * ld + j);        // warp-broadcast
-        acc[r][0] = fmaf(x.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[0].y, acc[r][1]);
-        acc[r][2] = fmaf(x.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[0].w, acc[r][3]);
-        acc[r][0] = fmaf(x.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[1].y, acc[r][1]);
-        acc[r][2] = fmaf(x.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[1].w, acc[r][3]);
-        acc[r][0] = fmaf(x.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[2].y, acc[r][1]);
-        acc[r][2] = fmaf(x.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[2].w, acc[r][3]);
-        acc[r][0] = fmaf(x.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[3].y, acc[r][1]);
-        acc[r][2] = fmaf(x.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[3].w, acc[r][3]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = wn[i];
+    float4 wa[kJ], wb[kJ];
+    load_rows<kJ>(wa, mp, stride4, jhi - jlo);
+    for (int j = jlo; j < jhi; j += 2 * kJ) {
+      if (j + kJ < jhi) load_rows<kJ>(wb, mp + kJ * stride4, stride4, jhi - j - kJ);
+      consume_rows<R, kJ>(wa, X, ld, j, jhi - j, acc);
+      if (j + 2 * kJ < jhi) load_rows<kJ>(wa, mp + 2 * kJ * stride4, stride4, jhi - j - 2 * kJ);
+      if (j + kJ < jhi) consume_rows<R, kJ>(wb, X, ld, j + kJ, jhi - j - kJ, acc);
+      mp += 2 * kJ * stride4;
     }
   }
   if (c0 < C) {

@@ -52,7 +52,7 @@ __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_
 // One CTA = R batch rows through the whole chain: five network passes driven by ONE loop so that the layer code is
 // instantiated once (the fully inlined five-call version was 143 KB of SASS and stalled on instruction fetch).
 template <int R>
-__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 1)
 td3_critic_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
                   const float* __restrict__ noise /*[B][2] unit normal*/, int B, Td3Hyper hp, float* __restrict__ loss /*[2]*/,
                   float* __restrict__ q_out /*nullable [2][B]*/, float* __restrict__ y_out /*nullable [B]*/, int32_t* __restrict__ steps,
@@ -130,7 +130,7 @@ td3_critic_kernel(Arena ar, const float* __restrict__ params, const float* __res
 // ---- actor phase: robot.py:369-398 up to the optimiser step ---------------------------------------------------------
 //   L = -mean(Q1(s, pi(s)));  gradient w.r.t. the actor only (critic-1 parameter gradients are discarded by the reference)
 template <int R>
-__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 1)
 td3_actor_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp, const int32_t* __restrict__ idx,
                  int B, float* __restrict__ loss /*[1]*/, int32_t* __restrict__ steps, double* __restrict__ beta_pows) {
   MlpSmem<R> sc;                      // critic pass (activations kept, backward for dQ/da)
@@ -390,7 +390,7 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
 
 // ---- plain forward of one network over B rows (actor inference for get_next_action, parity checks of Q-values) ------
 template <int R>
-__global__ void __launch_bounds__(kThreads, (R <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 1)
 mlp_forward_kernel(NetShape s, const float* __restrict__ P, const float* __restrict__ Pt, const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/,
                    int B) {
   MlpSmem<R> sm;
