@@ -48,68 +48,140 @@ __device__ void mt_regenerate_warp(uint32_t* mt, int lane) {
   }
 }
 
-// Kernel A: swap lists.  J[s*n + i] = j_i for i = 1..n-1 (entry 0 unused).
-__global__ void __launch_bounds__(32)
+// Kernel A: swap lists.  J[s*n + i] = j_i for i = 1..n-1 (entry 0 unused).  One CTA of 256 threads.
+//
+// A round takes up to 256 consecutive raw draws, thread t owning draw t.  With i swaps still to draw, thread t's bound
+// (i minus the number of accepted draws before it) lies in [i - t, i].  If the mask is the same at both ends the draw is
+// classified without knowing the exact bound: v <= i - t  -> accepted whatever happened before ("sure"),
+// v > i -> rejected, in between -> "maybe" (a band of at most t values out of >= 2^k, ~1 % of the draws).  Threads whose
+// range crosses a power of two are maybes too; the round is sized (32..256) so that there are at most 32 of those.  One
+// block scan ranks the sure draws; thread 0 then resolves the few maybes in order with their exact bounds, and a second
+// pass adds the accepted maybes into every thread's rank.  The round ends early at the draw that completes a sample.
+constexpr int kSampleThreads = 256;
+
+__device__ __forceinline__ void mt_regenerate_block(uint32_t* mt, uint32_t* raw, int t) {
+  constexpr int N = RTD3_MT_N, M = 397;
+  const int lo[3] = {0, N - M, 2 * (N - M)}, hi[3] = {N - M, 2 * (N - M), N};
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {               // every range reads only words finished by earlier ranges (or still old)
+    const int kk = lo[ph] + t;
+    uint32_t v = 0;
+    if (kk < hi[ph]) v = mt_twist(mt[kk], mt[kk + 1 < N ? kk + 1 : 0], mt[kk + M < N ? kk + M : kk + M - N]);
+    __syncthreads();
+    if (kk < hi[ph]) mt[kk] = v;
+    __syncthreads();
+  }
+  for (int k = t; k < N; k += kSampleThreads) raw[k] = mt_temper(mt[k]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSampleThreads)
 sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count, int32_t* __restrict__ J) {
-  __shared__ uint32_t mt[RTD3_MT_N];
-  const int lane = threadIdx.x;
-  for (int k = lane; k < RTD3_MT_N; k += 32) mt[k] = b.mt[(int64_t)k * b.n + stream_id];
-  int pos = b.pos[stream_id];
-  __syncwarp();
+  __shared__ uint32_t mt[RTD3_MT_N], raw[RTD3_MT_N];
+  __shared__ int w_sure[2][8], w_maybe[2][8], w_macc[2][8];
+  __shared__ int m_S[kSampleThreads], m_acc[kSampleThreads];
+  __shared__ uint32_t m_raw[kSampleThreads];
+  __shared__ int s_last[2], s_macc_total[2];
+  int par = 0;                                       // round parity: control words alternate between two buffers
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t lt = (1u << lane) - 1u;
+  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) {
+    mt[k] = b.mt[(int64_t)k * b.n + stream_id];
+    raw[k] = mt_temper(mt[k]);
+  }
+  int pos = b.pos[stream_id];
+  if (t == 0) { s_last[0] = -1; s_macc_total[0] = 0; }
+  __syncthreads();
+
   for (int s = 0; s < count; ++s) {
     int32_t* Js = J + (int64_t)s * n;
-    int i = n - 1;                                  // swaps still to draw: indices i, i-1, ..., 1
+    int i = n - 1;                                  // swaps still to draw: indices i, i-1, ..., 1 (same value in every thread)
     while (i >= 1) {
       if (pos >= RTD3_MT_N) {
-        mt_regenerate_warp(mt, lane);
+        mt_regenerate_block(mt, raw, t);
         pos = 0;
       }
-      const int g = min(32, RTD3_MT_N - pos);
-      const bool active = lane < g;
-      const uint32_t raw = active ? mt_temper(mt[pos + lane]) : 0u;
-      // accepted(L) = (raw_L & mask(i_L)) <= i_L with i_L = i - #accepted lanes below L (i_L >= 1).
-      // Fast path: evaluate it under the two extreme assumptions (no lower lane accepted / every lower lane accepted);
-      // the truth lies between them, so if both ballots agree that is the answer (all but ~1 % of the groups).
-      // Otherwise iterate the ballot to its fixed point.
-      auto decide = [&](uint32_t assumed, int& bound, uint32_t& val) {
-        bound = i - __popc(assumed & lt);
-        const uint32_t mask = bound >= 1 ? (0xffffffffu >> __clz(bound)) : 0u;
-        val = raw & mask;
-        return __ballot_sync(0xffffffffu, active && bound >= 1 && val <= (uint32_t)bound);
-      };
-      int my_i, bi;
-      uint32_t v, bv;
-      const uint32_t acc_hi = decide(0u, my_i, v);
-      const uint32_t acc_lo = decide(0xffffffffu, bi, bv);
-      uint32_t acc = acc_hi;
-      // (the sandwich argument needs one mask for the whole group: no power-of-two crossing within reach of i)
-      const bool one_mask = __clz(i) == __clz(max(i - 31, 1));
-      if (acc_lo != acc_hi || !one_mask) {
-        uint32_t prev;
-        do {
-          prev = acc;
-          acc = decide(prev, my_i, v);
-        } while (acc != prev);
-      } else {
-        acc = decide(acc_hi, my_i, v);             // bounds / values under the agreed set
+      // round size: stay on one mask level while the distance to the next power of two allows rounds of >= 32 draws
+      const int lvl = 31 - __clz(i);                // mask(i) = 2^(lvl+1) - 1
+      const int gap = i - (1 << lvl);               // bounds down to i - gap keep mask(i)
+      const int gmax = kSampleThreads;
+      const int g = min(min(max(gap + 1, 32), gmax), RTD3_MT_N - pos);
+      const bool active = t < g;
+      const uint32_t rw = active ? raw[pos + t] : 0u;
+      const int lo = i - t;                          // bound if every earlier draw of the round was accepted
+      const bool uniform = lo >= 1 && __clz(lo) == __clz(i);
+      const uint32_t v_hi = rw & (0xffffffffu >> __clz(i));
+      const bool sure = active && uniform && (int)v_hi <= lo;
+      const bool maybe = active && !sure && lo < i && ((uniform && (int)v_hi <= i) || (!uniform && i - t < i));
+      const uint32_t bs = __ballot_sync(0xffffffffu, sure), bm = __ballot_sync(0xffffffffu, maybe);
+      if (lane == 0) { w_sure[par][warp] = __popc(bs); w_maybe[par][warp] = __popc(bm); }
+      if (t == 0) { s_last[par ^ 1] = -1; s_macc_total[par ^ 1] = 0; }   // next round's words (nobody reads them now)
+      __syncthreads();
+      int S = __popc(bs & lt), mpos = __popc(bm & lt), total_sure = 0, total_maybe = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        if (w < warp) { S += w_sure[par][w]; mpos += w_maybe[par][w]; }
+        total_sure += w_sure[par][w];
+        total_maybe += w_maybe[par][w];
       }
-      if (acc & (1u << lane)) Js[my_i] = (int32_t)v;
-      const int n_acc = __popc(acc);
-      if (n_acc >= i) {
-        // the sample completes inside this group: the accepted lane with bound 1 is its last draw
-        const uint32_t last = __ballot_sync(0xffffffffu, (acc & (1u << lane)) && my_i == 1);
-        pos += (31 - __clz(last)) + 1;              // later draws of the group belong to the next sample
-        i = 0;
-      } else {
-        pos += g;
-        i -= n_acc;
+      int rank = S;
+      bool accepted = sure;
+      uint32_t v = v_hi;
+      if (total_maybe > 0) {                         // block-uniform branch
+        if (maybe) { m_S[mpos] = S; m_raw[mpos] = rw; }   // compacted in stream order
+        __syncthreads();
+        if (warp == 0) {
+          // the undecided draws, 32 at a time: bound_q = i - (sure draws before q) - (accepted undecided draws before q);
+          // the last term is resolved by iterating the ballot to its fixed point (lane L depends only on lanes < L)
+          int extra = 0;
+          for (int q0 = 0; q0 < total_maybe; q0 += 32) {
+            const int q = q0 + lane;
+            const bool on = q < total_maybe;
+            const int Sq = on ? m_S[q] : 0;
+            const uint32_t rq = on ? m_raw[q] : 0u;
+            uint32_t acc = 0u, prev;
+            do {
+              prev = acc;
+              const int bound = i - Sq - extra - __popc(prev & lt);
+              const bool a = on && bound >= 1 && (int)(rq & (0xffffffffu >> __clz(max(bound, 1)))) <= bound;
+              acc = __ballot_sync(0xffffffffu, a);
+            } while (acc != prev);
+            if (on) m_acc[q] = (acc >> lane) & 1;
+            extra += __popc(acc);
+          }
+          if (lane == 0) s_macc_total[par] = extra;
+        }
+        __syncthreads();
+        const bool macc = maybe && m_acc[mpos] != 0;
+        const uint32_t ba = __ballot_sync(0xffffffffu, macc);
+        if (lane == 0) w_macc[par][warp] = __popc(ba);
+        __syncthreads();
+        int before = __popc(ba & lt);
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          if (w < warp) before += w_macc[par][w];
+        rank = S + before;
+        if (maybe) {
+          accepted = macc;
+          v = rw & (0xffffffffu >> __clz(max(i - rank, 1)));
+        }
       }
+      const int my_i = i - rank;
+      const bool valid = accepted && my_i >= 1;
+      if (valid) {
+        Js[my_i] = (int32_t)v;
+        if (my_i == 1) s_last[par] = t;              // the draw that completes this sample
+      }
+      __syncthreads();
+      const int total_acc = total_sure + s_macc_total[par];
+      const int last = s_last[par];
+      par ^= 1;
+      if (total_acc >= i) { pos += last + 1; i = 0; }
+      else { pos += g; i -= total_acc; }
     }
   }
-  __syncwarp();
-  for (int k = lane; k < RTD3_MT_N; k += 32) b.mt[(int64_t)k * b.n + stream_id] = mt[k];
-  if (lane == 0) b.pos[stream_id] = pos;
+  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) b.mt[(int64_t)k * b.n + stream_id] = mt[k];
+  if (t == 0) b.pos[stream_id] = pos;
 }
 
 // Kernel B: out[s][p] = x[p] after the shuffle, by unwinding the swaps from position p.
@@ -187,7 +259,7 @@ extern "C" int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  sample_swaps_kernel<<<1, 32, 0, st>>>(*bank, stream_id, n, count, scratch);
+  sample_swaps_kernel<<<1, kSampleThreads, 0, st>>>(*bank, stream_id, n, count, scratch);
   RTD3_LAUNCHED();
   const size_t smem = (size_t)((n + 3) & ~3) * 4;
   sample_trace_kernel<<<count, 256, smem, st>>>(scratch, n, batch, out);

@@ -207,3 +207,20 @@ def test_underfilled_replay_raises_like_the_reference(pkg):
     rb = pkg.ReplayBuffer(100, seed=0)
     with pytest.raises(TypeError):
         agent.train_critic(rb)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 64, 100, 255, 256, 257, 511, 513, 1000, 4095, 4096, 4097, 10000, 20011])
+def test_sample_indices_exact_for_many_sizes(pkg, n):
+    """Power-of-two neighbourhoods exercise the mask-level crossings of random_interval; several consecutive draws exercise the
+    hand-over of the stream position between samples and across MT19937 regenerations."""
+    rb = pkg.ReplayBuffer(32768, seed=n)
+    k = torch.arange(n, dtype=torch.float32, device="cuda")
+    rb.push(torch.stack([k, k], 1), torch.stack([k, k], 1), k, torch.stack([k, k], 1), torch.zeros(n, dtype=torch.bool, device="cuda"))
+    rs = np.random.RandomState(n)
+    B = max(1, min(n, 97))
+    got = rb.sample_indices(B, 7).cpu().numpy()
+    exp = np.stack([rs.choice(n, B, replace=False) for _ in range(7)])
+    assert (got == exp).all()
+    got2 = rb.sample_indices(n, 2).cpu().numpy()          # full permutations, stream continues
+    exp2 = np.stack([rs.choice(n, n, replace=False) for _ in range(2)])
+    assert (got2 == exp2).all()
