@@ -245,38 +245,43 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
 
 
 def bench_full_loop(rt, torch, dev, world, rank):
-    """configs[3]: the act -> step -> transition -> (episode end: TD3 update) loop, 8192 envs per GPU, gradients all-reduced."""
+    """configs[3]: the act -> step -> transition -> (episodes ended: TD3 update) loop, gradients all-reduced across ranks.
+    8192 envs per GPU (65536 over 8 GPUs) and, for the per-GPU ceiling, 65536 envs per GPU."""
     import torch.distributed as dist
     pg = dist.group.WORLD if world > 1 else None
-    n = 8192
-    env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
-    robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=50000)
-    robot.td3_agent.batch_size = 256
-    robot.td3_agent.num_epochs = 20
-    robot.memory.sampler = "philox"
-    robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
-    tr = rt.BatchedTrainer(env, robot, noise="randn")
-    for _ in range(8):
-        tr.tick()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ticks, upd0, steps0 = 120, robot.num_updates, int(tr.steps_bought.sum())
-    e0.record()
-    for _ in range(ticks):
-        tr.tick()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    st = torch.tensor([float(int(tr.steps_bought.sum()) - steps0)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(st)
-    ms = float(t[0])
-    return {"envs_total": n * world, "ticks": ticks, "ms_per_tick": ms / ticks, "env_steps_per_sec": float(st[0]) / (ms * 1e-3),
-            "td3_updates_in_window": (robot.num_updates - upd0), "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
-            "note": "host-driven tick loop (5 launches + 1 flag read per tick); exploration noise torch.randn, replay sampling philox"}
+    rows = []
+    for n in (8192, 65536):
+        env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
+        robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 4 * n))
+        robot.td3_agent.batch_size = 256
+        robot.td3_agent.num_epochs = 20
+        robot.memory.sampler = "philox"
+        robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
+        tr = rt.BatchedTrainer(env, robot, noise="randn", graph=True, check_interval=8)
+        for _ in range(16):
+            tr.tick()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ticks, upd0, steps0 = 240, robot.num_updates, int(tr.steps_bought.sum())
+        e0.record()
+        for _ in range(ticks):
+            tr.tick()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        st = torch.tensor([float(int(tr.steps_bought.sum()) - steps0)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(st)
+        ms = float(t[0])
+        rows.append({"envs_per_gpu": n, "envs_total": n * world, "ticks": ticks, "ms_per_tick": ms / ticks,
+                     "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
+                     "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
+                     "note": "one CUDA graph per tick, finished-episode counter read every 8 ticks; noise torch.randn, replay sampling philox"})
+        del tr, robot, env
+    return rows
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):

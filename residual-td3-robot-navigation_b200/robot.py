@@ -112,7 +112,6 @@ class Robot:
         # one.  The default N keeps the reference's rhythm (every env finishes about one episode between updates) and is
         # exactly the reference for the single-env drop-in (robot.py:480-483).
         self.episodes_per_update = self.num_envs
-        self._episodes_since_update = 0
 
     # ---- reference attributes (single-env views of the device state) --------------------------------------------
     def _scalar(self, t):
@@ -132,18 +131,27 @@ class Robot:
         return torch.as_tensor(np.asarray(state, dtype=np.float32).reshape(self.num_envs, 2)).to(self.device).t().contiguous()
 
     # ---- robot.py:443-506 ------------------------------------------------------------------------------------------
-    def get_next_action_type(self, state, money_remaining):
-        n = self.num_envs
-        self._any_update.zero_()
+    def advance_action_types(self):
+        """Device half of get_next_action_type: the per-env state machine (robot.py:443-489 with reset() :492-506); finished
+        episodes are counted into a device counter.  No host synchronisation, so it can sit inside a CUDA graph."""
         _lib.check(_lib.lib().rtd3_robot_next_action_type(
             _lib.ptr(self._num_episodes), _lib.ptr(self._demo_flag), _lib.ptr(self._plan_index), _lib.ptr(self._path_length),
             _lib.ptr(self._goal_reached), _lib.ptr(self._stuck_flag), _lib.ptr(self._noise_scale), _lib.ptr(self._type),
-            _lib.ptr(self._update), _lib.ptr(self._any_update), n, _lib.stream_ptr(self.device)), "robot_next_action_type")
-        self._episodes_since_update += int(self._any_update.item())
-        if self._episodes_since_update >= self.episodes_per_update:   # robot.py:480-483: reset() then td3_update(memory)
-            self._episodes_since_update = 0
+            _lib.ptr(self._update), _lib.ptr(self._any_update), self.num_envs, _lib.stream_ptr(self.device)), "robot_next_action_type")
+        return self._type
+
+    def maybe_update(self):
+        """Host half: read the finished-episode counter and run td3_update when due (robot.py:480-483)."""
+        if int(self._any_update.item()) >= self.episodes_per_update:
+            self._any_update.zero_()
             self.td3_agent.td3_update(self.memory)
             self.num_updates += 1
+            return True
+        return False
+
+    def get_next_action_type(self, state, money_remaining):
+        self.advance_action_types()
+        self.maybe_update()
         if self.batched:
             return self._type
         return ACTION_TYPES[int(self._type[0].item())]

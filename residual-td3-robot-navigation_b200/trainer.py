@@ -37,7 +37,12 @@ def allreduce_grads_(flat_grads, group=None):
 
 
 class BatchedTrainer:
-    def __init__(self, environment, robot, noise="mt19937"):
+    """`graph=True` captures the device work of one tick (state machine, act, step, transition + replay push, masked reset)
+    in a CUDA graph and looks at the finished-episode counter only every `check_interval` ticks, so the tick costs one graph
+    launch instead of a dozen kernel launches and a device->host read.  With `graph=False, check_interval=1` every tick is
+    launched eagerly and checked immediately (the single-env-like behaviour)."""
+
+    def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1):
         if environment.num_envs != robot.num_envs:
             raise ValueError("environment and robot must hold the same envs")
         self.env, self.robot = environment, robot
@@ -48,26 +53,60 @@ class BatchedTrainer:
         self.steps_bought = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self.resets_bought = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self.ticks = 0
+        self.check_interval = max(1, int(check_interval))
         self._prev = torch.empty((2, self.n), dtype=torch.float32, device=self.device)
+        self._z = torch.zeros((2, self.n), dtype=torch.float64, device=self.device)
+        self._use_graph = bool(graph)
+        self._graph = None
 
     def money_remaining(self, tick_charge=0.0):
         c = constants
         return (c.STARTING_MONEY - self.resets_bought * c.COST_PER_RESET - self.steps_bought * c.COST_PER_STEP - self.ticks * tick_charge)
 
-    def tick(self):
+    def _device_tick(self):
         env, robot = self.env, self.robot
-        types = robot.get_next_action_type(None, None)                        # int8 [N]; td3_update inside when due
-        stepping = types == 0
+        types = robot.advance_action_types()                                  # int8 [N]
         z = None
         if self.noise == "randn":
-            z = torch.randn((2, self.n), dtype=torch.float64, device=self.device)
+            z = self._z.normal_()
         self._prev.copy_(env._state)
         state = self._prev.t()
         action = robot.get_next_action_training(state, None, noise=z, types=types)
         next_state = env.step(action)                                         # null action where the env is not stepping
         robot.process_transition(state, action, next_state, None, types=types)
         env.reset(mask=types == 2)
-        self.steps_bought += stepping
+        self.steps_bought += (types == 0)
         self.resets_bought += (types == 2)
-        self.ticks += 1
         return types
+
+    def tick(self):
+        if self._use_graph:
+            if self._graph is None:
+                self.robot.td3_agent.sync_transposed(force=False)
+                self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
+                g = torch.cuda.CUDAGraph()
+                before = _launches()
+                with torch.cuda.graph(g):
+                    self._types = self._device_tick()
+                self._graph, self._graph_launches = g, _launches() - before
+                _add_launches(-self._graph_launches)
+            self._graph.replay()
+            _add_launches(self._graph_launches)
+            self.robot.memory._mark_device_advanced()                         # rows were pushed by the replayed kernels
+            types = self._types
+        else:
+            types = self._device_tick()
+        self.ticks += 1
+        if self.ticks % self.check_interval == 0:
+            self.robot.maybe_update()                                         # robot-learning.py:68 -> robot.py:480-483
+        return types
+
+
+def _launches():
+    from . import _lib
+    return _lib.launch_count()
+
+
+def _add_launches(n):
+    from . import _lib
+    _lib.lib().rtd3_launch_count_add(n)

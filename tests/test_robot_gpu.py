@@ -197,3 +197,24 @@ def test_philox_sampler_range_and_determinism(pkg):
     rb2.sampler = "philox"
     assert torch.equal(a, rb2.sample_indices(8192, 6))
     assert not torch.equal(a, rb.sample_indices(8192, 6))   # the counter advances
+
+
+def test_graphed_trainer_matches_eager_trainer(pkg, env_golden):
+    """The CUDA-graph tick replays exactly the eager tick (same kernels, same RNG streams): identical states and replay rows."""
+    g = env_golden
+    outs = []
+    for use_graph in (False, True):
+        env = pkg.Environment(num_envs=256, seed=5, maps=(g["speed"], g["angle"]))
+        robot = pkg.Robot(env.goal_state, hidden=64, layers=2, seed=3, buffer_size=40000)
+        torch.manual_seed(0)
+        robot.td3_agent.actor_network.load_flat(np.random.RandomState(0).normal(0, 0.05, robot.td3_agent.actor_network.count()).astype(np.float32))
+        robot.episodes_per_update = 10 ** 9                 # no learner update: compare the env/robot pipeline only
+        tr = pkg.BatchedTrainer(env, robot, graph=use_graph, check_interval=4)
+        for _ in range(70):
+            tr.tick()
+        rows = len(robot.memory)
+        outs.append((env.robot_state.clone(), rows, robot.memory.s[:rows].sum().item(), robot.memory.r[:rows].sum().item(),
+                     tr.steps_bought.clone(), tr.resets_bought.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert outs[0][2] == pytest.approx(outs[1][2], rel=1e-6) and outs[0][3] == pytest.approx(outs[1][3], rel=1e-6)
+    assert torch.equal(outs[0][4], outs[1][4]) and torch.equal(outs[0][5], outs[1][5])
