@@ -238,6 +238,21 @@ int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, i
                                     uint8_t* goal_reached, uint8_t* stuck_flag, double* noise_scale, int8_t* type_out,
                                     uint8_t* update_out, int32_t* any_update, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM, TF32) large-batch forward - opt-in throughput mode, not the parity path
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Rebuild params_u, the chunk-major (UMMA shared-memory operand order) copy of all hidden-layer weights of the
+ * arena: Wu[(k/4)*H + n][k%4] = W[n][k]; other entries are copied in place. */
+int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_u, void* stream);
+
+/* Forward of one network (robot.py:153-159 / 193-200) for 128-row batch tiles on the 5th-gen tensor cores:
+ * hidden H x H layers as tcgen05.mma.kind::tf32 with fp32 accumulators in TMEM, first / output layer in fp32.
+ * param_off = rtd3_td3_param_offset(net). hidden % 32 == 0, 64..256; layers >= 2.  Agrees with rtd3_mlp_forward
+ * to TF32 round-off (~1e-3 relative). */
+int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, int64_t param_off, const float* params,
+                              const float* params_u, const float* x, float* y, int64_t batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,274 @@
+// Large-batch network forward on the 5th-generation tensor cores (tcgen05 + TMEM), TF32 operands, fp32 accumulate.
+// Opt-in throughput mode (TD3.precision = "tf32"): the north star asks for tensor cores "only where the shapes
+// justify it" - a 128-row batch tile against an H x H hidden layer (M=128, N=H<=256, K=H) does, the 4..16-row tiles of
+// the small-batch learner do not.  fp32 FFMA (rtd3_mlp.cuh) stays the parity path; this one is checked against it
+// at TF32 tolerance (tests/test_tc_gpu.py).
+//
+// One CTA = 128 batch rows through the whole network (robot.py:153-159 / 193-200):
+//   first layer (in <= 4) and output layer (out <= 2): FFMA by the 128 row threads;
+//   every hidden H x H layer: D[128 x H] (TMEM, fp32) = X[128 x H] * W^T, issued as H/8 tcgen05.mma.kind::tf32 by ONE
+//   thread, operands in shared memory in the no-swizzle K-major canonical layout (16 B k-chunks, 8-row core matrices):
+//       X : chunk-major [H/4][128 rows][4]   (LBO = 2048 B between k-chunks, SBO = 128 B between 8-row groups)
+//       W : chunk-major [H/4][H rows n][4]   (LBO = 16*H B,                  SBO = 128 B) - kept in exactly this order in a
+//           third parameter arena (params_u), so a 32-wide K slab is ONE contiguous cp.async.bulk (TMA) per stage;
+//   epilogue: the row threads read their TMEM lane with tcgen05.ld (32 columns at a time), add bias, ReLU, and write the
+//   next layer's X straight back in the chunk layout (16 B per 4 columns, consecutive rows -> conflict-free).
+#include "rtd3_common.cuh"
+#include "rtd3_mlp.cuh"
+
+namespace rtd3 {
+
+constexpr int kTcRows = 128;          // batch rows per CTA = UMMA M
+constexpr int kTcThreads = 192;       // warps 0-3: row threads / epilogue, warp 4: TMA producer, warp 5: MMA issuer
+constexpr int kTcKSlab = 32;          // K per pipeline stage = 4 MMAs of K=8
+constexpr int kTcStages = 2;
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;       // leading byte offset (between the two k-chunks of one MMA), bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;       // stride byte offset (between 8-row core matrices), bits [32,46)
+  d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
+  return d;                                                // layout type 0 = no swizzle, base offset 0
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory plan (bytes): X [H/4][128][4] | W stages [2][8][H][4] | small params | barriers | tmem base
+__host__ __device__ inline size_t tc_smem_bytes(int hid, int layers) {
+  return (size_t)hid * 512 + (size_t)kTcStages * hid * 128 + ((size_t)hid * 4 + hid + (size_t)(layers - 1) * hid + 2 * hid + 4) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, const float* __restrict__ Pu /*chunk-major hidden weights*/,
+                      const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/, int B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int H = s.hid, L = s.layers;
+  float* Xs = reinterpret_cast<float*>(smem_raw);                                   // [H/4][128][4]
+  float* Ws = Xs + (size_t)H * 128;                                                 // [2][8][H][4]
+  float* small = Ws + (size_t)kTcStages * H * 32;
+  float* W1 = small;                    // [H][4] (zero-padded input dim)
+  float* b1 = W1 + H * 4;               // [H]
+  float* bh = b1 + H;                   // [L-1][H]
+  float* Wo = bh + (L - 1) * H;         // [2][H]
+  float* bo = Wo + 2 * H;               // [2] (+2 pad)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bo + 4);                             // full[2], empty[2], acc_ready
+  uint64_t* full = bars, *empty = bars + kTcStages, *acc_ready = bars + 2 * kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int r0 = blockIdx.x * kTcRows;
+
+  // ---- setup: small parameters to smem, barriers, TMEM allocation -------------------------------------------------
+  for (int i = t; i < H * 4; i += kTcThreads) {
+    const int c = i >> 2, j = i & 3;
+    W1[i] = j < s.in ? __ldg(P + net_w_off(s, 0) + c * s.in + j) : 0.f;
+  }
+  for (int i = t; i < H; i += kTcThreads) b1[i] = __ldg(P + net_b_off(s, 0) + i);
+  for (int l = 1; l < L; ++l)
+    for (int i = t; i < H; i += kTcThreads) bh[(l - 1) * H + i] = __ldg(P + net_b_off(s, l) + i);
+  for (int i = t; i < 2 * H; i += kTcThreads) Wo[i] = (i / H) < s.out ? __ldg(P + net_w_off(s, L) + i) : 0.f;
+  if (t < 2) bo[t] = t < s.out ? __ldg(P + net_b_off(s, L) + t) : 0.f;
+  if (t == 0) {
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- first layer by the row threads: X = relu(b1 + x0 W1^T), written in the chunk layout ---------------------------
+  if (t < kTcRows) {
+    const int row = r0 + t;
+    float x0[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < B)
+      for (int j = 0; j < s.in; ++j) x0[j] = x[(int64_t)row * s.in + j];
+    for (int c = 0; c < H; c += 4) {
+      float4 h;
+      float* hp = &h.x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(W1 + (c + q) * 4);
+        float v = b1[c + q];
+        v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
+        hp[q] = fmaxf(v, 0.f);
+      }
+      *reinterpret_cast<float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + t * 4) = h;
+    }
+  }
+  fence_proxy_async();                  // generic-proxy writes of X -> visible to the tensor core (async proxy)
+  __syncthreads();
+
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = H, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+  const int slabs = H / kTcKSlab;
+  const uint32_t stage_bytes = (uint32_t)H * (kTcKSlab / 4) * 16;      // 8 chunks x H rows x 16 B
+  uint32_t it_p = 0, it_c = 0;                                         // slab counters of producer / MMA issuer (continue across layers)
+
+  for (int l = 1; l < L; ++l) {
+    if (warp == 4 && lane == 0) {
+      // ===== TMA producer: one contiguous bulk copy per K slab of this layer's chunk-major weights =====
+      const float* Wu = Pu + net_w_off(s, l);
+      for (int ks = 0; ks < slabs; ++ks, ++it_p) {
+        const int st = it_p % kTcStages;
+        mbar_wait(empty + st, ((it_p / kTcStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(full + st, stage_bytes);
+        bulk_g2s(Ws + (size_t)st * H * 32, Wu + (size_t)ks * H * 32, stage_bytes, full + st);
+      }
+    } else if (warp == 5 && lane == 0) {
+      // ===== MMA issuer =====
+      for (int ks = 0; ks < slabs; ++ks, ++it_c) {
+        const int st = it_c % kTcStages;
+        mbar_wait(full + st, (it_c / kTcStages) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k4 = 0; k4 < kTcKSlab / 8; ++k4) {
+          const uint64_t ad = umma_desc_kmajor(smem_u32(Xs + (size_t)(ks * 8 + k4 * 2) * (kTcRows * 4)), kTcRows * 16, 128);
+          const uint64_t bd = umma_desc_kmajor(smem_u32(Ws + (size_t)st * H * 32 + (size_t)(k4 * 2) * H * 4), (uint32_t)H * 16, 128);
+          umma_tf32(tmem, ad, bd, idesc, (ks | k4) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty + st);                      // frees the weight stage once these MMAs have read it
+      }
+      umma_commit(acc_ready);                         // accumulator complete (commits track all prior MMAs)
+    }
+    if (t < kTcRows) {
+      // ===== epilogue: TMEM -> registers -> bias + ReLU -> next X (in place: every MMA that read X has completed) =====
+      mbar_wait(acc_ready, (l - 1) & 1);
+      tc_fence_after();
+      const float* bias = bh + (l - 1) * H;
+      for (int cb = 0; cb < H; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 h;
+          h.x = fmaxf(v[4 * q + 0] + bias[cb + 4 * q + 0], 0.f);
+          h.y = fmaxf(v[4 * q + 1] + bias[cb + 4 * q + 1], 0.f);
+          h.z = fmaxf(v[4 * q + 2] + bias[cb + 4 * q + 2], 0.f);
+          h.w = fmaxf(v[4 * q + 3] + bias[cb + 4 * q + 3], 0.f);
+          *reinterpret_cast<float4*>(Xs + (size_t)((cb >> 2) + q) * (kTcRows * 4) + t * 4) = h;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+    }
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  // ---- output layer by the row threads ----------------------------------------------------------------------------------
+  if (t < kTcRows && r0 + t < B) {
+    float o0 = bo[0], o1 = bo[1];
+    for (int c = 0; c < H; c += 4) {
+      const float4 h = *reinterpret_cast<const float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + t * 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(Wo + c), w1 = *reinterpret_cast<const float4*>(Wo + H + c);
+      o0 = fmaf(h.x, w0.x, o0); o0 = fmaf(h.y, w0.y, o0); o0 = fmaf(h.z, w0.z, o0); o0 = fmaf(h.w, w0.w, o0);
+      o1 = fmaf(h.x, w1.x, o1); o1 = fmaf(h.y, w1.y, o1); o1 = fmaf(h.z, w1.z, o1); o1 = fmaf(h.w, w1.w, o1);
+    }
+    y[(int64_t)(r0 + t) * s.out] = o0;
+    if (s.out > 1) y[(int64_t)(r0 + t) * s.out + 1] = o1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+}
+
+// chunk-major copy of the hidden-layer weights: Wu[(k/4)*H + n][k%4] = W[n][k]; everything else keeps its place
+__device__ __forceinline__ int64_t chunk_major_index(const NetShape& s, int64_t net_off, int64_t i) {
+  const int64_t o = i - net_off;
+  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
+  if (o < first) return i;
+  const int64_t o2 = o - first;
+  const int64_t l = o2 / blk, rem = o2 - l * blk;
+  if (l >= s.layers - 1 || rem >= (int64_t)s.hid * s.hid) return i;
+  const int64_t n = rem / s.hid, k = rem - n * s.hid;
+  return net_off + first + l * blk + ((k >> 2) * s.hid + n) * 4 + (k & 3);
+}
+
+__global__ void sync_chunk_major_kernel(NetShape actor, NetShape critic, int64_t sa, int64_t sc, const float* __restrict__ params,
+                                        float* __restrict__ params_u) {
+  const int64_t n_online = sa + 2 * sc, total = 2 * n_online;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i < n_online ? i : i - n_online;
+    const int net = j < sa ? 0 : (j < sa + sc ? 1 : 2);
+    const int64_t off = (i < n_online ? 0 : n_online) + (net == 0 ? 0 : (net == 1 ? sa : sa + sc));
+    params_u[chunk_major_index(net == 0 ? actor : critic, off, i)] = params[i];
+  }
+}
+
+}  // namespace rtd3
+
+using namespace rtd3;
+
+extern "C" {
+
+/* Rebuild the chunk-major (UMMA operand order) copy of all hidden-layer weights from the torch-layout arena. */
+int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_u, void* stream) {
+  RTD3_CHECK_ARG(params && params_u && hidden >= 4 && layers >= 1, "bad argument");
+  const NetShape a{2, hidden, layers, 2}, c{4, hidden, layers, 1};
+  sync_chunk_major_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, c, net_stride(a), net_stride(c), params, params_u);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+/* Network forward on tcgen05 tensor cores (TF32 operands, fp32 accumulate) for batch tiles of 128 rows.
+ * net: 0/3 actor (2->H..->2), else critic (4->H..->1); param_off: offset of the network's slot in both arenas.
+ * Requires hidden % 32 == 0, 64 <= hidden <= 256. */
+int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, int64_t param_off, const float* params, const float* params_u,
+                              const float* x, float* y, int64_t batch, void* stream) {
+  RTD3_CHECK_ARG(params && params_u && x && y, "null argument");
+  RTD3_CHECK_ARG(hidden % 32 == 0 && hidden >= 64 && hidden <= 256 && layers >= 2 && layers <= kMaxLayers,
+                 "tf32 path needs hidden in {64..256} divisible by 32 and at least one hidden-to-hidden layer");
+  RTD3_CHECK_ARG(batch >= 0 && batch < (1ll << 31), "bad batch");
+  if (batch == 0) return 0;
+  const NetShape s = is_actor ? NetShape{2, hidden, layers, 2} : NetShape{4, hidden, layers, 1};
+  const size_t smem = tc_smem_bytes(hidden, layers);
+  static size_t attr = 0;
+  if (smem > attr) {
+    RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int grid = (int)ceil_div(batch, kTcRows);
+  mlp_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, params_u + param_off, x, y, (int)batch);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

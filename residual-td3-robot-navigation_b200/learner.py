@@ -287,6 +287,10 @@ class TD3:
         self.params = torch.zeros((total,), dtype=torch.float32, device=self.device)
         self.params_t = torch.zeros((total,), dtype=torch.float32, device=self.device)   # hidden weights transposed (forward layout)
         self._t_stale = True
+        # "fp32": every product in fp32 FFMA (the parity path).  "tf32": forward passes of >= 128 rows run on the tcgen05 tensor
+        # cores with TF32 operands (throughput mode; ~1e-3 relative on the outputs) when the width allows it (hidden % 32 == 0).
+        self.precision = "fp32"
+        self.params_u = None
         self.grads = torch.zeros((total // 2,), dtype=torch.float32, device=self.device)
         self.adam_m = torch.zeros_like(self.grads)
         self.adam_v = torch.zeros_like(self.grads)
@@ -318,6 +322,7 @@ class TD3:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.last_losses = None
+        self._u_stale = True
         self._graphs = {}
         if self.world > 1:                  # initialise the communicator outside of any graph capture
             import torch.distributed as dist
@@ -344,6 +349,21 @@ class TD3:
             _lib.check(_lib.lib().rtd3_td3_sync_transposed(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t),
                                                            _lib.stream_ptr(self.device)), "td3_sync_transposed")
             self._t_stale = False
+            self._u_stale = True
+
+    def _tc_ok(self, batch):
+        return self.precision == "tf32" and self.hidden % 32 == 0 and 64 <= self.hidden <= 256 and self.layers >= 2 and batch >= 128
+
+    def _sync_chunk_major(self):
+        """Chunk-major weight copy for the tensor-core forward; rebuilt whenever the parameters may have changed (the
+        optimiser steps mark it stale)."""
+        if self.params_u is None:
+            self.params_u = torch.zeros_like(self.params)
+            self._u_stale = True
+        if self._u_stale:
+            _lib.check(_lib.lib().rtd3_tc_sync_weights(self.hidden, self.layers, _lib.ptr(self.params), _lib.ptr(self.params_u),
+                                                       _lib.stream_ptr(self.device)), "tc_sync_weights")
+            self._u_stale = False
 
     def flat_grad(self, net):
         return self.grads[self._off[net]:self._off[net] + self._cnt[net]]
@@ -354,6 +374,12 @@ class TD3:
         out_dim = 2 if net in (NET_ACTOR, NET_T_ACTOR) else 1
         y = torch.empty((x.shape[0], out_dim), dtype=torch.float32, device=self.device)
         self.sync_transposed(force=False)
+        if self._tc_ok(x.shape[0]):
+            self._sync_chunk_major()
+            _lib.check(_lib.lib().rtd3_mlp_forward_tf32(self.hidden, self.layers, 1 if net in (NET_ACTOR, NET_T_ACTOR) else 0, self._off[net],
+                                                        _lib.ptr(self.params), _lib.ptr(self.params_u), _lib.ptr(x), _lib.ptr(y), x.shape[0],
+                                                        _lib.stream_ptr(self.device)), "mlp_forward_tf32")
+            return y
         _lib.check(_lib.lib().rtd3_mlp_forward(self._handle, net, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(x), _lib.ptr(y), x.shape[0],
                                                _lib.stream_ptr(self.device)), "mlp_forward")
         return y
@@ -389,6 +415,7 @@ class TD3:
         self._allreduce()
 
     def _adam(self, nets, polyak):
+        self._u_stale = True
         _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
