@@ -244,15 +244,49 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
     return out
 
 
+def bench_forward(rt, torch, dev):
+    """Actor forward (2 -> 256 -> 256 -> 2) of the act hook at rollout-sized batches: fp32 FFMA kernel vs the tcgen05 / TMEM
+    TF32 kernel (opt-in throughput mode).  Tensor-pipe roofline: measured dense bf16 peak / 2 as the TF32 reference."""
+    H, L = 256, 2
+    agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L), device=dev)
+    agent.sync_transposed()
+    _, bf16_peak, _ = load_peaks()
+    rows = []
+    for B in (65536, 1 << 20):
+        xs = [torch.rand((B, 2), device=dev) * 100 - 50 for _ in range(3)]
+        flops = 2.0 * B * (2 * H + (L - 1) * H * H + 2 * H)
+        for precision in ("fp32", "tf32"):
+            agent.precision = precision
+            for k in range(3):
+                agent.forward(0, xs[k])
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for k in range(reps):
+                agent.forward(0, xs[k % 3])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            row = {"batch": B, "precision": precision, "us": round(us, 1), "rows_per_sec": B / (us * 1e-6), "tflops": flops / us / 1e6}
+            if precision == "tf32":
+                row["frac_of_tf32_peak"] = row["tflops"] / (bf16_peak / 2)
+            else:
+                row["frac_of_nominal_fp32_peak"] = row["tflops"] / FP32_FFMA_PEAK_TFLOPS
+            rows.append(row)
+    return rows
+
+
 def bench_full_loop(rt, torch, dev, world, rank):
     """configs[3]: the act -> step -> transition -> (episodes ended: TD3 update) loop, gradients all-reduced across ranks.
     8192 envs per GPU (65536 over 8 GPUs) and, for the per-GPU ceiling, 65536 envs per GPU."""
     import torch.distributed as dist
     pg = dist.group.WORLD if world > 1 else None
     rows = []
-    for n in (8192, 65536):
+    for n, precision in ((8192, "fp32"), (65536, "fp32"), (65536, "tf32")):
         env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
         robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 4 * n))
+        robot.td3_agent.precision = precision          # "tf32": the actor forward of the act hook runs on tcgen05 tensor cores
         robot.td3_agent.batch_size = 256
         robot.td3_agent.num_epochs = 20
         robot.memory.sampler = "philox"
@@ -276,7 +310,7 @@ def bench_full_loop(rt, torch, dev, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(st)
         ms = float(t[0])
-        rows.append({"envs_per_gpu": n, "envs_total": n * world, "ticks": ticks, "ms_per_tick": ms / ticks,
+        rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "ticks": ticks, "ms_per_tick": ms / ticks,
                      "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
                      "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
                      "note": "one CUDA graph per tick, finished-episode counter read every 8 ticks; noise torch.randn, replay sampling philox"})
@@ -415,6 +449,7 @@ def run_b200(args):
             del bx, ba
         extra["step_kernel_sweep"] = sweep
     td3_rows = None if args.no_td3 else bench_td3(rt, torch, dev, world, rank, cpu=not args.no_cpu)
+    fwd_rows = None if (args.no_td3 or rank != 0) else bench_forward(rt, torch, dev)
     loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
     sampler.in_region = False
     sampler.stop()
@@ -444,6 +479,8 @@ def run_b200(args):
         line.update(extra)
         if td3_rows is not None:
             line["td3"] = td3_rows
+        if fwd_rows is not None:
+            line["actor_forward"] = fwd_rows
         if loop_row is not None:
             line["full_loop"] = loop_row
         print(json.dumps(line))
