@@ -27,6 +27,10 @@ ACTION_RANGE = 7.5
 SEED = 1707366464
 ROLL_BYTES_PER_ENV_STEP = 16   # 8 B action read + 8 B state written; state stays in registers
 STEP_BYTES_PER_ENV_STEP = 24   # single-step kernel: state in 8 + action in 8 + state out 8
+# dram__bytes_read.sum + dram__bytes_write.sum of one env_rollout_tma_kernel launch at 4096 envs x 1000 steps, from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_summaries.md (32.905 MB read + 0.454 MB written: the actions are read
+# once = algorithmic; the 32.8 MB trajectory is still in the 126 MB L2 when the kernel ends)
+ROLLOUT_NCU_DRAM_BYTES = 32905472 + 454144
 
 
 def load_peaks():
@@ -329,9 +333,20 @@ def run_b200(args):
             t_sample = 200                                                             # ~13 core-seconds of the reference loop
             v_all, wall, total = cpu_env_steps(ENVS, t_sample, procs, pool)
         v_one, _, _ = cpu_env_steps(64, 16, 1, None)
+        # the same arithmetic vectorised over the envs in numpy (not how the reference runs, reported for context)
+        from oracle import env_oracle as eo
+        sp_, an_ = eo.synthetic_maps(0)
+        rs_ = np.random.RandomState(0)
+        st_ = rs_.uniform(0, 98.9999, (ENVS, 2))
+        ac_ = rs_.uniform(-ACTION_RANGE, ACTION_RANGE, (50, ENVS, 2))
+        t0_ = time.perf_counter()
+        for t_ in range(50):
+            st_ = eo.step_batch(sp_, an_, st_, ac_[t_])
+        v_vec = ENVS * 50 / (time.perf_counter() - t0_)
         cpu = {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
                "sample": "%d envs x %d steps (%.1f s wall) of the rollout, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
-                         % (ENVS, t_sample, wall, procs, v_one)}
+                         % (ENVS, t_sample, wall, procs, v_one),
+               "vectorised_numpy_1core": v_vec}
 
     import torch
     import torch.distributed as dist
@@ -466,7 +481,7 @@ def run_b200(args):
                        "envs_per_gpu": n, "rollout_steps": T, "kernel": "env_rollout_kernel<traj>",
                        "l2": "inputs rotate over %d action + %d trajectory buffers (%.0f MB > 126 MB L2)" % (R, R, 2 * R * per_buf / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind,
+                         "traffic": (ROLLOUT_NCU_DRAM_BYTES if (n == ENVS and T == T_STEPS) else None), "peak_kind": peak_kind,
                          "note": "%d B per env-step (action in 8 B, state out 8 B; state lives in registers) x %d env-steps per launch; "
                                  "4096 envs = 128 warps on 148 SMs, so this config is latency-bound (see step_kernel_sweep for HBM-sized batches)"
                                  % (ROLL_BYTES_PER_ENV_STEP, n * T)},
