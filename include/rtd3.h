@@ -77,7 +77,8 @@ int32_t rtd3_env_dynamics(rtd3_env* h, const float* x, const float* y, const flo
  * every step; x,y are updated to the final state.  State lives in registers across the T steps. */
 int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, float* traj, int64_t n,
                          int64_t T, void* stream);
-/* Test hook: non-zero forces the cp.async variant of the rollout kernel even where the bulk-async one applies. */
+/* Test hook: 1 forces the cp.async variant of the rollout kernel, 2 the single-warp TMA variant (instead of the
+ * warp-pair TMA kernel used for latency-bound batches), 0 restores the automatic choice. */
 void rtd3_env_force_plain_rollout(int32_t on);
 
 /* ------------------------------------------------------------------------------------------------

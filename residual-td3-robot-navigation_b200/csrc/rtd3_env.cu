@@ -380,6 +380,150 @@ env_rollout_tma_kernel(const float2* __restrict__ g_table, float* __restrict__ x
   if (kTraj && lane == 0) bulk_wait<0>();       // the stores must have left shared memory before the CTA exits
 }
 
+// ---- T-step rollout, warp-pair variant: chain warp + helper warp per 32 envs -------------------------------------------
+// At 4096 envs every SM gets one warp, and that warp's issue slots - not memory - bound the TMA kernel above (31
+// instr/step, of which only 13 are the state recurrence; ncu r1: 42 % fixed-latency waits).  Here the recurrence runs
+// alone on the CHAIN warp (per step: one LDS.64 of the pre-clipped action, the 13-instruction chain, two STS of the new
+// state); a HELPER warp on another scheduler of the same SM waits for the TMA action tiles, clips them (or flags the
+// chunk for the careful NaN path), re-arms the loads and issues the trajectory tile stores.  The two meet on mbarriers
+// over double-buffered shared-memory tiles.
+struct PairSmem {
+  static constexpr int kBars = 16;   // full[8] | prepped[2] | consumed[2] | outfull[2] | outfree[2]
+};
+
+template <bool kTraj, int kStages>
+__global__ void __launch_bounds__(256)
+env_rollout_pair_kernel(const float2* __restrict__ g_table, float* __restrict__ x, float* __restrict__ y,
+                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_traj, int64_t n, int64_t T) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* s_table = reinterpret_cast<float2*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, npairs = blockDim.x >> 6;
+  const int pair = warp >> 1;
+  const bool is_chain = (warp & 1) == 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes + 16) + pair * PairSmem::kBars;
+  uint64_t* full = bars, *prepped = bars + 8, *consumed = bars + 10, *outfull = bars + 12, *outfree = bars + 14;
+  // per pair: kStages raw tiles | 2 prepped tiles (float2 per step and env = 2 tiles' worth each... [kU][32] float2 = 4 KB) | 2 out tiles
+  float* tiles = reinterpret_cast<float*>(smem_raw + ((kTableBytes + 16 + npairs * PairSmem::kBars * 8 + 127) & ~127u));
+  float* my = tiles + (size_t)pair * (kStages + 4) * kTileFloats;
+  float* raw = my;                                   // [kStages][kU*2][32]
+  float2* prep = reinterpret_cast<float2*>(my + kStages * kTileFloats);                 // [2][kU][32]
+  float* outt = my + (kStages + 2) * kTileFloats;    // [2][kU*2][32]
+  __shared__ int s_flag[4][2];                       // careful flag per pair and prepped buffer
+  if (lane == 0 && is_chain) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(prepped + b, 32); mbar_init(consumed + b, 32); mbar_init(outfull + b, 32); mbar_init(outfree + b, 1); }
+    fence_mbar_init();
+  }
+  stage_table(s_table, bar, g_table);   // contains the __syncthreads that publishes the barrier inits
+
+  const int64_t i0 = ((int64_t)blockIdx.x * npairs + pair) * 32;
+  if (i0 >= n) return;
+  const int64_t chunks = (T + kU - 1) / kU;
+
+  if (!is_chain) {
+    // ================================= helper warp =================================
+    auto issue_load = [&](int64_t c) {
+      if (c < chunks && lane == 0) {
+        const int s = (int)(c % kStages);
+        mbar_arrive_expect_tx(full + s, kTileFloats * 4);
+        tma_load_2d(raw + s * kTileFloats, &tm_act, (int)i0, (int)(c * (2 * kU)), full + s);
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) issue_load(s);
+    for (int64_t c = 0; c < chunks; ++c) {
+      const int s = (int)(c % kStages), b = (int)(c & 1);
+      mbar_wait(full + s, (uint32_t)((c / kStages) & 1));
+      mbar_wait(consumed + b, (uint32_t)(((c >> 1) & 1) ^ 1));       // the chain warp is done with prepped tile b (first two pass)
+      const float* tin = raw + s * kTileFloats + lane;
+      float ax[kU], ay[kU], nanacc = 0.0f;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        ax[u] = tin[(2 * u) * 32];
+        ay[u] = tin[(2 * u + 1) * 32];
+        nanacc = fmaf(ax[u], 0.0f, nanacc);
+        nanacc = fmaf(ay[u], 0.0f, nanacc);
+      }
+      const bool careful = __any_sync(0xffffffffu, nanacc != 0.0f) || (T - c * kU) < kU;
+      float2* tp = prep + b * (kU * 32) + lane;
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        tp[u * 32] = careful ? make_float2(ax[u], ay[u])
+                             : make_float2(fminf(fmaxf(ax[u], -kMaxAction), kMaxAction), fminf(fmaxf(ay[u], -kMaxAction), kMaxAction));
+      if (lane == 0) s_flag[pair][b] = careful ? 1 : 0;
+      __syncwarp();
+      issue_load(c + kStages);                                       // raw stage s is in registers / prepped now
+      mbar_arrive(prepped + b);
+      if (kTraj && c >= 1) {                                         // trajectory tile of the previous chunk
+        const int pb = (int)((c - 1) & 1);
+        mbar_wait(outfull + pb, (uint32_t)(((c - 1) >> 1) & 1));
+        fence_proxy_async();
+        if (lane == 0) {
+          tma_store_2d(&tm_traj, (int)i0, (int)((c - 1) * (2 * kU)), outt + pb * kTileFloats);
+          bulk_commit();
+          bulk_wait_read<1>();                                       // the store of chunk c-2 has read its tile ...
+          if (c >= 2) mbar_arrive(outfree + (int)(c & 1));           // ... which is the tile chunk c will write
+        }
+        __syncwarp();
+      }
+    }
+    if (kTraj) {
+      const int pb = (int)((chunks - 1) & 1);
+      mbar_wait(outfull + pb, (uint32_t)(((chunks - 1) >> 1) & 1));
+      fence_proxy_async();
+      if (lane == 0) {
+        tma_store_2d(&tm_traj, (int)i0, (int)((chunks - 1) * (2 * kU)), outt + pb * kTileFloats);
+        bulk_commit();
+        bulk_wait<0>();
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ================================= chain warp =================================
+  const int64_t i = i0 + lane;
+  const bool live = i < n;
+  float sx = live ? fminf(fmaxf(x[i], 0.0f), 99.99999f) : 0.0f;
+  float sy = live ? fminf(fmaxf(y[i], 0.0f), 99.99999f) : 0.0f;
+  const uint32_t addr_bias = smem_u32(s_table) - 0x4B000000u * 808u;
+  mbar_wait(bar, 0);
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int b = (int)(c & 1);
+    mbar_wait(prepped + b, (uint32_t)((c >> 1) & 1));
+    if (kTraj && c >= 2) mbar_wait(outfree + b, (uint32_t)(((c >> 1) - 1) & 1));   // out tile b has been stored (chunk c-2)
+    const bool careful = s_flag[pair][b] != 0;
+    const float2* tp = prep + b * (kU * 32) + lane;
+    float* tout = outt + b * kTileFloats + lane;
+    if (!careful) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const float2 a = tp[u * 32];
+        StepIn in;
+        in.ax = a.x; in.ay = a.y; in.lo = 0.0f; in.hi = kClipHi; in.bad = false;
+        rollout_step(addr_bias, in, sx, sy);
+        if (kTraj) { tout[(2 * u) * 32] = sx; tout[(2 * u + 1) * 32] = sy; }
+      }
+    } else {
+      const int steps = (int)min((int64_t)kU, T - c * kU);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (u < steps) {
+          const float2 a = tp[u * 32];
+          const StepIn in = prep_action(a.x, a.y);
+          rollout_step(addr_bias, in, sx, sy);
+        }
+        if (kTraj) { tout[(2 * u) * 32] = sx; tout[(2 * u + 1) * 32] = sy; }
+      }
+    }
+    mbar_arrive(consumed + b);
+    if (kTraj) mbar_arrive(outfull + b);
+  }
+  if (live) { x[i] = sx; y[i] = sy; }
+}
+
 // ---- seeded init / reset on per-env legacy MT19937 streams ------------------------------------
 __global__ void mt_seed_kernel(rtd3_mt_bank b, const uint32_t* __restrict__ seeds) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,6 +608,7 @@ static int32_t check_bank(const rtd3_mt_bank* b) {
 using namespace rtd3;
 
 static bool g_force_plain_rollout = false;
+static int g_rollout_variant = 0;            // test hook: 1 = single-warp TMA kernel instead of the warp-pair kernel
 
 // cuTensorMapEncodeTiled comes from the driver (libcuda); it is looked up at run time so that librtd3.so links against
 // the runtime only.  If the lookup fails the rollout falls back to the cp.async kernel.
@@ -496,7 +641,7 @@ static int32_t make_plane_map(CUtensorMap* tm, const float* base, int64_t n, int
 
 extern "C" {
 
-void rtd3_env_force_plain_rollout(int32_t on) { g_force_plain_rollout = on != 0; }
+void rtd3_env_force_plain_rollout(int32_t on) { g_force_plain_rollout = on == 1; g_rollout_variant = on == 2 ? 1 : 0; }
 
 int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   RTD3_CHECK_ARG(out, "out is null");
@@ -518,6 +663,8 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
@@ -605,7 +752,14 @@ int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, 
     const int wpc = deep ? (int)std::max<int64_t>(1, std::min<int64_t>(8, ceil_div(warps_total, (int64_t)h->num_sms))) : 8;
     const int bgrid = (int)ceil_div(warps_total, wpc);
     const int bsmem = ((kTableBytes + 16 + wpc * stages * 8 + 127) & ~127) + wpc * (stages + 2) * kTileFloats * 4;
-    if (deep) {
+    if (deep && g_rollout_variant != 1) {
+      // latency-bound batches: one chain warp + one helper warp per 32 envs, up to 2 pairs per CTA
+      const int ppc = (int)std::max<int64_t>(1, std::min<int64_t>(2, ceil_div(warps_total, (int64_t)h->num_sms)));
+      const int pgrid = (int)ceil_div(warps_total, ppc);
+      const int psmem = ((kTableBytes + 16 + ppc * PairSmem::kBars * 8 + 127) & ~127) + ppc * (kDeep + 4) * kTileFloats * 4;
+      if (traj) env_rollout_pair_kernel<true, kDeep><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+      else env_rollout_pair_kernel<false, kDeep><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+    } else if (deep) {
       if (traj) env_rollout_tma_kernel<true, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
       else env_rollout_tma_kernel<false, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
     } else {

@@ -164,14 +164,15 @@ def test_rollout_teacher_forced_vs_golden_trajectory(pkg, env_golden):
         assert_state_close(out, ref)
 
 
-@pytest.mark.parametrize("plain", [False, True])
+@pytest.mark.parametrize("plain", [0, 1, 2])
 @pytest.mark.parametrize("n,T", [(8, 32), (4096, 50), (1000, 17), (70000, 33), (65536, 40), (4096, 1000), (32, 16), (64, 15)])
 def test_rollout_equals_repeated_steps(pkg, env_golden, n, T, plain):
-    """Both rollout kernels (bulk-async tiles for n % 32 == 0, per-thread cp.async otherwise / when forced)."""
+    """All rollout kernels: 0 = automatic (warp-pair TMA kernel for latency-bound sizes, single-warp TMA for large ones),
+    1 = per-thread cp.async ring (also the fallback for n % 4 != 0), 2 = single-warp TMA kernel everywhere."""
     g = env_golden
-    if T == 1000 and plain:
-        pytest.skip("long case once")
-    pkg._lib.lib().rtd3_env_force_plain_rollout(1 if plain else 0)
+    if T == 1000 and plain == 1:
+        pytest.skip("long case once per TMA variant")
+    pkg._lib.lib().rtd3_env_force_plain_rollout(plain)
     try:
         _rollout_vs_steps(pkg, g, n, T)
     finally:
