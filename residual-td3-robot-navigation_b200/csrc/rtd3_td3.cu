@@ -1,5 +1,7 @@
 // Residual-TD3 learner hot path: replay ring, minibatch gather, twin-critic / actor steps, Adam + Polyak.
 // Reference behaviour: /root/reference/robot.py:58-124 (ReplayBuffer), :128-206 (networks), :258-398 (TD3).
+#include <cstdlib>
+
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
 
@@ -441,8 +443,8 @@ static bool shape_ok(const NetShape& s) {
 
 using namespace rtd3;
 
-constexpr int kNumTiles = 3;
-static const int kRowTiles[kNumTiles] = {4, 8, 16};
+constexpr int kNumTiles = 4;
+static const int kRowTiles[kNumTiles] = {2, 4, 8, 16};
 
 struct rtd3_td3 {
   Arena ar;
@@ -453,10 +455,13 @@ struct rtd3_td3 {
 
 // Rows per CTA: few rows while the batch cannot fill the SMs (latency-bound), more rows once it can (every CTA
 // re-streams all weights from L2, so larger tiles cut that traffic).
+static int g_tile_override = -1;   // development hook (RTD3_TILE environment variable): force a row-tile index
 static inline int pick_tile(int64_t B, int num_sms) {
-  if (B <= 4 * (int64_t)num_sms) return 0;
-  if (B <= 16 * (int64_t)num_sms) return 1;
-  return 2;
+  if (g_tile_override >= 0) return g_tile_override;
+  if (B <= 2 * (int64_t)num_sms) return 0;
+  if (B <= 4 * (int64_t)num_sms) return 1;
+  if (B <= 16 * (int64_t)num_sms) return 2;
+  return 3;
 }
 
 static size_t actor_phase_smem(const Arena& ar, int R) {
@@ -502,15 +507,19 @@ int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t 
     h->smem_actor[i] = actor_phase_smem(h->ar, R);
     h->smem_fwd[i] = mlp_smem_bytes(R, hidden, 0);
   }
-  RTD3_CUDA(set_smem(td3_critic_kernel<4>, h->smem_critic[0]));
-  RTD3_CUDA(set_smem(td3_critic_kernel<8>, h->smem_critic[1]));
-  RTD3_CUDA(set_smem(td3_critic_kernel<16>, h->smem_critic[2]));
-  RTD3_CUDA(set_smem(td3_actor_kernel<4>, h->smem_actor[0]));
-  RTD3_CUDA(set_smem(td3_actor_kernel<8>, h->smem_actor[1]));
-  RTD3_CUDA(set_smem(td3_actor_kernel<16>, h->smem_actor[2]));
-  RTD3_CUDA(set_smem(mlp_forward_kernel<4>, h->smem_fwd[0]));
-  RTD3_CUDA(set_smem(mlp_forward_kernel<8>, h->smem_fwd[1]));
-  RTD3_CUDA(set_smem(mlp_forward_kernel<16>, h->smem_fwd[2]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<2>, h->smem_critic[0]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<4>, h->smem_critic[1]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<8>, h->smem_critic[2]));
+  RTD3_CUDA(set_smem(td3_critic_kernel<16>, h->smem_critic[3]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<2>, h->smem_actor[0]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<4>, h->smem_actor[1]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<8>, h->smem_actor[2]));
+  RTD3_CUDA(set_smem(td3_actor_kernel<16>, h->smem_actor[3]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<2>, h->smem_fwd[0]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<4>, h->smem_fwd[1]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<8>, h->smem_fwd[2]));
+  RTD3_CUDA(set_smem(mlp_forward_kernel<16>, h->smem_fwd[3]));
+  if (const char* e = getenv("RTD3_TILE")) g_tile_override = atoi(e);
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;
@@ -553,7 +562,7 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* para
   cudaStream_t st = (cudaStream_t)stream;
 #define RTD3_CRITIC(RR) \
   td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
-  if (ti == 0) RTD3_CRITIC(4); else if (ti == 1) RTD3_CRITIC(8); else RTD3_CRITIC(16);
+  if (ti == 0) RTD3_CRITIC(2); else if (ti == 1) RTD3_CRITIC(4); else if (ti == 2) RTD3_CRITIC(8); else RTD3_CRITIC(16);
 #undef RTD3_CRITIC
   RTD3_LAUNCHED();
   WgradSlots slots;
@@ -573,7 +582,7 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* param
   const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
 #define RTD3_ACTOR(RR) td3_actor_kernel<RR><<<grid, kThreads, h->smem_actor[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows)
-  if (ti == 0) RTD3_ACTOR(4); else if (ti == 1) RTD3_ACTOR(8); else RTD3_ACTOR(16);
+  if (ti == 0) RTD3_ACTOR(2); else if (ti == 1) RTD3_ACTOR(4); else if (ti == 2) RTD3_ACTOR(8); else RTD3_ACTOR(16);
 #undef RTD3_ACTOR
   RTD3_LAUNCHED();
   WgradSlots slots;
@@ -606,7 +615,7 @@ int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const fl
   const int grid = (int)((batch + R - 1) / R);
   cudaStream_t st = (cudaStream_t)stream;
 #define RTD3_FWD(RR) mlp_forward_kernel<RR><<<grid, kThreads, h->smem_fwd[ti], st>>>(s, params + h->ar.off(net), params_t + h->ar.off(net), x, y, (int)batch)
-  if (ti == 0) RTD3_FWD(4); else if (ti == 1) RTD3_FWD(8); else RTD3_FWD(16);
+  if (ti == 0) RTD3_FWD(2); else if (ti == 1) RTD3_FWD(4); else if (ti == 2) RTD3_FWD(8); else RTD3_FWD(16);
 #undef RTD3_FWD
   RTD3_LAUNCHED();
   return 0;
