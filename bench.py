@@ -216,28 +216,33 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         rb.push(s, a, r, s2, (torch.arange(n, device=dev) % 50) == 49)
         if B > n:
             rb.sampler = "philox"                         # with replacement: the exact sampler needs batch <= rows
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        reps, ms_s, ms_u = 4, [], []
-        for rep in range(reps):                           # rep 0 captures the graph / warms up
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        reps, ms_s, ms_u, ms_full = 4, [], [], []
+        for rep in range(reps):                           # rep 0 captures the graphs / warms up
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
             ev[0].record()
-            idx = rb.sample_indices(B, epochs + (epochs + 1) // 2)
+            idx = rb.sample_indices(B, epochs + (epochs + 1) // 2)      # the index draw alone ...
             ev[1].record()
-            agent.td3_update(rb, idx=idx)
+            agent.td3_update(rb, idx=idx)                               # ... the update alone ...
             ev[2].record()
             torch.cuda.synchronize(dev)
+            ev[3].record()
+            agent.td3_update(rb)                                        # ... and the call a user makes: draw + update, pipelined
+            ev[4].record()
+            torch.cuda.synchronize(dev)
             if rep > 0:
-                ms_s.append(ev[0].elapsed_time(ev[1])); ms_u.append(ev[1].elapsed_time(ev[2]))
-        t = torch.tensor([float(np.median(ms_s)), float(np.median(ms_u))], device=dev, dtype=torch.float64)
+                ms_s.append(ev[0].elapsed_time(ev[1])); ms_u.append(ev[1].elapsed_time(ev[2])); ms_full.append(ev[3].elapsed_time(ev[4]))
+        t = torch.tensor([float(np.median(ms_s)), float(np.median(ms_u)), float(np.median(ms_full))], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_sample, ms_update = float(t[0]), float(t[1])
+        ms_sample, ms_update, ms_call = float(t[0]), float(t[1]), float(t[2])
         flops = td3_flops_per_epoch(B * world, H, L) * epochs
         row = {"shape": label, "global_batch": B * world, "epochs": epochs, "sampler": rb.sampler,
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
-               "updates_per_sec": epochs / ((ms_update + ms_sample) * 1e-3), "updates_per_sec_update_only": epochs / (ms_update * 1e-3),
+               "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
+               "updates_per_sec_update_only": epochs / (ms_update * 1e-3),
                "tflops_fp32": flops / (ms_update * 1e-3) / 1e12,
                "frac_of_nominal_fp32_peak": flops / (ms_update * 1e-3) / 1e12 / (FP32_FFMA_PEAK_TFLOPS * world)}
         if cpu and rank == 0 and world == 1:

@@ -69,6 +69,7 @@ class ReplayBuffer:
         if seed is not None:
             self._bank.seed(seed)
         self._scratch = None
+        self._in_session = False
 
     def _total(self):
         if self._host_stale:
@@ -133,13 +134,25 @@ class ReplayBuffer:
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty((need,), dtype=torch.int32, device=self.device)
         scratch = self._scratch
-        if self._numpy_global:
+        if self._numpy_global and not self._in_session:
             self._bank.sync_from_numpy()
         _lib.check(_lib.lib().rtd3_sample_indices_mt19937(self._bank.ref, 0, self.size, batch_size, count, _lib.ptr(out),
                                                           _lib.ptr(scratch), _lib.stream_ptr(self.device)), "sample_indices")
-        if self._numpy_global:
+        if self._numpy_global and not self._in_session:
             self._bank.sync_to_numpy()
         return out
+
+    def begin_sampling_session(self):
+        """Several sample_indices calls in a row (a TD3 update draws its index sets in chunks): mirror numpy's global stream
+        into the device bank once at the start and back once at the end instead of around every call."""
+        if self._numpy_global:
+            self._bank.sync_from_numpy()
+        self._in_session = True
+
+    def end_sampling_session(self):
+        self._in_session = False
+        if self._numpy_global:
+            self._bank.sync_to_numpy()
 
     def gather(self, idx):
         B = idx.numel()
@@ -323,6 +336,8 @@ class TD3:
             self.world = dist.get_world_size(process_group)
         self.last_losses = None
         self._u_stale = True
+        self._side_stream = None
+        self.sample_chunk_epochs = 10       # epochs per pipelined chunk of td3_update (0 = draw all index sets up front)
         self._graphs = {}
         if self.world > 1:                  # initialise the communicator outside of any graph capture
             import torch.distributed as dist
@@ -480,9 +495,16 @@ class TD3:
     def td3_update(self, replay_buffer, noise=None, idx=None, use_graph=True):
         """robot.py:258-285: `num_epochs` critic steps, an actor step + the three Polyak updates every
         `policy_update_delay`-th epoch.  Returns (critic_losses `[E,2]`, actor_losses `[E_actor]`) as device tensors -
-        the values the reference collects at robot.py:274-280.  The whole loop is one CUDA graph (captured on first use per
-        replay buffer / shape), so an update is a single host call: index draw, noise draw, graph launch."""
+        the values the reference collects at robot.py:274-280.
+
+        The epoch loop is a CUDA graph.  When the index sets are drawn here (idx is None) the update is pipelined in chunks
+        of `sample_chunk_epochs` epochs: the exact MT19937 index draw of chunk g+1 runs on a side stream (it needs one SM)
+        while chunk g trains, so its cost hides behind the training kernels instead of preceding them."""
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
+        C = self.sample_chunk_epochs
+        if (idx is None and use_graph and self.world == 1 and C > 0 and E % C == 0 and C % delay == 0 and E > C
+                and len(replay_buffer) >= B):
+            return self._td3_update_pipelined(replay_buffer, noise, C)
         n_actor = len([e for e in range(E) if e % delay == 0])
         count = E + n_actor
         if idx is None:
@@ -490,38 +512,93 @@ class TD3:
             if idx is None:
                 raise TypeError("cannot unpack non-iterable NoneType object")
         B = idx.shape[1]
-        key = (id(replay_buffer), E, B, delay)
-        st = self._graphs.get(key)
-        if st is None:
-            st = {"idx": torch.zeros((count, B), dtype=torch.int32, device=self.device),
-                  "noise": torch.zeros((E, B, 2), dtype=torch.float32, device=self.device),
-                  "closs": torch.zeros((E, 2), dtype=torch.float32, device=self.device),
-                  "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None}
-            self._row_scratch(B)
-            self._graphs[key] = st
+        st = self._update_state(replay_buffer, E, B, delay)
         self.sync_transposed(force=False)
         st["idx"].copy_(idx)
         if noise is None:
             st["noise"].normal_()                                     # torch.randn_like, robot.py:338 (unseeded there)
         else:
             st["noise"].copy_(noise)
-        # NCCL collectives are issued eagerly between the kernels: the data-parallel loop is not graph-captured
-        if use_graph and self.world == 1:
-            if st["graph"] is None:
-                graph = torch.cuda.CUDAGraph()
-                before = _lib.launch_count()
-                with torch.cuda.graph(graph):
-                    st["closs"].zero_()
-                    st["aloss"].zero_()
-                    self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
-                st["graph"] = graph
-                st["launches"] = _lib.launch_count() - before      # kernels inside the graph (capture itself ran none)
-                _lib.lib().rtd3_launch_count_add(-st["launches"])
-            st["graph"].replay()
-            _lib.lib().rtd3_launch_count_add(st["launches"])
-        else:
-            st["closs"].zero_()
-            st["aloss"].zero_()
-            self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+        self._launch_epochs(replay_buffer, st, use_graph, E)
         self.last_losses = (st["closs"], st["aloss"][:n_actor])
+        return self.last_losses
+
+    def _update_state(self, replay_buffer, E, B, delay):
+        """Persistent buffers (and, once captured, the CUDA graph) of an E-epoch block for this replay buffer / batch size."""
+        n_actor = len([e for e in range(E) if e % delay == 0])
+        key = (id(replay_buffer), E, B, delay)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"idx": torch.zeros((E + n_actor, B), dtype=torch.int32, device=self.device),
+                  "noise": torch.zeros((E, B, 2), dtype=torch.float32, device=self.device),
+                  "closs": torch.zeros((E, 2), dtype=torch.float32, device=self.device),
+                  "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None, "launches": 0}
+            self._row_scratch(B)
+            self._graphs[key] = st
+        return st
+
+    def _launch_epochs(self, replay_buffer, st, use_graph, E):
+        saved, self.num_epochs = self.num_epochs, E
+        try:
+            # NCCL collectives are issued eagerly between the kernels: the data-parallel loop is not graph-captured
+            if use_graph and self.world == 1:
+                if st["graph"] is None:
+                    graph = torch.cuda.CUDAGraph()
+                    before = _lib.launch_count()
+                    with torch.cuda.graph(graph):
+                        st["closs"].zero_()
+                        st["aloss"].zero_()
+                        self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+                    st["graph"] = graph
+                    st["launches"] = _lib.launch_count() - before      # kernels inside the graph (capture itself ran none)
+                    _lib.lib().rtd3_launch_count_add(-st["launches"])
+                st["graph"].replay()
+                _lib.lib().rtd3_launch_count_add(st["launches"])
+            else:
+                st["closs"].zero_()
+                st["aloss"].zero_()
+                self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+        finally:
+            self.num_epochs = saved
+
+    def _td3_update_pipelined(self, replay_buffer, noise, C):
+        E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
+        chunks = E // C
+        n_actor_c = len([e for e in range(C) if e % delay == 0])
+        per_chunk = C + n_actor_c
+        st = self._update_state(replay_buffer, C, B, delay)
+        closs = torch.empty((E, 2), dtype=torch.float32, device=self.device)
+        aloss = torch.empty((chunks * n_actor_c,), dtype=torch.float32, device=self.device)
+        if noise is None:
+            noise = self._noise((E, B, 2))
+        self.sync_transposed(force=False)
+        main = torch.cuda.current_stream(self.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_stream(main)                                # the replay rows pushed so far are visible to the sampler
+        replay_buffer.begin_sampling_session()
+        try:
+            def draw(g):
+                with torch.cuda.stream(side):
+                    out = replay_buffer.sample_indices(B, per_chunk)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                return out, ev
+            nxt = draw(0)
+            for g in range(chunks):
+                idx_g, ev = nxt
+                main.wait_event(ev)
+                st["idx"].copy_(idx_g)
+                st["noise"].copy_(noise[g * C:(g + 1) * C])
+                idx_g.record_stream(main)
+                if g + 1 < chunks:
+                    nxt = draw(g + 1)                          # runs while chunk g trains (it only touches its scratch and the RNG bank)
+                self._launch_epochs(replay_buffer, st, True, C)
+                closs[g * C:(g + 1) * C].copy_(st["closs"])
+                aloss[g * n_actor_c:(g + 1) * n_actor_c].copy_(st["aloss"][:n_actor_c])
+            main.wait_stream(side)
+        finally:
+            replay_buffer.end_sampling_session()
+        self.last_losses = (closs, aloss)
         return self.last_losses

@@ -224,3 +224,34 @@ def test_sample_indices_exact_for_many_sizes(pkg, n):
     got2 = rb.sample_indices(n, 2).cpu().numpy()          # full permutations, stream continues
     exp2 = np.stack([rs.choice(n, n, replace=False) for _ in range(2)])
     assert (got2 == exp2).all()
+
+
+def test_pipelined_update_equals_unpipelined(pkg, td3_golden):
+    """td3_update drawing its index sets in chunks on a side stream (overlapped with training) gives exactly the result of
+    drawing all of them up front: same MT19937 stream, same epochs."""
+    g = td3_golden
+    outs = []
+    for chunk in (0, 10):
+        agent, rb = make_agent(pkg, g), fill_replay(pkg, g, seed=42)
+        agent.num_epochs, agent.sample_chunk_epochs = 30, chunk
+        noise = torch.randn((30, agent.batch_size, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+        closs, aloss = agent.td3_update(rb, noise=noise)
+        outs.append((closs.clone(), aloss.clone(), agent.params.clone(), rb.sample_indices(5, 1).clone()))
+    # losses are summed over CTAs with float atomics (order varies run to run); parameters are deterministic
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=0)
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-5, atol=0)
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][3], outs[1][3])             # the RNG stream ends at the same position
+
+
+def test_pipelined_update_numpy_global_stream(pkg, td3_golden):
+    g = td3_golden
+    agent, rb = make_agent(pkg, g), fill_replay(pkg, g, seed=None)     # unseeded: numpy's global stream, like the reference
+    agent.num_epochs = 20
+    np.random.seed(123)
+    agent.td3_update(rb)
+    after = np.random.uniform()
+    rs = np.random.RandomState(123)
+    for _ in range(30):                                                # 20 critic + 10 actor draws (robot.py:326, 382)
+        rs.choice(len(rb), agent.batch_size, replace=False)
+    assert after == rs.uniform()
