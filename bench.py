@@ -423,9 +423,8 @@ def run_b200(args):
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step(k):
-        d_act = h_act[k % 2].to(dev, non_blocking=True)
-        traj = env.rollout(d_act, record=True)                         # public API ([T,2,N] planes in, [T,N,2] view out)
-        h_traj[k % 2].copy_(traj.permute(0, 2, 1), non_blocking=True)
+        # the public host-buffer API: pinned actions in, pinned trajectory out, copies pipelined with the kernel inside the call
+        env.rollout_host(h_act[k % 2], h_traj[k % 2])
 
     for k in range(3):
         e2e_step(k)

@@ -65,6 +65,8 @@ class Environment:
         if not self._numpy_global:
             self._bank.seed(configuration.RANDOM_SEED if seed is None else seed)
         self.step_variant = STEP_AUTO
+        self._pipe = None
+        self._pipe_buf = None
         self.set_init_and_goal()
         if maps is None:
             self.set_dynamics()
@@ -188,6 +190,54 @@ class Environment:
                                                _lib.ptr(planes), _lib.ptr(traj), n, T,
                                                _lib.stream_ptr(self.device)), "env_rollout")
         return traj.permute(0, 2, 1) if record else None
+
+    def rollout_host(self, actions_host, out_host=None, chunks=8):
+        """`rollout` for HOST buffers: `actions_host` pinned float32 `[T,2,N]` (planes), `out_host` pinned `[T,2,N]` or None.
+        The T steps are cut into `chunks` time slices; the host->device copy of slice c+1, the rollout kernel of slice c and
+        the device->host copy of slice c-1 run on three streams, so a call costs about one PCIe transfer of the larger
+        direction instead of copy + kernel + copy in sequence.  Returns `out_host` (a fresh pinned tensor if None was given);
+        the call returns once the result is on the host."""
+        n = self.num_envs
+        if actions_host.dim() != 3 or actions_host.shape[1:] != (2, n) or actions_host.dtype != torch.float32:
+            raise ValueError("actions_host must be float32 [T,2,%d]" % n)
+        T = actions_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty((T, 2, n), dtype=torch.float32).pin_memory()
+        if self._pipe is None:
+            self._pipe = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        s_in, s_out = self._pipe
+        main = torch.cuda.current_stream(self.device)
+        if self._pipe_buf is None or self._pipe_buf[0].shape != (T, 2, n):
+            self._pipe_buf = (torch.empty((T, 2, n), dtype=torch.float32, device=self.device),
+                              torch.empty((T, 2, n), dtype=torch.float32, device=self.device))
+        d_act, d_traj = self._pipe_buf
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        bounds = [round(c * T / chunks) for c in range(chunks + 1)]
+        ev_in = []
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            with torch.cuda.stream(s_in):
+                d_act[lo:hi].copy_(actions_host[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+            ev_in.append(e)
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi == lo:
+                continue
+            main.wait_event(ev_in[c])
+            _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
+                                                   _lib.ptr(d_act[lo:hi]), _lib.ptr(d_traj[lo:hi]), n, hi - lo,
+                                                   _lib.stream_ptr(self.device)), "env_rollout")
+            e = torch.cuda.Event()
+            e.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                out_host[lo:hi].copy_(d_traj[lo:hi], non_blocking=True)
+        main.wait_stream(s_out)
+        main.synchronize()
+        return out_host
 
     # ---- environment.py:130-137 ---------------------------------------------------------------------
     def reset(self, mask=None):

@@ -241,3 +241,18 @@ def test_full_size_properties(pkg):
     env.step_variant = 2
     s2 = env.step(a.t())
     assert torch.equal(s1, s2)                            # both table paths agree bit for bit
+
+
+def test_rollout_host_equals_device_rollout(pkg, env_golden):
+    g = env_golden
+    n, T = 4096, 100
+    env_a = pkg.Environment(num_envs=n, seed=3, maps=(g["speed"], g["angle"]))
+    env_b = pkg.Environment(num_envs=n, seed=3, maps=(g["speed"], g["angle"]))
+    env_a.reset(); env_b.reset()
+    h_act = (torch.rand((T, 2, n)) * 15 - 7.5).pin_memory()
+    out = env_a.rollout_host(h_act, chunks=7)
+    ref = env_b.rollout(h_act.cuda())
+    assert torch.equal(out.cuda().permute(0, 2, 1), ref)
+    assert torch.equal(env_a.robot_state, env_b.robot_state)
+    out2 = torch.empty((T, 2, n)).pin_memory()
+    assert env_a.rollout_host(h_act, out2, chunks=1) is out2
