@@ -482,12 +482,12 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "batched dynamics rollout: %d envs x %d steps per GPU, random actions U(-7.5,7.5) (configs[1])" % (n, T),
-                       "envs_per_gpu": n, "rollout_steps": T, "kernel": "env_rollout_kernel<traj>",
+                       "envs_per_gpu": n, "rollout_steps": T, "kernel": "env_rollout_pair_kernel<traj> (TMA tiles, chain + helper warp per 32 envs)",
                        "l2": "inputs rotate over %d action + %d trajectory buffers (%.0f MB > 126 MB L2)" % (R, R, 2 * R * per_buf / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": (ROLLOUT_NCU_DRAM_BYTES if (n == ENVS and T == T_STEPS) else None), "peak_kind": peak_kind,
                          "note": "%d B per env-step (action in 8 B, state out 8 B; state lives in registers) x %d env-steps per launch; "
-                                 "4096 envs = 128 warps on 148 SMs, so this config is latency-bound (see step_kernel_sweep for HBM-sized batches)"
+                                 "4096 envs = 128 chain warps (+128 helper warps) on 148 SMs: one dependent chain per SM, so this config is latency-bound (see step_kernel_sweep for HBM-sized batches)"
                                  % (ROLL_BYTES_PER_ENV_STEP, n * T)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": per_buf, "d2h_bytes_per_step": per_buf,

@@ -57,18 +57,30 @@ __device__ void mt_regenerate_warp(uint32_t* mt, int lane) {
 // range crosses a power of two are maybes too; the round is sized (32..256) so that there are at most 32 of those.  One
 // block scan ranks the sure draws; thread 0 then resolves the few maybes in order with their exact bounds, and a second
 // pass adds the accepted maybes into every thread's rank.  The round ends early at the draw that completes a sample.
-constexpr int kSampleThreads = 256;
+#ifndef RTD3_SAMPLE_THREADS
+#define RTD3_SAMPLE_THREADS 256
+#endif
+constexpr int kSampleThreads = RTD3_SAMPLE_THREADS;
+constexpr int kSampleWarps = kSampleThreads / 32;
 
 __device__ __forceinline__ void mt_regenerate_block(uint32_t* mt, uint32_t* raw, int t) {
   constexpr int N = RTD3_MT_N, M = 397;
   const int lo[3] = {0, N - M, 2 * (N - M)}, hi[3] = {N - M, 2 * (N - M), N};
 #pragma unroll
   for (int ph = 0; ph < 3; ++ph) {               // every range reads only words finished by earlier ranges (or still old)
-    const int kk = lo[ph] + t;
-    uint32_t v = 0;
-    if (kk < hi[ph]) v = mt_twist(mt[kk], mt[kk + 1 < N ? kk + 1 : 0], mt[kk + M < N ? kk + M : kk + M - N]);
+    // a range is at most 227 words: with fewer threads each one handles several, all read before any is written
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = lo[ph] + t + q * kSampleThreads;
+      v[q] = (kk < hi[ph]) ? mt_twist(mt[kk], mt[kk + 1 < N ? kk + 1 : 0], mt[kk + M < N ? kk + M : kk + M - N]) : 0u;
+    }
     __syncthreads();
-    if (kk < hi[ph]) mt[kk] = v;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = lo[ph] + t + q * kSampleThreads;
+      if (kk < hi[ph]) mt[kk] = v[q];
+    }
     __syncthreads();
   }
   for (int k = t; k < N; k += kSampleThreads) raw[k] = mt_temper(mt[k]);
@@ -119,7 +131,7 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
       __syncthreads();
       int S = __popc(bs & lt), mpos = __popc(bm & lt), total_sure = 0, total_maybe = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < kSampleWarps; ++w) {
         if (w < warp) { S += w_sure[par][w]; mpos += w_maybe[par][w]; }
         total_sure += w_sure[par][w];
         total_maybe += w_maybe[par][w];
@@ -158,7 +170,7 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
         __syncthreads();
         int before = __popc(ba & lt);
 #pragma unroll
-        for (int w = 0; w < 8; ++w)
+        for (int w = 0; w < kSampleWarps; ++w)
           if (w < warp) before += w_macc[par][w];
         rank = S + before;
         if (maybe) {
