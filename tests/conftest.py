@@ -44,3 +44,8 @@ def td3_golden():
 @pytest.fixture(scope="session")
 def robot_golden():
     return load_golden("robot_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def trace_golden():
+    return load_golden("trace_golden.npz")

@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference (build container only).
 
-    python tests/golden/make_golden.py [env|replay|td3|robot|all]
+    python tests/golden/make_golden.py [env|replay|td3|robot|all]      (and: trace - the configs[0] driver-loop trace)
 
 Imports /root/reference/{environment,robot}.py through oracle/ref_loader.py (import stubs only
 for perlin_noise / pyglet / matplotlib, none of which touch hot-path arithmetic) and writes
@@ -348,3 +348,73 @@ if __name__ == "__main__":
         make_td3()
     if what in ("robot", "all"):
         make_robot()
+
+
+def make_trace():
+    """configs[0]: the reference's own driver loop (robot-learning.py:66-101, training branch, without pyglet) on one env:
+    seeded start/goal, three demonstrations, the first episodes and the first TD3 update.  The wall-clock money term is
+    replaced by zero so that the run is deterministic.  Demonstrations, torch-side randomness (initial weights, target
+    noise) and every per-tick observable are recorded."""
+    import torch
+    env_m, rob_m, constants = load_reference()
+    torch.set_num_threads(1)
+    speed, angle = synthetic_maps(0)
+    np.random.seed(SEED0)
+    torch.manual_seed(0)
+    environment = env_m.Environment()
+    environment.dynamics_speed, environment.dynamics_angle = speed, angle
+    state = environment.reset()
+    robot = rob_m.Robot(environment.goal_state)
+    out = {"goal": np.array(environment.goal_state), "region": np.array(environment.robot_init_region), "state0": np.array(state)}
+    for k, net in (("actor", robot.td3_agent.actor_network), ("critic1", robot.td3_agent.critic_network_1), ("critic2", robot.td3_agent.critic_network_2)):
+        out["w_" + k] = _flat_params(net)
+    noises = []
+    real_randn_like = torch.randn_like
+    def capturing_randn_like(t, *a, **kw):
+        z = real_randn_like(t, *a, **kw)
+        noises.append(z.numpy().copy())
+        return z
+    torch.randn_like = capturing_randn_like
+    losses = []
+    real_tc, real_ta = robot.td3_agent.train_critic, robot.td3_agent.train_actor
+    robot.td3_agent.train_critic = lambda rb: (lambda r: (losses.append(("c",) + r), r)[1])(real_tc(rb))
+    robot.td3_agent.train_actor = lambda rb: (lambda r: (losses.append(("a", r)), r)[1])(real_ta(rb))
+    types, states, actions, rewards, dones, demos_s, demos_a = [], [], [], [], [], [], []
+    demos_bought = resets_bought = steps_bought = 0
+    try:
+        for tick in range(130):
+            money = constants.STARTING_MONEY - (demos_bought * constants.COST_PER_DEMO + resets_bought * constants.COST_PER_RESET +
+                                                steps_bought * constants.COST_PER_STEP)
+            action_type = robot.get_next_action_type(state, money)
+            types.append({"step": 0, "demo": 1, "reset": 2}[action_type])
+            act = np.zeros(2)
+            if action_type == "reset":
+                state = environment.reset()
+                resets_bought += 1
+            elif action_type == "demo":
+                ds, da = environment.get_demonstration()
+                demos_s.append(np.array(ds)); demos_a.append(np.array(da))
+                robot.process_demonstration(ds, da, money)
+                demos_bought += 1
+            else:
+                act = robot.get_next_action_training(state, money)
+                next_state = environment.step(act)
+                robot.process_transition(state, act, next_state, money)
+                row = robot.memory.buffer[(robot.memory.position - 1) % robot.memory.capacity]
+                rewards.append(row[2]); dones.append(row[4])
+                state = next_state
+                steps_bought += 1
+            states.append(np.array(state)); actions.append(np.array(act))
+    finally:
+        torch.randn_like = real_randn_like
+    out.update(types=np.array(types), states=np.array(states), actions=np.array(actions), step_rewards=np.array(rewards),
+               step_dones=np.array(dones), demo_states=np.array(demos_s), demo_actions=np.array(demos_a),
+               update_noise=np.array(noises, dtype=np.float32), n_updates=np.int64(len(noises) // 100),
+               critic_losses=np.array([l[1:] for l in losses if l[0] == "c"]), actor_losses=np.array([l[1] for l in losses if l[0] == "a"]),
+               replay_len=np.int64(len(robot.memory)), final_uniform=np.float64(np.random.uniform()))
+    np.savez_compressed(os.path.join(HERE, "trace_golden.npz"), **out)
+    print("trace_golden.npz: types", np.bincount(types), "updates", out["n_updates"], "replay", out["replay_len"])
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
+    make_trace()

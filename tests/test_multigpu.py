@@ -1,0 +1,20 @@
+"""Data-parallel learner on real GPUs (needs >= 2; skipped on the single-GPU box): tools/dp_check.py under torchrun."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(180)
+def test_data_parallel_learner_two_gpus():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=170)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "-> OK" in out.stdout
