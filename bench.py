@@ -467,6 +467,31 @@ def run_b200(args):
                               "env_steps_per_sec": big / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
             del bx, ba
         extra["step_kernel_sweep"] = sweep
+        # the T-step rollout kernel at HBM-sized batches (16 B per env-step: action in, state out)
+        rsweep = []
+        for big, Tb in ((65536, 256), (1 << 20, 64), (1 << 22, 16)):
+            envb = rt.Environment(num_envs=big, seed=5, maps=(speed, angle), device=dev)
+            envb.reset()
+            ab = [torch.rand((Tb, 2, big), device=dev) * 15 - 7.5 for _ in range(2)]
+            tb = torch.empty((Tb, 2, big), dtype=torch.float32, device=dev)
+            def go(k):
+                rt._lib.check(L.rtd3_env_rollout(envb._handle, rt._lib.ptr(envb._state[0]), rt._lib.ptr(envb._state[1]),
+                                                 rt._lib.ptr(ab[k % 2]), rt._lib.ptr(tb), big, Tb, sp))
+            for k in range(2):
+                go(k)
+            torch.cuda.synchronize(dev)
+            reps = 10
+            e0.record(stream)
+            for k in range(reps):
+                go(k)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / reps
+            gbs = big * Tb * ROLL_BYTES_PER_ENV_STEP / (us * 1e-6) / 1e9
+            rsweep.append({"kernel": "env_rollout (auto variant)", "envs": big, "steps": Tb, "us": round(us, 1),
+                           "env_steps_per_sec": big * Tb / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
+            del envb, ab, tb
+        extra["rollout_kernel_sweep"] = rsweep
     td3_rows = None if args.no_td3 else bench_td3(rt, torch, dev, world, rank, cpu=not args.no_cpu)
     fwd_rows = None if (args.no_td3 or rank != 0) else bench_forward(rt, torch, dev)
     loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
