@@ -228,7 +228,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
+#pragma unroll 8
     for (int b = b_lo + warp; b < b_hi; b += 8) {
       const float4 z = n_ok ? __ldg(reinterpret_cast<const float4*>(dz + (int64_t)b * H + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 x0 = k_ok0 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
