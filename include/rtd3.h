@@ -188,10 +188,11 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* param
 /* torch.optim.Adam step (lr, betas 0.9/0.999, eps 1e-8; robot.py:237-239, 356-363, 393-395) on the nets
  * selected by `nets` (bit 0 actor, bit 1 critic1, bit 2 critic2) using grads*grad_scale (grad_scale = 1/world
  * after a gradient all-reduce), zeroing the consumed gradients; then TD3.soft_update (robot.py:293-310)
- * on the target nets selected by `polyak` (same bit layout) with the freshly updated online parameters. */
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* grads, float* adam_m, float* adam_v, const double* beta_pows,
-                             int32_t nets, float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau,
-                             void* stream);
+ * on the target nets selected by `polyak` (same bit layout) with the freshly updated online parameters.
+ * params_uv (nullable): the tensor-core operand copies of the arena (see rtd3_tc_sync_weights), kept in step too. */
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* params_uv, float* grads, float* adam_m, float* adam_v,
+                             const double* beta_pows, int32_t nets, float lr_actor, float lr_critic, float grad_scale, int32_t polyak,
+                             float tau, void* stream);
 
 /* Forward of one network of the arena (robot.py:153-159 / 193-200): x [batch][in] -> y [batch][out]. */
 int32_t rtd3_mlp_forward(rtd3_td3* h, int32_t net, const float* params, const float* params_t, const float* x, float* y,
@@ -243,9 +244,11 @@ int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, i
  * Tensor-core (tcgen05 / TMEM, TF32) large-batch forward - opt-in throughput mode, not the parity path
  * ---------------------------------------------------------------------------------------------- */
 
-/* Rebuild params_u, the chunk-major (UMMA shared-memory operand order) copy of all hidden-layer weights of the
- * arena: Wu[(k/4)*H + n][k%4] = W[n][k]; other entries are copied in place. */
-int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_u, void* stream);
+/* Rebuild params_uv = [u | v] (2 x arena floats), the chunk-major (UMMA shared-memory operand order) copies of all
+ * hidden-to-hidden weights, rounded to TF32 (round to nearest):
+ *   u (forward):         Wu[(k/4)*H + n][k%4] = W[n][k]        v (input gradient):  Wv[(n/4)*H + k][n%4] = W[n][k]
+ * other entries are copied in place. */
+int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_uv, void* stream);
 
 /* Forward of one network (robot.py:153-159 / 193-200) for 128-row batch tiles on the 5th-gen tensor cores:
  * hidden H x H layers as tcgen05.mma.kind::tf32 with fp32 accumulators in TMEM, first / output layer in fp32.
@@ -253,6 +256,22 @@ int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params
  * to TF32 round-off (~1e-3 relative). */
 int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, int64_t param_off, const float* params,
                               const float* params_u, const float* x, float* y, int64_t batch, void* stream);
+
+/* 1 if the tensor-core learner steps below support this handle's shape (layers == 2, hidden 128 or 256). */
+int32_t rtd3_td3_tf32_supported(const rtd3_td3* h);
+
+/* rtd3_td3_critic_step / rtd3_td3_actor_step (robot.py:312-366, 369-398) for large batches on the tensor cores:
+ * 64-row batch tiles, hidden products (forward, input gradient, weight gradient) as tcgen05.mma.kind::tf32 with
+ * accumulators in TMEM, weight gradients reduced over the batch tiles by TMA reduce-adds into `grads` (which must be
+ * zero on entry - rtd3_td3_adam_polyak re-zeroes what it consumes).  Same arguments as the fp32 calls, with
+ * params_uv (rtd3_tc_sync_weights / rtd3_td3_adam_polyak keep it) instead of params_t and no row scratch.
+ * Agrees with the fp32 calls to TF32 round-off; opt-in throughput mode, not the parity path. */
+int32_t rtd3_td3_critic_step_tf32(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const float* rp_s,
+                                  const float* rp_a, const float* rp_r, const float* rp_s2, const float* rp_notdone, const int32_t* idx,
+                                  const float* noise, int32_t batch, float gamma, float policy_noise, float noise_clip, float max_action,
+                                  float* loss2, float* q_out, float* y_out, int32_t* steps, double* beta_pows, void* stream);
+int32_t rtd3_td3_actor_step_tf32(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const float* rp_s,
+                                 const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,8 @@
 //   next layer's X straight back in the chunk layout (16 B per 4 columns, consecutive rows -> conflict-free).
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
+#include "rtd3_tc.cuh"
+#include "rtd3_td3.cuh"
 
 namespace rtd3 {
 
@@ -22,48 +24,6 @@ constexpr int kTcRows = 128;          // batch rows per CTA = UMMA M
 constexpr int kTcThreads = 192;       // warps 0-3: row threads / epilogue, warp 4: TMA producer, warp 5: MMA issuer
 constexpr int kTcKSlab = 32;          // K per pipeline stage = 4 MMAs of K=8
 constexpr int kTcStages = 2;
-
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address, bits [0,14)
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;       // leading byte offset (between the two k-chunks of one MMA), bits [16,30)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;       // stride byte offset (between 8-row core matrices), bits [32,46)
-  d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
-  return d;                                                // layout type 0 = no swizzle, base offset 0
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // Shared-memory plan (bytes): X [H/4][128][4] | W stages [2][8][H][4] | small params | barriers | tmem base
 __host__ __device__ inline size_t tc_smem_bytes(int hid, int layers) {
@@ -210,26 +170,19 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
 }
 
-// chunk-major copy of the hidden-layer weights: Wu[(k/4)*H + n][k%4] = W[n][k]; everything else keeps its place
-__device__ __forceinline__ int64_t chunk_major_index(const NetShape& s, int64_t net_off, int64_t i) {
-  const int64_t o = i - net_off;
-  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
-  if (o < first) return i;
-  const int64_t o2 = o - first;
-  const int64_t l = o2 / blk, rem = o2 - l * blk;
-  if (l >= s.layers - 1 || rem >= (int64_t)s.hid * s.hid) return i;
-  const int64_t n = rem / s.hid, k = rem - n * s.hid;
-  return net_off + first + l * blk + ((k >> 2) * s.hid + n) * 4 + (k & 3);
-}
-
+// Rebuild both chunk-major copies of the whole arena (u: forward operand order, v: input-gradient operand order).
 __global__ void sync_chunk_major_kernel(NetShape actor, NetShape critic, int64_t sa, int64_t sc, const float* __restrict__ params,
-                                        float* __restrict__ params_u) {
+                                        float* __restrict__ params_uv) {
   const int64_t n_online = sa + 2 * sc, total = 2 * n_online;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i < n_online ? i : i - n_online;
     const int net = j < sa ? 0 : (j < sa + sc ? 1 : 2);
     const int64_t off = (i < n_online ? 0 : n_online) + (net == 0 ? 0 : (net == 1 ? sa : sa + sc));
-    params_u[chunk_major_index(net == 0 ? actor : critic, off, i)] = params[i];
+    const NetShape& s = net == 0 ? actor : critic;
+    const bool hidden = is_hidden_weight(s, off, i);
+    const float p = params[i];
+    params_uv[chunk_major_index(s, off, i)] = hidden ? tf32_rn(p) : p;
+    params_uv[total + chunk_major_index_v(s, off, i)] = hidden ? tf32_rn(p) : p;
   }
 }
 
@@ -240,10 +193,10 @@ using namespace rtd3;
 extern "C" {
 
 /* Rebuild the chunk-major (UMMA operand order) copy of all hidden-layer weights from the torch-layout arena. */
-int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_u, void* stream) {
-  RTD3_CHECK_ARG(params && params_u && hidden >= 4 && layers >= 1, "bad argument");
+int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params, float* params_uv, void* stream) {
+  RTD3_CHECK_ARG(params && params_uv && hidden >= 4 && layers >= 1, "bad argument");
   const NetShape a{2, hidden, layers, 2}, c{4, hidden, layers, 1};
-  sync_chunk_major_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, c, net_stride(a), net_stride(c), params, params_u);
+  sync_chunk_major_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(a, c, net_stride(a), net_stride(c), params, params_uv);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -4,48 +4,10 @@
 
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
+#include "rtd3_tc.cuh"
+#include "rtd3_td3.cuh"
 
 namespace rtd3 {
-
-struct ReplayView {
-  const float2* s;
-  const float2* a;
-  const float* r;
-  const float2* s2;
-  const float* notdone;
-};
-
-struct Td3Hyper {
-  float gamma, policy_noise, noise_clip, max_action;
-};
-
-// Parameter arena: [actor | critic1 | critic2 | target actor | target critic1 | target critic2], each slot padded to 4 floats.
-struct Arena {
-  NetShape actor, critic;
-  __host__ __device__ int64_t sa() const { return net_stride(actor); }
-  __host__ __device__ int64_t sc() const { return net_stride(critic); }
-  __host__ __device__ int64_t off(int net) const {   // 0 actor, 1 critic1, 2 critic2, 3..5 targets
-    const int64_t a = sa(), c = sc();
-    switch (net) {
-      case 0: return 0;
-      case 1: return a;
-      case 2: return a + c;
-      case 3: return a + 2 * c;
-      case 4: return 2 * a + 2 * c;
-      default: return 2 * a + 3 * c;
-    }
-  }
-  __host__ __device__ int64_t online_total() const { return sa() + 2 * sc(); }
-  __host__ __device__ int64_t total() const { return 2 * online_total(); }
-};
-
-// Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
-// beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
-__device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {
-  steps[o] += 1;
-  beta_pows[2 * o] *= 0.9;
-  beta_pows[2 * o + 1] *= 0.999;
-}
 
 // ---- critic phase: robot.py:312-366 up to (not including) the optimiser steps ------------------------------------
 //   y = r + gamma * min(Q1', Q2')(s2, clip(pi'(s2) + clip(noise*sigma, +-c), +-5)) * notdone
@@ -351,7 +313,7 @@ __global__ void td3_sync_transposed_kernel(Arena ar, const float* __restrict__ p
   }
 }
 
-__global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ grads, float* __restrict__ m,
+__global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ params_uv, float* __restrict__ grads, float* __restrict__ m,
                                        float* __restrict__ v, const double* __restrict__ beta_pows, int nets, float lr_actor,
                                        float lr_critic, float grad_scale, int polyak, float tau) {
   __shared__ float s_step[2], s_bc2[2];
@@ -379,6 +341,12 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
       p = p - s_step[o] * (mi / denom);
       params[i] = p;
       params_t[transposed_index(net == 0 ? ar.actor : ar.critic, ar.off(net), i)] = p;
+      if (params_uv) {                                                  // tensor-core operand copies (see rtd3_td3.cuh)
+        const NetShape& s = net == 0 ? ar.actor : ar.critic;
+        const float pr = is_hidden_weight(s, ar.off(net), i) ? tf32_rn(p) : p;
+        params_uv[chunk_major_index(s, ar.off(net), i)] = pr;
+        params_uv[ar.total() + chunk_major_index_v(s, ar.off(net), i)] = pr;
+      }
     }
     if ((polyak >> net) & 1) {
       const int64_t ti = n_online + i;                                // target slots mirror the online layout
@@ -386,6 +354,10 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
       const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
       params[ti] = tv;
       params_t[transposed_index(net == 0 ? ar.actor : ar.critic, n_online + ar.off(net), ti)] = tv;
+      if (params_uv) {
+        const NetShape& s = net == 0 ? ar.actor : ar.critic;
+        params_uv[chunk_major_index(s, n_online + ar.off(net), ti)] = is_hidden_weight(s, n_online + ar.off(net), ti) ? tf32_rn(tv) : tv;
+      }
     }
   }
 }
@@ -442,16 +414,6 @@ static bool shape_ok(const NetShape& s) {
 }  // namespace rtd3
 
 using namespace rtd3;
-
-constexpr int kNumTiles = 4;
-static const int kRowTiles[kNumTiles] = {2, 4, 8, 16};
-
-struct rtd3_td3 {
-  Arena ar;
-  int device;
-  int num_sms;
-  size_t smem_critic[kNumTiles], smem_actor[kNumTiles], smem_fwd[kNumTiles];
-};
 
 // Rows per CTA: few rows while the batch cannot fill the SMs (latency-bound), more rows once it can (every CTA
 // re-streams all weights from L2, so larger tiles cut that traffic).
@@ -591,13 +553,13 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* param
   return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st);
 }
 
-int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
+int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* params_uv, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
                              float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau, void* stream) {
   RTD3_CHECK_ARG(h && params && params_t && grads && adam_m && adam_v && beta_pows, "null argument");
   const int64_t n = h->ar.online_total();
   const int block = 256;
   const int grid = (int)std::min<int64_t>(ceil_div(n, block), (int64_t)h->num_sms * 8);
-  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, params_t, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
+  td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, params_t, params_uv, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
                                                                     lr_critic, grad_scale, polyak, tau);
   RTD3_LAUNCHED();
   return 0;

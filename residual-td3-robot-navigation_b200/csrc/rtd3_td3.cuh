@@ -1,0 +1,90 @@
+// Types shared by the fp32 learner kernels (rtd3_td3.cu) and the tensor-core learner (rtd3_tc_learner.cu).
+#pragma once
+#include "rtd3_common.cuh"
+#include "rtd3_mlp.cuh"
+
+namespace rtd3 {
+
+struct ReplayView {
+  const float2* s;
+  const float2* a;
+  const float* r;
+  const float2* s2;
+  const float* notdone;
+};
+
+struct Td3Hyper {
+  float gamma, policy_noise, noise_clip, max_action;
+};
+
+// Parameter arena: [actor | critic1 | critic2 | target actor | target critic1 | target critic2], each slot padded to 4 floats.
+struct Arena {
+  NetShape actor, critic;
+  __host__ __device__ int64_t sa() const { return net_stride(actor); }
+  __host__ __device__ int64_t sc() const { return net_stride(critic); }
+  __host__ __device__ int64_t off(int net) const {   // 0 actor, 1 critic1, 2 critic2, 3..5 targets
+    const int64_t a = sa(), c = sc();
+    switch (net) {
+      case 0: return 0;
+      case 1: return a;
+      case 2: return a + c;
+      case 3: return a + 2 * c;
+      case 4: return 2 * a + 2 * c;
+      default: return 2 * a + 3 * c;
+    }
+  }
+  __host__ __device__ int64_t online_total() const { return sa() + 2 * sc(); }
+  __host__ __device__ int64_t total() const { return 2 * online_total(); }
+};
+
+// Tensor-core operand copies of the arena (params_uv = [u | v], each `total()` floats).  Hidden-to-hidden weights W_l [H][H]
+// (l = 1..L-1) are stored chunk-major at the offset of W_l and rounded to TF32 (round-to-nearest):
+//   u (forward, B operand K-major):            Wu[(k/4)*H + n][k%4] = W[n][k]
+//   v (input gradient, B operand K-major of W^T): Wv[(n/4)*H + k][n%4] = W[n][k]
+// every other parameter keeps its place and value.
+__host__ __device__ inline bool is_hidden_weight(const NetShape& s, int64_t net_off, int64_t i) {
+  const int64_t o = i - net_off;
+  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
+  if (o < first) return false;
+  const int64_t o2 = o - first;
+  const int64_t l = o2 / blk, rem = o2 - l * blk;
+  return l < s.layers - 1 && rem < (int64_t)s.hid * s.hid;
+}
+__host__ __device__ inline int64_t chunk_major_index(const NetShape& s, int64_t net_off, int64_t i) {
+  if (!is_hidden_weight(s, net_off, i)) return i;
+  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
+  const int64_t o2 = i - net_off - first;
+  const int64_t l = o2 / blk, rem = o2 - l * blk;
+  const int64_t n = rem / s.hid, k = rem - n * s.hid;
+  return net_off + first + l * blk + ((k >> 2) * s.hid + n) * 4 + (k & 3);
+}
+__host__ __device__ inline int64_t chunk_major_index_v(const NetShape& s, int64_t net_off, int64_t i) {
+  if (!is_hidden_weight(s, net_off, i)) return i;
+  const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid;
+  const int64_t o2 = i - net_off - first;
+  const int64_t l = o2 / blk, rem = o2 - l * blk;
+  const int64_t n = rem / s.hid, k = rem - n * s.hid;
+  return net_off + first + l * blk + ((n >> 2) * s.hid + k) * 4 + (n & 3);
+}
+
+// Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
+// beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
+__device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {
+  steps[o] += 1;
+  beta_pows[2 * o] *= 0.9;
+  beta_pows[2 * o + 1] *= 0.999;
+}
+
+}  // namespace rtd3
+
+// the opaque learner handle of the C ABI
+constexpr int kNumTiles = 4;
+static constexpr int kRowTiles[kNumTiles] = {2, 4, 8, 16};
+
+struct rtd3_td3 {
+  rtd3::Arena ar;
+  int device;
+  int num_sms;
+  size_t smem_critic[kNumTiles], smem_actor[kNumTiles], smem_fwd[kNumTiles];
+};
+

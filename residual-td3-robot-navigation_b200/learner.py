@@ -300,10 +300,12 @@ class TD3:
         self.params = torch.zeros((total,), dtype=torch.float32, device=self.device)
         self.params_t = torch.zeros((total,), dtype=torch.float32, device=self.device)   # hidden weights transposed (forward layout)
         self._t_stale = True
-        # "fp32": every product in fp32 FFMA (the parity path).  "tf32": forward passes of >= 128 rows run on the tcgen05 tensor
-        # cores with TF32 operands (throughput mode; ~1e-3 relative on the outputs) when the width allows it (hidden % 32 == 0).
+        # "fp32": every product in fp32 FFMA (the parity path).  "tf32": forward passes of >= 128 rows, and critic / actor steps
+        # of >= `tc_min_batch` rows (2 x 128 or 2 x 256 networks), run on the tcgen05 tensor cores with TF32 operands (throughput
+        # mode; ~1e-3 relative on the outputs).
         self.precision = "fp32"
-        self.params_u = None
+        self.tc_min_batch = 1024
+        self.params_u = None                # [u | v]: tensor-core operand copies of the arena, 2 x total floats
         self.grads = torch.zeros((total // 2,), dtype=torch.float32, device=self.device)
         self.adam_m = torch.zeros_like(self.grads)
         self.adam_v = torch.zeros_like(self.grads)
@@ -373,12 +375,16 @@ class TD3:
         """Chunk-major weight copy for the tensor-core forward; rebuilt whenever the parameters may have changed (the
         optimiser steps mark it stale)."""
         if self.params_u is None:
-            self.params_u = torch.zeros_like(self.params)
+            self.params_u = torch.zeros((2 * self.params.numel(),), dtype=torch.float32, device=self.device)
             self._u_stale = True
         if self._u_stale:
             _lib.check(_lib.lib().rtd3_tc_sync_weights(self.hidden, self.layers, _lib.ptr(self.params), _lib.ptr(self.params_u),
                                                        _lib.stream_ptr(self.device)), "tc_sync_weights")
             self._u_stale = False
+
+    def _tc_learner_ok(self, batch):
+        return (self.precision == "tf32" and batch >= self.tc_min_batch
+                and bool(_lib.lib().rtd3_td3_tf32_supported(self._handle)))
 
     def flat_grad(self, net):
         return self.grads[self._off[net]:self._off[net] + self._cnt[net]]
@@ -411,18 +417,38 @@ class TD3:
             self._scratch = torch.empty((need,), dtype=torch.float32, device=self.device)
         return self._scratch
 
-    def _critic_step(self, rb, idx, noise, loss2, q_out=None, y_out=None):
+    def _critic_step(self, rb, idx, noise, loss2, q_out=None, y_out=None, apply=True):
+        """Gradients of both critics into `grads`; `apply` = all-reduce + Adam (False leaves the raw gradients, for tests)."""
         B = idx.numel()
+        if self._tc_learner_ok(B):
+            self._sync_chunk_major()
+            _lib.check(_lib.lib().rtd3_td3_critic_step_tf32(
+                self._handle, _lib.ptr(self.params), _lib.ptr(self.params_u), _lib.ptr(self.grads), _lib.ptr(rb.s), _lib.ptr(rb.a),
+                _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise,
+                self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
+                _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step_tf32")
+            if apply:
+                self._allreduce()
+                self._adam(nets=0b110, polyak=0)
+            return
         _lib.check(_lib.lib().rtd3_td3_critic_step(
             self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads), _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(rb.a),
             _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), _lib.ptr(idx), _lib.ptr(noise), B, self.gamma, self.policy_noise,
             self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
             _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step")
-        self._allreduce()
-        self._adam(nets=0b110, polyak=0)
+        if apply:
+            self._allreduce()
+            self._adam(nets=0b110, polyak=0)
 
     def _actor_step(self, rb, idx, loss1):
         B = idx.numel()
+        if self._tc_learner_ok(B):
+            self._sync_chunk_major()
+            _lib.check(_lib.lib().rtd3_td3_actor_step_tf32(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_u), _lib.ptr(self.grads),
+                                                           _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1), _lib.ptr(self.steps),
+                                                           _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_actor_step_tf32")
+            self._allreduce()
+            return
         _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads),
                                                   _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1),
                                                   _lib.ptr(self.steps), _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)),
@@ -430,8 +456,12 @@ class TD3:
         self._allreduce()
 
     def _adam(self, nets, polyak):
-        self._u_stale = True
-        _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+        # the optimiser kernel keeps the tensor-core copies in step once they exist and are current
+        keep_uv = self.params_u is not None and not self._u_stale
+        if not keep_uv:
+            self._u_stale = True
+        _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t),
+                                                   _lib.ptr(self.params_u if keep_uv else None), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
 
@@ -526,7 +556,7 @@ class TD3:
     def _update_state(self, replay_buffer, E, B, delay):
         """Persistent buffers (and, once captured, the CUDA graph) of an E-epoch block for this replay buffer / batch size."""
         n_actor = len([e for e in range(E) if e % delay == 0])
-        key = (id(replay_buffer), E, B, delay)
+        key = (id(replay_buffer), E, B, delay, self.precision, self._tc_learner_ok(B))
         st = self._graphs.get(key)
         if st is None:
             st = {"idx": torch.zeros((E + n_actor, B), dtype=torch.int32, device=self.device),
@@ -539,6 +569,9 @@ class TD3:
 
     def _launch_epochs(self, replay_buffer, st, use_graph, E):
         saved, self.num_epochs = self.num_epochs, E
+        tf32 = self.precision == "tf32"
+        if tf32:
+            self._sync_chunk_major()         # current before the loop; every optimiser step inside keeps it in step
         try:
             # NCCL collectives are issued eagerly between the kernels: the data-parallel loop is not graph-captured
             if use_graph and self.world == 1:
@@ -560,6 +593,8 @@ class TD3:
                 self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
         finally:
             self.num_epochs = saved
+            if not tf32:
+                self._u_stale = True         # a replayed graph does not run _adam's bookkeeping
 
     def _td3_update_pipelined(self, replay_buffer, noise, C):
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay

@@ -4,9 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import rtd3_b200 as rt
 
-def run(B, H, L, epochs=100, reps=3, sampler=True):
+def run(B, H, L, epochs=100, reps=3, sampler=True, precision="fp32"):
     torch.manual_seed(0)
     agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L), batch_size=B, num_epochs=epochs)
+    agent.precision = precision
     n = 10000
     rb = rt.ReplayBuffer(n, seed=0)
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -31,10 +32,13 @@ def run(B, H, L, epochs=100, reps=3, sampler=True):
         ev[2].record()
         torch.cuda.synchronize()
         ts, tu = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    print("B=%d H=%d L=%d: sampler %.3f ms, update %.3f ms for %d epochs -> %.1f us/epoch, %.0f updates/s (update only), %.0f with sampler; launches %d"
+    print(precision, "B=%d H=%d L=%d: sampler %.3f ms, update %.3f ms for %d epochs -> %.1f us/epoch, %.0f updates/s (update only), %.0f with sampler; launches %d"
           % (B, H, L, ts, tu, epochs, tu * 1e3 / epochs, epochs / (tu * 1e-3), epochs / ((tu + ts) * 1e-3), rt._lib.launch_count()))
 
 if __name__ == "__main__":
     run(100, 200, 3)
     run(256, 256, 2)
     run(8192, 256, 2, epochs=20)
+    for B in (1024, 2048, 4096, 8192, 16384, 65536):
+        run(B, 256, 2, epochs=20, sampler=False)
+        run(B, 256, 2, epochs=20, sampler=False, precision="tf32")
