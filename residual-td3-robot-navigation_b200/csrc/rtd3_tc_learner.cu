@@ -31,9 +31,11 @@
 namespace rtd3 {
 
 constexpr int kLtRows = 64;           // batch rows per CTA = UMMA M of the forward / dX products
-constexpr int kLtThreads = 320;       // warps 0-7: row / epilogue threads, warp 8: TMA producer, warp 9: MMA issuer
-constexpr int kLtEpi = 256;
-constexpr int kLtEpiMma = 288;        // named barrier 2: epilogue warps + the MMA warp
+constexpr int kLtEpiWarps = 16;       // 4 per scheduler: the fp32 phases between the products are issue / latency bound
+constexpr int kLtEpi = kLtEpiWarps * 32;
+constexpr int kLtThreads = kLtEpi + 64;   // warps 0-15: row / epilogue threads, warp 16: TMA producer, warp 17: MMA issuer
+constexpr int kLtEpiMma = kLtEpi + 32;    // named barrier 2: epilogue warps + the MMA warp
+constexpr int kLtColGroups = kLtEpi / kLtRows;   // thread t: row t % 64, column group t / 64 (first / output layer)
 
 // Shared-memory plan in floats (the base is aligned to 1024 B by hand: the dW staging tiles are SWIZZLE_128B boxes).
 template <int H>
@@ -54,12 +56,20 @@ struct Lt {
   static constexpr int oS = oIn0 + 256;             // [64][8] per-row scalars
   static constexpr int oOut = oS + 512;             // [64][2] network output
   static constexpr int oDout = oOut + 128;          // [64][2] gradient w.r.t. the output
-  static constexpr int oPart = oDout + 128;         // [4][64][2] partial sums of the output layer / input gradient
-  static constexpr int oBar = oPart + 512;          // full[2] empty[2] acc_ready stage_free (uint64) + tmem slot
+  static constexpr int oPart = oDout + 128;         // [8][64][2] partial sums of the output layer / input gradient
+  static constexpr int oBar = oPart + kLtColGroups * 128;          // full[2] empty[2] acc_ready stage_free (uint64) + tmem slot
   static constexpr int kFloats = oBar + 16;
   static constexpr size_t kBytes = (size_t)kFloats * 4 + 1024;
   static_assert(2 * kStage <= kStageRegion, "weight stages exceed their region");   // = the two re-laid dW operands of lt_dw
 };
+
+// Development aid: phase timestamps of CTA 0 / thread 0 (rtd3_debug_lt_prof), off unless switched on.
+__device__ long long g_lt_prof[128];
+__device__ int g_lt_prof_on = 0;
+#define LT_STAMP(i)                                                                                 \
+  do {                                                                                              \
+    if (g_lt_prof_on && blockIdx.x == 0 && threadIdx.x == 0) g_lt_prof[(i)] = clock64();             \
+  } while (0)
 
 struct LtCtx {
   uint32_t tmem;
@@ -87,41 +97,109 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---- small parameters of one network -> shared memory (epilogue threads) ------------------------------------------------
+// Two halves so that the global-load latency hides behind a streamed product: lt_small_fetch issues the loads into
+// registers (call it before waiting for an accumulator), lt_small_store writes them to shared memory once the previous
+// network's parameters are no longer read.
 template <int H>
-__device__ __forceinline__ void lt_load_small(float* sm, const float* __restrict__ P, const NetShape& s) {
-  using L = Lt<H>;
+struct LtSmall {
+  static constexpr int kW0 = (4 * H + kLtEpi - 1) / kLtEpi, kB = (H + kLtEpi - 1) / kLtEpi, kWo = (2 * H + kLtEpi - 1) / kLtEpi;
+  float w0[kW0], b0[kB], b1[kB], wo[kWo], bo;
+};
+
+template <int H>
+__device__ __forceinline__ void lt_small_fetch(LtSmall<H>& r, const float* __restrict__ P, const NetShape& s) {
+  using S = LtSmall<H>;
   const int t = threadIdx.x;
-  for (int i = t; i < H * 4; i += kLtEpi) {
-    const int c = i >> 2, j = i & 3;
-    sm[L::oW0 + i] = j < s.in ? __ldg(P + c * s.in + j) : 0.f;
+#pragma unroll
+  for (int k = 0; k < S::kW0; ++k) {
+    const int i = t + k * kLtEpi, c = i >> 2, j = i & 3;
+    r.w0[k] = (i < 4 * H && j < s.in) ? __ldg(P + c * s.in + j) : 0.f;
   }
-  for (int i = t; i < H; i += kLtEpi) {
-    sm[L::oB + i] = __ldg(P + net_b_off(s, 0) + i);
-    sm[L::oB + H + i] = __ldg(P + net_b_off(s, 1) + i);
+#pragma unroll
+  for (int k = 0; k < S::kB; ++k) {
+    const int i = t + k * kLtEpi;
+    r.b0[k] = i < H ? __ldg(P + net_b_off(s, 0) + i) : 0.f;
+    r.b1[k] = i < H ? __ldg(P + net_b_off(s, 1) + i) : 0.f;
   }
-  for (int i = t; i < 2 * H; i += kLtEpi) sm[L::oWo + i] = (i / H) < s.out ? __ldg(P + net_w_off(s, 2) + i) : 0.f;
-  if (t < 4) sm[L::oBo + t] = t < s.out ? __ldg(P + net_b_off(s, 2) + t) : 0.f;
+#pragma unroll
+  for (int k = 0; k < S::kWo; ++k) {
+    const int i = t + k * kLtEpi;
+    r.wo[k] = (i < 2 * H && (i / H) < s.out) ? __ldg(P + net_w_off(s, 2) + i) : 0.f;
+  }
+  r.bo = (t < 4 && t < s.out) ? __ldg(P + net_b_off(s, 2) + t) : 0.f;
+}
+
+template <int H>
+__device__ __forceinline__ void lt_small_store(float* sm, const LtSmall<H>& r) {
+  using L = Lt<H>;
+  using S = LtSmall<H>;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < S::kW0; ++k)
+    if (t + k * kLtEpi < 4 * H) sm[L::oW0 + t + k * kLtEpi] = r.w0[k];
+#pragma unroll
+  for (int k = 0; k < S::kB; ++k) {
+    const int i = t + k * kLtEpi;
+    if (i < H) { sm[L::oB + i] = r.b0[k]; sm[L::oB + H + i] = r.b1[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < S::kWo; ++k)
+    if (t + k * kLtEpi < 2 * H) sm[L::oWo + t + k * kLtEpi] = r.wo[k];
+  if (t < 4) sm[L::oBo + t] = r.bo;
   bar_sync(1, kLtEpi);
 }
 
+template <int H>
+__device__ __forceinline__ void lt_load_small(float* sm, const float* __restrict__ P, const NetShape& s) {
+  LtSmall<H> r;
+  lt_small_fetch<H>(r, P, s);
+  lt_small_store<H>(sm, r);
+}
+
 // ---- first layer: X[r][c] = tf32(relu(b0[c] + sum_j in0[r][j] W0[c][j])) in the chunk layout ------------------------------
+// A warp takes every 8th 4-column chunk (weights broadcast from shared memory, held in registers for two rows per lane).
 template <int H>
 __device__ __forceinline__ void lt_layer0(float* sm, int buf) {
   using L = Lt<H>;
-  const int t = threadIdx.x, r = t & 63, cq = t >> 6;
-  const float4 x = ld4(sm + L::oIn0 + r * 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 xa = ld4(sm + L::oIn0 + lane * 4), xb = ld4(sm + L::oIn0 + (lane + 32) * 4);
 #pragma unroll 2
-  for (int c = cq * (H / 4); c < (cq + 1) * (H / 4); c += 4) {
-    float hv[4];
+  for (int c = warp; c < H / 4; c += kLtEpiWarps) {
+    const float4 b = ld4(sm + L::oB + 4 * c);
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+    float ha[4], hb[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 w = ld4(sm + L::oW0 + (c + q) * 4);
-      float v = sm[L::oB + c + q];
-      v = fmaf(x.x, w.x, v); v = fmaf(x.y, w.y, v); v = fmaf(x.z, w.z, v); v = fmaf(x.w, w.w, v);
-      hv[q] = tf32_rn(fmaxf(v, 0.f));
+      const float4 w = ld4(sm + L::oW0 + (4 * c + q) * 4);
+      float va = bv[q], vb = bv[q];
+      va = fmaf(xa.x, w.x, va); va = fmaf(xa.y, w.y, va); va = fmaf(xa.z, w.z, va); va = fmaf(xa.w, w.w, va);
+      vb = fmaf(xb.x, w.x, vb); vb = fmaf(xb.y, w.y, vb); vb = fmaf(xb.z, w.z, vb); vb = fmaf(xb.w, w.w, vb);
+      ha[q] = tf32_rn(fmaxf(va, 0.f));
+      hb[q] = tf32_rn(fmaxf(vb, 0.f));
     }
-    st4(sm + buf + ((c >> 2) * kLtRows + r) * 4, make_float4(hv[0], hv[1], hv[2], hv[3]));
+    st4(sm + buf + (c * kLtRows + lane) * 4, make_float4(ha[0], ha[1], ha[2], ha[3]));
+    st4(sm + buf + (c * kLtRows + lane + 32) * 4, make_float4(hb[0], hb[1], hb[2], hb[3]));
   }
+}
+
+// Sum V values per lane over the 32 lanes of a warp with V-1 + log2(32/V) shuffles (log2(V) halving exchanges, then a butterfly
+// over the remaining lane bits) instead of 5V.  Afterwards the lanes with (lane & (32/V - 1)) == 0 hold in v[0] the total of
+// value number lane / (32/V).
+template <int V>
+__device__ __forceinline__ void warp_reduce_many(float (&v)[V]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int w = V / 2, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? v[i] : v[i + w];
+      const float keep = hi ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+#pragma unroll
+  for (int bit = (32 / V) >> 1; bit >= 1; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
 }
 
 // ---- streamed product: TMEM[64 x H] = X(a_buf)[64 x H] * Wg^T, Wg chunk-major [H/4][H][4] in global memory --------------
@@ -133,7 +211,7 @@ __device__ __forceinline__ void lt_gemm(float* sm, LtCtx& cx, const float* __res
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::oBar);
   uint64_t *full = bars, *empty = bars + 2, *acc = bars + 4, *sfree = bars + 5;
   constexpr uint32_t kBytes = (uint32_t)L::kStage * 4;
-  if (warp == 8) {
+  if (warp == kLtEpiWarps) {
     if (lane == 0) {
       if (gate) {                                   // the stages are aliased by the dW staging tiles: wait for that drain
         mbar_wait(sfree, cx.gate_phase);
@@ -147,7 +225,7 @@ __device__ __forceinline__ void lt_gemm(float* sm, LtCtx& cx, const float* __res
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == kLtEpiWarps + 1) {
     bar_sync(2, kLtEpiMma);
     if (lane == 0) {
       tc_fence_after();
@@ -189,8 +267,8 @@ __device__ __forceinline__ void lt_dw(float* sm, LtCtx& cx, int dz_buf, int h_bu
   constexpr int kOp = H * 32;                        // floats of one re-laid operand (32 rows x H)
 #pragma unroll 1
   for (int round = 0; round < 2; ++round) {
-    if (warp == 8) {
-    } else if (warp == 9) {
+    if (warp == kLtEpiWarps) {
+    } else if (warp == kLtEpiWarps + 1) {
       bar_sync(2, kLtEpiMma);
       if (lane == 0) {
         tc_fence_after();
@@ -239,22 +317,25 @@ __device__ __forceinline__ void lt_drain(float* sm, LtCtx& cx, const CUtensorMap
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::oBar);
   uint64_t *acc = bars + 4, *sfree = bars + 5;
-  if (warp < 8) {
+  if (warp < kLtEpiWarps) {
     const int q = warp & 3, ch = warp >> 2;
     mbar_wait(acc, cx.acc_phase);
     cx.acc_phase ^= 1;
     tc_fence_after();
-    float* stg = sm + L::oStage + warp * 2048;       // two 32 x 32 fp32 tiles (4 KB each, 1024 B aligned)
-    int it = 0;
+    float* stg = sm + L::oStage + warp * 1024;       // one 32 x 32 fp32 tile per warp (4 KB, 1024 B aligned)
+    // every CTA reduces into the same H x H block of the arena: start at a CTA-dependent block so that the L2 does not see
+    // all CTAs hitting the same addresses at the same time
+    constexpr int kBlk = H / 128, kIter = (H / 128) * kBlk;   // 32-column blocks of this warp's column quarter, times row halves
 #pragma unroll 1
-    for (int hf = 0; hf < H / 128; ++hf) {
-#pragma unroll 1
-      for (int cb = ch * (H / 2); cb < (ch + 1) * (H / 2); cb += 32, ++it) {
+    for (int it = 0; it < kIter; ++it) {
+      {
+        const int e = (it + (int)blockIdx.x) % kIter;
+        const int hf = e / kBlk, cb = ch * (H / 4) + (e % kBlk) * 32;
         float v[32];
         tmem_ld32(cx.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * H + cb), v);
-        float* dst = stg + (it & 1) * 1024;
-        if (it >= 2) {
-          if (lane == 0) bulk_wait_read<1>();        // the reduce that read this tile two iterations ago has consumed it
+        float* dst = stg;
+        if (it >= 1) {
+          if (lane == 0) bulk_wait_read<0>();        // the previous reduce has consumed the tile (4 warps per scheduler interleave)
           __syncwarp();
         }
 #pragma unroll
@@ -290,7 +371,7 @@ __device__ __forceinline__ void lt_epilogue(float* sm, LtCtx& cx, int bias_off, 
   cx.acc_phase ^= 1;
   tc_fence_after();
 #pragma unroll 1
-  for (int cb = ch * (H / 2); cb < (ch + 1) * (H / 2); cb += 32) {
+  for (int cb = ch * (H / 4); cb < (ch + 1) * (H / 4); cb += 32) {
     float v[32];
     tmem_ld32(cx.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)cb, v);
     if (lane < 16) {
@@ -330,7 +411,7 @@ __device__ __forceinline__ void lt_epilogue_din(float* sm, LtCtx& cx) {
   const float4 x = ld4(sm + L::oIn0 + r * 4);
   float d0 = 0.f, d1 = 0.f;
 #pragma unroll 1
-  for (int cb = ch * (H / 2); cb < (ch + 1) * (H / 2); cb += 32) {
+  for (int cb = ch * (H / 4); cb < (ch + 1) * (H / 4); cb += 32) {
     float v[32];
     tmem_ld32(cx.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)cb, v);
 #pragma unroll
@@ -357,7 +438,7 @@ __device__ __forceinline__ void lt_out_layer(float* sm, int buf) {
   const int t = threadIdx.x, r = t & 63, cq = t >> 6;
   float p0 = 0.f, p1 = 0.f;
 #pragma unroll 4
-  for (int c = cq * (H / 4); c < (cq + 1) * (H / 4); c += 4) {
+  for (int c = cq * (H / kLtColGroups); c < (cq + 1) * (H / kLtColGroups); c += 4) {
     const float4 h = ld4(sm + buf + ((c >> 2) * kLtRows + r) * 4);
     const float4 w0 = ld4(sm + L::oWo + c), w1 = ld4(sm + L::oWo + H + c);
     p0 = fmaf(h.x, w0.x, p0); p0 = fmaf(h.y, w0.y, p0); p0 = fmaf(h.z, w0.z, p0); p0 = fmaf(h.w, w0.w, p0);
@@ -371,7 +452,7 @@ __device__ __forceinline__ void lt_out_layer(float* sm, int buf) {
     for (int o = 0; o < 2; ++o) {
       float v = sm[L::oBo + o];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) v += sm[L::oPart + (g * kLtRows + t) * 2 + o];
+      for (int g = 0; g < kLtColGroups; ++g) v += sm[L::oPart + (g * kLtRows + t) * 2 + o];
       sm[L::oOut + t * 2 + o] = v;
     }
   }
@@ -379,68 +460,70 @@ __device__ __forceinline__ void lt_out_layer(float* sm, int buf) {
 
 // ---- backward through the output layer, in place on buf (h1 -> dz1), with the sums the small gradients need ----------------
 //   gWout[o][c] = sum_r dout[r][o] h1[r][c];   dz1[r][c] = relu'(h1) * sum_o dout[r][o] Wo[o][c];   gb1[c] = sum_r dz1[r][c]
-template <int H>
-__device__ __forceinline__ void lt_bwd_out(float* sm, int buf, int nout) {
+template <int H, int NOUT>
+__device__ __forceinline__ void lt_bwd_out(float* sm, int buf) {
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float2 da = *reinterpret_cast<const float2*>(sm + L::oDout + lane * 2);
   const float2 db = *reinterpret_cast<const float2*>(sm + L::oDout + (lane + 32) * 2);
-#pragma unroll 1
-  for (int c = warp; c < H / 4; c += 8) {
+  constexpr int V = NOUT == 1 ? 8 : 16;              // [gWout row 0 (4) | gb1 (4) | gWout row 1 (4) | pad]
+#pragma unroll 2
+  for (int c = warp; c < H / 4; c += kLtEpiWarps) {
     float* pa = sm + buf + (c * kLtRows + lane) * 4;
     float* pb = pa + 32 * 4;
     const float4 ha = ld4(pa), hb = ld4(pb);
     const float4 w0 = ld4(sm + L::oWo + 4 * c), w1 = ld4(sm + L::oWo + H + 4 * c);
     const float hav[4] = {ha.x, ha.y, ha.z, ha.w}, hbv[4] = {hb.x, hb.y, hb.z, hb.w};
     const float w0v[4] = {w0.x, w0.y, w0.z, w0.w}, w1v[4] = {w1.x, w1.y, w1.z, w1.w};
-    float za[4], zb[4], s0[4], s1[4], sb[4];
+    float za[4], zb[4], v[V];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       za[j] = hav[j] > 0.f ? tf32_rn(fmaf(da.x, w0v[j], da.y * w1v[j])) : 0.f;
       zb[j] = hbv[j] > 0.f ? tf32_rn(fmaf(db.x, w0v[j], db.y * w1v[j])) : 0.f;
-      s0[j] = fmaf(da.x, hav[j], db.x * hbv[j]);
-      s1[j] = fmaf(da.y, hav[j], db.y * hbv[j]);
-      sb[j] = za[j] + zb[j];
+      v[j] = fmaf(da.x, hav[j], db.x * hbv[j]);
+      v[4 + j] = za[j] + zb[j];
+      if (NOUT > 1) { v[8 + j] = fmaf(da.y, hav[j], db.y * hbv[j]); v[12 + j] = 0.f; }
     }
     st4(pa, make_float4(za[0], za[1], za[2], za[3]));
     st4(pb, make_float4(zb[0], zb[1], zb[2], zb[3]));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      s0[j] = warp_sum(s0[j]);
-      sb[j] = warp_sum(sb[j]);
-      if (nout > 1) s1[j] = warp_sum(s1[j]);
-    }
-    if (lane == 0) {
-      st4(sm + L::oG + 6 * H + 4 * c, make_float4(s0[0], s0[1], s0[2], s0[3]));
-      if (nout > 1) st4(sm + L::oG + 7 * H + 4 * c, make_float4(s1[0], s1[1], s1[2], s1[3]));
-      st4(sm + L::oG + 5 * H + 4 * c, make_float4(sb[0], sb[1], sb[2], sb[3]));
+    warp_reduce_many<V>(v);
+    if ((lane & (32 / V - 1)) == 0) {
+      const int j = lane / (32 / V);                 // value number: 0-3 gWout[0], 4-7 gb1, 8-11 gWout[1]
+      if (j < 4) sm[L::oG + 6 * H + 4 * c + j] = v[0];
+      else if (j < 8) sm[L::oG + 5 * H + 4 * c + (j - 4)] = v[0];
+      else if (j < 12) sm[L::oG + 7 * H + 4 * c + (j - 8)] = v[0];
     }
   }
 }
 
 // ---- first-layer gradients from dz0 (buf): gb0[c] = sum_r dz0[r][c];  gW0[c][j] = sum_r dz0[r][c] in0[r][j] -----------------
-template <int H>
-__device__ __forceinline__ void lt_colsum_in(float* sm, int buf, int nin) {
+template <int H, int NIN>
+__device__ __forceinline__ void lt_colsum_in(float* sm, int buf) {
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 xa4 = ld4(sm + L::oIn0 + lane * 4), xb4 = ld4(sm + L::oIn0 + (lane + 32) * 4);
   const float xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w}, xb[4] = {xb4.x, xb4.y, xb4.z, xb4.w};
-#pragma unroll 1
-  for (int c = warp; c < H / 4; c += 8) {
+  constexpr int V = NIN == 4 ? 32 : 16;              // value q * (1 + NIN) + k: k = 0 bias, k >= 1 input k-1, of column 4c + q
+#pragma unroll 2
+  for (int c = warp; c < H / 4; c += kLtEpiWarps) {
     const float4 za4 = ld4(sm + buf + (c * kLtRows + lane) * 4), zb4 = ld4(sm + buf + (c * kLtRows + lane + 32) * 4);
     const float za[4] = {za4.x, za4.y, za4.z, za4.w}, zb[4] = {zb4.x, zb4.y, zb4.z, zb4.w};
+    float v[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float b = warp_sum(za[q] + zb[q]);
-      float w[4];
+      v[q * (1 + NIN)] = za[q] + zb[q];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = j < nin ? warp_sum(fmaf(za[q], xa[j], zb[q] * xb[j])) : 0.f;
-      if (lane == 0) {
-        const int col = 4 * c + q;
-        sm[L::oG + H * nin + col] = b;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nin) sm[L::oG + col * nin + j] = w[j];
+      for (int j = 0; j < NIN; ++j) v[q * (1 + NIN) + 1 + j] = fmaf(za[q], xa[j], zb[q] * xb[j]);
+    }
+    warp_reduce_many<V>(v);
+    if ((lane & (32 / V - 1)) == 0) {
+      const int i = lane / (32 / V);
+      if (i < 4 * (1 + NIN)) {
+        const int q = i / (1 + NIN), k = i - q * (1 + NIN), col = 4 * c + q;
+        if (k == 0) sm[L::oG + H * NIN + col] = v[0];
+        else sm[L::oG + col * NIN + k - 1] = v[0];
       }
     }
   }
@@ -481,7 +564,7 @@ __device__ __forceinline__ float* lt_setup(LtCtx& cx) {
     mbar_init(bars + 0, 1); mbar_init(bars + 1, 1);     // full
     mbar_init(bars + 2, 1); mbar_init(bars + 3, 1);     // empty
     mbar_init(bars + 4, 1);                             // acc_ready
-    mbar_init(bars + 5, 8);                             // stage_free: one arrival per epilogue warp
+    mbar_init(bars + 5, kLtEpiWarps);                   // stage_free: one arrival per epilogue warp
     fence_mbar_init();
   }
   if (t < 32) {
@@ -528,8 +611,11 @@ td3_critic_tc_kernel(Arena ar, const float* __restrict__ params, const float* __
     in0[t * 4 + 0] = s2.x; in0[t * 4 + 1] = s2.y; in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;
   }
   __syncthreads();
+  LT_STAMP(0);
   const float* Pu = params_uv;                    // forward operand order
   const float* Pv = params_uv + ar.total();       // input-gradient operand order
+  LtSmall<H> sp;                                  // small parameters of the next pass, fetched one product ahead
+  if (warp < kLtEpiWarps) lt_small_fetch<H>(sp, params + ar.off(3), ar.actor);
 
   // pass 0: target actor(s2); 1, 2: target critics(s2, a'); 3, 4: critics(s, a) forward + backward
 #pragma unroll 1
@@ -539,13 +625,18 @@ td3_critic_tc_kernel(Arena ar, const float* __restrict__ params, const float* __
     const bool train = pass >= 3;
     const int64_t w1 = ar.off(net) + net_w_off(shape, 1);
     const int hbuf = train ? L::oBufB : L::oBufA;
-    if (warp < 8) {
-      lt_load_small<H>(sm, params + ar.off(net), shape);
+    if (warp < kLtEpiWarps) {
+      lt_small_store<H>(sm, sp);
+      LT_STAMP(1 + pass * 16 + 0);
       lt_layer0<H>(sm, L::oBufA);
+      LT_STAMP(1 + pass * 16 + 1);
     }
     lt_gemm<H>(sm, cx, Pu + w1, L::oBufA, false);
-    if (warp < 8) {
+    if (warp < kLtEpiWarps) {
+      if (pass < 4) lt_small_fetch<H>(sp, params + ar.off(pass == 0 ? 4 : (pass == 1 ? 5 : pass - 1)), ar.critic);   // next pass's network
+      LT_STAMP(1 + pass * 16 + 2);
       lt_epilogue<H, 0>(sm, cx, L::oB + H, hbuf);
+      LT_STAMP(1 + pass * 16 + 3);
       bar_sync(1, kLtEpi);
       lt_out_layer<H>(sm, hbuf);
       if (t < kLtRows) {
@@ -581,21 +672,31 @@ td3_critic_tc_kernel(Arena ar, const float* __restrict__ params, const float* __
         }
       }
       bar_sync(1, kLtEpi);
-      if (train) lt_bwd_out<H>(sm, L::oBufB, 1);
+      LT_STAMP(1 + pass * 16 + 4);
+      if (train) lt_bwd_out<H, 1>(sm, L::oBufB);
+      LT_STAMP(1 + pass * 16 + 5);
     }
     if (train) {
       lt_dw<H>(sm, cx, L::oBufB, L::oBufA);
+      LT_STAMP(1 + pass * 16 + 6);
       lt_drain<H>(sm, cx, &maps.dw[pass - 3]);
+      LT_STAMP(1 + pass * 16 + 7);
       lt_gemm<H>(sm, cx, Pv + w1, L::oBufB, true);
-      if (warp < 8) {
+      if (warp < kLtEpiWarps) {
+        LT_STAMP(1 + pass * 16 + 8);
         lt_epilogue<H, 1>(sm, cx, 0, L::oBufA);
+        LT_STAMP(1 + pass * 16 + 9);
         bar_sync(1, kLtEpi);
-        lt_colsum_in<H>(sm, L::oBufA, 4);
+        lt_colsum_in<H, 4>(sm, L::oBufA);
+        LT_STAMP(1 + pass * 16 + 10);
         lt_reduce_small<H>(sm, grads + ar.off(net), shape);
+        LT_STAMP(1 + pass * 16 + 11);
       }
     }
   }
+  LT_STAMP(90);
   lt_teardown(cx);
+  LT_STAMP(91);
 }
 
 // ================================================================================================================================
@@ -628,12 +729,14 @@ td3_actor_tc_kernel(Arena ar, const float* __restrict__ params, const float* __r
   const int64_t wa = ar.off(0) + net_w_off(ar.actor, 1), wc = ar.off(1) + net_w_off(ar.critic, 1);
 
   // ---- a = pi(s) (fed the raw replay state, robot.py:386): h0a -> A, h1a -> B (kept for the backward pass) ----
-  if (warp < 8) {
+  LtSmall<H> sp;
+  if (warp < kLtEpiWarps) {
     lt_load_small<H>(sm, params + ar.off(0), ar.actor);
     lt_layer0<H>(sm, L::oBufA);
   }
   lt_gemm<H>(sm, cx, Pu + wa, L::oBufA, false);
-  if (warp < 8) {
+  if (warp < kLtEpiWarps) {
+    lt_small_fetch<H>(sp, params + ar.off(1), ar.critic);
     lt_epilogue<H, 0>(sm, cx, L::oB + H, L::oBufB);
     bar_sync(1, kLtEpi);
     lt_out_layer<H>(sm, L::oBufB);
@@ -643,11 +746,12 @@ td3_actor_tc_kernel(Arena ar, const float* __restrict__ params, const float* __r
     }
     bar_sync(1, kLtEpi);
     // ---- Q1(s, a): h0c -> A (h0a is recomputed later), h1c in place ----
-    lt_load_small<H>(sm, params + ar.off(1), ar.critic);
+    lt_small_store<H>(sm, sp);
     lt_layer0<H>(sm, L::oBufA);
   }
   lt_gemm<H>(sm, cx, Pu + wc, L::oBufA, false);
-  if (warp < 8) {
+  if (warp < kLtEpiWarps) {
+    lt_small_fetch<H>(sp, params + ar.off(0), ar.actor);     // for the backward pass through the actor
     lt_epilogue<H, 0>(sm, cx, L::oB + H, L::oBufA);
     bar_sync(1, kLtEpi);
     lt_out_layer<H>(sm, L::oBufA);
@@ -659,31 +763,34 @@ td3_actor_tc_kernel(Arena ar, const float* __restrict__ params, const float* __r
       if ((t & 31) == 0) atomicAdd(loss, l);
     }
     bar_sync(1, kLtEpi);
-    lt_bwd_out<H>(sm, L::oBufA, 1);          // dz1c in place (the critic's small-gradient sums land in the staging and are ignored)
+    lt_bwd_out<H, 1>(sm, L::oBufA);          // dz1c in place (the critic's small-gradient sums land in the staging and are ignored)
   }
   // ---- dQ/da through critic 1: only the input gradient, nothing stored ----
   lt_gemm<H>(sm, cx, Pv + wc, L::oBufA, false);
-  if (warp < 8) {
+  if (warp < kLtEpiWarps) {
     lt_epilogue_din<H>(sm, cx);
     bar_sync(1, kLtEpi);
     if (t < kLtRows) {
-      dout[t * 2] = sm[L::oPart + t * 2] + sm[L::oPart + (kLtRows + t) * 2];
-      dout[t * 2 + 1] = sm[L::oPart + t * 2 + 1] + sm[L::oPart + (kLtRows + t) * 2 + 1];
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { d0 += sm[L::oPart + (g * kLtRows + t) * 2]; d1 += sm[L::oPart + (g * kLtRows + t) * 2 + 1]; }
+      dout[t * 2] = d0;
+      dout[t * 2 + 1] = d1;
       in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;      // back to the actor's input
     }
     bar_sync(1, kLtEpi);
     // ---- backward through the actor ----
-    lt_load_small<H>(sm, params + ar.off(0), ar.actor);
-    lt_bwd_out<H>(sm, L::oBufB, 2);          // h1a -> dz1a, gWout, gb1
+    lt_small_store<H>(sm, sp);
+    lt_bwd_out<H, 2>(sm, L::oBufB);          // h1a -> dz1a, gWout, gb1
     lt_layer0<H>(sm, L::oBufA);              // recompute h0a
   }
   lt_dw<H>(sm, cx, L::oBufB, L::oBufA);
   lt_drain<H>(sm, cx, &maps.dw[0]);
   lt_gemm<H>(sm, cx, Pv + wa, L::oBufB, true);
-  if (warp < 8) {
+  if (warp < kLtEpiWarps) {
     lt_epilogue<H, 1>(sm, cx, 0, L::oBufA);
     bar_sync(1, kLtEpi);
-    lt_colsum_in<H>(sm, L::oBufA, 2);
+    lt_colsum_in<H, 2>(sm, L::oBufA);
     lt_reduce_small<H>(sm, grads + ar.off(0), ar.actor);
   }
   lt_teardown(cx);
@@ -730,6 +837,13 @@ static cudaError_t lt_set_smem(K kernel, size_t bytes) {
 }
 
 extern "C" {
+
+/* Development aid: switch the phase timestamps of the tf32 critic kernel on/off; out (nullable) receives the 128 clock64 stamps. */
+int32_t rtd3_debug_lt_prof(int32_t on, long long* out) {
+  RTD3_CUDA(cudaMemcpyToSymbol(g_lt_prof_on, &on, sizeof(int)));
+  if (out) RTD3_CUDA(cudaMemcpyFromSymbol(out, g_lt_prof, sizeof(long long) * 128));
+  return 0;
+}
 
 int32_t rtd3_td3_tf32_supported(const rtd3_td3* h) { return (h && lt_shape_ok(h)) ? 1 : 0; }
 
