@@ -163,6 +163,8 @@ TD3_SHAPES = [  # (label, batch, hidden, layers, epochs): configs[2] benchmark s
     ("B256_2x256", 256, 256, 2, 100),
     ("B100_3x200_reference_shape", 100, 200, 3, 100),
     ("B8192_2x256", 8192, 256, 2, 20),
+    ("B8192_2x256_tf32_tcgen05", 8192, 256, 2, 20),      # same shape on the tensor-core learner (opt-in precision="tf32")
+    ("B65536_2x256_tf32_tcgen05", 65536, 256, 2, 10),
 ]
 FP32_FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal: 148 SMs x 128 lanes x 2 flop x 1.965 GHz
 
@@ -206,7 +208,10 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         torch.manual_seed(0)
         agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L),
                        batch_size=B, num_epochs=epochs, device=dev, process_group=pg)
-        n = 10000
+        tf32 = label.endswith("tcgen05")
+        if tf32:
+            agent.precision = "tf32"
+        n = 10000 if B <= 10000 else 2 * B                # the reference's buffer size (robot.py:36) unless the batch needs more rows
         rb = rt.ReplayBuffer(n, device=dev, seed=rank)
         g = torch.Generator(device=dev).manual_seed(rank)
         s = torch.rand((n, 2), device=dev, generator=g) * 98.9999
@@ -214,8 +219,8 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         s2 = (s + a).clamp(0, 98.9999)
         r = -torch.linalg.norm(s2 - torch.tensor([80., 20.], device=dev), dim=1)
         rb.push(s, a, r, s2, (torch.arange(n, device=dev) % 50) == 49)
-        if B > n:
-            rb.sampler = "philox"                         # with replacement: the exact sampler needs batch <= rows
+        if B > 10000:
+            rb.sampler = "philox"                         # throughput sampler (the exact MT19937 protocol is timed on the shapes above)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         reps, ms_s, ms_u, ms_full = 4, [], [], []
         for rep in range(reps):                           # rep 0 captures the graphs / warms up
@@ -243,9 +248,15 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
                "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
                "updates_per_sec_update_only": epochs / (ms_update * 1e-3),
-               "tflops_fp32": flops / (ms_update * 1e-3) / 1e12,
-               "frac_of_nominal_fp32_peak": flops / (ms_update * 1e-3) / 1e12 / (FP32_FFMA_PEAK_TFLOPS * world)}
-        if cpu and rank == 0 and world == 1:
+               "precision": "tf32 (tcgen05.mma kind::tf32, fp32 accumulate in TMEM)" if tf32 else "fp32 (FFMA)"}
+        tfl = flops / (ms_update * 1e-3) / 1e12
+        if tf32:
+            row["tflops_tf32"] = tfl
+            row["frac_of_tf32_peak"] = tfl / (load_peaks()[1] / 2 * world)      # TF32 dense = half the measured bf16 figure
+        else:
+            row["tflops_fp32"] = tfl
+            row["frac_of_nominal_fp32_peak"] = tfl / (FP32_FFMA_PEAK_TFLOPS * world)
+        if cpu and rank == 0 and world == 1 and not tf32:
             e_cpu = 40 if B <= 256 else 4
             row["cpu_port_updates_per_sec"] = cpu_td3_epochs_per_sec(B, H, L, e_cpu)
         out.append(row)
