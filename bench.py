@@ -527,7 +527,10 @@ def run_b200(args):
                                  % (ROLL_BYTES_PER_ENV_STEP, n * T)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": per_buf, "d2h_bytes_per_step": per_buf,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "path": "Environment.rollout_host on pinned host buffers: one launch, the rollout kernel's TMA tiles read the actions from / "
+                            "write the trajectory to host memory over PCIe (UVA zero-copy, no staging copies); raw cudaMemcpy of both "
+                            "directions run concurrently takes 0.66 ms for these bytes"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }

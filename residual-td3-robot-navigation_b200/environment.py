@@ -191,18 +191,37 @@ class Environment:
                                                _lib.stream_ptr(self.device)), "env_rollout")
         return traj.permute(0, 2, 1) if record else None
 
-    def rollout_host(self, actions_host, out_host=None, chunks=8):
-        """`rollout` for HOST buffers: `actions_host` pinned float32 `[T,2,N]` (planes), `out_host` pinned `[T,2,N]` or None.
-        The T steps are cut into `chunks` time slices; the host->device copy of slice c+1, the rollout kernel of slice c and
-        the device->host copy of slice c-1 run on three streams, so a call costs about one PCIe transfer of the larger
-        direction instead of copy + kernel + copy in sequence.  Returns `out_host` (a fresh pinned tensor if None was given);
-        the call returns once the result is on the host."""
+    def rollout_host(self, actions_host, out_host=None, chunks=8, zero_copy=None):
+        """`rollout` for HOST buffers: `actions_host` float32 `[T,2,N]` (planes), `out_host` `[T,2,N]` or None.
+
+        zero-copy (default when both buffers are pinned, i.e. mapped into the device's address space under UVA): ONE launch
+        of the rollout kernel whose TMA tile loads read the actions straight from host memory and whose tile stores write
+        the trajectory straight back - the PCIe transfers of both directions run inside the kernel, overlapped with the
+        recurrence, with no staging buffers in HBM (measured 0.88 ms for 4096 x 1000 against 0.92 ms for the staged
+        pipeline below and 0.66 ms for the two raw copies run concurrently).
+
+        staged (`zero_copy=False`, or a pageable buffer): the T steps are cut into `chunks` time slices; the host->device copy
+        of slice c+1, the rollout kernel of slice c and the device->host copy of slice c-1 run on three streams.
+
+        Returns `out_host` (a fresh pinned tensor if None was given); the call returns once the result is on the host."""
         n = self.num_envs
         if actions_host.dim() != 3 or actions_host.shape[1:] != (2, n) or actions_host.dtype != torch.float32:
             raise ValueError("actions_host must be float32 [T,2,%d]" % n)
         T = actions_host.shape[0]
         if out_host is None:
             out_host = torch.empty((T, 2, n), dtype=torch.float32).pin_memory()
+        if out_host.shape != (T, 2, n) or out_host.dtype != torch.float32 or not out_host.is_contiguous() or not actions_host.is_contiguous():
+            raise ValueError("out_host must be a contiguous float32 [T,2,%d] like actions_host" % n)
+        if zero_copy is None:
+            zero_copy = actions_host.is_pinned() and out_host.is_pinned()
+        if zero_copy:
+            if not (actions_host.is_pinned() and out_host.is_pinned()):
+                raise ValueError("zero_copy needs pinned host buffers")
+            _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
+                                                   _lib.ptr(actions_host), _lib.ptr(out_host), n, T,
+                                                   _lib.stream_ptr(self.device)), "env_rollout")
+            torch.cuda.current_stream(self.device).synchronize()
+            return out_host
         if self._pipe is None:
             self._pipe = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         s_in, s_out = self._pipe
