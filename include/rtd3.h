@@ -273,6 +273,10 @@ int32_t rtd3_td3_critic_step_tf32(rtd3_td3* h, const float* params, const float*
 int32_t rtd3_td3_actor_step_tf32(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const float* rp_s,
                                  const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream);
 
+/* Development aid: switch the phase timestamps of the tf32 critic kernel (clock64 of CTA 0 / thread 0 at every phase
+ * boundary) on or off; `out` (nullable, host memory, 128 entries) receives the stamps of the last launch. */
+int32_t rtd3_debug_lt_prof(int32_t on, long long* out);
+
 #ifdef __cplusplus
 }
 #endif

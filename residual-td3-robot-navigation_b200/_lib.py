@@ -60,6 +60,7 @@ _SIGNATURES = {
     "rtd3_td3_tf32_supported": (c_int32, [_P]),
     "rtd3_td3_critic_step_tf32": (c_int32, [_P] * 11 + [c_int32, c_float, c_float, c_float, c_float] + [_P] * 6),
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),
+    "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
     "rtd3_robot_transition": (c_int32, [_P] * 16 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
