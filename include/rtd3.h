@@ -31,6 +31,8 @@ extern "C" {
 #define RTD3_WORLD_SIZE 100          /* constants.py:6  */
 #define RTD3_MAP_CELLS 10000         /* 100 x 100 cells, indexed [x][y] (environment.py:105-111) */
 #define RTD3_MT_N 624                /* MT19937 state words */
+#define RTD3_DEMO_GRID 32            /* demonstration-state grid of rtd3_robot_transition: 32 x 32 cells ... */
+#define RTD3_DEMO_CELL 4.0           /* ... of side 4 (covers [0,128)^2; points outside sit in the nearest border cell) */
 
 #define RTD3_ERR_ARG (-1)
 #define RTD3_ERR_STATE (-2)
@@ -222,13 +224,18 @@ int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* 
  * float64 shared by all envs, applied where demo_flag is set), check_if_stuck on the pre-step state
  * (robot.py:509-538, -50 penalty), done = plan_index == path_length - 1, and the replay push of the n rows at
  * (position + i) % capacity (rp_s == NULL skips the push).  reward float32 [n] (reward64 nullable float64).
+ * demo_cell_start (nullable int32 [RTD3_DEMO_GRID^2 + 1]): when given, `demo` is sorted by grid cell
+ * (cell = clamp(floor(x / RTD3_DEMO_CELL)) * RTD3_DEMO_GRID + clamp(floor(y / RTD3_DEMO_CELL)), cell c owning points
+ * [demo_cell_start[c], demo_cell_start[c+1])) and the nearest demonstration state is found by an exact ring search on
+ * that grid instead of the full sweep - same float64 operations per candidate, bit-identical result.
  * type (nullable int8 [n]): only envs of type 0 ('step') are processed; their rows are then compacted behind the
  * ring's device row counter rp_total (uint64 [1], rows ever pushed; required with type, optional otherwise -
  * when given it is advanced by n). */
 int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index,
                               const int32_t* path_length, const float* sx, const float* sy, const float* ax, const float* ay,
-                              const float* nx, const float* ny, const double* demo, int64_t num_demo, float* reward,
+                              const float* nx, const float* ny, const double* demo, const int32_t* demo_cell_start,
+                              int64_t num_demo, float* reward,
                               double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2,
                               float* rp_notdone, int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type,
                               int64_t n, void* stream);

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
-    "rtd3_robot_transition": (c_int32, [_P] * 16 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
+    "rtd3_robot_transition": (c_int32, [_P] * 17 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
     "rtd3_robot_next_action_type": (c_int32, [_P] * 10 + [c_int64, _P]),
 }
 

@@ -88,7 +88,9 @@ def test_transition_batched_flags_bit_exact_vs_oracle(pkg):
     goals = rs.uniform(5, 95, (n, 2))
     demos = rs.uniform(0, 99, (700, 2))
     robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=20000)
+    robot.demo_grid_min_points = 1                          # exercise the exact grid search against the oracle's cdist-style min
     robot.set_demonstration_states(demos)
+    assert robot._demo_cells is not None
     robot._demo_flag.fill_(1)
     robot._path_length.fill_(9)
     orcs = []
@@ -218,3 +220,41 @@ def test_graphed_trainer_matches_eager_trainer(pkg, env_golden):
     assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
     assert outs[0][2] == pytest.approx(outs[1][2], rel=1e-6) and outs[0][3] == pytest.approx(outs[1][3], rel=1e-6)
     assert torch.equal(outs[0][4], outs[1][4]) and torch.equal(outs[0][5], outs[1][5])
+
+
+@pytest.mark.parametrize("m", [64, 700, 11355])
+def test_demo_grid_search_is_bit_identical_to_the_full_sweep(pkg, m):
+    """robot.py:753: the proximity term is the min over ALL demonstration states.  The exact ring search on the uniform grid
+     must return the very same float64 as the full sweep: clustered demo paths (the reference's 3 785 states
+    per demonstration), augmentation noise pushing points outside [0,100), queries on cell edges / world borders / far from
+    every demo."""
+    n = 4096
+    rs = np.random.RandomState(m)
+    t = np.linspace(0, 1, m // 3 + 1)[:, None]
+    paths = [np.array([[5.0, 80.0]]) * (1 - t) + np.array([[90.0, 15.0]]) * t + rs.normal(0, s, (t.shape[0], 2)) for s in (0.5, 2.5, 6.0)]
+    demos = np.concatenate(paths)[:m]
+    demos[:5] = [[-3.0, 50.0], [104.5, 20.0], [50.0, -7.0], [131.0, 140.0], [99.99, 99.99]]      # outside the world / the grid
+    goals = np.tile(np.array([[500.0, 500.0]]), (n, 1))                                           # never reached: the demo term always counts
+    nxt = rs.uniform(0, 98.9999, (n, 2)).astype(np.float32)
+    nxt[:64, 0] = np.arange(64, dtype=np.float32) * 4.0 % 100                                     # on vertical cell edges
+    nxt[64:128, 1] = np.float32(98.9999)                                                          # world border
+    nxt[128:192] = np.float32(0.0)
+    nxt[192:256] = (demos[rs.randint(0, m, 64)]).clip(0, 98.9999).astype(np.float32)              # on top of demo states
+    cur = nxt.copy()
+    act = np.zeros((n, 2), np.float32)
+    out = []
+    for min_points in (10 ** 9, 1):                       # full sweep, then the grid
+        robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=20000)
+        robot.demo_grid_min_points = min_points
+        robot.set_demonstration_states(demos)
+        assert (robot._demo_cells is None) == (min_points > m)
+        robot._demo_flag.fill_(1)
+        robot.process_transition(torch.from_numpy(cur).cuda(), torch.from_numpy(act).cuda(), torch.from_numpy(nxt).cuda(), None)
+        out.append(robot._reward64.cpu().numpy().copy())
+    assert np.array_equal(out[0], out[1])
+    # and against cdist-style numpy on a few rows (the reference's own arithmetic, float64)
+    for i in (0, 70, 130, 200, 4095):
+        p = nxt[i].astype(np.float64)
+        d = np.sqrt(((demos - p) ** 2).sum(axis=1)).min()
+        ref = -np.linalg.norm(p - goals[i]) + 10 * (-d)
+        np.testing.assert_allclose(out[1][i], ref, rtol=1e-13)
