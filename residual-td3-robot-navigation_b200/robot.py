@@ -145,7 +145,12 @@ class Robot:
 
     def maybe_update(self):
         """Host half: read the finished-episode counter and run td3_update when due (robot.py:480-483)."""
-        if int(self._any_update.item()) >= self.episodes_per_update:
+        if self.td3_agent.world > 1:
+            from .trainer import update_due
+            due = update_due(self._any_update, self.episodes_per_update, self.td3_agent.process_group)
+        else:
+            due = int(self._any_update.item()) >= self.episodes_per_update
+        if due:
             self._any_update.zero_()
             self.td3_agent.td3_update(self.memory)
             self.num_updates += 1

@@ -36,6 +36,20 @@ def allreduce_grads_(flat_grads, group=None):
     return world
 
 
+def update_due(local_count, episodes_per_update, group=None):
+    """Whether a learner update is due, decided identically on every rank: the data-parallel `td3_update` all-reduces its
+    gradients, so all ranks must enter it in the same tick.  `local_count` (int tensor `[1]`, this rank's finished-episode
+    counter) is SUM-all-reduced and compared with `episodes_per_update` x world; with a single rank it is compared directly.
+    (A rank-local decision deadlocked the 2-GPU full-loop run: one rank entered the update's all-reduce, the other did not.)"""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        total = local_count.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return int(total.item()) >= int(episodes_per_update) * world
+    return int(local_count.item()) >= int(episodes_per_update)
+
+
 class BatchedTrainer:
     """`graph=True` captures the device work of one tick (state machine, act, step, transition + replay push, masked reset)
     in a CUDA graph and looks at the finished-episode counter only every `check_interval` ticks, so the tick costs one graph

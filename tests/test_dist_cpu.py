@@ -73,3 +73,39 @@ def test_gradient_allreduce_world2_gloo():
     for rank, seen, err, scale, _ in res:
         assert seen == 2
         assert err <= 1e-6 * max(1.0, scale)
+
+
+def _due_worker(rank, world, port, q):
+    import rtd3_b200 as rt
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        # (local counts per rank, episodes_per_update): ranks disagree locally, the collective decision must be the same
+        for counts, thr in (((5, 0), 4), ((5, 4), 4), ((0, 0), 1), ((3, 5), 4), ((8, 0), 4)):
+            out.append(rt.trainer.update_due(torch.tensor([counts[rank]], dtype=torch.int32), thr))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_update_decision_is_collective_world2_gloo():
+    """The full loop's `td3_update` all-reduces gradients, so every rank must take the same update / no-update decision in the
+    same tick (a rank-local decision deadlocked the 2-GPU run): SUM of the finished-episode counters against threshold x world."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_due_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert res[0] == res[1] == [False, True, False, True, True]
+
+
+def test_update_decision_single_rank():
+    import rtd3_b200 as rt
+    assert rt.trainer.update_due(torch.tensor([3]), 3) and not rt.trainer.update_due(torch.tensor([2]), 3)
