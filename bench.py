@@ -154,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 
@@ -541,9 +541,22 @@ def run_b200(args):
             line["actor_forward"] = fwd_rows
         if loop_row is not None:
             line["full_loop"] = loop_row
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -559,6 +572,12 @@ def main():
     ap.add_argument("--no-td3", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout on the
+    # first communicator): point fd 1 at stderr for the whole run and keep the real stdout for the result line only.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
