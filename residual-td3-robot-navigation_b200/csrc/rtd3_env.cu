@@ -387,15 +387,19 @@ env_rollout_tma_kernel(const float2* __restrict__ g_table, float* __restrict__ x
 // state); a HELPER warp on another scheduler of the same SM waits for the TMA action tiles, clips them (or flags the
 // chunk for the careful NaN path), re-arms the loads and issues the trajectory tile stores.  The two meet on mbarriers
 // over double-buffered shared-memory tiles.
+constexpr int kPairU = 32;        // steps per tile of the pair kernel
+constexpr int kPairStages = 4;    // action tiles in flight (128 steps of lead, as kDeep x kU)
 struct PairSmem {
   static constexpr int kBars = 16;   // full[8] | prepped[2] | consumed[2] | outfull[2] | outfree[2]
 };
 
-template <bool kTraj, int kStages>
+template <bool kTraj, int kStages, int kUp>
 __global__ void __launch_bounds__(256)
 env_rollout_pair_kernel(const float2* __restrict__ g_table, float* __restrict__ x, float* __restrict__ y,
                         const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_traj, int64_t n, int64_t T) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kU = kUp;                            // steps per action / trajectory tile of this kernel (shadows the file-wide kU)
+  constexpr int kTileFloats = kU * 2 * 32;
   float2* s_table = reinterpret_cast<float2*>(smem_raw);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + kTableBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, npairs = blockDim.x >> 6;
@@ -625,10 +629,10 @@ static void load_encode_tiled() {
 }
 
 // [T][2][n] float32 planes as a 2-D tensor: inner dim n, outer dim 2T, box = 32 envs x 2*kU rows
-static int32_t make_plane_map(CUtensorMap* tm, const float* base, int64_t n, int64_t T) {
+static int32_t make_plane_map(CUtensorMap* tm, const float* base, int64_t n, int64_t T, int steps_per_tile = kU) {
   const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)(2 * T)};
   const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
-  const cuuint32_t box[2] = {32, 2 * kU};
+  const cuuint32_t box[2] = {32, (cuuint32_t)(2 * steps_per_tile)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -663,8 +667,8 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
-  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
-  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<true, kPairStages, kPairU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
+  RTD3_CUDA(cudaFuncSetAttribute(env_rollout_pair_kernel<false, kPairStages, kPairU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll - 1024));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
@@ -753,12 +757,14 @@ int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, 
     const int bgrid = (int)ceil_div(warps_total, wpc);
     const int bsmem = ((kTableBytes + 16 + wpc * stages * 8 + 127) & ~127) + wpc * (stages + 2) * kTileFloats * 4;
     if (deep && g_rollout_variant != 1) {
-      // latency-bound batches: one chain warp + one helper warp per 32 envs, up to 2 pairs per CTA
+      // latency-bound batches: one chain warp + one helper warp per 32 envs, up to 2 pairs per CTA; tiles of kPairU steps
+      // (the per-tile hand-over - two barrier waits, the flag read, two arrives - was ~20 % of the chain warp's samples at 16)
       const int ppc = (int)std::max<int64_t>(1, std::min<int64_t>(2, ceil_div(warps_total, (int64_t)h->num_sms)));
       const int pgrid = (int)ceil_div(warps_total, ppc);
-      const int psmem = ((kTableBytes + 16 + ppc * PairSmem::kBars * 8 + 127) & ~127) + ppc * (kDeep + 4) * kTileFloats * 4;
-      if (traj) env_rollout_pair_kernel<true, kDeep><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
-      else env_rollout_pair_kernel<false, kDeep><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+      const int psmem = ((kTableBytes + 16 + ppc * PairSmem::kBars * 8 + 127) & ~127) + ppc * (kPairStages + 4) * (kPairU * 2 * 32) * 4;
+      if (make_plane_map(&tm_act, actions, n, T, kPairU) != 0 || make_plane_map(&tm_traj, traj ? traj : actions, n, T, kPairU) != 0) return RTD3_ERR_STATE;
+      if (traj) env_rollout_pair_kernel<true, kPairStages, kPairU><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
+      else env_rollout_pair_kernel<false, kPairStages, kPairU><<<pgrid, ppc * 64, psmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
     } else if (deep) {
       if (traj) env_rollout_tma_kernel<true, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);
       else env_rollout_tma_kernel<false, kDeep><<<bgrid, wpc * 32, bsmem, st>>>(h->table, x, y, tm_act, tm_traj, n, T);

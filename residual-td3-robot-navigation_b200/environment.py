@@ -191,17 +191,19 @@ class Environment:
                                                _lib.stream_ptr(self.device)), "env_rollout")
         return traj.permute(0, 2, 1) if record else None
 
-    def rollout_host(self, actions_host, out_host=None, chunks=8, zero_copy=None):
-        """`rollout` for HOST buffers: `actions_host` float32 `[T,2,N]` (planes), `out_host` `[T,2,N]` or None.
+    def rollout_host(self, actions_host, out_host=None, chunks=8, mode=None):
+        """`rollout` for HOST buffers: `actions_host` float32 `[T,2,N]` (planes), `out_host` `[T,2,N]` or None.  Pinned buffers
+        are mapped into the device's address space (UVA), so the rollout kernel's TMA tiles can cross PCIe themselves:
 
-        zero-copy (default when both buffers are pinned, i.e. mapped into the device's address space under UVA): ONE launch
-        of the rollout kernel whose TMA tile loads read the actions straight from host memory and whose tile stores write
-        the trajectory straight back - the PCIe transfers of both directions run inside the kernel, overlapped with the
-        recurrence, with no staging buffers in HBM (measured 0.88 ms for 4096 x 1000 against 0.92 ms for the staged
-        pipeline below and 0.66 ms for the two raw copies run concurrently).
-
-        staged (`zero_copy=False`, or a pageable buffer): the T steps are cut into `chunks` time slices; the host->device copy
-        of slice c+1, the rollout kernel of slice c and the device->host copy of slice c-1 run on three streams.
+        mode "zero_copy" (default for pinned buffers): ONE launch; the kernel's TMA tile loads read the actions from host memory
+            and its tile stores write the trajectory back, both overlapped with the recurrence, nothing staged in HBM
+            (0.91-0.93 ms per synchronous call for 4096 x 1000);
+        mode "hybrid": the T steps are cut into `chunks` time slices; the copy engine brings the actions of slice c+1 to HBM
+            while the kernel runs slice c and writes its trajectory tiles straight to the host buffer (0.95 ms per synchronous
+            call; 0.85 ms when calls are issued back to back without a host sync in between);
+        mode "staged" (any buffers; the default when one is pageable): H2D copy of slice c+1, kernel of slice c and D2H copy of
+            slice c-1 on three streams (0.92 ms).
+        For reference, the two raw copies run concurrently take 0.66 ms for these bytes: every mode is PCIe-bound.
 
         Returns `out_host` (a fresh pinned tensor if None was given); the call returns once the result is on the host."""
         n = self.num_envs
@@ -212,20 +214,23 @@ class Environment:
             out_host = torch.empty((T, 2, n), dtype=torch.float32).pin_memory()
         if out_host.shape != (T, 2, n) or out_host.dtype != torch.float32 or not out_host.is_contiguous() or not actions_host.is_contiguous():
             raise ValueError("out_host must be a contiguous float32 [T,2,%d] like actions_host" % n)
-        if zero_copy is None:
-            zero_copy = actions_host.is_pinned() and out_host.is_pinned()
-        if zero_copy:
-            if not (actions_host.is_pinned() and out_host.is_pinned()):
-                raise ValueError("zero_copy needs pinned host buffers")
+        pinned = actions_host.is_pinned() and out_host.is_pinned()
+        if mode is None:
+            mode = "zero_copy" if pinned else "staged"
+        if mode not in ("hybrid", "zero_copy", "staged"):
+            raise ValueError("mode must be 'hybrid', 'zero_copy' or 'staged'")
+        if mode != "staged" and not pinned:
+            raise ValueError("mode %r needs pinned host buffers" % mode)
+        main = torch.cuda.current_stream(self.device)
+        if mode == "zero_copy":
             _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
                                                    _lib.ptr(actions_host), _lib.ptr(out_host), n, T,
                                                    _lib.stream_ptr(self.device)), "env_rollout")
-            torch.cuda.current_stream(self.device).synchronize()
+            main.synchronize()
             return out_host
         if self._pipe is None:
             self._pipe = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         s_in, s_out = self._pipe
-        main = torch.cuda.current_stream(self.device)
         if self._pipe_buf is None or self._pipe_buf[0].shape != (T, 2, n):
             self._pipe_buf = (torch.empty((T, 2, n), dtype=torch.float32, device=self.device),
                               torch.empty((T, 2, n), dtype=torch.float32, device=self.device))
@@ -246,9 +251,12 @@ class Environment:
             if hi == lo:
                 continue
             main.wait_event(ev_in[c])
+            dst = out_host if mode == "hybrid" else d_traj
             _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
-                                                   _lib.ptr(d_act[lo:hi]), _lib.ptr(d_traj[lo:hi]), n, hi - lo,
+                                                   _lib.ptr(d_act[lo:hi]), _lib.ptr(dst[lo:hi]), n, hi - lo,
                                                    _lib.stream_ptr(self.device)), "env_rollout")
+            if mode == "hybrid":
+                continue
             e = torch.cuda.Event()
             e.record(main)
             with torch.cuda.stream(s_out):

@@ -250,21 +250,27 @@ def test_rollout_host_equals_device_rollout(pkg, env_golden):
     env_b = pkg.Environment(num_envs=n, seed=3, maps=(g["speed"], g["angle"]))
     env_a.reset(); env_b.reset()
     h_act = (torch.rand((T, 2, n)) * 15 - 7.5).pin_memory()
-    out = env_a.rollout_host(h_act, chunks=7, zero_copy=False)          # staged three-stream pipeline
+    out = env_a.rollout_host(h_act, chunks=7, mode="staged")           # staged three-stream pipeline
     ref = env_b.rollout(h_act.cuda())
     assert torch.equal(out.cuda().permute(0, 2, 1), ref)
     assert torch.equal(env_a.robot_state, env_b.robot_state)
     out2 = torch.empty((T, 2, n)).pin_memory()
-    assert env_a.rollout_host(h_act, out2, chunks=1, zero_copy=False) is out2
+    assert env_a.rollout_host(h_act, out2, chunks=1, mode="staged") is out2
     ref2 = env_b.rollout(h_act.cuda())
     assert torch.equal(out2.cuda().permute(0, 2, 1), ref2)
     out3 = torch.empty((T, 2, n)).pin_memory()
     before = pkg._lib.launch_count()
-    assert env_a.rollout_host(h_act, out3) is out3                       # pinned buffers: zero-copy, the kernel itself crosses PCIe
+    assert env_a.rollout_host(h_act, out3) is out3                       # pinned default: one launch, the kernel itself crosses PCIe both ways
     assert pkg._lib.launch_count() - before == 1
     ref3 = env_b.rollout(h_act.cuda())
     assert torch.equal(out3.cuda().permute(0, 2, 1), ref3)
     assert torch.equal(env_a.robot_state, env_b.robot_state)
+    out5 = torch.empty((T, 2, n)).pin_memory()
+    assert env_a.rollout_host(h_act, out5, chunks=6, mode="hybrid") is out5   # H2D slices by the copy engine, trajectory written to the host by the kernel
+    ref5 = env_b.rollout(h_act.cuda())
+    assert torch.equal(out5.cuda().permute(0, 2, 1), ref5)
+    with pytest.raises(ValueError):
+        env_a.rollout_host(h_act.clone(), mode="zero_copy")
     pageable = h_act.clone()                                             # a pageable input falls back to the staged pipeline
     out4 = env_a.rollout_host(pageable, chunks=3)
     ref4 = env_b.rollout(h_act.cuda())

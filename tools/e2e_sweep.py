@@ -50,3 +50,30 @@ try:
     print("zero-copy result equals device rollout:", bool(torch.equal(out.cuda().permute(0, 2, 1), ref)))
 except Exception as e:
     print("zero-copy failed:", e)
+
+# hybrid: the kernel reads the pinned actions itself (zero-copy in), trajectory slices go back through the copy engine
+s_out = torch.cuda.Stream()
+def hybrid(chunks, reverse=False):
+    main = torch.cuda.current_stream()
+    s_out.wait_stream(main)
+    bounds = [round(c * T / chunks) for c in range(chunks + 1)]
+    for c in range(chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if not reverse:
+            rt._lib.check(L.rtd3_env_rollout(env._handle, rt._lib.ptr(env._state[0]), rt._lib.ptr(env._state[1]), rt._lib.ptr(acts[lo:hi]), rt._lib.ptr(d[lo:hi]), N, hi - lo,
+                                             rt._lib.stream_ptr(env.device)), "hy")
+            e = torch.cuda.Event(); e.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                out[lo:hi].copy_(d[lo:hi], non_blocking=True)
+        else:      # staged H2D, zero-copy out
+            with torch.cuda.stream(s_out):
+                d[lo:hi].copy_(acts[lo:hi], non_blocking=True)
+                e = torch.cuda.Event(); e.record(s_out)
+            main.wait_event(e)
+            rt._lib.check(L.rtd3_env_rollout(env._handle, rt._lib.ptr(env._state[0]), rt._lib.ptr(env._state[1]), rt._lib.ptr(d[lo:hi]), rt._lib.ptr(out[lo:hi]), N, hi - lo,
+                                             rt._lib.stream_ptr(env.device)), "hy")
+    main.wait_stream(s_out)
+for chunks in (4, 8, 16):
+    t = timed(lambda: hybrid(chunks)); print("hybrid zero-copy in + D2H slices, %2d chunks: %.3f ms -> %.3e env-steps/s" % (chunks, t * 1e3, N * T / t))
+    t = timed(lambda: hybrid(chunks, True)); print("hybrid H2D slices + zero-copy out, %2d chunks: %.3f ms -> %.3e env-steps/s" % (chunks, t * 1e3, N * T / t))
