@@ -588,13 +588,17 @@ __global__ void init_goal_region_kernel(rtd3_mt_bank b, double* __restrict__ goa
 // environment.py:130-137
 __global__ void env_reset_kernel(rtd3_mt_bank b, const double* __restrict__ region, const uint8_t* __restrict__ mask,
                                  float* __restrict__ x, float* __restrict__ y, double* __restrict__ state64) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b.n) return;
-  if (mask && !mask[i]) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = b.n;
-  MtStream s{b.mt + i, n, b.pos[i]};
-  const double sx = s.uniform(region[i], region[n + i]);           // x in [left, right)
-  const double sy = s.uniform(region[2 * n + i], region[3 * n + i]);   // y in [bottom, top)
+  const bool active = i < n && (!mask || mask[i]);
+  if (!__any_sync(0xffffffffu, active)) return;
+  const int64_t ii = active ? i : 0;
+  MtStream s{b.mt + ii, n, active ? b.pos[ii] : 0};
+  // lo + (hi - lo) * u with numpy's two roundings; the draws go through the warp-cooperative wrap (see rtd3_mt.cuh)
+  const double ux = mt_next_double_warp(s, active), uy = mt_next_double_warp(s, active);
+  if (!active) return;
+  const double sx = __dadd_rn(region[i], __dmul_rn(__dsub_rn(region[n + i], region[i]), ux));                   // x in [left, right)
+  const double sy = __dadd_rn(region[2 * n + i], __dmul_rn(__dsub_rn(region[3 * n + i], region[2 * n + i]), uy));   // y in [bottom, top)
   // float32 rounding must not reach 100.0 (the cell index would leave the map): cap at the largest float below it
   x[i] = fminf((float)sx, 99.99999f); y[i] = fminf((float)sy, 99.99999f);
   if (state64) { state64[i] = sx; state64[n + i] = sy; }

@@ -70,6 +70,58 @@ struct MtStream {
   }
 };
 
+// The twist of one stream by a whole warp (all 32 lanes must call it): the serial loop above costs ~200 us when a single lane of
+// a warp runs it (624 dependent iterations of uncoalesced loads - it made EVERY masked reset of 65 536 envs take 200 us, because
+// the streams' positions are spread over the whole cycle after the goal rejection loop and ~0.6 % of them wrap per call).
+// Word k needs the OLD words k, k+1 and word (k+397) % 624, which is old for k < 227 and already new for k >= 227 (k-227 lies
+// more than a warp behind), and word 623 pairs with the NEW word 0: walking k upwards 32 words at a time, with all reads of a
+// group before its writes, reproduces the serial order exactly.
+__device__ __forceinline__ void mt_regenerate_warp(uint32_t* w, int64_t stride) {
+  constexpr int N = RTD3_MT_N, M = 397;
+  const int lane = threadIdx.x & 31;
+  for (int k0 = 0; k0 < N; k0 += 32) {
+    const int k = k0 + lane;
+    uint32_t cur = 0, nxt = 0, far = 0;
+    if (k < N) {
+      cur = w[(int64_t)k * stride];
+      nxt = w[(int64_t)(k + 1 < N ? k + 1 : 0) * stride];
+      far = w[(int64_t)(k + M < N ? k + M : k + M - N) * stride];
+    }
+    __syncwarp();
+    if (k < N) {
+      const uint32_t yv = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+      w[(int64_t)k * stride] = far ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+  }
+}
+
+// next_u32 for a warp whose lanes hold independent streams (lane-private `s`, `active` lanes draw): streams that have to wrap are
+// twisted one after the other by the whole warp.  All 32 lanes must call it.
+__device__ __forceinline__ uint32_t mt_next_u32_warp(MtStream& s, bool active) {
+  uint32_t need = __ballot_sync(0xffffffffu, active && s.pos >= RTD3_MT_N);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const unsigned long long wp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.w, src);
+    mt_regenerate_warp(reinterpret_cast<uint32_t*>((uintptr_t)wp), s.stride);
+    if ((int)(threadIdx.x & 31) == src) s.pos = 0;
+  }
+  uint32_t yv = 0;
+  if (active) {
+    yv = s.at(s.pos++);
+    yv ^= yv >> 11;
+    yv ^= (yv << 7) & 0x9d2c5680u;
+    yv ^= (yv << 15) & 0xefc60000u;
+    yv ^= yv >> 18;
+  }
+  return yv;
+}
+__device__ __forceinline__ double mt_next_double_warp(MtStream& s, bool active) {
+  const uint32_t a = mt_next_u32_warp(s, active) >> 5, b = mt_next_u32_warp(s, active) >> 6;
+  return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+
 // legacy_gauss with the spare kept in the bank. log/sqrt are float64 device libm (<= 1 ulp of glibc).
 __device__ inline double mt_gauss(MtStream& s, int& has_gauss, double& spare) {
   if (has_gauss) {

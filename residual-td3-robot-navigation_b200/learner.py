@@ -533,7 +533,7 @@ class TD3:
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
         C = self.sample_chunk_epochs
         if (idx is None and use_graph and self.world == 1 and C > 0 and E % C == 0 and C % delay == 0 and E > C
-                and len(replay_buffer) >= B):
+                and len(replay_buffer) >= B and getattr(replay_buffer, "sampler", "mt19937") == "mt19937"):   # the Philox draw costs microseconds: nothing to hide
             return self._td3_update_pipelined(replay_buffer, noise, C)
         n_actor = len([e for e in range(E) if e % delay == 0])
         count = E + n_actor

@@ -5,6 +5,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 env = rt.Environment(num_envs=n, seed=1)
 robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100, buffer_size=4 * n)
 robot.episodes_per_update = 10 ** 9
+robot.td3_agent.precision = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
 tr = rt.BatchedTrainer(env, robot, noise="randn", graph=False)
 for _ in range(12):
