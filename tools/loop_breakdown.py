@@ -28,3 +28,13 @@ print("tick(), no updates     : %.1f us/tick, host %.1f us/tick" % timed(tr.tick
 tr, robot = build(True)
 u0 = robot.num_updates
 print("tick(), with updates   : %.1f us/tick, host %.1f us/tick" % timed(tr.tick), "updates", robot.num_updates - u0)
+ag = robot.td3_agent
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ag.td3_update(robot.memory)
+    torch.cuda.synchronize(); print("td3_update(memory) call: %.2f ms (E=%d, B=%d, rows %d, sampler %s)" % ((time.perf_counter() - t0) * 1e3, ag.num_epochs, ag.batch_size, len(robot.memory), robot.memory.sampler))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(5): ag.td3_update(robot.memory)
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
