@@ -52,14 +52,11 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
   float* part = reinterpret_cast<float*>(bars + 2 * kTcStages + 2);                 // [2 column halves][128 rows][2] output-layer partial sums
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int r0 = blockIdx.x * kTcRows;
   const int rt = (warp & 3) * 32 + lane;            // row threads: tile row (= TMEM lane) ...
   const int c_lo = (warp >> 2) * (H / 2), c_hi = c_lo + H / 2;   // ... and column half of this thread
-  // CTAs of a cluster read the same weight slabs: each loads 1/C of a slab and multicasts it to all of them (L2 reads / C)
-  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int tiles = (B + kTcRows - 1) / kTcRows;
 
-  // ---- setup: small parameters to smem, barriers, TMEM allocation -------------------------------------------------
+  // ---- setup (once per CTA: the kernel is persistent over its tiles): small parameters, barriers, TMEM allocation -----
   for (int i = t; i < H * 4; i += kTcThreads) {
     const int c = i >> 2, j = i & 3;
     W1[i] = j < s.in ? __ldg(P + net_w_off(s, 0) + c * s.in + j) : 0.f;
@@ -70,7 +67,7 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
   for (int i = t; i < 2 * H; i += kTcThreads) Wo[i] = (i / H) < s.out ? __ldg(P + net_w_off(s, L) + i) : 0.f;
   if (t < 2) bo[t] = t < s.out ? __ldg(P + net_b_off(s, L) + t) : 0.f;
   if (t == 0) {
-    for (int i = 0; i < kTcStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, csize); }   // a stage is free when every CTA's MMAs have read it
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
@@ -79,116 +76,122 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (csize > 1) cluster_sync_all();            // barriers of every CTA initialised before any remote arrival / multicast
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-
-  // ---- first layer by the row threads: X = relu(b1 + x0 W1^T), written in the chunk layout ---------------------------
-  if (warp < kTcRowWarps) {
-    const int row = r0 + rt;
-    float x0[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < B)
-      for (int j = 0; j < s.in; ++j) x0[j] = x[(int64_t)row * s.in + j];
-    for (int c = c_lo; c < c_hi; c += 4) {
-      float4 h;
-      float* hp = &h.x;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(W1 + (c + q) * 4);
-        float v = b1[c + q];
-        v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
-        hp[q] = fmaxf(v, 0.f);
-      }
-      *reinterpret_cast<float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + rt * 4) = h;
-    }
-  }
-  fence_proxy_async();                  // generic-proxy writes of X -> visible to the tensor core (async proxy)
-  __syncthreads();
 
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = H, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
   const int slabs = H / kTcKSlab;
   const uint32_t stage_bytes = (uint32_t)H * (kTcKSlab / 4) * 16;      // 8 chunks x H rows x 16 B
-  uint32_t it_p = 0, it_c = 0;                                         // slab counters of producer / MMA issuer (continue across layers)
+  constexpr int kRowMma = (kTcRowWarps + 1) * 32;                      // named barrier 2: row warps + the MMA warp
 
-  for (int l = 1; l < L; ++l) {
-    if (warp == kTcRowWarps && lane == 0) {
-      // ===== TMA producer: one contiguous bulk copy per K slab of this layer's chunk-major weights =====
-      const float* Wu = Pu + net_w_off(s, l);
-      for (int ks = 0; ks < slabs; ++ks, ++it_p) {
-        const int st = it_p % kTcStages;
-        mbar_wait(empty + st, ((it_p / kTcStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(full + st, stage_bytes);
-        if (csize > 1) {
-          const uint32_t part = stage_bytes / csize;
-          bulk_g2s_multicast(Ws + (size_t)st * H * 32 + crank * (part / 4), Wu + (size_t)ks * H * 32 + crank * (part / 4), part, full + st, cmask);
-        } else {
-          bulk_g2s(Ws + (size_t)st * H * 32, Wu + (size_t)ks * H * 32, stage_bytes, full + st);
+  if (warp == kTcRowWarps) {
+    // ===== TMA producer: free-running over (tile, layer, K slab); one contiguous bulk copy per slab.  It is throttled only by the
+    // stage ring, so the first slabs of the next tile arrive while the row warps still work on the current one.
+    if (lane == 0) {
+      uint32_t it_p = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        for (int l = 1; l < L; ++l) {
+          const float* Wu = Pu + net_w_off(s, l);
+          for (int ks = 0; ks < slabs; ++ks, ++it_p) {
+            const int st = it_p % kTcStages;
+            mbar_wait(empty + st, ((it_p / kTcStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(full + st, stage_bytes);
+            bulk_g2s(Ws + (size_t)st * H * 32, Wu + (size_t)ks * H * 32, stage_bytes, full + st);
+          }
         }
+    }
+  } else if (warp == kTcRowWarps + 1) {
+    // ===== MMA issuer =====
+    uint32_t it_c = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+      for (int l = 1; l < L; ++l) {
+        bar_sync(2, kRowMma);                         // X of this layer is in shared memory, the accumulator has been drained
+        if (lane == 0) {
+          tc_fence_after();
+          for (int ks = 0; ks < slabs; ++ks, ++it_c) {
+            const int st = it_c % kTcStages;
+            mbar_wait(full + st, (it_c / kTcStages) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < kTcKSlab / 8; ++k4) {
+              const uint64_t ad = umma_desc_kmajor(smem_u32(Xs + (size_t)(ks * 8 + k4 * 2) * (kTcRows * 4)), kTcRows * 16, 128);
+              const uint64_t bd = umma_desc_kmajor(smem_u32(Ws + (size_t)st * H * 32 + (size_t)(k4 * 2) * H * 4), (uint32_t)H * 16, 128);
+              umma_tf32(tmem, ad, bd, idesc, (ks | k4) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty + st);                  // frees the weight stage once these MMAs have read it
+          }
+          umma_commit(acc_ready);                     // accumulator complete (commits track all prior MMAs)
+        }
+        __syncwarp();
       }
-    } else if (warp == kTcRowWarps + 1 && lane == 0) {
-      // ===== MMA issuer =====
-      for (int ks = 0; ks < slabs; ++ks, ++it_c) {
-        const int st = it_c % kTcStages;
-        mbar_wait(full + st, (it_c / kTcStages) & 1);
+  } else {
+    // ===== row warps: first layer, epilogues, output layer =====
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int r0 = tile * kTcRows;
+      const int row = r0 + rt;
+      float x0[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < B)
+        for (int j = 0; j < s.in; ++j) x0[j] = x[(int64_t)row * s.in + j];
+      // first layer: X = relu(b1 + x0 W1^T) in the chunk layout (the previous tile's readers of X are past their last barrier)
+      for (int c = c_lo; c < c_hi; c += 4) {
+        float4 h;
+        float* hp = &h.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(W1 + (c + q) * 4);
+          float v = b1[c + q];
+          v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
+          hp[q] = fmaxf(v, 0.f);
+        }
+        *reinterpret_cast<float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + rt * 4) = h;
+      }
+      for (int l = 1; l < L; ++l) {
+        fence_proxy_async();                          // generic-proxy writes of X -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        bar_sync(2, kRowMma);
+        // epilogue: TMEM -> registers -> bias + ReLU -> next X (in place: every MMA that read X has completed)
+        mbar_wait(acc_ready, acc_phase);
+        acc_phase ^= 1;
         tc_fence_after();
+        const float* bias = bh + (l - 1) * H;
+        for (int cb = c_lo; cb < c_hi; cb += 32) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-        for (int k4 = 0; k4 < kTcKSlab / 8; ++k4) {
-          const uint64_t ad = umma_desc_kmajor(smem_u32(Xs + (size_t)(ks * 8 + k4 * 2) * (kTcRows * 4)), kTcRows * 16, 128);
-          const uint64_t bd = umma_desc_kmajor(smem_u32(Ws + (size_t)st * H * 32 + (size_t)(k4 * 2) * H * 4), (uint32_t)H * 16, 128);
-          umma_tf32(tmem, ad, bd, idesc, (ks | k4) != 0 ? 1u : 0u);
+          for (int q = 0; q < 8; ++q) {
+            float4 h;
+            h.x = fmaxf(v[4 * q + 0] + bias[cb + 4 * q + 0], 0.f);
+            h.y = fmaxf(v[4 * q + 1] + bias[cb + 4 * q + 1], 0.f);
+            h.z = fmaxf(v[4 * q + 2] + bias[cb + 4 * q + 2], 0.f);
+            h.w = fmaxf(v[4 * q + 3] + bias[cb + 4 * q + 3], 0.f);
+            *reinterpret_cast<float4*>(Xs + (size_t)((cb >> 2) + q) * (kTcRows * 4) + rt * 4) = h;
+          }
         }
-        if (csize > 1) umma_commit_multicast(empty + st, cmask);   // frees the stage in every CTA that writes into it ...
-        else umma_commit(empty + st);                              // ... once these MMAs have read it
+        tc_fence_before();
       }
-      umma_commit(acc_ready);                         // accumulator complete (commits track all prior MMAs)
-    }
-    if (warp < kTcRowWarps) {
-      // ===== epilogue: TMEM -> registers -> bias + ReLU -> next X (in place: every MMA that read X has completed) =====
-      mbar_wait(acc_ready, (l - 1) & 1);
-      tc_fence_after();
-      const float* bias = bh + (l - 1) * H;
-      for (int cb = c_lo; cb < c_hi; cb += 32) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)cb, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 h;
-          h.x = fmaxf(v[4 * q + 0] + bias[cb + 4 * q + 0], 0.f);
-          h.y = fmaxf(v[4 * q + 1] + bias[cb + 4 * q + 1], 0.f);
-          h.z = fmaxf(v[4 * q + 2] + bias[cb + 4 * q + 2], 0.f);
-          h.w = fmaxf(v[4 * q + 3] + bias[cb + 4 * q + 3], 0.f);
-          *reinterpret_cast<float4*>(Xs + (size_t)((cb >> 2) + q) * (kTcRows * 4) + rt * 4) = h;
-        }
+      bar_sync(1, kTcRowWarps * 32);                  // both column halves of every row are written
+      // output layer: each thread sums its column half, the halves meet in shared memory
+      float o0 = 0.f, o1 = 0.f;
+      for (int c = c_lo; c < c_hi; c += 4) {
+        const float4 h = *reinterpret_cast<const float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + rt * 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(Wo + c), w1 = *reinterpret_cast<const float4*>(Wo + H + c);
+        o0 = fmaf(h.x, w0.x, o0); o0 = fmaf(h.y, w0.y, o0); o0 = fmaf(h.z, w0.z, o0); o0 = fmaf(h.w, w0.w, o0);
+        o1 = fmaf(h.x, w1.x, o1); o1 = fmaf(h.y, w1.y, o1); o1 = fmaf(h.z, w1.z, o1); o1 = fmaf(h.w, w1.w, o1);
       }
-      tc_fence_before();
-      fence_proxy_async();
+      part[((warp >> 2) * kTcRows + rt) * 2] = o0;
+      part[((warp >> 2) * kTcRows + rt) * 2 + 1] = o1;
+      bar_sync(1, kTcRowWarps * 32);
+      if (warp < 4 && row < B) {
+        y[(int64_t)row * s.out] = bo[0] + part[rt * 2] + part[(kTcRows + rt) * 2];
+        if (s.out > 1) y[(int64_t)row * s.out + 1] = bo[1] + part[rt * 2 + 1] + part[(kTcRows + rt) * 2 + 1];
+      }
     }
-    __syncthreads();
-    tc_fence_after();
-  }
-
-  // ---- output layer by the row threads: each sums its column half, the halves meet in shared memory ---------------------
-  if (warp < kTcRowWarps) {
-    float o0 = 0.f, o1 = 0.f;
-    for (int c = c_lo; c < c_hi; c += 4) {
-      const float4 h = *reinterpret_cast<const float4*>(Xs + (size_t)(c >> 2) * (kTcRows * 4) + rt * 4);
-      const float4 w0 = *reinterpret_cast<const float4*>(Wo + c), w1 = *reinterpret_cast<const float4*>(Wo + H + c);
-      o0 = fmaf(h.x, w0.x, o0); o0 = fmaf(h.y, w0.y, o0); o0 = fmaf(h.z, w0.z, o0); o0 = fmaf(h.w, w0.w, o0);
-      o1 = fmaf(h.x, w1.x, o1); o1 = fmaf(h.y, w1.y, o1); o1 = fmaf(h.z, w1.z, o1); o1 = fmaf(h.w, w1.w, o1);
-    }
-    part[((warp >> 2) * kTcRows + rt) * 2] = o0;
-    part[((warp >> 2) * kTcRows + rt) * 2 + 1] = o1;
-  }
-  __syncthreads();
-  if (warp < 4 && r0 + rt < B) {
-    y[(int64_t)(r0 + rt) * s.out] = bo[0] + part[rt * 2] + part[(kTcRows + rt) * 2];
-    if (s.out > 1) y[(int64_t)(r0 + rt) * s.out + 1] = bo[1] + part[rt * 2 + 1] + part[(kTcRows + rt) * 2 + 1];
   }
   tc_fence_before();
-  if (csize > 1) cluster_sync_all();            // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  else __syncthreads();
+  __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
 }
 
@@ -211,8 +214,6 @@ __global__ void sync_chunk_major_kernel(NetShape actor, NetShape critic, int64_t
 }  // namespace rtd3
 
 using namespace rtd3;
-
-static int g_tc_cluster = [] { const char* e = getenv("RTD3_TC_CLUSTER"); const int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();   // multicast measured slower (57.8 / 64.0 / 66.3 us at 65536 rows for 1 / 2 / 4): the products are not L2-bound, and a stage is only free once the slowest CTA of the cluster has read it
 
 extern "C" {
 
@@ -242,22 +243,16 @@ int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, 
     RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  // clusters of g_tc_cluster CTAs share each weight slab through TMA multicast (grid rounded up: the surplus CTAs work on masked rows)
+  // persistent: one CTA per SM (193 KB of shared memory each) walking its tiles; setup and TMEM allocation happen once per CTA
   const int tiles = (int)ceil_div(batch, kTcRows);
-  const int cl = tiles >= g_tc_cluster ? g_tc_cluster : 1;
-  const int grid = (tiles + cl - 1) / cl * cl;
-  if (cl > 1) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    const float* P = params + param_off; const float* Pu = params_u + param_off; int Bi = (int)batch;
-    RTD3_CUDA(cudaLaunchKernelEx(&cfg, mlp_forward_tc_kernel, s, P, Pu, x, y, Bi));
-  } else {
-    mlp_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, params_u + param_off, x, y, (int)batch);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    RTD3_CUDA(cudaGetDevice(&dev));
+    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  mlp_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, params_u + param_off, x, y, (int)batch);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -26,6 +26,8 @@ tr, robot = build(False)
 print("graph replay only      : %.1f us/tick on the GPU, %.1f us/tick of host issue time" % timed(lambda: tr._graph.replay()))
 print("tick(), no updates     : %.1f us/tick, host %.1f us/tick" % timed(tr.tick))
 tr, robot = build(True)
+while robot.num_updates < 1:
+    tr.tick()
 u0 = robot.num_updates
 print("tick(), with updates   : %.1f us/tick, host %.1f us/tick" % timed(tr.tick), "updates", robot.num_updates - u0)
 ag = robot.td3_agent
