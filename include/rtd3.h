@@ -106,10 +106,11 @@ int32_t rtd3_mt_draw_gauss(const rtd3_mt_bank* bank, double* out, int64_t k, voi
 int32_t rtd3_env_init_goal_region(const rtd3_mt_bank* bank, double* goal, double* region, void* stream);
 
 /* Environment.reset / get_random_robot_init_state (environment.py:130-137) for the envs whose
- * mask byte is non-zero (mask NULL = all).  Writes float32 state x,y; if state64 ([2][n] float64)
+ * mask byte is non-zero (mask NULL = all), or - with mask_equals >= 0 - equal to mask_equals (so that the int8 action
+ * types of rtd3_robot_next_action_type can be passed as they are: mask_equals = 2 resets the 'reset' envs).  Writes float32 state x,y; if state64 ([2][n] float64)
  * is non-NULL also the reference's float64 draw, which is bit-exact vs numpy. */
-int32_t rtd3_env_reset(const rtd3_mt_bank* bank, const double* region, const uint8_t* mask, float* x, float* y,
-                       double* state64, void* stream);
+int32_t rtd3_env_reset(const rtd3_mt_bank* bank, const double* region, const uint8_t* mask, int32_t mask_equals, float* x,
+                       float* y, double* state64, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay ring + minibatch sampling           (robot.py:58-124)
@@ -246,6 +247,10 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
 int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, int32_t* plan_index, int32_t* path_length,
                                     uint8_t* goal_reached, uint8_t* stuck_flag, double* noise_scale, int8_t* type_out,
                                     uint8_t* update_out, int32_t* any_update, int64_t n, void* stream);
+
+/* Money counters of the driver loop (robot-learning.py:78, 86, 99: one reset / one step bought) for n envs in one launch:
+ * steps[i] += (type[i] == 0), resets[i] += (type[i] == 2). */
+int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, TF32) large-batch forward - opt-in throughput mode, not the parity path

@@ -39,7 +39,7 @@ _SIGNATURES = {
     "rtd3_mt_draw_u32": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
     "rtd3_mt_draw_gauss": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
     "rtd3_env_init_goal_region": (c_int32, [POINTER(MtBankStruct), _P, _P, _P]),
-    "rtd3_env_reset": (c_int32, [POINTER(MtBankStruct), _P, _P, _P, _P, _P, _P]),
+    "rtd3_env_reset": (c_int32, [POINTER(MtBankStruct), _P, _P, c_int32, _P, _P, _P, _P]),
     "rtd3_replay_push": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rtd3_replay_gather": (c_int32, [_P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P]),
     "rtd3_sample_indices_mt19937": (c_int32, [POINTER(MtBankStruct), c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
@@ -61,6 +61,7 @@ _SIGNATURES = {
     "rtd3_td3_critic_step_tf32": (c_int32, [_P] * 11 + [c_int32, c_float, c_float, c_float, c_float] + [_P] * 6),
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),
     "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
+    "rtd3_trainer_tally": (c_int32, [_P, _P, _P, c_int64, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
     "rtd3_robot_transition": (c_int32, [_P] * 17 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),

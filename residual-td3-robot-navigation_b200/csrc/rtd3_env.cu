@@ -586,11 +586,11 @@ __global__ void init_goal_region_kernel(rtd3_mt_bank b, double* __restrict__ goa
 }
 
 // environment.py:130-137
-__global__ void env_reset_kernel(rtd3_mt_bank b, const double* __restrict__ region, const uint8_t* __restrict__ mask,
+__global__ void env_reset_kernel(rtd3_mt_bank b, const double* __restrict__ region, const uint8_t* __restrict__ mask, int mask_equals,
                                  float* __restrict__ x, float* __restrict__ y, double* __restrict__ state64) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = b.n;
-  const bool active = i < n && (!mask || mask[i]);
+  const bool active = i < n && (!mask || (mask_equals >= 0 ? mask[i] == (uint8_t)mask_equals : mask[i] != 0));
   if (!__any_sync(0xffffffffu, active)) return;
   const int64_t ii = active ? i : 0;
   MtStream s{b.mt + ii, n, active ? b.pos[ii] : 0};
@@ -826,12 +826,12 @@ int32_t rtd3_env_init_goal_region(const rtd3_mt_bank* bank, double* goal, double
   return 0;
 }
 
-int32_t rtd3_env_reset(const rtd3_mt_bank* bank, const double* region, const uint8_t* mask, float* x, float* y,
+int32_t rtd3_env_reset(const rtd3_mt_bank* bank, const double* region, const uint8_t* mask, int32_t mask_equals, float* x, float* y,
                        double* state64, void* stream) {
   if (int32_t e = check_bank(bank)) return e;
   RTD3_CHECK_ARG(region && x && y, "null argument");
   if (bank->n == 0) return 0;
-  env_reset_kernel<<<(int)ceil_div(bank->n, 128), 128, 0, (cudaStream_t)stream>>>(*bank, region, mask, x, y, state64);
+  env_reset_kernel<<<(int)ceil_div(bank->n, 128), 128, 0, (cudaStream_t)stream>>>(*bank, region, mask, mask_equals, x, y, state64);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -297,7 +297,23 @@ __global__ void robot_action_type_kernel(int32_t* __restrict__ num_episodes, uin
 
 using namespace rtd3;
 
+__global__ void trainer_tally_kernel(const int8_t* __restrict__ type, int64_t* __restrict__ steps, int64_t* __restrict__ resets, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int8_t t = type[i];
+  if (t == 0) steps[i] += 1;
+  else if (t == 2) resets[i] += 1;
+}
+
 extern "C" {
+
+int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, int64_t n, void* stream) {
+  RTD3_CHECK_ARG(type && steps && resets && n >= 0, "bad argument");
+  if (n == 0) return 0;
+  trainer_tally_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(type, steps, resets, n);
+  RTD3_LAUNCHED();
+  return 0;
+}
 
 int32_t rtd3_robot_baseline(const float* x, const float* y, const double* goal, float* base, int64_t n, void* stream) {
   RTD3_CHECK_ARG(x && y && goal && base && n >= 0, "bad argument");

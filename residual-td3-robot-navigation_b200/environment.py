@@ -267,13 +267,19 @@ class Environment:
         return out_host
 
     # ---- environment.py:130-137 ---------------------------------------------------------------------
-    def reset(self, mask=None):
-        """Redraw the start state inside the fixed init region (all envs, or those where `mask` is set)."""
-        m = None
+    def reset(self, mask=None, where_equals=None):
+        """Redraw the start state inside the fixed init region: all envs, those where `mask` is set, or - `where_equals` given -
+        those where the int8 / uint8 tensor `mask` equals that value (the action types of the batched loop go in as they are)."""
+        m, eq = None, -1
         if mask is not None:
-            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if where_equals is not None:
+                if mask.dtype not in (torch.int8, torch.uint8):
+                    raise TypeError("where_equals needs an int8 / uint8 tensor")
+                m, eq = mask.to(self.device).contiguous(), int(where_equals)
+            else:
+                m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         self._rng_in()
-        _lib.check(_lib.lib().rtd3_env_reset(self._bank.ref, _lib.ptr(self._region), _lib.ptr(m), _lib.ptr(self._state[0]),
+        _lib.check(_lib.lib().rtd3_env_reset(self._bank.ref, _lib.ptr(self._region), _lib.ptr(m), eq, _lib.ptr(self._state[0]),
                                              _lib.ptr(self._state[1]), _lib.ptr(self._state64),
                                              _lib.stream_ptr(self.device)), "env_reset")
         self._rng_out()

@@ -88,9 +88,10 @@ class BatchedTrainer:
         action = robot.get_next_action_training(state, None, noise=z, types=types)
         next_state = env.step(action)                                         # null action where the env is not stepping
         robot.process_transition(state, action, next_state, None, types=types)
-        env.reset(mask=types == 2)
-        self.steps_bought += (types == 0)
-        self.resets_bought += (types == 2)
+        env.reset(mask=types, where_equals=2)                                 # the 'reset' envs, straight from the type array
+        from . import _lib
+        _lib.check(_lib.lib().rtd3_trainer_tally(_lib.ptr(types), _lib.ptr(self.steps_bought), _lib.ptr(self.resets_bought), self.n,
+                                                 _lib.stream_ptr(self.device)), "trainer_tally")
         return types
 
     def tick(self):
