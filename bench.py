@@ -337,6 +337,8 @@ def bench_full_loop(rt, torch, dev, world, rank):
                      "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
                      "note": "one CUDA graph per tick, finished-episode counter read every 8 ticks; noise torch.randn, replay sampling philox"})
         del tr, robot, env
+        import gc
+        gc.collect()                                     # finalise the handles (cudaFree) now, not inside the next config's graph capture
     return rows
 
 # ------------------------------------------------------------------------------------------ GPU arm

@@ -119,6 +119,37 @@ def require_cuda(t, dtype, name):
     return t
 
 
+class capture:
+    """`torch.cuda.graph(graph)` with Python's cyclic garbage collector held off for the duration of the capture.  A collection
+    that happens to run inside the capture can finalise objects of an earlier experiment (environments, learners: reference cycles
+    keep them alive until the collector finds them) whose destructors call cudaFree - a prohibited call while a stream is
+    capturing, which invalidates the capture (seen as 'operation failed due to a previous error during capture' at the next
+    launch; whether it happened depended on how much garbage earlier code had produced)."""
+
+    def __init__(self, graph):
+        self._ctx = torch.cuda.graph(graph)
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self._was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._ctx.__enter__()
+        except BaseException:
+            if self._was_enabled:
+                gc.enable()
+            raise
+
+    def __exit__(self, *exc):
+        import gc
+        try:
+            return self._ctx.__exit__(*exc)
+        finally:
+            if self._was_enabled:
+                gc.enable()
+
+
 def launch_count():
     return int(lib().rtd3_launch_count())
 

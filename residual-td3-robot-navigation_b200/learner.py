@@ -578,7 +578,7 @@ class TD3:
                 if st["graph"] is None:
                     graph = torch.cuda.CUDAGraph()
                     before = _lib.launch_count()
-                    with torch.cuda.graph(graph):
+                    with _lib.capture(graph):
                         st["closs"].zero_()
                         st["aloss"].zero_()
                         self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])

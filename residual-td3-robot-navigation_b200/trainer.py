@@ -101,7 +101,7 @@ class BatchedTrainer:
                 self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
                 g = torch.cuda.CUDAGraph()
                 before = _launches()
-                with torch.cuda.graph(g):
+                with _capture(g):
                     self._types = self._device_tick()
                 self._graph, self._graph_launches = g, _launches() - before
                 _add_launches(-self._graph_launches)
@@ -115,6 +115,11 @@ class BatchedTrainer:
         if self.ticks % self.check_interval == 0:
             self.robot.maybe_update()                                         # robot-learning.py:68 -> robot.py:480-483
         return types
+
+
+def _capture(graph):
+    from . import _lib
+    return _lib.capture(graph)
 
 
 def _launches():
