@@ -548,12 +548,36 @@ __global__ void mt_draw_u32_kernel(rtd3_mt_bank b, uint32_t* __restrict__ out, i
 }
 
 __global__ void mt_draw_gauss_kernel(rtd3_mt_bank b, double* __restrict__ out, int64_t k) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b.n) return;
-  MtStream s{b.mt + i, b.n, b.pos[i]};
-  int hg = b.has_gauss[i];
-  double sp = b.gauss[i];
-  for (int64_t j = 0; j < k; ++j) out[j * b.n + i] = mt_gauss(s, hg, sp);
+  // legacy_gauss (rtd3_mt.cuh: mt_gauss) for one stream per lane, warp-synchronous so that wrapping streams are twisted by the whole
+  // warp: this is the exploration noise of every tick in the exact-noise mode, and ~1 % of the streams wrap per call
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < b.n;
+  if (!__any_sync(0xffffffffu, active)) return;
+  const int64_t ii = active ? i : 0;
+  MtStream s{b.mt + ii, b.n, active ? b.pos[ii] : 0};
+  int hg = active ? b.has_gauss[ii] : 0;
+  double sp = active ? b.gauss[ii] : 0.0;
+  for (int64_t j = 0; j < k; ++j) {
+    double v = 0.0;
+    bool searching = active && !hg;
+    if (active && hg) { v = sp; sp = 0.0; hg = 0; }
+    while (__any_sync(0xffffffffu, searching)) {
+      const double u1 = mt_next_double_warp(s, searching), u2 = mt_next_double_warp(s, searching);
+      if (searching) {
+        const double x1 = __dsub_rn(__dmul_rn(2.0, u1), 1.0), x2 = __dsub_rn(__dmul_rn(2.0, u2), 1.0);
+        const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+        if (!(r2 >= 1.0 || r2 == 0.0)) {
+          const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+          sp = __dmul_rn(f, x1);
+          hg = 1;
+          v = __dmul_rn(f, x2);
+          searching = false;
+        }
+      }
+    }
+    if (active) out[j * b.n + i] = v;
+  }
+  if (!active) return;
   b.pos[i] = s.pos;
   b.has_gauss[i] = hg;
   b.gauss[i] = sp;
