@@ -41,8 +41,10 @@ constexpr int kLtColGroups = kLtEpi / kLtRows;   // thread t: row t % 64, column
 template <int H>
 struct Lt {
   static constexpr int kBuf = H * kLtRows;          // one activation buffer [H/4][64][4]
-  static constexpr int kStage = H * 32;             // one K slab of 32: [8 chunks][H][4]
-  static constexpr int kSlabs = H / 32;
+  static constexpr int kSlabK = 16;                 // K per weight slab = 2 MMAs
+  static constexpr int kStages = 4;                 // slabs in flight: the TMA latency (~800 cycles) against 256 cycles of MMA per slab
+  static constexpr int kStage = H * kSlabK;         // one K slab: [kSlabK/4 chunks][H][4]
+  static constexpr int kSlabs = H / kSlabK;
   static constexpr int oBufA = 0;
   static constexpr int oBufB = kBuf;
   static constexpr int oStage = 2 * kBuf;           // 2 weight stages, aliased by the dW staging tiles (8 warps x 2 x 4 KB)
@@ -58,9 +60,9 @@ struct Lt {
   static constexpr int oDout = oOut + 128;          // [64][2] gradient w.r.t. the output
   static constexpr int oPart = oDout + 128;         // [8][64][2] partial sums of the output layer / input gradient
   static constexpr int oBar = oPart + kLtColGroups * 128;          // full[2] empty[2] acc_ready stage_free (uint64) + tmem slot
-  static constexpr int kFloats = oBar + 16;
+  static constexpr int kFloats = oBar + 32;         // full[4] empty[4] acc_ready stage_free (uint64) + tmem slot
   static constexpr size_t kBytes = (size_t)kFloats * 4 + 1024;
-  static_assert(2 * kStage <= kStageRegion, "weight stages exceed their region");   // = the two re-laid dW operands of lt_dw
+  static_assert(kStages * kStage <= kStageRegion && 2 * H * 32 <= kStageRegion, "weight stages / re-laid dW operands exceed their region");   // = the two re-laid dW operands of lt_dw
 };
 
 // Development aid: phase timestamps of CTA 0 / thread 0 (rtd3_debug_lt_prof), off unless switched on.
@@ -209,7 +211,7 @@ __device__ __forceinline__ void lt_gemm(float* sm, LtCtx& cx, const float* __res
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::oBar);
-  uint64_t *full = bars, *empty = bars + 2, *acc = bars + 4, *sfree = bars + 5;
+  uint64_t *full = bars, *empty = bars + L::kStages, *acc = bars + 2 * L::kStages, *sfree = bars + 2 * L::kStages + 1;
   constexpr uint32_t kBytes = (uint32_t)L::kStage * 4;
   if (warp == kLtEpiWarps) {
     if (lane == 0) {
@@ -218,8 +220,8 @@ __device__ __forceinline__ void lt_gemm(float* sm, LtCtx& cx, const float* __res
         cx.gate_phase ^= 1;
       }
       for (int ks = 0; ks < L::kSlabs; ++ks, ++cx.it_p) {
-        const int st = cx.it_p & 1;
-        mbar_wait(empty + st, ((cx.it_p >> 1) & 1) ^ 1);
+        const int st = cx.it_p % L::kStages;
+        mbar_wait(empty + st, ((cx.it_p / L::kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(full + st, kBytes);
         bulk_g2s(sm + L::oStage + st * L::kStage, Wg + (size_t)ks * L::kStage, kBytes, full + st);
       }
@@ -232,12 +234,12 @@ __device__ __forceinline__ void lt_gemm(float* sm, LtCtx& cx, const float* __res
       // D = F32, A = B = TF32, both K-major, N = H, M = 64
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(kLtRows >> 4) << 24);
       for (int ks = 0; ks < L::kSlabs; ++ks, ++cx.it_c) {
-        const int st = cx.it_c & 1;
-        mbar_wait(full + st, (cx.it_c >> 1) & 1);
+        const int st = cx.it_c % L::kStages;
+        mbar_wait(full + st, (cx.it_c / L::kStages) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const int kk = ks * 4 + k4;                // K step of 8 = chunks 2kk, 2kk+1
+        for (int k4 = 0; k4 < L::kSlabK / 8; ++k4) {
+          const int kk = ks * (L::kSlabK / 8) + k4;  // K step of 8 = chunks 2kk, 2kk+1
           const uint64_t ad = umma_desc_kmajor(smem_u32(sm + a_buf + kk * (2 * kLtRows * 4)), kLtRows * 16, 128);
           const uint64_t bd = umma_desc_kmajor(smem_u32(sm + L::oStage + st * L::kStage + k4 * (2 * H * 4)), (uint32_t)H * 16, 128);
           umma_tf32(cx.tmem, ad, bd, idesc, kk != 0 ? 1u : 0u);
@@ -263,7 +265,7 @@ template <int H>
 __device__ __forceinline__ void lt_dw(float* sm, LtCtx& cx, int dz_buf, int h_buf) {
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 4;
+  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 2 * L::kStages;
   constexpr int kOp = H * 32;                        // floats of one re-laid operand (32 rows x H)
 #pragma unroll 1
   for (int round = 0; round < 2; ++round) {
@@ -316,7 +318,7 @@ __device__ __forceinline__ void lt_drain(float* sm, LtCtx& cx, const CUtensorMap
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::oBar);
-  uint64_t *acc = bars + 4, *sfree = bars + 5;
+  uint64_t *acc = bars + 2 * L::kStages, *sfree = bars + 2 * L::kStages + 1;
   if (warp < kLtEpiWarps) {
     const int q = warp & 3, ch = warp >> 2;
     mbar_wait(acc, cx.acc_phase);
@@ -364,7 +366,7 @@ template <int H, int kMode>
 __device__ __forceinline__ void lt_epilogue(float* sm, LtCtx& cx, int bias_off, int dst_buf) {
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 4;
+  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 2 * L::kStages;
   const int q = warp & 3, ch = warp >> 2;
   const int r = 16 * q + (lane & 15);               // M = 64: row i sits in TMEM lane (i % 16) + 32 * (i / 16)
   mbar_wait(acc, cx.acc_phase);
@@ -402,7 +404,7 @@ template <int H>
 __device__ __forceinline__ void lt_epilogue_din(float* sm, LtCtx& cx) {
   using L = Lt<H>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 4;
+  uint64_t* acc = reinterpret_cast<uint64_t*>(sm + L::oBar) + 2 * L::kStages;
   const int q = warp & 3, ch = warp >> 2;
   const int r = 16 * q + (lane & 15);
   mbar_wait(acc, cx.acc_phase);
@@ -558,13 +560,12 @@ __device__ __forceinline__ float* lt_setup(LtCtx& cx) {
   extern __shared__ unsigned char lt_raw[];
   float* sm = reinterpret_cast<float*>(lt_raw + ((1024u - (smem_u32(lt_raw) & 1023u)) & 1023u));   // stays in the shared window
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::oBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * L::kStages + 2);
   const int t = threadIdx.x;
   if (t == 0) {
-    mbar_init(bars + 0, 1); mbar_init(bars + 1, 1);     // full
-    mbar_init(bars + 2, 1); mbar_init(bars + 3, 1);     // empty
-    mbar_init(bars + 4, 1);                             // acc_ready
-    mbar_init(bars + 5, kLtEpiWarps);                   // stage_free: one arrival per epilogue warp
+    for (int i = 0; i < 2 * L::kStages; ++i) mbar_init(bars + i, 1);   // full[kStages], empty[kStages]
+    mbar_init(bars + 2 * L::kStages, 1);                // acc_ready
+    mbar_init(bars + 2 * L::kStages + 1, kLtEpiWarps);  // stage_free: one arrival per epilogue warp
     fence_mbar_init();
   }
   if (t < 32) {
