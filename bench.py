@@ -27,10 +27,10 @@ ACTION_RANGE = 7.5
 SEED = 1707366464
 ROLL_BYTES_PER_ENV_STEP = 16   # 8 B action read + 8 B state written; state stays in registers
 STEP_BYTES_PER_ENV_STEP = 24   # single-step kernel: state in 8 + action in 8 + state out 8
-# dram__bytes_read.sum + dram__bytes_write.sum of one env_rollout_tma_kernel launch at 4096 envs x 1000 steps, from the
-# `ncu --set full` capture summarised in profiles/r1_ncu_summaries.md (32.905 MB read + 0.454 MB written: the actions are read
+# dram__bytes_read.sum + dram__bytes_write.sum of one env_rollout_pair_kernel launch at 4096 envs x 1000 steps, from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_summaries.md (32.923 MB read + 0.561 MB written: the actions are read
 # once = algorithmic; the 32.8 MB trajectory is still in the 126 MB L2 when the kernel ends)
-ROLLOUT_NCU_DRAM_BYTES = 32905472 + 454144
+ROLLOUT_NCU_DRAM_BYTES = 32922880 + 560640
 
 
 def load_peaks():
