@@ -313,6 +313,28 @@ __global__ void td3_sync_transposed_kernel(Arena ar, const float* __restrict__ p
   }
 }
 
+// Where arena element o (offset inside its network's slot) sits in the derived copies, decomposed ONCE per element in 32-bit
+// arithmetic: the 64-bit divisions of transposed_index / chunk_major_index (five calls per element) made this kernel ~13 us.
+struct CopyIndex {
+  int t, u, v;          // offsets inside the slot in the transposed / forward chunk-major / input-gradient chunk-major copies
+  bool hidden;          // a hidden-to-hidden weight (the only entries that move, and that are TF32-rounded in u / v)
+};
+__device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
+  CopyIndex c{o, o, o, false};
+  const int first = s.in * s.hid + s.hid, blk = s.hid * s.hid + s.hid;
+  if (o < first) return c;
+  const unsigned o2 = (unsigned)(o - first);
+  const unsigned l = o2 / (unsigned)blk, rem = o2 - l * (unsigned)blk;
+  if ((int)l >= s.layers - 1 || rem >= (unsigned)(s.hid * s.hid)) return c;
+  const unsigned n = rem / (unsigned)s.hid, k = rem - n * (unsigned)s.hid;
+  const int base = first + (int)l * blk;
+  c.hidden = true;
+  c.t = base + (int)(k * s.hid + n);
+  c.u = base + (int)((((k >> 2) * s.hid + n) << 2) + (k & 3u));
+  c.v = base + (int)((((n >> 2) * s.hid + k) << 2) + (n & 3u));
+  return c;
+}
+
 __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ params_uv, float* __restrict__ grads, float* __restrict__ m,
                                        float* __restrict__ v, const double* __restrict__ beta_pows, int nets, float lr_actor,
                                        float lr_critic, float grad_scale, int polyak, float tau) {
@@ -324,12 +346,16 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
     s_bc2[threadIdx.x] = (float)sqrt(bc2);
   }
   __syncthreads();
-  const int64_t n_online = ar.online_total();
-  const int64_t c1 = ar.off(1);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_online; i += (int64_t)gridDim.x * blockDim.x) {
-    const int net = i < c1 ? 0 : (i < ar.off(2) ? 1 : 2);
+  const int n_online = (int)ar.online_total(), total = (int)ar.total();
+  const int off1 = (int)ar.off(1), off2 = (int)ar.off(2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_online; i += gridDim.x * blockDim.x) {
+    const int net = i < off1 ? 0 : (i < off2 ? 1 : 2);
+    const bool do_adam = (nets >> net) & 1, do_polyak = (polyak >> net) & 1;
+    if (!do_adam && !do_polyak) continue;
+    const int noff = net == 0 ? 0 : (net == 1 ? off1 : off2);
+    const CopyIndex ci = copy_index(net == 0 ? ar.actor : ar.critic, i - noff);
     float p = params[i];
-    if ((nets >> net) & 1) {
+    if (do_adam) {
       const int o = net == 0 ? 0 : 1;
       const float g = grads[i] * grad_scale;
       grads[i] = 0.f;
@@ -340,24 +366,20 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
       const float denom = sqrtf(vi) / s_bc2[o] + 1e-8f;
       p = p - s_step[o] * (mi / denom);
       params[i] = p;
-      params_t[transposed_index(net == 0 ? ar.actor : ar.critic, ar.off(net), i)] = p;
+      params_t[noff + ci.t] = p;
       if (params_uv) {                                                  // tensor-core operand copies (see rtd3_td3.cuh)
-        const NetShape& s = net == 0 ? ar.actor : ar.critic;
-        const float pr = is_hidden_weight(s, ar.off(net), i) ? tf32_rn(p) : p;
-        params_uv[chunk_major_index(s, ar.off(net), i)] = pr;
-        params_uv[ar.total() + chunk_major_index_v(s, ar.off(net), i)] = pr;
+        const float pr = ci.hidden ? tf32_rn(p) : p;
+        params_uv[noff + ci.u] = pr;
+        params_uv[total + noff + ci.v] = pr;
       }
     }
-    if ((polyak >> net) & 1) {
-      const int64_t ti = n_online + i;                                // target slots mirror the online layout
+    if (do_polyak) {
+      const int ti = n_online + i;                                    // target slots mirror the online layout
       // torch evaluates target*(1-tau) + source*tau as three separately rounded float32 ops (robot.py:309): no fma here
       const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
       params[ti] = tv;
-      params_t[transposed_index(net == 0 ? ar.actor : ar.critic, n_online + ar.off(net), ti)] = tv;
-      if (params_uv) {
-        const NetShape& s = net == 0 ? ar.actor : ar.critic;
-        params_uv[chunk_major_index(s, n_online + ar.off(net), ti)] = is_hidden_weight(s, n_online + ar.off(net), ti) ? tf32_rn(tv) : tv;
-      }
+      params_t[n_online + noff + ci.t] = tv;
+      if (params_uv) params_uv[n_online + noff + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
     }
   }
 }
