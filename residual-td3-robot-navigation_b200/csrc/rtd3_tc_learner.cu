@@ -325,14 +325,16 @@ __device__ __forceinline__ void lt_drain(float* sm, LtCtx& cx, const CUtensorMap
     cx.acc_phase ^= 1;
     tc_fence_after();
     float* stg = sm + L::oStage + warp * 1024;       // one 32 x 32 fp32 tile per warp (4 KB, 1024 B aligned)
-    // every CTA reduces into the same H x H block of the arena: start at a CTA-dependent block so that the L2 does not see
-    // all CTAs hitting the same addresses at the same time
-    constexpr int kBlk = H / 128, kIter = (H / 128) * kBlk;   // 32-column blocks of this warp's column quarter, times row halves
+    // Every CTA reduces into the same H x H block of the arena, and the L2 serialises reduce-adds to one address.  The four warps
+    // of a TMEM sub-partition (ch = 0..3) share its kTiles = (row halves) x (32-column blocks) tiles, kIter each; which tile a
+    // warp takes at step `it` is rotated by the CTA index, so that at any moment the CTAs are spread over all kTiles positions
+    // (with a rotation over the warp's own kIter tiles only, a quarter of the CTAs hit the same addresses at the same time).
+    constexpr int kTiles = (H / 128) * (H / 32), kIter = kTiles / 4;
 #pragma unroll 1
     for (int it = 0; it < kIter; ++it) {
       {
-        const int e = (it + (int)blockIdx.x) % kIter;
-        const int hf = e / kBlk, cb = ch * (H / 4) + (e % kBlk) * 32;
+        const int e = (ch * kIter + it + (int)blockIdx.x) % kTiles;
+        const int hf = e / (H / 32), cb = (e % (H / 32)) * 32;
         float v[32];
         tmem_ld32(cx.tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * H + cb), v);
         float* dst = stg;
