@@ -321,7 +321,7 @@ def bench_full_loop(rt, torch, dev, world, rank):
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ticks, upd0, steps0 = 240, robot.num_updates, int(tr.steps_bought.sum())
+        ticks, upd0, steps0 = 480, robot.num_updates, int(tr.steps_bought.sum())   # long enough to average over the update cadence
         e0.record()
         for _ in range(ticks):
             tr.tick()
