@@ -23,14 +23,15 @@
 namespace rtd3 {
 
 constexpr int kTcRows = 128;          // batch rows per CTA = UMMA M
-constexpr int kTcRowWarps = 8;        // two per TMEM sub-partition: warp w serves rows 32*(w%4).. and column half w/4
-constexpr int kTcThreads = (kTcRowWarps + 2) * 32;   // warps 0-7: row threads / epilogue, warp 8: TMA producer, warp 9: MMA issuer
+constexpr int kTcRowWarps = 16;       // four per TMEM sub-partition: warp w serves rows 32*(w%4).. and column quarter w/4 (H % 128 == 0),
+constexpr int kTcColParts = kTcRowWarps / 4;   // else two active per sub-partition with column halves (H % 64 == 0)
+constexpr int kTcThreads = (kTcRowWarps + 2) * 32;   // warps 0-15: row threads / epilogue, warp 16: TMA producer, warp 17: MMA issuer
 constexpr int kTcKSlab = 32;          // K per pipeline stage = 4 MMAs of K=8
 constexpr int kTcStages = 2;
 
 // Shared-memory plan (bytes): X [H/4][128][4] | W stages [2][8][H][4] | small params | barriers | tmem base
 __host__ __device__ inline size_t tc_smem_bytes(int hid, int layers) {
-  return (size_t)hid * 512 + (size_t)kTcStages * hid * 128 + ((size_t)hid * 4 + hid + (size_t)(layers - 1) * hid + 2 * hid + 4) * 4 + 64 + 2 * kTcRows * 2 * 4;
+  return (size_t)hid * 512 + (size_t)kTcStages * hid * 128 + ((size_t)hid * 4 + hid + (size_t)(layers - 1) * hid + 2 * hid + 4) * 4 + 64 + kTcColParts * kTcRows * 2 * 4;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -49,11 +50,15 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
   uint64_t* bars = reinterpret_cast<uint64_t*>(bo + 4);                             // full[2], empty[2], acc_ready
   uint64_t* full = bars, *empty = bars + kTcStages, *acc_ready = bars + 2 * kTcStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
-  float* part = reinterpret_cast<float*>(bars + 2 * kTcStages + 2);                 // [2 column halves][128 rows][2] output-layer partial sums
+  float* part = reinterpret_cast<float*>(bars + 2 * kTcStages + 2);                 // [column parts][128 rows][2] output-layer partial sums
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int rt = (warp & 3) * 32 + lane;            // row threads: tile row (= TMEM lane) ...
-  const int c_lo = (warp >> 2) * (H / 2), c_hi = c_lo + H / 2;   // ... and column half of this thread
+  // ... and column part of this thread: quarters when every quarter is a whole number of 32-column TMEM loads, else halves or
+  // the whole row (the surplus warps of each sub-partition then idle through the barriers with an empty column range)
+  const int parts = (H % (32 * kTcColParts) == 0) ? kTcColParts : ((H % 64 == 0) ? 2 : 1);
+  const int cpart = warp >> 2;
+  const int c_lo = cpart < parts ? cpart * (H / parts) : 0, c_hi = cpart < parts ? c_lo + H / parts : 0;
   const int tiles = (B + kTcRows - 1) / kTcRows;
 
   // ---- setup (once per CTA: the kernel is persistent over its tiles): small parameters, barriers, TMEM allocation -----
@@ -172,7 +177,7 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
         }
         tc_fence_before();
       }
-      bar_sync(1, kTcRowWarps * 32);                  // both column halves of every row are written
+      bar_sync(1, kTcRowWarps * 32);                  // all column parts of every row are written
       // output layer: each thread sums its column half, the halves meet in shared memory
       float o0 = 0.f, o1 = 0.f;
       for (int c = c_lo; c < c_hi; c += 4) {
@@ -181,12 +186,15 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
         o0 = fmaf(h.x, w0.x, o0); o0 = fmaf(h.y, w0.y, o0); o0 = fmaf(h.z, w0.z, o0); o0 = fmaf(h.w, w0.w, o0);
         o1 = fmaf(h.x, w1.x, o1); o1 = fmaf(h.y, w1.y, o1); o1 = fmaf(h.z, w1.z, o1); o1 = fmaf(h.w, w1.w, o1);
       }
-      part[((warp >> 2) * kTcRows + rt) * 2] = o0;
-      part[((warp >> 2) * kTcRows + rt) * 2 + 1] = o1;
+      part[(cpart * kTcRows + rt) * 2] = o0;        // warps without columns contribute zeros
+      part[(cpart * kTcRows + rt) * 2 + 1] = o1;
       bar_sync(1, kTcRowWarps * 32);
       if (warp < 4 && row < B) {
-        y[(int64_t)row * s.out] = bo[0] + part[rt * 2] + part[(kTcRows + rt) * 2];
-        if (s.out > 1) y[(int64_t)row * s.out + 1] = bo[1] + part[rt * 2 + 1] + part[(kTcRows + rt) * 2 + 1];
+        float y0 = bo[0], y1 = bo[1];
+#pragma unroll
+        for (int c = 0; c < kTcColParts; ++c) { y0 += part[(c * kTcRows + rt) * 2]; y1 += part[(c * kTcRows + rt) * 2 + 1]; }
+        y[(int64_t)row * s.out] = y0;
+        if (s.out > 1) y[(int64_t)row * s.out + 1] = y1;
       }
     }
   }

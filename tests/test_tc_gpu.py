@@ -8,7 +8,7 @@ from oracle import td3_oracle as to
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("H,L,B", [(256, 2, 128), (256, 2, 1000), (256, 3, 4096), (128, 2, 300), (64, 4, 129), (256, 2, 65536)])
+@pytest.mark.parametrize("H,L,B", [(256, 2, 128), (256, 2, 1000), (256, 3, 4096), (128, 2, 300), (64, 4, 129), (256, 2, 65536), (96, 2, 700), (160, 3, 257), (192, 2, 20000)])
 def test_tf32_forward_matches_fp32_forward(pkg, H, L, B):
     torch.manual_seed(0)
     agent = pkg.TD3(pkg.Residual_Actor_Network(H, L), pkg.Residual_Critic_Network(H, L), pkg.Residual_Critic_Network(H, L))
