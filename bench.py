@@ -304,7 +304,9 @@ def bench_full_loop(rt, torch, dev, world, rank):
     pg = dist.group.WORLD if world > 1 else None
     rows = []
     # 8192 envs per GPU x 8 GPUs = the 65 536 envs of configs[3]; 65 536 per GPU = the large end of the metric's env range
-    for n, precision in ((8192, "fp32"), (8192, "tf32"), (65536, "fp32"), (65536, "tf32")):
+    # "hooks": one launch per reference hook (ten per tick); "fused": rtd3_tick_pre / actor forward / rtd3_tick_post, eight ticks per graph
+    for n, precision, form in ((8192, "fp32", "hooks"), (8192, "tf32", "hooks"), (8192, "tf32", "fused"),
+                               (65536, "fp32", "hooks"), (65536, "tf32", "hooks"), (65536, "tf32", "fused")):
         env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
         robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 4 * n))
         robot.td3_agent.precision = precision          # "tf32": the actor forward of the act hook runs on tcgen05 tensor cores
@@ -312,19 +314,20 @@ def bench_full_loop(rt, torch, dev, world, rank):
         robot.td3_agent.num_epochs = 20
         robot.memory.sampler = "philox"
         robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
-        tr = rt.BatchedTrainer(env, robot, noise="randn", graph=True, check_interval=8)
+        fused = form == "fused"
+        tr = rt.BatchedTrainer(env, robot, noise="philox" if fused else "randn", graph=True, check_interval=8, fused=fused)
+        advance = tr.run if fused else (lambda k: [tr.tick() for _ in range(k)])
         warm = 0
         while warm < 16 or (robot.num_updates < 1 and warm < 400):      # past the first learner update: its one-time graph
-            tr.tick()                                                  # capture (tens of ms) is not part of the steady state
-            warm += 1
+            advance(8)                                                 # capture (tens of ms) is not part of the steady state
+            warm += 8
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ticks, upd0, steps0 = 480, robot.num_updates, int(tr.steps_bought.sum())   # long enough to average over the update cadence
         e0.record()
-        for _ in range(ticks):
-            tr.tick()
+        advance(ticks)
         e1.record()
         torch.cuda.synchronize(dev)
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -333,10 +336,12 @@ def bench_full_loop(rt, torch, dev, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(st)
         ms = float(t[0])
-        rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "ticks": ticks, "ms_per_tick": ms / ticks,
+        rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "tick": form, "ticks": ticks, "ms_per_tick": ms / ticks,
                      "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
                      "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
-                     "note": "one CUDA graph per tick, finished-episode counter read every 8 ticks; noise torch.randn, replay sampling philox"})
+                     "note": ("three launches per tick, eight ticks per CUDA graph; noise Philox inside the tick kernel" if fused else
+                              "ten launches per tick, one CUDA graph per tick; noise torch.randn")
+                             + "; finished-episode counter read every 8 ticks; replay sampling philox"})
         del tr, robot, env
         import gc
         gc.collect()                                     # finalise the handles (cudaFree) now, not inside the next config's graph capture

@@ -253,6 +253,77 @@ int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, i
 int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused tick of the batched driver loop        (robot-learning.py:66-101, training branch)
+ * ---------------------------------------------------------------------------------------------- */
+/* Everything one tick touches, for n envs.  HOST struct of DEVICE pointers (same arrays as the per-hook entry points above take). */
+typedef struct rtd3_tick_state {
+  int64_t n;
+  /* Environment */
+  float* x;                     /* [n] robot_state planes, stepped / reset in place */
+  float* y;
+  const double* goal;           /* [2][n] */
+  const double* region;         /* [4][n] left,right,bottom,top */
+  double* state64;              /* nullable [2][n]: float64 value of the last reset draw */
+  rtd3_mt_bank env_bank;        /* the envs' reset streams */
+  /* Robot episode state (robot.py:421-438) */
+  int32_t* num_episodes;        /* [n] */
+  uint8_t* demo_flag;
+  int32_t* plan_index;
+  int32_t* path_length;
+  uint8_t* goal_reached;
+  uint8_t* stuck_flag;
+  double* noise_scale;
+  float* hist;                  /* [5][2][n] */
+  int32_t* hist_count;
+  int32_t* hist_head;
+  int8_t* type;                 /* [n] out: 0 'step', 1 'demo', 2 'reset' */
+  uint8_t* update;              /* [n] out: episode ended in this tick */
+  int32_t* any_update;          /* [1] accumulates the number of ended episodes */
+  /* per-tick outputs */
+  float* base;                  /* [n][2] actor input (state - goal) written by rtd3_tick_pre */
+  float* ax;                    /* [n] action planes */
+  float* ay;
+  float* prev_x;                /* nullable [n]: pre-step state */
+  float* prev_y;
+  float* reward;                /* [n] (stepping envs only) */
+  double* reward64;             /* nullable */
+  uint8_t* done;                /* [n] */
+  /* demonstration states shared by all envs (as rtd3_robot_transition) */
+  const double* demo;
+  const int32_t* demo_cell_start;
+  int64_t num_demo;
+  /* replay ring (masked push through the device row counter) */
+  float* rp_s;
+  float* rp_a;
+  float* rp_r;
+  float* rp_s2;
+  float* rp_notdone;
+  int64_t capacity;
+  uint64_t* rp_total;
+  /* money counters (robot-learning.py:78, 86, 99) */
+  int64_t* steps_bought;        /* [n] */
+  int64_t* resets_bought;       /* [n] */
+  /* exploration noise of mode RTD3_TICK_NOISE_PHILOX: normals = f(philox_seed, tick_counter[0], env) */
+  uint64_t philox_seed;
+  uint64_t* tick_counter;       /* nullable [1]; incremented by rtd3_tick_pre */
+} rtd3_tick_state;
+
+#define RTD3_TICK_NOISE_NONE 0     /* get_next_action_testing: no exploration noise (robot.py:575-595) */
+#define RTD3_TICK_NOISE_GIVEN 1    /* unit normals supplied ([2][n] float64, e.g. rtd3_mt_draw_gauss: numpy-exact) */
+#define RTD3_TICK_NOISE_PHILOX 2   /* unit normals generated in the kernel (Philox4x32-10 + Box-Muller, throughput mode) */
+
+/* First half of a tick: rtd3_robot_next_action_type (robot.py:443-506; robot-learning.py:68) and rtd3_robot_baseline
+ * (robot.py:556) in one launch.  The caller then runs the actor forward on t->base. */
+int32_t rtd3_tick_pre(const rtd3_tick_state* t, void* stream);
+
+/* Second half, one launch: rtd3_robot_compose_action (robot.py:560-567), rtd3_env_step (environment.py:122-127),
+ * rtd3_robot_transition with the masked replay push (robot.py:645-675), rtd3_trainer_tally and rtd3_env_reset for the envs whose
+ * type is 'reset' (robot-learning.py:82-101).  residual: [n][2] actor output.  Leaves every array bit-identical to the sequence
+ * of those calls. */
+int32_t rtd3_tick_post(rtd3_env* h, const rtd3_tick_state* t, const float* residual, const double* unit_noise, int32_t noise_mode,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, TF32) large-batch forward - opt-in throughput mode, not the parity path
  * ---------------------------------------------------------------------------------------------- */
 

@@ -20,6 +20,23 @@ class MtBankStruct(Structure):
     _fields_ = [("mt", c_void_p), ("pos", c_void_p), ("has_gauss", c_void_p), ("gauss", c_void_p), ("n", c_int64)]
 
 
+class TickStateStruct(Structure):
+    """`rtd3_tick_state` of include/rtd3.h (same field order)."""
+    _fields_ = ([("n", c_int64)]
+                + [(k, c_void_p) for k in ("x", "y", "goal", "region", "state64")]
+                + [("env_bank", MtBankStruct)]
+                + [(k, c_void_p) for k in ("num_episodes", "demo_flag", "plan_index", "path_length", "goal_reached", "stuck_flag", "noise_scale",
+                                           "hist", "hist_count", "hist_head", "type", "update", "any_update",
+                                           "base", "ax", "ay", "prev_x", "prev_y", "reward", "reward64", "done",
+                                           "demo", "demo_cell_start")]
+                + [("num_demo", c_int64)]
+                + [(k, c_void_p) for k in ("rp_s", "rp_a", "rp_r", "rp_s2", "rp_notdone")]
+                + [("capacity", c_int64), ("rp_total", c_void_p), ("steps_bought", c_void_p), ("resets_bought", c_void_p),
+                   ("philox_seed", c_uint64), ("tick_counter", c_void_p)])
+
+
+TICK_NOISE_NONE, TICK_NOISE_GIVEN, TICK_NOISE_PHILOX = 0, 1, 2
+
 _P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -62,6 +79,8 @@ _SIGNATURES = {
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),
     "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
     "rtd3_trainer_tally": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "rtd3_tick_pre": (c_int32, [POINTER(TickStateStruct), _P]),
+    "rtd3_tick_post": (c_int32, [_P, POINTER(TickStateStruct), _P, _P, c_int32, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
     "rtd3_robot_transition": (c_int32, [_P] * 17 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),

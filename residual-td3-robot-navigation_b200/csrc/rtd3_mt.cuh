@@ -73,27 +73,48 @@ struct MtStream {
 // The twist of one stream by a whole warp (all 32 lanes must call it): the serial loop above costs ~200 us when a single lane of
 // a warp runs it (624 dependent iterations of uncoalesced loads - it made EVERY masked reset of 65 536 envs take 200 us, because
 // the streams' positions are spread over the whole cycle after the goal rejection loop and ~0.6 % of them wrap per call).
-// Word k needs the OLD words k, k+1 and word (k+397) % 624, which is old for k < 227 and already new for k >= 227 (k-227 lies
-// more than a warp behind), and word 623 pairs with the NEW word 0: walking k upwards 32 words at a time, with all reads of a
-// group before its writes, reproduces the serial order exactly.
+// Here the 624 words are held in registers, word k = 32 j + lane in v[j] of that lane: ONE round of 20 independent loads, the
+// recurrence on warp shuffles, one round of stores (the first warp-wide version walked 32 words at a time through memory:
+// 20 dependent L2 round trips, ~20 us per twist).  Word k needs the OLD words k, k+1 and word (k+397) % 624, which is old for
+// k < 227 and already new for k >= 227 (k-227 lies 7-8 groups behind), and word 623 pairs with the NEW word 0: walking j upwards
+// with every shuffle of a group taken before the group is overwritten reproduces the serial order exactly.
 __device__ __forceinline__ void mt_regenerate_warp(uint32_t* w, int64_t stride) {
-  constexpr int N = RTD3_MT_N, M = 397;
+  constexpr int N = RTD3_MT_N, J = (RTD3_MT_N + 31) / 32;            // 20 groups; the last one holds words 608..623 in lanes 0..15
+  constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  for (int k0 = 0; k0 < N; k0 += 32) {
-    const int k = k0 + lane;
-    uint32_t cur = 0, nxt = 0, far = 0;
-    if (k < N) {
-      cur = w[(int64_t)k * stride];
-      nxt = w[(int64_t)(k + 1 < N ? k + 1 : 0) * stride];
-      far = w[(int64_t)(k + M < N ? k + M : k + M - N) * stride];
+  uint32_t v[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) v[j] = (32 * j + lane < N) ? w[(int64_t)(32 * j + lane) * stride] : 0u;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int k = 32 * j + lane;
+    uint32_t nxt = __shfl_down_sync(kFull, v[j], 1);                 // word k+1 for lanes 0..30 (old: taken before the write below)
+    const uint32_t first_of_next = __shfl_sync(kFull, j + 1 < J ? v[j + 1] : 0u, 0);
+    if (lane == 31) nxt = first_of_next;
+    if (j == J - 1) {
+      const uint32_t w0 = __shfl_sync(kFull, v[0], 0);               // word 623 pairs with the NEW word 0
+      if (k == N - 1) nxt = w0;
     }
-    __syncwarp();
-    if (k < N) {
-      const uint32_t yv = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-      w[(int64_t)k * stride] = far ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
+    uint32_t far;
+    if (j <= 6) {                                                    // k + 397 < 624 for the whole group: old words (j+12, lane+13) / (j+13, lane-19)
+      const int src = (lane + 13) & 31;
+      const uint32_t a = __shfl_sync(kFull, v[j + 12], src), b = __shfl_sync(kFull, v[j + 13], src);
+      far = lane + 13 < 32 ? a : b;
+    } else if (j >= 8) {                                             // new words k - 227 = (j-8, lane+29) / (j-7, lane-3)
+      const int src = (lane + 29) & 31;
+      const uint32_t a = __shfl_sync(kFull, v[j - 8], src), b = __shfl_sync(kFull, v[j - 7], src);
+      far = lane < 3 ? a : b;
+    } else {                                                         // j == 7: words 224..226 still pair with old 621..623, the rest with new 0..28
+      const uint32_t a = __shfl_sync(kFull, v[J - 1], (lane + 13) & 31), b = __shfl_sync(kFull, v[0], (lane + 29) & 31);
+      far = lane < 3 ? a : b;
     }
-    __syncwarp();
+    const uint32_t yv = (v[j] & 0x80000000u) | (nxt & 0x7fffffffu);
+    v[j] = far ^ (yv >> 1) ^ ((yv & 1u) ? 0x9908b0dfu : 0u);
   }
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (32 * j + lane < N) w[(int64_t)(32 * j + lane) * stride] = v[j];
+  __syncwarp();
 }
 
 // next_u32 for a warp whose lanes hold independent streams (lane-private `s`, `active` lanes draw): streams that have to wrap are
@@ -117,9 +138,32 @@ __device__ __forceinline__ uint32_t mt_next_u32_warp(MtStream& s, bool active) {
   }
   return yv;
 }
+// K consecutive words per active lane through ONE inlined copy of the twist (the loop is kept rolled: every inlined copy of
+// mt_regenerate_warp costs ~1.5 KB of code and its 20 state registers at the call site)
+template <int K>
+__device__ __forceinline__ void mt_next_words_warp(MtStream& s, bool active, uint32_t (&out)[K]) {
+#pragma unroll 1
+  for (int h = 0; h < K; ++h) {
+    const uint32_t t = mt_next_u32_warp(s, active);
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+      if (q == h) out[q] = t;
+  }
+}
+__device__ __forceinline__ double mt_double_from_words(uint32_t w0, uint32_t w1) {
+  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
+}
 __device__ __forceinline__ double mt_next_double_warp(MtStream& s, bool active) {
-  const uint32_t a = mt_next_u32_warp(s, active) >> 5, b = mt_next_u32_warp(s, active) >> 6;
-  return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+  uint32_t w[2] = {0u, 0u};
+  mt_next_words_warp<2>(s, active, w);
+  return mt_double_from_words(w[0], w[1]);
+}
+// two doubles in draw order (uniform(lo, hi, 2): x first, then y)
+__device__ __forceinline__ void mt_next_double2_warp(MtStream& s, bool active, double& u0, double& u1) {
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  mt_next_words_warp<4>(s, active, w);
+  u0 = mt_double_from_words(w[0], w[1]);
+  u1 = mt_double_from_words(w[2], w[3]);
 }
 
 // legacy_gauss with the spare kept in the bank. log/sqrt are float64 device libm (<= 1 ulp of glibc).

@@ -54,9 +54,17 @@ class BatchedTrainer:
     """`graph=True` captures the device work of one tick (state machine, act, step, transition + replay push, masked reset)
     in a CUDA graph and looks at the finished-episode counter only every `check_interval` ticks, so the tick costs one graph
     launch instead of a dozen kernel launches and a device->host read.  With `graph=False, check_interval=1` every tick is
-    launched eagerly and checked immediately (the single-env-like behaviour)."""
+    launched eagerly and checked immediately (the single-env-like behaviour).
 
-    def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1):
+    `fused=True` runs the tick as three launches - `rtd3_tick_pre`, the actor forward, `rtd3_tick_post` (csrc/rtd3_tick.cu) -
+    instead of one launch per hook; every array ends up bit-identical (tests/test_tick_gpu.py), only the order in which the
+    stepping envs' rows land in the replay ring differs (it is atomic-ordered in both forms).  `run(ticks)` with `graph=True`
+    replays `check_interval` fused ticks from ONE graph.
+
+    noise: "mt19937" per-env numpy-legacy streams (exact mode); "randn" torch's generator; "philox" (fused only) normals
+    generated inside `rtd3_tick_post` from (seed, device tick counter, env)."""
+
+    def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1, fused=False, philox_seed=0x5eed):
         if environment.num_envs != robot.num_envs:
             raise ValueError("environment and robot must hold the same envs")
         self.env, self.robot = environment, robot
@@ -72,12 +80,22 @@ class BatchedTrainer:
         self._z = torch.zeros((2, self.n), dtype=torch.float64, device=self.device)
         self._use_graph = bool(graph)
         self._graph = None
+        self._graph_k = None
+        self.fused = bool(fused)
+        if noise == "philox" and not self.fused:
+            raise ValueError('noise="philox" is generated inside the fused tick kernel: pass fused=True')
+        if noise not in ("mt19937", "randn", "philox"):
+            raise ValueError("unknown noise mode %r" % (noise,))
+        self.philox_seed = int(philox_seed)
+        self._tick_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def money_remaining(self, tick_charge=0.0):
         c = constants
         return (c.STARTING_MONEY - self.resets_bought * c.COST_PER_RESET - self.steps_bought * c.COST_PER_STEP - self.ticks * tick_charge)
 
     def _device_tick(self):
+        if self.fused:
+            return self._device_tick_fused()
         env, robot = self.env, self.robot
         types = robot.advance_action_types()                                  # int8 [N]
         z = None
@@ -93,6 +111,75 @@ class BatchedTrainer:
         _lib.check(_lib.lib().rtd3_trainer_tally(_lib.ptr(types), _lib.ptr(self.steps_bought), _lib.ptr(self.resets_bought), self.n,
                                                  _lib.stream_ptr(self.device)), "trainer_tally")
         return types
+
+    def _tick_state(self):
+        """`rtd3_tick_state` over this trainer's arrays (device pointers; rebuilt per call because the demonstration set and
+        the actor input may have been replaced since the last one)."""
+        from . import _lib
+        env, robot, rb = self.env, self.robot, self.robot.memory
+        p = lambda t: None if t is None else t.data_ptr()
+        t = _lib.TickStateStruct()
+        t.n = self.n
+        t.x, t.y, t.goal, t.region, t.state64 = p(env._state[0]), p(env._state[1]), p(robot._goal), p(env._region), p(env._state64)
+        t.env_bank = env._bank._struct
+        for k in ("num_episodes", "demo_flag", "plan_index", "path_length", "goal_reached", "stuck_flag", "noise_scale", "hist", "hist_count",
+                  "hist_head", "type", "update", "any_update", "base", "reward", "reward64", "done"):
+            setattr(t, k, p(getattr(robot, "_" + k)))
+        t.ax, t.ay = p(robot._action[0]), p(robot._action[1])
+        t.prev_x, t.prev_y = p(self._prev[0]), p(self._prev[1])
+        t.demo, t.demo_cell_start = p(robot._demo_dev), p(robot._demo_cells)
+        t.num_demo = 0 if robot._demo_dev is None else robot._demo_dev.shape[0]
+        t.rp_s, t.rp_a, t.rp_r, t.rp_s2, t.rp_notdone = p(rb.s), p(rb.a), p(rb.r), p(rb.s2), p(rb.notdone)
+        t.capacity, t.rp_total = rb.capacity, p(rb._total_dev)
+        t.steps_bought, t.resets_bought = p(self.steps_bought), p(self.resets_bought)
+        t.philox_seed, t.tick_counter = self.philox_seed, p(self._tick_counter)
+        return t
+
+    def _device_tick_fused(self):
+        from . import _lib
+        from .learner import NET_ACTOR
+        env, robot = self.env, self.robot
+        if self.n > robot.memory.capacity:
+            raise ValueError("more envs than replay rows: raise buffer_size")
+        L, sp = _lib.lib(), _lib.stream_ptr(self.device)
+        t = self._tick_state()
+        _lib.check(L.rtd3_tick_pre(_lib.ctypes.byref(t), sp), "tick_pre")
+        z, mode = None, _lib.TICK_NOISE_PHILOX
+        if self.noise == "mt19937":
+            z, mode = robot.generate_noise(), _lib.TICK_NOISE_GIVEN
+        elif self.noise == "randn":
+            z, mode = self._z.normal_(), _lib.TICK_NOISE_GIVEN
+        residual = robot.td3_agent.forward(NET_ACTOR, robot._base)            # residual_action, robot.py:598-624
+        _lib.check(L.rtd3_tick_post(env._handle, _lib.ctypes.byref(t), _lib.ptr(residual), _lib.ptr(z), mode, sp), "tick_post")
+        robot.memory._mark_device_advanced()
+        return robot._type
+
+    def run(self, ticks):
+        """`ticks` ticks.  With `graph=True, fused=True` they are replayed `check_interval` at a time from ONE captured graph (the
+        finished-episode counter is read, and a due `td3_update` runs, between the replays exactly where `tick()` would do it)."""
+        K = self.check_interval
+        done = 0
+        while done < ticks:
+            if self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
+                if self._graph_k is None:
+                    self.robot.td3_agent.sync_transposed(force=False)
+                    self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
+                    g = torch.cuda.CUDAGraph()
+                    before = _launches()
+                    with _capture(g):
+                        for _ in range(K):
+                            self._types = self._device_tick()
+                    self._graph_k, self._graph_k_launches = g, _launches() - before
+                    _add_launches(-self._graph_k_launches)
+                self._graph_k.replay()
+                _add_launches(self._graph_k_launches)
+                self.robot.memory._mark_device_advanced()
+                self.ticks += K
+                done += K
+                self.robot.maybe_update()
+            else:
+                self.tick()
+                done += 1
 
     def tick(self):
         if self._use_graph:

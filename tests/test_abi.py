@@ -62,3 +62,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_tick_state_struct_layout_matches_the_header(pkg, tmp_path):
+    """`_lib.TickStateStruct` (ctypes) against `rtd3_tick_state` as gcc lays it out from include/rtd3.h: every field offset."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    T = pkg._lib.TickStateStruct
+    names = [f[0] for f in T._fields_]
+    src = tmp_path / "off.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rtd3.h"\nint main(void){\n'
+                   + "".join('printf("%%zu\\n", offsetof(rtd3_tick_state, %s));\n' % k for k in names)
+                   + 'printf("%zu\\n", sizeof(rtd3_tick_state));\nreturn 0;}\n')
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [getattr(T, k).offset for k in names] + [ctypes.sizeof(T)]
