@@ -31,8 +31,8 @@ extern "C" {
 #define RTD3_WORLD_SIZE 100          /* constants.py:6  */
 #define RTD3_MAP_CELLS 10000         /* 100 x 100 cells, indexed [x][y] (environment.py:105-111) */
 #define RTD3_MT_N 624                /* MT19937 state words */
-#define RTD3_DEMO_GRID 32            /* demonstration-state grid of rtd3_robot_transition: 32 x 32 cells ... */
-#define RTD3_DEMO_CELL 4.0           /* ... of side 4 (covers [0,128)^2; points outside sit in the nearest border cell) */
+#define RTD3_DEMO_GRID 100           /* candidate lists of the nearest-demonstration search (rtd3_demo_lists): 100 x 100 cells ... */
+#define RTD3_DEMO_CELL 1.0           /* ... of side 1, the world's own cells; queries outside [0,100)^2 sweep the whole set */
 
 #define RTD3_ERR_ARG (-1)
 #define RTD3_ERR_STATE (-2)
@@ -225,21 +225,30 @@ int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* 
  * float64 shared by all envs, applied where demo_flag is set), check_if_stuck on the pre-step state
  * (robot.py:509-538, -50 penalty), done = plan_index == path_length - 1, and the replay push of the n rows at
  * (position + i) % capacity (rp_s == NULL skips the push).  reward float32 [n] (reward64 nullable float64).
- * demo_cell_start (nullable int32 [RTD3_DEMO_GRID^2 + 1]): when given, `demo` is sorted by grid cell
- * (cell = clamp(floor(x / RTD3_DEMO_CELL)) * RTD3_DEMO_GRID + clamp(floor(y / RTD3_DEMO_CELL)), cell c owning points
- * [demo_cell_start[c], demo_cell_start[c+1])) and the nearest demonstration state is found by an exact ring search on
- * that grid instead of the full sweep - same float64 operations per candidate, bit-identical result.
+ * demo_list_start (nullable int32 [RTD3_DEMO_GRID^2 + 1]) / demo_list (float64 [total][2]): the candidate lists built by
+ * rtd3_demo_lists.  When given, a query in cell c = floor(x) * RTD3_DEMO_GRID + floor(y) evaluates only the states
+ * demo_list[demo_list_start[c] .. demo_list_start[c+1]) - same float64 operations per candidate as the full sweep and the
+ * true nearest state is among them, so the result is bit-identical; `demo` must still hold the whole set (queries outside
+ * the grid sweep it).
  * type (nullable int8 [n]): only envs of type 0 ('step') are processed; their rows are then compacted behind the
  * ring's device row counter rp_total (uint64 [1], rows ever pushed; required with type, optional otherwise -
  * when given it is advanced by n). */
 int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index,
                               const int32_t* path_length, const float* sx, const float* sy, const float* ax, const float* ay,
-                              const float* nx, const float* ny, const double* demo, const int32_t* demo_cell_start,
-                              int64_t num_demo, float* reward,
+                              const float* nx, const float* ny, const double* demo, const int32_t* demo_list_start,
+                              const double* demo_list, int64_t num_demo, float* reward,
                               double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2,
                               float* rp_notdone, int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type,
                               int64_t n, void* stream);
+
+/* Candidate lists for the nearest-demonstration term of compute_reward (robot.py:753: cdist(...).min() over ALL demonstration
+ * states).  For every 1 x 1 cell of the world: the states that can be the nearest one for some point of the cell - a state is
+ * dropped when another state is closer at all four corners of the cell (then it is closer everywhere in it); tested against the
+ * states nearest to the corners and the centre.  Two passes over demo [num_demo][2] float64, one CTA per cell:
+ *   list == NULL: counts int32 [RTD3_DEMO_GRID^2] receives the list sizes (the caller turns them into start offsets);
+ *   list != NULL: start int32 [RTD3_DEMO_GRID^2 + 1] given, the lists are written to list [start[cells]][2] float64. */
+int32_t rtd3_demo_lists(const double* demo, int64_t num_demo, int32_t* counts, const int32_t* start, double* list, void* stream);
 
 /* Robot.get_next_action_type + Robot.reset (robot.py:443-506) for n envs.  type_out int8 [n]: 0 'step',
  * 1 'demo', 2 'reset'; update_out uint8 [n] marks envs whose episode ended (where the reference calls
@@ -290,7 +299,8 @@ typedef struct rtd3_tick_state {
   uint8_t* done;                /* [n] */
   /* demonstration states shared by all envs (as rtd3_robot_transition) */
   const double* demo;
-  const int32_t* demo_cell_start;
+  const int32_t* demo_list_start;
+  const double* demo_list;
   int64_t num_demo;
   /* replay ring (masked push through the device row counter) */
   float* rp_s;

@@ -28,7 +28,7 @@ class TickStateStruct(Structure):
                 + [(k, c_void_p) for k in ("num_episodes", "demo_flag", "plan_index", "path_length", "goal_reached", "stuck_flag", "noise_scale",
                                            "hist", "hist_count", "hist_head", "type", "update", "any_update",
                                            "base", "ax", "ay", "prev_x", "prev_y", "reward", "reward64", "done",
-                                           "demo", "demo_cell_start")]
+                                           "demo", "demo_list_start", "demo_list")]
                 + [("num_demo", c_int64)]
                 + [(k, c_void_p) for k in ("rp_s", "rp_a", "rp_r", "rp_s2", "rp_notdone")]
                 + [("capacity", c_int64), ("rp_total", c_void_p), ("steps_bought", c_void_p), ("resets_bought", c_void_p),
@@ -83,7 +83,8 @@ _SIGNATURES = {
     "rtd3_tick_post": (c_int32, [_P, POINTER(TickStateStruct), _P, _P, c_int32, _P]),
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
-    "rtd3_robot_transition": (c_int32, [_P] * 17 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
+    "rtd3_demo_lists": (c_int32, [_P, c_int64, _P, _P, _P, _P]),
+    "rtd3_robot_transition": (c_int32, [_P] * 18 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
     "rtd3_robot_next_action_type": (c_int32, [_P] * 10 + [c_int64, _P]),
 }
 

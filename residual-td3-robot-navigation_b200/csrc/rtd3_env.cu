@@ -641,7 +641,6 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<true, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
   RTD3_CUDA(cudaFuncSetAttribute(env_rollout_tma_kernel<false, kShallow>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll));
-  if (int32_t e = tick_set_attributes()) return e;
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;

@@ -13,8 +13,6 @@ struct rtd3_env {
 
 namespace rtd3 {
 
-int32_t tick_set_attributes();   // rtd3_tick.cu
-
 // One env-step, the rotation form of environment.py:100-117 (no atan2):
 //   s' = clip(s + speed*(ax*cos(rot) - ay*sin(rot), ax*sin(rot) + ay*cos(rot)), 0, 98.9999)
 // split into the part that does not depend on the state (StepIn, off the dependent chain of a rollout) and the

@@ -40,20 +40,97 @@ __global__ void robot_compose_kernel(const float* __restrict__ x, const float* _
   if (action64) { action64[i] = cx; action64[n + i] = cy; }
 }
 
-// process_transition for n envs; demo points ([m][2] float64, shared by all envs) are swept from shared memory.
-template <bool kStagePts>
-__global__ void __launch_bounds__(512)
+// process_transition for n envs; demo points ([m][2] float64, shared by all envs): candidate lists or a sweep from shared memory.
+__global__ void __launch_bounds__(256)
 robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ ax,
                         const float* __restrict__ ay, const float* __restrict__ nx, const float* __restrict__ ny,
-                        const double* __restrict__ demo, const int32_t* __restrict__ cell_start /*nullable*/, int64_t m,
-                        float* __restrict__ reward_out, double* __restrict__ reward64,
+                        const double* __restrict__ demo, const int32_t* __restrict__ list_start /*nullable*/,
+                        const double* __restrict__ list_pts, int64_t m, float* __restrict__ reward_out, double* __restrict__ reward64,
                         uint8_t* __restrict__ done_out, ReplayRing ring, const int8_t* __restrict__ type /*nullable: only type 0 steps*/,
                         int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n && (!type || type[i] == 0);
   const int64_t ii = live ? i : 0;
-  transition_env<kStagePts>(st, sx[ii], sy[ii], ax[ii], ay[ii], nx[ii], ny[ii], live, i, n, demo, cell_start, m, reward_out, reward64, done_out,
-                            ring, type != nullptr);
+  transition_env(st, sx[ii], sy[ii], ax[ii], ay[ii], nx[ii], ny[ii], live, i, n, demo, list_start, list_pts, m, reward_out, reward64, done_out,
+                 ring, type != nullptr);
+}
+
+// Candidate lists of the nearest-demonstration search (see nearest_demo_sq, rtd3_robot.cuh): one CTA per 1 x 1 cell.
+//   phase A: the states nearest to the cell's four corners and to its centre (p*_0..4);
+//   phase B: state p is kept iff, for EVERY p*_a, p is at least as close as p*_a at SOME corner (1e-9 relative slack).
+// kFill = false counts the survivors per cell, kFill = true writes them to out[start[cell] ...] (any order: the query takes a min).
+template <bool kFill>
+__global__ void __launch_bounds__(256) demo_lists_kernel(const double2* __restrict__ pts, int m, int32_t* __restrict__ counts,
+                                                         const int32_t* __restrict__ start, double2* __restrict__ out) {
+  __shared__ double s_bd[8][5];
+  __shared__ int s_bi[8][5];
+  __shared__ double s_thr[5][4];
+  __shared__ int s_count;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double x0 = (double)(c / kDemoGrid) * kDemoCell, y0 = (double)(c % kDemoGrid) * kDemoCell;
+  const double ax[5] = {x0, x0, x0 + kDemoCell, x0 + kDemoCell, x0 + 0.5 * kDemoCell};
+  const double ay[5] = {y0, y0 + kDemoCell, y0, y0 + kDemoCell, y0 + 0.5 * kDemoCell};
+  auto dist2 = [](double qx, double qy, double2 p) { const double dx = qx - p.x, dy = qy - p.y; return fma(dy, dy, dx * dx); };
+  double bd[5];
+  int bi[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) { bd[a] = INFINITY; bi[a] = 0; }
+  for (int k = tid; k < m; k += 256) {
+    const double2 p = __ldg(pts + k);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const double d = dist2(ax[a], ay[a], p);
+      if (d < bd[a]) { bd[a] = d; bi[a] = k; }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd[a], o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi[a], o);
+      if (od < bd[a]) { bd[a] = od; bi[a] = oi; }
+    }
+    if (lane == 0) { s_bd[warp][a] = bd[a]; s_bi[warp][a] = bi[a]; }
+  }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  if (tid < 20) {                                                    // thread (a, corner): |corner - p*_a|^2 with the slack
+    const int a = tid >> 2, j = tid & 3;
+    double d = s_bd[0][a];
+    int k = s_bi[0][a];
+    for (int w = 1; w < 8; ++w)
+      if (s_bd[w][a] < d) { d = s_bd[w][a]; k = s_bi[w][a]; }
+    s_thr[a][j] = dist2(ax[j], ay[j], __ldg(pts + k)) * kDemoKeep;
+  }
+  __syncthreads();
+  int mine = 0;
+  for (int base = 0; base < m; base += 256) {
+    const int k = base + tid;
+    bool keep = false;
+    double2 p = make_double2(0.0, 0.0);
+    if (k < m) {
+      p = __ldg(pts + k);
+      const double d0 = dist2(ax[0], ay[0], p), d1 = dist2(ax[1], ay[1], p), d2 = dist2(ax[2], ay[2], p), d3 = dist2(ax[3], ay[3], p);
+      keep = true;
+#pragma unroll
+      for (int a = 0; a < 5; ++a) keep = keep && (d0 <= s_thr[a][0] || d1 <= s_thr[a][1] || d2 <= s_thr[a][2] || d3 <= s_thr[a][3]);
+    }
+    const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+    if (kFill) {
+      int wbase = 0;
+      if (lane == 0 && kept) wbase = atomicAdd(&s_count, __popc(kept));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (keep) out[(int64_t)start[c] + wbase + __popc(kept & ((1u << lane) - 1u))] = p;
+    } else if (lane == 0) {
+      mine += __popc(kept);
+    }
+  }
+  if (!kFill) {
+    if (lane == 0 && mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (tid == 0) counts[c] = s_count;
+  }
 }
 
 // get_next_action_type + reset  (robot.py:443-506).  type: 0 'step', 1 'demo', 2 'reset'; update[i] = 1 where the
@@ -113,16 +190,26 @@ int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* 
   return 0;
 }
 
+int32_t rtd3_demo_lists(const double* demo, int64_t num_demo, int32_t* counts, const int32_t* start, double* list, void* stream) {
+  RTD3_CHECK_ARG(demo && num_demo >= 1 && num_demo < (1ll << 31), "bad demonstration set");
+  RTD3_CHECK_ARG((list == nullptr) ? (counts != nullptr) : (start != nullptr), "count pass needs counts, fill pass needs start and list");
+  if (!list) demo_lists_kernel<false><<<kDemoCells, 256, 0, (cudaStream_t)stream>>>((const double2*)demo, (int)num_demo, counts, nullptr, nullptr);
+  else demo_lists_kernel<true><<<kDemoCells, 256, 0, (cudaStream_t)stream>>>((const double2*)demo, (int)num_demo, nullptr, start, (double2*)list);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
 int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index, const int32_t* path_length,
                               const float* sx, const float* sy, const float* ax, const float* ay, const float* nx, const float* ny,
-                              const double* demo, const int32_t* demo_cell_start, int64_t num_demo, float* reward, double* reward64,
-                              uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2, float* rp_notdone, int64_t capacity,
-                              int64_t position, uint64_t* rp_total, const int8_t* type, int64_t n, void* stream) {
+                              const double* demo, const int32_t* demo_list_start, const double* demo_list, int64_t num_demo, float* reward,
+                              double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2, float* rp_notdone,
+                              int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type, int64_t n, void* stream) {
   RTD3_CHECK_ARG(goal && hist && hist_count && hist_head && goal_reached && stuck_flag && demo_flag && plan_index && path_length,
                  "null robot state");
   RTD3_CHECK_ARG(sx && sy && ax && ay && nx && ny && reward && done, "null transition array");
   RTD3_CHECK_ARG(num_demo == 0 || demo, "demo set missing");
+  RTD3_CHECK_ARG((demo_list_start == nullptr) == (demo_list == nullptr), "demo_list_start and demo_list go together");
   RTD3_CHECK_ARG(n >= 0, "negative n");
   RTD3_CHECK_ARG(!rp_s || (rp_a && rp_r && rp_s2 && rp_notdone && capacity > 0 && position >= 0 && position < capacity && n <= capacity),
                  "bad replay ring");
@@ -130,19 +217,9 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
   RobotState st{goal, hist, hist_count, hist_head, goal_reached, stuck_flag, demo_flag, plan_index, path_length};
   RTD3_CHECK_ARG(!(type && rp_s) || rp_total, "a masked push needs the ring's device row counter");
   ReplayRing ring{(float2*)rp_s, (float2*)rp_a, rp_r, (float2*)rp_s2, rp_notdone, capacity, position, (unsigned long long*)rp_total};
-  if (demo_cell_start && num_demo > 0 && num_demo <= kDemoStageMax) {
-    const size_t dyn = (size_t)num_demo * sizeof(double2);
-    static size_t attr = 0;
-    if (dyn > attr) {
-      RTD3_CUDA(cudaFuncSetAttribute(robot_transition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDemoStageMax * sizeof(double2))));
-      attr = kDemoStageMax * sizeof(double2);
-    }
-    robot_transition_kernel<true><<<(int)ceil_div(n, 512), 512, dyn, (cudaStream_t)stream>>>(st, sx, sy, ax, ay, nx, ny, demo, demo_cell_start, num_demo,
-                                                                                             reward, reward64, done, ring, type, n);
-  } else {
-    robot_transition_kernel<false><<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(st, sx, sy, ax, ay, nx, ny, demo, demo_cell_start, num_demo,
-                                                                                             reward, reward64, done, ring, type, n);
-  }
+  const int block = n <= 148 * 256 ? 128 : 256;      // a small batch spread over more SMs
+  robot_transition_kernel<<<(int)ceil_div(n, block), block, 0, (cudaStream_t)stream>>>(st, sx, sy, ax, ay, nx, ny, demo, demo_list_start, demo_list,
+                                                                                      num_demo, reward, reward64, done, ring, type, n);
   RTD3_LAUNCHED();
   return 0;
 }

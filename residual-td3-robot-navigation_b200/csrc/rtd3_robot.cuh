@@ -31,10 +31,10 @@ struct ReplayRing {
   unsigned long long* total;   // device counter of rows ever pushed (nullable); authoritative for masked pushes
 };
 
-constexpr int kDemoGrid = RTD3_DEMO_GRID;             // cells per side of the demonstration-state grid
-constexpr double kDemoCell = RTD3_DEMO_CELL;           // cell side (a power of two: cell edges are exact in float64)
+constexpr int kDemoGrid = RTD3_DEMO_GRID;             // cells per side of the candidate-list grid (the world's own 100 x 100 cells)
+constexpr double kDemoCell = RTD3_DEMO_CELL;           // cell side 1: cell edges are exact in float64
 constexpr int kDemoCells = kDemoGrid * kDemoGrid;
-constexpr int64_t kDemoStageMax = 13000;               // points that fit the shared-memory copy (208 KB) next to the static arrays
+constexpr double kDemoKeep = 1.0 + 1e-9;               // slack of the candidate test, far above the rounding of a squared distance
 
 // baseline_action = state - goal (robot.py:556 / 586), cast to float32 as torch.FloatTensor does (robot.py:612)
 __device__ __forceinline__ float2 baseline_env(float x, float y, double gx, double gy) {
@@ -83,122 +83,74 @@ __device__ __forceinline__ int action_type_env(int32_t* __restrict__ num_episode
   return type;
 }
 
-// All threads of the CTA must call this (block-wide barriers for the demo staging, warp ballots for the compacted push).
+// Nearest demonstration state (squared distance, float64) for a query inside the world.
+// Candidate lists (built by demo_lists_kernel, rtd3_robot.cu): for every 1 x 1 cell of the world the
+// demonstration states that can be the nearest one for SOME point of the cell.  A state p cannot be nearest anywhere in the
+// cell if another state p* is closer at all four corners: |q-p|^2 - |q-p*|^2 is linear in q, so if it is positive at the corners
+// it is positive on the whole (convex) cell.  The lists keep what survives that test against five p* (the states nearest to the
+// four corners and to the centre); for the reference's 11 355 states after three demonstrations the mean list holds 5 states
+// (median 1, maximum 79).  The query evaluates every candidate with the same three float64 operations as the full sweep, and the
+// minimum over any subset that contains the true nearest state is the same number: bit-identical to robot.py:753's cdist min.
+__device__ __forceinline__ double nearest_demo_sq(const double px, const double py, const double* __restrict__ demo, const int64_t m,
+                                                  const int32_t* __restrict__ list_start, const double* __restrict__ list_pts) {
+  double best = INFINITY;
+  const double2* pts = reinterpret_cast<const double2*>(demo);
+  int64_t k0 = 0, k1 = m;
+  if (list_start && px >= 0.0 && px < (double)kDemoGrid * kDemoCell && py >= 0.0 && py < (double)kDemoGrid * kDemoCell) {
+    const int c = (int)(px / kDemoCell) * kDemoGrid + (int)(py / kDemoCell);
+    k0 = list_start[c];
+    k1 = list_start[c + 1];
+    pts = reinterpret_cast<const double2*>(list_pts);
+  }                                                                  // a query outside the grid sweeps the whole set
+  for (int64_t k = k0; k < k1; ++k) {
+    const double2 t = __ldg(pts + k);
+    const double dx = px - t.x, dy = py - t.y;
+    best = fmin(best, fma(dy, dy, dx * dx));
+  }
+  return best;
+}
+
+// All threads of the CTA must call this (block-wide barriers for the demo sweep, warp ballots for the compacted push).
 // `live`: this thread holds an env that steps in this tick; (sx,sy) pre-step state, (ax,ay) action, (nx,ny) next state.
-// Demo points ([m][2] float64, shared by all envs) are swept from shared memory.
-template <bool kStagePts>
+// Demo points ([m][2] float64, shared by all envs): candidate lists when `list_start` is given, else swept from shared memory.
 __device__ __forceinline__ void transition_env(const RobotState& st, const float sxi, const float syi, const float axi, const float ayi,
                                                const float nxi, const float nyi, const bool live, const int64_t i, const int64_t n,
-                                               const double* __restrict__ demo, const int32_t* __restrict__ cell_start /*nullable*/, const int64_t m,
+                                               const double* __restrict__ demo, const int32_t* __restrict__ list_start /*nullable*/,
+                                               const double* __restrict__ list_pts, const int64_t m,
                                                float* __restrict__ reward_out, double* __restrict__ reward64, uint8_t* __restrict__ done_out,
                                                const ReplayRing& ring, const bool masked_push) {
   __shared__ double2 tile[512];
-  __shared__ int32_t s_cell[kDemoCells + 1];
   const int64_t ii = live ? i : 0;
   const double px = (double)nxi, py = (double)nyi;
   // compute_reward([next_state])  robot.py:741-762
   const double gd = norm2_np(__dsub_rn(px, st.goal[ii]), __dsub_rn(py, st.goal[n + ii]));
   const bool reached = (-gd >= -kGoalRadius);
-  // nearest demonstration state (only needed when the goal was not reached and there are demos): min over m points
+  // nearest demonstration state (only needed when the goal was not reached, the demo phase is over and there are demos)
   double best = INFINITY;
-  if (m > 0 && cell_start) {
-    // Exact search on a two-level uniform grid, warp-cooperative.  The points are sorted by fine cell
-    // (kDemoGrid x kDemoGrid cells of side kDemoCell; points outside the grid sit in the nearest border cell, whose box is
-    // therefore open on its outer sides).  A warp serves the queries of its 32 envs one after the other, all lanes on the
-    // same query (a per-thread traversal diverges into 32 serial walks: measured 2x SLOWER than the full sweep for queries
-    // far from the demonstrations): a strided subsample of the points gives an upper bound; the 64 blocks of 4 x 4 cells are
-    // tested two per lane, the 16 cells of a surviving block one per lane, and the points of a surviving cell are evaluated
-    // 32 at a time (coalesced 16 B loads).  A box is skipped when the distance from the query to it already exceeds the best
-    // distance found (1e-9 relative margin, far above the rounding of the three operations).  Every evaluated candidate goes
-    // through the same three float64 operations as the full sweep, and the minimum over any subset that contains the true
-    // nearest point is the same number, so the result is bit-identical to the sweep.
-    // With kStagePts the sorted points (16 B each, up to kDemoStageMax of them) are first copied to shared memory: the
-    // walk is a chain of short dependent loads, and from L2 their latency (not the arithmetic) was the whole cost - 230 us
-    // for 65 536 queries against 11 355 points, the same as the per-thread walk.
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    double2* s_pts = reinterpret_cast<double2*>(s_dyn);
-    for (int k = threadIdx.x; k <= kDemoCells; k += blockDim.x) s_cell[k] = cell_start[k];
-    if (kStagePts)
-      for (int64_t k = threadIdx.x; k < m; k += blockDim.x) s_pts[k] = __ldg(reinterpret_cast<const double2*>(demo) + k);
-    __syncthreads();
-    {
-      const double2* gpts = reinterpret_cast<const double2*>(demo);
-      const int lane = threadIdx.x & 31;
-      constexpr double kKeep = 1.0 - 1e-9;
-      constexpr int kB = kDemoGrid / 4;                              // blocks per side
-      auto gap = [](double p, int c, int cells) {                    // distance from p to the slab of cells [c, c + cells), open at the grid border
-        const double lo = c == 0 ? -INFINITY : (double)c * kDemoCell;
-        const double hi = c + cells >= kDemoGrid ? INFINITY : (double)(c + cells) * kDemoCell;
-        return fmax(fmax(lo - p, p - hi), 0.0);
-      };
-      auto warp_min = [](double v) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-        return v;
-      };
-      uint32_t todo = __ballot_sync(0xffffffffu, live && !reached);
-      const int64_t stride = max((int64_t)1, m / 128);
-      while (todo) {
-        const int q = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const double qx = __shfl_sync(0xffffffffu, px, q), qy = __shfl_sync(0xffffffffu, py, q);
-        double pm = INFINITY;                                        // this lane's partial minimum for query q
-        auto eval = [&](int64_t k) {
-          const double2 t = kStagePts ? s_pts[k] : __ldg(gpts + k);
-          const double dx = qx - t.x, dy = qy - t.y;
-          pm = fmin(pm, fma(dy, dy, dx * dx));
-        };
-        for (int64_t k = (int64_t)lane * stride; k < m; k += 32 * stride) eval(k);
-        double wb = warp_min(pm);                                    // upper bound, uniform over the warp
-        // block level: lane tests blocks `lane` and `lane + 32`
-        uint32_t bmask[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int b = lane + 32 * h, X = (b / kB) * 4, Y = (b % kB) * 4;
-          bool any = false;
-#pragma unroll
-          for (int gx = 0; gx < 4; ++gx) any |= s_cell[(X + gx) * kDemoGrid + Y + 4] != s_cell[(X + gx) * kDemoGrid + Y];
-          const double bx = gap(qx, X, 4), by = gap(qy, Y, 4);
-          bmask[h] = __ballot_sync(0xffffffffu, any && (bx * bx + by * by) * kKeep <= wb);
-        }
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t bm = bmask[h];
-          while (bm) {
-            const int b = __ffs(bm) - 1 + 32 * h;
-            bm &= bm - 1;
-            const int X = (b / kB) * 4, Y = (b % kB) * 4;
-            const double bx = gap(qx, X, 4), by = gap(qy, Y, 4);
-            if ((bx * bx + by * by) * kKeep > wb) continue;          // the bound has tightened since the block test (uniform)
-            // cell level: lanes 0-15 own the 16 cells of the block
-            const int gx = X + ((lane & 15) >> 2), gy = Y + (lane & 3);
-            const int k0 = s_cell[gx * kDemoGrid + gy], k1 = s_cell[gx * kDemoGrid + gy + 1];
-            const double fx = gap(qx, gx, 1), fy = gap(qy, gy, 1);
-            uint32_t cm = __ballot_sync(0xffffffffu, lane < 16 && k1 > k0 && (fx * fx + fy * fy) * kKeep <= wb);
-            while (cm) {
-              const int c = __ffs(cm) - 1;
-              cm &= cm - 1;
-              const int c0 = __shfl_sync(0xffffffffu, k0, c), c1 = __shfl_sync(0xffffffffu, k1, c);
-              for (int k = c0 + lane; k < c1; k += 32) eval(k);
-            }
-            wb = warp_min(pm);
-          }
-        }
-        if (lane == q) best = wb;
-      }
-    }
+  if (m > 0 && list_start) {
+    if (live && !reached && st.demo_flag[ii]) best = nearest_demo_sq(px, py, demo, m, list_start, list_pts);
   } else if (m > 0) {
+    double b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;      // four independent minimum chains
     for (int64_t base = 0; base < m; base += 512) {
       const int cnt = (int)min((int64_t)512, m - base);
       __syncthreads();
       for (int k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = reinterpret_cast<const double2*>(demo)[base + k];
       __syncthreads();
-#pragma unroll 4
-      for (int k = 0; k < cnt; ++k) {
+      int k = 0;
+      for (; k + 4 <= cnt; k += 4) {
+        const double dx0 = px - tile[k].x, dy0 = py - tile[k].y, dx1 = px - tile[k + 1].x, dy1 = py - tile[k + 1].y;
+        const double dx2 = px - tile[k + 2].x, dy2 = py - tile[k + 2].y, dx3 = px - tile[k + 3].x, dy3 = py - tile[k + 3].y;
+        b0 = fmin(b0, fma(dy0, dy0, dx0 * dx0));     // squared distance; sqrt once at the end (monotone)
+        b1 = fmin(b1, fma(dy1, dy1, dx1 * dx1));
+        b2 = fmin(b2, fma(dy2, dy2, dx2 * dx2));
+        b3 = fmin(b3, fma(dy3, dy3, dx3 * dx3));
+      }
+      for (; k < cnt; ++k) {
         const double dx = px - tile[k].x, dy = py - tile[k].y;
-        best = fmin(best, fma(dy, dy, dx * dx));     // squared distance; sqrt once at the end (monotone)
+        b0 = fmin(b0, fma(dy, dy, dx * dx));
       }
     }
+    best = fmin(fmin(b0, b1), fmin(b2, b3));
   }
   double reward = 0.0;
   bool done = false;

@@ -45,8 +45,7 @@ __global__ void __launch_bounds__(256) tick_pre_kernel(rtd3_tick_state t) {
   if (i == 0 && t.tick_counter) t.tick_counter[0] += 1ull;
 }
 
-template <bool kStagePts>
-__global__ void __launch_bounds__(512) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,
+__global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,
                                                         const float* __restrict__ residual /*[n][2]*/,
                                                         const double* __restrict__ unit_noise /*[2][n], mode 1*/, int noise_mode) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,8 +74,8 @@ __global__ void __launch_bounds__(512) tick_post_kernel(rtd3_tick_state t, const
   const RobotState st{t.goal, t.hist, t.hist_count, t.hist_head, t.goal_reached, t.stuck_flag, t.demo_flag, t.plan_index, t.path_length};
   const ReplayRing ring{(float2*)t.rp_s, (float2*)t.rp_a, t.rp_r, (float2*)t.rp_s2, t.rp_notdone, t.capacity, 0,
                         (unsigned long long*)t.rp_total};
-  transition_env<kStagePts>(st, x, y, ax, ay, nx, ny, live, i, n, t.demo, t.demo_cell_start, t.num_demo, t.reward, t.reward64, t.done, ring,
-                            true);
+  transition_env(st, x, y, ax, ay, nx, ny, live, i, n, t.demo, t.demo_list_start, t.demo_list, t.num_demo, t.reward, t.reward64, t.done, ring,
+                 true);
   if (in) {
     t.ax[i] = ax;
     t.ay[i] = ay;
@@ -101,15 +100,10 @@ static int32_t check_state(const rtd3_tick_state* t) {
   RTD3_CHECK_ARG(t->base && t->ax && t->ay && t->reward && t->done, "null tick output");
   RTD3_CHECK_ARG((t->prev_x == nullptr) == (t->prev_y == nullptr), "prev_x / prev_y go together");
   RTD3_CHECK_ARG(t->num_demo >= 0 && (t->num_demo == 0 || t->demo), "demo set missing");
+  RTD3_CHECK_ARG((t->demo_list_start == nullptr) == (t->demo_list == nullptr), "demo_list_start and demo_list go together");
   RTD3_CHECK_ARG(t->rp_s && t->rp_a && t->rp_r && t->rp_s2 && t->rp_notdone && t->rp_total && t->capacity > 0 && t->n <= t->capacity,
                  "bad replay ring");
   RTD3_CHECK_ARG(t->steps_bought && t->resets_bought, "null money counters");
-  return 0;
-}
-
-// Called by rtd3_env_create (per device, outside any stream capture): the staged demo search needs opt-in shared memory.
-int32_t tick_set_attributes() {
-  RTD3_CUDA(cudaFuncSetAttribute(tick_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDemoStageMax * sizeof(double2))));
   return 0;
 }
 
@@ -137,14 +131,9 @@ int32_t rtd3_tick_post(rtd3_env* h, const rtd3_tick_state* t, const float* resid
   RTD3_CHECK_ARG(noise_mode != RTD3_TICK_NOISE_PHILOX || t->tick_counter, "noise mode 'philox' needs the tick counter");
   if (t->n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (t->demo_cell_start && t->num_demo > 0 && t->num_demo <= kDemoStageMax) {
-    const size_t dyn = (size_t)t->num_demo * sizeof(double2);
-    tick_post_kernel<true><<<(int)ceil_div(t->n, 512), 512, dyn, st>>>(*t, h->table, residual, unit_noise, noise_mode);
-  } else {
-    // elementwise + a sweep over a few hundred demo points: small CTAs spread a small batch over more SMs
-    const int block = t->n <= (int64_t)h->num_sms * 256 ? 128 : 256;
-    tick_post_kernel<false><<<(int)ceil_div(t->n, block), block, 0, st>>>(*t, h->table, residual, unit_noise, noise_mode);
-  }
+  // elementwise work plus a few candidate demo states per env: small CTAs spread a small batch over more SMs
+  const int block = t->n <= (int64_t)h->num_sms * 256 ? 128 : 256;
+  tick_post_kernel<<<(int)ceil_div(t->n, block), block, 0, st>>>(*t, h->table, residual, unit_noise, noise_mode);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -34,7 +34,7 @@ GOAL_REWARD = 50
 DEMO_PROXIMITY_FACTOR = 10
 
 ACTION_TYPES = ("step", "demo", "reset")
-DEMO_GRID, DEMO_CELL = 32, 4.0          # RTD3_DEMO_GRID / RTD3_DEMO_CELL of include/rtd3.h
+DEMO_GRID, DEMO_CELL = 100, 1.0         # RTD3_DEMO_GRID / RTD3_DEMO_CELL of include/rtd3.h
 
 
 class PathToDraw:
@@ -76,9 +76,10 @@ class Robot:
         self.paths_to_draw = []
         self.demonstration_states = []
         self.demonstration_actions = []
-        self._demo_dev = None                                   # [M,2] float64 on the device (sorted by grid cell when _demo_cells is set)
-        self._demo_cells = None                                 # int32 [DEMO_GRID^2 + 1] cell offsets into _demo_dev, or None: full sweep
-        self.demo_grid_min_points = 4096                        # smaller sets are swept in full (the grid walk has ~1.5 us of latency per query and warp)
+        self._demo_dev = None                                   # [M,2] float64 on the device, the reference's order
+        self._demo_cells = None                                 # int32 [DEMO_GRID^2 + 1] offsets into _demo_list, or None: full sweep
+        self._demo_list = None                                  # [total,2] float64: per-cell candidate lists (rtd3_demo_lists)
+        self.demo_grid_min_points = 64                          # smaller sets are swept in full
         # per-env episode state (robot.py:421-438)
         self._num_episodes = torch.zeros(n, dtype=torch.int32, device=dev)
         self._noise_scale = torch.full((n,), float(INITIAL_NOISE), dtype=torch.float64, device=dev)
@@ -224,7 +225,7 @@ class Robot:
             _lib.ptr(self._goal), _lib.ptr(self._hist), _lib.ptr(self._hist_count), _lib.ptr(self._hist_head), _lib.ptr(self._goal_reached),
             _lib.ptr(self._stuck_flag), _lib.ptr(self._demo_flag), _lib.ptr(self._plan_index), _lib.ptr(self._path_length),
             _lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(ap[0]), _lib.ptr(ap[1]), _lib.ptr(npl[0]), _lib.ptr(npl[1]),
-            _lib.ptr(self._demo_dev), _lib.ptr(self._demo_cells), m, _lib.ptr(self._reward), _lib.ptr(self._reward64), _lib.ptr(self._done),
+            _lib.ptr(self._demo_dev), _lib.ptr(self._demo_cells), _lib.ptr(self._demo_list), m, _lib.ptr(self._reward), _lib.ptr(self._reward64), _lib.ptr(self._done),
             _lib.ptr(rb.s if push else None), _lib.ptr(rb.a), _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), rb.capacity,
             0 if types is not None else rb.position, _lib.ptr(rb._total_dev), _lib.ptr(types), n, _lib.stream_ptr(self.device)),
             "robot_transition")
@@ -277,25 +278,26 @@ class Robot:
         self._upload_demos()
 
     def _upload_demos(self):
-        """Demonstration states -> device.  From `demo_grid_min_points` points on they are sorted into the uniform grid that
-        `rtd3_robot_transition` searches exactly (robot.py:753's min over ALL demo states, without touching all of them);
-        `demonstration_states` itself keeps the reference's order."""
-        self._demo_cells = None
-        if self.demonstration_states:
-            arr = np.asarray([np.asarray(s, dtype=np.float64) for s in self.demonstration_states], dtype=np.float64)
-            if arr.shape[0] >= self.demo_grid_min_points:
-                G, side = DEMO_GRID, DEMO_CELL
-                cx = np.clip(np.floor(arr[:, 0] / side), 0, G - 1).astype(np.int64)
-                cy = np.clip(np.floor(arr[:, 1] / side), 0, G - 1).astype(np.int64)
-                cell = cx * G + cy
-                order = np.argsort(cell, kind="stable")
-                arr = arr[order]
-                start = np.zeros(G * G + 1, dtype=np.int32)
-                np.cumsum(np.bincount(cell, minlength=G * G), out=start[1:])
-                self._demo_cells = torch.from_numpy(start).to(self.device)
-            self._demo_dev = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device).contiguous()
-        else:
+        """Demonstration states -> device.  From `demo_grid_min_points` states on, `rtd3_demo_lists` builds the per-cell candidate
+        lists that `rtd3_robot_transition` / `rtd3_tick_post` search (robot.py:753's min over ALL demo states, evaluated on the
+        handful that can be nearest inside the query's cell); `demonstration_states` itself keeps the reference's order."""
+        self._demo_cells = self._demo_list = None
+        if not self.demonstration_states:
             self._demo_dev = None
+            return
+        arr = np.asarray([np.asarray(s, dtype=np.float64) for s in self.demonstration_states], dtype=np.float64)
+        self._demo_dev = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device).contiguous()
+        m = arr.shape[0]
+        if m >= self.demo_grid_min_points:
+            L, sp = _lib.lib(), _lib.stream_ptr(self.device)
+            cells = DEMO_GRID * DEMO_GRID
+            start = torch.zeros(cells + 1, dtype=torch.int32, device=self.device)
+            _lib.check(L.rtd3_demo_lists(_lib.ptr(self._demo_dev), m, _lib.ptr(start[1:]), None, None, sp), "demo_lists (count)")
+            start[1:] = torch.cumsum(start[1:], 0, dtype=torch.int32)
+            total = int(start[-1].item())
+            lists = torch.empty((total, 2), dtype=torch.float64, device=self.device)
+            _lib.check(L.rtd3_demo_lists(_lib.ptr(self._demo_dev), m, None, _lib.ptr(start), _lib.ptr(lists), sp), "demo_lists (fill)")
+            self._demo_cells, self._demo_list = start, lists
 
     def augment_demonstration_data(self, demonstration_states, demonstration_actions, noise_level=AUG_NOISE,
                                    interpolation_steps=AUG_INTERPOLATION, num_augmentations=NUM_AUGMENTS):

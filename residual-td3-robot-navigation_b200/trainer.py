@@ -127,7 +127,7 @@ class BatchedTrainer:
             setattr(t, k, p(getattr(robot, "_" + k)))
         t.ax, t.ay = p(robot._action[0]), p(robot._action[1])
         t.prev_x, t.prev_y = p(self._prev[0]), p(self._prev[1])
-        t.demo, t.demo_cell_start = p(robot._demo_dev), p(robot._demo_cells)
+        t.demo, t.demo_list_start, t.demo_list = p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list)
         t.num_demo = 0 if robot._demo_dev is None else robot._demo_dev.shape[0]
         t.rp_s, t.rp_a, t.rp_r, t.rp_s2, t.rp_notdone = p(rb.s), p(rb.a), p(rb.r), p(rb.s2), p(rb.notdone)
         t.capacity, t.rp_total = rb.capacity, p(rb._total_dev)

@@ -88,7 +88,7 @@ def test_transition_batched_flags_bit_exact_vs_oracle(pkg):
     goals = rs.uniform(5, 95, (n, 2))
     demos = rs.uniform(0, 99, (700, 2))
     robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=20000)
-    robot.demo_grid_min_points = 1                          # exercise the exact grid search against the oracle's cdist-style min
+    robot.demo_grid_min_points = 1                          # exercise the candidate lists against the oracle's cdist-style min
     robot.set_demonstration_states(demos)
     assert robot._demo_cells is not None
     robot._demo_flag.fill_(1)
@@ -224,11 +224,11 @@ def test_graphed_trainer_matches_eager_trainer(pkg, env_golden):
 
 @pytest.mark.parametrize("m", [64, 700, 11355])
 def test_demo_grid_search_is_bit_identical_to_the_full_sweep(pkg, m):
-    """robot.py:753: the proximity term is the min over ALL demonstration states.  The exact ring search on the uniform grid
-     must return the very same float64 as the full sweep: clustered demo paths (the reference's 3 785 states
-    per demonstration), augmentation noise pushing points outside [0,100), queries on cell edges / world borders / far from
-    every demo."""
-    n = 4096
+    """robot.py:753: the proximity term is the min over ALL demonstration states.  The candidate lists (rtd3_demo_lists: per
+    1 x 1 cell the states that can be nearest somewhere in the cell) must give the very same float64 as the full
+    sweep: clustered demo paths (the reference's 3 785 states per demonstration), augmentation noise pushing points outside
+    [0,100), queries on cell corners / edges / world borders / far from every demo / outside the world (those sweep the set)."""
+    n = 32768
     rs = np.random.RandomState(m)
     t = np.linspace(0, 1, m // 3 + 1)[:, None]
     paths = [np.array([[5.0, 80.0]]) * (1 - t) + np.array([[90.0, 15.0]]) * t + rs.normal(0, s, (t.shape[0], 2)) for s in (0.5, 2.5, 6.0)]
@@ -240,11 +240,16 @@ def test_demo_grid_search_is_bit_identical_to_the_full_sweep(pkg, m):
     nxt[64:128, 1] = np.float32(98.9999)                                                          # world border
     nxt[128:192] = np.float32(0.0)
     nxt[192:256] = (demos[rs.randint(0, m, 64)]).clip(0, 98.9999).astype(np.float32)              # on top of demo states
+    gx, gy = np.meshgrid(np.arange(100, dtype=np.float32), np.arange(100, dtype=np.float32), indexing="ij")
+    nxt[256:10256] = np.stack([gx.ravel(), gy.ravel()], 1)                                        # every cell corner
+    nxt[10256:10320] = np.nextafter(np.float32(rs.randint(1, 100, (64, 2))), np.float32(0))       # just below a cell corner
+    nxt[10320:10336] = [[-0.5, 50.0], [100.0, 50.0], [50.0, -2.0], [50.0, 100.25]] * 4            # outside the grid: full sweep
+    nxt[10336:10400] = np.float32(99.99999)                                                       # the largest reset state
     cur = nxt.copy()
     act = np.zeros((n, 2), np.float32)
     out = []
     for min_points in (10 ** 9, 1):                       # full sweep, then the grid
-        robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=20000)
+        robot = pkg.Robot(torch.from_numpy(goals).cuda(), seed=5, buffer_size=40000)
         robot.demo_grid_min_points = min_points
         robot.set_demonstration_states(demos)
         assert (robot._demo_cells is None) == (min_points > m)
@@ -253,8 +258,34 @@ def test_demo_grid_search_is_bit_identical_to_the_full_sweep(pkg, m):
         out.append(robot._reward64.cpu().numpy().copy())
     assert np.array_equal(out[0], out[1])
     # and against cdist-style numpy on a few rows (the reference's own arithmetic, float64)
-    for i in (0, 70, 130, 200, 4095):
+    for i in (0, 70, 130, 200, 4095, 256, 5000, 10255, 10260, 10320, 10323, 10399):
         p = nxt[i].astype(np.float64)
         d = np.sqrt(((demos - p) ** 2).sum(axis=1)).min()
         ref = -np.linalg.norm(p - goals[i]) + 10 * (-d)
         np.testing.assert_allclose(out[1][i], ref, rtol=1e-13)
+
+
+def test_demo_candidate_lists_are_small_and_complete(pkg):
+    """Structure of rtd3_demo_lists' output for a reference-like set (3 demonstration paths + 3 augmentations each, 11 355 states):
+    every cell has at least one candidate, the lists are short (the point of the structure), and every list entry is one of the
+    demonstration states."""
+    rs = np.random.RandomState(0)
+    pts = []
+    for _ in range(3):
+        a, b = rs.uniform(5, 95, 2), rs.uniform(5, 95, 2)
+        t = np.linspace(0, 1, 200)[:, None]
+        path = a * (1 - t) + b * t + np.cumsum(rs.normal(0, 0.3, (200, 2)), axis=0)
+        pts.append(path)
+        for _ in range(3):
+            pts.append(np.repeat(path[:-1], 6, axis=0) + rs.normal(0, 2.5, (199 * 6, 2)))
+            pts.append(path[-1:] + rs.normal(0, 2.5, (1, 2)))
+    demos = np.concatenate(pts)
+    assert demos.shape == (11355, 2)
+    robot = pkg.Robot(torch.zeros((4, 2), dtype=torch.float64, device="cuda"), seed=5, buffer_size=100)
+    robot.set_demonstration_states(demos)
+    start = robot._demo_cells.cpu().numpy()
+    sizes = np.diff(start)
+    assert start[0] == 0 and start[-1] == robot._demo_list.shape[0] and sizes.min() >= 1
+    assert sizes.mean() < 20 and sizes.max() < 400
+    have = {tuple(r) for r in demos}
+    assert all(tuple(r) in have for r in robot._demo_list.cpu().numpy())

@@ -1,4 +1,4 @@
-"""process_transition with the reference's 11 355 demonstration states: full sweep vs exact grid search (development aid)."""
+"""process_transition with the reference's 11 355 demonstration states: full sweep vs the candidate lists of rtd3_demo_lists (development aid)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -17,6 +17,15 @@ def run(n, m, min_points, name, near=False):
     robot.demo_grid_min_points = min_points
     if m:
         robot.set_demonstration_states(demos)
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        robot.set_demonstration_states(demos)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        if robot._demo_cells is not None:
+            sz = (robot._demo_cells[1:] - robot._demo_cells[:-1]).float()
+            print("           lists: built in %.2f ms, %d entries, mean %.1f max %d per cell" % (build_ms, robot._demo_list.shape[0], sz.mean().item(), int(sz.max())))
     robot._demo_flag.fill_(1)
     for _ in range(3):
         robot.process_transition(nxt, act, nxt, None)
@@ -31,5 +40,5 @@ for n in (4096, 65536):
     run(n, 0, 1, "no demos")
     for m in (64, 1000, 11355):
         run(n, m, 10 ** 9, "full sweep")
-        run(n, m, 1, "grid")
-    run(n, 11355, 1, "grid", near=True)
+        run(n, m, 1, "lists")
+    run(n, 11355, 1, "lists", near=True)

@@ -11,7 +11,14 @@ def build(n, fused, noise, precision, updates=False):
     robot.memory.sampler = "philox"
     if not updates:
         robot.episodes_per_update = 10 ** 9
-    robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
+    m = int(os.environ.get("DEMOS", "512"))
+    if m == 512:
+        robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
+    else:                                                   # reference-like: three noisy paths across the world
+        rs = np.random.RandomState(0)
+        t = np.linspace(0, 1, m // 3 + 1)[:, None]
+        robot.set_demonstration_states(np.concatenate([rs.uniform(5, 95, (1, 2)) * (1 - t) + rs.uniform(5, 95, (1, 2)) * t + rs.normal(0, 2.5, (t.shape[0], 2))
+                                                       for _ in range(3)])[:m])
     return rt.BatchedTrainer(env, robot, noise=noise, graph=True, check_interval=8, fused=fused), robot
 
 def timed(fn, reps):
@@ -22,7 +29,7 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps * 1e3, t_issue / reps * 1e6
 
 for n in [int(a) for a in sys.argv[1:]] or [8192, 65536]:
-    for precision in ("tf32", "fp32"):
+    for precision in os.environ.get("PRECISIONS", "tf32,fp32").split(","):
         for label, fused, noise, multi in (("hook-by-hook, 1-tick graph", False, "randn", False), ("fused, 1-tick graph", True, "philox", False),
                                           ("fused, 8-tick graph", True, "philox", True)):
             for updates in (False, True):
