@@ -350,6 +350,18 @@ int32_t rtd3_tc_sync_weights(int32_t hidden, int32_t layers, const float* params
 int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, int64_t param_off, const float* params,
                               const float* params_u, const float* x, float* y, int64_t batch, void* stream);
 
+/* fp16 copies of the hidden-to-hidden weights for rtd3_mlp_forward_f16: params_h holds 6 * (layers-1) * hidden^2 halves,
+ * matrix l of network net at ((net*(layers-1) + l-1) * hidden^2), in UMMA operand order Wh[(k/8)*H + n][k%8] = half(W[n][k]). */
+int32_t rtd3_tc_sync_weights_f16(int32_t hidden, int32_t layers, const float* params, uint16_t* params_h, void* stream);
+
+/* Forward of network `net` (0..5, arena order) with fp16 operands - the same 11-bit significand as TF32 in half the bytes, so the
+ * hidden weight (128 KB at H = 256) stays RESIDENT in shared memory instead of being streamed from L2 per 128-row tile, the
+ * tcgen05.mma.kind::f16 products accumulate in fp32 in two TMEM buffers, and the epilogue (bias, ReLU, fused output layer) of
+ * one tile overlaps the products of the next.  layers == 2, hidden % 32 == 0, 64..256.  First / output layer in fp32.
+ * Agrees with rtd3_mlp_forward to fp16-operand round-off (~1e-3 relative); opt-in throughput mode, not the parity path. */
+int32_t rtd3_mlp_forward_f16(int32_t hidden, int32_t layers, int32_t net, const float* params, const uint16_t* params_h, const float* x,
+                             float* y, int64_t batch, void* stream);
+
 /* 1 if the tensor-core learner steps below support this handle's shape (layers == 2, hidden 128 or 256). */
 int32_t rtd3_td3_tf32_supported(const rtd3_td3* h);
 

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "rtd3_mlp_forward": (c_int32, [_P, c_int32, _P, _P, _P, _P, c_int64, _P]),
     "rtd3_tc_sync_weights": (c_int32, [c_int32, c_int32, _P, _P, _P]),
     "rtd3_mlp_forward_tf32": (c_int32, [c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P, c_int64, _P]),
+    "rtd3_tc_sync_weights_f16": (c_int32, [c_int32, c_int32, _P, _P, _P]),
+    "rtd3_mlp_forward_f16": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P]),
     "rtd3_td3_tf32_supported": (c_int32, [_P]),
     "rtd3_td3_critic_step_tf32": (c_int32, [_P] * 11 + [c_int32, c_float, c_float, c_float, c_float] + [_P] * 6),
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),

@@ -14,6 +14,7 @@
 //   epilogue: the row threads read their TMEM lane with tcgen05.ld (32 columns at a time), add bias, ReLU, and write the
 //   next layer's X straight back in the chunk layout (16 B per 4 columns, consecutive rows -> conflict-free).
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
@@ -203,6 +204,200 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
 }
 
+// ---- f16 forward with the hidden weights RESIDENT in shared memory (layers == 2) ---------------------------------------------
+// The TF32 kernel above streams the 256 KB of W2 (H = 256) from L2 for every 128-row tile: its 64 KB of stage ring holds what
+// one TMA latency delivers, so the tile time is the weight stream, not the tensor core (12 us per tile against 2 us of MMAs).
+// fp16 operands carry the same 11-bit significand as TF32 in half the bytes: W2 is 128 KB and stays in shared memory for the
+// whole launch next to a 64 KB X tile, the MMAs run at the 16-bit rate (K = 16 per instruction), and nothing is streamed.
+// (Range: |W| <= sqrt(6/fan_in), post-ReLU first-layer activations are bounded by |state - goal| * |W1| < 400 << 65504; the
+// conversion saturates.)  With two accumulator buffers in TMEM the epilogue of tile i (bias, ReLU and the fused output layer,
+// straight from the accumulator: X is never written back) overlaps the MMAs of tile i+1:
+//   row warps : wait acc(i) -> first layer of tile i+1 into X -> barrier -> epilogue + output layer of tile i
+//   MMA warp  : barrier -> H/16 tcgen05.mma.kind::f16 into acc((i+1) & 1) -> commit
+// Wh: the hidden weight in the chunk-major order of the UMMA no-swizzle K-major layout, Wh[(k/8)*H + n][k%8] = half(W2[n][k])
+// (rtd3_tc_sync_weights_f16).
+constexpr int kHfThreads = (kTcRowWarps + 1) * 32;     // 16 row warps + the MMA warp
+
+__host__ __device__ inline size_t hf_smem_bytes(int hid) {
+  return (size_t)hid * kTcRows * 2 + (size_t)hid * hid * 2 + ((size_t)hid * 4 + hid + hid + 2 * hid + 4) * 4 + 64 + kTcColParts * kTcRows * 2 * 4;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
+  return r;
+}
+
+__global__ void __launch_bounds__(kHfThreads, 1)
+mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, const uint16_t* __restrict__ Wh /*[H/8][H][8] half*/,
+                       const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/, int B, uint32_t tmem_cols) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int H = s.hid;
+  unsigned char* Xs = smem_raw;                                      // [H/8][128 rows][8] half
+  unsigned char* Wr = Xs + (size_t)H * kTcRows * 2;                  // [H/8][H rows n][8] half, resident
+  float* W1 = reinterpret_cast<float*>(Wr + (size_t)H * H * 2);      // [H][4] (zero-padded input dim)
+  float* b1 = W1 + H * 4;               // [H]
+  float* b2 = b1 + H;                   // [H]
+  float* Wo = b2 + H;                   // [2][H]
+  float* bo = Wo + 2 * H;               // [2] (+2 pad)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bo + 4);               // acc_ready[2], w_full
+  uint64_t* acc_ready = bars, *w_full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* part = reinterpret_cast<float*>(bars + 4);                   // [column parts][128 rows][2] output-layer partial sums
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int rt = (warp & 3) * 32 + lane;
+  const int parts = (H % (32 * kTcColParts) == 0) ? kTcColParts : ((H % 64 == 0) ? 2 : 1);
+  const int cpart = warp >> 2;
+  const int c_lo = cpart < parts ? cpart * (H / parts) : 0, c_hi = cpart < parts ? c_lo + H / parts : 0;
+  const int tiles = (B + kTcRows - 1) / kTcRows;
+  constexpr int kRowMma = (kTcRowWarps + 1) * 32;
+
+  if (t == 0) {
+    mbar_init(acc_ready, 1);
+    mbar_init(acc_ready + 1, 1);
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  __syncthreads();                                                    // barriers initialised before the weight copies are issued
+  if (warp == kTcRowWarps && lane == 0) {
+    // the resident hidden weight: H*H*2 bytes as 8 bulk copies on one mbarrier, in flight during the setup and the first first-layer
+    const uint32_t bytes = (uint32_t)H * H * 2, chunk = bytes / 8;
+    mbar_arrive_expect_tx(w_full, bytes);
+    for (int c = 0; c < 8; ++c) bulk_g2s(Wr + (size_t)c * chunk, reinterpret_cast<const unsigned char*>(Wh) + (size_t)c * chunk, chunk, w_full);
+  }
+  for (int i = t; i < H * 4; i += kHfThreads) {
+    const int c = i >> 2, j = i & 3;
+    W1[i] = j < s.in ? __ldg(P + net_w_off(s, 0) + c * s.in + j) : 0.f;
+  }
+  for (int i = t; i < H; i += kHfThreads) { b1[i] = __ldg(P + net_b_off(s, 0) + i); b2[i] = __ldg(P + net_b_off(s, 1) + i); }
+  for (int i = t; i < 2 * H; i += kHfThreads) Wo[i] = (i / H) < s.out ? __ldg(P + net_w_off(s, 2) + i) : 0.f;
+  if (t < 2) bo[t] = t < s.out ? __ldg(P + net_b_off(s, 2) + t) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = H, M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+
+  if (warp == kTcRowWarps) {
+    // ===== MMA issuer =====
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      bar_sync(2, kRowMma);                           // X of this tile is in shared memory; accumulator (it & 1) has been drained
+      if (lane == 0) {
+        if (it == 0) mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint32_t acc = tmem + (it & 1u) * (uint32_t)H;
+        for (int k16 = 0; k16 < H / 16; ++k16) {
+          const uint64_t ad = umma_desc_kmajor(smem_u32(Xs + (size_t)(2 * k16) * (kTcRows * 16)), kTcRows * 16, 128);
+          const uint64_t bd = umma_desc_kmajor(smem_u32(Wr + (size_t)(2 * k16) * ((size_t)H * 16)), (uint32_t)H * 16, 128);
+          umma_f16(acc, ad, bd, idesc, k16 != 0 ? 1u : 0u);
+        }
+        umma_commit(acc_ready + (it & 1u));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== row warps =====
+    auto first_layer = [&](int tile) {               // X = half(relu(b1 + x0 W1^T)) of `tile` in the chunk layout
+      const int row = tile * kTcRows + rt;
+      float x0[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < B)
+        for (int j = 0; j < s.in; ++j) x0[j] = __ldg(x + (int64_t)row * s.in + j);
+      for (int c = c_lo; c < c_hi; c += 8) {
+        float h[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(W1 + (c + q) * 4);
+          float v = b1[c + q];
+          v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
+          h[q] = fmaxf(v, 0.f);
+        }
+        uint4 pk;
+        pk.x = pack_half2_sat(h[0], h[1]); pk.y = pack_half2_sat(h[2], h[3]); pk.z = pack_half2_sat(h[4], h[5]); pk.w = pack_half2_sat(h[6], h[7]);
+        *reinterpret_cast<uint4*>(Xs + ((size_t)(c >> 3) * kTcRows + rt) * 16) = pk;
+      }
+      fence_proxy_async();                            // generic-proxy writes of X -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      bar_sync(2, kRowMma);
+    };
+    if ((int)blockIdx.x < tiles) first_layer(blockIdx.x);
+    uint32_t it = 0, phase0 = 0, phase1 = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int row = tile * kTcRows + rt;
+      if (it & 1u) { mbar_wait(acc_ready + 1, phase1); phase1 ^= 1; }
+      else { mbar_wait(acc_ready, phase0); phase0 ^= 1; }
+      tc_fence_after();
+      // the MMAs of this tile have read X: the next tile's first layer may overwrite it, and its MMAs then run under the epilogue below
+      if (tile + (int)gridDim.x < tiles) first_layer(tile + gridDim.x);
+      // epilogue + output layer: y = bo + Wo relu(acc + b2), each thread over its column part of its row
+      float o0 = 0.f, o1 = 0.f;
+      const uint32_t acc = tmem + (it & 1u) * (uint32_t)H + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int cb = c_lo; cb < c_hi; cb += 32) {
+        float v[32];
+        tmem_ld32(acc + (uint32_t)cb, v);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float h = fmaxf(v[q] + b2[cb + q], 0.f);
+          o0 = fmaf(h, Wo[cb + q], o0);
+          o1 = fmaf(h, Wo[H + cb + q], o1);
+        }
+      }
+      tc_fence_before();
+      part[(cpart * kTcRows + rt) * 2] = o0;          // warps without columns contribute zeros
+      part[(cpart * kTcRows + rt) * 2 + 1] = o1;
+      bar_sync(1, kTcRowWarps * 32);
+      if (warp < 4 && row < B) {
+        float y0 = bo[0], y1 = bo[1];
+#pragma unroll
+        for (int c = 0; c < kTcColParts; ++c) { y0 += part[(c * kTcRows + rt) * 2]; y1 += part[(c * kTcRows + rt) * 2 + 1]; }
+        y[(int64_t)row * s.out] = y0;
+        if (s.out > 1) y[(int64_t)row * s.out + 1] = y1;
+      }
+      bar_sync(1, kTcRowWarps * 32);                  // `part` is free for the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+// fp16 arena: six slots of (L-1) hidden-to-hidden weights, nothing else: params_h[(net*(L-1) + l-1)*H*H + ((k/8)*H + n)*8 + k%8] =
+// half(W_l[n][k]) (every matrix 16 B aligned, which the torch-order slots of the fp32 arena are not)
+__global__ void sync_half_kernel(Arena ar, const float* __restrict__ params, uint16_t* __restrict__ params_h) {
+  const int64_t total = ar.total();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int net = 5;
+    while (net > 0 && i < ar.off(net)) --net;
+    const NetShape& s = (net % 3 == 0) ? ar.actor : ar.critic;
+    const int64_t off = ar.off(net);
+    if (!is_hidden_weight(s, off, i)) continue;
+    const int64_t first = (int64_t)s.in * s.hid + s.hid, blk = (int64_t)s.hid * s.hid + s.hid, hh = (int64_t)s.hid * s.hid;
+    const int64_t o2 = i - off - first;
+    const int64_t l = o2 / blk, rem = o2 - l * blk;
+    const int64_t n = rem / s.hid, k = rem - n * s.hid;
+    params_h[((int64_t)net * (s.layers - 1) + l) * hh + ((k >> 3) * s.hid + n) * 8 + (k & 7)] =
+        __half_as_ushort(__float2half_rn(fminf(fmaxf(params[i], -65504.f), 65504.f)));
+  }
+}
+
 // Rebuild both chunk-major copies of the whole arena (u: forward operand order, v: input-gradient operand order).
 __global__ void sync_chunk_major_kernel(NetShape actor, NetShape critic, int64_t sa, int64_t sc, const float* __restrict__ params,
                                         float* __restrict__ params_uv) {
@@ -261,6 +456,48 @@ int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, 
   }
   const int grid = tiles < num_sms ? tiles : num_sms;
   mlp_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, params_u + param_off, x, y, (int)batch);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+/* fp16 chunk-major copies of the hidden-to-hidden weights of all six networks (see mlp_forward_f16_kernel). */
+int32_t rtd3_tc_sync_weights_f16(int32_t hidden, int32_t layers, const float* params, uint16_t* params_h, void* stream) {
+  RTD3_CHECK_ARG(params && params_h && hidden >= 4 && layers >= 1, "bad argument");
+  const Arena ar{NetShape{2, hidden, layers, 2}, NetShape{4, hidden, layers, 1}};
+  sync_half_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(ar, params, params_h);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+/* Network forward with fp16 operands on the tcgen05 tensor cores, hidden weight resident in shared memory (layers == 2). */
+int32_t rtd3_mlp_forward_f16(int32_t hidden, int32_t layers, int32_t net, const float* params, const uint16_t* params_h, const float* x,
+                             float* y, int64_t batch, void* stream) {
+  RTD3_CHECK_ARG(params && params_h && x && y, "null argument");
+  RTD3_CHECK_ARG(hidden % 32 == 0 && hidden >= 64 && hidden <= 256 && layers == 2, "f16 path needs layers == 2 and hidden in {64..256} divisible by 32");
+  RTD3_CHECK_ARG(net >= 0 && net < 6, "net must be 0..5");
+  RTD3_CHECK_ARG(batch >= 0 && batch < (1ll << 31), "bad batch");
+  if (batch == 0) return 0;
+  const Arena ar{NetShape{2, hidden, layers, 2}, NetShape{4, hidden, layers, 1}};
+  const NetShape s = net % 3 == 0 ? ar.actor : ar.critic;
+  const int64_t param_off = ar.off(net);
+  const uint16_t* wh = params_h + (int64_t)net * (layers - 1) * hidden * hidden;
+  const size_t smem = hf_smem_bytes(hidden);
+  static size_t attr = 0;
+  if (smem > attr) {
+    RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int tiles = (int)ceil_div(batch, kTcRows);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    RTD3_CUDA(cudaGetDevice(&dev));
+    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)hidden) cols <<= 1;      // two accumulator buffers, a power of two of TMEM columns
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  mlp_forward_f16_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, wh, x, y, (int)batch, cols);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -338,6 +338,8 @@ class TD3:
             self.world = dist.get_world_size(process_group)
         self.last_losses = None
         self._u_stale = True
+        self.params_h = None                # fp16 copies of the hidden weights (rtd3_mlp_forward_f16), built on first use
+        self._h_stale = True
         self._side_stream = None
         self.sample_chunk_epochs = 10       # epochs per pipelined chunk of td3_update (0 = draw all index sets up front)
         self._graphs = {}
@@ -367,9 +369,38 @@ class TD3:
                                                            _lib.stream_ptr(self.device)), "td3_sync_transposed")
             self._t_stale = False
             self._u_stale = True
+            self._h_stale = True
+
+    def _tc_mode(self):
+        """"tf32" and "f16" both select the tensor-core paths; they differ in the forward kernel only."""
+        return self.precision in ("tf32", "f16")
 
     def _tc_ok(self, batch):
-        return self.precision == "tf32" and self.hidden % 32 == 0 and 64 <= self.hidden <= 256 and self.layers >= 2 and batch >= 128
+        return self._tc_mode() and self.hidden % 32 == 0 and 64 <= self.hidden <= 256 and self.layers >= 2 and batch >= 128
+
+    def _f16_ok(self, batch):
+        return self.precision == "f16" and self.layers == 2 and self._tc_ok(batch)
+
+    def _sync_half(self, force=False):
+        """fp16 copies of the hidden weights for the resident-weight forward; rebuilt whenever the parameters may have changed
+        (the optimiser steps mark them stale, and `td3_update` rebuilds them before it returns so that a captured tick graph,
+        which cannot run this bookkeeping, always reads current weights)."""
+        if self.params_h is None:
+            self.params_h = torch.zeros((6 * max(1, self.layers - 1) * self.hidden * self.hidden,), dtype=torch.float16, device=self.device)
+            self._h_stale = True
+        if force or self._h_stale:
+            _lib.check(_lib.lib().rtd3_tc_sync_weights_f16(self.hidden, self.layers, _lib.ptr(self.params), _lib.ptr(self.params_h),
+                                                           _lib.stream_ptr(self.device)), "tc_sync_weights_f16")
+            self._h_stale = False
+
+    def prepare_forward(self, batch):
+        """Bring every derived weight copy the forward of `batch` rows reads up to date (call before capturing a graph that
+        contains forwards: the capture must not record these one-off rebuilds)."""
+        self.sync_transposed(force=False)
+        if self._f16_ok(batch):
+            self._sync_half()
+        elif self._tc_ok(batch):
+            self._sync_chunk_major()
 
     def _sync_chunk_major(self):
         """Chunk-major weight copy for the tensor-core forward; rebuilt whenever the parameters may have changed (the
@@ -383,7 +414,7 @@ class TD3:
             self._u_stale = False
 
     def _tc_learner_ok(self, batch):
-        return (self.precision == "tf32" and batch >= self.tc_min_batch
+        return (self._tc_mode() and batch >= self.tc_min_batch
                 and bool(_lib.lib().rtd3_td3_tf32_supported(self._handle)))
 
     def flat_grad(self, net):
@@ -395,6 +426,11 @@ class TD3:
         out_dim = 2 if net in (NET_ACTOR, NET_T_ACTOR) else 1
         y = torch.empty((x.shape[0], out_dim), dtype=torch.float32, device=self.device)
         self.sync_transposed(force=False)
+        if self._f16_ok(x.shape[0]):
+            self._sync_half()
+            _lib.check(_lib.lib().rtd3_mlp_forward_f16(self.hidden, self.layers, net, _lib.ptr(self.params), _lib.ptr(self.params_h), _lib.ptr(x),
+                                                       _lib.ptr(y), x.shape[0], _lib.stream_ptr(self.device)), "mlp_forward_f16")
+            return y
         if self._tc_ok(x.shape[0]):
             self._sync_chunk_major()
             _lib.check(_lib.lib().rtd3_mlp_forward_tf32(self.hidden, self.layers, 1 if net in (NET_ACTOR, NET_T_ACTOR) else 0, self._off[net],
@@ -460,6 +496,7 @@ class TD3:
         keep_uv = self.params_u is not None and not self._u_stale
         if not keep_uv:
             self._u_stale = True
+        self._h_stale = True
         _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t),
                                                    _lib.ptr(self.params_u if keep_uv else None), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
@@ -569,7 +606,7 @@ class TD3:
 
     def _launch_epochs(self, replay_buffer, st, use_graph, E):
         saved, self.num_epochs = self.num_epochs, E
-        tf32 = self.precision == "tf32"
+        tf32 = self._tc_mode()
         if tf32:
             self._sync_chunk_major()         # current before the loop; every optimiser step inside keeps it in step
         try:
@@ -595,6 +632,9 @@ class TD3:
             self.num_epochs = saved
             if not tf32:
                 self._u_stale = True         # a replayed graph does not run _adam's bookkeeping
+            self._h_stale = True
+            if self.params_h is not None:
+                self._sync_half()            # a captured tick graph reads the fp16 copies: current again before the update returns
 
     def _td3_update_pipelined(self, replay_buffer, noise, C):
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay

@@ -162,7 +162,7 @@ class BatchedTrainer:
         while done < ticks:
             if self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
                 if self._graph_k is None:
-                    self.robot.td3_agent.sync_transposed(force=False)
+                    self.robot.td3_agent.prepare_forward(self.n)
                     self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
                     g = torch.cuda.CUDAGraph()
                     before = _launches()
@@ -184,7 +184,7 @@ class BatchedTrainer:
     def tick(self):
         if self._use_graph:
             if self._graph is None:
-                self.robot.td3_agent.sync_transposed(force=False)
+                self.robot.td3_agent.prepare_forward(self.n)
                 self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
                 g = torch.cuda.CUDAGraph()
                 before = _launches()
