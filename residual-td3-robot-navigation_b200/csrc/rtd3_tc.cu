@@ -219,7 +219,8 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
 constexpr int kHfThreads = (kTcRowWarps + 1) * 32;     // 16 row warps + the MMA warp
 
 __host__ __device__ inline size_t hf_smem_bytes(int hid) {
-  return (size_t)hid * kTcRows * 2 + (size_t)hid * hid * 2 + ((size_t)hid * 4 + hid + hid + 2 * hid + 4) * 4 + 64 + kTcColParts * kTcRows * 2 * 4;
+  // X | W2 resident | first-layer rows [H][8] | epilogue rows [H][4] | bo | barriers | two partial-sum buffers
+  return (size_t)hid * kTcRows * 2 + (size_t)hid * hid * 2 + ((size_t)hid * 8 + (size_t)hid * 4 + 4) * 4 + 64 + 2 * kTcColParts * kTcRows * 2 * 4;
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -246,15 +247,14 @@ mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/,
   const int H = s.hid;
   unsigned char* Xs = smem_raw;                                      // [H/8][128 rows][8] half
   unsigned char* Wr = Xs + (size_t)H * kTcRows * 2;                  // [H/8][H rows n][8] half, resident
-  float* W1 = reinterpret_cast<float*>(Wr + (size_t)H * H * 2);      // [H][4] (zero-padded input dim)
-  float* b1 = W1 + H * 4;               // [H]
-  float* b2 = b1 + H;                   // [H]
-  float* Wo = b2 + H;                   // [2][H]
-  float* bo = Wo + 2 * H;               // [2] (+2 pad)
+  // per-column parameter rows, one 16 B shared-memory load each (every lane of a warp reads the same column: a broadcast):
+  float* F1 = reinterpret_cast<float*>(Wr + (size_t)H * H * 2);      // [H][8]: in <= 2: {w0, w1, b1, 0, ...}; else {w0..w3, b1, 0, 0, 0}
+  float* E2 = F1 + H * 8;               // [H][4]: {b2, Wo[0][c], Wo[1][c], 0}
+  float* bo = E2 + H * 4;               // [2] (+2 pad)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bo + 4);               // acc_ready[2], w_full
   uint64_t* acc_ready = bars, *w_full = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* part = reinterpret_cast<float*>(bars + 4);                   // [column parts][128 rows][2] output-layer partial sums
+  float* part = reinterpret_cast<float*>(bars + 4);                   // [2 buffers][column parts][128 rows][2] output-layer partial sums
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int rt = (warp & 3) * 32 + lane;
@@ -281,12 +281,21 @@ mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/,
     mbar_arrive_expect_tx(w_full, bytes);
     for (int c = 0; c < 8; ++c) bulk_g2s(Wr + (size_t)c * chunk, reinterpret_cast<const unsigned char*>(Wh) + (size_t)c * chunk, chunk, w_full);
   }
+  const bool in2 = s.in <= 2;
+  for (int i = t; i < H * 8; i += kHfThreads) {
+    const int c = i >> 3, j = i & 7;
+    float v = 0.f;
+    if (j < s.in) v = __ldg(P + net_w_off(s, 0) + c * s.in + j);
+    else if (j == (in2 ? 2 : 4)) v = __ldg(P + net_b_off(s, 0) + c);
+    F1[i] = v;
+  }
   for (int i = t; i < H * 4; i += kHfThreads) {
     const int c = i >> 2, j = i & 3;
-    W1[i] = j < s.in ? __ldg(P + net_w_off(s, 0) + c * s.in + j) : 0.f;
+    float v = 0.f;
+    if (j == 0) v = __ldg(P + net_b_off(s, 1) + c);
+    else if (j - 1 < s.out) v = __ldg(P + net_w_off(s, 2) + (j - 1) * H + c);
+    E2[i] = v;
   }
-  for (int i = t; i < H; i += kHfThreads) { b1[i] = __ldg(P + net_b_off(s, 0) + i); b2[i] = __ldg(P + net_b_off(s, 1) + i); }
-  for (int i = t; i < 2 * H; i += kHfThreads) Wo[i] = (i / H) < s.out ? __ldg(P + net_w_off(s, 2) + i) : 0.f;
   if (t < 2) bo[t] = t < s.out ? __ldg(P + net_b_off(s, 2) + t) : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -316,19 +325,28 @@ mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/,
     }
   } else {
     // ===== row warps =====
-    auto first_layer = [&](int tile) {               // X = half(relu(b1 + x0 W1^T)) of `tile` in the chunk layout
+    auto load_x = [&](int tile, float (&x0)[4]) {   // this thread's input row of `tile`
       const int row = tile * kTcRows + rt;
-      float x0[4] = {0.f, 0.f, 0.f, 0.f};
-      if (row < B)
-        for (int j = 0; j < s.in; ++j) x0[j] = __ldg(x + (int64_t)row * s.in + j);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x0[j] = (row < B && j < s.in) ? __ldg(x + (int64_t)row * s.in + j) : 0.f;
+    };
+    auto first_layer = [&](const float (&x0)[4]) {   // X = half(relu(b1 + x0 W1^T)) in the chunk layout, then hand X to the MMA warp
       for (int c = c_lo; c < c_hi; c += 8) {
         float h[8];
+        if (in2) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 w = *reinterpret_cast<const float4*>(W1 + (c + q) * 4);
-          float v = b1[c + q];
-          v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
-          h[q] = fmaxf(v, 0.f);
+          for (int q = 0; q < 8; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(F1 + (c + q) * 8);
+            h[q] = fmaxf(fmaf(x0[1], w.y, fmaf(x0[0], w.x, w.z)), 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(F1 + (c + q) * 8);
+            float v = F1[(c + q) * 8 + 4];
+            v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
+            h[q] = fmaxf(v, 0.f);
+          }
         }
         uint4 pk;
         pk.x = pack_half2_sat(h[0], h[1]); pk.y = pack_half2_sat(h[2], h[3]); pk.z = pack_half2_sat(h[4], h[5]); pk.w = pack_half2_sat(h[6], h[7]);
@@ -338,15 +356,21 @@ mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/,
       tc_fence_before();
       bar_sync(2, kRowMma);
     };
-    if ((int)blockIdx.x < tiles) first_layer(blockIdx.x);
+    float xn[4];
+    if ((int)blockIdx.x < tiles) {
+      load_x(blockIdx.x, xn);
+      first_layer(xn);
+    }
     uint32_t it = 0, phase0 = 0, phase1 = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int row = tile * kTcRows + rt;
+      const bool more = tile + (int)gridDim.x < tiles;
+      if (more) load_x(tile + gridDim.x, xn);         // in flight while this tile's products finish
       if (it & 1u) { mbar_wait(acc_ready + 1, phase1); phase1 ^= 1; }
       else { mbar_wait(acc_ready, phase0); phase0 ^= 1; }
       tc_fence_after();
       // the MMAs of this tile have read X: the next tile's first layer may overwrite it, and its MMAs then run under the epilogue below
-      if (tile + (int)gridDim.x < tiles) first_layer(tile + gridDim.x);
+      if (more) first_layer(xn);
       // epilogue + output layer: y = bo + Wo relu(acc + b2), each thread over its column part of its row
       float o0 = 0.f, o1 = 0.f;
       const uint32_t acc = tmem + (it & 1u) * (uint32_t)H + ((uint32_t)((warp & 3) * 32) << 16);
@@ -355,23 +379,24 @@ mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/,
         tmem_ld32(acc + (uint32_t)cb, v);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          const float h = fmaxf(v[q] + b2[cb + q], 0.f);
-          o0 = fmaf(h, Wo[cb + q], o0);
-          o1 = fmaf(h, Wo[H + cb + q], o1);
+          const float4 e = *reinterpret_cast<const float4*>(E2 + (cb + q) * 4);
+          const float h = fmaxf(v[q] + e.x, 0.f);
+          o0 = fmaf(h, e.y, o0);
+          o1 = fmaf(h, e.z, o1);
         }
       }
       tc_fence_before();
-      part[(cpart * kTcRows + rt) * 2] = o0;          // warps without columns contribute zeros
-      part[(cpart * kTcRows + rt) * 2 + 1] = o1;
+      float* pt = part + (it & 1u) * (kTcColParts * kTcRows * 2);     // two buffers: tile i+1 writes the other one, and the barrier
+      pt[(cpart * kTcRows + rt) * 2] = o0;                            // of tile i+1 orders tile i+2's writes after tile i's reads
+      pt[(cpart * kTcRows + rt) * 2 + 1] = o1;                        // (warps without columns contribute zeros)
       bar_sync(1, kTcRowWarps * 32);
       if (warp < 4 && row < B) {
         float y0 = bo[0], y1 = bo[1];
 #pragma unroll
-        for (int c = 0; c < kTcColParts; ++c) { y0 += part[(c * kTcRows + rt) * 2]; y1 += part[(c * kTcRows + rt) * 2 + 1]; }
+        for (int c = 0; c < kTcColParts; ++c) { y0 += pt[(c * kTcRows + rt) * 2]; y1 += pt[(c * kTcRows + rt) * 2 + 1]; }
         y[(int64_t)row * s.out] = y0;
         if (s.out > 1) y[(int64_t)row * s.out + 1] = y1;
       }
-      bar_sync(1, kTcRowWarps * 32);                  // `part` is free for the next tile
     }
   }
   tc_fence_before();
