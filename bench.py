@@ -266,7 +266,8 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
 
 def bench_forward(rt, torch, dev):
     """Actor forward (2 -> 256 -> 256 -> 2) of the act hook at rollout-sized batches: fp32 FFMA kernel vs the tcgen05 / TMEM
-    TF32 kernel (opt-in throughput mode).  Tensor-pipe roofline: measured dense bf16 peak / 2 as the TF32 reference."""
+    TF32 kernel (weights streamed per tile) and the f16 kernel (weights resident; both opt-in throughput modes).  Tensor-pipe
+    roofline: the measured dense bf16 peak for 16-bit operands, half of it as the TF32 reference."""
     H, L = 256, 2
     agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L), device=dev)
     agent.sync_transposed()
@@ -275,7 +276,7 @@ def bench_forward(rt, torch, dev):
     for B in (65536, 1 << 20):
         xs = [torch.rand((B, 2), device=dev) * 100 - 50 for _ in range(3)]
         flops = 2.0 * B * (2 * H + (L - 1) * H * H + 2 * H)
-        for precision in ("fp32", "tf32"):
+        for precision in ("fp32", "tf32", "f16"):
             agent.precision = precision
             for k in range(3):
                 agent.forward(0, xs[k])
@@ -291,6 +292,9 @@ def bench_forward(rt, torch, dev):
             row = {"batch": B, "precision": precision, "us": round(us, 1), "rows_per_sec": B / (us * 1e-6), "tflops": flops / us / 1e6}
             if precision == "tf32":
                 row["frac_of_tf32_peak"] = row["tflops"] / (bf16_peak / 2)
+            elif precision == "f16":
+                row["frac_of_16bit_dense_peak"] = row["tflops"] / bf16_peak
+                row["kernel"] = "mlp_forward_f16_kernel: fp16 operands, hidden weight resident in shared memory, tcgen05.mma.kind::f16"
             else:
                 row["frac_of_nominal_fp32_peak"] = row["tflops"] / FP32_FFMA_PEAK_TFLOPS
             rows.append(row)
@@ -305,15 +309,18 @@ def bench_full_loop(rt, torch, dev, world, rank):
     rows = []
     # 8192 envs per GPU x 8 GPUs = the 65 536 envs of configs[3]; 65 536 per GPU = the large end of the metric's env range
     # "hooks": one launch per reference hook (ten per tick); "fused": rtd3_tick_pre / actor forward / rtd3_tick_post, eight ticks per graph
-    for n, precision, form in ((8192, "fp32", "hooks"), (8192, "tf32", "hooks"), (8192, "tf32", "fused"),
-                               (65536, "fp32", "hooks"), (65536, "tf32", "hooks"), (65536, "tf32", "fused")):
+    rs = np.random.RandomState(0)
+    tt = np.linspace(0, 1, 3785)[:, None]                # 3 x 3785 = the 11 355 demonstration states the reference holds after its 3 demos
+    demos = np.concatenate([rs.uniform(5, 95, (1, 2)) * (1 - tt) + rs.uniform(5, 95, (1, 2)) * tt + rs.normal(0, 2.5, (3785, 2)) for _ in range(3)])
+    for n, precision, form in ((8192, "fp32", "hooks"), (8192, "tf32", "hooks"), (8192, "f16", "fused"),
+                               (65536, "tf32", "hooks"), (65536, "f16", "fused")):
         env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
         robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 4 * n))
         robot.td3_agent.precision = precision          # "tf32": the actor forward of the act hook runs on tcgen05 tensor cores
         robot.td3_agent.batch_size = 256
         robot.td3_agent.num_epochs = 20
         robot.memory.sampler = "philox"
-        robot.set_demonstration_states(np.random.RandomState(0).uniform(0, 99, (512, 2)))
+        robot.set_demonstration_states(demos)
         fused = form == "fused"
         tr = rt.BatchedTrainer(env, robot, noise="philox" if fused else "randn", graph=True, check_interval=8, fused=fused)
         advance = tr.run if fused else (lambda k: [tr.tick() for _ in range(k)])
@@ -338,7 +345,7 @@ def bench_full_loop(rt, torch, dev, world, rank):
         ms = float(t[0])
         rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "tick": form, "ticks": ticks, "ms_per_tick": ms / ticks,
                      "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
-                     "td3_epochs_per_update": 20, "replay_rows_per_gpu": len(robot.memory),
+                     "td3_epochs_per_update": 20, "td3_batch": 256, "replay_rows_per_gpu": len(robot.memory), "demo_states": int(demos.shape[0]),
                      "note": ("three launches per tick, eight ticks per CUDA graph; noise Philox inside the tick kernel" if fused else
                               "ten launches per tick, one CUDA graph per tick; noise torch.randn")
                              + "; finished-episode counter read every 8 ticks; replay sampling philox"})
