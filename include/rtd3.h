@@ -333,6 +333,15 @@ int32_t rtd3_tick_pre(const rtd3_tick_state* t, void* stream);
 int32_t rtd3_tick_post(rtd3_env* h, const rtd3_tick_state* t, const float* residual, const double* unit_noise, int32_t noise_mode,
                        void* stream);
 
+/* `ticks` consecutive ticks in ONE launch, the actor (2 -> hidden -> hidden -> 2, network 0 of the arena) evaluated in the kernel
+ * by the f16 resident-weight forward (rtd3_mlp_forward_f16; params_h from rtd3_tc_sync_weights_f16): every CTA runs all the ticks
+ * of its 128-env tiles - envs are independent - so the hidden weight is loaded once per launch and a tick costs no launch.
+ * Leaves every array as `ticks` rounds of rtd3_tick_pre / rtd3_mlp_forward_f16 / rtd3_tick_post would (the replay rows in another
+ * order); the Philox noise of tick k is keyed tick_base + k + 1 (tick_base = ticks run so far), and tick_counter is left at
+ * tick_base + ticks.  noise_mode NONE or PHILOX; needs demo_list_start (or num_demo == 0); layers == 2, hidden % 32 == 0, 64..256. */
+int32_t rtd3_tick_run_f16(rtd3_env* h, const rtd3_tick_state* t, int32_t hidden, int32_t layers, const float* params,
+                          const uint16_t* params_h, int32_t noise_mode, int64_t ticks, uint64_t tick_base, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, TF32) large-batch forward - opt-in throughput mode, not the parity path
  * ---------------------------------------------------------------------------------------------- */

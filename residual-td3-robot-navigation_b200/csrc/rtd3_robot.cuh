@@ -110,16 +110,17 @@ __device__ __forceinline__ double nearest_demo_sq(const double px, const double 
   return best;
 }
 
-// All threads of the CTA must call this (block-wide barriers for the demo sweep, warp ballots for the compacted push).
+// Whole warps must call this (warp ballots for the compacted push); with kAllowSweep all threads of the CTA (block-wide barriers
+// of the demo sweep).
 // `live`: this thread holds an env that steps in this tick; (sx,sy) pre-step state, (ax,ay) action, (nx,ny) next state.
 // Demo points ([m][2] float64, shared by all envs): candidate lists when `list_start` is given, else swept from shared memory.
+template <bool kAllowSweep = true>
 __device__ __forceinline__ void transition_env(const RobotState& st, const float sxi, const float syi, const float axi, const float ayi,
                                                const float nxi, const float nyi, const bool live, const int64_t i, const int64_t n,
                                                const double* __restrict__ demo, const int32_t* __restrict__ list_start /*nullable*/,
                                                const double* __restrict__ list_pts, const int64_t m,
                                                float* __restrict__ reward_out, double* __restrict__ reward64, uint8_t* __restrict__ done_out,
                                                const ReplayRing& ring, const bool masked_push) {
-  __shared__ double2 tile[512];
   const int64_t ii = live ? i : 0;
   const double px = (double)nxi, py = (double)nyi;
   // compute_reward([next_state])  robot.py:741-762
@@ -129,7 +130,10 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
   double best = INFINITY;
   if (m > 0 && list_start) {
     if (live && !reached && st.demo_flag[ii]) best = nearest_demo_sq(px, py, demo, m, list_start, list_pts);
-  } else if (m > 0) {
+  } else if (kAllowSweep && m > 0) {
+    // (callers that cannot take a block-wide barrier here - a subset of the CTA's warps - instantiate kAllowSweep = false and
+    // guarantee lists or m == 0)
+    __shared__ double2 tile[512];
     double b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;      // four independent minimum chains
     for (int64_t base = 0; base < m; base += 512) {
       const int cnt = (int)min((int64_t)512, m - base);

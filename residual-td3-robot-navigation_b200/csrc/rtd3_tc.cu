@@ -19,6 +19,7 @@
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
 #include "rtd3_tc.cuh"
+#include "rtd3_tc_f16.cuh"
 #include "rtd3_td3.cuh"
 
 namespace rtd3 {
@@ -214,188 +215,66 @@ mlp_forward_tc_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, 
 // straight from the accumulator: X is never written back) overlaps the MMAs of tile i+1:
 //   row warps : wait acc(i) -> first layer of tile i+1 into X -> barrier -> epilogue + output layer of tile i
 //   MMA warp  : barrier -> H/16 tcgen05.mma.kind::f16 into acc((i+1) & 1) -> commit
-// Wh: the hidden weight in the chunk-major order of the UMMA no-swizzle K-major layout, Wh[(k/8)*H + n][k%8] = half(W2[n][k])
-// (rtd3_tc_sync_weights_f16).
-constexpr int kHfThreads = (kTcRowWarps + 1) * 32;     // 16 row warps + the MMA warp
-
-__host__ __device__ inline size_t hf_smem_bytes(int hid) {
-  // X | W2 resident | first-layer rows [H][8] | epilogue rows [H][4] | bo | barriers | two partial-sum buffers
-  return (size_t)hid * kTcRows * 2 + (size_t)hid * hid * 2 + ((size_t)hid * 8 + (size_t)hid * 4 + 4) * 4 + 64 + 2 * kTcColParts * kTcRows * 2 * 4;
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
-  return r;
-}
-
+// The per-tile pieces live in rtd3_tc_f16.cuh (the multi-tick kernel of rtd3_tick.cu runs the same code).
 __global__ void __launch_bounds__(kHfThreads, 1)
 mlp_forward_f16_kernel(NetShape s, const float* __restrict__ P /*torch layout*/, const uint16_t* __restrict__ Wh /*[H/8][H][8] half*/,
                        const float* __restrict__ x /*[B][in]*/, float* __restrict__ y /*[B][out]*/, int B, uint32_t tmem_cols) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int H = s.hid;
-  unsigned char* Xs = smem_raw;                                      // [H/8][128 rows][8] half
-  unsigned char* Wr = Xs + (size_t)H * kTcRows * 2;                  // [H/8][H rows n][8] half, resident
-  // per-column parameter rows, one 16 B shared-memory load each (every lane of a warp reads the same column: a broadcast):
-  float* F1 = reinterpret_cast<float*>(Wr + (size_t)H * H * 2);      // [H][8]: in <= 2: {w0, w1, b1, 0, ...}; else {w0..w3, b1, 0, 0, 0}
-  float* E2 = F1 + H * 8;               // [H][4]: {b2, Wo[0][c], Wo[1][c], 0}
-  float* bo = E2 + H * 4;               // [2] (+2 pad)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bo + 4);               // acc_ready[2], w_full
-  uint64_t* acc_ready = bars, *w_full = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* part = reinterpret_cast<float*>(bars + 4);                   // [2 buffers][column parts][128 rows][2] output-layer partial sums
-
+  const HfSmem m = hf_carve(smem_raw, H);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int rt = (warp & 3) * 32 + lane;
-  const int parts = (H % (32 * kTcColParts) == 0) ? kTcColParts : ((H % 64 == 0) ? 2 : 1);
-  const int cpart = warp >> 2;
-  const int c_lo = cpart < parts ? cpart * (H / parts) : 0, c_hi = cpart < parts ? c_lo + H / parts : 0;
-  const int tiles = (B + kTcRows - 1) / kTcRows;
-  constexpr int kRowMma = (kTcRowWarps + 1) * 32;
-
-  if (t == 0) {
-    mbar_init(acc_ready, 1);
-    mbar_init(acc_ready + 1, 1);
-    mbar_init(w_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  __syncthreads();                                                    // barriers initialised before the weight copies are issued
-  if (warp == kTcRowWarps && lane == 0) {
-    // the resident hidden weight: H*H*2 bytes as 8 bulk copies on one mbarrier, in flight during the setup and the first first-layer
-    const uint32_t bytes = (uint32_t)H * H * 2, chunk = bytes / 8;
-    mbar_arrive_expect_tx(w_full, bytes);
-    for (int c = 0; c < 8; ++c) bulk_g2s(Wr + (size_t)c * chunk, reinterpret_cast<const unsigned char*>(Wh) + (size_t)c * chunk, chunk, w_full);
-  }
+  const int rt = (warp & 3) * 32 + lane, cpart = warp >> 2;
+  int c_lo, c_hi;
+  hf_columns(H, cpart, c_lo, c_hi);
+  const int tiles = (B + kHfRows - 1) / kHfRows;
   const bool in2 = s.in <= 2;
-  for (int i = t; i < H * 8; i += kHfThreads) {
-    const int c = i >> 3, j = i & 7;
-    float v = 0.f;
-    if (j < s.in) v = __ldg(P + net_w_off(s, 0) + c * s.in + j);
-    else if (j == (in2 ? 2 : 4)) v = __ldg(P + net_b_off(s, 0) + c);
-    F1[i] = v;
-  }
-  for (int i = t; i < H * 4; i += kHfThreads) {
-    const int c = i >> 2, j = i & 3;
-    float v = 0.f;
-    if (j == 0) v = __ldg(P + net_b_off(s, 1) + c);
-    else if (j - 1 < s.out) v = __ldg(P + net_w_off(s, 2) + (j - 1) * H + c);
-    E2[i] = v;
-  }
-  if (t < 2) bo[t] = t < s.out ? __ldg(P + net_b_off(s, 2) + t) : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = hf_setup(m, s, P, Wh, tmem_cols);
+  const uint32_t idesc = hf_idesc(H);
 
-  // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = H, M = 128
-  const uint32_t idesc = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
-
-  if (warp == kTcRowWarps) {
+  if (warp == kHfRowWarps) {
     // ===== MMA issuer =====
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      bar_sync(2, kRowMma);                           // X of this tile is in shared memory; accumulator (it & 1) has been drained
+      bar_sync(2, kHfRowMma);                         // X of this tile is in shared memory; accumulator (it & 1) has been drained
       if (lane == 0) {
-        if (it == 0) mbar_wait(w_full, 0);
-        tc_fence_after();
-        const uint32_t acc = tmem + (it & 1u) * (uint32_t)H;
-        for (int k16 = 0; k16 < H / 16; ++k16) {
-          const uint64_t ad = umma_desc_kmajor(smem_u32(Xs + (size_t)(2 * k16) * (kTcRows * 16)), kTcRows * 16, 128);
-          const uint64_t bd = umma_desc_kmajor(smem_u32(Wr + (size_t)(2 * k16) * ((size_t)H * 16)), (uint32_t)H * 16, 128);
-          umma_f16(acc, ad, bd, idesc, k16 != 0 ? 1u : 0u);
-        }
-        umma_commit(acc_ready + (it & 1u));
+        if (it == 0) mbar_wait(m.w_full, 0);
+        hf_issue_tile(m, H, tmem + (it & 1u) * (uint32_t)H, idesc, m.acc_ready + (it & 1u));
       }
       __syncwarp();
     }
   } else {
     // ===== row warps =====
     auto load_x = [&](int tile, float (&x0)[4]) {   // this thread's input row of `tile`
-      const int row = tile * kTcRows + rt;
+      const int row = tile * kHfRows + rt;
 #pragma unroll
       for (int j = 0; j < 4; ++j) x0[j] = (row < B && j < s.in) ? __ldg(x + (int64_t)row * s.in + j) : 0.f;
-    };
-    auto first_layer = [&](const float (&x0)[4]) {   // X = half(relu(b1 + x0 W1^T)) in the chunk layout, then hand X to the MMA warp
-      for (int c = c_lo; c < c_hi; c += 8) {
-        float h[8];
-        if (in2) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(F1 + (c + q) * 8);
-            h[q] = fmaxf(fmaf(x0[1], w.y, fmaf(x0[0], w.x, w.z)), 0.f);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(F1 + (c + q) * 8);
-            float v = F1[(c + q) * 8 + 4];
-            v = fmaf(x0[0], w.x, v); v = fmaf(x0[1], w.y, v); v = fmaf(x0[2], w.z, v); v = fmaf(x0[3], w.w, v);
-            h[q] = fmaxf(v, 0.f);
-          }
-        }
-        uint4 pk;
-        pk.x = pack_half2_sat(h[0], h[1]); pk.y = pack_half2_sat(h[2], h[3]); pk.z = pack_half2_sat(h[4], h[5]); pk.w = pack_half2_sat(h[6], h[7]);
-        *reinterpret_cast<uint4*>(Xs + ((size_t)(c >> 3) * kTcRows + rt) * 16) = pk;
-      }
-      fence_proxy_async();                            // generic-proxy writes of X -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      bar_sync(2, kRowMma);
     };
     float xn[4];
     if ((int)blockIdx.x < tiles) {
       load_x(blockIdx.x, xn);
-      first_layer(xn);
+      hf_first_layer(m, xn, in2, rt, c_lo, c_hi);
+      bar_sync(2, kHfRowMma);
     }
     uint32_t it = 0, phase0 = 0, phase1 = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int row = tile * kTcRows + rt;
+      const int row = tile * kHfRows + rt;
       const bool more = tile + (int)gridDim.x < tiles;
       if (more) load_x(tile + gridDim.x, xn);         // in flight while this tile's products finish
-      if (it & 1u) { mbar_wait(acc_ready + 1, phase1); phase1 ^= 1; }
-      else { mbar_wait(acc_ready, phase0); phase0 ^= 1; }
+      if (it & 1u) { mbar_wait(m.acc_ready + 1, phase1); phase1 ^= 1; }
+      else { mbar_wait(m.acc_ready, phase0); phase0 ^= 1; }
       tc_fence_after();
       // the MMAs of this tile have read X: the next tile's first layer may overwrite it, and its MMAs then run under the epilogue below
-      if (more) first_layer(xn);
-      // epilogue + output layer: y = bo + Wo relu(acc + b2), each thread over its column part of its row
-      float o0 = 0.f, o1 = 0.f;
-      const uint32_t acc = tmem + (it & 1u) * (uint32_t)H + ((uint32_t)((warp & 3) * 32) << 16);
-      for (int cb = c_lo; cb < c_hi; cb += 32) {
-        float v[32];
-        tmem_ld32(acc + (uint32_t)cb, v);
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float4 e = *reinterpret_cast<const float4*>(E2 + (cb + q) * 4);
-          const float h = fmaxf(v[q] + e.x, 0.f);
-          o0 = fmaf(h, e.y, o0);
-          o1 = fmaf(h, e.z, o1);
-        }
+      if (more) {
+        hf_first_layer(m, xn, in2, rt, c_lo, c_hi);
+        bar_sync(2, kHfRowMma);
       }
-      tc_fence_before();
-      float* pt = part + (it & 1u) * (kTcColParts * kTcRows * 2);     // two buffers: tile i+1 writes the other one, and the barrier
-      pt[(cpart * kTcRows + rt) * 2] = o0;                            // of tile i+1 orders tile i+2's writes after tile i's reads
-      pt[(cpart * kTcRows + rt) * 2 + 1] = o1;                        // (warps without columns contribute zeros)
-      bar_sync(1, kTcRowWarps * 32);
+      // two part buffers: tile i+1 writes the other one, and the barrier of tile i+1 orders tile i+2's writes after tile i's reads
+      hf_epilogue(m, tmem + (it & 1u) * (uint32_t)H + ((uint32_t)((warp & 3) * 32) << 16), rt, cpart, c_lo, c_hi, (int)(it & 1u));
+      bar_sync(1, kHfRowThreads);
       if (warp < 4 && row < B) {
-        float y0 = bo[0], y1 = bo[1];
-#pragma unroll
-        for (int c = 0; c < kTcColParts; ++c) { y0 += pt[(c * kTcRows + rt) * 2]; y1 += pt[(c * kTcRows + rt) * 2 + 1]; }
-        y[(int64_t)row * s.out] = y0;
-        if (s.out > 1) y[(int64_t)row * s.out + 1] = y1;
+        const float2 o = hf_output(m, rt, (int)(it & 1u));
+        y[(int64_t)row * s.out] = o.x;
+        if (s.out > 1) y[(int64_t)row * s.out + 1] = o.y;
       }
     }
   }
@@ -512,7 +391,7 @@ int32_t rtd3_mlp_forward_f16(int32_t hidden, int32_t layers, int32_t net, const 
     RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  const int tiles = (int)ceil_div(batch, kTcRows);
+  const int tiles = (int)ceil_div(batch, kHfRows);
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

@@ -13,6 +13,7 @@
 #include "rtd3_env_step.cuh"
 #include "rtd3_mt.cuh"
 #include "rtd3_robot.cuh"
+#include "rtd3_tc_f16.cuh"
 
 namespace rtd3 {
 
@@ -45,14 +46,14 @@ __global__ void __launch_bounds__(256) tick_pre_kernel(rtd3_tick_state t) {
   if (i == 0 && t.tick_counter) t.tick_counter[0] += 1ull;
 }
 
-__global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,
-                                                        const float* __restrict__ residual /*[n][2]*/,
-                                                        const double* __restrict__ unit_noise /*[2][n], mode 1*/, int noise_mode) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Second half of a tick for env i (`in`: i < n; whole warps call this): compose the action from the actor's residual, step,
+// process_transition, money counters, masked reset.  tick_index keys the Philox noise.
+template <bool kAllowSweep>
+__device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const float2* __restrict__ table, const int64_t i, const bool in,
+                                              const int type, const float2 res, const double* __restrict__ unit_noise, const int noise_mode,
+                                              const uint64_t tick_index) {
   const int64_t n = t.n;
-  const bool in = i < n;
   const int64_t ii = in ? i : 0;
-  const int type = in ? (int)t.type[ii] : 1;
   const bool live = in && type == 0;
   const float x = t.x[ii], y = t.y[ii];
   // get_next_action_training: envs that do not step in this tick get a null action (robot-learning.py:82-95)
@@ -60,9 +61,9 @@ __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, co
   if (live) {
     double zx = 0.0, zy = 0.0;
     if (noise_mode == RTD3_TICK_NOISE_GIVEN) { zx = unit_noise[i]; zy = unit_noise[n + i]; }
-    else if (noise_mode == RTD3_TICK_NOISE_PHILOX) philox_normal2(t.philox_seed, t.tick_counter[0], (uint64_t)i, zx, zy);
+    else if (noise_mode == RTD3_TICK_NOISE_PHILOX) philox_normal2(t.philox_seed, tick_index, (uint64_t)i, zx, zy);
     double cx, cy;
-    compose_env(x, y, t.goal[i], t.goal[n + i], reinterpret_cast<const float2*>(residual)[i], noise_mode != RTD3_TICK_NOISE_NONE, zx, zy,
+    compose_env(x, y, t.goal[i], t.goal[n + i], res, noise_mode != RTD3_TICK_NOISE_NONE, zx, zy,
                 noise_mode != RTD3_TICK_NOISE_NONE ? t.noise_scale[i] : 0.0, cx, cy);
     ax = (float)cx;
     ay = (float)cy;
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, co
   const RobotState st{t.goal, t.hist, t.hist_count, t.hist_head, t.goal_reached, t.stuck_flag, t.demo_flag, t.plan_index, t.path_length};
   const ReplayRing ring{(float2*)t.rp_s, (float2*)t.rp_a, t.rp_r, (float2*)t.rp_s2, t.rp_notdone, t.capacity, 0,
                         (unsigned long long*)t.rp_total};
-  transition_env(st, x, y, ax, ay, nx, ny, live, i, n, t.demo, t.demo_list_start, t.demo_list, t.num_demo, t.reward, t.reward64, t.done, ring,
-                 true);
+  transition_env<kAllowSweep>(st, x, y, ax, ay, nx, ny, live, i, n, t.demo, t.demo_list_start, t.demo_list, t.num_demo, t.reward, t.reward64, t.done,
+                              ring, true);
   if (in) {
     t.ax[i] = ax;
     t.ay[i] = ay;
@@ -87,6 +88,96 @@ __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, co
   }
   // Environment.reset where the tick is a 'reset' (warp-synchronous: wrapping MT19937 streams are twisted by the whole warp)
   reset_env_warp(t.env_bank, t.region, in && type == 2, i, t.x, t.y, t.state64);
+}
+
+__global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,
+                                                           const float* __restrict__ residual /*[n][2]*/,
+                                                           const double* __restrict__ unit_noise /*[2][n], mode 1*/, int noise_mode) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < t.n;
+  const int64_t ii = in ? i : 0;
+  tick_post_env<true>(t, table, i, in, in ? (int)t.type[ii] : 1, reinterpret_cast<const float2*>(residual)[ii], unit_noise, noise_mode,
+                      t.tick_counter ? t.tick_counter[0] : 0ull);
+}
+
+// ---- K ticks in ONE launch (actor 2 -> H -> H -> 2 on the f16 resident-weight forward, rtd3_tc_f16.cuh) -------------------------
+// Envs are independent, so a CTA can run all K ticks of its 128-env tile without talking to any other CTA: the actor's hidden
+// weight is loaded into shared memory once per launch instead of once per tick, and a tick costs no launch at all.  Per tick:
+//   owner threads (warps 0-3, one env each): state machine + actor input  -> barrier
+//   16 row warps: first layer into X                                       -> barrier with the MMA warp -> products -> epilogue -> barrier
+//   owner threads: residual from the partial sums, then tick_post_env (action, step, transition, replay push, reset)
+// Same device functions, same order per env as rtd3_tick_pre / rtd3_mlp_forward_f16 / rtd3_tick_post: bit-identical arrays
+// (tests/test_tick_gpu.py).  Needs candidate lists or no demonstration states (no block-wide sweep here) and Philox or no noise.
+__global__ void __launch_bounds__(kHfThreads, 1)
+tick_f16_kernel(rtd3_tick_state t, const float2* __restrict__ table, NetShape s, const float* __restrict__ P, const uint16_t* __restrict__ Wh,
+                int noise_mode, int K, uint64_t tick_base, uint32_t tmem_cols) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int H = s.hid;
+  const HfSmem m = hf_carve(smem_raw, H);
+  float2* sbase = reinterpret_cast<float2*>(m.extra);                 // [128] actor input of the tile's envs
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rt = (warp & 3) * 32 + lane, cpart = warp >> 2;
+  int c_lo, c_hi;
+  hf_columns(H, cpart, c_lo, c_hi);
+  const int64_t n = t.n;
+  const int tiles = (int)((n + kHfRows - 1) / kHfRows);
+  const uint32_t tmem = hf_setup(m, s, P, Wh, tmem_cols);
+  const uint32_t idesc = hf_idesc(H);
+
+  if (warp == kHfRowWarps) {
+    bool first = true;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+      for (int k = 0; k < K; ++k) {
+        bar_sync(2, kHfRowMma);                       // X of this (tile, tick) is in shared memory, the accumulator has been drained
+        if (lane == 0) {
+          if (first) mbar_wait(m.w_full, 0);
+          hf_issue_tile(m, H, tmem, idesc, m.acc_ready);
+        }
+        first = false;
+        __syncwarp();
+      }
+  } else {
+    const bool owner = cpart == 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t i = (int64_t)tile * kHfRows + rt;
+      const bool in = i < n;
+      for (int k = 0; k < K; ++k) {
+        int type = 1;
+        if (owner) {
+          bool upd = false;
+          float2 base = make_float2(0.f, 0.f);
+          if (in) {
+            type = action_type_env(t.num_episodes, t.demo_flag, t.plan_index, t.path_length, t.goal_reached, t.stuck_flag, t.noise_scale, i, upd);
+            t.type[i] = (int8_t)type;
+            t.update[i] = upd ? 1 : 0;
+            base = baseline_env(t.x[i], t.y[i], t.goal[i], t.goal[n + i]);
+            reinterpret_cast<float2*>(t.base)[i] = base;
+          }
+          const uint32_t ended = __ballot_sync(0xffffffffu, upd);
+          if (ended && lane == 0) atomicAdd(t.any_update, __popc(ended));
+          sbase[rt] = base;
+        }
+        bar_sync(1, kHfRowThreads);
+        const float2 b = sbase[rt];
+        const float x0[4] = {b.x, b.y, 0.f, 0.f};
+        hf_first_layer(m, x0, true, rt, c_lo, c_hi);
+        bar_sync(2, kHfRowMma);
+        mbar_wait(m.acc_ready, phase);
+        phase ^= 1;
+        tc_fence_after();
+        hf_epilogue(m, tmem + ((uint32_t)((warp & 3) * 32) << 16), rt, cpart, c_lo, c_hi, 0);
+        bar_sync(1, kHfRowThreads);
+        // the other twelve warps go on to wait for the next tick's actor input; sbase / part are rewritten only after barriers the
+        // owners reach after they are done reading them
+        if (owner) tick_post_env<false>(t, table, i, in, type, hf_output(m, rt, 0), nullptr, noise_mode, tick_base + (uint64_t)k + 1ull);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+  if (blockIdx.x == 0 && tid == 0 && t.tick_counter) t.tick_counter[0] = tick_base + (uint64_t)K;   // as K launches of rtd3_tick_pre leave it
 }
 
 static int32_t check_state(const rtd3_tick_state* t) {
@@ -134,6 +225,32 @@ int32_t rtd3_tick_post(rtd3_env* h, const rtd3_tick_state* t, const float* resid
   // elementwise work plus a few candidate demo states per env: small CTAs spread a small batch over more SMs
   const int block = t->n <= (int64_t)h->num_sms * 256 ? 128 : 256;
   tick_post_kernel<<<(int)ceil_div(t->n, block), block, 0, st>>>(*t, h->table, residual, unit_noise, noise_mode);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_tick_run_f16(rtd3_env* h, const rtd3_tick_state* t, int32_t hidden, int32_t layers, const float* params,
+                          const uint16_t* params_h, int32_t noise_mode, int64_t ticks, uint64_t tick_base, void* stream) {
+  if (int32_t e = check_state(t)) return e;
+  RTD3_CHECK_ARG(h && h->has_map, "environment has no dynamics map (call rtd3_env_set_map)");
+  RTD3_CHECK_ARG(params && params_h, "null parameters");
+  RTD3_CHECK_ARG(hidden % 32 == 0 && hidden >= 64 && hidden <= 256 && layers == 2, "needs layers == 2 and hidden in {64..256} divisible by 32");
+  RTD3_CHECK_ARG(noise_mode == RTD3_TICK_NOISE_NONE || noise_mode == RTD3_TICK_NOISE_PHILOX, "noise must be none or philox");
+  RTD3_CHECK_ARG(t->num_demo == 0 || t->demo_list_start, "needs candidate lists (rtd3_demo_lists) or no demonstration states");
+  RTD3_CHECK_ARG(ticks >= 0 && ticks < (1ll << 30), "bad tick count");
+  if (t->n == 0 || ticks == 0) return 0;
+  const NetShape s{2, hidden, layers, 2};
+  const size_t smem = hf_smem_bytes(hidden) + kHfRows * sizeof(float2);
+  static size_t attr = 0;
+  if (smem > attr) {
+    RTD3_CUDA(cudaFuncSetAttribute(tick_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  uint32_t cols = 32;
+  while (cols < (uint32_t)hidden) cols <<= 1;
+  const int64_t tiles = ceil_div(t->n, kHfRows);
+  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  tick_f16_kernel<<<grid, kHfThreads, smem, (cudaStream_t)stream>>>(*t, h->table, s, params, params_h, noise_mode, (int)ticks, tick_base, cols);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -87,6 +87,7 @@ class BatchedTrainer:
         if noise not in ("mt19937", "randn", "philox"):
             raise ValueError("unknown noise mode %r" % (noise,))
         self.philox_seed = int(philox_seed)
+        self.multi_tick_kernel = True         # run() may use rtd3_tick_run_f16 (see _multi_tick_ok)
         self._tick_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def money_remaining(self, tick_charge=0.0):
@@ -154,13 +155,38 @@ class BatchedTrainer:
         robot.memory._mark_device_advanced()
         return robot._type
 
+    def _multi_tick_ok(self):
+        """`rtd3_tick_run_f16` applies: fused ticks, f16 actor forward (2 x H), Philox noise, candidate lists or no demo states."""
+        agent, robot = self.robot.td3_agent, self.robot
+        return (self.fused and self.multi_tick_kernel and self.noise == "philox" and agent._f16_ok(self.n)
+                and (robot._demo_dev is None or robot._demo_cells is not None))
+
+    def _run_multi_tick(self, K):
+        from . import _lib
+        agent = self.robot.td3_agent
+        if self.n > self.robot.memory.capacity:
+            raise ValueError("more envs than replay rows: raise buffer_size")
+        agent.prepare_forward(self.n)
+        t = self._tick_state()
+        _lib.check(_lib.lib().rtd3_tick_run_f16(self.env._handle, _lib.ctypes.byref(t), agent.hidden, agent.layers, _lib.ptr(agent.params),
+                                                _lib.ptr(agent.params_h), _lib.TICK_NOISE_PHILOX, K, self.ticks, _lib.stream_ptr(self.device)),
+                   "tick_run_f16")
+        self.robot.memory._mark_device_advanced()
+        self._types = self.robot._type
+
     def run(self, ticks):
-        """`ticks` ticks.  With `graph=True, fused=True` they are replayed `check_interval` at a time from ONE captured graph (the
-        finished-episode counter is read, and a due `td3_update` runs, between the replays exactly where `tick()` would do it)."""
+        """`ticks` ticks, `check_interval` at a time (the finished-episode counter is read, and a due `td3_update` runs, between
+        the blocks exactly where `tick()` would do it).  A block is ONE launch of the multi-tick kernel when `_multi_tick_ok()`,
+        else - with `graph=True, fused=True` - one replay of a graph holding `check_interval` fused ticks."""
         K = self.check_interval
         done = 0
         while done < ticks:
-            if self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
+            if self._multi_tick_ok() and self.ticks % K == 0 and ticks - done >= K:
+                self._run_multi_tick(K)
+                self.ticks += K
+                done += K
+                self.robot.maybe_update()
+            elif self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
                 if self._graph_k is None:
                     self.robot.td3_agent.prepare_forward(self.n)
                     self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)

@@ -156,3 +156,28 @@ def test_tick_argument_errors(pkg, env_golden):
     assert L.rtd3_tick_pre(lib.ctypes.byref(t), None) == -1
     with pytest.raises(ValueError):
         pkg.BatchedTrainer(env, robot, noise="philox", fused=False)
+
+
+@pytest.mark.parametrize("n,m,hidden", [(2048, 400, 64), (8192, 11355, 256), (20000, 0, 128), (333, 700, 96)])
+def test_multi_tick_kernel_matches_the_three_launch_tick(pkg, env_golden, n, m, hidden):
+    """rtd3_tick_run_f16 (check_interval ticks in ONE launch, actor forward inside the kernel) against the fused three-launch tick
+    with the same f16 forward: the same device functions run per env in the same order, so every array must be bit-identical.
+    20 000 envs: more tiles than SMs (a CTA runs all ticks of one tile, then of the next); 333: a ragged last tile."""
+    snaps = []
+    for multi in (False, True):
+        env, robot, tr = _build(pkg, env_golden, n, _demo_path(m) if m else None, True, noise="philox", graph=False, check_interval=8,
+                                hidden=hidden, grid_min=64)
+        robot.td3_agent.precision = "f16"
+        tr.multi_tick_kernel = multi
+        assert tr._multi_tick_ok() == multi
+        before = pkg._lib.launch_count()
+        tr.run(8 * 9 + 3)                                   # nine blocks of 8 ticks + three single ticks
+        launches = pkg._lib.launch_count() - before
+        snaps.append(_snapshot(env, robot, tr))
+        assert tr.ticks == 75 and int(tr._tick_counter.item()) == 75
+        if multi:
+            assert launches <= 9 + 3 * 3 + 2                # one launch per block (+ the one-off weight copies)
+    (a, rows_a, tab_a), (b, rows_b, tab_b) = snaps
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert rows_a == rows_b and rows_a > 0 and np.array_equal(tab_a, tab_b)

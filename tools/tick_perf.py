@@ -31,9 +31,12 @@ def timed(fn, reps):
 for n in [int(a) for a in sys.argv[1:]] or [8192, 65536]:
     for precision in os.environ.get("PRECISIONS", "tf32,fp32").split(","):
         for label, fused, noise, multi in (("hook-by-hook, 1-tick graph", False, "randn", False), ("fused, 1-tick graph", True, "philox", False),
-                                          ("fused, 8-tick graph", True, "philox", True)):
+                                          ("fused, 8-tick graph", True, "philox", True), ("fused, 8-tick kernel", True, "philox", "kernel")):
+            if multi == "kernel" and precision != "f16":
+                continue
             for updates in (False, True):
                 tr, robot = build(n, fused, noise, precision, updates)
+                tr.multi_tick_kernel = multi == "kernel"
                 loop = (lambda k: tr.run(k)) if multi else (lambda k: [tr.tick() for _ in range(k)])
                 loop(160 if updates else 32)
                 u0 = robot.num_updates
