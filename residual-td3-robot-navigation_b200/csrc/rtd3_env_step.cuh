@@ -70,23 +70,61 @@ struct SmemTable {
 };
 
 // Environment.reset for the lanes of one warp (environment.py:130-137): `active` lanes draw a new start state from their env's
-// MT19937 stream.  All 32 lanes must call it (streams that wrap are twisted by the whole warp, rtd3_mt.cuh).
-__device__ __forceinline__ void reset_env_warp(const rtd3_mt_bank& b, const double* __restrict__ region, bool active, int64_t i,
-                                               float* __restrict__ x, float* __restrict__ y, double* __restrict__ state64) {
+// MT19937 stream.  All 32 lanes must call both halves (streams that wrap are twisted by the whole warp, rtd3_mt.cuh).
+// Split in two so that a caller can put other work between the loads and their use: reset_load_warp issues the loads (stream
+// position, init region and - unless a lane's stream wraps within the next four words, ~0.6 % of the draws - the four state
+// words themselves, independent of each other), reset_finish_warp turns them into the state.
+struct ResetLoads {
+  int pos;
+  double left, right, bottom, top;
+  uint32_t w[4];
+  bool have_words;   // warp-uniform
+};
+
+__device__ __forceinline__ ResetLoads reset_load_warp(const rtd3_mt_bank& b, const double* __restrict__ region, bool active, int64_t i) {
+  ResetLoads r;
+  r.pos = 0; r.left = r.right = r.bottom = r.top = 0.0; r.have_words = false;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r.w[q] = 0u;
+  if (!__any_sync(0xffffffffu, active)) return r;
+  const int64_t n = b.n;
+  if (active) {
+    r.pos = b.pos[i];
+    r.left = region[i]; r.right = region[n + i]; r.bottom = region[2 * n + i]; r.top = region[3 * n + i];
+  }
+  r.have_words = !__any_sync(0xffffffffu, active && r.pos + 4 > RTD3_MT_N);
+  if (r.have_words && active) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.w[q] = mt_temper(b.mt[(int64_t)(r.pos + q) * n + i]);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void reset_finish_warp(const rtd3_mt_bank& b, bool active, int64_t i, ResetLoads& r, float* __restrict__ x,
+                                                  float* __restrict__ y, double* __restrict__ state64) {
   if (!__any_sync(0xffffffffu, active)) return;
   const int64_t n = b.n;
-  const int64_t ii = active ? i : 0;
-  MtStream s{b.mt + ii, n, active ? b.pos[ii] : 0};
-  // lo + (hi - lo) * u with numpy's two roundings; the draws go through the warp-cooperative wrap (see rtd3_mt.cuh)
-  double ux, uy;
-  mt_next_double2_warp(s, active, ux, uy);
+  int pos_after = r.pos + 4;
+  if (!r.have_words) {                               // a stream of this warp wraps: draw word by word through the warp twist
+    int pos = r.pos;
+    mt_next_words4_warp_slow(b.mt + (active ? i : 0), n, &pos, active, r.w);
+    pos_after = pos;
+  }
   if (!active) return;
-  const double sx = __dadd_rn(region[i], __dmul_rn(__dsub_rn(region[n + i], region[i]), ux));                   // x in [left, right)
-  const double sy = __dadd_rn(region[2 * n + i], __dmul_rn(__dsub_rn(region[3 * n + i], region[2 * n + i]), uy));   // y in [bottom, top)
+  // lo + (hi - lo) * u with numpy's two roundings
+  const double ux = mt_double_from_words(r.w[0], r.w[1]), uy = mt_double_from_words(r.w[2], r.w[3]);
+  const double sx = __dadd_rn(r.left, __dmul_rn(__dsub_rn(r.right, r.left), ux));        // x in [left, right)
+  const double sy = __dadd_rn(r.bottom, __dmul_rn(__dsub_rn(r.top, r.bottom), uy));      // y in [bottom, top)
   // float32 rounding must not reach 100.0 (the cell index would leave the map): cap at the largest float below it
   x[i] = fminf((float)sx, 99.99999f); y[i] = fminf((float)sy, 99.99999f);
   if (state64) { state64[i] = sx; state64[n + i] = sy; }
-  b.pos[i] = s.pos;
+  b.pos[i] = pos_after;
+}
+
+__device__ __forceinline__ void reset_env_warp(const rtd3_mt_bank& b, const double* __restrict__ region, bool active, int64_t i,
+                                               float* __restrict__ x, float* __restrict__ y, double* __restrict__ state64) {
+  ResetLoads r = reset_load_warp(b, region, active, i);
+  reset_finish_warp(b, active, i, r, x, y, state64);
 }
 
 }  // namespace rtd3

@@ -117,6 +117,14 @@ __device__ __forceinline__ void mt_regenerate_warp(uint32_t* w, int64_t stride) 
   __syncwarp();
 }
 
+__device__ __forceinline__ uint32_t mt_temper(uint32_t yv) {
+  yv ^= yv >> 11;
+  yv ^= (yv << 7) & 0x9d2c5680u;
+  yv ^= (yv << 15) & 0xefc60000u;
+  yv ^= yv >> 18;
+  return yv;
+}
+
 // next_u32 for a warp whose lanes hold independent streams (lane-private `s`, `active` lanes draw): streams that have to wrap are
 // twisted one after the other by the whole warp.  All 32 lanes must call it.
 __device__ __forceinline__ uint32_t mt_next_u32_warp(MtStream& s, bool active) {
@@ -128,15 +136,7 @@ __device__ __forceinline__ uint32_t mt_next_u32_warp(MtStream& s, bool active) {
     mt_regenerate_warp(reinterpret_cast<uint32_t*>((uintptr_t)wp), s.stride);
     if ((int)(threadIdx.x & 31) == src) s.pos = 0;
   }
-  uint32_t yv = 0;
-  if (active) {
-    yv = s.at(s.pos++);
-    yv ^= yv >> 11;
-    yv ^= (yv << 7) & 0x9d2c5680u;
-    yv ^= (yv << 15) & 0xefc60000u;
-    yv ^= yv >> 18;
-  }
-  return yv;
+  return active ? mt_temper(s.at(s.pos++)) : 0u;
 }
 // K consecutive words per active lane through ONE inlined copy of the twist (the loop is kept rolled: every inlined copy of
 // mt_regenerate_warp costs ~1.5 KB of code and its 20 state registers at the call site)
@@ -149,6 +149,15 @@ __device__ __forceinline__ void mt_next_words_warp(MtStream& s, bool active, uin
     for (int q = 0; q < K; ++q)
       if (q == h) out[q] = t;
   }
+}
+// The same, out of line: for callers whose common path never wraps (reset_finish_warp) and should not carry the twist's registers.
+static __device__ __noinline__ void mt_next_words4_warp_slow(uint32_t* w, int64_t stride, int* pos, bool active, uint32_t* out4) {
+  MtStream s{w, stride, *pos};
+  uint32_t o[4] = {0u, 0u, 0u, 0u};
+  mt_next_words_warp<4>(s, active, o);
+  *pos = s.pos;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out4[q] = o[q];
 }
 __device__ __forceinline__ double mt_double_from_words(uint32_t w0, uint32_t w1) {
   return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;

@@ -123,25 +123,51 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
                                                const ReplayRing& ring, const bool masked_push) {
   const int64_t ii = live ? i : 0;
   const double px = (double)nxi, py = (double)nyi;
+  // Every load this env needs is issued here, before the first dependent use and before any store (the compiler keeps loads
+  // behind earlier stores through pointers it cannot prove distinct): the kernel is a chain of L2 round trips (ncu: long-scoreboard
+  // stalls on the stuck ring, the time-out test and the flags, one after the other), and this makes it one.
+  const double goal_x = st.goal[ii], goal_y = st.goal[n + ii];
+  const bool demo_phase_over = st.demo_flag[ii] != 0;
+  int cnt = st.hist_count[ii], head = st.hist_head[ii];
+  float hx[kStuckSteps], hy[kStuckSteps];
+#pragma unroll
+  for (int k = 0; k < kStuckSteps; ++k) { hx[k] = st.hist[(int64_t)(2 * k) * n + ii]; hy[k] = st.hist[(int64_t)(2 * k + 1) * n + ii]; }
+  const bool timeout = st.plan_index[ii] == st.path_length[ii] - 1;
+  // memory.push (robot.py:675): the row's slot.  With a masked push the stepping envs are compacted by a warp ballot and one
+  // atomic per warp on the ring's row counter - issued now, consumed at the end.
+  int64_t p = 0;
+  if (ring.s) {
+    if (masked_push) {
+      const uint32_t act = __ballot_sync(0xffffffffu, live);
+      const int lane = threadIdx.x & 31;
+      unsigned long long base = 0;
+      if (lane == 0 && act) base = atomicAdd(ring.total, (unsigned long long)__popc(act));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      p = (int64_t)((base + __popc(act & ((1u << lane) - 1u))) % (unsigned long long)ring.capacity);
+    } else {
+      p = (ring.position + i) % ring.capacity;
+      if (i == 0 && ring.total) atomicAdd(ring.total, (unsigned long long)n);
+    }
+  }
   // compute_reward([next_state])  robot.py:741-762
-  const double gd = norm2_np(__dsub_rn(px, st.goal[ii]), __dsub_rn(py, st.goal[n + ii]));
+  const double gd = norm2_np(__dsub_rn(px, goal_x), __dsub_rn(py, goal_y));
   const bool reached = (-gd >= -kGoalRadius);
   // nearest demonstration state (only needed when the goal was not reached, the demo phase is over and there are demos)
   double best = INFINITY;
   if (m > 0 && list_start) {
-    if (live && !reached && st.demo_flag[ii]) best = nearest_demo_sq(px, py, demo, m, list_start, list_pts);
+    if (live && !reached && demo_phase_over) best = nearest_demo_sq(px, py, demo, m, list_start, list_pts);
   } else if (kAllowSweep && m > 0) {
     // (callers that cannot take a block-wide barrier here - a subset of the CTA's warps - instantiate kAllowSweep = false and
     // guarantee lists or m == 0)
     __shared__ double2 tile[512];
     double b0 = INFINITY, b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;      // four independent minimum chains
     for (int64_t base = 0; base < m; base += 512) {
-      const int cnt = (int)min((int64_t)512, m - base);
+      const int cnt_t = (int)min((int64_t)512, m - base);
       __syncthreads();
-      for (int k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = reinterpret_cast<const double2*>(demo)[base + k];
+      for (int k = threadIdx.x; k < cnt_t; k += blockDim.x) tile[k] = reinterpret_cast<const double2*>(demo)[base + k];
       __syncthreads();
       int k = 0;
-      for (; k + 4 <= cnt; k += 4) {
+      for (; k + 4 <= cnt_t; k += 4) {
         const double dx0 = px - tile[k].x, dy0 = py - tile[k].y, dx1 = px - tile[k + 1].x, dy1 = py - tile[k + 1].y;
         const double dx2 = px - tile[k + 2].x, dy2 = py - tile[k + 2].y, dx3 = px - tile[k + 3].x, dy3 = py - tile[k + 3].y;
         b0 = fmin(b0, fma(dy0, dy0, dx0 * dx0));     // squared distance; sqrt once at the end (monotone)
@@ -149,7 +175,7 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
         b2 = fmin(b2, fma(dy2, dy2, dx2 * dx2));
         b3 = fmin(b3, fma(dy3, dy3, dx3 * dx3));
       }
-      for (; k < cnt; ++k) {
+      for (; k < cnt_t; ++k) {
         const double dx = px - tile[k].x, dy = py - tile[k].y;
         b0 = fmin(b0, fma(dy, dy, dx * dx));
       }
@@ -165,19 +191,17 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
     } else if (m == 0) {
       reward = -gd;
     } else {
-      const double prox = st.demo_flag[i] ? -sqrt(best) : 0.0;
+      const double prox = demo_phase_over ? -sqrt(best) : 0.0;
       reward = __dadd_rn(-gd, __dmul_rn(10.0, prox));   // DEMO_PROXIMITY_FACTOR, robot.py:43, 760
     }
     // check_if_stuck(state)  robot.py:509-538, on the pre-step state
     const double cxs = (double)sxi, cys = (double)syi;
-    int cnt = st.hist_count[i], head = st.hist_head[i];
     bool stuck = false;
     if (cnt >= kStuckSteps) {
       stuck = true;
-      for (int k = 0; k < kStuckSteps; ++k) {
-        const double hx = (double)st.hist[(int64_t)(2 * k) * n + i], hy = (double)st.hist[(int64_t)(2 * k + 1) * n + i];
-        if (!(norm2_np(__dsub_rn(cxs, hx), __dsub_rn(cys, hy)) < kStuckThreshold)) stuck = false;
-      }
+#pragma unroll
+      for (int k = 0; k < kStuckSteps; ++k)
+        if (!(norm2_np(__dsub_rn(cxs, (double)hx[k]), __dsub_rn(cys, (double)hy[k])) < kStuckThreshold)) stuck = false;
       if (stuck) { cnt = 0; head = 0; }                 // previous_states.clear()
       else { head = (head + 1) % kStuckSteps; cnt -= 1; }   // pop(0)
     }
@@ -190,26 +214,11 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
       st.stuck_flag[i] = 1;
       reward = __dsub_rn(reward, kStuckPenalty);
     }
-    done = st.plan_index[i] == st.path_length[i] - 1;   // robot.py:672: time-out only
+    done = timeout;                                     // robot.py:672: time-out only
     reward_out[i] = (float)reward;
     if (reward64) reward64[i] = reward;
     done_out[i] = done ? 1 : 0;
-  }
-  if (ring.s) {                                         // memory.push  robot.py:675
-    int64_t p;
-    if (masked_push) {
-      // only some envs push: compact them with a warp ballot, one atomic per warp on the ring's row counter
-      const uint32_t act = __ballot_sync(0xffffffffu, live);
-      const int lane = threadIdx.x & 31;
-      unsigned long long base = 0;
-      if (lane == 0 && act) base = atomicAdd(ring.total, (unsigned long long)__popc(act));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      p = (int64_t)((base + __popc(act & ((1u << lane) - 1u))) % (unsigned long long)ring.capacity);
-    } else {
-      p = (ring.position + i) % ring.capacity;
-      if (i == 0 && ring.total) atomicAdd(ring.total, (unsigned long long)n);
-    }
-    if (live) {
+    if (ring.s) {
       ring.s[p] = make_float2(sxi, syi);
       ring.a[p] = make_float2(axi, ayi);
       ring.r[p] = (float)reward;

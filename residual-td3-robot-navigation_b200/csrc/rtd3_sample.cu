@@ -16,14 +16,6 @@
 
 namespace rtd3 {
 
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
-  y ^= y >> 11;
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  y ^= y >> 18;
-  return y;
-}
-
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
   const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
   return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);

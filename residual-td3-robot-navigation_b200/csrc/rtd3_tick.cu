@@ -56,6 +56,9 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
   const int64_t ii = in ? i : 0;
   const bool live = in && type == 0;
   const float x = t.x[ii], y = t.y[ii];
+  // the 'reset' envs' draws: loads issued now, consumed after the transition work (they do not depend on it)
+  ResetLoads rl = reset_load_warp(t.env_bank, t.region, in && type == 2, i);
+  const int64_t steps_before = (in && type == 0) ? t.steps_bought[i] : 0, resets_before = (in && type == 2) ? t.resets_bought[i] : 0;
   // get_next_action_training: envs that do not step in this tick get a null action (robot-learning.py:82-95)
   float ax = 0.f, ay = 0.f;
   if (live) {
@@ -83,11 +86,11 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
     if (t.prev_x) { t.prev_x[i] = x; t.prev_y[i] = y; }
     t.x[i] = nx;
     t.y[i] = ny;
-    if (type == 0) t.steps_bought[i] += 1;
-    else if (type == 2) t.resets_bought[i] += 1;
+    if (type == 0) t.steps_bought[i] = steps_before + 1;
+    else if (type == 2) t.resets_bought[i] = resets_before + 1;
   }
   // Environment.reset where the tick is a 'reset' (warp-synchronous: wrapping MT19937 streams are twisted by the whole warp)
-  reset_env_warp(t.env_bank, t.region, in && type == 2, i, t.x, t.y, t.state64);
+  reset_finish_warp(t.env_bank, in && type == 2, i, rl, t.x, t.y, t.state64);
 }
 
 __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,

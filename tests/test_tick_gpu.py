@@ -162,13 +162,16 @@ def test_tick_argument_errors(pkg, env_golden):
 def test_multi_tick_kernel_matches_the_three_launch_tick(pkg, env_golden, n, m, hidden):
     """rtd3_tick_run_f16 (check_interval ticks in ONE launch, actor forward inside the kernel) against the fused three-launch tick
     with the same f16 forward: the same device functions run per env in the same order, so every array must be bit-identical.
-    20 000 envs: more tiles than SMs (a CTA runs all ticks of one tile, then of the next); 333: a ragged last tile."""
+    20 000 envs: more tiles than SMs (a CTA runs all ticks of one tile, then of the next; the trainer itself only picks the kernel
+    for a single wave of tiles, so the test forces it); 333: a ragged last tile."""
     snaps = []
     for multi in (False, True):
         env, robot, tr = _build(pkg, env_golden, n, _demo_path(m) if m else None, True, noise="philox", graph=False, check_interval=8,
                                 hidden=hidden, grid_min=64)
         robot.td3_agent.precision = "f16"
         tr.multi_tick_kernel = multi
+        if multi and n > 148 * 128:
+            tr._multi_tick_ok = lambda: True                # force the kernel beyond one wave of tiles
         assert tr._multi_tick_ok() == multi
         before = pkg._lib.launch_count()
         tr.run(8 * 9 + 3)                                   # nine blocks of 8 ticks + three single ticks
