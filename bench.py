@@ -346,7 +346,10 @@ def bench_full_loop(rt, torch, dev, world, rank):
         rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "tick": form, "ticks": ticks, "ms_per_tick": ms / ticks,
                      "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
                      "td3_epochs_per_update": 20, "td3_batch": 256, "replay_rows_per_gpu": len(robot.memory), "demo_states": int(demos.shape[0]),
-                     "note": ("three launches per tick, eight ticks per CUDA graph; noise Philox inside the tick kernel" if fused else
+                     "note": (("eight ticks per launch of the multi-tick kernel rtd3_tick_run_f16 (actor forward inside); noise Philox in the kernel"
+                               if tr._multi_tick_ok() else
+                               "three launches per tick (rtd3_tick_pre / actor forward / rtd3_tick_post), eight ticks per CUDA graph; noise Philox inside the tick kernel")
+                              if fused else
                               "ten launches per tick, one CUDA graph per tick; noise torch.randn")
                              + "; finished-episode counter read every 8 ticks; replay sampling philox"})
         del tr, robot, env

@@ -262,6 +262,22 @@ int32_t rtd3_robot_next_action_type(int32_t* num_episodes, uint8_t* demo_flag, i
 int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Data-parallel learner: gradient all-reduce over NVLink peer memory        (no counterpart in the reference)
+ * ---------------------------------------------------------------------------------------------- */
+#define RTD3_P2P_MAX_WORLD 8
+/* SUM all-reduce of the ranks' flat gradient buffers in ONE launch per optimiser step over peer memory (CUDA IPC mappings across
+ * NVLink / NVSwitch), push model: every rank stores its gradients into slot [step parity][rank] of every rank's receive area,
+ * raises the peers' flags, waits for all flags of the step and adds the `world` slots of its own area in rank order (bit-identical
+ * sums on all ranks).  peer_recv / peer_flags: HOST arrays of `world` DEVICE pointers - rank r's receive area (2 * world * count
+ * floats, 16 B aligned) and flag array (RTD3_P2P_MAX_WORLD uint64, zero-initialised once) as mapped in THIS process.
+ * seq_counter: uint64 [1] in device memory, zero-initialised once; the kernel advances it (the step number is what the flags
+ * carry; every rank must issue the same sequence of calls).  out (count floats, private) receives the sum; local_grads (count
+ * floats, private) is read and cleared.  block_counter: uint32 [1], zero-initialised once.  A rank whose peers do not arrive within
+ * 20 s traps (the launch fails) instead of hanging.  A plain launch: it may be captured in a CUDA graph. */
+int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* seq_counter,
+                           float* out, float* local_grads, int64_t count, uint32_t* block_counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused tick of the batched driver loop        (robot-learning.py:66-101, training branch)
  * ---------------------------------------------------------------------------------------------- */
 /* Everything one tick touches, for n envs.  HOST struct of DEVICE pointers (same arrays as the per-hook entry points above take). */

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),
     "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
     "rtd3_trainer_tally": (c_int32, [_P, _P, _P, c_int64, _P]),
+    "rtd3_p2p_allreduce": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P]),
     "rtd3_tick_pre": (c_int32, [POINTER(TickStateStruct), _P]),
     "rtd3_tick_post": (c_int32, [_P, POINTER(TickStateStruct), _P, _P, c_int32, _P]),
     "rtd3_tick_run_f16": (c_int32, [_P, POINTER(TickStateStruct), c_int32, c_int32, _P, _P, c_int32, c_int64, c_uint64, _P]),

@@ -1,0 +1,139 @@
+// Gradient all-reduce of the data-parallel learner over NVLink peer memory (the one collective of the path).
+// Every rank owns a receive area its peers have mapped (CUDA IPC): recv[2][W][count] floats + a flag array.  One launch per
+// optimiser step, PUSH model - remote stores are fire-and-forget, remote loads are round trips:
+//   (1) every block copies its slice of the local gradient buffer into slot [step parity][rank] of EVERY rank's receive area
+//       (its own included) and clears the local slice for the next step;
+//   (2) the last block to finish (system-scope fences, a block counter) stores the step number into the peers' flag arrays;
+//   (3) every block waits until all W flags show this step, then adds the W slots of its own receive area in rank order - the
+//       same order on every rank, so the replicas stay bit-identical - into the private buffer the optimiser kernel consumes.
+// The two parities make a second barrier unnecessary: a rank overwrites slot [p] two steps later, after it has seen the flags of the
+// step in between, which every peer raises only after it has finished reading slot [p].
+// The step number lives in device memory and is advanced by the kernel, so a replayed CUDA graph counts on by itself; a rank whose
+// peers do not arrive within kSpinLimitNs traps instead of hanging.  (A pull version - flags, then loads from the peers' gradient
+// buffers, then a second barrier before they may be overwritten - took as long as the NCCL call it replaced: three serialised
+// NVLink round trips.)
+#include <algorithm>
+
+#include "rtd3_common.cuh"
+
+namespace rtd3 {
+
+constexpr int kP2pMaxWorld = RTD3_P2P_MAX_WORLD;
+constexpr unsigned long long kSpinLimitNs = 20ull * 1000 * 1000 * 1000;
+
+struct P2pPeers {
+  float* recv[kP2pMaxWorld];                 // rank q's receive area as mapped here: [2][W][count] floats
+  unsigned long long* flags[kP2pMaxWorld];   // rank q's flag array: flags[r] = last step rank r has pushed completely
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
+  if (ld_acquire_sys(p) >= seq) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(p) < seq)
+    if (global_ns() - t0 > kSpinLimitNs) asm volatile("trap;");
+}
+__device__ __forceinline__ float4 ld_fresh(const float4* p) {   // written by a peer during this launch: not from a stale line
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <int kWorld>
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter, float* __restrict__ out,
+                                                            float* __restrict__ local_grads, int64_t count4, unsigned int* block_counter) {
+  __shared__ bool s_last;
+  __shared__ unsigned long long s_seq;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_seq = *reinterpret_cast<volatile unsigned long long*>(seq_counter) + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int64_t slot = ((int64_t)(seq & 1ull) * kWorld + rank) * count4;      // [parity][rank] in every receive area
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // (1) push (the kernels that produced local_grads precede this one in stream order)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < count4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(local_grads)[i];
+#pragma unroll
+    for (int q = 0; q < kWorld; ++q) reinterpret_cast<float4*>(peers.recv[q])[slot + i] = v;
+    reinterpret_cast<float4*>(local_grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // (2) the last block of this rank raises the flags
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(block_counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (tid < kWorld) {
+      __threadfence_system();
+      st_release_sys(peers.flags[tid] + rank, seq);
+    }
+    if (tid == 0) {
+      *block_counter = 0u;                             // every block of this launch has passed the counter ...
+      *seq_counter = seq;                              // ... and has read the step number
+    }
+  }
+  // (3) all W gradients of this step have landed here: add them in rank order
+  if (tid < kWorld) wait_flag(peers.flags[rank] + tid, seq);
+  __syncthreads();
+  const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * count4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < count4; i += stride) {
+    float4 v[kWorld];
+#pragma unroll
+    for (int r = 0; r < kWorld; ++r) v[r] = ld_fresh(mine + (int64_t)r * count4 + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < kWorld; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
+}  // namespace rtd3
+
+using namespace rtd3;
+
+extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* seq_counter,
+                                      float* out, float* local_grads, int64_t count, uint32_t* block_counter, void* stream) {
+  RTD3_CHECK_ARG(peer_recv && peer_flags && out && local_grads && block_counter && seq_counter, "null argument");
+  RTD3_CHECK_ARG(world >= 2 && world <= kP2pMaxWorld && rank >= 0 && rank < world, "bad rank / world");
+  RTD3_CHECK_ARG(count > 0 && count % 4 == 0, "count must be a positive multiple of 4");
+  P2pPeers p{};
+  for (int r = 0; r < world; ++r) {
+    RTD3_CHECK_ARG(peer_recv[r] && peer_flags[r], "null peer pointer");
+    RTD3_CHECK_ARG((uintptr_t)peer_recv[r] % 16 == 0 && (uintptr_t)peer_flags[r] % 8 == 0, "misaligned peer pointer");
+    p.recv[r] = peer_recv[r];
+    p.flags[r] = (unsigned long long*)peer_flags[r];
+  }
+  // all blocks spin on flags, so the grid must be co-resident: at most 4 CTAs of 256 threads per SM; one float4 per thread where
+  // the buffer allows it (0.8 MB at 2 x 256 = 200 CTAs)
+  const int64_t count4 = count / 4;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    RTD3_CUDA(cudaGetDevice(&dev));
+    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = (int)std::min<int64_t>(4 * (int64_t)num_sms, ceil_div(count4, 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* sc = (unsigned long long*)seq_counter;
+  switch (world) {
+#define RTD3_P2P_CASE(W) case W: p2p_allreduce_kernel<W><<<grid, 256, 0, st>>>(p, rank, sc, out, local_grads, count4, block_counter); break;
+    RTD3_P2P_CASE(2) RTD3_P2P_CASE(3) RTD3_P2P_CASE(4) RTD3_P2P_CASE(5) RTD3_P2P_CASE(6) RTD3_P2P_CASE(7) RTD3_P2P_CASE(8)
+#undef RTD3_P2P_CASE
+  }
+  RTD3_LAUNCHED();
+  return 0;
+}

@@ -285,7 +285,7 @@ class TD3:
 
     def __init__(self, actor_network, critic_network_1, critic_network_2, actor_lr=ACTOR_LR, critic_lr=CRITIC_LR, gamma=GAMMA,
                  tau=TAU, policy_noise=TARGET_POLICY_NOISE, noise_clip=NOISE_CLIP, policy_update_delay=POLICY_UPDATE_DELAY,
-                 num_epochs=TD3_EPOCHS, batch_size=TD3_BATCH_SIZE, device=None, process_group=None):
+                 num_epochs=TD3_EPOCHS, batch_size=TD3_BATCH_SIZE, device=None, process_group=None, dp_collective=None):
         self.device = _device(device)
         self.hidden, self.layers = actor_network.hidden, actor_network.layers
         for net in (critic_network_1, critic_network_2):
@@ -343,10 +343,51 @@ class TD3:
         self._side_stream = None
         self.sample_chunk_epochs = 10       # epochs per pipelined chunk of td3_update (0 = draw all index sets up front)
         self._graphs = {}
+        self._p2p = None
         if self.world > 1:                  # initialise the communicator outside of any graph capture
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=process_group)
             self.grads.zero_()
+            import os
+            dp_collective = dp_collective or os.environ.get("RTD3_DP_COLLECTIVE", "nccl")
+            self.dp_collective = dp_collective
+            if dp_collective == "p2p":
+                self._setup_p2p()
+            elif dp_collective != "nccl":
+                raise ValueError("dp_collective must be 'nccl' or 'p2p'")
+
+    def _setup_p2p(self):
+        """Gradient all-reduce over NVLink peer memory (`rtd3_p2p_allreduce`): a receive area + flag array per rank that every
+        peer maps through CUDA IPC (the handles travel once over the process group); the step kernels keep writing `self.grads`,
+        the optimiser kernel consumes the private sum `self._grads_sum`."""
+        import ctypes
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        pg, world = self.process_group, self.world
+        rank = dist.get_rank(pg)
+        if world > 8:
+            raise ValueError("the peer-memory all-reduce serves up to 8 ranks (one NVSwitch box)")
+        G = self.grads.numel()
+        buf = torch.zeros((2 * world * G + 32,), dtype=torch.float32, device=self.device)   # receive slots [2][world][G] | flags
+        torch.cuda.synchronize(self.device)
+        handles = [None] * world
+        dist.all_gather_object(handles, reduce_tensor(buf), group=pg)
+        peers = []
+        for q in range(world):
+            if q == rank:
+                peers.append(buf)
+                continue
+            fn, args = handles[q]
+            args = list(args)
+            args[6] = self.device.index                 # open the peer's handle in THIS device's context: a P2P mapping
+            peers.append(fn(*args))
+        self._grads_sum = torch.zeros((G,), dtype=torch.float32, device=self.device)
+        c = ctypes.c_void_p * world
+        self._p2p = {"peers": peers, "rank": rank, "seq": torch.zeros((1,), dtype=torch.int64, device=self.device), "count": G,
+                     "recv": c(*[t.data_ptr() for t in peers]), "flags": c(*[t.data_ptr() + 4 * 2 * world * G for t in peers]),
+                     "counter": torch.zeros((1,), dtype=torch.int32, device=self.device)}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=pg)                          # every rank has mapped every buffer before the first launch
 
     def __del__(self):
         try:
@@ -443,6 +484,12 @@ class TD3:
 
     # ---- the three device steps -------------------------------------------------------------------------
     def _allreduce(self):
+        if self._p2p is not None:
+            p = self._p2p
+            _lib.check(_lib.lib().rtd3_p2p_allreduce(p["recv"], p["flags"], p["rank"], self.world, _lib.ptr(p["seq"]), _lib.ptr(self._grads_sum),
+                                                     _lib.ptr(self.grads), p["count"], _lib.ptr(p["counter"]), _lib.stream_ptr(self.device)),
+                       "p2p_allreduce")
+            return
         if self.world > 1:
             from .trainer import allreduce_grads_
             allreduce_grads_(self.grads, self.process_group)
@@ -498,7 +545,8 @@ class TD3:
             self._u_stale = True
         self._h_stale = True
         _lib.check(_lib.lib().rtd3_td3_adam_polyak(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t),
-                                                   _lib.ptr(self.params_u if keep_uv else None), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+                                                   _lib.ptr(self.params_u if keep_uv else None),
+                                                   _lib.ptr(self._grads_sum if self._p2p is not None else self.grads), _lib.ptr(self.adam_m),
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
 
@@ -610,8 +658,9 @@ class TD3:
         if tf32:
             self._sync_chunk_major()         # current before the loop; every optimiser step inside keeps it in step
         try:
-            # NCCL collectives are issued eagerly between the kernels: the data-parallel loop is not graph-captured
-            if use_graph and self.world == 1:
+            # NCCL collectives are issued eagerly between the kernels: that data-parallel loop is not graph-captured.  The
+            # peer-memory all-reduce is a plain launch (its step counter lives in device memory) and is captured with the rest.
+            if use_graph and (self.world == 1 or self._p2p is not None):
                 if st["graph"] is None:
                     graph = torch.cuda.CUDAGraph()
                     before = _lib.launch_count()

@@ -57,7 +57,8 @@ def _planes(t, n):
 
 
 class Robot:
-    def __init__(self, goal_state, hidden=None, layers=None, device=None, seed=None, process_group=None, buffer_size=BUFFER_SIZE):
+    def __init__(self, goal_state, hidden=None, layers=None, device=None, seed=None, process_group=None, buffer_size=BUFFER_SIZE,
+                 dp_collective=None):
         if not torch.cuda.is_available():
             raise RuntimeError("Robot needs a CUDA device (B200); there is no CPU path")
         self.batched = isinstance(goal_state, torch.Tensor)
@@ -110,7 +111,8 @@ class Robot:
         if hidden is not None:
             kw = {"hidden": hidden, "layers": layers if layers is not None else 3}
         self.td3_agent = TD3(actor_network=Residual_Actor_Network(**kw), critic_network_1=Residual_Critic_Network(**kw),
-                             critic_network_2=Residual_Critic_Network(**kw), device=dev, process_group=process_group)
+                             critic_network_2=Residual_Critic_Network(**kw), device=dev, process_group=process_group,
+                             dp_collective=dp_collective)
         self.num_updates = 0
         # One shared learner serves all envs: an update runs once `episodes_per_update` env-episodes have ended since the last
         # one.  The default N keeps the reference's rhythm (every env finishes about one episode between updates) and is
