@@ -245,6 +245,7 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         ms_sample, ms_update, ms_call = float(t[0]), float(t[1]), float(t[2])
         flops = td3_flops_per_epoch(B * world, H, L) * epochs
         row = {"shape": label, "global_batch": B * world, "epochs": epochs, "sampler": rb.sampler,
+               "dp_collective": getattr(agent, "dp_collective", None) if world > 1 else None,
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
                "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
                "updates_per_sec_update_only": epochs / (ms_update * 1e-3),

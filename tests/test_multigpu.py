@@ -18,3 +18,14 @@ def test_data_parallel_learner_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=170)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "-> OK" in out.stdout
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.timeout(180)
+def test_data_parallel_learner_two_gpus_peer_memory_allreduce():
+    """The same check with the gradient all-reduce over NVLink peer memory (rtd3_p2p_allreduce) inside the update's CUDA graph."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=170, env=dict(os.environ, RTD3_DP_COLLECTIVE="p2p"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "-> OK" in out.stdout
