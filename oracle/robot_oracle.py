@@ -95,3 +95,39 @@ class RobotOracle:
         else:
             self.plan_index += 1
         return action_type
+
+
+# ---- the candidate-list rule of the nearest-demonstration search (csrc/rtd3_robot.cu: demo_lists_kernel), restated -------------
+# robot.py:753 takes cdist(next_state, demonstration_states).min() over ALL states.  The device evaluates, for a query in the
+# 1 x 1 cell c, only the states of c's candidate list.  The rule that builds the lists is restated here so that its claim - the
+# minimum over the list equals the minimum over all states, for every point of the cell - can be checked on the CPU against the
+# reference's own expression.
+def demo_candidate_lists(points, grid=100, cell=1.0, keep=1.0 + 1e-9):
+    """Per cell (x-major index cx * grid + cy): indices of the states kept.  A state p is dropped when, for one of five anchor
+    states p* (the states nearest to the cell's four corners and to its centre), p* is closer than p at ALL four corners:
+    |q-p|^2 - |q-p*|^2 is linear in q, so p* is then closer everywhere in the (convex) cell."""
+    P = np.asarray(points, dtype=np.float64)
+    lists = []
+    for cx in range(grid):
+        x0, x1 = cx * cell, (cx + 1) * cell
+        dx0, dx1 = (x0 - P[:, 0]) ** 2, (x1 - P[:, 0]) ** 2
+        for cy in range(grid):
+            y0, y1 = cy * cell, (cy + 1) * cell
+            dy0, dy1 = (y0 - P[:, 1]) ** 2, (y1 - P[:, 1]) ** 2
+            d = np.stack([dx0 + dy0, dx0 + dy1, dx1 + dy0, dx1 + dy1])                  # [4 corners, M]
+            dc = (x0 + 0.5 * cell - P[:, 0]) ** 2 + (y0 + 0.5 * cell - P[:, 1]) ** 2
+            stars = [int(np.argmin(d[k])) for k in range(4)] + [int(np.argmin(dc))]
+            ok = np.ones(P.shape[0], dtype=bool)
+            for st in stars:
+                ok &= (d <= d[:, st:st + 1] * keep).any(axis=0)
+            lists.append(np.nonzero(ok)[0])
+    return lists
+
+
+def nearest_demo_distance(query, points, lists=None, grid=100, cell=1.0):
+    """min_j ||query - points[j]|| as robot.py:753 evaluates it (float64), over the query's candidate list when `lists` is given."""
+    P = np.asarray(points, dtype=np.float64)
+    q = np.asarray(query, dtype=np.float64)
+    if lists is not None and 0 <= q[0] < grid * cell and 0 <= q[1] < grid * cell:
+        P = P[lists[int(q[0] / cell) * grid + int(q[1] / cell)]]
+    return np.sqrt(((P - q) ** 2).sum(axis=1)).min()

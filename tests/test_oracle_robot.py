@@ -49,3 +49,27 @@ def test_state_machine(robot_golden):
         assert r.current_noise_scale == g["sm_noise"][t]
     assert r.updates == int(g["sm_updates"])
     assert list(g["sm_types"][:5]) == [1, 1, 1, 2, 0]       # exactly three demos are bought, then a reset (SURVEY a-11)
+
+
+def test_candidate_lists_contain_the_nearest_state_for_every_query():
+    """The rule behind rtd3_demo_lists (restated in the oracle): a state that another state beats at all four corners of a cell
+    cannot be nearest inside it.  Checked against the reference's expression - the min over ALL states (robot.py:753) - on a
+    clustered path with augmentation-like noise (some states outside the world) plus uniform states, for queries that include every
+    cell corner, cell edges and random interior points."""
+    from oracle.robot_oracle import demo_candidate_lists, nearest_demo_distance
+    rs = np.random.RandomState(0)
+    t = np.linspace(0, 1, 500)[:, None]
+    pts = np.concatenate([np.array([[5.0, 80.0]]) * (1 - t) + np.array([[90.0, 15.0]]) * t + rs.normal(0, 2.5, (500, 2)),
+                          rs.uniform(-3, 103, (200, 2))])
+    grid = 40                                              # a 40 x 40 corner of the world keeps the pure-numpy build short
+    lists = demo_candidate_lists(pts, grid=grid)
+    sizes = np.array([len(l) for l in lists])
+    assert sizes.min() >= 1 and sizes.mean() < 12
+    gx, gy = np.meshgrid(np.arange(grid, dtype=np.float64), np.arange(grid, dtype=np.float64), indexing="ij")
+    queries = np.concatenate([np.stack([gx.ravel(), gy.ravel()], 1),                                   # cell corners
+                              np.stack([gx.ravel() + 0.5, gy.ravel()], 1),                             # edge midpoints
+                              rs.uniform(0, grid, (3000, 2)),
+                              np.float32(rs.uniform(0, grid, (1000, 2))).astype(np.float64)])          # float32 states, as on the device
+    queries = queries[(queries < grid).all(axis=1)]
+    for q in queries:
+        assert nearest_demo_distance(q, pts, lists, grid=grid) == nearest_demo_distance(q, pts)          # bit-identical float64
