@@ -131,7 +131,9 @@ def run_reference(args):
     if rank != 0:
         return
     procs = os.cpu_count() or 1
-    t_sample = 8                                       # 4096 envs x 8 steps per bench step (bounded sample)
+    # 4096 envs x 48 of the 1000 rollout steps per bench step: a bounded sample (~0.12 s on 16 cores, 25 s for the default 200
+    # steps) long enough that the workers' per-job set-up does not count against the reference (with 8 steps it halved its rate)
+    t_sample = 48
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
         for _ in range(args.warmup):
