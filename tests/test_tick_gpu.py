@@ -184,3 +184,21 @@ def test_multi_tick_kernel_matches_the_three_launch_tick(pkg, env_golden, n, m, 
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert rows_a == rows_b and rows_a > 0 and np.array_equal(tab_a, tab_b)
+
+
+def test_philox_noise_matches_the_oracle(pkg, env_golden):
+    """The normals generated inside rtd3_tick_post against oracle/philox.py (pinned to Philox4x32-10 by the Random123 known-answer
+    vectors): with a zero baseline, a zero residual and noise_scale * 5 == 1 the action IS the clipped normal of (seed, tick 1, env)."""
+    from oracle.philox import normal2
+    n = 4096
+    env, robot, tr = _build(pkg, env_golden, n, None, True, noise="philox")
+    tr.philox_seed = 0x123456789A                            # both key words in use
+    robot._num_episodes.fill_(10)
+    robot._demo_flag.fill_(1)
+    robot._noise_scale.fill_(0.2)
+    robot.td3_agent.actor_network.load_flat(np.zeros(robot.td3_agent.actor_network.count(), np.float32))
+    robot._goal.copy_(env._state.double())
+    tr.tick()
+    got = robot._action.cpu().numpy()                        # [2, n]
+    want = np.array([normal2(0x123456789A, 1, e) for e in range(n)]).T
+    np.testing.assert_allclose(got, np.clip(want, -5, 5).astype(np.float32), rtol=1e-6, atol=1e-7)
