@@ -80,3 +80,25 @@ def test_tick_state_struct_layout_matches_the_header(pkg, tmp_path):
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert got == [getattr(T, k).offset for k in names] + [ctypes.sizeof(T)]
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu(pkg):
+    """Argument checks of the fused-tick / candidate-list / f16-forward / peer-memory entry points run before any launch."""
+    L, lib = pkg._lib.lib(), pkg._lib
+    t = lib.TickStateStruct()
+    assert L.rtd3_tick_pre(None, None) == -1
+    assert L.rtd3_tick_pre(ctypes.byref(t), None) == -1 and b"null" in L.rtd3_last_error()           # every pointer of the struct is NULL
+    assert L.rtd3_tick_post(None, ctypes.byref(t), None, None, 0, None) == -1
+    assert L.rtd3_tick_run_f16(None, ctypes.byref(t), 256, 2, None, None, 0, 8, 0, None) == -1
+    assert L.rtd3_demo_lists(None, 10, None, None, None, None) == -1
+    one = ctypes.c_double(0.0)
+    assert L.rtd3_demo_lists(ctypes.byref(one), 0, None, None, None, None) == -1                        # an empty set has no lists
+    assert L.rtd3_demo_lists(ctypes.byref(one), 5, None, None, None, None) == -1                        # count pass without counts
+    assert L.rtd3_mlp_forward_f16(200, 2, 0, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 128, None) == -1
+    assert L.rtd3_mlp_forward_f16(256, 3, 0, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 128, None) == -1
+    assert L.rtd3_mlp_forward_f16(256, 2, 6, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 128, None) == -1
+    ptrs = (ctypes.c_void_p * 2)(0, 0)
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 1, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # world 1
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 9, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # world 9
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 6, ctypes.byref(one), None) == -1    # count % 4
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # null peers
