@@ -190,8 +190,9 @@ class BatchedTrainer:
                 done += K
                 self.robot.maybe_update()
             elif self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
+                self.robot.td3_agent.prepare_forward(self.n)
+                self._check_graphs()
                 if self._graph_k is None:
-                    self.robot.td3_agent.prepare_forward(self.n)
                     self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
                     g = torch.cuda.CUDAGraph()
                     before = _launches()
@@ -210,10 +211,21 @@ class BatchedTrainer:
                 self.tick()
                 done += 1
 
+    def _check_graphs(self):
+        """A captured tick holds the device pointers of the demonstration set and the choice of forward kernel: drop the graphs
+        when either has changed since the capture (`set_demonstration_states`, `process_demonstration`, `precision`)."""
+        robot, agent = self.robot, self.robot.td3_agent
+        p = lambda t: None if t is None else t.data_ptr()
+        sig = (p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list), agent.precision, p(agent.params_u), p(agent.params_h))
+        if sig != getattr(self, "_graph_sig", None):
+            self._graph = self._graph_k = None
+            self._graph_sig = sig
+
     def tick(self):
         if self._use_graph:
+            self.robot.td3_agent.prepare_forward(self.n)      # (allocates the operand copies the signature below looks at)
+            self._check_graphs()
             if self._graph is None:
-                self.robot.td3_agent.prepare_forward(self.n)
                 self.robot.td3_agent._row_scratch(self.robot.td3_agent.batch_size)
                 g = torch.cuda.CUDAGraph()
                 before = _launches()

@@ -202,3 +202,22 @@ def test_philox_noise_matches_the_oracle(pkg, env_golden):
     got = robot._action.cpu().numpy()                        # [2, n]
     want = np.array([normal2(0x123456789A, 1, e) for e in range(n)]).T
     np.testing.assert_allclose(got, np.clip(want, -5, 5).astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_captured_ticks_follow_a_replaced_demonstration_set(pkg, env_golden, multi):
+    """A captured tick holds the device pointers of the demonstration set: after `set_demonstration_states` the graphs must be
+    re-captured (single-tick graph via tick(), eight-tick graph via run()) - compared with eager fused ticks."""
+    snaps = []
+    for graph in (False, True):
+        env, robot, tr = _build(pkg, env_golden, 512, _demo_path(300), True, noise="philox", graph=graph, check_interval=4)
+        tr.multi_tick_kernel = False
+        advance = tr.run if multi else (lambda k: [tr.tick() for _ in range(k)])
+        advance(60)
+        robot.set_demonstration_states(_demo_path(900, seed=3) + np.array([[10.0, -20.0]]))
+        advance(60)
+        snaps.append(_snapshot(env, robot, tr))
+    (a, rows_a, tab_a), (b, rows_b, tab_b) = snaps
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert rows_a == rows_b and np.array_equal(tab_a, tab_b)
