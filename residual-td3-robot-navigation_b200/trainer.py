@@ -216,7 +216,11 @@ class BatchedTrainer:
         when either has changed since the capture (`set_demonstration_states`, `process_demonstration`, `precision`)."""
         robot, agent = self.robot, self.robot.td3_agent
         p = lambda t: None if t is None else t.data_ptr()
-        sig = (p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list), agent.precision, p(agent.params_u), p(agent.params_h))
+        # of the operand copies only the one this precision's forward reads (the learner allocates `params_u` at its first
+        # tensor-core-mode update: with it in the signature the f16 tick was re-captured - a gc.collect() and 24 launches - right
+        # after the first update, inside whatever was being timed)
+        fwd = p(agent.params_h) if agent._f16_ok(self.n) else (p(agent.params_u) if agent._tc_ok(self.n) else None)
+        sig = (p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list), agent.precision, fwd)
         if sig != getattr(self, "_graph_sig", None):
             self._graph = self._graph_k = None
             self._graph_sig = sig
