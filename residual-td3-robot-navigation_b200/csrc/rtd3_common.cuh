@@ -14,6 +14,10 @@ namespace rtd3 {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Per-device caches (rtd3_runtime.cu): function attributes and SM counts belong to a device, so they are keyed by the CURRENT
+// device and guarded by a mutex (a process may drive several GPUs from several host threads).
+cudaError_t ensure_dyn_smem(const void* kernel, size_t bytes);   // cudaFuncAttributeMaxDynamicSharedMemorySize >= bytes on this device
+cudaError_t current_num_sms(int* out);                           // multiprocessor count of the current device
 
 #define RTD3_CHECK_ARG(cond, msg)                                   \
   do {                                                              \

@@ -120,12 +120,8 @@ extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* 
   // all blocks spin on flags, so the grid must be co-resident: at most 4 CTAs of 256 threads per SM; one float4 per thread where
   // the buffer allows it (0.8 MB at 2 x 256 = 200 CTAs)
   const int64_t count4 = count / 4;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    RTD3_CUDA(cudaGetDevice(&dev));
-    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  RTD3_CUDA(current_num_sms(&num_sms));
   const int grid = (int)std::min<int64_t>(4 * (int64_t)num_sms, ceil_div(count4, 256));
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* sc = (unsigned long long*)seq_counter;

@@ -2,6 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "rtd3_common.cuh"
 
@@ -16,6 +19,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::mutex g_dev_mutex;
+static std::map<std::pair<const void*, int>, size_t> g_smem_attr;   // (kernel, device) -> bytes already granted
+static std::map<int, int> g_num_sms;
+
+cudaError_t ensure_dyn_smem(const void* kernel, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  size_t& have = g_smem_attr[std::make_pair(kernel, dev)];
+  if (bytes <= have) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
+cudaError_t current_num_sms(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  auto it = g_num_sms.find(dev);
+  if (it == g_num_sms.end()) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    it = g_num_sms.emplace(dev, n).first;
+  }
+  *out = it->second;
+  return cudaSuccess;
+}
 }  // namespace rtd3
 
 extern "C" {

@@ -244,11 +244,7 @@ extern "C" int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t
   RTD3_CHECK_ARG(n <= 56000, "replay sizes above 56000 rows are not supported by the exact sampler");
   if (count == 0) return 0;
   RTD3_CHECK_ARG(scratch, "scratch (count * n int32) is required");
-  static bool attr_set = false;
-  if (!attr_set) {
-    RTD3_CUDA(cudaFuncSetAttribute(sample_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56000 * 4));
-    attr_set = true;
-  }
+  RTD3_CUDA(ensure_dyn_smem((const void*)sample_trace_kernel, 56000 * 4));
   cudaStream_t st = (cudaStream_t)stream;
   sample_swaps_kernel<<<1, kSampleThreads, 0, st>>>(*bank, stream_id, n, count, scratch);
   RTD3_LAUNCHED();

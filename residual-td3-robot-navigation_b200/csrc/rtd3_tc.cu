@@ -345,19 +345,11 @@ int32_t rtd3_mlp_forward_tf32(int32_t hidden, int32_t layers, int32_t is_actor, 
   if (batch == 0) return 0;
   const NetShape s = is_actor ? NetShape{2, hidden, layers, 2} : NetShape{4, hidden, layers, 1};
   const size_t smem = tc_smem_bytes(hidden, layers);
-  static size_t attr = 0;
-  if (smem > attr) {
-    RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  RTD3_CUDA(ensure_dyn_smem((const void*)mlp_forward_tc_kernel, smem));
   // persistent: one CTA per SM (193 KB of shared memory each) walking its tiles; setup and TMEM allocation happen once per CTA
   const int tiles = (int)ceil_div(batch, kTcRows);
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    RTD3_CUDA(cudaGetDevice(&dev));
-    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  RTD3_CUDA(current_num_sms(&num_sms));
   const int grid = tiles < num_sms ? tiles : num_sms;
   mlp_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(s, params + param_off, params_u + param_off, x, y, (int)batch);
   RTD3_LAUNCHED();
@@ -386,18 +378,10 @@ int32_t rtd3_mlp_forward_f16(int32_t hidden, int32_t layers, int32_t net, const 
   const int64_t param_off = ar.off(net);
   const uint16_t* wh = params_h + (int64_t)net * (layers - 1) * hidden * hidden;
   const size_t smem = hf_smem_bytes(hidden);
-  static size_t attr = 0;
-  if (smem > attr) {
-    RTD3_CUDA(cudaFuncSetAttribute(mlp_forward_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  RTD3_CUDA(ensure_dyn_smem((const void*)mlp_forward_f16_kernel, smem));
   const int tiles = (int)ceil_div(batch, kHfRows);
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    RTD3_CUDA(cudaGetDevice(&dev));
-    RTD3_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  RTD3_CUDA(current_num_sms(&num_sms));
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)hidden) cols <<= 1;      // two accumulator buffers, a power of two of TMEM columns
   const int grid = tiles < num_sms ? tiles : num_sms;

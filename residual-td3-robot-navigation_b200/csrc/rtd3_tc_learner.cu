@@ -868,13 +868,12 @@ int32_t rtd3_td3_critic_step_tf32(rtd3_td3* h, const float* params, const float*
   Td3Hyper hp{gamma, policy_noise, noise_clip, max_action};
   const int grid = (batch + kLtRows - 1) / kLtRows;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr128 = false, attr256 = false;
   if (H == 128) {
-    if (!attr128) { RTD3_CUDA(lt_set_smem(td3_critic_tc_kernel<128>, Lt<128>::kBytes)); attr128 = true; }
+    RTD3_CUDA(ensure_dyn_smem((const void*)td3_critic_tc_kernel<128>, Lt<128>::kBytes));
     td3_critic_tc_kernel<128><<<grid, kLtThreads, Lt<128>::kBytes, st>>>(h->ar, params, params_uv, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out,
                                                                           steps, beta_pows, maps);
   } else {
-    if (!attr256) { RTD3_CUDA(lt_set_smem(td3_critic_tc_kernel<256>, Lt<256>::kBytes)); attr256 = true; }
+    RTD3_CUDA(ensure_dyn_smem((const void*)td3_critic_tc_kernel<256>, Lt<256>::kBytes));
     td3_critic_tc_kernel<256><<<grid, kLtThreads, Lt<256>::kBytes, st>>>(h->ar, params, params_uv, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out,
                                                                           steps, beta_pows, maps);
   }
@@ -896,12 +895,11 @@ int32_t rtd3_td3_actor_step_tf32(rtd3_td3* h, const float* params, const float* 
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
   const int grid = (batch + kLtRows - 1) / kLtRows;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr128 = false, attr256 = false;
   if (H == 128) {
-    if (!attr128) { RTD3_CUDA(lt_set_smem(td3_actor_tc_kernel<128>, Lt<128>::kBytes)); attr128 = true; }
+    RTD3_CUDA(ensure_dyn_smem((const void*)td3_actor_tc_kernel<128>, Lt<128>::kBytes));
     td3_actor_tc_kernel<128><<<grid, kLtThreads, Lt<128>::kBytes, st>>>(h->ar, params, params_uv, grads, rp, idx, batch, loss1, steps, beta_pows, maps);
   } else {
-    if (!attr256) { RTD3_CUDA(lt_set_smem(td3_actor_tc_kernel<256>, Lt<256>::kBytes)); attr256 = true; }
+    RTD3_CUDA(ensure_dyn_smem((const void*)td3_actor_tc_kernel<256>, Lt<256>::kBytes));
     td3_actor_tc_kernel<256><<<grid, kLtThreads, Lt<256>::kBytes, st>>>(h->ar, params, params_uv, grads, rp, idx, batch, loss1, steps, beta_pows, maps);
   }
   RTD3_LAUNCHED();

@@ -241,14 +241,13 @@ int32_t rtd3_tick_run_f16(rtd3_env* h, const rtd3_tick_state* t, int32_t hidden,
   RTD3_CHECK_ARG(noise_mode == RTD3_TICK_NOISE_NONE || noise_mode == RTD3_TICK_NOISE_PHILOX, "noise must be none or philox");
   RTD3_CHECK_ARG(t->num_demo == 0 || t->demo_list_start, "needs candidate lists (rtd3_demo_lists) or no demonstration states");
   RTD3_CHECK_ARG(ticks >= 0 && ticks < (1ll << 30), "bad tick count");
+  // CTAs run their ticks without a grid-wide barrier, so two CTAs can be up to `ticks` ticks apart: the rows they reserve through
+  // the ring counter must not alias, i.e. everything one launch can push has to fit in the ring.
+  RTD3_CHECK_ARG(ticks * t->n <= t->capacity, "replay ring smaller than ticks * n rows: CTAs of a multi-tick launch could overwrite each other's rows");
   if (t->n == 0 || ticks == 0) return 0;
   const NetShape s{2, hidden, layers, 2};
   const size_t smem = hf_smem_bytes(hidden) + kHfRows * sizeof(float2);
-  static size_t attr = 0;
-  if (smem > attr) {
-    RTD3_CUDA(cudaFuncSetAttribute(tick_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  RTD3_CUDA(ensure_dyn_smem((const void*)tick_f16_kernel, smem));
   uint32_t cols = 32;
   while (cols < (uint32_t)hidden) cols <<= 1;
   const int64_t tiles = ceil_div(t->n, kHfRows);

@@ -57,6 +57,7 @@ class Environment:
         _lib.check(_lib.lib().rtd3_env_create(_lib.ctypes.byref(self._handle), self.device.index or 0), "env_create")
         self._state = torch.zeros((2, n), dtype=torch.float32, device=self.device)        # x plane, y plane
         self._state64 = torch.zeros((2, n), dtype=torch.float64, device=self.device)      # last reset draw (float64)
+        self._state_np = None                                                             # single env: cached host copy of the state
         self._goal = torch.zeros((2, n), dtype=torch.float64, device=self.device)
         self._region = torch.zeros((4, n), dtype=torch.float64, device=self.device)       # left,right,bottom,top
         self._bank = MtBank(n, self.device)
@@ -93,8 +94,13 @@ class Environment:
     # ---- reference attributes -----------------------------------------------------------------------
     @property
     def robot_state(self):
+        """Single env: a float64 numpy `[2]` array, the SAME object until the state next changes (the reference returns
+        `self.robot_state` itself from `step`, environment.py:127, so `env.step(a) is env.robot_state`).  Batched: the `[N,2]`
+        view of the device planes."""
         if self.num_envs == 1:
-            return self._state[:, 0].double().cpu().numpy()
+            if self._state_np is None:
+                self._state_np = self._state[:, 0].double().cpu().numpy()
+            return self._state_np
         return self._state.t()
 
     @robot_state.setter
@@ -102,6 +108,7 @@ class Environment:
         if self.num_envs == 1 and not isinstance(value, torch.Tensor):
             value = torch.as_tensor(np.asarray(value, dtype=np.float32).reshape(1, 2))
         self._state.copy_(_planes(value.to(self.device), self.num_envs, "robot_state"))
+        self._state_np = None
 
     @property
     def goal_state(self):
@@ -166,6 +173,7 @@ class Environment:
         _lib.check(_lib.lib().rtd3_env_step(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
                                             _lib.ptr(ap[0]), _lib.ptr(ap[1]), n, self.step_variant,
                                             _lib.stream_ptr(self.device)), "env_step")
+        self._state_np = None
         return self.robot_state
 
     def rollout(self, actions, record=True):
@@ -189,6 +197,7 @@ class Environment:
         _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
                                                _lib.ptr(planes), _lib.ptr(traj), n, T,
                                                _lib.stream_ptr(self.device)), "env_rollout")
+        self._state_np = None
         return traj.permute(0, 2, 1) if record else None
 
     def rollout_host(self, actions_host, out_host=None, chunks=8, mode=None):
@@ -222,6 +231,7 @@ class Environment:
         if mode != "staged" and not pinned:
             raise ValueError("mode %r needs pinned host buffers" % mode)
         main = torch.cuda.current_stream(self.device)
+        self._state_np = None
         if mode == "zero_copy":
             _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
                                                    _lib.ptr(actions_host), _lib.ptr(out_host), n, T,
@@ -284,15 +294,19 @@ class Environment:
                                              _lib.stream_ptr(self.device)), "env_reset")
         self._rng_out()
         if self.num_envs == 1:
-            return self._state64[:, 0].cpu().numpy()      # the reference returns the float64 draw itself
+            # the reference returns the float64 draw itself, and it IS robot_state afterwards (environment.py:131-132); the
+            # device keeps its float32 rounding
+            self._state_np = self._state64[:, 0].cpu().numpy()
+            return self._state_np
         return self.robot_state
 
     def get_random_robot_init_state(self):
         """environment.py:135-137: a draw that does not move the robot."""
-        keep = self._state.clone()
+        keep, keep_np = self._state.clone(), self._state_np
         out = self.reset()
         out = out.copy() if self.num_envs == 1 else out.clone()
         self._state.copy_(keep)
+        self._state_np = keep_np
         return out
 
     # ---- environment.py:140-179 (SURVEY.md 8 row f-1: the 80 000 serial dynamics calls become 4 rollouts of 100 paths) ----

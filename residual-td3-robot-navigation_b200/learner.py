@@ -312,6 +312,7 @@ class TD3:
         self.steps = torch.zeros((2,), dtype=torch.int32, device=self.device)       # Adam step counters {actor, critics}
         self.beta_pows = torch.ones((4,), dtype=torch.float64, device=self.device)  # {0.9^t, 0.999^t} per optimiser
         self._scratch = None
+        self._scratch_retired = []
 
         # online networks adopt arena slots 0..2; targets are copies (copy.deepcopy, robot.py:232-234)
         self.actor_network, self.critic_network_1, self.critic_network_2 = actor_network, critic_network_1, critic_network_2
@@ -348,6 +349,12 @@ class TD3:
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=process_group)
             self.grads.zero_()
+            # Replicas must START identical: every rank drew its initial weights from its own CPU torch generator (unseeded in
+            # the reference, robot.py:164), so rank 0's networks are broadcast and the targets re-copied from them (robot.py:232-234).
+            # Adam moments, step counters and beta powers are zeros / ones on every rank by construction.
+            dist.broadcast(self.params[:half], group=process_group, group_src=0)
+            self.params[half:].copy_(self.params[:half])
+            self._t_stale = self._u_stale = self._h_stale = True
             import os
             dp_collective = dp_collective or os.environ.get("RTD3_DP_COLLECTIVE", "nccl")
             self.dp_collective = dp_collective
@@ -388,6 +395,13 @@ class TD3:
                      "counter": torch.zeros((1,), dtype=torch.int32, device=self.device)}
         torch.cuda.synchronize(self.device)
         dist.barrier(group=pg)                          # every rank has mapped every buffer before the first launch
+
+    def replica_checksum(self):
+        """Order-independent exact checksums of the learner state (int64 sums of the float32 bit patterns of the parameter arena
+        and the Adam moments, plus the step counters) -> int64 `[4]` device tensor.  Data-parallel replicas that received the same
+        reduced gradients hold bit-identical state, so MIN and MAX of this over the ranks agree (`trainer.replicas_identical`)."""
+        bits = lambda t: t.view(torch.int32).to(torch.int64).sum()
+        return torch.stack([bits(self.params), bits(self.adam_m), bits(self.adam_v), self.steps.to(torch.int64).sum()])
 
     def __del__(self):
         try:
@@ -497,6 +511,8 @@ class TD3:
     def _row_scratch(self, B):
         need = int(_lib.lib().rtd3_td3_scratch_floats(self._handle, B))
         if self._scratch is None or self._scratch.numel() < need:
+            if self._scratch is not None:
+                self._scratch_retired.append(self._scratch)    # captured graphs (update and tick graphs) hold its address: never freed
             self._scratch = torch.empty((need,), dtype=torch.float32, device=self.device)
         return self._scratch
 
@@ -700,8 +716,8 @@ class TD3:
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self.device)
         side = self._side_stream
-        side.wait_stream(main)                                # the replay rows pushed so far are visible to the sampler
-        replay_buffer.begin_sampling_session()
+        replay_buffer.begin_sampling_session()                # uploads numpy's stream into the device bank with main-stream kernels ...
+        side.wait_stream(main)                                # ... so only now: those writes and the rows pushed so far are visible to the sampler
         try:
             def draw(g):
                 with torch.cuda.stream(side):

@@ -176,6 +176,29 @@ class Robot:
         self._noise_scale *= NOISE_DECAY
         self._path_length += PATH_INCREASE
 
+    # ---- robot.py:509-538 ------------------------------------------------------------------------------------------
+    def check_if_stuck(self, state):
+        """The reference's stuck test on the PRE-step state, as a stand-alone call (process_transition runs the same logic inside
+        `rtd3_robot_transition`, on the same device-side history ring `[5][2][N]`): with five earlier states held and all of them
+        closer than STUCK_THRESHOLD the robot is stuck and the history is cleared, otherwise the oldest state is dropped; the
+        state is then appended.  Returns a bool (single env) or a bool tensor `[N]`."""
+        n = self.num_envs
+        sp = self._state_planes(state)                                           # [2,N] float32, what the ring stores
+        cnt, head = self._hist_count.long(), self._hist_head.long()
+        full = cnt >= STUCK_STEPS
+        d = sp.double()[None] - self._hist.double()                               # [5,2,N]
+        dist = torch.sqrt(d[:, 1] * d[:, 1] + d[:, 0] * d[:, 0])
+        stuck = full & (dist < STUCK_THRESHOLD).all(dim=0)
+        head = torch.where(stuck, torch.zeros_like(head), torch.where(full, (head + 1) % STUCK_STEPS, head))
+        cnt = torch.where(stuck, torch.zeros_like(cnt), torch.where(full, cnt - 1, cnt))
+        slot = (head + cnt) % STUCK_STEPS
+        env = torch.arange(n, device=self.device)
+        self._hist[slot, 0, env] = sp[0]
+        self._hist[slot, 1, env] = sp[1]
+        self._hist_count.copy_((cnt + 1).to(torch.int32))
+        self._hist_head.copy_(head.to(torch.int32))
+        return stuck if self.batched else bool(stuck[0].item())
+
     # ---- robot.py:541-642 ------------------------------------------------------------------------------------------
     def _act(self, state, noise, types=None):
         n = self.num_envs
@@ -265,8 +288,15 @@ class Robot:
         goal = self._goal[:, 0].cpu().numpy()
         nxt = demonstration_states[1:].astype(np.float64)
         gd = -np.sqrt(((nxt - goal) ** 2).sum(axis=1))
-        # compute_reward with demo_flag still False: -distance, or GOAL_REWARD inside the goal radius (robot.py:709-716)
-        rew = np.where(gd >= -constants.TEST_DISTANCE_THRESHOLD, float(GOAL_REWARD), gd)
+        # compute_reward([next_state]) per transition (robot.py:709-716 -> :727-762): GOAL_REWARD inside the goal radius, else
+        # -distance plus - once demo_flag is set, i.e. for a demonstration processed after the demo phase - the proximity term
+        # against the demonstration states held NOW (this demonstration and its augmentations included, robot.py:693-697)
+        shaped = gd
+        if bool(self._demo_flag[0].item()):
+            demos = np.asarray([np.asarray(s, dtype=np.float64) for s in self.demonstration_states], dtype=np.float64)
+            near = np.array([np.sqrt(((demos - q) ** 2).sum(axis=1)).min() for q in nxt])
+            shaped = gd + DEMO_PROXIMITY_FACTOR * (-near)
+        rew = np.where(gd >= -constants.TEST_DISTANCE_THRESHOLD, float(GOAL_REWARD), shaped)
         done = np.zeros(T - 1, dtype=bool)
         done[-1] = True
         cu = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)

@@ -36,6 +36,19 @@ def allreduce_grads_(flat_grads, group=None):
     return world
 
 
+def replicas_identical(td3_agent, group=None):
+    """True iff every rank's learner state (parameters incl. targets, Adam moments, step counters) is bit-identical: the exact
+    integer checksums of `TD3.replica_checksum` are MIN- and MAX-all-reduced and compared.  Collective: call it on all ranks."""
+    import torch.distributed as dist
+    c = td3_agent.replica_checksum()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return True
+    lo, hi = c.clone(), c.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool((lo == hi).all().item())
+
+
 def update_due(local_count, episodes_per_update, group=None):
     """Whether a learner update is due, decided identically on every rank: the data-parallel `td3_update` all-reduces its
     gradients, so all ranks must enter it in the same tick.  `local_count` (int tensor `[1]`, this rank's finished-episode
@@ -161,7 +174,10 @@ class BatchedTrainer:
         # one 128-env tile per CTA: with more tiles than SMs a CTA runs its tiles one after the other (all ticks of one, then of
         # the next) and the three-launch tick, which overlaps them, is faster (65 536 envs: 60 against 36 us per tick)
         one_wave = (self.n + 127) // 128 <= torch.cuda.get_device_properties(self.device).multi_processor_count
-        return (self.fused and self.multi_tick_kernel and one_wave and self.noise == "philox" and agent._f16_ok(self.n)
+        # CTAs of the multi-tick launch drift apart by up to K ticks: everything a launch can push must fit in the ring, otherwise
+        # two CTAs could reserve the same slot (rows mixing two transitions) - the three-launch tick serialises and has no such bound
+        fits = self.check_interval * self.n <= robot.memory.capacity
+        return (self.fused and self.multi_tick_kernel and one_wave and fits and self.noise == "philox" and agent._f16_ok(self.n)
                 and (robot._demo_dev is None or robot._demo_cells is not None))
 
     def _run_multi_tick(self, K):
@@ -188,6 +204,7 @@ class BatchedTrainer:
                 self._run_multi_tick(K)
                 self.ticks += K
                 done += K
+                self.env._state_np = None
                 self.robot.maybe_update()
             elif self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
                 self.robot.td3_agent.prepare_forward(self.n)
@@ -206,6 +223,7 @@ class BatchedTrainer:
                 self.robot.memory._mark_device_advanced()
                 self.ticks += K
                 done += K
+                self.env._state_np = None
                 self.robot.maybe_update()
             else:
                 self.tick()
@@ -244,6 +262,7 @@ class BatchedTrainer:
         else:
             types = self._device_tick()
         self.ticks += 1
+        self.env._state_np = None                                             # the kernels moved the state under the host cache
         if self.ticks % self.check_interval == 0:
             self.robot.maybe_update()                                         # robot-learning.py:68 -> robot.py:480-483
         return types
