@@ -274,8 +274,89 @@ int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, 
  * carry; every rank must issue the same sequence of calls).  out (count floats, private) receives the sum; local_grads (count
  * floats, private) is read and cleared.  block_counter: uint32 [1], zero-initialised once.  A rank whose peers do not arrive within
  * 20 s traps (the launch fails) instead of hanging.  A plain launch: it may be captured in a CUDA graph. */
+/* slot_floats: distance between two slots of a receive area (>= count, a multiple of 4; the area holds 2 * world * slot_floats
+ * floats).  Calls of different `count` may alternate on one area (critic gradients, then actor gradients) as long as they use the
+ * same slot_floats. */
 int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* seq_counter,
-                           float* out, float* local_grads, int64_t count, uint32_t* block_counter, void* stream);
+                           float* out, float* local_grads, int64_t count, int64_t slot_floats, uint32_t* block_counter, void* stream);
+
+/* The same arguments as a HOST struct (what rtd3_td3_update takes). `sum`: private buffer the optimiser reads (same indexing as grads). */
+typedef struct rtd3_p2p_state {
+  float* const* peer_recv;
+  uint64_t* const* peer_flags;
+  int32_t rank;
+  int32_t world;
+  uint64_t* seq_counter;
+  float* sum;
+  int64_t slot_floats;
+  uint32_t* block_counter;
+} rtd3_p2p_state;
+
+/* NCCL communicator of the data-parallel learner (north star: "NCCL over NVLink used only for the actor/critic gradient allreduce").
+ * librtd3 resolves libnccl.so.2 at run time (the copy already loaded into the process - torch's - else the system one); there is no
+ * link-time dependency.  The host creates a unique id on one rank (rtd3_comm_unique_id, HOST buffer of RTD3_COMM_ID_BYTES), hands it
+ * to the other ranks over any channel it has, and every rank calls rtd3_comm_create (collective).  Errors: 1000 + ncclResult_t. */
+#define RTD3_COMM_ID_BYTES 128
+typedef struct rtd3_comm rtd3_comm;
+int32_t rtd3_comm_nccl_version(void);                      /* e.g. 22809, -1 if NCCL cannot be loaded */
+int32_t rtd3_comm_unique_id(uint8_t* id_out);              /* HOST [RTD3_COMM_ID_BYTES] */
+int32_t rtd3_comm_create(rtd3_comm** out, const uint8_t* id /*HOST*/, int32_t rank, int32_t world, int32_t device);
+int32_t rtd3_comm_destroy(rtd3_comm* comm);
+int32_t rtd3_comm_world(const rtd3_comm* comm);
+int32_t rtd3_comm_rank(const rtd3_comm* comm);
+/* SUM all-reduce, in place, of the flat fp32 gradient buffer over the ranks of `comm` on `stream`.  The optimiser
+ * then applies grad_scale = 1/world.  A plain stream operation on our own communicator: capturable in a CUDA graph. */
+int32_t rtd3_allreduce_grads(rtd3_comm* comm, float* flat_grads, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TD3.td3_update (robot.py:258-285) in one call
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rtd3_td3_update_args {
+  /* learner state (arena notes above) */
+  float* params;
+  float* params_t;
+  float* params_uv;              /* nullable unless tf32: tensor-core operand copies, kept in step */
+  float* grads;
+  float* adam_m;
+  float* adam_v;
+  float* scratch;                /* rtd3_td3_scratch_floats(batch) floats (fp32 steps) */
+  int32_t* steps;                /* [2] */
+  double* beta_pows;             /* [4] */
+  /* replay ring */
+  const float* rp_s;
+  const float* rp_a;
+  const float* rp_r;
+  const float* rp_s2;
+  const float* rp_notdone;
+  /* minibatches: index sets in the order the reference draws them (critic of epoch 0, actor of epoch 0, critic of epoch 1, ...) */
+  const int32_t* idx;            /* [epochs + ceil(epochs / policy_update_delay)][batch] */
+  int32_t batch;
+  int32_t epochs;
+  int32_t policy_update_delay;   /* robot.py:278 */
+  /* target-policy smoothing noise (robot.py:338): a unit-normal tensor [epochs][batch][2], or NULL = generated in the critic kernel
+   * from Philox4x32-10 keyed (noise_seed, noise_counter[0] + epoch, row); the call then advances noise_counter by `epochs` */
+  const float* noise;
+  uint64_t noise_seed;
+  uint64_t* noise_counter;       /* DEVICE uint64 [1] */
+  float gamma, policy_noise, noise_clip, max_action, lr_actor, lr_critic, tau;
+  /* outputs: the values the reference collects at robot.py:274-280 */
+  float* critic_losses;          /* [epochs][2] */
+  float* actor_losses;           /* [ceil(epochs / policy_update_delay)] */
+  /* data-parallel learner: world > 1 needs exactly one of comm (NCCL) / p2p (peer memory) */
+  int32_t world;
+  int32_t tf32;                  /* 1: rtd3_td3_*_step_tf32 (tcgen05) instead of the fp32 steps */
+  rtd3_comm* comm;
+  const rtd3_p2p_state* p2p;
+} rtd3_td3_update_args;
+
+/* The unit normals rtd3_td3_update's critic kernels generate for step `counter` (= noise_counter[0] + epoch): out [rows][2] float32 =
+ * Box-Muller of two 53-bit uniforms from Philox4x32-10, counter (row lo, row hi, step lo, step hi), key (seed lo, seed hi). */
+int32_t rtd3_td3_target_noise(uint64_t seed, uint64_t counter, float* out, int64_t rows, void* stream);
+
+/* The epoch loop of TD3.td3_update: per epoch rtd3_td3_critic_step -> [all-reduce of the critic gradients] -> Adam on both critics;
+ * every policy_update_delay-th epoch rtd3_td3_actor_step -> [all-reduce of the actor gradients] -> Adam on the actor + the three
+ * Polyak updates.  Everything is issued on `stream` without synchronising (capturable in one CUDA graph). */
+int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused tick of the batched driver loop        (robot-learning.py:66-101, training branch)

@@ -36,6 +36,24 @@ class TickStateStruct(Structure):
 
 
 TICK_NOISE_NONE, TICK_NOISE_GIVEN, TICK_NOISE_PHILOX = 0, 1, 2
+COMM_ID_BYTES = 128
+
+
+class P2pStateStruct(Structure):
+    """`rtd3_p2p_state` of include/rtd3.h."""
+    _fields_ = [("peer_recv", c_void_p), ("peer_flags", c_void_p), ("rank", c_int32), ("world", c_int32), ("seq_counter", c_void_p),
+                ("sum", c_void_p), ("slot_floats", c_int64), ("block_counter", c_void_p)]
+
+
+class Td3UpdateArgs(Structure):
+    """`rtd3_td3_update_args` of include/rtd3.h (same field order)."""
+    _fields_ = ([(k, c_void_p) for k in ("params", "params_t", "params_uv", "grads", "adam_m", "adam_v", "scratch", "steps", "beta_pows",
+                                         "rp_s", "rp_a", "rp_r", "rp_s2", "rp_notdone", "idx")]
+                + [("batch", c_int32), ("epochs", c_int32), ("policy_update_delay", c_int32)]
+                + [("noise", c_void_p), ("noise_seed", c_uint64), ("noise_counter", c_void_p)]
+                + [(k, c_float) for k in ("gamma", "policy_noise", "noise_clip", "max_action", "lr_actor", "lr_critic", "tau")]
+                + [("critic_losses", c_void_p), ("actor_losses", c_void_p), ("world", c_int32), ("tf32", c_int32), ("comm", c_void_p),
+                   ("p2p", POINTER(P2pStateStruct))])
 
 _P = c_void_p
 _SIGNATURES = {
@@ -81,7 +99,16 @@ _SIGNATURES = {
     "rtd3_td3_actor_step_tf32": (c_int32, [_P] * 6 + [c_int32, _P, _P, _P, _P]),
     "rtd3_debug_lt_prof": (c_int32, [c_int32, _P]),
     "rtd3_trainer_tally": (c_int32, [_P, _P, _P, c_int64, _P]),
-    "rtd3_p2p_allreduce": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P]),
+    "rtd3_p2p_allreduce": (c_int32, [_P, _P, c_int32, c_int32, _P, _P, _P, c_int64, c_int64, _P, _P]),
+    "rtd3_comm_nccl_version": (c_int32, []),
+    "rtd3_comm_unique_id": (c_int32, [_P]),
+    "rtd3_comm_create": (c_int32, [POINTER(c_void_p), _P, c_int32, c_int32, c_int32]),
+    "rtd3_comm_destroy": (c_int32, [_P]),
+    "rtd3_comm_world": (c_int32, [_P]),
+    "rtd3_comm_rank": (c_int32, [_P]),
+    "rtd3_allreduce_grads": (c_int32, [_P, _P, c_int64, _P]),
+    "rtd3_td3_update": (c_int32, [_P, POINTER(Td3UpdateArgs), _P]),
+    "rtd3_td3_target_noise": (c_int32, [c_uint64, c_uint64, _P, c_int64, _P]),
     "rtd3_tick_pre": (c_int32, [POINTER(TickStateStruct), _P]),
     "rtd3_tick_post": (c_int32, [_P, POINTER(TickStateStruct), _P, _P, c_int32, _P]),
     "rtd3_tick_run_f16": (c_int32, [_P, POINTER(TickStateStruct), c_int32, c_int32, _P, _P, c_int32, c_int64, c_uint64, _P]),

@@ -53,14 +53,17 @@ __device__ __forceinline__ float4 ld_fresh(const float4* p) {   // written by a 
 
 template <int kWorld>
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter, float* __restrict__ out,
-                                                            float* __restrict__ local_grads, int64_t count4, unsigned int* block_counter) {
+                                                            float* __restrict__ local_grads, int64_t count4, int64_t stride4,
+                                                            unsigned int* block_counter) {
   __shared__ bool s_last;
   __shared__ unsigned long long s_seq;
   const int tid = threadIdx.x;
   if (tid == 0) s_seq = *reinterpret_cast<volatile unsigned long long*>(seq_counter) + 1ull;
   __syncthreads();
   const unsigned long long seq = s_seq;
-  const int64_t slot = ((int64_t)(seq & 1ull) * kWorld + rank) * count4;      // [parity][rank] in every receive area
+  // [parity][rank] in every receive area; slots are `stride4` apart whatever this call's count (calls of different sizes may
+  // alternate - critic and actor gradients - and a slot of one parity must never reach into the other parity's half)
+  const int64_t slot = ((int64_t)(seq & 1ull) * kWorld + rank) * stride4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   // (1) push (the kernels that produced local_grads precede this one in stream order)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < count4; i += stride) {
@@ -89,11 +92,11 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int 
   // (3) all W gradients of this step have landed here: add them in rank order
   if (tid < kWorld) wait_flag(peers.flags[rank] + tid, seq);
   __syncthreads();
-  const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * count4;
+  const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * stride4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < count4; i += stride) {
     float4 v[kWorld];
 #pragma unroll
-    for (int r = 0; r < kWorld; ++r) v[r] = ld_fresh(mine + (int64_t)r * count4 + i);
+    for (int r = 0; r < kWorld; ++r) v[r] = ld_fresh(mine + (int64_t)r * stride4 + i);
     float4 acc = v[0];
 #pragma unroll
     for (int r = 1; r < kWorld; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
@@ -106,10 +109,12 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int 
 using namespace rtd3;
 
 extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* seq_counter,
-                                      float* out, float* local_grads, int64_t count, uint32_t* block_counter, void* stream) {
+                                      float* out, float* local_grads, int64_t count, int64_t slot_floats, uint32_t* block_counter, void* stream) {
   RTD3_CHECK_ARG(peer_recv && peer_flags && out && local_grads && block_counter && seq_counter, "null argument");
   RTD3_CHECK_ARG(world >= 2 && world <= kP2pMaxWorld && rank >= 0 && rank < world, "bad rank / world");
   RTD3_CHECK_ARG(count > 0 && count % 4 == 0, "count must be a positive multiple of 4");
+  RTD3_CHECK_ARG(slot_floats >= count && slot_floats % 4 == 0, "slot_floats must be a multiple of 4 and at least count");
+  RTD3_CHECK_ARG((uintptr_t)out % 16 == 0 && (uintptr_t)local_grads % 16 == 0, "out / local_grads must be 16 B aligned");
   P2pPeers p{};
   for (int r = 0; r < world; ++r) {
     RTD3_CHECK_ARG(peer_recv[r] && peer_flags[r], "null peer pointer");
@@ -126,7 +131,7 @@ extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* 
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* sc = (unsigned long long*)seq_counter;
   switch (world) {
-#define RTD3_P2P_CASE(W) case W: p2p_allreduce_kernel<W><<<grid, 256, 0, st>>>(p, rank, sc, out, local_grads, count4, block_counter); break;
+#define RTD3_P2P_CASE(W) case W: p2p_allreduce_kernel<W><<<grid, 256, 0, st>>>(p, rank, sc, out, local_grads, count4, slot_floats / 4, block_counter); break;
     RTD3_P2P_CASE(2) RTD3_P2P_CASE(3) RTD3_P2P_CASE(4) RTD3_P2P_CASE(5) RTD3_P2P_CASE(6) RTD3_P2P_CASE(7) RTD3_P2P_CASE(8)
 #undef RTD3_P2P_CASE
   }

@@ -647,9 +647,10 @@ td3_critic_tc_kernel(Arena ar, const float* __restrict__ params, const float* __
         float* dout = sm + L::oDout;
         if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
           const int row = min(r0 + t, B - 1);
+          const float2 zn = target_noise(noise, hp, row);
 #pragma unroll
           for (int o = 0; o < 2; ++o) {
-            float e = noise[row * 2 + o] * hp.policy_noise;
+            float e = (o == 0 ? zn.x : zn.y) * hp.policy_noise;
             e = fminf(fmaxf(e, -hp.noise_clip), hp.noise_clip);
             in0[t * 4 + 2 + o] = fminf(fmaxf(out[t * 2 + o] + e, -hp.max_action), hp.max_action);
           }
@@ -834,10 +835,6 @@ static int32_t make_dw_map(CUtensorMap* tm, float* base, int H) {
 
 static bool lt_shape_ok(const rtd3_td3* h) { return h->ar.actor.layers == 2 && (h->ar.actor.hid == 128 || h->ar.actor.hid == 256); }
 
-template <typename K>
-static cudaError_t lt_set_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
 
 extern "C" {
 
@@ -858,16 +855,24 @@ int32_t rtd3_td3_critic_step_tf32(rtd3_td3* h, const float* params, const float*
                  "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   RTD3_CHECK_ARG(lt_shape_ok(h), "the tf32 learner needs layers == 2 and hidden in {128, 256}");
+  ReplayView rp{(const float2*)rp_s, (const float2*)rp_a, rp_r, (const float2*)rp_s2, rp_notdone};
+  Td3Hyper hp{gamma, policy_noise, noise_clip, max_action, 0ull, nullptr, 0ull};
+  return critic_step_tc_launch(h, params, params_uv, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+int32_t rtd3::critic_step_tc_launch(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const ReplayView& rp, const int32_t* idx,
+                                    const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out, int32_t* steps,
+                                    double* beta_pows, cudaStream_t st) {
+  RTD3_CHECK_ARG(lt_shape_ok(h), "the tf32 learner needs layers == 2 and hidden in {128, 256}");
   const int H = h->ar.critic.hid;
   LtMaps maps;
   for (int c = 0; c < 2; ++c) {
     const int32_t rc = make_dw_map(&maps.dw[c], grads + h->ar.off(1 + c) + net_w_off(h->ar.critic, 1), H);
     if (rc) return rc;
   }
-  ReplayView rp{(const float2*)rp_s, (const float2*)rp_a, rp_r, (const float2*)rp_s2, rp_notdone};
-  Td3Hyper hp{gamma, policy_noise, noise_clip, max_action};
   const int grid = (batch + kLtRows - 1) / kLtRows;
-  cudaStream_t st = (cudaStream_t)stream;
   if (H == 128) {
     RTD3_CUDA(ensure_dyn_smem((const void*)td3_critic_tc_kernel<128>, Lt<128>::kBytes));
     td3_critic_tc_kernel<128><<<grid, kLtThreads, Lt<128>::kBytes, st>>>(h->ar, params, params_uv, grads, rp, idx, noise, batch, hp, loss2, q_out, y_out,
@@ -880,6 +885,8 @@ int32_t rtd3_td3_critic_step_tf32(rtd3_td3* h, const float* params, const float*
   RTD3_LAUNCHED();
   return 0;
 }
+
+extern "C" {
 
 int32_t rtd3_td3_actor_step_tf32(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const float* rp_s, const int32_t* idx,
                                  int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {

@@ -54,9 +54,10 @@ td3_critic_kernel(Arena ar, const float* __restrict__ params, const float* __res
     if (t < R) {
       if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
         const int row = min(r0 + t, B - 1);
+        const float2 zn = target_noise(noise, hp, row);
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-          float e = noise[row * 2 + o] * hp.policy_noise;
+          float e = (o == 0 ? zn.x : zn.y) * hp.policy_noise;
           e = fminf(fmaxf(e, -hp.noise_clip), hp.noise_clip);
           in0[t * 4 + 2 + o] = fminf(fmaxf(out[t * 2 + o] + e, -hp.max_action), hp.max_action);
         }
@@ -539,11 +540,18 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* para
                  "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, (const float2*)rp_a, rp_r, (const float2*)rp_s2, rp_notdone};
-  Td3Hyper hp{gamma, policy_noise, noise_clip, max_action};
+  Td3Hyper hp{gamma, policy_noise, noise_clip, max_action, 0ull, nullptr, 0ull};
+  return critic_step_launch(h, params, params_t, grads, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
+                                 const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
+                                 int32_t* steps, double* beta_pows, cudaStream_t st) {
   const int ti = pick_tile(batch, h->num_sms);
   const int R = kRowTiles[ti];
   const int grid = (batch + R - 1) / R;
-  cudaStream_t st = (cudaStream_t)stream;
 #define RTD3_CRITIC(RR) \
   td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
   if (ti == 0) RTD3_CRITIC(2); else if (ti == 1) RTD3_CRITIC(4); else if (ti == 2) RTD3_CRITIC(8); else RTD3_CRITIC(16);
@@ -555,6 +563,8 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* para
   slots.scratch_off[0] = 0; slots.scratch_off[1] = per;
   return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st);
 }
+
+extern "C" {
 
 int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
                             int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {
@@ -626,6 +636,102 @@ int32_t rtd3_replay_gather(const float* s, const float* a, const float* r, const
   replay_gather_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rp, idx, batch, (float2*)out_s, (float2*)out_a, out_r,
                                                                               (float2*)out_s2, out_notdone);
   RTD3_LAUNCHED();
+  return 0;
+}
+
+
+// ---- TD3.td3_update (robot.py:258-285) as ONE call: the epoch loop, the gradient all-reduce of the data-parallel learner and the
+// optimiser / Polyak steps issued on `stream` (plain launches: the whole call can be captured in a CUDA graph, the NCCL node included).
+__global__ void advance_counter_kernel(unsigned long long* counter, unsigned long long by) { counter[0] += by; }
+
+__global__ void target_noise_kernel(Td3Hyper hp, float2* __restrict__ out, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) out[i] = target_noise(nullptr, hp, (int)i);
+}
+
+static int32_t update_allreduce(const rtd3_td3_update_args* a, int64_t off, int64_t count, cudaStream_t st) {
+  if (a->world <= 1) return 0;
+  if (a->p2p) {
+    const rtd3_p2p_state* p = a->p2p;
+    return rtd3_p2p_allreduce(p->peer_recv, p->peer_flags, p->rank, p->world, p->seq_counter, p->sum + off, a->grads + off, count, p->slot_floats,
+                              p->block_counter, st);
+  }
+  return rtd3_allreduce_grads(a->comm, a->grads + off, count, st);
+}
+
+int32_t rtd3_td3_target_noise(uint64_t seed, uint64_t counter, float* out, int64_t rows, void* stream) {
+  RTD3_CHECK_ARG(out && rows >= 0 && rows < (1ll << 31), "bad argument");
+  if (rows == 0) return 0;
+  // the generator of the critic kernels (rtd3_td3.cuh: target_noise), evaluated for rows 0..rows-1 of step `counter`
+  const Td3Hyper hp{0.f, 0.f, 0.f, 0.f, (unsigned long long)seed, nullptr, (unsigned long long)counter};
+  target_noise_kernel<<<(int)ceil_div(rows, 256), 256, 0, (cudaStream_t)stream>>>(hp, (float2*)out, rows);
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream) {
+  RTD3_CHECK_ARG(h && a, "null argument");
+  RTD3_CHECK_ARG(a->params && a->params_t && a->grads && a->adam_m && a->adam_v && a->steps && a->beta_pows, "null learner state");
+  RTD3_CHECK_ARG(a->rp_s && a->rp_a && a->rp_r && a->rp_s2 && a->rp_notdone && a->idx, "null replay ring / index sets");
+  RTD3_CHECK_ARG(a->batch > 0 && a->epochs >= 0 && a->policy_update_delay >= 1, "bad batch / epochs / policy_update_delay");
+  RTD3_CHECK_ARG(a->critic_losses && a->actor_losses, "null loss outputs");
+  RTD3_CHECK_ARG(a->noise || a->noise_counter, "either a noise tensor or the device noise counter is required");
+  RTD3_CHECK_ARG(a->world >= 1 && (a->world == 1 || a->comm || a->p2p), "world > 1 needs a communicator (rtd3_comm) or a peer-memory state");
+  RTD3_CHECK_ARG(!a->p2p || (a->p2p->world == a->world && a->p2p->sum), "peer-memory state of another world size");
+  const bool tc = a->tf32 != 0;
+  RTD3_CHECK_ARG(!tc || (a->params_uv && rtd3_td3_tf32_supported(h)), "tf32 needs params_uv and a 2 x 128 / 2 x 256 learner");
+  RTD3_CHECK_ARG(tc || a->scratch, "the fp32 steps need the row scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int E = a->epochs, B = a->batch, delay = a->policy_update_delay;
+  if (E == 0) return 0;
+  const int n_actor = (E + delay - 1) / delay;
+  RTD3_CUDA(cudaMemsetAsync(a->critic_losses, 0, sizeof(float) * 2 * (size_t)E, st));
+  RTD3_CUDA(cudaMemsetAsync(a->actor_losses, 0, sizeof(float) * (size_t)n_actor, st));
+  const ReplayView rp{(const float2*)a->rp_s, (const float2*)a->rp_a, a->rp_r, (const float2*)a->rp_s2, a->rp_notdone};
+  const ReplayView rp_actor{(const float2*)a->rp_s, nullptr, nullptr, nullptr, nullptr};
+  Td3Hyper hp{a->gamma, a->policy_noise, a->noise_clip, a->max_action, (unsigned long long)a->noise_seed,
+              (const unsigned long long*)a->noise_counter, 0ull};
+  float* opt_grads = (a->world > 1 && a->p2p) ? a->p2p->sum : a->grads;      // what the optimiser consumes
+  const float scale = 1.0f / (float)a->world;
+  const int64_t off_c = h->ar.off(1), n_online = h->ar.online_total();
+  int64_t k = 0, ka = 0;
+  int32_t rc = 0;
+  for (int e = 0; e < E; ++e) {
+    hp.noise_index = (unsigned long long)e;
+    const float* nz = a->noise ? a->noise + (int64_t)e * B * 2 : nullptr;
+    const int32_t* ix = a->idx + k * B;
+    ++k;
+    if (tc)
+      rc = critic_step_tc_launch(h, a->params, a->params_uv, a->grads, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr, a->steps,
+                                 a->beta_pows, st);
+    else
+      rc = critic_step_launch(h, a->params, a->params_t, a->grads, a->scratch, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr,
+                              a->steps, a->beta_pows, st);
+    if (rc) return rc;
+    if ((rc = update_allreduce(a, off_c, n_online - off_c, st))) return rc;
+    if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b110, a->lr_actor,
+                                   a->lr_critic, scale, 0, a->tau, st)))
+      return rc;
+    if (e % delay == 0) {
+      const int32_t* ixa = a->idx + k * B;
+      ++k;
+      if (tc)
+        rc = rtd3_td3_actor_step_tf32(h, a->params, a->params_uv, a->grads, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st);
+      else
+        rc = rtd3_td3_actor_step(h, a->params, a->params_t, a->grads, a->scratch, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st);
+      ++ka;
+      if (rc) return rc;
+      if ((rc = update_allreduce(a, 0, off_c, st))) return rc;
+      if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b001, a->lr_actor,
+                                     a->lr_critic, scale, 0b111, a->tau, st)))
+        return rc;
+    }
+  }
+  (void)rp_actor;
+  if (!a->noise) {
+    advance_counter_kernel<<<1, 1, 0, st>>>((unsigned long long*)a->noise_counter, (unsigned long long)E);
+    RTD3_LAUNCHED();
+  }
   return 0;
 }
 

@@ -15,7 +15,21 @@ struct ReplayView {
 
 struct Td3Hyper {
   float gamma, policy_noise, noise_clip, max_action;
+  // target-policy smoothing noise (robot.py:338) when no noise tensor is supplied: unit normals from Philox4x32-10 keyed
+  // (noise_seed, noise_counter[0] + noise_index, batch row).  The counter lives in device memory (a replayed CUDA graph draws fresh
+  // noise); noise_index is the epoch inside one update; rtd3_td3_update advances the counter by `epochs` when it is done.
+  unsigned long long noise_seed;
+  const unsigned long long* noise_counter;   // nullable: counts as 0
+  unsigned long long noise_index;
 };
+
+// robot.py:338: the two unit normals of batch row `row` - from the supplied tensor, else generated here
+__device__ __forceinline__ float2 target_noise(const float* __restrict__ noise, const Td3Hyper& hp, int row) {
+  if (noise) return make_float2(noise[row * 2], noise[row * 2 + 1]);
+  double z0, z1;
+  philox_normal2(hp.noise_seed, (hp.noise_counter ? hp.noise_counter[0] : 0ull) + hp.noise_index, (uint64_t)row, z0, z1);
+  return make_float2((float)z0, (float)z1);
+}
 
 // Parameter arena: [actor | critic1 | critic2 | target actor | target critic1 | target critic2], each slot padded to 4 floats.
 struct Arena {
@@ -75,6 +89,17 @@ __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_
   beta_pows[2 * o + 1] *= 0.999;
 }
 
+}  // namespace rtd3
+
+// launch helpers shared by the public step entry points and rtd3_td3_update (rtd3_td3.cu, rtd3_tc_learner.cu)
+struct rtd3_td3;
+namespace rtd3 {
+int32_t critic_step_launch(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
+                           const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
+                           int32_t* steps, double* beta_pows, cudaStream_t st);
+int32_t critic_step_tc_launch(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const ReplayView& rp, const int32_t* idx,
+                              const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out, int32_t* steps,
+                              double* beta_pows, cudaStream_t st);
 }  // namespace rtd3
 
 // the opaque learner handle of the C ABI

@@ -17,20 +17,6 @@
 
 namespace rtd3 {
 
-// Two unit normals for (env, tick) from Philox4x32-10 + Box-Muller in float64 (throughput-mode exploration noise: counter-based,
-// so a replayed CUDA graph draws fresh noise every tick from the device tick counter).
-__device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t tick, uint64_t env, double& z0, double& z1) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)tick, (uint32_t)(tick >> 32)),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const double u1 = ((double)(r.x >> 5) * 67108864.0 + (double)(r.y >> 6)) / 9007199254740992.0;   // [0,1), 53 bits
-  const double u2 = ((double)(r.z >> 5) * 67108864.0 + (double)(r.w >> 6)) / 9007199254740992.0;
-  const double rad = sqrt(-2.0 * log(1.0 - u1));                                                  // 1 - u1 in (0,1]
-  double s, c;
-  sincospi(2.0 * u2, &s, &c);
-  z0 = rad * c;
-  z1 = rad * s;
-}
-
 __global__ void __launch_bounds__(256) tick_pre_kernel(rtd3_tick_state t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = t.n;

@@ -30,6 +30,8 @@ TD3_BATCH_SIZE = 100
 GAMMA = 0.99
 TAU = 0.001
 
+DEFAULT_DP_COLLECTIVE = "nccl"       # "nccl": rtd3_allreduce_grads on our own communicator; "p2p": rtd3_p2p_allreduce (peer memory)
+
 HIDDEN = 200     # robot.py:145-148
 LAYERS = 3
 
@@ -345,6 +347,12 @@ class TD3:
         self.sample_chunk_epochs = 10       # epochs per pipelined chunk of td3_update (0 = draw all index sets up front)
         self._graphs = {}
         self._p2p = None
+        self._comm = None
+        # target-policy smoothing noise (robot.py:338, torch.randn_like - unseeded in the reference): generated inside the critic
+        # kernels from Philox4x32-10 keyed (noise_seed, device step counter, batch row) unless a noise tensor is injected
+        self.noise_seed = 0x7d3
+        self._noise_counter = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._noise_steps = 0               # host mirror of the counter (what the next single-step call uses)
         if self.world > 1:                  # initialise the communicator outside of any graph capture
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=process_group)
@@ -356,12 +364,37 @@ class TD3:
             self.params[half:].copy_(self.params[:half])
             self._t_stale = self._u_stale = self._h_stale = True
             import os
-            dp_collective = dp_collective or os.environ.get("RTD3_DP_COLLECTIVE", "nccl")
+            dp_collective = dp_collective or os.environ.get("RTD3_DP_COLLECTIVE", DEFAULT_DP_COLLECTIVE)
             self.dp_collective = dp_collective
             if dp_collective == "p2p":
                 self._setup_p2p()
-            elif dp_collective != "nccl":
+            elif dp_collective == "nccl":
+                self._setup_comm()
+            else:
                 raise ValueError("dp_collective must be 'nccl' or 'p2p'")
+
+    def _setup_comm(self):
+        """Our own NCCL communicator behind the C ABI (`rtd3_comm_create`; the unique id travels once over the process group):
+        `rtd3_allreduce_grads` on it is a plain stream operation, so the data-parallel update is captured in ONE CUDA graph, NCCL
+        node included (torch's ProcessGroupNCCL collectives are not capturable together with foreign launches on this stack)."""
+        import torch.distributed as dist
+        pg = self.process_group
+        rank = dist.get_rank(pg)
+        ident = [None]
+        if rank == 0:
+            buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
+            _lib.check(_lib.lib().rtd3_comm_unique_id(buf), "comm_unique_id")
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, group=pg, group_src=0)
+        buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(ident[0])
+        self._comm = ctypes.c_void_p()
+        torch.cuda.synchronize(self.device)
+        _lib.check(_lib.lib().rtd3_comm_create(ctypes.byref(self._comm), buf, rank, self.world, self.device.index or 0), "comm_create")
+        # first collective outside of any capture (connection set-up allocates)
+        _lib.check(_lib.lib().rtd3_allreduce_grads(self._comm, _lib.ptr(self.grads), self.grads.numel(), _lib.stream_ptr(self.device)),
+                   "allreduce_grads (warm-up)")
+        torch.cuda.synchronize(self.device)
+        self.grads.zero_()
 
     def _setup_p2p(self):
         """Gradient all-reduce over NVLink peer memory (`rtd3_p2p_allreduce`): a receive area + flag array per rank that every
@@ -393,6 +426,9 @@ class TD3:
         self._p2p = {"peers": peers, "rank": rank, "seq": torch.zeros((1,), dtype=torch.int64, device=self.device), "count": G,
                      "recv": c(*[t.data_ptr() for t in peers]), "flags": c(*[t.data_ptr() + 4 * 2 * world * G for t in peers]),
                      "counter": torch.zeros((1,), dtype=torch.int32, device=self.device)}
+        p = self._p2p
+        p["struct"] = _lib.P2pStateStruct(ctypes.cast(p["recv"], ctypes.c_void_p), ctypes.cast(p["flags"], ctypes.c_void_p), rank, world,
+                                          p["seq"].data_ptr(), self._grads_sum.data_ptr(), G, p["counter"].data_ptr())
         torch.cuda.synchronize(self.device)
         dist.barrier(group=pg)                          # every rank has mapped every buffer before the first launch
 
@@ -405,6 +441,9 @@ class TD3:
 
     def __del__(self):
         try:
+            if getattr(self, "_comm", None):
+                _lib.lib().rtd3_comm_destroy(self._comm)
+                self._comm = None
             if getattr(self, "_handle", None):
                 _lib.lib().rtd3_td3_destroy(self._handle)
                 self._handle = None
@@ -497,16 +536,22 @@ class TD3:
         return y
 
     # ---- the three device steps -------------------------------------------------------------------------
-    def _allreduce(self):
+    def _grad_range(self, nets):
+        """(offset, count) of the gradient floats of the critics (nets = 0b110) or the actor (0b001) in the flat buffer."""
+        return (self._off[1], self.grads.numel() - self._off[1]) if nets == 0b110 else (0, self._off[1])
+
+    def _allreduce(self, nets):
+        """SUM over the ranks of the gradients one optimiser step consumes."""
+        if self.world == 1:
+            return
+        off, count = self._grad_range(nets)
         if self._p2p is not None:
             p = self._p2p
-            _lib.check(_lib.lib().rtd3_p2p_allreduce(p["recv"], p["flags"], p["rank"], self.world, _lib.ptr(p["seq"]), _lib.ptr(self._grads_sum),
-                                                     _lib.ptr(self.grads), p["count"], _lib.ptr(p["counter"]), _lib.stream_ptr(self.device)),
+            _lib.check(_lib.lib().rtd3_p2p_allreduce(p["recv"], p["flags"], p["rank"], self.world, _lib.ptr(p["seq"]), _lib.ptr(self._grads_sum[off:]),
+                                                     _lib.ptr(self.grads[off:]), count, p["count"], _lib.ptr(p["counter"]), _lib.stream_ptr(self.device)),
                        "p2p_allreduce")
-            return
-        if self.world > 1:
-            from .trainer import allreduce_grads_
-            allreduce_grads_(self.grads, self.process_group)
+        else:
+            _lib.check(_lib.lib().rtd3_allreduce_grads(self._comm, _lib.ptr(self.grads[off:]), count, _lib.stream_ptr(self.device)), "allreduce_grads")
 
     def _row_scratch(self, B):
         need = int(_lib.lib().rtd3_td3_scratch_floats(self._handle, B))
@@ -527,7 +572,7 @@ class TD3:
                 self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
                 _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step_tf32")
             if apply:
-                self._allreduce()
+                self._allreduce(0b110)
                 self._adam(nets=0b110, polyak=0)
             return
         _lib.check(_lib.lib().rtd3_td3_critic_step(
@@ -536,7 +581,7 @@ class TD3:
             self.noise_clip, float(self.max_action), _lib.ptr(loss2), _lib.ptr(q_out), _lib.ptr(y_out), _lib.ptr(self.steps),
             _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_critic_step")
         if apply:
-            self._allreduce()
+            self._allreduce(0b110)
             self._adam(nets=0b110, polyak=0)
 
     def _actor_step(self, rb, idx, loss1):
@@ -546,13 +591,13 @@ class TD3:
             _lib.check(_lib.lib().rtd3_td3_actor_step_tf32(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_u), _lib.ptr(self.grads),
                                                            _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1), _lib.ptr(self.steps),
                                                            _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)), "td3_actor_step_tf32")
-            self._allreduce()
+            self._allreduce(0b001)
             return
         _lib.check(_lib.lib().rtd3_td3_actor_step(self._handle, _lib.ptr(self.params), _lib.ptr(self.params_t), _lib.ptr(self.grads),
                                                   _lib.ptr(self._row_scratch(B)), _lib.ptr(rb.s), _lib.ptr(idx), B, _lib.ptr(loss1),
                                                   _lib.ptr(self.steps), _lib.ptr(self.beta_pows), _lib.stream_ptr(self.device)),
                    "td3_actor_step")
-        self._allreduce()
+        self._allreduce(0b001)
 
     def _adam(self, nets, polyak):
         # the optimiser kernel keeps the tensor-core copies in step once they exist and are current
@@ -566,8 +611,15 @@ class TD3:
                                                    _lib.ptr(self.adam_v), _lib.ptr(self.beta_pows), nets, self.actor_lr, self.critic_lr,
                                                    1.0 / self.world, polyak, self.tau, _lib.stream_ptr(self.device)), "td3_adam_polyak")
 
-    def _noise(self, shape):
-        return torch.randn(shape, dtype=torch.float32, device=self.device)      # torch.randn_like, robot.py:338 (unseeded there)
+    def _noise(self, rows):
+        """The unit normals `[rows,2]` the critic kernels would generate for the next step (`rtd3_td3_target_noise`: the same
+        Philox4x32-10 stream), for the single-step API; advances the step counter like an update of one epoch does."""
+        out = torch.empty((rows, 2), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().rtd3_td3_target_noise(self.noise_seed, self._noise_steps, _lib.ptr(out), rows, _lib.stream_ptr(self.device)),
+                   "td3_target_noise")
+        self._noise_steps += 1
+        self._noise_counter += 1
+        return out
 
     # ---- reference methods --------------------------------------------------------------------------------
     def train_critic(self, replay_buffer, noise=None, idx=None, q_out=None, y_out=None):
@@ -578,7 +630,7 @@ class TD3:
                 raise TypeError("cannot unpack non-iterable NoneType object")     # what the reference raises when under-filled
             idx = idx[0]
         idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
-        noise = self._noise((idx.numel(), 2)) if noise is None else noise.to(self.device, torch.float32).contiguous()
+        noise = self._noise(idx.numel()) if noise is None else noise.to(self.device, torch.float32).contiguous()
         loss2 = torch.zeros((2,), dtype=torch.float32, device=self.device)
         self.sync_transposed(force=False)
         self._critic_step(replay_buffer, idx, noise, loss2, q_out, y_out)
@@ -612,16 +664,33 @@ class TD3:
             self.tau = old_tau
 
     def _run_epochs(self, rb, idx, noise, closs, aloss):
-        """The epoch loop of robot.py:272-285 as a stream of kernel launches (capturable in a CUDA graph)."""
-        k = ka = 0
-        for e in range(self.num_epochs):
-            self._critic_step(rb, idx[k], noise[e], closs[e])
-            k += 1
-            if e % self.policy_update_delay == 0:
-                self._actor_step(rb, idx[k], aloss[ka:ka + 1])
-                k += 1
-                ka += 1
-                self._adam(nets=0b001, polyak=0b111)
+        """The epoch loop of robot.py:272-285: ONE call of `rtd3_td3_update`, which issues the step kernels, the gradient
+        all-reduces and the optimiser kernels on the current stream (capturable in a CUDA graph).  noise None: generated in the
+        critic kernels (Philox, keyed by the device step counter, which the call advances)."""
+        B = idx.shape[1]
+        tc = self._tc_learner_ok(B)
+        keep_uv = self.params_u is not None and not self._u_stale
+        if tc and not keep_uv:
+            raise RuntimeError("tensor-core operand copies are stale: call _sync_chunk_major() first")
+        if not keep_uv:
+            self._u_stale = True
+        self._h_stale = True
+        a = _lib.Td3UpdateArgs()
+        p = lambda t: None if t is None else t.data_ptr()
+        a.params, a.params_t, a.params_uv = p(self.params), p(self.params_t), p(self.params_u if keep_uv else None)
+        a.grads, a.adam_m, a.adam_v, a.scratch = p(self.grads), p(self.adam_m), p(self.adam_v), p(None if tc else self._row_scratch(B))
+        a.steps, a.beta_pows = p(self.steps), p(self.beta_pows)
+        a.rp_s, a.rp_a, a.rp_r, a.rp_s2, a.rp_notdone = p(rb.s), p(rb.a), p(rb.r), p(rb.s2), p(rb.notdone)
+        a.idx, a.batch, a.epochs, a.policy_update_delay = p(idx), B, self.num_epochs, self.policy_update_delay
+        a.noise, a.noise_seed, a.noise_counter = p(noise), self.noise_seed, p(self._noise_counter)
+        a.gamma, a.policy_noise, a.noise_clip, a.max_action = self.gamma, self.policy_noise, self.noise_clip, float(self.max_action)
+        a.lr_actor, a.lr_critic, a.tau = self.actor_lr, self.critic_lr, self.tau
+        a.critic_losses, a.actor_losses = p(closs), p(aloss)
+        a.world, a.tf32 = self.world, 1 if tc else 0
+        a.comm = self._comm if (self.world > 1 and self._p2p is None) else None
+        if self.world > 1 and self._p2p is not None:
+            a.p2p = ctypes.pointer(self._p2p["struct"])
+        _lib.check(_lib.lib().rtd3_td3_update(self._handle, ctypes.byref(a), _lib.stream_ptr(self.device)), "td3_update")
 
     def td3_update(self, replay_buffer, noise=None, idx=None, use_graph=True):
         """robot.py:258-285: `num_epochs` critic steps, an actor step + the three Polyak updates every
@@ -633,7 +702,7 @@ class TD3:
         while chunk g trains, so its cost hides behind the training kernels instead of preceding them."""
         E, B, delay = self.num_epochs, self.batch_size, self.policy_update_delay
         C = self.sample_chunk_epochs
-        if (idx is None and use_graph and self.world == 1 and C > 0 and E % C == 0 and C % delay == 0 and E > C
+        if (idx is None and use_graph and C > 0 and E % C == 0 and C % delay == 0 and E > C
                 and len(replay_buffer) >= B and getattr(replay_buffer, "sampler", "mt19937") == "mt19937"):   # the Philox draw costs microseconds: nothing to hide
             return self._td3_update_pipelined(replay_buffer, noise, C)
         n_actor = len([e for e in range(E) if e % delay == 0])
@@ -643,25 +712,23 @@ class TD3:
             if idx is None:
                 raise TypeError("cannot unpack non-iterable NoneType object")
         B = idx.shape[1]
-        st = self._update_state(replay_buffer, E, B, delay)
+        st = self._update_state(replay_buffer, E, B, delay, noise is not None)
         self.sync_transposed(force=False)
         st["idx"].copy_(idx)
-        if noise is None:
-            st["noise"].normal_()                                     # torch.randn_like, robot.py:338 (unseeded there)
-        else:
+        if noise is not None:                                         # injected (parity tests); else generated in the critic kernels
             st["noise"].copy_(noise)
         self._launch_epochs(replay_buffer, st, use_graph, E)
         self.last_losses = (st["closs"], st["aloss"][:n_actor])
         return self.last_losses
 
-    def _update_state(self, replay_buffer, E, B, delay):
+    def _update_state(self, replay_buffer, E, B, delay, injected_noise=False):
         """Persistent buffers (and, once captured, the CUDA graph) of an E-epoch block for this replay buffer / batch size."""
         n_actor = len([e for e in range(E) if e % delay == 0])
-        key = (id(replay_buffer), E, B, delay, self.precision, self._tc_learner_ok(B))
+        key = (id(replay_buffer), E, B, delay, self.precision, self._tc_learner_ok(B), bool(injected_noise))
         st = self._graphs.get(key)
         if st is None:
             st = {"idx": torch.zeros((E + n_actor, B), dtype=torch.int32, device=self.device),
-                  "noise": torch.zeros((E, B, 2), dtype=torch.float32, device=self.device),
+                  "noise": torch.zeros((E, B, 2), dtype=torch.float32, device=self.device) if injected_noise else None,
                   "closs": torch.zeros((E, 2), dtype=torch.float32, device=self.device),
                   "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None, "launches": 0}
             self._row_scratch(B)
@@ -674,15 +741,13 @@ class TD3:
         if tf32:
             self._sync_chunk_major()         # current before the loop; every optimiser step inside keeps it in step
         try:
-            # NCCL collectives are issued eagerly between the kernels: that data-parallel loop is not graph-captured.  The
-            # peer-memory all-reduce is a plain launch (its step counter lives in device memory) and is captured with the rest.
-            if use_graph and (self.world == 1 or self._p2p is not None):
+            # Both collectives of the data-parallel learner are plain stream operations (our own NCCL communicator, or the
+            # peer-memory kernel whose step counter lives in device memory): the update is ONE graph at any world size.
+            if use_graph:
                 if st["graph"] is None:
                     graph = torch.cuda.CUDAGraph()
                     before = _lib.launch_count()
                     with _lib.capture(graph):
-                        st["closs"].zero_()
-                        st["aloss"].zero_()
                         self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
                     st["graph"] = graph
                     st["launches"] = _lib.launch_count() - before      # kernels inside the graph (capture itself ran none)
@@ -690,9 +755,9 @@ class TD3:
                 st["graph"].replay()
                 _lib.lib().rtd3_launch_count_add(st["launches"])
             else:
-                st["closs"].zero_()
-                st["aloss"].zero_()
                 self._run_epochs(replay_buffer, st["idx"], st["noise"], st["closs"], st["aloss"])
+            if st["noise"] is None:
+                self._noise_steps += E       # host mirror of the device step counter the kernels just advanced
         finally:
             self.num_epochs = saved
             if not tf32:
@@ -706,11 +771,9 @@ class TD3:
         chunks = E // C
         n_actor_c = len([e for e in range(C) if e % delay == 0])
         per_chunk = C + n_actor_c
-        st = self._update_state(replay_buffer, C, B, delay)
+        st = self._update_state(replay_buffer, C, B, delay, noise is not None)
         closs = torch.empty((E, 2), dtype=torch.float32, device=self.device)
         aloss = torch.empty((chunks * n_actor_c,), dtype=torch.float32, device=self.device)
-        if noise is None:
-            noise = self._noise((E, B, 2))
         self.sync_transposed(force=False)
         main = torch.cuda.current_stream(self.device)
         if self._side_stream is None:
@@ -730,7 +793,8 @@ class TD3:
                 idx_g, ev = nxt
                 main.wait_event(ev)
                 st["idx"].copy_(idx_g)
-                st["noise"].copy_(noise[g * C:(g + 1) * C])
+                if noise is not None:
+                    st["noise"].copy_(noise[g * C:(g + 1) * C])
                 idx_g.record_stream(main)
                 if g + 1 < chunks:
                     nxt = draw(g + 1)                          # runs while chunk g trains (it only touches its scratch and the RNG bank)

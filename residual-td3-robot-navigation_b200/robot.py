@@ -114,6 +114,7 @@ class Robot:
                              critic_network_2=Residual_Critic_Network(**kw), device=dev, process_group=process_group,
                              dp_collective=dp_collective)
         self.num_updates = 0
+        self._snap = None
         # One shared learner serves all envs: an update runs once `episodes_per_update` env-episodes have ended since the last
         # one.  The default N keeps the reference's rhythm (every env finishes about one episode between updates) and is
         # exactly the reference for the single-env drop-in (robot.py:480-483).
@@ -147,7 +148,8 @@ class Robot:
         return self._type
 
     def maybe_update(self):
-        """Host half: read the finished-episode counter and run td3_update when due (robot.py:480-483)."""
+        """Host half: read the finished-episode counter and run td3_update when due (robot.py:480-483).  Synchronous: the host
+        waits for the device counter (and, data parallel, for the all-reduce of the ranks' counters)."""
         if self.td3_agent.world > 1:
             from .trainer import update_due
             due = update_due(self._any_update, self.episodes_per_update, self.td3_agent.process_group)
@@ -159,6 +161,37 @@ class Robot:
             self.num_updates += 1
             return True
         return False
+
+    def maybe_update_async(self):
+        """`maybe_update` without a host wait on the critical path.  Every call (a) looks at the counter snapshot the PREVIOUS call
+        put in flight - by now it has landed in pinned host memory, the device is already running the ticks enqueued since - and
+        runs td3_update when `episodes_per_update` (x world) episodes have ended, then (b) puts the next snapshot in flight: the
+        device moves the finished-episode counter into a staging word (data parallel: SUM-all-reduced over the ranks, so every rank
+        takes the same decision in the same call and enters the update's collectives together) and copies it to the host.
+        The decision therefore lags the device by one call (one block of `check_interval` ticks)."""
+        agent = self.td3_agent
+        if self._snap is None:
+            self._snap = {"dev": torch.zeros(1, dtype=torch.int64, device=self.device), "host": torch.zeros(1, dtype=torch.int64).pin_memory(),
+                          "event": None, "seen": 0}
+        snap = self._snap
+        ran = False
+        if snap["event"] is not None:
+            snap["event"].synchronize()
+            snap["seen"] += int(snap["host"][0])
+            if snap["seen"] >= self.episodes_per_update * agent.world:
+                snap["seen"] = 0
+                agent.td3_update(self.memory)
+                self.num_updates += 1
+                ran = True
+        snap["dev"].copy_(self._any_update)
+        self._any_update.zero_()
+        if agent.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(snap["dev"], op=dist.ReduceOp.SUM, group=agent.process_group)
+        snap["host"].copy_(snap["dev"], non_blocking=True)
+        snap["event"] = torch.cuda.Event()
+        snap["event"].record(torch.cuda.current_stream(self.device))
+        return ran
 
     def get_next_action_type(self, state, money_remaining):
         self.advance_action_types()

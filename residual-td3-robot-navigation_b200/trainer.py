@@ -77,7 +77,8 @@ class BatchedTrainer:
     noise: "mt19937" per-env numpy-legacy streams (exact mode); "randn" torch's generator; "philox" (fused only) normals
     generated inside `rtd3_tick_post` from (seed, device tick counter, env)."""
 
-    def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1, fused=False, philox_seed=0x5eed):
+    def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1, fused=False, philox_seed=0x5eed,
+                 async_check=False):
         if environment.num_envs != robot.num_envs:
             raise ValueError("environment and robot must hold the same envs")
         self.env, self.robot = environment, robot
@@ -101,6 +102,9 @@ class BatchedTrainer:
             raise ValueError("unknown noise mode %r" % (noise,))
         self.philox_seed = int(philox_seed)
         self.multi_tick_kernel = True         # run() may use rtd3_tick_run_f16 (see _multi_tick_ok)
+        # async_check: the "is a learner update due" test never makes the host wait for the device (Robot.maybe_update_async: the
+        # decision is taken from the counter snapshot of the previous block); False = the synchronous test after every block
+        self.async_check = bool(async_check)
         self._tick_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
 
     def money_remaining(self, tick_charge=0.0):
@@ -205,7 +209,7 @@ class BatchedTrainer:
                 self.ticks += K
                 done += K
                 self.env._state_np = None
-                self.robot.maybe_update()
+                self._maybe_update()
             elif self._use_graph and self.fused and K > 1 and self.ticks % K == 0 and ticks - done >= K:
                 self.robot.td3_agent.prepare_forward(self.n)
                 self._check_graphs()
@@ -224,10 +228,13 @@ class BatchedTrainer:
                 self.ticks += K
                 done += K
                 self.env._state_np = None
-                self.robot.maybe_update()
+                self._maybe_update()
             else:
                 self.tick()
                 done += 1
+
+    def _maybe_update(self):
+        return self.robot.maybe_update_async() if self.async_check else self.robot.maybe_update()
 
     def _check_graphs(self):
         """A captured tick holds the device pointers of the demonstration set and the choice of forward kernel: drop the graphs
@@ -264,7 +271,7 @@ class BatchedTrainer:
         self.ticks += 1
         self.env._state_np = None                                             # the kernels moved the state under the host cache
         if self.ticks % self.check_interval == 0:
-            self.robot.maybe_update()                                         # robot-learning.py:68 -> robot.py:480-483
+            self._maybe_update()                                         # robot-learning.py:68 -> robot.py:480-483
         return types
 
 

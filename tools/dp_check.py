@@ -14,7 +14,7 @@ def main():
     H, L, B = 256, 2, 256
     torch.manual_seed(0)
     def agent(pg, batch):
-        torch.manual_seed(0)
+        torch.manual_seed(0 if pg is None else rank)      # ranks start from DIFFERENT weights: the constructor broadcasts rank 0's
         return rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L), batch_size=batch,
                       process_group=pg, num_epochs=6)
     n = 5000
