@@ -98,7 +98,44 @@ def test_new_entry_points_reject_bad_arguments_without_a_gpu(pkg):
     assert L.rtd3_mlp_forward_f16(256, 3, 0, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 128, None) == -1
     assert L.rtd3_mlp_forward_f16(256, 2, 6, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 128, None) == -1
     ptrs = (ctypes.c_void_p * 2)(0, 0)
-    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 1, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # world 1
-    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 9, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # world 9
-    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 6, ctypes.byref(one), None) == -1    # count % 4
-    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, ctypes.byref(one), None) == -1   # null peers
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 1, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, 16, ctypes.byref(one), None) == -1   # world 1
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 9, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, 16, ctypes.byref(one), None) == -1   # world 9
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 6, 16, ctypes.byref(one), None) == -1    # count % 4
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, 16, ctypes.byref(one), None) == -1   # null peers
+    assert L.rtd3_p2p_allreduce(ptrs, ptrs, 0, 2, ctypes.byref(one), ctypes.byref(one), ctypes.byref(one), 16, 8, ctypes.byref(one), None) == -1    # slot < count
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu(pkg):
+    """rtd3_td3_update / rtd3_comm_* / rtd3_allreduce_grads / rtd3_td3_target_noise check their arguments before touching a device."""
+    L, lib = pkg._lib.lib(), pkg._lib
+    a = lib.Td3UpdateArgs()
+    assert L.rtd3_td3_update(None, ctypes.byref(a), None) == -1
+    assert L.rtd3_allreduce_grads(None, None, 4, None) == -1
+    assert L.rtd3_comm_unique_id(None) == -1
+    assert L.rtd3_comm_create(None, None, 0, 1, 0) == -1
+    assert L.rtd3_comm_world(None) == -1 and L.rtd3_comm_rank(None) == -1 and L.rtd3_comm_destroy(None) == 0
+    assert L.rtd3_td3_target_noise(1, 2, None, 8, None) == -1
+    assert L.rtd3_comm_nccl_version() >= 20000          # resolved at run time from the NCCL copy torch ships
+
+
+def test_ctypes_structs_match_the_header_layout(pkg, tmp_path):
+    """The HOST structs of the ABI as ctypes sees them == as a C compiler lays them out from include/rtd3.h (sizeof + every offset)."""
+    import subprocess
+    lib = pkg._lib
+    structs = {"rtd3_tick_state": lib.TickStateStruct, "rtd3_td3_update_args": lib.Td3UpdateArgs, "rtd3_p2p_state": lib.P2pStateStruct,
+               "rtd3_mt_bank": lib.MtBankStruct}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rtd3.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for field, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, field, cname, field))
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, field)]) == getattr(cls, field).offset, (cname, field)
