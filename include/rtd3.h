@@ -100,6 +100,9 @@ int32_t rtd3_mt_seed(const rtd3_mt_bank* bank, const uint32_t* seeds, void* stre
 int32_t rtd3_mt_draw_u32(const rtd3_mt_bank* bank, uint32_t* out, int64_t k, void* stream);
 /* np.random.normal(0,1) draws (legacy polar method with spare): out[k][n] float64. */
 int32_t rtd3_mt_draw_gauss(const rtd3_mt_bank* bank, double* out, int64_t k, void* stream);
+/* The same for the streams i with where[i] == equals only (where: DEVICE int8 [n], e.g. the tick types: the reference draws its
+ * exploration noise on 'step' ticks only); the other streams are not advanced and receive zeros.  where == NULL: all streams. */
+int32_t rtd3_mt_draw_gauss_where(const rtd3_mt_bank* bank, double* out, int64_t k, const int8_t* where, int32_t equals, void* stream);
 
 /* Environment.set_init_and_goal (environment.py:28-56) for n envs, each on its own stream.
  * goal [2][n] float64, region [4][n] float64 = left,right,bottom,top.  Bit-exact vs numpy. */
@@ -410,17 +413,33 @@ typedef struct rtd3_tick_state {
   /* money counters (robot-learning.py:78, 86, 99) */
   int64_t* steps_bought;        /* [n] */
   int64_t* resets_bought;       /* [n] */
-  /* exploration noise of mode RTD3_TICK_NOISE_PHILOX: normals = f(philox_seed, tick_counter[0], env) */
+  /* exploration noise of mode RTD3_TICK_NOISE_PHILOX: normals = f(philox_seed, ticks run incl. this one, env) */
   uint64_t philox_seed;
-  uint64_t* tick_counter;       /* nullable [1]; incremented by rtd3_tick_pre */
+  uint64_t* tick_counter;       /* nullable [2]: word 0 = ticks completed (advanced by rtd3_tick_post), word 1 = scratch of the tick in flight */
+  /* Scheduler of the driver loop (robot-learning.py:45-50 money, :66-103 purchase gates and the switch to testing, :104-117 test
+   * branch).  mode == NULL: training branch only, every purchase goes through (the arrays below are then ignored). */
+  uint8_t* mode;                /* [n] 0 training, 1 testing, 2 finished */
+  int64_t* demos_bought;        /* [n] */
+  int32_t* test_ticks;          /* [n] ticks spent in testing */
+  double* test_best;            /* [n] best distance to the goal seen in testing (initialise to +inf) */
+  uint8_t* test_success;        /* [n] reached the goal: distance <= 5 (constants.py:50) */
+  uint8_t* penalty;             /* [n] overspent by more than 1 at the switch (robot-learning.py:73-75) */
+  double tick_seconds;          /* deterministic stand-in for the wall-clock money term: cpu_time = ticks elapsed * tick_seconds */
+  int64_t test_timeout_ticks;   /* TEST_TIMEOUT (constants.py:53, compared with wall time at robot-learning.py:115) in ticks */
 } rtd3_tick_state;
+
+/* values of rtd3_tick_state.type beyond 0 'step' / 1 'demo' / 2 'reset' (scheduler only) */
+#define RTD3_TICK_TYPE_SWITCH 3    /* money < 0: environment.reset() and on to testing (robot-learning.py:70-80) */
+#define RTD3_TICK_TYPE_SKIP 4      /* the purchase was not affordable: nothing happens in this tick */
+#define RTD3_TICK_TYPE_TEST 5      /* a test step: get_next_action_testing, step, distance check (robot-learning.py:104-117) */
+#define RTD3_TICK_TYPE_IDLE 6      /* the env's run is over */
 
 #define RTD3_TICK_NOISE_NONE 0     /* get_next_action_testing: no exploration noise (robot.py:575-595) */
 #define RTD3_TICK_NOISE_GIVEN 1    /* unit normals supplied ([2][n] float64, e.g. rtd3_mt_draw_gauss: numpy-exact) */
 #define RTD3_TICK_NOISE_PHILOX 2   /* unit normals generated in the kernel (Philox4x32-10 + Box-Muller, throughput mode) */
 
-/* First half of a tick: rtd3_robot_next_action_type (robot.py:443-506; robot-learning.py:68) and rtd3_robot_baseline
- * (robot.py:556) in one launch.  The caller then runs the actor forward on t->base. */
+/* First half of a tick: rtd3_robot_next_action_type (robot.py:443-506; robot-learning.py:68), the scheduler's purchase gates when
+ * t->mode is set, and rtd3_robot_baseline (robot.py:556) in one launch.  The caller then runs the actor forward on t->base. */
 int32_t rtd3_tick_pre(const rtd3_tick_state* t, void* stream);
 
 /* Second half, one launch: rtd3_robot_compose_action (robot.py:560-567), rtd3_env_step (environment.py:122-127),

@@ -8,7 +8,7 @@ from .environment import Environment, synthetic_maps  # noqa: F401
 from .rng import MtBank  # noqa: F401
 from .learner import ReplayBuffer, Residual_Actor_Network, Residual_Critic_Network, TD3  # noqa: F401
 from .robot import Robot  # noqa: F401
-from .trainer import BatchedTrainer, shard_range  # noqa: F401
+from .trainer import BatchedTrainer, DriverLoop, shard_range  # noqa: F401
 
 __all__ = ["Environment", "MtBank", "synthetic_maps", "constants", "configuration", "ReplayBuffer", "Residual_Actor_Network",
-           "Residual_Critic_Network", "TD3", "Robot", "BatchedTrainer", "shard_range"]
+           "Residual_Critic_Network", "TD3", "Robot", "BatchedTrainer", "DriverLoop", "shard_range"]

@@ -32,10 +32,13 @@ class TickStateStruct(Structure):
                 + [("num_demo", c_int64)]
                 + [(k, c_void_p) for k in ("rp_s", "rp_a", "rp_r", "rp_s2", "rp_notdone")]
                 + [("capacity", c_int64), ("rp_total", c_void_p), ("steps_bought", c_void_p), ("resets_bought", c_void_p),
-                   ("philox_seed", c_uint64), ("tick_counter", c_void_p)])
+                   ("philox_seed", c_uint64), ("tick_counter", c_void_p)]
+                + [(k, c_void_p) for k in ("mode", "demos_bought", "test_ticks", "test_best", "test_success", "penalty")]
+                + [("tick_seconds", c_double), ("test_timeout_ticks", c_int64)])
 
 
 TICK_NOISE_NONE, TICK_NOISE_GIVEN, TICK_NOISE_PHILOX = 0, 1, 2
+TICK_TYPE_STEP, TICK_TYPE_DEMO, TICK_TYPE_RESET, TICK_TYPE_SWITCH, TICK_TYPE_SKIP, TICK_TYPE_TEST, TICK_TYPE_IDLE = range(7)
 COMM_ID_BYTES = 128
 
 
@@ -73,6 +76,7 @@ _SIGNATURES = {
     "rtd3_mt_seed": (c_int32, [POINTER(MtBankStruct), _P, _P]),
     "rtd3_mt_draw_u32": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
     "rtd3_mt_draw_gauss": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P]),
+    "rtd3_mt_draw_gauss_where": (c_int32, [POINTER(MtBankStruct), _P, c_int64, _P, c_int32, _P]),
     "rtd3_env_init_goal_region": (c_int32, [POINTER(MtBankStruct), _P, _P, _P]),
     "rtd3_env_reset": (c_int32, [POINTER(MtBankStruct), _P, _P, c_int32, _P, _P, _P, _P]),
     "rtd3_replay_push": (c_int32, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
@@ -178,7 +182,9 @@ class capture:
     launch; whether it happened depended on how much garbage earlier code had produced)."""
 
     def __init__(self, graph):
-        self._ctx = torch.cuda.graph(graph)
+        # thread_local: only THIS thread's unsafe CUDA calls invalidate the capture.  The default ("global") also forbids them to
+        # every other thread of the process for the duration - e.g. the service threads of an NCCL communicator, which then fail.
+        self._ctx = torch.cuda.graph(graph, capture_error_mode="thread_local")
 
     def __enter__(self):
         import gc

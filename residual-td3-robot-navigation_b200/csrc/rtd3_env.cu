@@ -487,11 +487,16 @@ __global__ void mt_draw_u32_kernel(rtd3_mt_bank b, uint32_t* __restrict__ out, i
   b.pos[i] = s.pos;
 }
 
-__global__ void mt_draw_gauss_kernel(rtd3_mt_bank b, double* __restrict__ out, int64_t k) {
+__global__ void mt_draw_gauss_kernel(rtd3_mt_bank b, double* __restrict__ out, int64_t k, const int8_t* __restrict__ where, int equals) {
   // legacy_gauss (rtd3_mt.cuh: mt_gauss) for one stream per lane, warp-synchronous so that wrapping streams are twisted by the whole
   // warp: this is the exploration noise of every tick in the exact-noise mode, and ~1 % of the streams wrap per call
+  // `where` (nullable): only the streams with where[i] == equals draw - the others keep their position and get zeros (the
+  // reference draws its exploration noise on 'step' ticks only, robot.py:560 via robot-learning.py:97)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < b.n;
+  const bool inside = i < b.n;
+  const bool active = inside && (!where || (int)where[i] == equals);
+  if (inside && !active)
+    for (int64_t j = 0; j < k; ++j) out[j * b.n + i] = 0.0;
   if (!__any_sync(0xffffffffu, active)) return;
   const int64_t ii = active ? i : 0;
   MtStream s{b.mt + ii, b.n, active ? b.pos[ii] : 0};
@@ -773,10 +778,14 @@ int32_t rtd3_mt_draw_u32(const rtd3_mt_bank* bank, uint32_t* out, int64_t k, voi
 }
 
 int32_t rtd3_mt_draw_gauss(const rtd3_mt_bank* bank, double* out, int64_t k, void* stream) {
+  return rtd3_mt_draw_gauss_where(bank, out, k, nullptr, 0, stream);
+}
+
+int32_t rtd3_mt_draw_gauss_where(const rtd3_mt_bank* bank, double* out, int64_t k, const int8_t* where, int32_t equals, void* stream) {
   if (int32_t e = check_bank(bank)) return e;
   RTD3_CHECK_ARG(out && k >= 0, "bad out/k");
   if (bank->n == 0 || k == 0) return 0;
-  mt_draw_gauss_kernel<<<(int)ceil_div(bank->n, 128), 128, 0, (cudaStream_t)stream>>>(*bank, out, k);
+  mt_draw_gauss_kernel<<<(int)ceil_div(bank->n, 128), 128, 0, (cudaStream_t)stream>>>(*bank, out, k, where, equals);
   RTD3_LAUNCHED();
   return 0;
 }

@@ -17,19 +17,64 @@
 
 namespace rtd3 {
 
+// Tick types: 0 'step', 1 'demo', 2 'reset' (what get_next_action_type returned, and - with the scheduler - the purchase went through),
+// 3 training budget exhausted: environment.reset() and on to testing (robot-learning.py:70-80), 4 not affordable: nothing happens this
+// tick (robot-learning.py:86-87, 93-94, 96), 5 a test step (robot-learning.py:104-117), 6 the env's run is over.
+constexpr int kTypeSwitch = RTD3_TICK_TYPE_SWITCH, kTypeSkip = RTD3_TICK_TYPE_SKIP, kTypeTest = RTD3_TICK_TYPE_TEST,
+              kTypeIdle = RTD3_TICK_TYPE_IDLE;
+constexpr double kStartingMoney = 100.0, kCostStep = 0.01, kCostCpuSecond = 0.03;   // constants.py:43-45
+constexpr long long kCostDemo = 20, kCostReset = 5;                                   // constants.py:46-47
+constexpr double kTestDistance = 5.0;                                                 // constants.py:50
+
+// calculate_remaining_money (robot-learning.py:45-50) with the wall clock replaced by ticks * tick_seconds: Python adds the two
+// integer products first, then the two float products, left to right
+__device__ __forceinline__ double money_remaining(long long demos, long long resets, long long steps, uint64_t ticks, double tick_seconds) {
+  const double cpu = __dmul_rn((double)ticks, tick_seconds);
+  const double spent = __dadd_rn(__dadd_rn((double)(demos * kCostDemo + resets * kCostReset), __dmul_rn((double)steps, kCostStep)),
+                                 __dmul_rn(cpu, kCostCpuSecond));
+  return __dsub_rn(kStartingMoney, spent);
+}
+
+// The training / testing dispatch of update(dt) (robot-learning.py:66-103) for env i at tick `tick_index` (ticks elapsed before this
+// one).  Without the scheduler arrays (t.mode == NULL) it is get_next_action_type alone: every purchase goes through.
+__device__ __forceinline__ int schedule_env(const rtd3_tick_state& t, const int64_t i, const uint64_t tick_index, bool& upd) {
+  upd = false;
+  if (t.mode) {
+    const int mode = t.mode[i];
+    if (mode == 1) return kTypeTest;
+    if (mode == 2) return kTypeIdle;
+  }
+  int type = action_type_env(t.num_episodes, t.demo_flag, t.plan_index, t.path_length, t.goal_reached, t.stuck_flag, t.noise_scale, i, upd);
+  if (!t.mode) return type;
+  const double money = money_remaining(t.demos_bought[i], t.resets_bought[i], t.steps_bought[i], tick_index, t.tick_seconds);
+  if (money < 0.0) {                                       // robot-learning.py:70-80
+    if (money < -1.0) t.penalty[i] = 1;
+    t.mode[i] = 1;
+    return kTypeSwitch;
+  }
+  if (type == 2) return money >= (double)kCostReset ? 2 : kTypeSkip;
+  if (type == 1) {
+    if (!(money >= (double)kCostDemo)) return kTypeSkip;
+    t.demos_bought[i] += 1;                                // robot-learning.py:92 (the demonstration itself is the caller's job)
+    return 1;
+  }
+  return money >= kCostStep ? 0 : kTypeSkip;
+}
+
 __global__ void __launch_bounds__(256) tick_pre_kernel(rtd3_tick_state t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = t.n;
   bool upd = false;
   if (i < n) {
-    t.type[i] = (int8_t)action_type_env(t.num_episodes, t.demo_flag, t.plan_index, t.path_length, t.goal_reached, t.stuck_flag,
-                                        t.noise_scale, i, upd);
+    t.type[i] = (int8_t)schedule_env(t, i, t.tick_counter ? t.tick_counter[0] : 0ull, upd);
     t.update[i] = upd ? 1 : 0;
     reinterpret_cast<float2*>(t.base)[i] = baseline_env(t.x[i], t.y[i], t.goal[i], t.goal[n + i]);
   }
   const uint32_t ended = __ballot_sync(0xffffffffu, upd);
   if (ended && (threadIdx.x & 31) == 0) atomicAdd(t.any_update, __popc(ended));
-  if (i == 0 && t.tick_counter) t.tick_counter[0] += 1ull;
+  // tick counter: every thread of this kernel reads word 0 (ticks completed), so the advanced value goes to word 1, which
+  // tick_post_kernel reads (all threads) and copies back to word 0 - no kernel writes a word its other blocks read
+  if (i == 0 && t.tick_counter) t.tick_counter[1] = t.tick_counter[0] + 1ull;
 }
 
 // Second half of a tick for env i (`in`: i < n; whole warps call this): compose the action from the actor's residual, step,
@@ -41,9 +86,11 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
   const int64_t n = t.n;
   const int64_t ii = in ? i : 0;
   const bool live = in && type == 0;
+  const bool testing = in && type == kTypeTest;
+  const bool resets = in && (type == 2 || type == kTypeSwitch);
   const float x = t.x[ii], y = t.y[ii];
   // the 'reset' envs' draws: loads issued now, consumed after the transition work (they do not depend on it)
-  ResetLoads rl = reset_load_warp(t.env_bank, t.region, in && type == 2, i);
+  ResetLoads rl = reset_load_warp(t.env_bank, t.region, resets, i);
   const int64_t steps_before = (in && type == 0) ? t.steps_bought[i] : 0, resets_before = (in && type == 2) ? t.resets_bought[i] : 0;
   // get_next_action_training: envs that do not step in this tick get a null action (robot-learning.py:82-95)
   float ax = 0.f, ay = 0.f;
@@ -54,6 +101,11 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
     double cx, cy;
     compose_env(x, y, t.goal[i], t.goal[n + i], res, noise_mode != RTD3_TICK_NOISE_NONE, zx, zy,
                 noise_mode != RTD3_TICK_NOISE_NONE ? t.noise_scale[i] : 0.0, cx, cy);
+    ax = (float)cx;
+    ay = (float)cy;
+  } else if (testing) {                                   // get_next_action_testing: no exploration noise (robot.py:572-595)
+    double cx, cy;
+    compose_env(x, y, t.goal[i], t.goal[n + i], res, false, 0.0, 0.0, 0.0, cx, cy);
     ax = (float)cx;
     ay = (float)cy;
   }
@@ -75,8 +127,18 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
     if (type == 0) t.steps_bought[i] = steps_before + 1;
     else if (type == 2) t.resets_bought[i] = resets_before + 1;
   }
+  if (testing) {                                          // robot-learning.py:107-117
+    const double dist = norm2_np(__dsub_rn((double)nx, t.goal[i]), __dsub_rn((double)ny, t.goal[n + i]));
+    const int ticks = t.test_ticks[i] + 1;
+    t.test_ticks[i] = ticks;
+    bool over = false;
+    if (dist <= kTestDistance) { t.test_success[i] = 1; over = true; }
+    if (dist < t.test_best[i]) t.test_best[i] = dist;
+    if ((int64_t)ticks >= t.test_timeout_ticks) over = true;
+    if (over) t.mode[i] = 2;
+  }
   // Environment.reset where the tick is a 'reset' (warp-synchronous: wrapping MT19937 streams are twisted by the whole warp)
-  reset_finish_warp(t.env_bank, in && type == 2, i, rl, t.x, t.y, t.state64);
+  reset_finish_warp(t.env_bank, resets, i, rl, t.x, t.y, t.state64);
 }
 
 __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, const float2* __restrict__ table,
@@ -85,8 +147,10 @@ __global__ void __launch_bounds__(256, 2) tick_post_kernel(rtd3_tick_state t, co
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = i < t.n;
   const int64_t ii = in ? i : 0;
-  tick_post_env<true>(t, table, i, in, in ? (int)t.type[ii] : 1, reinterpret_cast<const float2*>(residual)[ii], unit_noise, noise_mode,
-                      t.tick_counter ? t.tick_counter[0] : 0ull);
+  // the Philox noise of a tick is keyed by the number of ticks run including this one (word 1 of the counter, see tick_pre_kernel)
+  const uint64_t tick_index = t.tick_counter ? t.tick_counter[1] : 0ull;
+  tick_post_env<true>(t, table, i, in, in ? (int)t.type[ii] : 1, reinterpret_cast<const float2*>(residual)[ii], unit_noise, noise_mode, tick_index);
+  if (i == 0 && t.tick_counter) t.tick_counter[0] = tick_index;
 }
 
 // ---- K ticks in ONE launch (actor 2 -> H -> H -> 2 on the f16 resident-weight forward, rtd3_tc_f16.cuh) -------------------------
@@ -137,7 +201,7 @@ tick_f16_kernel(rtd3_tick_state t, const float2* __restrict__ table, NetShape s,
           bool upd = false;
           float2 base = make_float2(0.f, 0.f);
           if (in) {
-            type = action_type_env(t.num_episodes, t.demo_flag, t.plan_index, t.path_length, t.goal_reached, t.stuck_flag, t.noise_scale, i, upd);
+            type = schedule_env(t, i, tick_base + (uint64_t)k, upd);
             t.type[i] = (int8_t)type;
             t.update[i] = upd ? 1 : 0;
             base = baseline_env(t.x[i], t.y[i], t.goal[i], t.goal[n + i]);
@@ -166,7 +230,7 @@ tick_f16_kernel(rtd3_tick_state t, const float2* __restrict__ table, NetShape s,
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
-  if (blockIdx.x == 0 && tid == 0 && t.tick_counter) t.tick_counter[0] = tick_base + (uint64_t)K;   // as K launches of rtd3_tick_pre leave it
+  if (blockIdx.x == 0 && tid == 0 && t.tick_counter) t.tick_counter[0] = t.tick_counter[1] = tick_base + (uint64_t)K;   // as K ticks leave it
 }
 
 static int32_t check_state(const rtd3_tick_state* t) {
@@ -184,6 +248,11 @@ static int32_t check_state(const rtd3_tick_state* t) {
   RTD3_CHECK_ARG(t->rp_s && t->rp_a && t->rp_r && t->rp_s2 && t->rp_notdone && t->rp_total && t->capacity > 0 && t->n <= t->capacity,
                  "bad replay ring");
   RTD3_CHECK_ARG(t->steps_bought && t->resets_bought, "null money counters");
+  if (t->mode) {
+    RTD3_CHECK_ARG(t->demos_bought && t->test_ticks && t->test_best && t->test_success && t->penalty, "scheduler arrays missing (mode is set)");
+    RTD3_CHECK_ARG(t->tick_counter, "the scheduler charges time per tick: tick_counter is required");
+    RTD3_CHECK_ARG(t->tick_seconds >= 0.0 && t->test_timeout_ticks > 0, "bad tick_seconds / test_timeout_ticks");
+  }
   return 0;
 }
 

@@ -30,6 +30,7 @@ TD3_BATCH_SIZE = 100
 GAMMA = 0.99
 TAU = 0.001
 
+_COMMS = {}                          # (process group id, device) -> rtd3_comm handle (see TD3._setup_comm)
 DEFAULT_DP_COLLECTIVE = "nccl"       # "nccl": rtd3_allreduce_grads on our own communicator; "p2p": rtd3_p2p_allreduce (peer memory)
 
 HIDDEN = 200     # robot.py:145-148
@@ -380,6 +381,12 @@ class TD3:
         import torch.distributed as dist
         pg = self.process_group
         rank = dist.get_rank(pg)
+        # ONE communicator per (process group, device) for the life of the process, shared by every learner built on it: creating
+        # and destroying communicators is itself collective, and Python finalises learners at unpredictable, rank-dependent points
+        key = (id(pg), self.device.index or 0)
+        if key in _COMMS:
+            self._comm = _COMMS[key]
+            return
         ident = [None]
         if rank == 0:
             buf = (ctypes.c_uint8 * _lib.COMM_ID_BYTES)()
@@ -390,6 +397,7 @@ class TD3:
         self._comm = ctypes.c_void_p()
         torch.cuda.synchronize(self.device)
         _lib.check(_lib.lib().rtd3_comm_create(ctypes.byref(self._comm), buf, rank, self.world, self.device.index or 0), "comm_create")
+        _COMMS[key] = self._comm
         # first collective outside of any capture (connection set-up allocates)
         _lib.check(_lib.lib().rtd3_allreduce_grads(self._comm, _lib.ptr(self.grads), self.grads.numel(), _lib.stream_ptr(self.device)),
                    "allreduce_grads (warm-up)")
@@ -441,9 +449,6 @@ class TD3:
 
     def __del__(self):
         try:
-            if getattr(self, "_comm", None):
-                _lib.lib().rtd3_comm_destroy(self._comm)
-                self._comm = None
             if getattr(self, "_handle", None):
                 _lib.lib().rtd3_td3_destroy(self._handle)
                 self._handle = None

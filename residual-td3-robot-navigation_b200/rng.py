@@ -48,9 +48,12 @@ class MtBank:
         _lib.check(_lib.lib().rtd3_mt_draw_u32(self.ref, _lib.ptr(out), k, _lib.stream_ptr(self.device)), "mt_draw_u32")
         return out
 
-    def draw_gauss(self, k):
+    def draw_gauss(self, k, where=None, equals=0):
+        """k legacy normals per stream `[k,n]`; `where` (int8 `[n]`) restricts the draw to the streams with where == equals (the
+        others are not advanced and get zeros)."""
         out = torch.empty((k, self.n), dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib().rtd3_mt_draw_gauss(self.ref, _lib.ptr(out), k, _lib.stream_ptr(self.device)), "mt_draw_gauss")
+        _lib.check(_lib.lib().rtd3_mt_draw_gauss_where(self.ref, _lib.ptr(out), k, _lib.ptr(where), int(equals), _lib.stream_ptr(self.device)),
+                   "mt_draw_gauss_where")
         return out
 
     # ---- numpy global-state mirroring (single stream) ----

@@ -247,11 +247,13 @@ class Robot:
             return self._action.t()
         return self._action64[:, 0].cpu().numpy()
 
-    def generate_noise(self, shape=None):
-        """Unit normals `[2,N]` float64 in the order np.random.normal draws them (robot.py:640: x then y per env)."""
+    def generate_noise(self, shape=None, types=None):
+        """Unit normals `[2,N]` float64 in the order np.random.normal draws them (robot.py:640: x then y per env).  `types` (batched:
+        the tick's action types): only the envs whose type is 'step' draw - the reference calls generate_noise on 'step' ticks
+        only, so an env's stream advances exactly as its own reference run would."""
         if self._numpy_global:
             self._bank.sync_from_numpy()
-        z = self._bank.draw_gauss(2)
+        z = self._bank.draw_gauss(2, where=types, equals=0)
         if self._numpy_global:
             self._bank.sync_to_numpy()
         return z
@@ -260,7 +262,7 @@ class Robot:
         """`noise`: optional injected unit normals `[2,N]` float64 (tests / throughput mode); default draws them from the
         MT19937 streams.  `types` (batched): the tensor get_next_action_type returned - envs that are not stepping in
         this tick get a null action."""
-        z = self.generate_noise() if noise is None else noise.to(self.device, torch.float64).contiguous()
+        z = self.generate_noise(types=types) if noise is None else noise.to(self.device, torch.float64).contiguous()
         return self._act(state, z, types)
 
     def get_next_action_testing(self, state):

@@ -63,6 +63,123 @@ def update_due(local_count, episodes_per_update, group=None):
     return int(local_count.item()) >= int(episodes_per_update)
 
 
+class DriverLoop:
+    """The reference's driver, robot-learning.py:19-117, for ONE env, without pyglet: `update()` is the body of `update(dt)` with the
+    script's globals as attributes (`mode, demos_bought, resets_bought, steps_bought, test_best_distance, penalty, state`).  It calls
+    the drop-in `Environment` / `Robot` hooks exactly where the script calls the reference's, so with a numpy `[2]` goal the numpy
+    global stream is consumed as in the reference.  Two deliberate differences, both for determinism: the wall-clock term of
+    `calculate_remaining_money` (robot-learning.py:47) is `ticks x tick_seconds` (default 1/UPDATE_RATE s, the interval the script
+    schedules `update` at) instead of `time.time()`, and the test time-out (robot-learning.py:115) is counted in the same ticks;
+    `pyglet.app.exit()` becomes `finished = True`."""
+
+    def __init__(self, environment, robot, state=None, tick_seconds=None, verbose=False):
+        self.environment, self.robot = environment, robot
+        self.state = environment.reset() if state is None else state          # robot-learning.py:22
+        self.mode = "training"
+        self.demos_bought = self.resets_bought = self.steps_bought = 0
+        self.test_ticks = 0
+        self.test_best_distance = float("inf")
+        self.penalty = False
+        self.success = False
+        self.finished = False
+        self.ticks = 0                                                        # update() calls so far = the deterministic clock
+        self.tick_seconds = (1.0 / constants.UPDATE_RATE) if tick_seconds is None else float(tick_seconds)
+        self.test_timeout_ticks = max(1, int(round(constants.TEST_TIMEOUT / self.tick_seconds))) if self.tick_seconds > 0 else 1000
+        self.verbose = verbose
+        self.last_action_type = None
+
+    @classmethod
+    def from_seed(cls, seed=None, maps=None, **kw):
+        """robot-learning.py:19-24: seed numpy's global stream, build the environment, reset it, build the robot on its goal."""
+        import numpy as np
+        from . import configuration
+        from .environment import Environment
+        from .robot import Robot
+        np.random.seed(configuration.RANDOM_SEED if seed is None else seed)
+        environment = Environment(maps=maps)
+        state = environment.reset()
+        return cls(environment, Robot(environment.goal_state), state, **kw)
+
+    def _say(self, msg):
+        if self.verbose:
+            print(msg)
+
+    def calculate_remaining_money(self):
+        c = constants
+        cpu_time_bought = self.ticks * self.tick_seconds
+        money_spent = (self.demos_bought * c.COST_PER_DEMO + self.resets_bought * c.COST_PER_RESET + self.steps_bought * c.COST_PER_STEP
+                       + cpu_time_bought * c.COST_PER_CPU_SECOND)
+        return c.STARTING_MONEY - money_spent
+
+    def update(self):
+        """One call of update(dt) (robot-learning.py:54-117).  Returns the action type of a training tick, 'test' for a test step,
+        None once the run is over."""
+        import numpy as np
+        c = constants
+        environment, robot = self.environment, self.robot
+        if self.finished:
+            return None
+        if self.mode == "training":
+            money_remaining = self.calculate_remaining_money()
+            action_type = robot.get_next_action_type(self.state, money_remaining)
+            money_remaining = self.calculate_remaining_money()
+            self.ticks += 1
+            self.last_action_type = action_type
+            if money_remaining < 0:
+                if money_remaining < -1.0:
+                    self._say("You have overspent by more than 1! A 10% penalty will be applied to the score.")
+                    self.penalty = True
+                self.state = environment.reset()
+                self.mode = "testing"
+                self._say("Training has finished, moving to testing.")
+                return "switch"
+            if action_type == "reset":
+                if money_remaining >= c.COST_PER_RESET:
+                    self.state = environment.reset()
+                    self.resets_bought += 1
+                else:
+                    self._say("Insufficient money to buy a reset.")
+            elif action_type == "demo":
+                if money_remaining >= c.COST_PER_DEMO:
+                    demonstration_states, demonstration_actions = environment.get_demonstration()
+                    robot.process_demonstration(demonstration_states, demonstration_actions, money_remaining)
+                    self.demos_bought += 1
+                else:
+                    self._say("Insufficient money to buy a demo.")
+            elif action_type == "step":
+                if money_remaining >= c.COST_PER_STEP:
+                    action = robot.get_next_action_training(self.state, money_remaining)
+                    next_state = environment.step(action)
+                    robot.process_transition(self.state, action, next_state, money_remaining)
+                    self.state = next_state
+                    self.steps_bought += 1
+            else:
+                raise ValueError("Invalid value for action_type: %s" % (action_type,))
+            return action_type
+        action = robot.get_next_action_testing(self.state)
+        next_state = environment.step(action)
+        distance = np.linalg.norm(next_state - environment.goal_state)
+        self.state = next_state
+        self.test_ticks += 1
+        if distance <= c.TEST_DISTANCE_THRESHOLD:
+            self._say("The robot reached the goal! Time: %s." % (self.test_ticks * self.tick_seconds,))
+            self.success = self.finished = True
+        if distance < self.test_best_distance:
+            self.test_best_distance = distance
+        if self.test_ticks >= self.test_timeout_ticks:
+            self._say("The robot did not reach the goal in time. Best distance: %s." % (self.test_best_distance,))
+            self.finished = True
+        return "test"
+
+    def run(self, max_ticks=None):
+        """Call update() until the run is over (or `max_ticks` calls); returns the number of calls made."""
+        k = 0
+        while not self.finished and (max_ticks is None or k < max_ticks):
+            self.update()
+            k += 1
+        return k
+
+
 class BatchedTrainer:
     """`graph=True` captures the device work of one tick (state machine, act, step, transition + replay push, masked reset)
     in a CUDA graph and looks at the finished-episode counter only every `check_interval` ticks, so the tick costs one graph
@@ -78,7 +195,7 @@ class BatchedTrainer:
     generated inside `rtd3_tick_post` from (seed, device tick counter, env)."""
 
     def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1, fused=False, philox_seed=0x5eed,
-                 async_check=False):
+                 async_check=False, scheduler=False, tick_seconds=None):
         if environment.num_envs != robot.num_envs:
             raise ValueError("environment and robot must hold the same envs")
         self.env, self.robot = environment, robot
@@ -105,11 +222,49 @@ class BatchedTrainer:
         # async_check: the "is a learner update due" test never makes the host wait for the device (Robot.maybe_update_async: the
         # decision is taken from the counter snapshot of the previous block); False = the synchronous test after every block
         self.async_check = bool(async_check)
-        self._tick_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._tick_counter = torch.zeros(2, dtype=torch.int64, device=self.device)      # [ticks completed, scratch of the tick in flight]
+        # scheduler: the rest of update(dt) (robot-learning.py:45-50, 66-117) as per-env device state inside the fused tick kernels -
+        # money gates on every purchase, demos_bought, the switch to testing once the money is gone, the test branch (success
+        # within TEST_DISTANCE_THRESHOLD, best distance, time-out).  The wall-clock term of the money (COST_PER_CPU_SECOND) is
+        # charged deterministically: `tick_seconds` per tick (default: the 1/UPDATE_RATE s the reference schedules update(dt) at).
+        self.scheduler = bool(scheduler)
+        self.tick_seconds = (1.0 / constants.UPDATE_RATE) if tick_seconds is None else float(tick_seconds)
+        if self.scheduler:
+            if not self.fused:
+                raise ValueError("the scheduler lives in the fused tick kernels: pass fused=True (the hook-by-hook form is driven "
+                                 "from the host like the reference's update(dt): trainer.DriverLoop)")
+            dev = self.device
+            self.mode = torch.zeros(self.n, dtype=torch.uint8, device=dev)              # 0 training, 1 testing, 2 finished
+            self.demos_bought = torch.zeros(self.n, dtype=torch.int64, device=dev)
+            self.test_ticks = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            self.test_best_distance = torch.full((self.n,), float("inf"), dtype=torch.float64, device=dev)
+            self.test_success = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+            self.penalty = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+            self.test_timeout_ticks = max(1, int(round(constants.TEST_TIMEOUT / self.tick_seconds))) if self.tick_seconds > 0 else 1000
 
-    def money_remaining(self, tick_charge=0.0):
+    def money_remaining(self, tick_charge=None):
+        """calculate_remaining_money (robot-learning.py:45-50) per env, float64 `[N]`; the wall-clock term is ticks x tick_charge
+        money (default: tick_seconds x COST_PER_CPU_SECOND with the scheduler, else 0)."""
         c = constants
-        return (c.STARTING_MONEY - self.resets_bought * c.COST_PER_RESET - self.steps_bought * c.COST_PER_STEP - self.ticks * tick_charge)
+        if tick_charge is None:
+            tick_charge = self.tick_seconds * c.COST_PER_CPU_SECOND if self.scheduler else 0.0
+        demos = self.demos_bought if self.scheduler else 0
+        return (c.STARTING_MONEY - (demos * c.COST_PER_DEMO + self.resets_bought * c.COST_PER_RESET + self.steps_bought.double() * c.COST_PER_STEP
+                                    + self.ticks * tick_charge))
+
+    def all_finished(self):
+        """Scheduler: every env has finished its test phase (device -> host read)."""
+        return self.scheduler and bool((self.mode == 2).all().item())
+
+    def results(self):
+        """Scheduler: what the reference prints at the end of a run (robot-learning.py:111, 116), per env, as numpy arrays."""
+        if not self.scheduler:
+            raise RuntimeError("results() needs scheduler=True")
+        f = lambda t: t.cpu().numpy()
+        return {"mode": f(self.mode), "success": f(self.test_success).astype(bool), "test_ticks": f(self.test_ticks),
+                "test_time": f(self.test_ticks) * self.tick_seconds, "test_best_distance": f(self.test_best_distance),
+                "penalty": f(self.penalty).astype(bool), "demos_bought": f(self.demos_bought), "resets_bought": f(self.resets_bought),
+                "steps_bought": f(self.steps_bought)}
 
     def _device_tick(self):
         if self.fused:
@@ -151,6 +306,10 @@ class BatchedTrainer:
         t.capacity, t.rp_total = rb.capacity, p(rb._total_dev)
         t.steps_bought, t.resets_bought = p(self.steps_bought), p(self.resets_bought)
         t.philox_seed, t.tick_counter = self.philox_seed, p(self._tick_counter)
+        if self.scheduler:
+            t.mode, t.demos_bought, t.test_ticks, t.test_best = p(self.mode), p(self.demos_bought), p(self.test_ticks), p(self.test_best_distance)
+            t.test_success, t.penalty = p(self.test_success), p(self.penalty)
+            t.tick_seconds, t.test_timeout_ticks = self.tick_seconds, self.test_timeout_ticks
         return t
 
     def _device_tick_fused(self):
@@ -164,7 +323,7 @@ class BatchedTrainer:
         _lib.check(L.rtd3_tick_pre(_lib.ctypes.byref(t), sp), "tick_pre")
         z, mode = None, _lib.TICK_NOISE_PHILOX
         if self.noise == "mt19937":
-            z, mode = robot.generate_noise(), _lib.TICK_NOISE_GIVEN
+            z, mode = robot.generate_noise(types=robot._type), _lib.TICK_NOISE_GIVEN
         elif self.noise == "randn":
             z, mode = self._z.normal_(), _lib.TICK_NOISE_GIVEN
         residual = robot.td3_agent.forward(NET_ACTOR, robot._base)            # residual_action, robot.py:598-624

@@ -49,3 +49,8 @@ def robot_golden():
 @pytest.fixture(scope="session")
 def trace_golden():
     return load_golden("trace_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def loop_golden():
+    return load_golden("loop_golden.npz")

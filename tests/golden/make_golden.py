@@ -418,3 +418,119 @@ def make_trace():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
     make_trace()
+
+
+def make_loop():
+    """configs[0], the WHOLE run of the reference's driver (robot-learning.py:19-117 without pyglet): training until the money is
+    gone (three demonstrations, episodes with their TD3 updates, purchases refused once they are not affordable), the switch to
+    testing, the test phase until success or time-out.  The wall-clock money term is charged as 0.1 s per update() call (the
+    interval the script schedules update at) and the test time-out is counted in the same ticks - the only changes to the script's
+    logic, made so that the run is deterministic (trainer.DriverLoop restates exactly this)."""
+    import torch
+    env_m, rob_m, constants = load_reference()
+    torch.set_num_threads(1)
+    speed, angle = synthetic_maps(0)
+    np.random.seed(SEED0)
+    torch.manual_seed(0)
+    environment = env_m.Environment()
+    environment.dynamics_speed, environment.dynamics_angle = speed, angle
+    state = environment.reset()
+    robot = rob_m.Robot(environment.goal_state)
+    noises = []
+    real_randn_like = torch.randn_like
+    def capturing_randn_like(t, *a, **kw):
+        z = real_randn_like(t, *a, **kw)
+        noises.append(z.numpy().copy())
+        return z
+    torch.randn_like = capturing_randn_like
+    losses = []
+    real_tc, real_ta = robot.td3_agent.train_critic, robot.td3_agent.train_actor
+    robot.td3_agent.train_critic = lambda rb: (lambda r: (losses.append(("c",) + r), r)[1])(real_tc(rb))
+    robot.td3_agent.train_actor = lambda rb: (lambda r: (losses.append(("a", r)), r)[1])(real_ta(rb))
+    TICK_SECONDS = 0.1
+    timeout_ticks = int(round(constants.TEST_TIMEOUT / TICK_SECONDS))
+    mode, ticks = "training", 0
+    demos_bought = resets_bought = steps_bought = 0
+    test_ticks, test_best, penalty, success, finished = 0, np.inf, False, False, False
+    kinds, states, actions, moneys, demos_s, demos_a, step_rewards, step_dones = [], [], [], [], [], [], [], []
+    code = {"step": 0, "demo": 1, "reset": 2, "switch": 3, "skip": 4, "test": 5}
+
+    def money_now():
+        spent = (demos_bought * constants.COST_PER_DEMO + resets_bought * constants.COST_PER_RESET + steps_bought * constants.COST_PER_STEP
+                 + (ticks * TICK_SECONDS) * constants.COST_PER_CPU_SECOND)
+        return constants.STARTING_MONEY - spent
+    try:
+        while not finished:
+            act = np.zeros(2)
+            if mode == "training":
+                money = money_now()
+                action_type = robot.get_next_action_type(state, money)
+                money = money_now()
+                ticks += 1
+                moneys.append(money)
+                kind = action_type
+                if money < 0:
+                    penalty = money < -1.0
+                    state = environment.reset()
+                    mode = "testing"
+                    kind = "switch"
+                elif action_type == "reset":
+                    if money >= constants.COST_PER_RESET:
+                        state = environment.reset()
+                        resets_bought += 1
+                    else:
+                        kind = "skip"
+                elif action_type == "demo":
+                    if money >= constants.COST_PER_DEMO:
+                        ds, da = environment.get_demonstration()
+                        demos_s.append(np.array(ds)); demos_a.append(np.array(da))
+                        robot.process_demonstration(ds, da, money)
+                        demos_bought += 1
+                    else:
+                        kind = "skip"
+                else:
+                    if money >= constants.COST_PER_STEP:
+                        act = robot.get_next_action_training(state, money)
+                        next_state = environment.step(act)
+                        robot.process_transition(state, act, next_state, money)
+                        row = robot.memory.buffer[(robot.memory.position - 1) % robot.memory.capacity]
+                        step_rewards.append(row[2]); step_dones.append(row[4])
+                        state = next_state
+                        steps_bought += 1
+                    else:
+                        kind = "skip"
+            else:
+                act = robot.get_next_action_testing(state)
+                next_state = environment.step(act)
+                distance = np.linalg.norm(next_state - environment.goal_state)
+                state = next_state
+                test_ticks += 1
+                moneys.append(np.nan)
+                kind = "test"
+                if distance <= constants.TEST_DISTANCE_THRESHOLD:
+                    success = finished = True
+                if distance < test_best:
+                    test_best = distance
+                if test_ticks >= timeout_ticks:
+                    finished = True
+            kinds.append(code[kind]); states.append(np.array(state, dtype=np.float64)); actions.append(np.array(act, dtype=np.float64))
+    finally:
+        torch.randn_like = real_randn_like
+    out = {"goal": np.array(environment.goal_state), "region": np.array(environment.robot_init_region),
+           "kinds": np.array(kinds, dtype=np.int8), "states": np.array(states), "actions": np.array(actions), "money": np.array(moneys),
+           "step_rewards": np.array(step_rewards, dtype=np.float64), "step_dones": np.array(step_dones),
+           "demo_states": np.array(demos_s), "demo_actions": np.array(demos_a),
+           "update_noise": np.array(noises, dtype=np.float32), "n_updates": np.int64(len(noises) // 100),
+           "critic_losses": np.array([l[1:] for l in losses if l[0] == "c"]), "actor_losses": np.array([l[1] for l in losses if l[0] == "a"]),
+           "demos_bought": np.int64(demos_bought), "resets_bought": np.int64(resets_bought), "steps_bought": np.int64(steps_bought),
+           "training_ticks": np.int64(ticks), "test_ticks": np.int64(test_ticks), "test_best_distance": np.float64(test_best),
+           "success": np.bool_(success), "penalty": np.bool_(penalty), "tick_seconds": np.float64(TICK_SECONDS),
+           "final_actor": _flat_params(robot.td3_agent.actor_network), "replay_len": np.int64(len(robot.memory)),
+           "final_uniform": np.float64(np.random.uniform())}
+    np.savez_compressed(os.path.join(HERE, "loop_golden.npz"), **out)
+    print("loop_golden.npz: kinds", np.bincount(kinds), "training ticks", ticks, "test ticks", test_ticks, "success", success,
+          "best", test_best, "updates", out["n_updates"], "bought", demos_bought, resets_bought, steps_bought)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "loop":
+    make_loop()

@@ -177,7 +177,7 @@ def test_multi_tick_kernel_matches_the_three_launch_tick(pkg, env_golden, n, m, 
         tr.run(8 * 9 + 3)                                   # nine blocks of 8 ticks + three single ticks
         launches = pkg._lib.launch_count() - before
         snaps.append(_snapshot(env, robot, tr))
-        assert tr.ticks == 75 and int(tr._tick_counter.item()) == 75
+        assert tr.ticks == 75 and int(tr._tick_counter[0].item()) == 75
         if multi:
             assert launches <= 9 + 3 * 3 + 2                # one launch per block (+ the one-off weight copies)
     (a, rows_a, tab_a), (b, rows_b, tab_b) = snaps
