@@ -8,6 +8,8 @@ import numpy as np, torch, torch.distributed as dist
 import rtd3_b200 as rt
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("RTD3_HANG_DUMP_S", "120")), exit=True)     # a hung rank prints where it is stuck
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

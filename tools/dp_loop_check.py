@@ -19,6 +19,8 @@ from rtd3_b200.trainer import replicas_identical
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("RTD3_HANG_DUMP_S", "120")), exit=True)     # a hung rank prints where it is stuck
     mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     envs = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
