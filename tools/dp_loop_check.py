@@ -20,7 +20,8 @@ from rtd3_b200.trainer import replicas_identical
 
 def main():
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("RTD3_HANG_DUMP_S", "120")), exit=True)     # a hung rank prints where it is stuck
+    arm = lambda: faulthandler.dump_traceback_later(int(os.environ.get("RTD3_HANG_DUMP_S", "150")), exit=True)   # a hung rank prints where it is stuck
+    arm()
     mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     envs = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -32,6 +33,7 @@ def main():
     ok = True
 
     # ---- (1) DP epoch time, B = 256 per rank, 2 x 256
+    arm()
     H, L, B, E = 256, 2, 256, 100
     agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L), batch_size=B,
                    num_epochs=E, device=dev, process_group=pg, dp_collective=mode)
@@ -70,6 +72,7 @@ def main():
     tt = np.linspace(0, 1, 3785)[:, None]
     demos = np.concatenate([rs.uniform(5, 95, (1, 2)) * (1 - tt) + rs.uniform(5, 95, (1, 2)) * tt + rs.normal(0, 2.5, (3785, 2)) for _ in range(3)])
     for async_check in (False, True):
+        arm()
         env = rt.Environment(num_envs=envs, seed=1707366464 + rank * envs, device=dev)
         robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 8 * envs),
                          dp_collective=mode)
