@@ -22,7 +22,8 @@ STEP_AUTO, STEP_SMEM, STEP_LDG = 0, 1, 2
 def synthetic_maps(seed=0):
     """Benchmark maps: low-pass filtered uniform noise `u`, speed = sigmoid(10*(u-0.5))
     (the reference's stretch, environment.py:81-83), angle = u; float32 `[100,100]` indexed `[x][y]`.
-    The reference's own Perlin generator is an unpinned third-party package; maps are inputs here."""
+    `Environment()` without `maps=` builds the reference's own Perlin maps (`perlin_maps`); the benchmarks and parity tests pass
+    these instead (the same tensors go to the oracle and to the kernels)."""
     W = constants.WORLD_SIZE
     u = np.random.RandomState(seed).rand(W, W)
     for _ in range(3):
@@ -31,6 +32,75 @@ def synthetic_maps(seed=0):
     u = ((u - u.min()) / (u.max() - u.min())).astype(np.float32)
     speed = (1 / (1 + np.exp(-10 * (u - 0.5)))).astype(np.float32)
     return speed, u.copy()
+
+
+# ---- environment.py:59-95: the reference's own maps ------------------------------------------------------------------------------
+# The reference builds them with the third-party `perlin_noise` package (PyPI "perlin-noise", unpinned, not vendored, absent from this
+# image): speed = sigmoid-stretched sum of three octaves (5, 10, 20 with weights 1, 0.5, 0.25), angle = one octave (5), both min-max
+# normalised, all seeded by configuration.RANDOM_SEED.  PARITY UNPINNED: `_PerlinNoise` restates that package's published algorithm
+# (release 1.12: per lattice corner a gradient vector of `random.uniform(-1, 1)` components from Python's generator seeded with
+# seed * hasher(corner); corner weight = product of the quintic fade 6t^5 - 15t^4 + 10t^3 of 1 - |distance| per axis; value = sum over
+# the cell's corners of weight * dot(gradient, offset)) from its documentation; no reference test or fixture pins the map contents,
+# and the maps are INPUTS of the hot path (identical tensors go to the oracle and the kernels).
+class _PerlinNoise:
+    def __init__(self, octaves=1, seed=1):
+        self.octaves, self.seed = octaves, seed
+        self._grad = {}
+
+    @staticmethod
+    def _fade(t):
+        return 6 * t ** 5 - 15 * t ** 4 + 10 * t ** 3
+
+    def _gradient(self, corner):
+        g = self._grad.get(corner)
+        if g is None:
+            import random
+            h = max(1, int(abs(sum((10 ** k) * c for k, c in enumerate(corner)) + 1)))
+            rnd = random.Random(self.seed * h)
+            g = self._grad[corner] = tuple(rnd.uniform(-1, 1) for _ in corner)
+        return g
+
+    def __call__(self, coordinates):
+        import itertools
+        import math
+        p = [c * self.octaves for c in coordinates]
+        boxes = [(math.floor(c), math.floor(c + 1)) for c in p]
+        total = 0.0
+        for corner in itertools.product(*boxes):
+            d = [a - b for a, b in zip(p, corner)]
+            w = 1.0
+            for dist in d:
+                w *= self._fade(1 - abs(dist))
+            total += w * sum(gc * dc for gc, dc in zip(self._gradient(corner), d))
+        return total
+
+
+_PERLIN_CACHE = {}
+
+
+def perlin_maps(seed=None):
+    """`Environment.set_dynamics` (environment.py:59-95) -> (speed, angle) float32 `[100,100]` indexed `[x][y]`; cached per seed (the
+    reference seeds the generator with configuration.RANDOM_SEED, so every Environment of a process has the same maps)."""
+    seed = configuration.RANDOM_SEED if seed is None else int(seed)
+    if seed not in _PERLIN_CACHE:
+        W = constants.WORLD_SIZE
+        n1, n2, n3 = _PerlinNoise(5, seed), _PerlinNoise(10, seed), _PerlinNoise(20, seed)
+        cells = np.zeros([W, W], dtype=np.float32)
+        for col in range(W):
+            for row in range(W):
+                q = [col / W, row / W]
+                cells[col, row] = n1(q) + 0.5 * n2(q) + 0.25 * n3(q)
+        norm = (cells - np.min(cells)) / (np.max(cells) - np.min(cells))
+        speed = 1 / (1 + np.exp(-10 * (norm - 0.5)))                       # stretch_factor 10, environment.py:81-83
+        na = _PerlinNoise(5, seed)
+        cells = np.zeros([W, W], dtype=np.float32)
+        for col in range(W):
+            for row in range(W):
+                cells[col, row] = na([col / W, row / W])
+        angle = (cells - np.min(cells)) / (np.max(cells) - np.min(cells))
+        _PERLIN_CACHE[seed] = (speed.astype(np.float32), angle.astype(np.float32))
+    s, a = _PERLIN_CACHE[seed]
+    return s.copy(), a.copy()
 
 
 def _planes(t, n, name):
@@ -129,9 +199,9 @@ class Environment:
                                                         _lib.stream_ptr(self.device)), "env_init_goal_region")
         self._rng_out()
 
-    # ---- environment.py:59-95 (map contents are inputs; generator parity is unpinned) ------------------
+    # ---- environment.py:59-95 (map contents are inputs; generator parity is unpinned, see perlin_maps) ------------------
     def set_dynamics(self):
-        self.set_maps(*synthetic_maps(0))
+        self.set_maps(*perlin_maps(configuration.RANDOM_SEED))
 
     def set_maps(self, speed, angle):
         W = constants.WORLD_SIZE
