@@ -157,7 +157,7 @@ def test_demonstration_pipeline_single_env(pkg, env_golden):
     assert len(robot.demonstration_states) == 200 + 3 * (199 * 6 + 1)      # 3 785 per demo (SURVEY: 11 355 after 3 demos)
     assert len(robot.paths_to_draw) == 4
     assert not robot.goal_reached
-    assert (env.robot_state == state.astype(np.float32).astype(np.float64)).all()   # planning did not move the robot
+    assert env.robot_state is state                                          # planning did not move the robot (same object, as in the reference)
 
 
 def test_batched_trainer_loop_and_masked_push(pkg, env_golden):

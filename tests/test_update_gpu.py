@@ -55,13 +55,17 @@ def test_update_with_kernel_noise_equals_update_with_that_noise_injected(pkg, H,
         pkg._lib.check(pkg._lib.lib().rtd3_td3_target_noise(99, e, pkg._lib.ptr(noise[e]), B, pkg._lib.stream_ptr()))
     c1, l1 = a1.td3_update(rb, idx=idx)                    # noise generated in the kernels, steps 0..E-1
     c2, l2 = a2.td3_update(rb, idx=idx, noise=noise)
-    assert torch.equal(a1.params, a2.params) and torch.equal(c1, c2) and torch.equal(l1, l2)
+    # parameters bit-identical; the reported losses are sums of per-CTA partial sums added atomically (order varies run to run)
+    assert torch.equal(a1.params, a2.params)
+    torch.testing.assert_close(c1, c2, rtol=1e-6, atol=0)
+    torch.testing.assert_close(l1, l2, rtol=1e-6, atol=0)
     assert int(a1._noise_counter.item()) == E and a1._noise_steps == E
     c1b, _ = a1.td3_update(rb, idx=idx)                    # the replayed graph draws FRESH noise (device counter)
     for e in range(E):
         pkg._lib.check(pkg._lib.lib().rtd3_td3_target_noise(99, E + e, pkg._lib.ptr(noise[e]), B, pkg._lib.stream_ptr()))
     c2b, _ = a2.td3_update(rb, idx=idx, noise=noise)
-    assert torch.equal(a1.params, a2.params) and torch.equal(c1b, c2b)
+    assert torch.equal(a1.params, a2.params)
+    torch.testing.assert_close(c1b, c2b, rtol=1e-6, atol=0)
     assert int(a1._noise_counter.item()) == 2 * E
 
 
@@ -84,8 +88,8 @@ def test_update_entry_point_vs_oracle_and_eager_steps(pkg):
                          (a2.target_critic_network_2, a2.critic_network_2)):
                 a2.soft_update(t, s, a2.tau)
     assert torch.equal(a1.params, a2.params)
-    np.testing.assert_array_equal(closs.cpu().numpy(), np.asarray(cl, dtype=np.float32))
-    np.testing.assert_array_equal(aloss.cpu().numpy(), np.asarray(al, dtype=np.float32))
+    np.testing.assert_allclose(closs.cpu().numpy(), np.asarray(cl, dtype=np.float32), rtol=1e-6)    # (atomically summed partial losses)
+    np.testing.assert_allclose(aloss.cpu().numpy(), np.asarray(al, dtype=np.float32), rtol=1e-6)
     # oracle
     a3 = make_agent(pkg, H, L, B, E, seed=3)
     orc = to.TD3Oracle(a3.flat(0).cpu().numpy(), a3.flat(1).cpu().numpy(), a3.flat(2).cpu().numpy(), hidden=H, layers=L)
@@ -168,6 +172,7 @@ def test_multi_tick_launch_refuses_a_ring_it_could_corrupt(pkg):
     reports it, and BatchedTrainer.run falls back to the three-launch tick, whose rows are then bit-identical to the eager ticks."""
     n, K = 256, 8
     def build(cap):
+        torch.manual_seed(4)                                 # the networks draw their initial weights from torch's generator
         env = pkg.Environment(num_envs=n, seed=11)
         robot = pkg.Robot(env.goal_state, hidden=64, layers=2, seed=5, buffer_size=cap)
         robot.td3_agent.precision = "f16"
