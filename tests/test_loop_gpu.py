@@ -5,7 +5,9 @@
 2. N oracle driver loops (oracle/driver_oracle.py, pinned to that golden) with seeds s+i against `BatchedTrainer` in every form the
    throughput path uses - hook by hook, fused tick, eight fused ticks per CUDA graph, the multi-tick kernel - and, with the
    scheduler, through the whole run of every env.
-Bars: tick kinds, flags, counters, money, reset draws bit-exact; states and actions 1e-5 relative, teacher-forced.
+Bars: tick kinds, flags, counters, money, reset draws bit-exact; states 1e-5 relative, teacher-forced (same float32 state and action in);
+actions 1e-4 absolute - the float32 round-off of an actor whose inputs (state - goal) are O(100), which the reference's own float32
+torch forward carries as well.
 """
 import numpy as np
 import pytest
@@ -174,7 +176,8 @@ def lockstep_tick(env, robot, tr, ors, t, scheduler):
         elif kind in (do.STEP, do.TEST):
             d.state = prev[i]
             a = d.action(kind)
-            assert close(act[i], a), "tick %d env %d action %s vs %s" % (t, i, act[i], a)
+            assert np.abs(act[i] - a).max() <= 1e-4, "tick %d env %d action %s vs %s" % (t, i, act[i], a)
+            assert ((np.abs(act[i]) == 5) == (np.abs(a) == 5)).all() or np.abs(np.abs(a) - 5).min() < 1e-4, (t, i)   # same clips
             nxt = eo.step_scalar(d.speed, d.angle, prev[i], act[i])
             assert close(state[i], nxt), "tick %d env %d state %s vs %s" % (t, i, state[i], nxt)
             d.finish_tick(kind, act[i], state[i])
@@ -203,9 +206,9 @@ def test_block_forms_vs_oracle_loops(pkg, env_golden, form):
     are compared - and re-synchronised - at the block boundaries: counters and flags exact, states to the drift of eight float32
     steps."""
     maps = (env_golden["speed"], env_golden["angle"])
-    n, K = 64, 8
-    noise = "mt19937" if form == "graph8_mt19937" else "philox"
     multi = form == "multi_tick_kernel"
+    n, K = (128 if multi else 64), 8                    # (the kernel's tensor-core forward takes whole 128-env tiles)
+    noise = "mt19937" if form == "graph8_mt19937" else "philox"
     env, robot, tr = build(pkg, n, maps, noise, True, graph=True, interval=K, zero_head=multi, precision="f16" if multi else "fp32",
                            capacity=20000)
     tr.multi_tick_kernel = multi
@@ -270,10 +273,10 @@ def test_scheduler_in_the_block_forms_matches_eager_ticks(pkg, env_golden):
         tr.multi_tick_kernel = form == "multi"
         assert tr._multi_tick_ok() == (form == "multi")
         if form == "eager":
-            for _ in range(40 * K):
+            for _ in range(120 * K):
                 tr.tick()
         else:
-            tr.run(40 * K)
+            tr.run(120 * K)
         assert tr.all_finished()
         snap = {k: v.copy() if isinstance(v, np.ndarray) else v for k, v in tr.results().items()}
         snap["state"] = env._state.cpu().numpy()
