@@ -361,6 +361,17 @@ int32_t rtd3_td3_target_noise(uint64_t seed, uint64_t counter, float* out, int64
  * Polyak updates.  Everything is issued on `stream` without synchronising (capturable in one CUDA graph). */
 int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* args, void* stream);
 
+/* The same update as ONE persistent cooperative kernel (csrc/rtd3_coop.cu) - the small-batch learner: one CTA per SM stays
+ * resident for all `epochs`, every hidden-layer product is tiled over all SMs, the layers of the chain are separated by grid-wide
+ * barriers instead of kernel launches, Adam / Polyak and (world > 1, peer memory only: args->p2p) the gradient all-reduce are stages
+ * of the same kernel.  fp32 (FFMA), layers >= 2, batch <= 4096; same arithmetic as the step kernels up to summation order
+ * (losses / Q-values within the 1e-3 parity bar).  args->scratch, params_uv, comm and tf32 are not used.
+ * coop_scratch: rtd3_td3_coop_scratch_floats(batch) floats, 16 B aligned, ZERO-initialised once by the caller (its first words are
+ * the grid barrier) and then left to the kernel. */
+int32_t rtd3_td3_coop_supported(const rtd3_td3* h, int32_t batch);
+int64_t rtd3_td3_coop_scratch_floats(const rtd3_td3* h, int32_t batch);
+int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* args, float* coop_scratch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused tick of the batched driver loop        (robot-learning.py:66-101, training branch)
  * ---------------------------------------------------------------------------------------------- */

@@ -644,6 +644,14 @@ int32_t rtd3_replay_gather(const float* s, const float* a, const float* r, const
 // optimiser / Polyak steps issued on `stream` (plain launches: the whole call can be captured in a CUDA graph, the NCCL node included).
 __global__ void advance_counter_kernel(unsigned long long* counter, unsigned long long by) { counter[0] += by; }
 
+}  // extern "C"
+int32_t rtd3::advance_noise_counter(uint64_t* counter, uint64_t by, cudaStream_t st) {
+  advance_counter_kernel<<<1, 1, 0, st>>>((unsigned long long*)counter, (unsigned long long)by);
+  RTD3_LAUNCHED();
+  return 0;
+}
+extern "C" {
+
 __global__ void target_noise_kernel(Td3Hyper hp, float2* __restrict__ out, int64_t rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows) out[i] = target_noise(nullptr, hp, (int)i);
@@ -728,10 +736,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
     }
   }
   (void)rp_actor;
-  if (!a->noise) {
-    advance_counter_kernel<<<1, 1, 0, st>>>((unsigned long long*)a->noise_counter, (unsigned long long)E);
-    RTD3_LAUNCHED();
-  }
+  if (!a->noise) return advance_noise_counter(a->noise_counter, (uint64_t)E, st);
   return 0;
 }
 

@@ -349,6 +349,10 @@ class TD3:
         self._graphs = {}
         self._p2p = None
         self._comm = None
+        # "coop": td3_update runs as ONE persistent cooperative kernel (csrc/rtd3_coop.cu) whenever it applies - fp32, layers >= 2,
+        # batch <= 4096, single GPU or the peer-memory collective; "steps": always the per-step kernels of rtd3_td3.cu
+        self.update_kernel = "coop"
+        self._coop_scratch = {}
         # target-policy smoothing noise (robot.py:338, torch.randn_like - unseeded in the reference): generated inside the critic
         # kernels from Philox4x32-10 keyed (noise_seed, device step counter, batch row) unless a noise tensor is injected
         self.noise_seed = 0x7d3
@@ -674,6 +678,9 @@ class TD3:
         critic kernels (Philox, keyed by the device step counter, which the call advances)."""
         B = idx.shape[1]
         tc = self._tc_learner_ok(B)
+        coop = self._coop_ok(B)
+        if coop:
+            self._u_stale = True                                     # the cooperative kernel keeps params / params_t only
         keep_uv = self.params_u is not None and not self._u_stale
         if tc and not keep_uv:
             raise RuntimeError("tensor-core operand copies are stale: call _sync_chunk_major() first")
@@ -695,7 +702,24 @@ class TD3:
         a.comm = self._comm if (self.world > 1 and self._p2p is None) else None
         if self.world > 1 and self._p2p is not None:
             a.p2p = ctypes.pointer(self._p2p["struct"])
+        if coop:
+            _lib.check(_lib.lib().rtd3_td3_update_coop(self._handle, ctypes.byref(a), _lib.ptr(self._coop_buffer(B)), _lib.stream_ptr(self.device)),
+                       "td3_update_coop")
+            return
         _lib.check(_lib.lib().rtd3_td3_update(self._handle, ctypes.byref(a), _lib.stream_ptr(self.device)), "td3_update")
+
+    def _coop_ok(self, B):
+        return (self.update_kernel == "coop" and not self._tc_learner_ok(B) and (self.world == 1 or self._p2p is not None)
+                and bool(_lib.lib().rtd3_td3_coop_supported(self._handle, B)))
+
+    def _coop_buffer(self, B):
+        """Activation scratch + grid-barrier words of the cooperative kernel for batch B: zero-initialised once, then owned by the
+        kernel (captured graphs hold its address: never freed while the learner lives)."""
+        buf = self._coop_scratch.get(B)
+        if buf is None:
+            n = int(_lib.lib().rtd3_td3_coop_scratch_floats(self._handle, B))
+            buf = self._coop_scratch[B] = torch.zeros((n,), dtype=torch.float32, device=self.device)
+        return buf
 
     def td3_update(self, replay_buffer, noise=None, idx=None, use_graph=True):
         """robot.py:258-285: `num_epochs` critic steps, an actor step + the three Polyak updates every
@@ -729,7 +753,7 @@ class TD3:
     def _update_state(self, replay_buffer, E, B, delay, injected_noise=False):
         """Persistent buffers (and, once captured, the CUDA graph) of an E-epoch block for this replay buffer / batch size."""
         n_actor = len([e for e in range(E) if e % delay == 0])
-        key = (id(replay_buffer), E, B, delay, self.precision, self._tc_learner_ok(B), bool(injected_noise))
+        key = (id(replay_buffer), E, B, delay, self.precision, self._tc_learner_ok(B), bool(injected_noise), self._coop_ok(B))
         st = self._graphs.get(key)
         if st is None:
             st = {"idx": torch.zeros((E + n_actor, B), dtype=torch.int32, device=self.device),
@@ -737,6 +761,8 @@ class TD3:
                   "closs": torch.zeros((E, 2), dtype=torch.float32, device=self.device),
                   "aloss": torch.zeros((max(1, n_actor),), dtype=torch.float32, device=self.device), "graph": None, "launches": 0}
             self._row_scratch(B)
+            if self._coop_ok(B):
+                self._coop_buffer(B)                                 # allocated (and zeroed) outside of the graph capture
             self._graphs[key] = st
         return st
 

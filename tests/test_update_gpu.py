@@ -196,3 +196,42 @@ def test_multi_tick_launch_refuses_a_ring_it_could_corrupt(pkg):
     assert torch.equal(key(robot.memory), key(robot2.memory))
     env3, robot3, tr3 = build(n * K)
     assert tr3._multi_tick_ok()
+
+
+@pytest.mark.parametrize("H,L,B,E", [(256, 2, 256, 6), (200, 3, 100, 6), (64, 2, 48, 5), (128, 4, 33, 4), (32, 2, 700, 3)])
+def test_cooperative_update_kernel_vs_step_kernels_and_oracle(pkg, H, L, B, E):
+    """The persistent cooperative kernel (rtd3_td3_update_coop) against the per-step kernels (same arithmetic, another summation
+    order: parameters within one Adam step, >= 99 % of them within 2e-6) and against the numpy oracle (losses 1e-3)."""
+    rb = synthetic_replay(pkg, 3000)
+    rs = np.random.RandomState(2)
+    n_idx = E + (E + 1) // 2
+    idx = torch.from_numpy(rs.randint(0, 3000, (n_idx, B)).astype(np.int32)).cuda()
+    noise = torch.from_numpy(rs.normal(size=(E, B, 2)).astype(np.float32)).cuda()
+    a_coop, a_steps = make_agent(pkg, H, L, B, E, seed=7), make_agent(pkg, H, L, B, E, seed=7)
+    a_steps.update_kernel = "steps"
+    assert a_coop._coop_ok(B) and not a_steps._coop_ok(B)
+    p0 = a_coop.params.clone()
+    c1, l1 = a_coop.td3_update(rb, idx=idx, noise=noise)
+    c2, l2 = a_steps.td3_update(rb, idx=idx, noise=noise)
+    torch.testing.assert_close(c1, c2, rtol=2e-4, atol=1e-4)
+    torch.testing.assert_close(l1, l2, rtol=2e-4, atol=1e-4)
+    d1, d2 = (a_coop.params - p0).double(), (a_steps.params - p0).double()
+    assert float((d1 - d2).abs().max()) <= 2.05e-5 * (E // 2 + 1)
+    assert float(((d1 - d2).abs() <= 2e-6).double().mean()) >= 0.99
+    assert torch.equal(a_coop.steps, a_steps.steps) and torch.equal(a_coop.beta_pows, a_steps.beta_pows)
+    # transposed copies kept in step: a forward after the update agrees
+    x = torch.rand((50, 2), device="cuda") * 20 - 10
+    torch.testing.assert_close(a_coop.actor_network(x), a_steps.actor_network(x), rtol=1e-4, atol=1e-4)
+    a3 = make_agent(pkg, H, L, B, E, seed=7)
+    orc = to.TD3Oracle(a3.flat(0).cpu().numpy(), a3.flat(1).cpu().numpy(), a3.flat(2).cpu().numpy(), hidden=H, layers=L)
+    ro = to.ReplayOracle(3000)
+    ro.s[:], ro.a[:], ro.r[:], ro.s2[:] = rb.s.cpu().numpy(), rb.a.cpu().numpy(), rb.r.cpu().numpy(), rb.s2.cpu().numpy()
+    ro.done[:] = rb.notdone.cpu().numpy() < 0.5
+    ro.size = 3000
+    oc, oa = orc.td3_update(ro, list(idx.cpu().numpy()), list(noise.cpu().numpy()), E)
+    np.testing.assert_allclose(c1.cpu().numpy(), np.asarray(oc), rtol=1e-3)
+    np.testing.assert_allclose(l1.cpu().numpy(), np.asarray(oa), rtol=1e-3)
+    # a second, graph-replayed update keeps agreeing
+    c1b, _ = a_coop.td3_update(rb, idx=idx, noise=noise)
+    c2b, _ = a_steps.td3_update(rb, idx=idx, noise=noise)
+    torch.testing.assert_close(c1b, c2b, rtol=5e-4, atol=1e-4)
