@@ -46,8 +46,15 @@ struct GridBarrier {
   unsigned int* count;
   volatile unsigned int* gen;
 };
-__device__ __forceinline__ void grid_sync(const GridBarrier& b) {
+__device__ int g_prof_slot;
+__device__ __forceinline__ void grid_sync(const GridBarrier& b, long long* prof = nullptr) {
   __syncthreads();
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {      // time at which block 0 ARRIVES (its own work of the stage is done)
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    const int s = g_prof_slot;
+    if (s < 126) { prof[s] = now; g_prof_slot = s + 1; }
+  }
   if (threadIdx.x == 0) {
     const unsigned int g = *b.gen;
     __threadfence();
@@ -61,6 +68,12 @@ __device__ __forceinline__ void grid_sync(const GridBarrier& b) {
     __threadfence();
   }
   __syncthreads();
+  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {      // ... and at which the barrier released it
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    const int s = g_prof_slot;
+    if (s < 126) { prof[s] = now; g_prof_slot = s + 1; }
+  }
 }
 
 // ---- arguments -----------------------------------------------------------------------------------------------------------------
@@ -70,6 +83,7 @@ struct CoopPeers {
 };
 
 struct CoopArgs {
+  long long* prof;           // nullable (development): block 0 stamps %globaltimer at every stage boundary of the last epoch
   Arena ar;
   float* params;
   float* params_t;
@@ -152,7 +166,7 @@ __device__ __forceinline__ void load_b_chunk(const TileOp& op, float* Bs, int k0
 }
 
 // A chunk: rows m0..m0+31, reduction k0..k0+31 -> As[r][kk]
-__device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const float* in_s, int m0, int k0) {
+__device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const float* in_s, const float* w_s, int m0, int k0) {
   const int t = threadIdx.x;
   if (op.akind == A_GLOBAL) {
     const int r = t >> 3, kq = t & 7;                    // 32 rows x 8 float4
@@ -169,8 +183,8 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + kq * 4 + i;
       if (m < op.M && k < op.Kred) {
-        float s = ldcg(op.b0 + k);
-        for (int j = 0; j < op.in_dim; ++j) s = fmaf(in_s[r * 4 + j], ldcg(op.W0 + k * op.in_dim + j), s);
+        float s = w_s[4 * kMaxHidden + k];
+        for (int j = 0; j < op.in_dim; ++j) s = fmaf(in_s[r * 4 + j], w_s[k * op.in_dim + j], s);
         vv[i] = fmaxf(s, 0.f);
       }
     }
@@ -183,9 +197,9 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < op.M && k < op.Kred) {
       const float4 h = ldcg4(op.Hmask + (int64_t)m * op.Hd + k);
-      const float4 w0 = ldcg4(op.Wout + k);
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k);
       float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (op.out_dim > 1) w1 = ldcg4(op.Wout + op.Hd + k);
+      if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + k);
       const float d0 = in_s[r * 4], d1 = in_s[r * 4 + 1];
       v.x = h.x > 0.f ? fmaf(d0, w0.x, d1 * w1.x) : 0.f;
       v.y = h.y > 0.f ? fmaf(d0, w0.y, d1 * w1.y) : 0.f;
@@ -203,9 +217,9 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
         v = ldcg4(op.A + (int64_t)b * op.lda + n);
       } else {
         const float4 h = ldcg4(op.Hmask + (int64_t)b * op.Hd + n);
-        const float4 w0 = ldcg4(op.Wout + n);
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + n);
         float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (op.out_dim > 1) w1 = ldcg4(op.Wout + op.Hd + n);
+        if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + n);
         const float d0 = ldcg(op.dout + (int64_t)b * 2), d1 = ldcg(op.dout + (int64_t)b * 2 + 1);
         v.x = h.x > 0.f ? fmaf(d0, w0.x, d1 * w1.x) : 0.f;
         v.y = h.y > 0.f ? fmaf(d0, w0.y, d1 * w1.y) : 0.f;
@@ -221,13 +235,18 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
 }
 
 template <int TN>
-__device__ void gemm_tile(const TileOp& op, int tm, int tn, float* smem) {
+__device__ void gemm_tile(const TileOp& op_in, int tm, int tn, float* smem) {
   constexpr int NT = TN / 16;                            // outputs per thread along n (4 or 2)
   float* As = smem;                                      // [2][CTM][kAld]
   float* Bs = smem + 2 * CTM * kAld;                     // [2][CTK][TN]
   float* in_s = Bs + 2 * CTK * TN;                       // [CTM][4]
-  float* rsum = in_s + CTM * 4;                          // [CTM] row sums of A (bias gradients)
+  float* w_s = in_s + CTM * 4;                           // [5][kMaxHidden]: first layer (W0 | b0) or output layer weights of the generators
+  __shared__ TileOp s_op;                                // the operation, out of the caller's local memory
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  __syncthreads();                                       // the previous tile's readers are done with the shared buffers
+  if (t == 0) s_op = op_in;
+  __syncthreads();
+  const TileOp& op = s_op;
   const int m0 = tm * CTM, n0 = tn * TN;
   float acc[2][NT];
 #pragma unroll
@@ -237,29 +256,31 @@ __device__ void gemm_tile(const TileOp& op, int tm, int tn, float* smem) {
   float my_rsum = 0.f;
   const bool want_rsum = op.ekind == E_GRAD && op.bias_grad && tn == 0;
 
-  __syncthreads();                                       // the previous tile's readers are done with the shared buffers
   if (op.akind == A_GEN_FIRST) {
     if (t < CTM * 4) {
       const int r = t >> 2, j = t & 3;
       in_s[t] = (m0 + r < op.M && j < op.in_dim) ? ldcg(op.gen_in + (int64_t)(m0 + r) * 4 + j) : 0.f;
     }
-  } else if (op.akind == A_GEN_DOUT) {
-    if (t < CTM * 2) {
+    for (int q = t; q < op.Hd * op.in_dim; q += kCT) w_s[q] = ldcg(op.W0 + q);          // W0 [Hd][in]
+    for (int q = t; q < op.Hd; q += kCT) w_s[4 * kMaxHidden + q] = ldcg(op.b0 + q);
+  } else if (op.akind == A_GEN_DOUT || op.akind == AT_GEN_DOUT) {
+    if (op.akind == A_GEN_DOUT && t < CTM * 2) {
       const int r = t >> 1, o = t & 1;
       in_s[r * 4 + o] = (m0 + r < op.M) ? ldcg(op.dout + (int64_t)(m0 + r) * 2 + o) : 0.f;
     }
+    for (int q = t; q < op.Hd * op.out_dim; q += kCT) w_s[q] = ldcg(op.Wout + q);        // Wout [out][Hd]
   }
   __syncthreads();
 
   const int nchunks = (op.Kred + CTK - 1) / CTK;
   load_b_chunk<TN>(op, Bs, 0, n0);
-  load_a_chunk(op, As, in_s, m0, 0);
+  load_a_chunk(op, As, in_s, w_s, m0, 0);
   cp_commit();
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
     if (c + 1 < nchunks) {
       load_b_chunk<TN>(op, Bs + (cur ^ 1) * CTK * TN, (c + 1) * CTK, n0);
-      load_a_chunk(op, As + (cur ^ 1) * CTM * kAld, in_s, m0, (c + 1) * CTK);
+      load_a_chunk(op, As + (cur ^ 1) * CTM * kAld, in_s, w_s, m0, (c + 1) * CTK);
       cp_commit();
       cp_wait<1>();
     } else {
@@ -296,7 +317,6 @@ __device__ void gemm_tile(const TileOp& op, int tm, int tn, float* smem) {
     }
     __syncthreads();
   }
-  (void)rsum;
 
   // epilogue
 #pragma unroll
@@ -444,55 +464,64 @@ __device__ __forceinline__ void out_layer_row(const NetRef& nr, const float* __r
   o1 = nr.s.out > 1 ? v1 + ldcg(bo + 1) : 0.f;
 }
 
-// gWout[o][k] = sum_b dout[b][o] H_{L-1}[b][k]; gbout[o] = sum_b dout[b][o]: one thread per (net, k), `jobs` = nets * Hd
-__device__ void out_grads(const CoopArgs& a, const Scratch& sc, const NetRef* nets, int nnets, int first_job_block) {
+// Batch reductions of the small gradients, one job = one network x 32 consecutive hidden units, dealt to the CTAs from
+// `first_block` on: the 8 warps of a CTA take every 8th batch row (lanes = the 32 units: one coalesced 128 B load per row, eight
+// rows in flight per warp), the partial sums meet in shared memory.
+//   kind 0: gWout[o][k] = sum_b dout[b][o] H_{L-1}[b][k], gbout[o] = sum_b dout[b][o]
+//   kind 1: gW0[n][j]   = sum_b dZ0[b][n] in[b][j],        gb0[n]   = sum_b dZ0[b][n]
+__device__ void small_grads(const CoopArgs& a, const Scratch& sc, const NetRef* nets, int nnets, int kind, int first_block, float* smem) {
   const int Hd = nets[0].s.hid;
-  const int jobs = nnets * Hd;
-  // spread over the CTAs starting at first_job_block (the GEMM tiles of the same stage start at CTA 0)
+  const int nch = (Hd + 31) / 32;
+  const int jobs = nnets * nch;
   const int nb = (int)gridDim.x;
-  const int vb = ((int)blockIdx.x - first_job_block % nb + nb) % nb;
-  for (int j = vb * kCT + (int)threadIdx.x; j < jobs; j += nb * kCT) {
-    const int ni = j / Hd, k = j - ni * Hd;
+  const int vb = ((int)blockIdx.x - first_block % nb + nb) % nb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* red = smem;                                     // [8 warps][32 lanes][6]
+  for (int job = vb; job < jobs; job += nb) {
+    const int ni = job / nch, u = (job - ni * nch) * 32 + lane;     // this lane's hidden unit
     const NetRef& nr = nets[ni];
-    const float* Hl = sc.H(nr.slot, nr.s.layers - 1);
+    const float* X = kind == 0 ? sc.H(nr.slot, nr.s.layers - 1) : sc.dZ(nr.slot, 0);
     const float* d = sc.dout(nr.slot);
-    float g0 = 0.f, g1 = 0.f, s0 = 0.f, s1 = 0.f;
-    for (int b = 0; b < a.B; ++b) {
-      const float h = ldcg(Hl + (int64_t)b * Hd + k);
-      const float d0 = ldcg(d + 2 * b), d1 = ldcg(d + 2 * b + 1);
-      g0 = fmaf(d0, h, g0); g1 = fmaf(d1, h, g1);
-      s0 += d0; s1 += d1;
-    }
-    float* gw = nr.G + net_w_off(nr.s, nr.s.layers);
-    gw[k] = g0;
-    if (nr.s.out > 1) gw[Hd + k] = g1;
-    if (k == 0) {
-      float* gb = nr.G + net_b_off(nr.s, nr.s.layers);
-      gb[0] = s0;
-      if (nr.s.out > 1) gb[1] = s1;
-    }
-  }
-}
-
-// gW0[n][j] = sum_b dZ0[b][n] in[b][j]; gb0[n] = sum_b dZ0[b][n]: one thread per (net, n)
-__device__ void first_grads(const CoopArgs& a, const Scratch& sc, const NetRef* nets, int nnets) {
-  const int Hd = nets[0].s.hid;
-  const int jobs = nnets * Hd;
-  for (int j = (int)blockIdx.x * kCT + (int)threadIdx.x; j < jobs; j += (int)gridDim.x * kCT) {
-    const int ni = j / Hd, n = j - ni * Hd;
-    const NetRef& nr = nets[ni];
-    const float* dz = sc.dZ(nr.slot, 0);
     const float* in = sc.in4(nr.slot);
-    float gb = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < a.B; ++b) {
-      const float d = ldcg(dz + (int64_t)b * Hd + n);
-      const float4 x = ldcg4(in + (int64_t)b * 4);
-      gb += d;
-      gw[0] = fmaf(d, x.x, gw[0]); gw[1] = fmaf(d, x.y, gw[1]); gw[2] = fmaf(d, x.z, gw[2]); gw[3] = fmaf(d, x.w, gw[3]);
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    __syncthreads();                                     // the previous job's / stage's readers of `red` are done
+#pragma unroll 8
+    for (int b = warp; b < a.B; b += 8) {
+      const float x = u < Hd ? ldcg(X + (int64_t)b * Hd + u) : 0.f;
+      if (kind == 0) {
+        const float d0 = ldcg(d + 2 * b), d1 = ldcg(d + 2 * b + 1);
+        acc[0] = fmaf(d0, x, acc[0]); acc[1] = fmaf(d1, x, acc[1]);
+        acc[2] += d0; acc[3] += d1;
+      } else {
+        const float4 q = ldcg4(in + (int64_t)b * 4);
+        acc[0] = fmaf(x, q.x, acc[0]); acc[1] = fmaf(x, q.y, acc[1]); acc[2] = fmaf(x, q.z, acc[2]); acc[3] = fmaf(x, q.w, acc[3]);
+        acc[4] += x;
+      }
     }
-    nr.G[net_b_off(nr.s, 0) + n] = gb;
-    for (int jj = 0; jj < nr.s.in; ++jj) nr.G[net_w_off(nr.s, 0) + n * nr.s.in + jj] = gw[jj];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) red[(warp * 32 + lane) * 6 + q] = acc[q];
+    __syncthreads();
+    if (warp == 0 && u < Hd) {
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] += red[(w * 32 + lane) * 6 + q];
+      if (kind == 0) {
+        float* gw = nr.G + net_w_off(nr.s, nr.s.layers);
+        gw[u] = v[0];
+        if (nr.s.out > 1) gw[Hd + u] = v[1];
+        if (u == 0) {
+          float* gb = nr.G + net_b_off(nr.s, nr.s.layers);
+          gb[0] = v[2];
+          if (nr.s.out > 1) gb[1] = v[3];
+        }
+      } else {
+        nr.G[net_b_off(nr.s, 0) + u] = v[4];
+        for (int jj = 0; jj < nr.s.in; ++jj) nr.G[net_w_off(nr.s, 0) + u * nr.s.in + jj] = v[jj];
+      }
+    }
   }
+  __syncthreads();
 }
 
 // The one-hidden-layer case has no dZ_0 array (the top gradient is generated): L >= 2 is required by the launcher.
@@ -622,7 +651,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
   unsigned long long seq = a.world > 1 ? *reinterpret_cast<volatile unsigned long long*>(a.seq_counter) : 0ull;
   int k_idx = 0, ka = 0;
 
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) g_prof_slot = 0;
   for (int e = 0; e < a.E; ++e) {
+    long long* prof = (e == a.E - 1) ? a.prof : nullptr;
     // =============================================================== critic step (robot.py:312-366)
     {
       const int32_t* idx = a.idx + (int64_t)k_idx * B;
@@ -640,11 +671,11 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         sc.rowval(0)[b] = a.rp.r[j];
         sc.rowval(1)[b] = a.rp.notdone[j];
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
         TileOp ops[3] = {fwd_op(a, sc, ta, l, false), fwd_op(a, sc, c1, l, true), fwd_op(a, sc, c2, l, true)};
         run_gemm_stage(ops, 3, coop_smem);
-        grid_sync(a.bar);
+        grid_sync(a.bar, prof);
       }
       // a' = clip(pi'(s2) + clip(noise * sigma, +-c), +-max_action)        robot.py:338-339
       for (int b = global_warp(); b < B; b += total_warps()) {
@@ -664,11 +695,11 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
           *reinterpret_cast<float4*>(sc.in4(2) + 4 * b) = in;
         }
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
         TileOp ops[2] = {fwd_op(a, sc, tc1, l, false), fwd_op(a, sc, tc2, l, false)};
         run_gemm_stage(ops, 2, coop_smem);
-        grid_sync(a.bar);
+        grid_sync(a.bar, prof);
       }
       // y, Q, losses, dout                                               robot.py:342-353
       for (int b = global_warp(); b < B; b += total_warps()) {
@@ -686,7 +717,7 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
           sc.rowval(3)[b] = d2 * d2 / (float)B;
         }
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       reduce_rows_to(sc.rowval(2), B, a.critic_losses + 2 * e);
       if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 64) {           // second loss by warp 1 of block 0
         float s = 0.f;
@@ -699,14 +730,14 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       for (int l = L - 1; l >= 1; --l) {
         TileOp ops[4] = {dx_op(a, sc, c1, l), dx_op(a, sc, c2, l), dw_op(a, sc, c1, l), dw_op(a, sc, c2, l)};
         run_gemm_stage(ops, 4, coop_smem);
-        if (l == L - 1) out_grads(a, sc, trained, 2, 4 * tiles_of(ops[0], 64));
-        grid_sync(a.bar);
+        if (l == L - 1) small_grads(a, sc, trained, 2, 0, 4 * tiles_of(ops[0], 64), coop_smem);
+        grid_sync(a.bar, prof);
       }
-      first_grads(a, sc, trained, 2);
-      grid_sync(a.bar);
+      small_grads(a, sc, trained, 2, 1, 0, coop_smem);
+      grid_sync(a.bar, prof);
       if (a.world > 1) ++seq;
       adam_stage(a, 0b110, 0, seq);
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
     }
     // =============================================================== actor step (robot.py:369-398) + Polyak (robot.py:283-285)
     if (e % a.delay == 0) {
@@ -718,11 +749,11 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         const float2 s = a.rp.s[idx[b]];
         *reinterpret_cast<float4*>(sc.in4(0) + 4 * b) = make_float4(s.x, s.y, 0.f, 0.f);   // the actor is fed the raw state, robot.py:386
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
         TileOp ops[1] = {fwd_op(a, sc, ac, l, true)};
         run_gemm_stage(ops, 1, coop_smem);
-        grid_sync(a.bar);
+        grid_sync(a.bar, prof);
       }
       for (int b = global_warp(); b < B; b += total_warps()) {
         float o0, o1;
@@ -733,11 +764,11 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
           *reinterpret_cast<float2*>(sc.dout(1) + 2 * b) = make_float2(-1.0f / (float)B, 0.f);   // d(-mean Q)/dQ
         }
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
         TileOp ops[1] = {fwd_op(a, sc, c1, l, true)};
         run_gemm_stage(ops, 1, coop_smem);
-        grid_sync(a.bar);
+        grid_sync(a.bar, prof);
       }
       // loss = -mean Q1(s, pi(s)) (per-row terms, summed after the next barrier); then critic-1 backward for dQ/d(input)
       for (int b = global_warp(); b < B; b += total_warps()) {
@@ -748,7 +779,7 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       for (int l = L - 1; l >= 1; --l) {
         TileOp ops[1] = {dx_op(a, sc, c1, l)};
         run_gemm_stage(ops, 1, coop_smem);
-        grid_sync(a.bar);
+        grid_sync(a.bar, prof);
       }
       reduce_rows_to(sc.rowval(4), B, a.actor_losses + ka);
       ++ka;
@@ -767,25 +798,25 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         g1 = warp_sum(g1);
         if (lane == 0) *reinterpret_cast<float2*>(sc.dout(0) + 2 * b) = make_float2(g0, g1);
       }
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
       const NetRef trained[1] = {ac};
       for (int l = L - 1; l >= 1; --l) {
         TileOp ops[2] = {dx_op(a, sc, ac, l), dw_op(a, sc, ac, l)};
         run_gemm_stage(ops, 2, coop_smem);
-        if (l == L - 1) out_grads(a, sc, trained, 1, 2 * tiles_of(ops[0], 64));
-        grid_sync(a.bar);
+        if (l == L - 1) small_grads(a, sc, trained, 1, 0, 2 * tiles_of(ops[0], 64), coop_smem);
+        grid_sync(a.bar, prof);
       }
-      first_grads(a, sc, trained, 1);
-      grid_sync(a.bar);
+      small_grads(a, sc, trained, 1, 1, 0, coop_smem);
+      grid_sync(a.bar, prof);
       if (a.world > 1) ++seq;
       adam_stage(a, 0b001, 0b111, seq);
-      grid_sync(a.bar);
+      grid_sync(a.bar, prof);
     }
   }
   if (a.world > 1 && blockIdx.x == 0 && threadIdx.x == 0) *a.seq_counter = seq;
 }
 
-constexpr size_t kCoopSmemBytes = (2 * CTM * kAld + 2 * CTK * 64 + CTM * 4 + CTM) * sizeof(float);
+constexpr size_t kCoopSmemBytes = (2 * CTM * kAld + 2 * CTK * 64 + CTM * 4 + 5 * kMaxHidden) * sizeof(float);
 
 }  // namespace rtd3
 
@@ -804,6 +835,14 @@ int64_t rtd3_td3_coop_scratch_floats(const rtd3_td3* h, int32_t batch) {
   return Scratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers) + 64;    // + the barrier words
 }
 
+static long long* g_coop_prof = nullptr;
+/* Development aid: DEVICE buffer of 128 int64 that the next cooperative updates stamp with %globaltimer at every stage boundary of
+ * their last epoch (arrival of block 0 at the barrier, release from it); NULL switches it off. */
+int32_t rtd3_debug_coop_prof(long long* device_buf) {
+  g_coop_prof = device_buf;
+  return 0;
+}
+
 int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* a, float* coop_scratch, void* stream) {
   RTD3_CHECK_ARG(h && a && coop_scratch, "null argument");
   RTD3_CHECK_ARG(a->params && a->params_t && a->grads && a->adam_m && a->adam_v && a->steps && a->beta_pows, "null learner state");
@@ -818,6 +857,7 @@ int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* a, float* 
   if (a->epochs == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   CoopArgs c{};
+  c.prof = g_coop_prof;
   c.ar = h->ar;
   c.params = a->params; c.params_t = a->params_t; c.grads = a->grads; c.adam_m = a->adam_m; c.adam_v = a->adam_v;
   c.steps = a->steps; c.beta_pows = a->beta_pows;

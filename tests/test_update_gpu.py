@@ -77,6 +77,7 @@ def test_update_entry_point_vs_oracle_and_eager_steps(pkg):
     idx = torch.from_numpy(rs.randint(0, 1000, (E + 3, B)).astype(np.int32)).cuda()
     noise = torch.from_numpy(rs.normal(size=(E, B, 2)).astype(np.float32)).cuda()
     a1, a2 = make_agent(pkg, H, L, B, E, seed=3), make_agent(pkg, H, L, B, E, seed=3)
+    a1.update_kernel = "steps"                                  # the per-step kernels behind rtd3_td3_update (bit-identical to the eager calls)
     closs, aloss = a1.td3_update(rb, idx=idx, noise=noise, use_graph=False)
     k = 0
     cl, al = [], []

@@ -31,6 +31,19 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             print("B=%d %dx%d %s: %.1f us/epoch" % (B, L, H, kernel, e0.elapsed_time(e1) * 1e3 / (reps * E)), flush=True)
+            if kernel == "coop" and os.environ.get("RTD3_COOP_PROF"):
+                buf = torch.zeros(128, dtype=torch.int64, device=dev)
+                rt._lib.lib().rtd3_debug_coop_prof(rt._lib.ptr(buf))
+                ag.td3_update(rb, idx=idx, use_graph=False)
+                torch.cuda.synchronize()
+                rt._lib.lib().rtd3_debug_coop_prof(None)
+                st = buf.cpu().numpy()
+                st = st[st > 0]
+                # stamps alternate: arrival of block 0 at barrier k, release from barrier k
+                work = [(st[i] - (st[i - 1] if i else st[0])) / 1e3 for i in range(0, len(st), 2)]
+                wait = [(st[i + 1] - st[i]) / 1e3 for i in range(0, len(st) - 1, 2)]
+                print("   last epoch, block 0: work before each barrier (us):", " ".join("%.1f" % w for w in work))
+                print("   barrier wait (us):", " ".join("%.1f" % w for w in wait), " total %.1f" % ((st[-1] - st[0]) / 1e3), flush=True)
 
 if __name__ == "__main__":
     main()
