@@ -33,6 +33,7 @@ extern "C" {
 #define RTD3_MT_N 624                /* MT19937 state words */
 #define RTD3_DEMO_GRID 100           /* candidate lists of the nearest-demonstration search (rtd3_demo_lists): 100 x 100 cells ... */
 #define RTD3_DEMO_CELL 1.0           /* ... of side 1, the world's own cells; queries outside [0,100)^2 sweep the whole set */
+#define RTD3_ENV_DEMO_CELLS 625      /* per-env demonstration sets: 25 x 25 grid of 4 x 4 cells (rtd3_robot_process_demonstration) */
 
 #define RTD3_ERR_ARG (-1)
 #define RTD3_ERR_STATE (-2)
@@ -236,6 +237,9 @@ int32_t rtd3_robot_compose_action(const float* x, const float* y, const double* 
  * type (nullable int8 [n]): only envs of type 0 ('step') are processed; their rows are then compacted behind the
  * ring's device row counter rp_total (uint64 [1], rows ever pushed; required with type, optional otherwise -
  * when given it is advanced by n). */
+/* env_demo_pts / env_demo_cells / env_demo_count / env_demo_cap (nullable): PER-ENV demonstration sets as built by
+ * rtd3_robot_process_demonstration; when given, env i's proximity term looks at its own set (exact nearest state by a ring search over
+ * the env's 25 x 25 grid - bit-identical to the sweep) and `demo` / the lists are ignored. */
 int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_count, int32_t* hist_head, uint8_t* goal_reached,
                               uint8_t* stuck_flag, const uint8_t* demo_flag, const int32_t* plan_index,
                               const int32_t* path_length, const float* sx, const float* sy, const float* ax, const float* ay,
@@ -243,7 +247,50 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
                               const double* demo_list, int64_t num_demo, float* reward,
                               double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2,
                               float* rp_notdone, int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type,
+                              const double* env_demo_pts, const int32_t* env_demo_cells, const int32_t* env_demo_count, int64_t env_demo_cap,
                               int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Demonstrations for a batch of envs          (environment.py:140-179, robot.py:679-718, 771-823)
+ * ---------------------------------------------------------------------------------------------- */
+/* Workspace of the planner for n envs, P paths, T steps, E elites (HOST struct of DEVICE pointers, all owned by the caller). */
+typedef struct rtd3_cem_workspace {
+  float* actions;        /* [T][2][P*n]  planning_actions of the current iteration; virtual env v = p*n + i */
+  float* x;              /* [P*n] rollout state (final states of the paths after an iteration) */
+  float* y;
+  float* start_x;        /* [n] robot_current_state of the planner (float32) */
+  float* start_y;
+  double* start64;       /* nullable [2][n]: its float64 draw */
+  double* rewards;       /* [n][P] planning_path_rewards of the current iteration */
+  int32_t* elite;        /* [n][E] indices_best_paths (ascending reward) */
+  int32_t* best;         /* [n] index_best_path of the current iteration */
+  float* mean;           /* [T][2][n] best_paths_action_mean */
+  float* std;            /* [T][2][n] best_paths_action_std_dev */
+  float* best_actions;   /* [T][2][n] */
+  float* traj;           /* [T][2][n] path of the best action sequence */
+} rtd3_cem_workspace;
+
+/* Environment.get_demonstration (environment.py:140-179) for the n envs of `bank` (each env's own numpy-legacy stream, own init
+ * region [4][n] and goal [2][n]): iterations it_begin..it_end-1 of the cross-entropy-method planner (it_begin == 0 also draws the
+ * start state; a full call is 0..iterations) and, with finish != 0, the demonstration itself: demo_states / demo_actions [n][T][2]
+ * float32 = the best path of the last iteration run (its start state and first T-1 states) and its actions.  Random draws and their
+ * order are the reference's (start: 2 doubles; iteration 0: one 32-bit word per action component; later: legacy_gauss per component;
+ * path-major, then step, then component); the P*n rollouts of an iteration are one launch of the rollout kernel. */
+int32_t rtd3_env_get_demonstration(rtd3_env* h, const rtd3_mt_bank* bank, const double* region, const double* goal, const rtd3_cem_workspace* w,
+                                   int32_t iterations, int32_t paths, int32_t steps, int32_t elites, int32_t it_begin, int32_t it_end,
+                                   int32_t finish, float* demo_states, float* demo_actions, void* stream);
+
+/* Robot.process_demonstration (robot.py:679-718) for n envs, each with its own demonstration [n][T][2] (float32 states / actions):
+ * appends the T states and `augments` augmentations (robot.py:771-823; noise from env i's stream of `bank`, drawn in the reference's
+ * order - the augmented actions' noise included) to env i's set `sets` [n][cap][2] float64 (set_count [n] advanced), rebuilds the env's
+ * search grid (sorted [n][cap][2], cells [n][RTD3_ENV_DEMO_CELLS + 1]) and pushes the T-1 transitions of every env into the replay ring
+ * behind rp_total (env-major; reward = compute_reward([next_state]), robot.py:727-762, with the env's demo_flag; done on the last one).
+ * rp_s == NULL skips the push.  The caller guarantees set_count[i] + T + augments * ((T-1) * (interpolation+1) + 1) <= cap. */
+int32_t rtd3_robot_process_demonstration(const rtd3_mt_bank* bank, const double* goal, const uint8_t* demo_flag, const float* demo_states,
+                                         const float* demo_actions, int32_t steps, double* sets, int32_t* set_count, double* sorted,
+                                         int32_t* cells, int64_t cap, int32_t augments, int32_t interpolation, double noise_level, float* rp_s,
+                                         float* rp_a, float* rp_r, float* rp_s2, float* rp_notdone, int64_t capacity, uint64_t* rp_total,
+                                         void* stream);
 
 /* Candidate lists for the nearest-demonstration term of compute_reward (robot.py:753: cdist(...).min() over ALL demonstration
  * states).  For every 1 x 1 cell of the world: the states that can be the nearest one for some point of the cell - a state is
@@ -440,6 +487,11 @@ typedef struct rtd3_tick_state {
   uint8_t* penalty;             /* [n] overspent by more than 1 at the switch (robot-learning.py:73-75) */
   double tick_seconds;          /* deterministic stand-in for the wall-clock money term: cpu_time = ticks elapsed * tick_seconds */
   int64_t test_timeout_ticks;   /* TEST_TIMEOUT (constants.py:53, compared with wall time at robot-learning.py:115) in ticks */
+  /* per-env demonstration sets (rtd3_robot_process_demonstration); env_demo_pts == NULL: the shared set above is used */
+  const double* env_demo_pts;   /* [n][env_demo_cap][2], sorted by grid cell */
+  const int32_t* env_demo_cells; /* [n][RTD3_ENV_DEMO_CELLS + 1] */
+  const int32_t* env_demo_count; /* [n] */
+  int64_t env_demo_cap;
 } rtd3_tick_state;
 
 /* values of rtd3_tick_state.type beyond 0 'step' / 1 'demo' / 2 'reset' (scheduler only) */

@@ -34,7 +34,14 @@ class TickStateStruct(Structure):
                 + [("capacity", c_int64), ("rp_total", c_void_p), ("steps_bought", c_void_p), ("resets_bought", c_void_p),
                    ("philox_seed", c_uint64), ("tick_counter", c_void_p)]
                 + [(k, c_void_p) for k in ("mode", "demos_bought", "test_ticks", "test_best", "test_success", "penalty")]
-                + [("tick_seconds", c_double), ("test_timeout_ticks", c_int64)])
+                + [("tick_seconds", c_double), ("test_timeout_ticks", c_int64)]
+                + [(k, c_void_p) for k in ("env_demo_pts", "env_demo_cells", "env_demo_count")] + [("env_demo_cap", c_int64)])
+
+
+class CemWorkspaceStruct(Structure):
+    """`rtd3_cem_workspace` of include/rtd3.h."""
+    _fields_ = [(k, c_void_p) for k in ("actions", "x", "y", "start_x", "start_y", "start64", "rewards", "elite", "best", "mean", "std",
+                                        "best_actions", "traj")]
 
 
 TICK_NOISE_NONE, TICK_NOISE_GIVEN, TICK_NOISE_PHILOX = 0, 1, 2
@@ -123,7 +130,10 @@ _SIGNATURES = {
     "rtd3_robot_baseline": (c_int32, [_P, _P, _P, _P, c_int64, _P]),
     "rtd3_robot_compose_action": (c_int32, [_P] * 10 + [c_int64, _P]),
     "rtd3_demo_lists": (c_int32, [_P, c_int64, _P, _P, _P, _P]),
-    "rtd3_robot_transition": (c_int32, [_P] * 18 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P, c_int64, _P]),
+    "rtd3_robot_transition": (c_int32, [_P] * 18 + [c_int64] + [_P] * 8 + [c_int64] * 2 + [_P, _P] + [_P, _P, _P, c_int64] + [c_int64, _P]),
+    "rtd3_env_get_demonstration": (c_int32, [_P, POINTER(MtBankStruct), _P, _P, POINTER(CemWorkspaceStruct)] + [c_int32] * 7 + [_P, _P, _P]),
+    "rtd3_robot_process_demonstration": (c_int32, [POINTER(MtBankStruct), _P, _P, _P, _P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32,
+                                                   c_double, _P, _P, _P, _P, _P, c_int64, _P, _P]),
     "rtd3_robot_next_action_type": (c_int32, [_P] * 10 + [c_int64, _P]),
 }
 

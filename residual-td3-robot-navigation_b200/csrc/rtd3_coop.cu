@@ -63,7 +63,8 @@ __device__ __forceinline__ void grid_sync(const GridBarrier& b, long long* prof 
       __threadfence();
       atomicAdd(const_cast<unsigned int*>(b.gen), 1u);
     } else {
-      while (*b.gen == g) {}
+      // poll with a back-off: up to a hundred idle CTAs reading one L2 line in a tight loop delay the loads of the CTAs that work
+      while (*b.gen == g) __nanosleep(40);
     }
     __threadfence();
   }
@@ -234,8 +235,9 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
   }
 }
 
+// (not inlined: the stages call it from a dozen places, and a fully inlined kernel was 560 KB of SASS)
 template <int TN>
-__device__ void gemm_tile(const TileOp& op_in, int tm, int tn, float* smem) {
+__device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, float* smem) {
   constexpr int NT = TN / 16;                            // outputs per thread along n (4 or 2)
   float* As = smem;                                      // [2][CTM][kAld]
   float* Bs = smem + 2 * CTM * kAld;                     // [2][CTK][TN]
@@ -426,7 +428,7 @@ __device__ __forceinline__ int tiles_of(const TileOp& op, int TN) { return ((op.
 
 // Run `nops` tile operations as one stage: the tiles of all of them are dealt round-robin to the CTAs.  Narrow tiles when the wide
 // ones would leave most SMs idle.
-__device__ void run_gemm_stage(const TileOp* ops, int nops, float* smem) {
+__device__ __noinline__ void run_gemm_stage(const TileOp* ops, int nops, float* smem) {
   int total64 = 0;
   for (int i = 0; i < nops; ++i) total64 += tiles_of(ops[i], 64);
   const bool narrow = 2 * total64 <= (int)gridDim.x;
@@ -469,7 +471,7 @@ __device__ __forceinline__ void out_layer_row(const NetRef& nr, const float* __r
 // rows in flight per warp), the partial sums meet in shared memory.
 //   kind 0: gWout[o][k] = sum_b dout[b][o] H_{L-1}[b][k], gbout[o] = sum_b dout[b][o]
 //   kind 1: gW0[n][j]   = sum_b dZ0[b][n] in[b][j],        gb0[n]   = sum_b dZ0[b][n]
-__device__ void small_grads(const CoopArgs& a, const Scratch& sc, const NetRef* nets, int nnets, int kind, int first_block, float* smem) {
+__device__ __noinline__ void small_grads(const CoopArgs& a, const Scratch& sc, const NetRef* nets, int nnets, int kind, int first_block, float* smem) {
   const int Hd = nets[0].s.hid;
   const int nch = (Hd + 31) / 32;
   const int jobs = nnets * nch;
@@ -554,7 +556,7 @@ __device__ __forceinline__ float ld_volatile_f32(const float* p) {
 // Adam (torch defaults, robot.py:237-239) on the nets of `nets` (bit 0 actor, 1 critic1, 2 critic2), then Polyak on `polyak`.
 // World > 1: the gradients are first pushed to every rank's receive slot, one flag per rank is raised after a grid barrier, and the
 // optimiser sums the `world` slots of this rank's area in rank order (bit-identical replicas).
-__device__ void adam_stage(const CoopArgs& a, int nets, int polyak, unsigned long long seq) {
+__device__ __noinline__ void adam_stage(const CoopArgs& a, int nets, int polyak, unsigned long long seq) {
   const int n_online = (int)a.ar.online_total();
   const int off1 = (int)a.ar.off(1), off2 = (int)a.ar.off(2);
   const int lo = (nets & 1) ? 0 : off1, hi = (nets & 6) ? n_online : off1;      // range of gradients this step produced

@@ -195,6 +195,30 @@ __device__ inline double mt_gauss(MtStream& s, int& has_gauss, double& spare) {
   return __dmul_rn(f, x2);
 }
 
+// legacy_gauss for the lanes of a warp holding independent streams (all 32 lanes must call it; `active` lanes draw): the rejection
+// loop runs until every active lane has its pair, wrapping streams are twisted by the whole warp.  hg / sp: the lane's spare.
+__device__ __forceinline__ double mt_gauss_warp(MtStream& s, bool active, int& hg, double& sp) {
+  double v = 0.0;
+  bool searching = active && !hg;
+  if (active && hg) { v = sp; sp = 0.0; hg = 0; }
+  while (__any_sync(0xffffffffu, searching)) {
+    double u1, u2;
+    mt_next_double2_warp(s, searching, u1, u2);
+    if (searching) {
+      const double x1 = __dsub_rn(__dmul_rn(2.0, u1), 1.0), x2 = __dsub_rn(__dmul_rn(2.0, u2), 1.0);
+      const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+      if (!(r2 >= 1.0 || r2 == 0.0)) {
+        const double f = sqrt(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+        sp = __dmul_rn(f, x1);
+        hg = 1;
+        v = __dmul_rn(f, x2);
+        searching = false;
+      }
+    }
+  }
+  return v;
+}
+
 // np.linalg.norm of a 2-vector as numpy evaluates it (sqrt(dot)): measured here to be
 // sqrt(fma(dy,dy, dx*dx)) - 0 mismatches in 2e5 random pairs ("threshold compares").
 __device__ __forceinline__ double norm2_np(double dx, double dy) { return sqrt(fma(dy, dy, __dmul_rn(dx, dx))); }

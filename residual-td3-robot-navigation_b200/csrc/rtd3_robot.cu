@@ -48,6 +48,7 @@ robot_transition_kernel(RobotState st, const float* __restrict__ sx, const float
                         const double* __restrict__ list_pts, int64_t m, float* __restrict__ reward_out, double* __restrict__ reward64,
                         uint8_t* __restrict__ done_out, ReplayRing ring, const int8_t* __restrict__ type /*nullable: only type 0 steps*/,
                         int64_t n) {
+  static_assert(kEnvCells == RTD3_ENV_DEMO_CELLS, "grid size of the per-env demonstration sets");
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n && (!type || type[i] == 0);
   const int64_t ii = live ? i : 0;
@@ -204,9 +205,11 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
                               const float* sx, const float* sy, const float* ax, const float* ay, const float* nx, const float* ny,
                               const double* demo, const int32_t* demo_list_start, const double* demo_list, int64_t num_demo, float* reward,
                               double* reward64, uint8_t* done, float* rp_s, float* rp_a, float* rp_r, float* rp_s2, float* rp_notdone,
-                              int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type, int64_t n, void* stream) {
+                              int64_t capacity, int64_t position, uint64_t* rp_total, const int8_t* type, const double* env_demo_pts,
+                              const int32_t* env_demo_cells, const int32_t* env_demo_count, int64_t env_demo_cap, int64_t n, void* stream) {
   RTD3_CHECK_ARG(goal && hist && hist_count && hist_head && goal_reached && stuck_flag && demo_flag && plan_index && path_length,
                  "null robot state");
+  RTD3_CHECK_ARG(!env_demo_pts || (env_demo_cells && env_demo_count && env_demo_cap > 0), "incomplete per-env demonstration sets");
   RTD3_CHECK_ARG(sx && sy && ax && ay && nx && ny && reward && done, "null transition array");
   RTD3_CHECK_ARG(num_demo == 0 || demo, "demo set missing");
   RTD3_CHECK_ARG((demo_list_start == nullptr) == (demo_list == nullptr), "demo_list_start and demo_list go together");
@@ -214,7 +217,8 @@ int32_t rtd3_robot_transition(const double* goal, float* hist, int32_t* hist_cou
   RTD3_CHECK_ARG(!rp_s || (rp_a && rp_r && rp_s2 && rp_notdone && capacity > 0 && position >= 0 && position < capacity && n <= capacity),
                  "bad replay ring");
   if (n == 0) return 0;
-  RobotState st{goal, hist, hist_count, hist_head, goal_reached, stuck_flag, demo_flag, plan_index, path_length};
+  RobotState st{goal, hist, hist_count, hist_head, goal_reached, stuck_flag, demo_flag, plan_index, path_length,
+                env_demo_pts, env_demo_cells, env_demo_count, env_demo_cap};
   RTD3_CHECK_ARG(!(type && rp_s) || rp_total, "a masked push needs the ring's device row counter");
   ReplayRing ring{(float2*)rp_s, (float2*)rp_a, rp_r, (float2*)rp_s2, rp_notdone, capacity, position, (unsigned long long*)rp_total};
   const int block = n <= 148 * 256 ? 128 : 256;      // a small batch spread over more SMs

@@ -23,7 +23,59 @@ struct RobotState {
   const uint8_t* demo_flag; // [n]
   const int32_t* plan_index;
   const int32_t* path_length;
+  // per-env demonstration sets (batched process_demonstration; all NULL / 0: the shared set passed next to this struct is used)
+  const double* env_pts;        // [n][env_cap][2] float64, every env's states sorted by grid cell (demo_grid_build_kernel)
+  const int32_t* env_cells;     // [n][kEnvCells + 1] start offsets of the cells in env_pts
+  const int32_t* env_count;     // [n] states held
+  int64_t env_cap;
 };
+
+// Per-env demonstration sets (each env of a batch has bought its own demonstrations, as each reference run does): a uniform
+// 25 x 25 grid of 4 x 4 cells per env, states outside the world filed under the nearest border cell.  The query scans the rings of
+// cells around its own cell until the best squared distance found is no larger than the squared distance to the border of the
+// scanned square (no state outside it can be nearer) - the same three float64 operations per candidate as the full sweep, and the
+// minimum over a set that contains the true nearest state: bit-identical to robot.py:753's cdist(...).min().
+constexpr int kEnvGrid = 25;
+constexpr double kEnvCell = 4.0;
+constexpr int kEnvCells = kEnvGrid * kEnvGrid;
+__device__ __forceinline__ int env_cell_coord(double v) {
+  const int c = (int)floor(v / kEnvCell);
+  return c < 0 ? 0 : (c > kEnvGrid - 1 ? kEnvGrid - 1 : c);
+}
+__device__ __forceinline__ double env_scan_cell(const double2* __restrict__ pts, const int32_t* __restrict__ cells, int gx, int gy, double px,
+                                                double py, double best) {
+  const int c = gx * kEnvGrid + gy;
+  const int k1 = cells[c + 1];
+  for (int k = cells[c]; k < k1; ++k) {
+    const double2 t = pts[k];
+    const double dx = px - t.x, dy = py - t.y;
+    best = fmin(best, fma(dy, dy, dx * dx));
+  }
+  return best;
+}
+__device__ __forceinline__ double nearest_demo_env_sq(double px, double py, const double2* __restrict__ pts, const int32_t* __restrict__ cells) {
+  const int cx = env_cell_coord(px), cy = env_cell_coord(py);
+  double best = INFINITY;
+  for (int r = 0; r < kEnvGrid; ++r) {
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
+    for (int gx = max(x0, 0); gx <= min(x1, kEnvGrid - 1); ++gx) {
+      if (gx == x0 || gx == x1) {
+        for (int gy = max(y0, 0); gy <= min(y1, kEnvGrid - 1); ++gy) best = env_scan_cell(pts, cells, gx, gy, px, py, best);
+      } else {
+        if (y0 >= 0) best = env_scan_cell(pts, cells, gx, y0, px, py, best);
+        if (y1 <= kEnvGrid - 1 && y1 != y0) best = env_scan_cell(pts, cells, gx, y1, px, py, best);
+      }
+    }
+    // states not scanned yet lie beyond the border of the scanned square on a side where cells remain
+    double bound = INFINITY;
+    if (x0 > 0) bound = fmin(bound, px - (double)x0 * kEnvCell);
+    if (x1 < kEnvGrid - 1) bound = fmin(bound, (double)(x1 + 1) * kEnvCell - px);
+    if (y0 > 0) bound = fmin(bound, py - (double)y0 * kEnvCell);
+    if (y1 < kEnvGrid - 1) bound = fmin(bound, (double)(y1 + 1) * kEnvCell - py);
+    if (bound == INFINITY || best <= bound * bound * (1.0 - 1e-12)) break;
+  }
+  return best;
+}
 
 struct ReplayRing {
   float2* s; float2* a; float* r; float2* s2; float* notdone;
@@ -154,7 +206,13 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
   const bool reached = (-gd >= -kGoalRadius);
   // nearest demonstration state (only needed when the goal was not reached, the demo phase is over and there are demos)
   double best = INFINITY;
-  if (m > 0 && list_start) {
+  int64_t m_env = m;                                    // demonstration states this env's reward looks at
+  if (st.env_pts) {
+    m_env = live ? (int64_t)st.env_count[i] : 0;
+    if (live && !reached && demo_phase_over && m_env > 0)
+      best = nearest_demo_env_sq(px, py, reinterpret_cast<const double2*>(st.env_pts) + (int64_t)i * st.env_cap,
+                                 st.env_cells + (int64_t)i * (kEnvCells + 1));
+  } else if (m > 0 && list_start) {
     if (live && !reached && demo_phase_over) best = nearest_demo_sq(px, py, demo, m, list_start, list_pts);
   } else if (kAllowSweep && m > 0) {
     // (callers that cannot take a block-wide barrier here - a subset of the CTA's warps - instantiate kAllowSweep = false and
@@ -188,7 +246,7 @@ __device__ __forceinline__ void transition_env(const RobotState& st, const float
     if (reached) {
       st.goal_reached[i] = 1;
       reward = kGoalReward;
-    } else if (m == 0) {
+    } else if (m_env == 0) {
       reward = -gd;
     } else {
       const double prox = demo_phase_over ? -sqrt(best) : 0.0;

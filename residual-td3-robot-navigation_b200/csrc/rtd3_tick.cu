@@ -113,7 +113,8 @@ __device__ __forceinline__ void tick_post_env(const rtd3_tick_state& t, const fl
   float nx, ny;
   step_one<true>(LdgTable{table}, x, y, ax, ay, nx, ny);
   // process_transition (reward, stuck ring, done, compacted replay push)
-  const RobotState st{t.goal, t.hist, t.hist_count, t.hist_head, t.goal_reached, t.stuck_flag, t.demo_flag, t.plan_index, t.path_length};
+  const RobotState st{t.goal, t.hist, t.hist_count, t.hist_head, t.goal_reached, t.stuck_flag, t.demo_flag, t.plan_index, t.path_length,
+                      t.env_demo_pts, t.env_demo_cells, t.env_demo_count, t.env_demo_cap};
   const ReplayRing ring{(float2*)t.rp_s, (float2*)t.rp_a, t.rp_r, (float2*)t.rp_s2, t.rp_notdone, t.capacity, 0,
                         (unsigned long long*)t.rp_total};
   transition_env<kAllowSweep>(st, x, y, ax, ay, nx, ny, live, i, n, t.demo, t.demo_list_start, t.demo_list, t.num_demo, t.reward, t.reward64, t.done,
@@ -248,6 +249,7 @@ static int32_t check_state(const rtd3_tick_state* t) {
   RTD3_CHECK_ARG(t->rp_s && t->rp_a && t->rp_r && t->rp_s2 && t->rp_notdone && t->rp_total && t->capacity > 0 && t->n <= t->capacity,
                  "bad replay ring");
   RTD3_CHECK_ARG(t->steps_bought && t->resets_bought, "null money counters");
+  RTD3_CHECK_ARG(!t->env_demo_pts || (t->env_demo_cells && t->env_demo_count && t->env_demo_cap > 0), "incomplete per-env demonstration sets");
   if (t->mode) {
     RTD3_CHECK_ARG(t->demos_bought && t->test_ticks && t->test_best && t->test_success && t->penalty, "scheduler arrays missing (mode is set)");
     RTD3_CHECK_ARG(t->tick_counter, "the scheduler charges time per tick: tick_counter is required");
@@ -294,7 +296,7 @@ int32_t rtd3_tick_run_f16(rtd3_env* h, const rtd3_tick_state* t, int32_t hidden,
   RTD3_CHECK_ARG(params && params_h, "null parameters");
   RTD3_CHECK_ARG(hidden % 32 == 0 && hidden >= 64 && hidden <= 256 && layers == 2, "needs layers == 2 and hidden in {64..256} divisible by 32");
   RTD3_CHECK_ARG(noise_mode == RTD3_TICK_NOISE_NONE || noise_mode == RTD3_TICK_NOISE_PHILOX, "noise must be none or philox");
-  RTD3_CHECK_ARG(t->num_demo == 0 || t->demo_list_start, "needs candidate lists (rtd3_demo_lists) or no demonstration states");
+  RTD3_CHECK_ARG(t->num_demo == 0 || t->demo_list_start || t->env_demo_pts, "needs candidate lists (rtd3_demo_lists), per-env sets or no demonstration states");
   RTD3_CHECK_ARG(ticks >= 0 && ticks < (1ll << 30), "bad tick count");
   // CTAs run their ticks without a grid-wide barrier, so two CTAs can be up to `ticks` ticks apart: the rows they reserve through
   // the ring counter must not alias, i.e. everything one launch can push has to fit in the ring.
