@@ -386,7 +386,7 @@ class Environment:
         every iteration run as one launch of the rollout kernel (float32 state, so paths agree with the float64
         reference to the per-step tolerance, not bit for bit)."""
         if self.num_envs != 1:
-            raise NotImplementedError("get_demonstration is defined for the single-env form")
+            return self._get_demonstration_batched()
         c = constants
         I, P, T, E = c.DEMOS_CEM_NUM_ITERATIONS, c.DEMOS_CEM_NUM_PATHS, c.DEMOS_CEM_PATH_LENGTH, c.DEMOS_CEM_NUM_ELITES
         planning_actions = np.zeros([I, P, T, 2], dtype=np.float32)
@@ -415,6 +415,35 @@ class Environment:
             std = np.std(planning_actions[it, elites], axis=0)
         best = np.argmax(planning_path_rewards[-1])
         return planning_paths[-1, best, 0:T], planning_actions[-1, best]
+
+    def _cem_workspace(self):
+        """Device buffers of the batched planner (`rtd3_cem_workspace`), allocated on first use and kept."""
+        if getattr(self, "_cem", None) is None:
+            c, n, dev = constants, self.num_envs, self.device
+            P, T, E = c.DEMOS_CEM_NUM_PATHS, c.DEMOS_CEM_PATH_LENGTH, c.DEMOS_CEM_NUM_ELITES
+            f32 = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+            t = {"actions": f32(T, 2, P * n), "x": f32(P * n), "y": f32(P * n), "start_x": f32(n), "start_y": f32(n),
+                 "start64": torch.zeros((2, n), dtype=torch.float64, device=dev), "rewards": torch.zeros((n, P), dtype=torch.float64, device=dev),
+                 "elite": torch.zeros((n, E), dtype=torch.int32, device=dev), "best": torch.zeros((n,), dtype=torch.int32, device=dev),
+                 "mean": f32(T, 2, n), "std": f32(T, 2, n), "best_actions": f32(T, 2, n), "traj": f32(T, 2, n)}
+            w = _lib.CemWorkspaceStruct(*[t[k].data_ptr() for k, _ in _lib.CemWorkspaceStruct._fields_])
+            self._cem = (t, w)
+        return self._cem
+
+    def _get_demonstration_batched(self, it_begin=0, it_end=None, finish=True):
+        """`get_demonstration` for all N envs at once (`rtd3_env_get_demonstration`): every env plans from its own start state to
+        its own goal on its own MT19937 stream - the draws and their order are the reference's - and the 100 x N rollouts of an
+        iteration are one launch of the rollout kernel.  Returns (states `[N,200,2]`, actions `[N,200,2]`) float32 CUDA tensors.
+        `it_begin / it_end / finish` run a part of the planner (tests look at the workspace between iterations)."""
+        c, n = constants, self.num_envs
+        I, P, T, E = c.DEMOS_CEM_NUM_ITERATIONS, c.DEMOS_CEM_NUM_PATHS, c.DEMOS_CEM_PATH_LENGTH, c.DEMOS_CEM_NUM_ELITES
+        t, w = self._cem_workspace()
+        states = torch.empty((n, T, 2), dtype=torch.float32, device=self.device) if finish else None
+        actions = torch.empty((n, T, 2), dtype=torch.float32, device=self.device) if finish else None
+        _lib.check(_lib.lib().rtd3_env_get_demonstration(self._handle, self._bank.ref, _lib.ptr(self._region), _lib.ptr(self._goal),
+                                                         _lib.ctypes.byref(w), I, P, T, E, it_begin, I if it_end is None else it_end, 1 if finish else 0,
+                                                         _lib.ptr(states), _lib.ptr(actions), _lib.stream_ptr(self.device)), "env_get_demonstration")
+        return states, actions
 
     # ---- environment.py:182-183 ---------------------------------------------------------------------
     def compute_reward(self, path):

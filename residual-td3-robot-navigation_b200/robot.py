@@ -35,6 +35,7 @@ DEMO_PROXIMITY_FACTOR = 10
 
 ACTION_TYPES = ("step", "demo", "reset")
 DEMO_GRID, DEMO_CELL = 100, 1.0         # RTD3_DEMO_GRID / RTD3_DEMO_CELL of include/rtd3.h
+ENV_DEMO_CELLS = 625                    # RTD3_ENV_DEMO_CELLS
 
 
 class PathToDraw:
@@ -81,6 +82,7 @@ class Robot:
         self._demo_cells = None                                 # int32 [DEMO_GRID^2 + 1] offsets into _demo_list, or None: full sweep
         self._demo_list = None                                  # [total,2] float64: per-cell candidate lists (rtd3_demo_lists)
         self.demo_grid_min_points = 64                          # smaller sets are swept in full
+        self._env_demo = None                                   # per-env sets (batched process_demonstration), else the shared set above
         # per-env episode state (robot.py:421-438)
         self._num_episodes = torch.zeros(n, dtype=torch.int32, device=dev)
         self._noise_scale = torch.full((n,), float(INITIAL_NOISE), dtype=torch.float64, device=dev)
@@ -279,6 +281,7 @@ class Robot:
         sp, ap, npl = self._state_planes(state), self._state_planes(action), self._state_planes(next_state)
         m = 0 if self._demo_dev is None else self._demo_dev.shape[0]
         rb = self.memory
+        d = self._env_demo
         if push and n > rb.capacity:
             raise ValueError("more envs than replay rows: raise buffer_size")
         _lib.check(_lib.lib().rtd3_robot_transition(
@@ -287,7 +290,9 @@ class Robot:
             _lib.ptr(sp[0]), _lib.ptr(sp[1]), _lib.ptr(ap[0]), _lib.ptr(ap[1]), _lib.ptr(npl[0]), _lib.ptr(npl[1]),
             _lib.ptr(self._demo_dev), _lib.ptr(self._demo_cells), _lib.ptr(self._demo_list), m, _lib.ptr(self._reward), _lib.ptr(self._reward64), _lib.ptr(self._done),
             _lib.ptr(rb.s if push else None), _lib.ptr(rb.a), _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), rb.capacity,
-            0 if types is not None else rb.position, _lib.ptr(rb._total_dev), _lib.ptr(types), n, _lib.stream_ptr(self.device)),
+            0 if types is not None else rb.position, _lib.ptr(rb._total_dev), _lib.ptr(types),
+            _lib.ptr(d["sorted"] if d else None), _lib.ptr(d["cells"] if d else None), _lib.ptr(d["count"] if d else None), d["cap"] if d else 0,
+            n, _lib.stream_ptr(self.device)),
             "robot_transition")
         if push:
             if types is None:
@@ -311,7 +316,7 @@ class Robot:
     # ---- robot.py:679-718, 771-823 (host side: "next" row f-2 of SURVEY.md 8) -------------------------------------------
     def process_demonstration(self, demonstration_states, demonstration_actions, money_remaining):
         if self.batched:
-            raise NotImplementedError("per-env demonstration sets are not batched yet; use set_demonstration_states")
+            return self._process_demonstration_batched(demonstration_states, demonstration_actions)
         demonstration_states = np.asarray(demonstration_states)
         demonstration_actions = np.asarray(demonstration_actions)
         self.demonstration_states.extend(demonstration_states)
@@ -338,6 +343,50 @@ class Robot:
         self.memory.push(cu(demonstration_states[:-1]), cu(demonstration_actions[:-1]), cu(rew), cu(demonstration_states[1:]),
                          torch.from_numpy(done).to(self.device))
         self._goal_reached.zero_()                              # robot.py:718
+
+    def _process_demonstration_batched(self, demonstration_states, demonstration_actions):
+        """process_demonstration for all N envs (`rtd3_robot_process_demonstration`): `[N,T,2]` float32 CUDA tensors, one
+        demonstration per env.  Every env keeps its OWN demonstration set, as every reference run does: the T states and their three
+        augmentations (noise from the env's stream, in the reference's draw order) are appended to it, its search grid is rebuilt,
+        and the env's T-1 transitions go into the shared replay ring.  From then on the proximity term of env i's reward looks at
+        env i's set.  (`demonstration_states` stays a host list only for the single-env form; `demonstration_sets()` reads these.)"""
+        n = self.num_envs
+        S = demonstration_states.to(self.device, torch.float32).contiguous()
+        A = demonstration_actions.to(self.device, torch.float32).contiguous()
+        if S.dim() != 3 or S.shape[0] != n or S.shape[2] != 2 or A.shape != S.shape:
+            raise ValueError("demonstration_states / demonstration_actions must be [%d,T,2]" % n)
+        T = S.shape[1]
+        per_demo = T + NUM_AUGMENTS * ((T - 1) * (AUG_INTERPOLATION + 1) + 1)
+        if self._env_demo is None:
+            cap = NUM_DEMO * per_demo
+            self._env_demo = {"cap": cap, "demos": 0,
+                              "sets": torch.zeros((n, cap, 2), dtype=torch.float64, device=self.device),
+                              "sorted": torch.zeros((n, cap, 2), dtype=torch.float64, device=self.device),
+                              "count": torch.zeros((n,), dtype=torch.int32, device=self.device),
+                              "cells": torch.zeros((n, ENV_DEMO_CELLS + 1), dtype=torch.int32, device=self.device)}
+        d = self._env_demo
+        if (d["demos"] + 1) * per_demo > d["cap"]:
+            grow = d["cap"] + NUM_DEMO * per_demo
+            for k in ("sets", "sorted"):
+                big = torch.zeros((n, grow, 2), dtype=torch.float64, device=self.device)
+                big[:, :d["cap"]] = d[k]
+                d[k] = big
+            d["cap"] = grow
+        rb = self.memory
+        _lib.check(_lib.lib().rtd3_robot_process_demonstration(
+            self._bank.ref, _lib.ptr(self._goal), _lib.ptr(self._demo_flag), _lib.ptr(S), _lib.ptr(A), T, _lib.ptr(d["sets"]), _lib.ptr(d["count"]),
+            _lib.ptr(d["sorted"]), _lib.ptr(d["cells"]), d["cap"], NUM_AUGMENTS, AUG_INTERPOLATION, float(AUG_NOISE), _lib.ptr(rb.s), _lib.ptr(rb.a),
+            _lib.ptr(rb.r), _lib.ptr(rb.s2), _lib.ptr(rb.notdone), rb.capacity, _lib.ptr(rb._total_dev), _lib.stream_ptr(self.device)),
+            "robot_process_demonstration")
+        d["demos"] += 1
+        rb._mark_device_advanced()
+        self._goal_reached.zero_()                              # robot.py:718
+
+    def demonstration_sets(self):
+        """Batched form: (states `[N,cap,2]` float64 in the reference's append order, counts `[N]`) of the per-env sets, or None."""
+        if self._env_demo is None:
+            return None
+        return self._env_demo["sets"], self._env_demo["count"]
 
     def set_demonstration_states(self, states):
         """Install a demonstration-state set `[M,2]` directly (batched mode: one set shared by all envs)."""

@@ -306,6 +306,9 @@ class BatchedTrainer:
         t.capacity, t.rp_total = rb.capacity, p(rb._total_dev)
         t.steps_bought, t.resets_bought = p(self.steps_bought), p(self.resets_bought)
         t.philox_seed, t.tick_counter = self.philox_seed, p(self._tick_counter)
+        if robot._env_demo is not None:
+            d = robot._env_demo
+            t.env_demo_pts, t.env_demo_cells, t.env_demo_count, t.env_demo_cap = p(d["sorted"]), p(d["cells"]), p(d["count"]), d["cap"]
         if self.scheduler:
             t.mode, t.demos_bought, t.test_ticks, t.test_best = p(self.mode), p(self.demos_bought), p(self.test_ticks), p(self.test_best_distance)
             t.test_success, t.penalty = p(self.test_success), p(self.penalty)
@@ -404,7 +407,9 @@ class BatchedTrainer:
         # tensor-core-mode update: with it in the signature the f16 tick was re-captured - a gc.collect() and 24 launches - right
         # after the first update, inside whatever was being timed)
         fwd = p(agent.params_h) if agent._f16_ok(self.n) else (p(agent.params_u) if agent._tc_ok(self.n) else None)
-        sig = (p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list), agent.precision, fwd)
+        ed = robot._env_demo
+        sig = (p(robot._demo_dev), p(robot._demo_cells), p(robot._demo_list), agent.precision, fwd,
+               None if ed is None else (p(ed["sorted"]), p(ed["cells"]), ed["cap"]))
         if sig != getattr(self, "_graph_sig", None):
             self._graph = self._graph_k = None
             self._graph_sig = sig
