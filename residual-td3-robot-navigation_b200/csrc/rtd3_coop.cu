@@ -243,12 +243,9 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
   float* Bs = smem + 2 * CTM * kAld;                     // [2][CTK][TN]
   float* in_s = Bs + 2 * CTK * TN;                       // [CTM][4]
   float* w_s = in_s + CTM * 4;                           // [5][kMaxHidden]: first layer (W0 | b0) or output layer weights of the generators
-  __shared__ TileOp s_op;                                // the operation, out of the caller's local memory
+  const TileOp& op = op_in;                              // lives in shared memory (see stage_ops)
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   __syncthreads();                                       // the previous tile's readers are done with the shared buffers
-  if (t == 0) s_op = op_in;
-  __syncthreads();
-  const TileOp& op = s_op;
   const int m0 = tm * CTM, n0 = tn * TN;
   float acc[2][NT];
 #pragma unroll
@@ -645,6 +642,12 @@ __device__ __forceinline__ void reduce_rows_to(const float* rows, int B, float* 
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------------------------
+// The tile operations of the current stage.  Built by ONE thread into shared memory: as per-thread local arrays they cost every
+// thread of every CTA ~100 local stores per stage (30 MB of L2 write traffic per stage over the grid - it made every stage, and
+// every L2 access of the kernel, several times slower; ncu r2a: 554 k local store instructions for two epochs).
+__shared__ TileOp s_ops[4];
+__shared__ NetRef s_nets[2];
+
 __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
   extern __shared__ __align__(16) float coop_smem[];
   const Scratch sc{a.scratch, (a.B + 31) / 32 * 32, a.ar.critic.hid, a.ar.critic.layers};
@@ -675,8 +678,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       }
       grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
-        TileOp ops[3] = {fwd_op(a, sc, ta, l, false), fwd_op(a, sc, c1, l, true), fwd_op(a, sc, c2, l, true)};
-        run_gemm_stage(ops, 3, coop_smem);
+        if (threadIdx.x == 0) { s_ops[0] = fwd_op(a, sc, ta, l, false); s_ops[1] = fwd_op(a, sc, c1, l, true); s_ops[2] = fwd_op(a, sc, c2, l, true); }
+        __syncthreads();
+        run_gemm_stage(s_ops, 3, coop_smem);
         grid_sync(a.bar, prof);
       }
       // a' = clip(pi'(s2) + clip(noise * sigma, +-c), +-max_action)        robot.py:338-339
@@ -699,8 +703,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       }
       grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
-        TileOp ops[2] = {fwd_op(a, sc, tc1, l, false), fwd_op(a, sc, tc2, l, false)};
-        run_gemm_stage(ops, 2, coop_smem);
+        if (threadIdx.x == 0) { s_ops[0] = fwd_op(a, sc, tc1, l, false); s_ops[1] = fwd_op(a, sc, tc2, l, false); }
+        __syncthreads();
+        run_gemm_stage(s_ops, 2, coop_smem);
         grid_sync(a.bar, prof);
       }
       // y, Q, losses, dout                                               robot.py:342-353
@@ -728,14 +733,15 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         if (lane == 0) a.critic_losses[2 * e + 1] = s;
       }
       // backward through the hidden layers, top down; the output-layer gradients ride along in the first of these stages
-      const NetRef trained[2] = {c1, c2};
+      if (threadIdx.x == 0) { s_nets[0] = c1; s_nets[1] = c2; }
       for (int l = L - 1; l >= 1; --l) {
-        TileOp ops[4] = {dx_op(a, sc, c1, l), dx_op(a, sc, c2, l), dw_op(a, sc, c1, l), dw_op(a, sc, c2, l)};
-        run_gemm_stage(ops, 4, coop_smem);
-        if (l == L - 1) small_grads(a, sc, trained, 2, 0, 4 * tiles_of(ops[0], 64), coop_smem);
+        if (threadIdx.x == 0) { s_ops[0] = dx_op(a, sc, c1, l); s_ops[1] = dx_op(a, sc, c2, l); s_ops[2] = dw_op(a, sc, c1, l); s_ops[3] = dw_op(a, sc, c2, l); }
+        __syncthreads();
+        run_gemm_stage(s_ops, 4, coop_smem);
+        if (l == L - 1) small_grads(a, sc, s_nets, 2, 0, 4 * tiles_of(s_ops[0], 64), coop_smem);
         grid_sync(a.bar, prof);
       }
-      small_grads(a, sc, trained, 2, 1, 0, coop_smem);
+      small_grads(a, sc, s_nets, 2, 1, 0, coop_smem);
       grid_sync(a.bar, prof);
       if (a.world > 1) ++seq;
       adam_stage(a, 0b110, 0, seq);
@@ -753,8 +759,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       }
       grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
-        TileOp ops[1] = {fwd_op(a, sc, ac, l, true)};
-        run_gemm_stage(ops, 1, coop_smem);
+        if (threadIdx.x == 0) s_ops[0] = fwd_op(a, sc, ac, l, true);
+        __syncthreads();
+        run_gemm_stage(s_ops, 1, coop_smem);
         grid_sync(a.bar, prof);
       }
       for (int b = global_warp(); b < B; b += total_warps()) {
@@ -768,8 +775,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       }
       grid_sync(a.bar, prof);
       for (int l = 1; l < L; ++l) {
-        TileOp ops[1] = {fwd_op(a, sc, c1, l, true)};
-        run_gemm_stage(ops, 1, coop_smem);
+        if (threadIdx.x == 0) s_ops[0] = fwd_op(a, sc, c1, l, true);
+        __syncthreads();
+        run_gemm_stage(s_ops, 1, coop_smem);
         grid_sync(a.bar, prof);
       }
       // loss = -mean Q1(s, pi(s)) (per-row terms, summed after the next barrier); then critic-1 backward for dQ/d(input)
@@ -779,8 +787,9 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         if (lane == 0) sc.rowval(4)[b] = -q / (float)B;
       }
       for (int l = L - 1; l >= 1; --l) {
-        TileOp ops[1] = {dx_op(a, sc, c1, l)};
-        run_gemm_stage(ops, 1, coop_smem);
+        if (threadIdx.x == 0) s_ops[0] = dx_op(a, sc, c1, l);
+        __syncthreads();
+        run_gemm_stage(s_ops, 1, coop_smem);
         grid_sync(a.bar, prof);
       }
       reduce_rows_to(sc.rowval(4), B, a.actor_losses + ka);
@@ -801,14 +810,15 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
         if (lane == 0) *reinterpret_cast<float2*>(sc.dout(0) + 2 * b) = make_float2(g0, g1);
       }
       grid_sync(a.bar, prof);
-      const NetRef trained[1] = {ac};
+      if (threadIdx.x == 0) s_nets[0] = ac;
       for (int l = L - 1; l >= 1; --l) {
-        TileOp ops[2] = {dx_op(a, sc, ac, l), dw_op(a, sc, ac, l)};
-        run_gemm_stage(ops, 2, coop_smem);
-        if (l == L - 1) small_grads(a, sc, trained, 1, 0, 2 * tiles_of(ops[0], 64), coop_smem);
+        if (threadIdx.x == 0) { s_ops[0] = dx_op(a, sc, ac, l); s_ops[1] = dw_op(a, sc, ac, l); }
+        __syncthreads();
+        run_gemm_stage(s_ops, 2, coop_smem);
+        if (l == L - 1) small_grads(a, sc, s_nets, 1, 0, 2 * tiles_of(s_ops[0], 64), coop_smem);
         grid_sync(a.bar, prof);
       }
-      small_grads(a, sc, trained, 1, 1, 0, coop_smem);
+      small_grads(a, sc, s_nets, 1, 1, 0, coop_smem);
       grid_sync(a.bar, prof);
       if (a.world > 1) ++seq;
       adam_stage(a, 0b001, 0b111, seq);

@@ -534,3 +534,63 @@ def make_loop():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "loop":
     make_loop()
+
+
+def make_demo():
+    """Demonstrations: the reference's CEM planner (environment.py:140-179) with its random draws recorded
+    (np.random.choice / np.random.normal are wrapped to log what they return - the reference itself is untouched), and
+    augment_demonstration_data (robot.py:771-823) on the planner's output."""
+    import torch
+    env_m, rob_m, constants = load_reference()
+    speed, angle = synthetic_maps(0)
+    out = {}
+    for k, seed in enumerate((SEED0, 77)):
+        np.random.seed(seed)
+        e = env_m.Environment()
+        e.dynamics_speed, e.dynamics_angle = speed, angle
+        e.reset()
+        choices, normals, locs, scales = [], [], [], []
+        real_choice, real_normal = np.random.choice, np.random.normal
+        def rec_choice(*a, **kw):
+            v = real_choice(*a, **kw)
+            choices.append(np.array(v))
+            return v
+        def rec_normal(loc=0.0, scale=1.0, size=None):
+            v = real_normal(loc, scale, size)
+            normals.append(np.array(v)); locs.append(np.array(loc)); scales.append(np.array(scale))
+            return v
+        np.random.choice, np.random.normal = rec_choice, rec_normal
+        try:
+            ds, da = e.get_demonstration()
+        finally:
+            np.random.choice, np.random.normal = real_choice, real_normal
+        P, T = constants.DEMOS_CEM_NUM_PATHS, constants.DEMOS_CEM_PATH_LENGTH
+        ch = np.array(choices).reshape(P, T, 2)
+        nm = np.array(normals).reshape(3, P, T, 2)
+        out.update({"seed_%d" % k: np.int64(seed), "goal_%d" % k: np.array(e.goal_state), "region_%d" % k: np.array(e.robot_init_region),
+                    "start_%d" % k: np.array(ds[0], dtype=np.float64), "it0_actions_%d" % k: ch[:4].astype(np.float32),
+                    "it1_draws_%d" % k: nm[0, :2], "it1_mean_%d" % k: np.array(locs[:T], dtype=np.float32),
+                    "it1_std_%d" % k: np.array(scales[:T], dtype=np.float32),
+                    "it3_mean_%d" % k: np.array(locs[2 * P * T:2 * P * T + T], dtype=np.float32),
+                    "demo_states_%d" % k: np.array(ds), "demo_actions_%d" % k: np.array(da),
+                    "uniform_after_plan_%d" % k: np.float64(np.random.uniform())})
+        # augmentation on this demonstration, from a fresh seed
+        torch.manual_seed(0)
+        robot = rob_m.Robot(e.goal_state)
+        np.random.seed(seed + 1)
+        robot.augment_demonstration_data(ds, da)
+        out.update({"aug_states_%d" % k: np.array([np.asarray(s, dtype=np.float64) for s in robot.demonstration_states]),
+                    "uniform_after_aug_%d" % k: np.float64(np.random.uniform())})
+        # process_demonstration rows (demo_flag False, as at the reference's call sites)
+        robot2 = rob_m.Robot(e.goal_state)
+        np.random.seed(seed + 2)
+        robot2.process_demonstration(ds, da, 100.0)
+        rows = robot2.memory.buffer
+        out.update({"rows_reward_%d" % k: np.array([r[2] for r in rows], dtype=np.float64), "rows_done_%d" % k: np.array([r[4] for r in rows]),
+                    "rows_state_%d" % k: np.array([r[0] for r in rows]), "n_demo_states_%d" % k: np.int64(len(robot2.demonstration_states))})
+    np.savez_compressed(os.path.join(HERE, "demo_golden.npz"), **out)
+    print("demo_golden.npz written:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "demo":
+    make_demo()
