@@ -42,39 +42,42 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 }
 
 // ---- grid barrier (all CTAs are co-resident: cooperative launch) ---------------------------------------------------------------
+// Arrival: one counter.  Release: kBarLines generation words in DIFFERENT 128 B lines; CTA b polls line b % kBarLines with a back-off.
+// (With every idle CTA polling ONE word in a tight loop, the L2 slice that owns it saturates - a hundred pollers against a slice
+// that serves about one request per clock - and every load of the working CTAs that maps to that slice queues behind them: all
+// stages of the kernel ran ~4x slower than their instruction counts explain, ncu r2a.)
+constexpr int kBarLines = 16;
+constexpr int kBarWords = 32 * (1 + kBarLines);          // floats of scratch header: counter line + generation lines
 struct GridBarrier {
   unsigned int* count;
-  volatile unsigned int* gen;
+  volatile unsigned int* gen;                            // gen[32 * g], g < kBarLines
 };
 __device__ int g_prof_slot;
+__device__ __forceinline__ void prof_stamp(long long* prof) {
+  long long now;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+  const int s = g_prof_slot;
+  if (s < 126) { prof[s] = now; g_prof_slot = s + 1; }
+}
 __device__ __forceinline__ void grid_sync(const GridBarrier& b, long long* prof = nullptr) {
   __syncthreads();
-  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {      // time at which block 0 ARRIVES (its own work of the stage is done)
-    long long now;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-    const int s = g_prof_slot;
-    if (s < 126) { prof[s] = now; g_prof_slot = s + 1; }
-  }
   if (threadIdx.x == 0) {
-    const unsigned int g = *b.gen;
+    if (prof && blockIdx.x == 0) prof_stamp(prof);       // block 0 ARRIVES: its own work of the stage is done
+    volatile unsigned int* mine = b.gen + 32 * (blockIdx.x % kBarLines);
+    const unsigned int g = *mine;
     __threadfence();
     if (atomicAdd(b.count, 1u) == gridDim.x - 1) {
       *b.count = 0u;
       __threadfence();
-      atomicAdd(const_cast<unsigned int*>(b.gen), 1u);
+#pragma unroll
+      for (int l = 0; l < kBarLines; ++l) b.gen[32 * l] = g + 1u;
     } else {
-      // poll with a back-off: up to a hundred idle CTAs reading one L2 line in a tight loop delay the loads of the CTAs that work
-      while (*b.gen == g) __nanosleep(40);
+      while (*mine == g) __nanosleep(32);
     }
     __threadfence();
+    if (prof && blockIdx.x == 0) prof_stamp(prof);       // ... and is released
   }
   __syncthreads();
-  if (prof && blockIdx.x == 0 && threadIdx.x == 0) {      // ... and at which the barrier released it
-    long long now;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-    const int s = g_prof_slot;
-    if (s < 126) { prof[s] = now; g_prof_slot = s + 1; }
-  }
 }
 
 // ---- arguments -----------------------------------------------------------------------------------------------------------------
@@ -844,7 +847,7 @@ int32_t rtd3_td3_coop_supported(const rtd3_td3* h, int32_t batch) {
 
 int64_t rtd3_td3_coop_scratch_floats(const rtd3_td3* h, int32_t batch) {
   if (!h) return -1;
-  return Scratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers) + 64;    // + the barrier words
+  return Scratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers) + kBarWords;    // + the barrier words
 }
 
 static long long* g_coop_prof = nullptr;
@@ -880,10 +883,10 @@ int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* a, float* 
   c.lr_actor = a->lr_actor; c.lr_critic = a->lr_critic; c.tau = a->tau;
   c.B = a->batch; c.E = a->epochs; c.delay = a->policy_update_delay;
   c.critic_losses = a->critic_losses; c.actor_losses = a->actor_losses;
-  // the first 64 floats of the scratch hold the barrier words (zero-initialised by the caller once; the barrier leaves them zero /
+  // the first kBarWords floats of the scratch hold the barrier words (zero-initialised by the caller once; the barrier leaves them zero /
   // monotone), the rest is the activation scratch
   c.bar = GridBarrier{reinterpret_cast<unsigned int*>(coop_scratch), reinterpret_cast<volatile unsigned int*>(coop_scratch) + 32};
-  c.scratch = coop_scratch + 64;
+  c.scratch = coop_scratch + kBarWords;
   c.world = a->world;
   if (a->world > 1) {
     const rtd3_p2p_state* p = a->p2p;

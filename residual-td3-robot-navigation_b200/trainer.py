@@ -195,7 +195,7 @@ class BatchedTrainer:
     generated inside `rtd3_tick_post` from (seed, device tick counter, env)."""
 
     def __init__(self, environment, robot, noise="mt19937", graph=False, check_interval=1, fused=False, philox_seed=0x5eed,
-                 async_check=False, scheduler=False, tick_seconds=None):
+                 async_check=False, scheduler=False, tick_seconds=None, demonstrations=False):
         if environment.num_envs != robot.num_envs:
             raise ValueError("environment and robot must hold the same envs")
         self.env, self.robot = environment, robot
@@ -222,6 +222,12 @@ class BatchedTrainer:
         # async_check: the "is a learner update due" test never makes the host wait for the device (Robot.maybe_update_async: the
         # decision is taken from the counter snapshot of the previous block); False = the synchronous test after every block
         self.async_check = bool(async_check)
+        # demonstrations: a 'demo' tick does what the reference does (robot-learning.py:88-92): every env plans its own
+        # demonstration (Environment.get_demonstration, batched CEM) and the robot processes it (per-env demonstration sets,
+        # augmentation, replay rows).  All envs request their demonstrations in lock step - ticks 0 .. NUM_DEMO-1 of a run
+        # (robot.py:468-470) - so no device -> host read is needed to know when.  False: 'demo' ticks are no-ops and the caller
+        # installs a shared set with Robot.set_demonstration_states.
+        self.demonstrations = bool(demonstrations)
         self._tick_counter = torch.zeros(2, dtype=torch.int64, device=self.device)      # [ticks completed, scratch of the tick in flight]
         # scheduler: the rest of update(dt) (robot-learning.py:45-50, 66-117) as per-env device state inside the fused tick kernels -
         # money gates on every purchase, demos_bought, the switch to testing once the money is gone, the test branch (success
@@ -366,7 +372,10 @@ class BatchedTrainer:
         K = self.check_interval
         done = 0
         while done < ticks:
-            if self._multi_tick_ok() and self.ticks % K == 0 and ticks - done >= K:
+            if self._demo_tick_due():
+                self.tick()
+                done += 1
+            elif self._multi_tick_ok() and self.ticks % K == 0 and ticks - done >= K:
                 self._run_multi_tick(K)
                 self.ticks += K
                 done += K
@@ -414,7 +423,26 @@ class BatchedTrainer:
             self._graph = self._graph_k = None
             self._graph_sig = sig
 
+    def _demo_tick_due(self):
+        from .robot import NUM_DEMO
+        return self.demonstrations and self.ticks < NUM_DEMO
+
+    def _buy_demonstrations(self):
+        """The 'demo' branch of update(dt) for all envs (robot-learning.py:88-92); the tick kernels have already advanced the
+        state machine and - with the scheduler - charged the demonstration."""
+        states, actions = self.env.get_demonstration()
+        self.robot.process_demonstration(states, actions, None)
+        self._graph = self._graph_k = None                  # the per-env sets may have been (re)allocated
+
     def tick(self):
+        if self._demo_tick_due():
+            types = self._device_tick()
+            self._buy_demonstrations()
+            self.ticks += 1
+            self.env._state_np = None
+            if self.ticks % self.check_interval == 0:
+                self._maybe_update()
+            return types
         if self._use_graph:
             self.robot.td3_agent.prepare_forward(self.n)      # (allocates the operand copies the signature below looks at)
             self._check_graphs()
