@@ -4,8 +4,11 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 Workload at every N (weak scaling, per GPU): BASELINE.json configs[1] - a batched dynamics rollout of 4096 envs,
-random actions U(-7.5, 7.5), 1000 steps.  One bench "step" = one such rollout = ONE launch of env_rollout_kernel.
+random actions U(-7.5, 7.5), 1000 steps.  One bench "step" = LAUNCHES_PER_STEP such rollouts back to back (one launch of the
+rollout kernel each), so that the timed window is tens of milliseconds and not a single millisecond of launch jitter.
 Inputs rotate through enough distinct action/trajectory buffers that the footprint exceeds the 126 MB L2.
+Both arms run the SAME workload: start states and actions come from numpy generators seeded per rank (make_workload), so the
+CPU arm steps exactly the envs, from exactly the states, with exactly the actions the GPU arm does.
 Prints ONE JSON line on rank 0 (see the task contract); `--impl reference` times the CPU oracle port instead.
 """
 import argparse
@@ -23,14 +26,21 @@ sys.path.insert(0, ROOT)
 
 ENVS = 4096          # configs[1]
 T_STEPS = 1000       # configs[1]
+LAUNCHES_PER_STEP = 64   # rollouts per bench step: 64 x ~47 us = 3 ms per step, 60 ms for a 20-step run
+E2E_CALLS_PER_STEP = 8   # host-buffer calls per e2e step: 8 x ~0.9 ms
 ACTION_RANGE = 7.5
 SEED = 1707366464
 ROLL_BYTES_PER_ENV_STEP = 16   # 8 B action read + 8 B state written; state stays in registers
 STEP_BYTES_PER_ENV_STEP = 24   # single-step kernel: state in 8 + action in 8 + state out 8
-# dram__bytes_read.sum + dram__bytes_write.sum of one env_rollout_pair_kernel launch at 4096 envs x 1000 steps, from the
-# `ncu --set full` capture summarised in profiles/r1_ncu_summaries.md (32.923 MB read + 0.561 MB written: the actions are read
-# once = algorithmic; the 32.8 MB trajectory is still in the 126 MB L2 when the kernel ends)
-ROLLOUT_NCU_DRAM_BYTES = 32922880 + 560640
+WORKLOAD = "batched dynamics rollout: %d envs x %d steps per GPU, random actions U(-7.5,7.5) (configs[1])" % (ENVS, T_STEPS)
+
+
+def make_workload(rank, n, T, buffers):
+    """Start states `[n,2]` and `buffers` action sets `[T,2,n]` (float32) of rank `rank`, identical in both arms."""
+    rs = np.random.RandomState((SEED + rank) % (2 ** 32))
+    starts = rs.uniform(0, 98.9999, (n, 2)).astype(np.float32)
+    acts = [rs.uniform(-ACTION_RANGE, ACTION_RANGE, (T, 2, n)).astype(np.float32) for _ in range(buffers)]
+    return starts, acts
 
 
 def load_peaks():
@@ -95,27 +105,29 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+_CPU_WORK = {}
+
+
 def _cpu_worker(args):
-    """Scalar oracle port: the reference's own per-env Python loop (environment.py:122-127) on this worker's envs."""
-    lo, hi, t_steps, seed = args
+    """Scalar oracle port: the reference's own per-env Python loop (environment.py:122-127) on this worker's envs, from the
+    workload's start states with the workload's actions (inherited from the parent through fork)."""
+    lo, hi, t0s, t1s = args
     from oracle import env_oracle as eo
-    speed, angle = eo.synthetic_maps(0)
-    rs = np.random.RandomState(seed)
-    n = hi - lo
-    states = rs.uniform(0, 98.9999, (n, 2))
-    actions = rs.uniform(-ACTION_RANGE, ACTION_RANGE, (t_steps, n, 2))
+    speed, angle = _CPU_WORK["maps"]
+    states, actions = _CPU_WORK["starts"], _CPU_WORK["actions"]
     t0 = time.perf_counter()
-    for i in range(n):
-        s = states[i]
-        for t in range(t_steps):
-            s = eo.step_scalar(speed, angle, s, actions[t, i])
-    return time.perf_counter() - t0, n * t_steps
+    for i in range(lo, hi):
+        s = states[i].astype(np.float64)
+        for t in range(t0s, t1s):
+            s = eo.step_scalar(speed, angle, s, actions[t, :, i])
+    return time.perf_counter() - t0, (hi - lo) * (t1s - t0s)
 
 
-def cpu_env_steps(envs, t_steps, procs, pool=None):
-    """env-steps/s of the oracle port over `procs` worker processes (each one GIL-bound core)."""
+def cpu_env_steps(envs, t_begin, t_end, procs, pool=None):
+    """env-steps/s of the oracle port over `procs` worker processes (each one GIL-bound core): envs 0..envs-1, rollout steps
+    t_begin..t_end-1 of the workload."""
     bounds = np.linspace(0, envs, procs + 1).astype(int)
-    jobs = [(int(bounds[k]), int(bounds[k + 1]), t_steps, 100 + k) for k in range(procs) if bounds[k + 1] > bounds[k]]
+    jobs = [(int(bounds[k]), int(bounds[k + 1]), t_begin, t_end) for k in range(procs) if bounds[k + 1] > bounds[k]]
     t0 = time.perf_counter()
     if pool is None:
         res = [_cpu_worker(j) for j in jobs]
@@ -126,38 +138,45 @@ def cpu_env_steps(envs, t_steps, procs, pool=None):
     return total / wall, wall, total
 
 
+def _cpu_prepare():
+    from oracle import env_oracle as eo
+    starts, acts = make_workload(0, ENVS, T_STEPS, 1)
+    _CPU_WORK.update(maps=eo.synthetic_maps(0), starts=starts, actions=acts[0])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     procs = os.cpu_count() or 1
-    # 4096 envs x 48 of the 1000 rollout steps per bench step: a bounded sample (~0.12 s on 16 cores, 25 s for the default 200
-    # steps) long enough that the workers' per-job set-up does not count against the reference (with 8 steps it halved its rate)
+    # 4096 envs x 48 of the 1000 rollout steps per bench step, walking through the workload's steps: a bounded sample (~0.12 s on
+    # 16 cores) long enough that the workers' per-job set-up does not count against the reference
     t_sample = 48
+    _cpu_prepare()
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
-        for _ in range(args.warmup):
-            cpu_env_steps(ENVS, t_sample, procs, pool)
+        for k in range(args.warmup):
+            cpu_env_steps(ENVS, 0, t_sample, procs, pool)
         t0 = time.perf_counter()
         total = 0
-        for _ in range(args.steps):
-            _, _, n = cpu_env_steps(ENVS, t_sample, procs, pool)
+        for k in range(args.steps):
+            lo = (k * t_sample) % (T_STEPS - t_sample)
+            _, _, n = cpu_env_steps(ENVS, lo, lo + t_sample, procs, pool)
             total += n
         wall = time.perf_counter() - t0
     value = total / wall
-    sample = "%d envs x %d of the %d rollout steps per bench step, scalar oracle port (oracle/env_oracle.py step_scalar), %d processes" % (
+    sample = "%d envs x %d of the %d rollout steps per bench step (the GPU arm's start states and actions), scalar oracle port (oracle/env_oracle.py step_scalar), %d processes" % (
         ENVS, t_sample, T_STEPS, procs)
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched dynamics rollout: %d envs x %d steps, random actions (configs[1])" % (ENVS, T_STEPS)},
+        "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
-
 
 
 # ------------------------------------------------------------------------------------------ TD3 legs

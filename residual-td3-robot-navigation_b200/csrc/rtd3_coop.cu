@@ -30,7 +30,7 @@
 namespace rtd3 {
 
 constexpr int kCT = 256;                 // threads per CTA
-constexpr int CTM = 32, CTK = 32;        // tile rows, reduction chunk
+constexpr int CTM = 32, CTK = 256;       // tile rows; reduction PANEL: the whole K of a hidden layer (<= 256) is staged at once
 constexpr int kAld = CTK + 4;            // row stride of the A tile in shared memory (16 B aligned rows, skewed banks)
 constexpr int kCoopMaxWorld = RTD3_P2P_MAX_WORLD;
 
@@ -157,10 +157,10 @@ struct TileOp {
   float* bias_grad;           // E_GRAD, nullable: row sums of A (n-tile 0 writes them)
 };
 
+// B panel: rows k0..k0+kload-1 of B [Kred][N], columns n0..n0+TN-1 -> Bs[kk][TN]  (bulk of the tile's traffic: cp.async, L2 only)
 template <int TN>
-__device__ __forceinline__ void load_b_chunk(const TileOp& op, float* Bs, int k0, int n0) {
-  constexpr int F4 = CTK * TN / 4;                       // float4 per chunk
-#pragma unroll
+__device__ __forceinline__ void load_b_panel(const TileOp& op, float* Bs, int k0, int kload, int n0) {
+  const int F4 = kload * (TN / 4);
   for (int q = threadIdx.x; q < F4; q += kCT) {
     const int kk = q / (TN / 4), nq = q - kk * (TN / 4);
     const int k = k0 + kk, n = n0 + nq * 4;
@@ -169,72 +169,80 @@ __device__ __forceinline__ void load_b_chunk(const TileOp& op, float* Bs, int k0
   }
 }
 
-// A chunk: rows m0..m0+31, reduction k0..k0+31 -> As[r][kk]
-__device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const float* in_s, const float* w_s, int m0, int k0) {
-  const int t = threadIdx.x;
+// A panel: rows m0..m0+31, reduction k0..k0+kload-1 -> As[r][kk]
+__device__ __forceinline__ void load_a_panel(const TileOp& op, float* As, const float* in_s, const float* w_s, int m0, int k0, int kload) {
+  const int kq_n = kload >> 2;                           // float4 per row
   if (op.akind == A_GLOBAL) {
-    const int r = t >> 3, kq = t & 7;                    // 32 rows x 8 float4
-    const int m = m0 + r, k = k0 + kq * 4;
-    const bool ok = m < op.M && k < op.Kred;
-    cp_async16_zfill(As + r * kAld + kq * 4, op.A + (int64_t)(ok ? m : 0) * op.lda + (ok ? k : 0), ok);
-  } else if (op.akind == A_GEN_FIRST) {
-    // h0[m][k] = relu(b0[k] + sum_j in[m][j] W0[k][j]); thread: 4 consecutive k of one row
-    const int r = t >> 3, kq = t & 7;
-    const int m = m0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    float* vv = reinterpret_cast<float*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + kq * 4 + i;
-      if (m < op.M && k < op.Kred) {
-        float s = w_s[4 * kMaxHidden + k];
-        for (int j = 0; j < op.in_dim; ++j) s = fmaf(in_s[r * 4 + j], w_s[k * op.in_dim + j], s);
-        vv[i] = fmaxf(s, 0.f);
-      }
+    for (int q = threadIdx.x; q < CTM * kq_n; q += kCT) {
+      const int r = q / kq_n, kq = q - r * kq_n;
+      const int m = m0 + r, k = k0 + kq * 4;
+      const bool ok = m < op.M && k < op.Kred;
+      cp_async16_zfill(As + r * kAld + kq * 4, op.A + (int64_t)(ok ? m : 0) * op.lda + (ok ? k : 0), ok);
     }
-    *reinterpret_cast<float4*>(As + r * kAld + kq * 4) = v;
-    if (op.H0_store && m < op.M && k0 + kq * 4 < op.Kred) *reinterpret_cast<float4*>(op.H0_store + (int64_t)m * op.Hd + k0 + kq * 4) = v;
+  } else if (op.akind == A_GEN_FIRST) {
+    // h0[m][k] = relu(b0[k] + sum_j in[m][j] W0[k][j]); 4 consecutive k of one row per item
+    for (int q = threadIdx.x; q < CTM * kq_n; q += kCT) {
+      const int r = q / kq_n, kq = q - r * kq_n;
+      const int m = m0 + r;
+      float vv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + kq * 4 + i;
+        if (m < op.M && k < op.Kred) {
+          float s = w_s[4 * kMaxHidden + k];
+          for (int j = 0; j < op.in_dim; ++j) s = fmaf(in_s[r * 4 + j], w_s[k * op.in_dim + j], s);
+          vv[i] = fmaxf(s, 0.f);
+        }
+      }
+      const float4 v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(As + r * kAld + kq * 4) = v;
+      if (op.H0_store && m < op.M && k0 + kq * 4 < op.Kred) *reinterpret_cast<float4*>(op.H0_store + (int64_t)m * op.Hd + k0 + kq * 4) = v;
+    }
   } else if (op.akind == A_GEN_DOUT) {
     // dz[m][k] = h[m][k] > 0 ? sum_o dout[m][o] Wout[o][k] : 0     (in_s holds dout of the tile's rows)
-    const int r = t >> 3, kq = t & 7;
-    const int m = m0 + r, k = k0 + kq * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < op.M && k < op.Kred) {
-      const float4 h = ldcg4(op.Hmask + (int64_t)m * op.Hd + k);
-      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k);
-      float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + k);
-      const float d0 = in_s[r * 4], d1 = in_s[r * 4 + 1];
-      v.x = h.x > 0.f ? fmaf(d0, w0.x, d1 * w1.x) : 0.f;
-      v.y = h.y > 0.f ? fmaf(d0, w0.y, d1 * w1.y) : 0.f;
-      v.z = h.z > 0.f ? fmaf(d0, w0.z, d1 * w1.z) : 0.f;
-      v.w = h.w > 0.f ? fmaf(d0, w0.w, d1 * w1.w) : 0.f;
-    }
-    *reinterpret_cast<float4*>(As + r * kAld + kq * 4) = v;
-  } else {
-    // transposed: As[r = output row (a hidden unit n)][kk = batch row]; source [batch][Hd], read 4 consecutive units of one batch row
-    const int bb = t >> 3, nq = t & 7;                   // 32 batch rows x 8 float4 of units
-    const int b = k0 + bb, n = m0 + nq * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < op.Kred && n < op.M) {
-      if (op.akind == AT_GLOBAL) {
-        v = ldcg4(op.A + (int64_t)b * op.lda + n);
-      } else {
-        const float4 h = ldcg4(op.Hmask + (int64_t)b * op.Hd + n);
-        const float4 w0 = *reinterpret_cast<const float4*>(w_s + n);
+    for (int q = threadIdx.x; q < CTM * kq_n; q += kCT) {
+      const int r = q / kq_n, kq = q - r * kq_n;
+      const int m = m0 + r, k = k0 + kq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < op.M && k < op.Kred) {
+        const float4 h = ldcg4(op.Hmask + (int64_t)m * op.Hd + k);
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + k);
         float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + n);
-        const float d0 = ldcg(op.dout + (int64_t)b * 2), d1 = ldcg(op.dout + (int64_t)b * 2 + 1);
+        if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + k);
+        const float d0 = in_s[r * 4], d1 = in_s[r * 4 + 1];
         v.x = h.x > 0.f ? fmaf(d0, w0.x, d1 * w1.x) : 0.f;
         v.y = h.y > 0.f ? fmaf(d0, w0.y, d1 * w1.y) : 0.f;
         v.z = h.z > 0.f ? fmaf(d0, w0.z, d1 * w1.z) : 0.f;
         v.w = h.w > 0.f ? fmaf(d0, w0.w, d1 * w1.w) : 0.f;
       }
+      *reinterpret_cast<float4*>(As + r * kAld + kq * 4) = v;
     }
-    As[(nq * 4 + 0) * kAld + bb] = v.x;
-    As[(nq * 4 + 1) * kAld + bb] = v.y;
-    As[(nq * 4 + 2) * kAld + bb] = v.z;
-    As[(nq * 4 + 3) * kAld + bb] = v.w;
+  } else {
+    // transposed: As[r = output row (a hidden unit n)][kk = batch row]; source [batch][Hd], 4 consecutive units of one batch row per item
+    for (int q = threadIdx.x; q < kload * (CTM / 4); q += kCT) {
+      const int bb = q >> 3, nq = q & 7;                 // CTM / 4 == 8 float4 of units per batch row
+      const int b = k0 + bb, n = m0 + nq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < op.Kred && n < op.M) {
+        if (op.akind == AT_GLOBAL) {
+          v = ldcg4(op.A + (int64_t)b * op.lda + n);
+        } else {
+          const float4 h = ldcg4(op.Hmask + (int64_t)b * op.Hd + n);
+          const float4 w0 = *reinterpret_cast<const float4*>(w_s + n);
+          float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (op.out_dim > 1) w1 = *reinterpret_cast<const float4*>(w_s + op.Hd + n);
+          const float d0 = ldcg(op.dout + (int64_t)b * 2), d1 = ldcg(op.dout + (int64_t)b * 2 + 1);
+          v.x = h.x > 0.f ? fmaf(d0, w0.x, d1 * w1.x) : 0.f;
+          v.y = h.y > 0.f ? fmaf(d0, w0.y, d1 * w1.y) : 0.f;
+          v.z = h.z > 0.f ? fmaf(d0, w0.z, d1 * w1.z) : 0.f;
+          v.w = h.w > 0.f ? fmaf(d0, w0.w, d1 * w1.w) : 0.f;
+        }
+      }
+      As[(nq * 4 + 0) * kAld + bb] = v.x;
+      As[(nq * 4 + 1) * kAld + bb] = v.y;
+      As[(nq * 4 + 2) * kAld + bb] = v.z;
+      As[(nq * 4 + 3) * kAld + bb] = v.w;
+    }
   }
 }
 
@@ -242,9 +250,9 @@ __device__ __forceinline__ void load_a_chunk(const TileOp& op, float* As, const 
 template <int TN>
 __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, float* smem) {
   constexpr int NT = TN / 16;                            // outputs per thread along n (4 or 2)
-  float* As = smem;                                      // [2][CTM][kAld]
-  float* Bs = smem + 2 * CTM * kAld;                     // [2][CTK][TN]
-  float* in_s = Bs + 2 * CTK * TN;                       // [CTM][4]
+  float* As = smem;                                      // [CTM][kAld]
+  float* Bs = smem + CTM * kAld;                         // [CTK][64]
+  float* in_s = Bs + CTK * 64;                           // [CTM][4]
   float* w_s = in_s + CTM * 4;                           // [5][kMaxHidden]: first layer (W0 | b0) or output layer weights of the generators
   const TileOp& op = op_in;                              // lives in shared memory (see stage_ops)
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
@@ -274,36 +282,31 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
   }
   __syncthreads();
 
-  const int nchunks = (op.Kred + CTK - 1) / CTK;
-  load_b_chunk<TN>(op, Bs, 0, n0);
-  load_a_chunk(op, As, in_s, w_s, m0, 0);
-  cp_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < nchunks) {
-      load_b_chunk<TN>(op, Bs + (cur ^ 1) * CTK * TN, (c + 1) * CTK, n0);
-      load_a_chunk(op, As + (cur ^ 1) * CTM * kAld, in_s, w_s, m0, (c + 1) * CTK);
-      cp_commit();
-      cp_wait<1>();
-    } else {
-      cp_wait<0>();
-    }
+  // The whole reduction range of a hidden layer (K <= 256) is staged in ONE go - one L2 round trip per tile instead of one per
+  // 32-wide chunk (the tile is a chain of dependent L2 accesses otherwise: with eight chunks it took 15-19 us, stage stamps r2) -
+  // and weight gradients, whose reduction runs over the batch, walk it in panels of 256 rows.
+  for (int k0 = 0; k0 < op.Kred; k0 += CTK) {
+    const int kp = min(CTK, op.Kred - k0);
+    const int kload = (kp + 31) & ~31;                   // zero-filled up to a multiple of 32
+    if (k0 > 0) __syncthreads();                         // the previous panel's readers are done
+    load_b_panel<TN>(op, Bs, k0, kload, n0);
+    load_a_panel(op, As, in_s, w_s, m0, k0, kload);
+    cp_commit();
+    cp_wait<0>();
     __syncthreads();
-    const float* a = As + cur * CTM * kAld;
-    const float* b = Bs + cur * CTK * TN;
-#pragma unroll
-    for (int kk = 0; kk < CTK; kk += 4) {
-      const float4 a0 = *reinterpret_cast<const float4*>(a + ty * kAld + kk);
-      const float4 a1 = *reinterpret_cast<const float4*>(a + (ty + 16) * kAld + kk);
+#pragma unroll 2
+    for (int kk = 0; kk < kload; kk += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(As + ty * kAld + kk);
+      const float4 a1 = *reinterpret_cast<const float4*>(As + (ty + 16) * kAld + kk);
       const float av0[4] = {a0.x, a0.y, a0.z, a0.w}, av1[4] = {a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float bv[NT];
         if (NT == 4) {
-          const float4 q = *reinterpret_cast<const float4*>(b + (kk + i) * TN + tx * 4);
+          const float4 q = *reinterpret_cast<const float4*>(Bs + (kk + i) * TN + tx * 4);
           bv[0] = q.x; bv[1] = q.y; bv[2] = q.z; bv[NT - 1] = q.w;
         } else {
-          const float2 q = *reinterpret_cast<const float2*>(b + (kk + i) * TN + tx * 2);
+          const float2 q = *reinterpret_cast<const float2*>(Bs + (kk + i) * TN + tx * 2);
           bv[0] = q.x; bv[1] = q.y;
         }
 #pragma unroll
@@ -315,9 +318,8 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
     }
     if (want_rsum && t < CTM) {
 #pragma unroll 8
-      for (int kk = 0; kk < CTK; ++kk) my_rsum += a[t * kAld + kk];
+      for (int kk = 0; kk < kload; ++kk) my_rsum += As[t * kAld + kk];
     }
-    __syncthreads();
   }
 
   // epilogue
@@ -449,21 +451,31 @@ __device__ __noinline__ void run_gemm_stage(const TileOp* ops, int nops, float* 
 __device__ __forceinline__ int global_warp() { return (int)blockIdx.x * (kCT / 32) + (int)(threadIdx.x >> 5); }
 __device__ __forceinline__ int total_warps() { return (int)gridDim.x * (kCT / 32); }
 
-// out[o] = bout[o] + sum_k H[row][k] Wout[o][k]   (one warp)
+// out[o] = bout[o] + sum_k H[row][k] Wout[o][k]   (one warp; float4 per lane, all loads of the row issued before the first use)
 __device__ __forceinline__ void out_layer_row(const NetRef& nr, const float* __restrict__ Hrow, float& o0, float& o1) {
   const int Hd = nr.s.hid, lane = threadIdx.x & 31;
   const float* W = nr.P + net_w_off(nr.s, nr.s.layers);
+  const bool two = nr.s.out > 1;
+  float4 h[2], w0[2], w1[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {                          // Hd <= 256: at most two float4 per lane
+    const int k = (u * 32 + lane) * 4;
+    const bool ok = k < Hd;
+    h[u] = ok ? ldcg4(Hrow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w0[u] = ok ? ldcg4(W + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w1[u] = (ok && two) ? ldcg4(W + Hd + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float v0 = 0.f, v1 = 0.f;
-  for (int k = lane; k < Hd; k += 32) {
-    const float h = ldcg(Hrow + k);
-    v0 = fmaf(h, ldcg(W + k), v0);
-    if (nr.s.out > 1) v1 = fmaf(h, ldcg(W + Hd + k), v1);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    v0 = fmaf(h[u].x, w0[u].x, v0); v0 = fmaf(h[u].y, w0[u].y, v0); v0 = fmaf(h[u].z, w0[u].z, v0); v0 = fmaf(h[u].w, w0[u].w, v0);
+    v1 = fmaf(h[u].x, w1[u].x, v1); v1 = fmaf(h[u].y, w1[u].y, v1); v1 = fmaf(h[u].z, w1[u].z, v1); v1 = fmaf(h[u].w, w1[u].w, v1);
   }
   v0 = warp_sum(v0);
   v1 = warp_sum(v1);
   const float* bo = nr.P + net_b_off(nr.s, nr.s.layers);
   o0 = v0 + ldcg(bo);
-  o1 = nr.s.out > 1 ? v1 + ldcg(bo + 1) : 0.f;
+  o1 = two ? v1 + ldcg(bo + 1) : 0.f;
 }
 
 // Batch reductions of the small gradients, one job = one network x 32 consecutive hidden units, dealt to the CTAs from
@@ -831,7 +843,7 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
   if (a.world > 1 && blockIdx.x == 0 && threadIdx.x == 0) *a.seq_counter = seq;
 }
 
-constexpr size_t kCoopSmemBytes = (2 * CTM * kAld + 2 * CTK * 64 + CTM * 4 + 5 * kMaxHidden) * sizeof(float);
+constexpr size_t kCoopSmemBytes = (CTM * kAld + CTK * 64 + CTM * 4 + 5 * kMaxHidden) * sizeof(float);
 
 }  // namespace rtd3
 
