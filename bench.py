@@ -104,6 +104,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`: pinned host buffers are then first-touched on the GPU's
+    own NUMA node, so the PCIe DMA of the host-buffer path does not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 _CPU_WORK = {}
 
@@ -381,29 +398,28 @@ def bench_full_loop(rt, torch, dev, world, rank):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
-    # ---- CPU baseline (rank 0, N=1 only): scalar oracle port on all host cores, bounded sample
+    # ---- CPU baseline (rank 0, N=1 only): scalar oracle port on all host cores, bounded sample of the SAME workload
     cpu = None
     if int(os.environ.get("RANK", "0")) == 0 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
         procs = os.cpu_count() or 1
+        _cpu_prepare()
         ctx = mp.get_context("fork")
         with ctx.Pool(procs) as pool:
-            cpu_env_steps(procs * 4, 8, procs, pool)                                   # warm the workers
+            cpu_env_steps(procs * 4, 0, 8, procs, pool)                                # warm the workers
             t_sample = 200                                                             # ~13 core-seconds of the reference loop
-            v_all, wall, total = cpu_env_steps(ENVS, t_sample, procs, pool)
-        v_one, _, _ = cpu_env_steps(64, 16, 1, None)
+            v_all, wall, total = cpu_env_steps(ENVS, 0, t_sample, procs, pool)
+        v_one, _, _ = cpu_env_steps(64, 0, 16, 1, None)
         # the same arithmetic vectorised over the envs in numpy (not how the reference runs, reported for context)
         from oracle import env_oracle as eo
-        sp_, an_ = eo.synthetic_maps(0)
-        rs_ = np.random.RandomState(0)
-        st_ = rs_.uniform(0, 98.9999, (ENVS, 2))
-        ac_ = rs_.uniform(-ACTION_RANGE, ACTION_RANGE, (50, ENVS, 2))
+        sp_, an_ = _CPU_WORK["maps"]
+        st_ = _CPU_WORK["starts"].astype(np.float64)
         t0_ = time.perf_counter()
         for t_ in range(50):
-            st_ = eo.step_batch(sp_, an_, st_, ac_[t_])
+            st_ = eo.step_batch(sp_, an_, st_, _CPU_WORK["actions"][t_].T)
         v_vec = ENVS * 50 / (time.perf_counter() - t0_)
         cpu = {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
-               "sample": "%d envs x %d steps (%.1f s wall) of the rollout, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
-                         % (ENVS, t_sample, wall, procs, v_one),
+               "sample": "%d envs x the first %d of the %d rollout steps (%.1f s wall), the GPU arm's start states and actions, scalar oracle port in %d processes; 1 process: %.3g env-steps/s"
+                         % (ENVS, t_sample, T_STEPS, wall, procs, v_one),
                "vectorised_numpy_1core": v_vec}
 
     import torch
@@ -419,25 +435,29 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, _, peak_kind = load_peaks()
 
+    bind_to_gpu_numa_node(local_rank)                    # pinned host buffers are first-touched on the GPU's own NUMA node
     n, T = args.envs, args.T
     speed, angle = rt.synthetic_maps(0)
     env = rt.Environment(num_envs=n, seed=SEED + rank * n, maps=(speed, angle), device=dev)   # env shard of this rank
-    env.reset()
-    start = env.robot_state.clone()
 
-    # rotating inputs: R action buffers + R trajectory buffers, footprint > L2 (126 MB)
+    # rotating inputs: R action buffers + R trajectory buffers, footprint > L2 (126 MB); the same numpy-generated workload as the
+    # CPU arm's (make_workload), uploaded before the timed region
     per_buf = T * 2 * n * 4
     R = max(2, int(np.ceil(160e6 / per_buf)) + 1)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = [(torch.rand((T, 2, n), device=dev, generator=gen) * (2 * ACTION_RANGE) - ACTION_RANGE) for _ in range(R)]
+    starts_np, acts_np = make_workload(rank, n, T, R)
+    env.robot_state = torch.from_numpy(starts_np).to(dev)
+    acts = [torch.from_numpy(a).to(dev) for a in acts_np]
     L = rt._lib.lib()
     trajs = [torch.empty((T, 2, n), dtype=torch.float32, device=dev) for _ in range(R)]
     stream = torch.cuda.current_stream(dev)
     sp = rt._lib.stream_ptr(dev)
+    LPS = args.launches_per_step
 
     def one_step(k):
-        rt._lib.check(L.rtd3_env_rollout(env._handle, rt._lib.ptr(env._state[0]), rt._lib.ptr(env._state[1]),
-                                         rt._lib.ptr(acts[k % R]), rt._lib.ptr(trajs[k % R]), n, T, sp))
+        for j in range(LPS):
+            q = (k * LPS + j) % R
+            rt._lib.check(L.rtd3_env_rollout(env._handle, rt._lib.ptr(env._state[0]), rt._lib.ptr(env._state[1]),
+                                             rt._lib.ptr(acts[q]), rt._lib.ptr(trajs[q]), n, T, sp))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -465,19 +485,19 @@ def run_b200(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    env_steps_total = float(n) * T * args.steps * world
+    env_steps_total = float(n) * T * args.steps * LPS * world
     value = env_steps_total / (ms * 1e-3)
 
     # ---- e2e: host action buffers -> public API -> host trajectory, copies inside the timed region
-    h_act = [torch.empty((T, 2, n), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for b in h_act:
-        b.uniform_(-ACTION_RANGE, ACTION_RANGE)
+    h_act = [torch.from_numpy(acts_np[j % R].copy()).pin_memory() for j in range(2)]      # the workload's actions, in pinned host memory
     h_traj = [torch.empty((T, 2, n), dtype=torch.float32).pin_memory() for _ in range(2)]
     e2e_steps = max(3, min(args.steps, 20))
+    EPS = E2E_CALLS_PER_STEP
 
     def e2e_step(k):
         # the public host-buffer API: pinned actions in, pinned trajectory out, copies pipelined with the kernel inside the call
-        env.rollout_host(h_act[k % 2], h_traj[k % 2])
+        for j in range(EPS):
+            env.rollout_host(h_act[(k + j) % 2], h_traj[(k + j) % 2])
 
     for k in range(3):
         e2e_step(k)
@@ -492,83 +512,87 @@ def run_b200(args):
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = float(n) * T * e2e_steps * world / (e2e_ms * 1e-3)
+    e2e_value = float(n) * T * e2e_steps * EPS * world / (e2e_ms * 1e-3)
 
-    # ---- side measurements on rank 0: single-step kernel at HBM-sized batches (24 B/env-step), both table paths
+    # ---- configs[4]: envs 1 k ... 1 M per GPU x {single-step kernel (24 B/env-step), T-step rollout kernel (16 B/env-step)} on EVERY
+    # rank (weak scaling: the same sizes per GPU, MAX time over the ranks, aggregate env-steps/s), plus the HBM-sized points
     extra = {}
-    if rank == 0 and not args.no_sweep:
+    if not args.no_sweep:
+        def timed(go, reps, warm=3):
+            for k in range(warm):
+                go(k)
+            barrier()
+            e0.record(stream)
+            for k in range(reps):
+                go(k)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) * 1e3 / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        cpu_rate = cpu["value"] if cpu else None
         sweep = []
-        for big in (1 << 20, 1 << 22, 1 << 24):
+        for big in (1 << 10, 1 << 12, 1 << 14, 1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24):
             bx = [torch.rand((2, big), device=dev) * 98 for _ in range(3)]          # 3 rotating sets: > L2 at 16M
             ba = [torch.rand((2, big), device=dev) * 15 - 7.5 for _ in range(3)]
             for variant, name in ((1, "smem"), (2, "ldg")):
+                if big < (1 << 20) and variant == 1:
+                    continue                                                        # (the staged table only pays at HBM-sized batches)
                 def go(k):
                     rt._lib.check(L.rtd3_env_step(env._handle, rt._lib.ptr(bx[k % 3][0]), rt._lib.ptr(bx[k % 3][1]),
                                                   rt._lib.ptr(ba[k % 3][0]), rt._lib.ptr(ba[k % 3][1]), big, variant, sp))
-                for k in range(3):
-                    go(k)
-                torch.cuda.synchronize(dev)
-                reps = 30
-                e0.record(stream)
-                for k in range(reps):
-                    go(k)
-                e1.record(stream)
-                torch.cuda.synchronize(dev)
-                us = e0.elapsed_time(e1) * 1e3 / reps
+                us = timed(go, 30)
                 gbs = big * STEP_BYTES_PER_ENV_STEP / (us * 1e-6) / 1e9
-                sweep.append({"kernel": "env_step_kernel/" + name, "envs": big, "us": round(us, 2),
-                              "env_steps_per_sec": big / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
+                sweep.append({"kernel": "env_step_kernel/" + name, "envs_per_gpu": big, "n_gpus": world, "us": round(us, 2),
+                              "env_steps_per_sec": big * world / (us * 1e-6), "GB/s_per_gpu": round(gbs, 1), "frac": round(gbs / hbm_peak, 3),
+                              "cpu_port_env_steps_per_sec": cpu_rate})
             del bx, ba
         extra["step_kernel_sweep"] = sweep
-        # the T-step rollout kernel at HBM-sized batches (16 B per env-step: action in, state out)
+        # the T-step rollout kernel (16 B per env-step: action in, state out)
         rsweep = []
-        for big, Tb in ((65536, 256), (1 << 20, 64), (1 << 22, 16)):
-            envb = rt.Environment(num_envs=big, seed=5, maps=(speed, angle), device=dev)
+        for big, Tb in ((1 << 10, 1000), (1 << 12, 1000), (1 << 14, 1000), (1 << 16, 256), (1 << 18, 128), (1 << 20, 64), (1 << 22, 16)):
+            envb = rt.Environment(num_envs=big, seed=5 + rank, maps=(speed, angle), device=dev)
             envb.reset()
             ab = [torch.rand((Tb, 2, big), device=dev) * 15 - 7.5 for _ in range(2)]
             tb = torch.empty((Tb, 2, big), dtype=torch.float32, device=dev)
             def go(k):
                 rt._lib.check(L.rtd3_env_rollout(envb._handle, rt._lib.ptr(envb._state[0]), rt._lib.ptr(envb._state[1]),
                                                  rt._lib.ptr(ab[k % 2]), rt._lib.ptr(tb), big, Tb, sp))
-            for k in range(2):
-                go(k)
-            torch.cuda.synchronize(dev)
-            reps = 10
-            e0.record(stream)
-            for k in range(reps):
-                go(k)
-            e1.record(stream)
-            torch.cuda.synchronize(dev)
-            us = e0.elapsed_time(e1) * 1e3 / reps
+            us = timed(go, 10, warm=2)
             gbs = big * Tb * ROLL_BYTES_PER_ENV_STEP / (us * 1e-6) / 1e9
-            rsweep.append({"kernel": "env_rollout (auto variant)", "envs": big, "steps": Tb, "us": round(us, 1),
-                           "env_steps_per_sec": big * Tb / (us * 1e-6), "GB/s": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
+            rsweep.append({"kernel": "env_rollout (auto variant)", "envs_per_gpu": big, "n_gpus": world, "steps": Tb, "us": round(us, 1),
+                           "env_steps_per_sec": big * Tb * world / (us * 1e-6), "GB/s_per_gpu": round(gbs, 1), "frac": round(gbs / hbm_peak, 3),
+                           "cpu_port_env_steps_per_sec": cpu_rate})
             del envb, ab, tb
         extra["rollout_kernel_sweep"] = rsweep
     td3_rows = None if args.no_td3 else bench_td3(rt, torch, dev, world, rank, cpu=not args.no_cpu)
-    fwd_rows = None if (args.no_td3 or rank != 0) else bench_forward(rt, torch, dev)
+    fwd_rows = None if (args.no_td3 or rank != 0 or world > 1) else bench_forward(rt, torch, dev)
     loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
     sampler.in_region = False
     sampler.stop()
 
     if rank == 0:
-        us_per_launch = ms * 1e3 / args.steps
+        us_per_launch = ms * 1e3 / (args.steps * LPS)
         alg_bytes = float(n) * T * ROLL_BYTES_PER_ENV_STEP
         achieved = alg_bytes / (us_per_launch * 1e-6) / 1e9
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batched dynamics rollout: %d envs x %d steps per GPU, random actions U(-7.5,7.5) (configs[1])" % (n, T),
-                       "envs_per_gpu": n, "rollout_steps": T, "kernel": "env_rollout_pair_kernel<traj> (TMA tiles, chain + helper warp per 32 envs)",
+            "config": {"workload": WORKLOAD if (n == ENVS and T == T_STEPS) else "batched dynamics rollout: %d envs x %d steps per GPU" % (n, T),
+                       "envs_per_gpu": n, "rollout_steps": T, "rollouts_per_bench_step": LPS,
+                       "kernel": "env_rollout_pair_kernel<traj> (TMA tiles, chain + helper warp per 32 envs)",
                        "l2": "inputs rotate over %d action + %d trajectory buffers (%.0f MB > 126 MB L2)" % (R, R, 2 * R * per_buf / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": (ROLLOUT_NCU_DRAM_BYTES if (n == ENVS and T == T_STEPS) else None), "peak_kind": peak_kind,
+                         "traffic": None, "peak_kind": peak_kind,
+                         "traffic_note": "not measurable inside this process; the ncu capture of this kernel (profiles/r1_ncu_summaries.md) read 32.9 MB + wrote 0.6 MB of DRAM per launch against 65.5 MB algorithmic (the trajectory is still in L2 at kernel end)",
                          "note": "%d B per env-step (action in 8 B, state out 8 B; state lives in registers) x %d env-steps per launch; "
                                  "4096 envs = 128 chain warps (+128 helper warps) on 148 SMs: one dependent chain per SM, so this config is latency-bound (see step_kernel_sweep for HBM-sized batches)"
                                  % (ROLL_BYTES_PER_ENV_STEP, n * T)},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": per_buf, "d2h_bytes_per_step": per_buf,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s",
+                    "h2d_bytes_per_step": per_buf * EPS, "d2h_bytes_per_step": per_buf * EPS, "calls_per_step": EPS,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "path": "Environment.rollout_host on pinned host buffers: one launch, the rollout kernel's TMA tiles read the actions from / "
                             "write the trajectory to host memory over PCIe (UVA zero-copy, no staging copies); raw cudaMemcpy of both "
@@ -604,9 +628,10 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--launches-per-step", type=int, default=LAUNCHES_PER_STEP)
     ap.add_argument("--envs", type=int, default=ENVS)
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--no-cpu", action="store_true")

@@ -418,7 +418,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* args, void* str
 int32_t rtd3_td3_coop_supported(const rtd3_td3* h, int32_t batch);
 int64_t rtd3_td3_coop_scratch_floats(const rtd3_td3* h, int32_t batch);
 int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* args, float* coop_scratch, void* stream);
-/* Development aid: DEVICE buffer of 128 int64 that the following cooperative updates stamp with %globaltimer at every stage boundary
+/* Development aid: DEVICE buffer of 256 int64 that the following cooperative updates stamp with %globaltimer at every stage boundary
  * of their last epoch (block 0: arrival at the grid barrier, release from it); NULL switches it off. */
 int32_t rtd3_debug_coop_prof(long long* device_buf);
 

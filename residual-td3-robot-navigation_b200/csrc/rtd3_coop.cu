@@ -53,6 +53,16 @@ struct GridBarrier {
   volatile unsigned int* gen;                            // gen[32 * g], g < kBarLines
 };
 __device__ int g_prof_slot;
+__device__ long long* g_tile_prof;          // development: phase stamps of block 0's tiles (second half of the prof buffer)
+__device__ int g_tile_slot;
+__device__ __forceinline__ void tile_stamp() {
+  if (g_tile_prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    const int s = g_tile_slot;
+    if (s < 120) { g_tile_prof[s] = now; g_tile_slot = s + 1; }
+  }
+}
 __device__ __forceinline__ void prof_stamp(long long* prof) {
   long long now;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -256,6 +266,7 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
   float* w_s = in_s + CTM * 4;                           // [5][kMaxHidden]: first layer (W0 | b0) or output layer weights of the generators
   const TileOp& op = op_in;                              // lives in shared memory (see stage_ops)
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  tile_stamp();
   __syncthreads();                                       // the previous tile's readers are done with the shared buffers
   const int m0 = tm * CTM, n0 = tn * TN;
   float acc[2][NT];
@@ -289,11 +300,15 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
     const int kp = min(CTK, op.Kred - k0);
     const int kload = (kp + 31) & ~31;                   // zero-filled up to a multiple of 32
     if (k0 > 0) __syncthreads();                         // the previous panel's readers are done
+    tile_stamp();
     load_b_panel<TN>(op, Bs, k0, kload, n0);
+    tile_stamp();
     load_a_panel(op, As, in_s, w_s, m0, k0, kload);
+    tile_stamp();
     cp_commit();
     cp_wait<0>();
     __syncthreads();
+    tile_stamp();
 #pragma unroll 2
     for (int kk = 0; kk < kload; kk += 4) {
       const float4 a0 = *reinterpret_cast<const float4*>(As + ty * kAld + kk);
@@ -322,6 +337,7 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
     }
   }
 
+  tile_stamp();
   // epilogue
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -344,6 +360,7 @@ __device__ __noinline__ void gemm_tile(const TileOp& op_in, int tm, int tn, floa
     else *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
   }
   if (want_rsum && t < CTM && m0 + t < op.M) op.bias_grad[m0 + t] = my_rsum;
+  tile_stamp();
 }
 
 // ---- operation builders -----------------------------------------------------------------------------------------------------------
@@ -671,9 +688,10 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
   unsigned long long seq = a.world > 1 ? *reinterpret_cast<volatile unsigned long long*>(a.seq_counter) : 0ull;
   int k_idx = 0, ka = 0;
 
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) g_prof_slot = 0;
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { g_prof_slot = 0; g_tile_slot = 0; g_tile_prof = nullptr; }
   for (int e = 0; e < a.E; ++e) {
     long long* prof = (e == a.E - 1) ? a.prof : nullptr;
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) g_tile_prof = a.prof + 128;
     // =============================================================== critic step (robot.py:312-366)
     {
       const int32_t* idx = a.idx + (int64_t)k_idx * B;
@@ -840,6 +858,7 @@ __global__ void __launch_bounds__(kCT, 1) td3_update_coop_kernel(CoopArgs a) {
       grid_sync(a.bar, prof);
     }
   }
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) g_tile_prof = nullptr;
   if (a.world > 1 && blockIdx.x == 0 && threadIdx.x == 0) *a.seq_counter = seq;
 }
 
@@ -863,7 +882,7 @@ int64_t rtd3_td3_coop_scratch_floats(const rtd3_td3* h, int32_t batch) {
 }
 
 static long long* g_coop_prof = nullptr;
-/* Development aid: DEVICE buffer of 128 int64 that the next cooperative updates stamp with %globaltimer at every stage boundary of
+/* Development aid: DEVICE buffer of 256 int64 that the next cooperative updates stamp with %globaltimer at every stage boundary of
  * their last epoch (arrival of block 0 at the barrier, release from it); NULL switches it off. */
 int32_t rtd3_debug_coop_prof(long long* device_buf) {
   g_coop_prof = device_buf;

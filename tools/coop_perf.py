@@ -32,12 +32,17 @@ def main():
             torch.cuda.synchronize()
             print("B=%d %dx%d %s: %.1f us/epoch" % (B, L, H, kernel, e0.elapsed_time(e1) * 1e3 / (reps * E)), flush=True)
             if kernel == "coop" and os.environ.get("RTD3_COOP_PROF"):
-                buf = torch.zeros(128, dtype=torch.int64, device=dev)
+                buf = torch.zeros(256, dtype=torch.int64, device=dev)
                 rt._lib.lib().rtd3_debug_coop_prof(rt._lib.ptr(buf))
                 ag.td3_update(rb, idx=idx, use_graph=False)
                 torch.cuda.synchronize()
                 rt._lib.lib().rtd3_debug_coop_prof(None)
-                st = buf.cpu().numpy()
+                full = buf.cpu().numpy()
+                ts = full[128:]
+                ts = ts[ts > 0]
+                # per tile of block 0: entry, [panel: start, B issued, A built, data landed], compute done, epilogue done
+                print("   block 0 tile phases (us since first stamp):", " ".join("%.1f" % ((v - ts[0]) / 1e3) for v in ts[:42]))
+                st = full[:128]
                 st = st[st > 0]
                 # stamps alternate: arrival of block 0 at barrier k, release from barrier k
                 work = [(st[i] - (st[i - 1] if i else st[0])) / 1e3 for i in range(0, len(st), 2)]
