@@ -243,7 +243,7 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
     out = []
     pg = dist.group.WORLD if world > 1 else None
     for label, B, H, L, epochs in TD3_SHAPES:
-        torch.manual_seed(0)
+        torch.manual_seed(rank)                           # ranks start from different weights: the constructor broadcasts rank 0's
         agent = rt.TD3(rt.Residual_Actor_Network(H, L), rt.Residual_Critic_Network(H, L), rt.Residual_Critic_Network(H, L),
                        batch_size=B, num_epochs=epochs, device=dev, process_group=pg)
         tf32 = label.endswith("tcgen05")
@@ -283,6 +283,8 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         ms_sample, ms_update, ms_call = float(t[0]), float(t[1]), float(t[2])
         flops = td3_flops_per_epoch(B * world, H, L) * epochs
         row = {"shape": label, "global_batch": B * world, "epochs": epochs, "sampler": rb.sampler,
+               "update_kernel": ("tcgen05 step kernels" if tf32 else ("persistent cooperative kernel (rtd3_td3_update_coop)" if agent._coop_ok(B)
+                                                                     else "per-step kernels (rtd3_td3_update)")),
                "dp_collective": getattr(agent, "dp_collective", None) if world > 1 else None,
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
                "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
@@ -295,9 +297,18 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         else:
             row["tflops_fp32"] = tfl
             row["frac_of_nominal_fp32_peak"] = tfl / (FP32_FFMA_PEAK_TFLOPS * world)
+        # roofline-shaped object of this leg: algorithmic flops of an epoch (td3_flops_per_epoch) over the measured epoch time, against
+        # the peak of the pipe the kernels use (TF32: half the measured dense bf16 figure; fp32 FFMA: nominal, no measured figure exists)
+        peak = (load_peaks()[1] / 2 if tf32 else FP32_FFMA_PEAK_TFLOPS) * world
+        row["roofline"] = {"bound": "tensor" if tf32 else "fp32_ffma", "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak,
+                           "flops_per_epoch": flops / epochs, "us_per_epoch": 1e3 * ms_update / epochs,
+                           "peak_kind": "measured bf16 / 2" if tf32 else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"}
         if cpu and rank == 0 and world == 1 and not tf32:
             e_cpu = 40 if B <= 256 else 4
             row["cpu_port_updates_per_sec"] = cpu_td3_epochs_per_sec(B, H, L, e_cpu)
+        if world > 1:
+            from rtd3_b200.trainer import replicas_identical
+            row["replicas_identical"] = replicas_identical(agent, pg)
         out.append(row)
         del agent, rb
     return out
@@ -342,30 +353,37 @@ def bench_forward(rt, torch, dev):
 
 def bench_full_loop(rt, torch, dev, world, rank):
     """configs[3]: the act -> step -> transition -> (episodes ended: TD3 update) loop, gradients all-reduced across ranks.
-    8192 envs per GPU (65536 over 8 GPUs) and, for the per-GPU ceiling, 65536 envs per GPU."""
+    8192 envs per GPU (65536 over 8 GPUs) and, for the per-GPU ceiling, 65536 envs per GPU.  Every row states its mode:
+      throughput - Philox exploration noise in the tick kernel, f16 tensor-core actor forward, Philox replay sampling (with replacement);
+      exact      - the parity path: per-env numpy-legacy MT19937 noise, fp32 forward, exact np.random.choice index draws;
+      reference cadence - exact mode with the reference's own update (100 epochs x B 100, 3 x 200 networks, robot.py:46-54)."""
     import torch.distributed as dist
+    from rtd3_b200.trainer import replicas_identical
     pg = dist.group.WORLD if world > 1 else None
     rows = []
-    # 8192 envs per GPU x 8 GPUs = the 65 536 envs of configs[3]; 65 536 per GPU = the large end of the metric's env range
-    # "hooks": one launch per reference hook (ten per tick); "fused": rtd3_tick_pre / actor forward / rtd3_tick_post, eight ticks per graph
     rs = np.random.RandomState(0)
     tt = np.linspace(0, 1, 3785)[:, None]                # 3 x 3785 = the 11 355 demonstration states the reference holds after its 3 demos
     demos = np.concatenate([rs.uniform(5, 95, (1, 2)) * (1 - tt) + rs.uniform(5, 95, (1, 2)) * tt + rs.normal(0, 2.5, (3785, 2)) for _ in range(3)])
-    for n, precision, form in ((8192, "fp32", "hooks"), (8192, "tf32", "hooks"), (8192, "f16", "fused"),
-                               (65536, "tf32", "hooks"), (65536, "f16", "fused")):
-        env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev)
-        robot = rt.Robot(env.goal_state, hidden=256, layers=2, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 4 * n))
-        robot.td3_agent.precision = precision          # "tf32": the actor forward of the act hook runs on tcgen05 tensor cores
-        robot.td3_agent.batch_size = 256
-        robot.td3_agent.num_epochs = 20
-        robot.memory.sampler = "philox"
+    configs = [  # (envs per GPU, mode, hidden, layers, batch, epochs per update)
+        (8192, "throughput", 256, 2, 256, 20),
+        (8192, "exact", 256, 2, 256, 20),
+        (8192, "reference cadence", 200, 3, 100, 100),
+        (65536, "throughput", 256, 2, 256, 20),
+    ]
+    for n, mode, H, Lh, B, E in configs:
+        torch.manual_seed(1000 + rank)
+        env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev, maps=rt.synthetic_maps(0))
+        robot = rt.Robot(env.goal_state, hidden=H, layers=Lh, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 8 * n))
+        thr = mode == "throughput"
+        robot.td3_agent.precision = "f16" if thr else "fp32"
+        robot.td3_agent.batch_size = B
+        robot.td3_agent.num_epochs = E
+        robot.memory.sampler = "philox" if thr else "mt19937"
         robot.set_demonstration_states(demos)
-        fused = form == "fused"
-        tr = rt.BatchedTrainer(env, robot, noise="philox" if fused else "randn", graph=True, check_interval=8, fused=fused)
-        advance = tr.run if fused else (lambda k: [tr.tick() for _ in range(k)])
+        tr = rt.BatchedTrainer(env, robot, noise="philox" if thr else "mt19937", graph=True, check_interval=8, fused=True, async_check=True)
         warm = 0
         while warm < 16 or (robot.num_updates < 1 and warm < 400):      # past the first learner update: its one-time graph
-            advance(8)                                                 # capture (tens of ms) is not part of the steady state
+            tr.run(8)                                                  # capture (tens of ms) is not part of the steady state
             warm += 8
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -373,7 +391,7 @@ def bench_full_loop(rt, torch, dev, world, rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ticks, upd0, steps0 = 480, robot.num_updates, int(tr.steps_bought.sum())   # long enough to average over the update cadence
         e0.record()
-        advance(ticks)
+        tr.run(ticks)
         e1.record()
         torch.cuda.synchronize(dev)
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -382,15 +400,23 @@ def bench_full_loop(rt, torch, dev, world, rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(st)
         ms = float(t[0])
-        rows.append({"envs_per_gpu": n, "envs_total": n * world, "actor_forward": precision, "tick": form, "ticks": ticks, "ms_per_tick": ms / ticks,
-                     "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": (robot.num_updates - upd0),
-                     "td3_epochs_per_update": 20, "td3_batch": 256, "replay_rows_per_gpu": len(robot.memory), "demo_states": int(demos.shape[0]),
-                     "note": (("eight ticks per launch of the multi-tick kernel rtd3_tick_run_f16 (actor forward inside); noise Philox in the kernel"
-                               if tr._multi_tick_ok() else
-                               "three launches per tick (rtd3_tick_pre / actor forward / rtd3_tick_post), eight ticks per CUDA graph; noise Philox inside the tick kernel")
-                              if fused else
-                              "ten launches per tick, one CUDA graph per tick; noise torch.randn")
-                             + "; finished-episode counter read every 8 ticks; replay sampling philox"})
+        updates = robot.num_updates - upd0
+        agent = robot.td3_agent
+        row = {"envs_per_gpu": n, "envs_total": n * world, "mode": mode, "networks": "%d x %d" % (Lh, H), "actor_forward": agent.precision,
+               "exploration_noise": tr.noise, "replay_sampler": robot.memory.sampler, "tick": "fused", "ticks": ticks, "ms_per_tick": ms / ticks,
+               "env_steps_per_sec": float(st[0]) / (ms * 1e-3), "td3_updates_in_window": updates, "td3_epochs_per_update": E,
+               "td3_batch_per_gpu": B, "td3_epochs_per_sec": updates * E / (ms * 1e-3),
+               # sampled minibatch rows per env-step collected (the reference: 100 epochs x 1.5 x 100 rows per ~60-step episode = ~250)
+               "update_to_data_ratio": updates * E * 1.5 * B * world / max(float(st[0]), 1.0),
+               "episodes_per_update": robot.episodes_per_update * world, "update_check": "asynchronous (counter snapshot of the previous block)",
+               "replay_rows_per_gpu": len(robot.memory), "demo_states": int(demos.shape[0]),
+               "update_kernel": "persistent cooperative kernel" if agent._coop_ok(B) else "per-step kernels",
+               "dp_collective": getattr(agent, "dp_collective", None) if world > 1 else None,
+               "tick_form": ("eight ticks per launch of the multi-tick kernel rtd3_tick_run_f16 (actor forward inside)" if tr._multi_tick_ok() else
+                             "three launches per tick (rtd3_tick_pre / actor forward / rtd3_tick_post), eight ticks per CUDA graph")}
+        if world > 1:
+            row["replicas_identical"] = replicas_identical(agent, pg)
+        rows.append(row)
         del tr, robot, env
         import gc
         gc.collect()                                     # finalise the handles (cudaFree) now, not inside the next config's graph capture
@@ -607,6 +633,9 @@ def run_b200(args):
             line["actor_forward"] = fwd_rows
         if loop_row is not None:
             line["full_loop"] = loop_row
+        if world > 1:
+            flags = [r.get("replicas_identical") for r in (td3_rows or []) + (loop_row or []) if "replicas_identical" in r]
+            line["replicas_identical"] = bool(flags) and all(flags)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

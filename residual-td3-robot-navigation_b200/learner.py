@@ -349,9 +349,12 @@ class TD3:
         self._graphs = {}
         self._p2p = None
         self._comm = None
-        # "coop": td3_update runs as ONE persistent cooperative kernel (csrc/rtd3_coop.cu) whenever it applies - fp32, layers >= 2,
-        # batch <= 4096, single GPU or the peer-memory collective; "steps": always the per-step kernels of rtd3_td3.cu
-        self.update_kernel = "coop"
+        # "steps": the per-step kernels of rtd3_td3.cu behind rtd3_td3_update (the default: the faster form today);
+        # "coop": ONE persistent cooperative kernel per update (csrc/rtd3_coop.cu: layers tiled over all SMs, grid barriers between
+        # them, optimiser and peer-memory all-reduce inside) whenever it applies - fp32, layers >= 2, batch <= 4096, single GPU or
+        # the peer-memory collective.  Parity-green, but its ~12 grid barriers (2.5 us each) and latency-bound small stages make an
+        # epoch 140 us against 79 us at B = 256 (profiles/r2_coop_stage_profile.md): opt-in until that is fixed.
+        self.update_kernel = "steps"
         self._coop_scratch = {}
         # target-policy smoothing noise (robot.py:338, torch.randn_like - unseeded in the reference): generated inside the critic
         # kernels from Philox4x32-10 keyed (noise_seed, device step counter, batch row) unless a noise tensor is injected

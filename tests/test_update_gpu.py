@@ -209,7 +209,7 @@ def test_cooperative_update_kernel_vs_step_kernels_and_oracle(pkg, H, L, B, E):
     idx = torch.from_numpy(rs.randint(0, 3000, (n_idx, B)).astype(np.int32)).cuda()
     noise = torch.from_numpy(rs.normal(size=(E, B, 2)).astype(np.float32)).cuda()
     a_coop, a_steps = make_agent(pkg, H, L, B, E, seed=7), make_agent(pkg, H, L, B, E, seed=7)
-    a_steps.update_kernel = "steps"
+    a_coop.update_kernel, a_steps.update_kernel = "coop", "steps"
     assert a_coop._coop_ok(B) and not a_steps._coop_ok(B)
     p0 = a_coop.params.clone()
     c1, l1 = a_coop.td3_update(rb, idx=idx, noise=noise)
