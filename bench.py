@@ -373,8 +373,11 @@ def bench_full_loop(rt, torch, dev, world, rank):
     for n, mode, H, Lh, B, E in configs:
         torch.manual_seed(1000 + rank)
         env = rt.Environment(num_envs=n, seed=SEED + rank * n, device=dev, maps=rt.synthetic_maps(0))
-        robot = rt.Robot(env.goal_state, hidden=H, layers=Lh, seed=100 + rank, device=dev, process_group=pg, buffer_size=max(50000, 8 * n))
         thr = mode == "throughput"
+        # throughput: a ring that holds eight ticks of every env (the multi-tick kernel's bound); exact: the reference's BUFFER_SIZE
+        # (robot.py:36) - the exact index draw shuffles the whole ring per minibatch, as np.random.choice does
+        robot = rt.Robot(env.goal_state, hidden=H, layers=Lh, seed=100 + rank, device=dev, process_group=pg,
+                         buffer_size=max(50000, 8 * n) if thr else 10000)
         robot.td3_agent.precision = "f16" if thr else "fp32"
         robot.td3_agent.batch_size = B
         robot.td3_agent.num_epochs = E
