@@ -122,19 +122,25 @@ extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* 
     p.recv[r] = peer_recv[r];
     p.flags[r] = (unsigned long long*)peer_flags[r];
   }
-  // all blocks spin on flags, so the grid must be co-resident: at most 4 CTAs of 256 threads per SM; one float4 per thread where
-  // the buffer allows it (0.8 MB at 2 x 256 = 200 CTAs)
+  // All blocks wait for the peers' flags, and a peer raises its flag from the LAST of its blocks: the grid must be co-resident
+  // whatever else runs on the device.  At most one CTA per SM, launched COOPERATIVELY - the runtime places a cooperative grid
+  // as a whole or not at all, so a kernel of another stream that holds some SMs delays the launch instead of starving blocks that
+  // others are spinning for (a concurrent kernel could have turned the spin into the 20 s trap).
   const int64_t count4 = count / 4;
   int num_sms = 0;
   RTD3_CUDA(current_num_sms(&num_sms));
-  const int grid = (int)std::min<int64_t>(4 * (int64_t)num_sms, ceil_div(count4, 256));
+  const int grid = (int)std::min<int64_t>((int64_t)num_sms, ceil_div(count4, 256));
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* sc = (unsigned long long*)seq_counter;
+  int64_t stride4 = slot_floats / 4;
+  void* kargs[] = {&p, &rank, &sc, &out, &local_grads, (void*)&count4, &stride4, &block_counter};
+  const void* fn = nullptr;
   switch (world) {
-#define RTD3_P2P_CASE(W) case W: p2p_allreduce_kernel<W><<<grid, 256, 0, st>>>(p, rank, sc, out, local_grads, count4, slot_floats / 4, block_counter); break;
+#define RTD3_P2P_CASE(W) case W: fn = (const void*)p2p_allreduce_kernel<W>; break;
     RTD3_P2P_CASE(2) RTD3_P2P_CASE(3) RTD3_P2P_CASE(4) RTD3_P2P_CASE(5) RTD3_P2P_CASE(6) RTD3_P2P_CASE(7) RTD3_P2P_CASE(8)
 #undef RTD3_P2P_CASE
   }
+  RTD3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), kargs, 0, st));
   RTD3_LAUNCHED();
   return 0;
 }
