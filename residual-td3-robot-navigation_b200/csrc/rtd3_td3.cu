@@ -152,6 +152,46 @@ td3_actor_kernel(Arena ar, const float* __restrict__ params, const float* __rest
   }
 }
 
+// Where arena element o (offset inside its network's slot) sits in the derived copies, decomposed ONCE per element in 32-bit
+// arithmetic: the 64-bit divisions of transposed_index / chunk_major_index (five calls per element) made this kernel ~13 us.
+struct CopyIndex {
+  int t, u, v;          // offsets inside the slot in the transposed / forward chunk-major / input-gradient chunk-major copies
+  bool hidden;          // a hidden-to-hidden weight (the only entries that move, and that are TF32-rounded in u / v)
+};
+__device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
+  CopyIndex c{o, o, o, false};
+  const int first = s.in * s.hid + s.hid, blk = s.hid * s.hid + s.hid;
+  if (o < first) return c;
+  const unsigned o2 = (unsigned)(o - first);
+  const unsigned l = o2 / (unsigned)blk, rem = o2 - l * (unsigned)blk;
+  if ((int)l >= s.layers - 1 || rem >= (unsigned)(s.hid * s.hid)) return c;
+  const unsigned n = rem / (unsigned)s.hid, k = rem - n * (unsigned)s.hid;
+  const int base = first + (int)l * blk;
+  c.hidden = true;
+  c.t = base + (int)(k * s.hid + n);
+  c.u = base + (int)((((k >> 2) * s.hid + n) << 2) + (k & 3u));
+  c.v = base + (int)((((n >> 2) * s.hid + k) << 2) + (n & 3u));
+  return c;
+}
+
+// Optional optimiser fused into the weight-gradient pass (single GPU, batch <= 512: every gradient element is final when its job
+// writes it): torch.optim.Adam on the element (the arithmetic of td3_adam_polyak_kernel, bit for bit) and, on request, the Polyak
+// blend of the matching target parameter - the two separate optimiser launches of an epoch (13 us at B = 256) disappear.
+struct AdamFuse {
+  float* params;            // nullptr: not fused, gradients are stored
+  float* params_t;
+  float* params_uv;         // nullable
+  float* m;
+  float* v;
+  const double* beta_pows;
+  float lr;
+  int opt;                  // 0 actor optimiser, 1 critic optimisers (index into beta_pows)
+  int polyak;               // blend the target copy of every updated parameter
+  float tau;
+  int n_online, total;
+  NetShape shape;
+};
+
 // ---- weight gradients from the row scratch, reduced over the batch without atomics -----------------------------------
 //   hidden layer l (1..L-1):  gW_l[n][k] = sum_b dz_l[b][n] * h_{l-1}[b][k]      32x32 output tiles
 //   every hidden layer l:     gb_l[n]    = sum_b dz_l[b][n];   l = 0 also gW_0[n][j] = sum_b dz_0[b][n] * in0[b][j]
@@ -164,16 +204,54 @@ struct WgradSlots {
 };
 
 __global__ void __launch_bounds__(kThreads)
-wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split) {
+wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split, AdamFuse fz) {
   __shared__ __align__(16) float red[8][32 * 32];
+  __shared__ float s_step, s_bc2;
+  if (fz.params && threadIdx.x == 0) {
+    const double bc1 = 1.0 - fz.beta_pows[2 * fz.opt], bc2 = 1.0 - fz.beta_pows[2 * fz.opt + 1];
+    s_step = (float)((double)fz.lr / bc1);
+    s_bc2 = (float)sqrt(bc2);
+  }
+  // one gradient element: stored (or accumulated), or consumed by the fused optimiser.  o = offset inside the net's slot
+  auto emit = [&](int64_t net_off, int64_t o, float g, bool atomic_acc) {
+    if (!fz.params) {
+      float* dst = grads + net_off + o;
+      if (atomic_acc) atomicAdd(dst, g); else *dst = g;
+      return;
+    }
+    const int64_t i = net_off + o;
+    const CopyIndex ci = copy_index(fz.shape, (int)o);
+    const float m0 = fz.m[i], v0 = fz.v[i];
+    const float mi = m0 + (g - m0) * 0.1f;                             // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v0 * 0.999f + (g * g) * 0.001f;                   // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    fz.m[i] = mi;
+    fz.v[i] = vi;
+    const float denom = sqrtf(vi) / s_bc2 + 1e-8f;
+    const float p = fz.params[i] - s_step * (mi / denom);
+    fz.params[i] = p;
+    fz.params_t[net_off + ci.t] = p;
+    if (fz.params_uv) {
+      const float pr = ci.hidden ? tf32_rn(p) : p;
+      fz.params_uv[net_off + ci.u] = pr;
+      fz.params_uv[fz.total + net_off + ci.v] = pr;
+    }
+    if (fz.polyak) {
+      const int64_t ti = fz.n_online + i;
+      const float tv = __fadd_rn(__fmul_rn(fz.params[ti], 1.0f - fz.tau), __fmul_rn(p, fz.tau));   // robot.py:309, three roundings
+      fz.params[ti] = tv;
+      fz.params_t[fz.n_online + net_off + ci.t] = tv;
+      if (fz.params_uv) fz.params_uv[fz.n_online + net_off + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
+    }
+  };
   const int H = s.hid, L = s.layers;
   const int nch = (H + 31) / 32;
   const int nT = (L - 1) * nch * nch, nS = L * nch;
   const int job = blockIdx.x;
   const int slot = blockIdx.y;
   const RowScratch rs{const_cast<float*>(scratch) + slots.scratch_off[slot], B, H, L};
-  float* G = grads + slots.grad_off[slot];
+  const int64_t G0 = slots.grad_off[slot];
   const bool atomic = gridDim.z > 1;
+  if (fz.params) __syncthreads();                        // s_step / s_bc2
   const int b_lo = blockIdx.z * rows_per_split, b_hi = min(B, b_lo + rows_per_split);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -219,9 +297,12 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     const int gn = n0 + (o >> 5), gk = k0 + (o & 31);
     if (gn < H && gk < H) {
-      float* dst = G + net_w_off(s, l) + (int64_t)gn * H + gk;
-      if (atomic) { atomicAdd(dst, v.x); atomicAdd(dst + 1, v.y); atomicAdd(dst + 2, v.z); atomicAdd(dst + 3, v.w); }
-      else *reinterpret_cast<float4*>(dst) = v;
+      const int64_t off = net_w_off(s, l) + (int64_t)gn * H + gk;
+      if (!fz.params && !atomic) {
+        *reinterpret_cast<float4*>(grads + G0 + off) = v;
+      } else {
+        emit(G0, off, v.x, atomic); emit(G0, off + 1, v.y, atomic); emit(G0, off + 2, v.z, atomic); emit(G0, off + 3, v.w, atomic);
+      }
     }
   } else if (job < nT + nS) {
     const int l = (job - nT) / nch, n = ((job - nT) % nch) * 32 + lane;
@@ -245,13 +326,9 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
       float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 5; ++q) v[q] += red[w][lane * 5 + q];
-      float* gb = G + net_b_off(s, l) + n;
-      if (atomic) atomicAdd(gb, v[0]); else *gb = v[0];
+      emit(G0, net_b_off(s, l) + n, v[0], atomic);
       if (l == 0) {
-        for (int j = 0; j < s.in; ++j) {
-          float* gw = G + net_w_off(s, 0) + n * s.in + j;
-          if (atomic) atomicAdd(gw, v[1 + j]); else *gw = v[1 + j];
-        }
+        for (int j = 0; j < s.in; ++j) emit(G0, net_w_off(s, 0) + n * s.in + j, v[1 + j], atomic);
       }
     }
   } else {
@@ -273,15 +350,9 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 4; ++q) v[q] += red[w][lane * 4 + q];
       if (k < H) {
-        for (int o = 0; o < s.out; ++o) {
-          float* gw = G + net_w_off(s, L) + (int64_t)o * H + k;
-          if (atomic) atomicAdd(gw, v[o]); else *gw = v[o];
-        }
+        for (int o = 0; o < s.out; ++o) emit(G0, net_w_off(s, L) + (int64_t)o * H + k, v[o], atomic);
       }
-      if (chunk == 0 && lane < s.out) {
-        float* gb = G + net_b_off(s, L) + lane;
-        if (atomic) atomicAdd(gb, v[2 + lane]); else *gb = v[2 + lane];
-      }
+      if (chunk == 0 && lane < s.out) emit(G0, net_b_off(s, L) + lane, v[2 + lane], atomic);
     }
   }
 }
@@ -312,28 +383,6 @@ __global__ void td3_sync_transposed_kernel(Arena ar, const float* __restrict__ p
     const int64_t base = (i < n_online ? 0 : n_online) + ar.off(net);
     params_t[transposed_index(net == 0 ? ar.actor : ar.critic, base, i)] = params[i];
   }
-}
-
-// Where arena element o (offset inside its network's slot) sits in the derived copies, decomposed ONCE per element in 32-bit
-// arithmetic: the 64-bit divisions of transposed_index / chunk_major_index (five calls per element) made this kernel ~13 us.
-struct CopyIndex {
-  int t, u, v;          // offsets inside the slot in the transposed / forward chunk-major / input-gradient chunk-major copies
-  bool hidden;          // a hidden-to-hidden weight (the only entries that move, and that are TF32-rounded in u / v)
-};
-__device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
-  CopyIndex c{o, o, o, false};
-  const int first = s.in * s.hid + s.hid, blk = s.hid * s.hid + s.hid;
-  if (o < first) return c;
-  const unsigned o2 = (unsigned)(o - first);
-  const unsigned l = o2 / (unsigned)blk, rem = o2 - l * (unsigned)blk;
-  if ((int)l >= s.layers - 1 || rem >= (unsigned)(s.hid * s.hid)) return c;
-  const unsigned n = rem / (unsigned)s.hid, k = rem - n * (unsigned)s.hid;
-  const int base = first + (int)l * blk;
-  c.hidden = true;
-  c.t = base + (int)(k * s.hid + n);
-  c.u = base + (int)((((k >> 2) * s.hid + n) << 2) + (k & 3u));
-  c.v = base + (int)((((n >> 2) * s.hid + k) << 2) + (n & 3u));
-  return c;
 }
 
 __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ params_uv, float* __restrict__ grads, float* __restrict__ m,
@@ -459,12 +508,13 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 }
 
 static int32_t launch_wgrad(rtd3_td3* h, const NetShape& s, const float* scratch, float* grads, const WgradSlots& slots, int nslots, int B,
-                            cudaStream_t st) {
+                            cudaStream_t st, const AdamFuse& fz = AdamFuse{}) {
   const int nch = (s.hid + 31) / 32;
   const int jobs = (s.layers - 1) * nch * nch + s.layers * nch + nch;
   const int rows_per_split = 512;
   const int bsplit = (B + rows_per_split - 1) / rows_per_split;
-  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, 0, st>>>(s, scratch, grads, slots, B, rows_per_split);
+  RTD3_CHECK_ARG(!fz.params || bsplit == 1, "the fused optimiser needs batch <= 512");
+  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, 0, st>>>(s, scratch, grads, slots, B, rows_per_split, fz);
   RTD3_LAUNCHED();
   return 0;
 }
@@ -546,9 +596,19 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* para
 
 }  // extern "C"
 
+static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
+                                 const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
+                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz);
+
 int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
                                  const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
                                  int32_t* steps, double* beta_pows, cudaStream_t st) {
+  return critic_step_fused(h, params, params_t, grads, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, st, AdamFuse{});
+}
+
+static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
+                                 const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
+                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz) {
   const int ti = pick_tile(batch, h->num_sms);
   const int R = kRowTiles[ti];
   const int grid = (batch + R - 1) / R;
@@ -561,13 +621,23 @@ int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* 
   const int64_t per = RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers);
   slots.grad_off[0] = h->ar.off(1); slots.grad_off[1] = h->ar.off(2);
   slots.scratch_off[0] = 0; slots.scratch_off[1] = per;
-  return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st);
+  return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st, fz);
 }
 
 extern "C" {
 
+static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
+                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz);
+
 int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
                             int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {
+  return actor_step_fused(h, params, params_t, grads, scratch, rp_s, idx, batch, loss1, steps, beta_pows, stream, AdamFuse{});
+}
+
+}  // extern "C"
+
+static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
+                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz) {
   RTD3_CHECK_ARG(h && params && params_t && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
@@ -582,8 +652,10 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* param
   WgradSlots slots;
   slots.grad_off[0] = h->ar.off(0); slots.grad_off[1] = 0;
   slots.scratch_off[0] = 0; slots.scratch_off[1] = 0;
-  return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st);
+  return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st, fz);
 }
+
+extern "C" {
 
 int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float* params_uv, float* grads, float* adam_m, float* adam_v, const double* beta_pows, int32_t nets,
                              float lr_actor, float lr_critic, float grad_scale, int32_t polyak, float tau, void* stream) {
@@ -702,6 +774,17 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
   float* opt_grads = (a->world > 1 && a->p2p) ? a->p2p->sum : a->grads;      // what the optimiser consumes
   const float scale = 1.0f / (float)a->world;
   const int64_t off_c = h->ar.off(1), n_online = h->ar.online_total();
+  // Single GPU, fp32 step kernels, batch <= 512 (no split weight-gradient pass): the optimiser - and on actor epochs the Polyak
+  // blends - run inside the weight-gradient kernels; the critics' targets are blended right after the critics' Adam step of the
+  // same epoch (the actor step in between reads neither the targets nor changes the critics: robot.py:278-285 gives the same values)
+  const bool fuse = a->world == 1 && !tc && B <= 512;
+  auto fuse_for = [&](bool actor, bool polyak) {
+    AdamFuse fz{};
+    fz.params = a->params; fz.params_t = a->params_t; fz.params_uv = a->params_uv; fz.m = a->adam_m; fz.v = a->adam_v;
+    fz.beta_pows = a->beta_pows; fz.lr = actor ? a->lr_actor : a->lr_critic; fz.opt = actor ? 0 : 1; fz.polyak = polyak ? 1 : 0;
+    fz.tau = a->tau; fz.n_online = (int)n_online; fz.total = (int)h->ar.total(); fz.shape = actor ? h->ar.actor : h->ar.critic;
+    return fz;
+  };
   int64_t k = 0, ka = 0;
   int32_t rc = 0;
   for (int e = 0; e < E; ++e) {
@@ -713,26 +796,31 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
       rc = critic_step_tc_launch(h, a->params, a->params_uv, a->grads, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr, a->steps,
                                  a->beta_pows, st);
     else
-      rc = critic_step_launch(h, a->params, a->params_t, a->grads, a->scratch, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr,
-                              a->steps, a->beta_pows, st);
+      rc = critic_step_fused(h, a->params, a->params_t, a->grads, a->scratch, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr,
+                             a->steps, a->beta_pows, st, fuse ? fuse_for(false, e % delay == 0) : AdamFuse{});
     if (rc) return rc;
-    if ((rc = update_allreduce(a, off_c, n_online - off_c, st))) return rc;
-    if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b110, a->lr_actor,
-                                   a->lr_critic, scale, 0, a->tau, st)))
-      return rc;
+    if (!fuse) {
+      if ((rc = update_allreduce(a, off_c, n_online - off_c, st))) return rc;
+      if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b110, a->lr_actor,
+                                     a->lr_critic, scale, 0, a->tau, st)))
+        return rc;
+    }
     if (e % delay == 0) {
       const int32_t* ixa = a->idx + k * B;
       ++k;
       if (tc)
         rc = rtd3_td3_actor_step_tf32(h, a->params, a->params_uv, a->grads, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st);
       else
-        rc = rtd3_td3_actor_step(h, a->params, a->params_t, a->grads, a->scratch, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st);
+        rc = actor_step_fused(h, a->params, a->params_t, a->grads, a->scratch, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st,
+                              fuse ? fuse_for(true, true) : AdamFuse{});
       ++ka;
       if (rc) return rc;
-      if ((rc = update_allreduce(a, 0, off_c, st))) return rc;
-      if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b001, a->lr_actor,
-                                     a->lr_critic, scale, 0b111, a->tau, st)))
-        return rc;
+      if (!fuse) {
+        if ((rc = update_allreduce(a, 0, off_c, st))) return rc;
+        if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b001, a->lr_actor,
+                                       a->lr_critic, scale, 0b111, a->tau, st)))
+          return rc;
+      }
     }
   }
   (void)rp_actor;
