@@ -32,7 +32,7 @@ TAU = 0.001
 
 _COMMS = {}                          # (process group id, device) -> rtd3_comm handle (see TD3._setup_comm)
 # "p2p": rtd3_p2p_allreduce, the peer-memory kernel (validated on 2, 4 and 8 B200 of one NVSwitch box: 8 GPUs, B = 256 per rank,
-# 107 us per data-parallel epoch against 129 us, full loop 62 against 72 us per tick - profiles/r2_dp_8gpu.md);
+# 107 us per data-parallel epoch against 129 us - profiles/r2_dp_8gpu.md);
 # "nccl": rtd3_allreduce_grads on our own NCCL communicator (any topology NCCL serves).  Both are part of the update's CUDA graph.
 DEFAULT_DP_COLLECTIVE = "p2p"
 
