@@ -40,54 +40,67 @@ __device__ void mt_regenerate_warp(uint32_t* mt, int lane) {
   }
 }
 
-// Kernel A: swap lists.  J[s*n + i] = j_i for i = 1..n-1 (entry 0 unused).  One CTA of 1024 threads.
+// Kernel A: swap lists.  J[s*n + i] = j_i for i = 1..n-1 (entry 0 unused).  One CTA of 256 threads.
 //
-// A round takes up to 1024 consecutive raw draws, thread t owning draw t.  With i swaps still to draw, thread t's bound
+// A round takes up to 256 consecutive raw draws, thread t owning draw t.  With i swaps still to draw, thread t's bound
 // (i minus the number of accepted draws before it) lies in [i - t, i].  If the mask is the same at both ends the draw is
 // classified without knowing the exact bound: v <= i - t  -> accepted whatever happened before ("sure"),
-// v > i -> rejected, in between -> "maybe" (a band of at most t values out of >= 2^k).  Threads whose range crosses a power of
-// two are maybes too; the round is sized so that it stays on one mask level wherever that leaves at least 32 draws.  One block scan
-// ranks the sure draws; warp 0 then resolves the maybes in order, 32 at a time, with their exact bounds (a ballot iterated to its
-// fixed point), and a second pass adds the accepted maybes into every thread's rank.  The round ends early at the draw that
-// completes a sample.
-//
-// The generator runs AHEAD of the consumer: its last four 624-word states live in a ring in shared memory (block b in slot b & 3,
-// raw word = tempered state word), so a round never stops at the end of a generator block and always has its 1024 words (the
-// first version cut every round at the block boundary and ran 256-thread rounds: ~65 rounds per shuffle of 10 000 instead of ~25).
-// At the end the state of the block that holds the next unread word goes back to the bank with numpy's lazy convention
-// (position 624 = "twist on the next draw").
+// v > i -> rejected, in between -> "maybe" (a band of at most t values out of >= 2^k, ~1 % of the draws).  Threads whose
+// range crosses a power of two are maybes too; the round is sized (32..256) so that there are at most 32 of those.  One
+// block scan ranks the sure draws; thread 0 then resolves the few maybes in order with their exact bounds, and a second
+// pass adds the accepted maybes into every thread's rank.  The round ends early at the draw that completes a sample.
+// (Round 2 tried 1024-draw rounds over a ring of four generator states, so that no round stops at the end of a 624-word block:
+// 14.1 ms per 150 draws against 13.3 here, and 16.0 with the round sized to keep ~32 draws undecided - the number of undecided
+// draws grows with the square of the round, and they are resolved by ONE warp; the serial resolver, not the round count, is the
+// floor.  A third variant decided the undecided draws block-parallel from their bound intervals [i - S - m, i - S] (the serial
+// resolver then runs only when a value falls inside its own window, ~never) with rounds of 2^(lvl-2) draws: bit-exact as well, and
+// 18.2 ms - a 1024-thread round costs ~3 us against ~1.5 us for a 256-thread round and the low mask levels force small rounds
+// either way.  gpurun_out/r2 sampler logs, git history (57e703c, the commit before this text); the version below is the fastest.)
 #ifndef RTD3_SAMPLE_THREADS
-#define RTD3_SAMPLE_THREADS 1024
+#define RTD3_SAMPLE_THREADS 256
 #endif
 constexpr int kSampleThreads = RTD3_SAMPLE_THREADS;
 constexpr int kSampleWarps = kSampleThreads / 32;
 
-// next generator state: dst = twist(src) (mt19937_gen), three ranges that only read finished words
-__device__ __forceinline__ void mt_next_block(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int t) {
+__device__ __forceinline__ void mt_regenerate_block(uint32_t* mt, uint32_t* raw, int t) {
   constexpr int N = RTD3_MT_N, M = 397;
-  if (t < N - M) dst[t] = mt_twist(src[t], src[t + 1], src[t + M]);                       // words 0..226: old, old, old
-  __syncthreads();
-  if (t >= N - M && t < 2 * (N - M)) dst[t] = mt_twist(src[t], src[t + 1], dst[t + M - N]);   // 227..453: far word is new
-  __syncthreads();
-  if (t >= 2 * (N - M) && t < N - 1) dst[t] = mt_twist(src[t], src[t + 1], dst[t + M - N]);   // 454..622
-  if (t == N - 1) dst[t] = mt_twist(src[t], dst[0], dst[M - 1]);                              // 623 pairs with the NEW word 0
+  const int lo[3] = {0, N - M, 2 * (N - M)}, hi[3] = {N - M, 2 * (N - M), N};
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {               // every range reads only words finished by earlier ranges (or still old)
+    // a range is at most 227 words: with fewer threads each one handles several, all read before any is written
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = lo[ph] + t + q * kSampleThreads;
+      v[q] = (kk < hi[ph]) ? mt_twist(mt[kk], mt[kk + 1 < N ? kk + 1 : 0], mt[kk + M < N ? kk + M : kk + M - N]) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = lo[ph] + t + q * kSampleThreads;
+      if (kk < hi[ph]) mt[kk] = v[q];
+    }
+    __syncthreads();
+  }
+  for (int k = t; k < N; k += kSampleThreads) raw[k] = mt_temper(mt[k]);
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kSampleThreads)
 sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count, int32_t* __restrict__ J) {
-  __shared__ uint32_t st[4][RTD3_MT_N];
-  __shared__ int w_sure[2][kSampleWarps], w_maybe[2][kSampleWarps], w_macc[2][kSampleWarps];
+  __shared__ uint32_t mt[RTD3_MT_N], raw[RTD3_MT_N];
+  __shared__ int w_sure[2][8], w_maybe[2][8], w_macc[2][8];
   __shared__ int m_S[kSampleThreads], m_acc[kSampleThreads];
   __shared__ uint32_t m_raw[kSampleThreads];
   __shared__ int s_last[2], s_macc_total[2];
   int par = 0;                                       // round parity: control words alternate between two buffers
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) st[0][k] = b.mt[(int64_t)k * b.n + stream_id];
-  // absolute word index from the start of block 0 (the bank's current state): next unread word, end of the generated words
-  long long head = b.pos[stream_id], gen_upto = RTD3_MT_N;
-  int latest = 0;                                    // newest generated block
+  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) {
+    mt[k] = b.mt[(int64_t)k * b.n + stream_id];
+    raw[k] = mt_temper(mt[k]);
+  }
+  int pos = b.pos[stream_id];
   if (t == 0) { s_last[0] = -1; s_macc_total[0] = 0; }
   __syncthreads();
 
@@ -95,24 +108,17 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
     int32_t* Js = J + (int64_t)s * n;
     int i = n - 1;                                  // swaps still to draw: indices i, i-1, ..., 1 (same value in every thread)
     while (i >= 1) {
-      while (gen_upto < head + kSampleThreads) {    // block-uniform: keep a full round of words ahead of the consumer
-        mt_next_block(st[latest & 3], st[(latest + 1) & 3], t);
-        ++latest;
-        gen_upto += RTD3_MT_N;
+      if (pos >= RTD3_MT_N) {
+        mt_regenerate_block(mt, raw, t);
+        pos = 0;
       }
       // round size: stay on one mask level while the distance to the next power of two allows rounds of >= 32 draws
       const int lvl = 31 - __clz(i);                // mask(i) = 2^(lvl+1) - 1
       const int gap = i - (1 << lvl);               // bounds down to i - gap keep mask(i)
-      // ... and no larger than 2^(lvl-2) draws: thread t's band of undecided values is t out of 2^(lvl+1), so a round leaves about
-      // g^2 / 2^(lvl+2) = 2^(lvl-6) draws undecided, and the refinement below decides all of them except with probability ~2^-8
-      const int g = min(min(max(gap + 1, 32), max(1 << max(lvl - 2, 0), 32)), kSampleThreads);
+      const int gmax = kSampleThreads;
+      const int g = min(min(max(gap + 1, 32), gmax), RTD3_MT_N - pos);
       const bool active = t < g;
-      uint32_t rw = 0u;
-      if (active) {
-        const long long a = head + t;
-        const int blk = (int)(a / RTD3_MT_N);
-        rw = mt_temper(st[blk & 3][(int)(a - (long long)blk * RTD3_MT_N)]);
-      }
+      const uint32_t rw = active ? raw[pos + t] : 0u;
       const int lo = i - t;                          // bound if every earlier draw of the round was accepted
       const bool uniform = lo >= 1 && __clz(lo) == __clz(i);
       const uint32_t v_hi = rw & (0xffffffffu >> __clz(i));
@@ -122,64 +128,17 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
       if (lane == 0) { w_sure[par][warp] = __popc(bs); w_maybe[par][warp] = __popc(bm); }
       if (t == 0) { s_last[par ^ 1] = -1; s_macc_total[par ^ 1] = 0; }   // next round's words (nobody reads them now)
       __syncthreads();
-      // exclusive scan over the warps' counts: every warp reads the 32 counts with its lanes and reduces with shuffles
-      int S, mpos, total_sure, total_maybe;
-      {
-        const int cs = lane < kSampleWarps ? w_sure[par][lane] : 0, cm = lane < kSampleWarps ? w_maybe[par][lane] : 0;
-        int ps = cs, pm = cm;
+      int S = __popc(bs & lt), mpos = __popc(bm & lt), total_sure = 0, total_maybe = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int us = __shfl_up_sync(0xffffffffu, ps, o), um = __shfl_up_sync(0xffffffffu, pm, o);
-          if (lane >= o) { ps += us; pm += um; }
-        }
-        total_sure = __shfl_sync(0xffffffffu, ps, 31);
-        total_maybe = __shfl_sync(0xffffffffu, pm, 31);
-        const int es = __shfl_sync(0xffffffffu, ps - cs, warp), em = __shfl_sync(0xffffffffu, pm - cm, warp);   // exclusive prefix of this warp
-        S = es + __popc(bs & lt);
-        mpos = em + __popc(bm & lt);
+      for (int w = 0; w < kSampleWarps; ++w) {
+        if (w < warp) { S += w_sure[par][w]; mpos += w_maybe[par][w]; }
+        total_sure += w_sure[par][w];
+        total_maybe += w_maybe[par][w];
       }
       int rank = S;
       bool accepted = sure;
       uint32_t v = v_hi;
-      // Refinement (block-parallel): with S sure draws and mpos undecided draws before it, an undecided draw's bound lies in
-      // [i - S - mpos, i - S].  If the mask is the same at both ends, v <= low end -> accepted, v > high end -> rejected whatever the
-      // earlier undecided draws do.  Only draws whose value falls into a window of mpos (a handful) values stay undecided - almost
-      // never - and only then does the serial resolver below run; otherwise one more block scan ranks the accepted draws.
-      bool still = false, racc = false;
-      if (maybe) {
-        const int hi_b = i - S, lo_b = i - S - mpos;
-        if (lo_b >= 1 && __clz(lo_b) == __clz(hi_b)) {
-          const int vv = (int)(rw & (0xffffffffu >> __clz(hi_b)));
-          if (vv <= lo_b) racc = true;
-          else if (vv <= hi_b) still = true;
-        } else {
-          still = true;
-        }
-      }
-      const int any_still = __syncthreads_or(still ? 1 : 0);
-      if (total_maybe > 0 && !any_still) {           // block-uniform: every undecided draw was decided by its bounds
-        const uint32_t ba = __ballot_sync(0xffffffffu, racc);
-        if (lane == 0) w_macc[par][warp] = __popc(ba);
-        __syncthreads();
-        int before, total_racc;
-        {
-          const int cc = lane < kSampleWarps ? w_macc[par][lane] : 0;
-          int pc = cc;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, pc, o);
-            if (lane >= o) pc += u;
-          }
-          total_racc = __shfl_sync(0xffffffffu, pc, 31);
-          before = __shfl_sync(0xffffffffu, pc - cc, warp) + __popc(ba & lt);
-        }
-        rank = S + before;
-        if (maybe) {
-          accepted = racc;
-          v = rw & (0xffffffffu >> __clz(max(i - rank, 1)));
-        }
-        if (t == 0) s_macc_total[par] = total_racc;
-      } else if (total_maybe > 0) {                  // block-uniform branch: the general, serial resolution
+      if (total_maybe > 0) {                         // block-uniform branch
         if (maybe) { m_S[mpos] = S; m_raw[mpos] = rw; }   // compacted in stream order
         __syncthreads();
         if (warp == 0) {
@@ -208,17 +167,10 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
         const uint32_t ba = __ballot_sync(0xffffffffu, macc);
         if (lane == 0) w_macc[par][warp] = __popc(ba);
         __syncthreads();
-        int before;
-        {
-          const int c = lane < kSampleWarps ? w_macc[par][lane] : 0;
-          int pc = c;
+        int before = __popc(ba & lt);
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, pc, o);
-            if (lane >= o) pc += u;
-          }
-          before = __shfl_sync(0xffffffffu, pc - c, warp) + __popc(ba & lt);
-        }
+        for (int w = 0; w < kSampleWarps; ++w)
+          if (w < warp) before += w_macc[par][w];
         rank = S + before;
         if (maybe) {
           accepted = macc;
@@ -235,16 +187,12 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
       const int total_acc = total_sure + s_macc_total[par];
       const int last = s_last[par];
       par ^= 1;
-      if (total_acc >= i) { head += last + 1; i = 0; }
-      else { head += g; i -= total_acc; }
+      if (total_acc >= i) { pos += last + 1; i = 0; }
+      else { pos += g; i -= total_acc; }
     }
   }
-  // back to the bank: the block that holds the next unread word (numpy's lazy form when it starts a block: position 624 of the one before)
-  long long blk = head / RTD3_MT_N;
-  int off = (int)(head - blk * RTD3_MT_N);
-  if (off == 0 && head > 0) { blk -= 1; off = RTD3_MT_N; }
-  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) b.mt[(int64_t)k * b.n + stream_id] = st[blk & 3][k];
-  if (t == 0) b.pos[stream_id] = off;
+  for (int k = t; k < RTD3_MT_N; k += kSampleThreads) b.mt[(int64_t)k * b.n + stream_id] = mt[k];
+  if (t == 0) b.pos[stream_id] = pos;
 }
 
 // Kernel B: out[s][p] = x[p] after the shuffle, by unwinding the swaps from position p.
