@@ -422,6 +422,15 @@ int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* args, floa
  * of their last epoch (block 0: arrival at the grid barrier, release from it); NULL switches it off. */
 int32_t rtd3_debug_coop_prof(long long* device_buf);
 
+/* Small-batch step kernels on thread-block clusters (csrc/rtd3_cluster.cu; the default of rtd3_td3_critic_step / rtd3_td3_actor_step /
+ * rtd3_td3_update for fp32 batches up to 1024): 1 if the step of `batch` rows runs on that path, and how many of its 8-CTA clusters the
+ * device can hold at once (cudaOccupancyMaxActiveClusters of the critic kernel; negative: CUDA error). */
+int32_t rtd3_td3_cluster_supported(const rtd3_td3* h, int32_t batch);
+int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch);
+/* Development aid: DEVICE buffers of 256 int64 each that the following cluster critic / actor kernels fill with clock64 stamps of
+ * CTA 0 at every stage boundary ([0] = number of stamps); NULL switches it off. */
+int32_t rtd3_debug_cluster_prof(long long* critic_buf, long long* actor_buf);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused tick of the batched driver loop        (robot-learning.py:66-101, training branch)
  * ---------------------------------------------------------------------------------------------- */

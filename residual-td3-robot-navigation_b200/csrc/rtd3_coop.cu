@@ -644,13 +644,10 @@ __device__ __noinline__ void adam_stage(const CoopArgs& a, int nets, int polyak,
       }
       g *= scale;
       const int o = net == 0 ? 0 : 1;
-      const float m0 = a.adam_m[i], v0 = a.adam_v[i];
-      const float mi = m0 + (g - m0) * 0.1f;                                  // exp_avg.lerp_(grad, 1 - beta1)
-      const float vi = v0 * 0.999f + (g * g) * 0.001f;                        // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      float mi = a.adam_m[i], vi = a.adam_v[i];
+      adam_element(g, mi, vi, p, s_step[o], s_bc2[o]);
       a.adam_m[i] = mi;
       a.adam_v[i] = vi;
-      const float denom = sqrtf(vi) / s_bc2[o] + 1e-8f;
-      p = p - s_step[o] * (mi / denom);
       a.params[i] = p;
       a.params_t[noff + ti] = p;
     }

@@ -203,15 +203,20 @@ struct WgradSlots {
   int64_t scratch_off[2];   // offset of the slot's row scratch
 };
 
+constexpr int kWgradRows = 256;                                   // batch rows staged per pass
+constexpr size_t kWgradSmem = 2 * kWgradRows * 32 * sizeof(float);  // dz slab + layer-input slab (the partial tiles alias them)
+
 __global__ void __launch_bounds__(kThreads)
 wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split, AdamFuse fz) {
-  __shared__ __align__(16) float red[8][32 * 32];
-  __shared__ float s_step, s_bc2;
-  if (fz.params && threadIdx.x == 0) {
-    const double bc1 = 1.0 - fz.beta_pows[2 * fz.opt], bc2 = 1.0 - fz.beta_pows[2 * fz.opt + 1];
-    s_step = (float)((double)fz.lr / bc1);
-    s_bc2 = (float)sqrt(bc2);
-  }
+  __shared__ __align__(16) float red_small[8][32 * 5];
+  // fused optimiser: bias corrections from the Adam clocks (loaded now, used after the batch reduction)
+  double bp1 = 0.0, bp2 = 0.0;
+  if (fz.params) { bp1 = fz.beta_pows[2 * fz.opt]; bp2 = fz.beta_pows[2 * fz.opt + 1]; }
+  float s_step = 0.f, s_bc2 = 1.f;
+  auto bias_corrections = [&]() {
+    s_step = (float)((double)fz.lr / (1.0 - bp1));
+    s_bc2 = (float)sqrt(1.0 - bp2);
+  };
   // one gradient element: stored (or accumulated), or consumed by the fused optimiser.  o = offset inside the net's slot
   auto emit = [&](int64_t net_off, int64_t o, float g, bool atomic_acc) {
     if (!fz.params) {
@@ -221,13 +226,10 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     const int64_t i = net_off + o;
     const CopyIndex ci = copy_index(fz.shape, (int)o);
-    const float m0 = fz.m[i], v0 = fz.v[i];
-    const float mi = m0 + (g - m0) * 0.1f;                             // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v0 * 0.999f + (g * g) * 0.001f;                   // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    float mi = fz.m[i], vi = fz.v[i], p = fz.params[i];
+    adam_element(g, mi, vi, p, s_step, s_bc2);
     fz.m[i] = mi;
     fz.v[i] = vi;
-    const float denom = sqrtf(vi) / s_bc2 + 1e-8f;
-    const float p = fz.params[i] - s_step * (mi / denom);
     fz.params[i] = p;
     fz.params_t[net_off + ci.t] = p;
     if (fz.params_uv) {
@@ -251,57 +253,117 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
   const RowScratch rs{const_cast<float*>(scratch) + slots.scratch_off[slot], B, H, L};
   const int64_t G0 = slots.grad_off[slot];
   const bool atomic = gridDim.z > 1;
-  if (fz.params) __syncthreads();                        // s_step / s_bc2
   const int b_lo = blockIdx.z * rows_per_split, b_hi = min(B, b_lo + rows_per_split);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (job < nT) {
+    // 32 x 32 tile of gW_l: both operand slabs ([rows][32] of dz_l and of h_{l-1}) are staged with ONE round of cp.async (the loop of
+    // dependent L2 loads it replaces ran at 8 warps per SM: ncu 2.7 long-scoreboard stalls per issue, 15 k of the kernel's 36 k cycles)
     const int l = 1 + job / (nch * nch);
     const int tile = job % (nch * nch);
     const int n0 = (tile / nch) * 32, k0 = (tile % nch) * 32;
     const float* dz = rs.dz(l);
     const float* x = rs.h(l - 1);
     const int ty = lane >> 2, tx = lane & 3;
-    const int n = n0 + ty * 4, k = k0 + tx * 8;
-    const bool n_ok = n < H, k_ok0 = k < H, k_ok1 = k + 4 < H;
+    float* sz = smem_f;
+    float* sx = smem_f + kWgradRows * 32;
+    // the optimiser's operands of this thread's 4 consecutive outputs, fetched under the batch reduction
+    const int o = threadIdx.x * 4;
+    const int gn = n0 + (o >> 5), gk = k0 + (o & 31);
+    const bool out_ok = gn < H && gk < H;
+    const int64_t off = net_w_off(s, l) + (int64_t)gn * H + gk;
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = m4, p4 = m4, t4 = m4;
+    if (fz.params && out_ok) {
+      m4 = *reinterpret_cast<const float4*>(fz.m + G0 + off);
+      v4 = *reinterpret_cast<const float4*>(fz.v + G0 + off);
+      p4 = *reinterpret_cast<const float4*>(fz.params + G0 + off);
+      if (fz.polyak) t4 = *reinterpret_cast<const float4*>(fz.params + fz.n_online + G0 + off);
+    }
     float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 8
-    for (int b = b_lo + warp; b < b_hi; b += 8) {
-      const float4 z = n_ok ? __ldg(reinterpret_cast<const float4*>(dz + (int64_t)b * H + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 x0 = k_ok0 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 x1 = k_ok1 ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)b * H + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float zz[4] = {z.x, z.y, z.z, z.w};
-      const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    for (int c0 = b_lo; c0 < b_hi; c0 += kWgradRows) {
+      const int rows = min(kWgradRows, b_hi - c0);
+      for (int i = threadIdx.x; i < rows * 8; i += kThreads) {
+        const int r = i >> 3, q4 = (i & 7) * 4;
+        if (n0 + q4 < H) cp_async16(sz + r * 32 + q4, dz + (int64_t)(c0 + r) * H + n0 + q4);
+        else *reinterpret_cast<float4*>(sz + r * 32 + q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + q4 < H) cp_async16(sx + r * 32 + q4, x + (int64_t)(c0 + r) * H + k0 + q4);
+        else *reinterpret_cast<float4*>(sx + r * 32 + q4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cp_commit();
+      cp_wait<0>();
+      __syncthreads();
+#pragma unroll 4
+      for (int b = warp; b < rows; b += 8) {
+        const float4 z = *reinterpret_cast<const float4*>(sz + b * 32 + ty * 4);
+        const float4 x0 = *reinterpret_cast<const float4*>(sx + b * 32 + tx * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(sx + b * 32 + tx * 8 + 4);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(zz[i], xx[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(zz[i], xx[j], acc[i][j]);
+      }
+      __syncthreads();
     }
+    float* red = smem_f;                      // [8][32 * 32], over the slabs
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float* dst = &red[warp][(ty * 4 + i) * 32 + tx * 8];
+      float* dst = red + warp * 1024 + (ty * 4 + i) * 32 + tx * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
     __syncthreads();
-    const int o = threadIdx.x * 4;            // 4 consecutive outputs of the 32x32 tile
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const float4 p = *reinterpret_cast<const float4*>(&red[w][o]);
+      const float4 p = *reinterpret_cast<const float4*>(red + w * 1024 + o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
-    const int gn = n0 + (o >> 5), gk = k0 + (o & 31);
-    if (gn < H && gk < H) {
-      const int64_t off = net_w_off(s, l) + (int64_t)gn * H + gk;
-      if (!fz.params && !atomic) {
-        *reinterpret_cast<float4*>(grads + G0 + off) = v;
+    if (out_ok) {
+      if (!fz.params) {
+        if (!atomic) *reinterpret_cast<float4*>(grads + G0 + off) = v;
+        else { atomicAdd(grads + G0 + off, v.x); atomicAdd(grads + G0 + off + 1, v.y); atomicAdd(grads + G0 + off + 2, v.z); atomicAdd(grads + G0 + off + 3, v.w); }
       } else {
-        emit(G0, off, v.x, atomic); emit(G0, off + 1, v.y, atomic); emit(G0, off + 2, v.z, atomic); emit(G0, off + 3, v.w, atomic);
+        // torch.optim.Adam on 4 consecutive elements of a hidden weight W_l[gn][gk..gk+3] (the arithmetic of emit(), element by element)
+        bias_corrections();
+        const float g4[4] = {v.x, v.y, v.z, v.w};
+        const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w}, po[4] = {p4.x, p4.y, p4.z, p4.w};
+        const float to[4] = {t4.x, t4.y, t4.z, t4.w};
+        float mn[4], vn[4], pn[4], tn[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          mn[e] = mo[e]; vn[e] = vo[e]; pn[e] = po[e];
+          adam_element(g4[e], mn[e], vn[e], pn[e], s_step, s_bc2);
+          tn[e] = __fadd_rn(__fmul_rn(to[e], 1.0f - fz.tau), __fmul_rn(pn[e], fz.tau));
+        }
+        const int64_t i0 = G0 + off;
+        *reinterpret_cast<float4*>(fz.m + i0) = make_float4(mn[0], mn[1], mn[2], mn[3]);
+        *reinterpret_cast<float4*>(fz.v + i0) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+        *reinterpret_cast<float4*>(fz.params + i0) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+        const int64_t wb = G0 + net_w_off(s, l);                                   // this weight matrix in the derived copies
+        const int64_t it = wb + (int64_t)gk * H + gn;                             // transposed copy: Wt[k][n]
+        const int64_t iu = wb + ((int64_t)(gk >> 2) * H + gn) * 4;                // chunk-major forward copy, k % 4 = 0..3 contiguous
+        const int64_t iv = wb + ((int64_t)(gn >> 2) * H + gk) * 4 + (gn & 3);     // chunk-major input-gradient copy, stride 4
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fz.params_t[it + (int64_t)e * H] = pn[e];
+        if (fz.params_uv) {
+          const float4 pr = make_float4(tf32_rn(pn[0]), tf32_rn(pn[1]), tf32_rn(pn[2]), tf32_rn(pn[3]));
+          *reinterpret_cast<float4*>(fz.params_uv + iu) = pr;
+          fz.params_uv[fz.total + iv] = pr.x; fz.params_uv[fz.total + iv + 4] = pr.y;
+          fz.params_uv[fz.total + iv + 8] = pr.z; fz.params_uv[fz.total + iv + 12] = pr.w;
+        }
+        if (fz.polyak) {
+          *reinterpret_cast<float4*>(fz.params + fz.n_online + i0) = make_float4(tn[0], tn[1], tn[2], tn[3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) fz.params_t[fz.n_online + it + (int64_t)e * H] = tn[e];
+          if (fz.params_uv)
+            *reinterpret_cast<float4*>(fz.params_uv + fz.n_online + iu) = make_float4(tf32_rn(tn[0]), tf32_rn(tn[1]), tf32_rn(tn[2]), tf32_rn(tn[3]));
+        }
       }
     }
   } else if (job < nT + nS) {
@@ -310,6 +372,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     const float* in0 = rs.in0();
     float ab = 0.f, aw[4] = {0.f, 0.f, 0.f, 0.f};
     if (n < H) {
+#pragma unroll 8
       for (int b = b_lo + warp; b < b_hi; b += 8) {
         const float d = __ldg(dz + (int64_t)b * H + n);
         ab += d;
@@ -319,13 +382,14 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
         }
       }
     }
-    float* r = &red[warp][lane * 5];
+    float* r = &red_small[warp][lane * 5];
     r[0] = ab; r[1] = aw[0]; r[2] = aw[1]; r[3] = aw[2]; r[4] = aw[3];
     __syncthreads();
     if (warp == 0 && n < H) {
+      if (fz.params) bias_corrections();
       float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       for (int w = 0; w < 8; ++w)
-        for (int q = 0; q < 5; ++q) v[q] += red[w][lane * 5 + q];
+        for (int q = 0; q < 5; ++q) v[q] += red_small[w][lane * 5 + q];
       emit(G0, net_b_off(s, l) + n, v[0], atomic);
       if (l == 0) {
         for (int j = 0; j < s.in; ++j) emit(G0, net_w_off(s, 0) + n * s.in + j, v[1 + j], atomic);
@@ -336,19 +400,21 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     const float* hl = rs.h(L - 1);
     const float* dout = rs.dout();
     float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
     for (int b = b_lo + warp; b < b_hi; b += 8) {
       const float2 d = __ldg(reinterpret_cast<const float2*>(dout + (int64_t)b * 2));
       const float h = k < H ? __ldg(hl + (int64_t)b * H + k) : 0.f;
       a0 = fmaf(d.x, h, a0); a1 = fmaf(d.y, h, a1);
       s0 += d.x; s1 += d.y;
     }
-    float* r = &red[warp][lane * 4];
+    float* r = &red_small[warp][lane * 4];
     r[0] = a0; r[1] = a1; r[2] = s0; r[3] = s1;
     __syncthreads();
     if (warp == 0) {
+      if (fz.params) bias_corrections();
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       for (int w = 0; w < 8; ++w)
-        for (int q = 0; q < 4; ++q) v[q] += red[w][lane * 4 + q];
+        for (int q = 0; q < 4; ++q) v[q] += red_small[w][lane * 4 + q];
       if (k < H) {
         for (int o = 0; o < s.out; ++o) emit(G0, net_w_off(s, L) + (int64_t)o * H + k, v[o], atomic);
       }
@@ -409,12 +475,10 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
       const int o = net == 0 ? 0 : 1;
       const float g = grads[i] * grad_scale;
       grads[i] = 0.f;
-      const float mi = m[i] + (g - m[i]) * 0.1f;                      // exp_avg.lerp_(grad, 1 - beta1)
-      const float vi = v[i] * 0.999f + (g * g) * 0.001f;              // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+      float mi = m[i], vi = v[i];
+      adam_element(g, mi, vi, p, s_step[o], s_bc2[o]);
       m[i] = mi;
       v[i] = vi;
-      const float denom = sqrtf(vi) / s_bc2[o] + 1e-8f;
-      p = p - s_step[o] * (mi / denom);
       params[i] = p;
       params_t[noff + ci.t] = p;
       if (params_uv) {                                                  // tensor-core operand copies (see rtd3_td3.cuh)
@@ -514,7 +578,8 @@ static int32_t launch_wgrad(rtd3_td3* h, const NetShape& s, const float* scratch
   const int rows_per_split = 512;
   const int bsplit = (B + rows_per_split - 1) / rows_per_split;
   RTD3_CHECK_ARG(!fz.params || bsplit == 1, "the fused optimiser needs batch <= 512");
-  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, 0, st>>>(s, scratch, grads, slots, B, rows_per_split, fz);
+  RTD3_CUDA(ensure_dyn_smem((const void*)wgrad_kernel, kWgradSmem));
+  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, kWgradSmem, st>>>(s, scratch, grads, slots, B, rows_per_split, fz);
   RTD3_LAUNCHED();
   return 0;
 }
@@ -609,14 +674,19 @@ int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* 
 static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
                                  const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
                                  int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz) {
-  const int ti = pick_tile(batch, h->num_sms);
-  const int R = kRowTiles[ti];
-  const int grid = (batch + R - 1) / R;
+  if (cluster_path_ok(h, batch)) {
+    const int32_t rc = critic_cluster_launch(h, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, st);
+    if (rc) return rc;
+  } else {
+    const int ti = pick_tile(batch, h->num_sms);
+    const int R = kRowTiles[ti];
+    const int grid = (batch + R - 1) / R;
 #define RTD3_CRITIC(RR) \
   td3_critic_kernel<RR><<<grid, kThreads, h->smem_critic[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows)
-  if (ti == 0) RTD3_CRITIC(2); else if (ti == 1) RTD3_CRITIC(4); else if (ti == 2) RTD3_CRITIC(8); else RTD3_CRITIC(16);
+    if (ti == 0) RTD3_CRITIC(2); else if (ti == 1) RTD3_CRITIC(4); else if (ti == 2) RTD3_CRITIC(8); else RTD3_CRITIC(16);
 #undef RTD3_CRITIC
-  RTD3_LAUNCHED();
+    RTD3_LAUNCHED();
+  }
   WgradSlots slots;
   const int64_t per = RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers);
   slots.grad_off[0] = h->ar.off(1); slots.grad_off[1] = h->ar.off(2);
@@ -641,14 +711,19 @@ static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* p
   RTD3_CHECK_ARG(h && params && params_t && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
-  const int ti = pick_tile(batch, h->num_sms);
-  const int R = kRowTiles[ti];
-  const int grid = (batch + R - 1) / R;
   cudaStream_t st = (cudaStream_t)stream;
+  if (cluster_path_ok(h, batch)) {
+    const int32_t rc = actor_cluster_launch(h, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows, st);
+    if (rc) return rc;
+  } else {
+    const int ti = pick_tile(batch, h->num_sms);
+    const int R = kRowTiles[ti];
+    const int grid = (batch + R - 1) / R;
 #define RTD3_ACTOR(RR) td3_actor_kernel<RR><<<grid, kThreads, h->smem_actor[ti], st>>>(h->ar, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows)
-  if (ti == 0) RTD3_ACTOR(2); else if (ti == 1) RTD3_ACTOR(4); else if (ti == 2) RTD3_ACTOR(8); else RTD3_ACTOR(16);
+    if (ti == 0) RTD3_ACTOR(2); else if (ti == 1) RTD3_ACTOR(4); else if (ti == 2) RTD3_ACTOR(8); else RTD3_ACTOR(16);
 #undef RTD3_ACTOR
-  RTD3_LAUNCHED();
+    RTD3_LAUNCHED();
+  }
   WgradSlots slots;
   slots.grad_off[0] = h->ar.off(0); slots.grad_off[1] = 0;
   slots.scratch_off[0] = 0; slots.scratch_off[1] = 0;

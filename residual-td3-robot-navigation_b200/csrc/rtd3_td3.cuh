@@ -81,6 +81,17 @@ __host__ __device__ inline int64_t chunk_major_index_v(const NetShape& s, int64_
   return net_off + first + l * blk + ((n >> 2) * s.hid + k) * 4 + (n & 3);
 }
 
+// One element of torch.optim.Adam (defaults, robot.py:237-239): exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g,
+// 1 - beta2); param -= step_size * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps).  Every rounding is spelled out so that the three
+// kernels that apply it (td3_adam_polyak_kernel, the optimiser fused into wgrad_kernel, the cooperative kernel) agree bit for bit -
+// left to the compiler, the contraction of a*b + c*d differs from one kernel to the next.
+__device__ __forceinline__ void adam_element(float g, float& m, float& v, float& p, float step, float sqrt_bc2) {
+  m = __fmaf_rn(__fsub_rn(g, m), 0.1f, m);
+  v = __fmaf_rn(__fmul_rn(g, g), 0.001f, __fmul_rn(v, 0.999f));
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), sqrt_bc2), 1e-8f);
+  p = __fsub_rn(p, __fmul_rn(step, __fdiv_rn(m, denom)));
+}
+
 // Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
 // beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
 __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {
@@ -101,6 +112,13 @@ int32_t advance_noise_counter(uint64_t* counter, uint64_t by, cudaStream_t st); 
 int32_t critic_step_tc_launch(rtd3_td3* h, const float* params, const float* params_uv, float* grads, const ReplayView& rp, const int32_t* idx,
                               const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out, int32_t* steps,
                               double* beta_pows, cudaStream_t st);
+// small batches on thread-block clusters (rtd3_cluster.cu)
+bool cluster_path_ok(const rtd3_td3* h, int batch);
+int32_t critic_cluster_launch(rtd3_td3* h, const float* params, const float* params_t, float* scratch, const ReplayView& rp, const int32_t* idx,
+                              const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out, int32_t* steps,
+                              double* beta_pows, cudaStream_t st);
+int32_t actor_cluster_launch(rtd3_td3* h, const float* params, const float* params_t, float* scratch, const ReplayView& rp, const int32_t* idx,
+                             int32_t batch, float* loss1, int32_t* steps, double* beta_pows, cudaStream_t st);
 }  // namespace rtd3
 
 // the opaque learner handle of the C ABI

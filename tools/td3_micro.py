@@ -26,7 +26,7 @@ def main(B=256, H=256, L=2):
     x = torch.rand((B, 2), device="cuda")
     ag.sync_transposed()
     L_ = _lib.lib(); sp = _lib.stream_ptr()
-    print("B=%d H=%d L=%d" % (B, H, L))
+    print("B=%d H=%d L=%d  cluster path %d, max active clusters %d" % (B, H, L, L_.rtd3_td3_cluster_supported(ag._handle, B), L_.rtd3_td3_cluster_occupancy(ag._handle, B)))
     print("  forward(actor)            %.1f us" % timeit(lambda: ag.forward(0, x)))
     print("  critic step (fwd/bwd+wgrad+adam) %.1f us" % timeit(lambda: ag._critic_step(rb, idx, noise, loss2)))
     print("  actor step (fwd/bwd+wgrad)       %.1f us" % timeit(lambda: ag._actor_step(rb, idx, loss1)))
@@ -34,6 +34,11 @@ def main(B=256, H=256, L=2):
     print("  empty launch (sync_transposed) %.1f us" % timeit(lambda: ag.sync_transposed()))
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for B in (16, 32, 64, 128, 256, 512):
+            main(B, 256, 2)
+        main(100, 200, 3)
+        sys.exit(0)
     main()
     main(100, 200, 3)
     main(8192, 256, 2)

@@ -38,6 +38,10 @@ def run(B, H, L, epochs=100, reps=3, sampler=True, precision="fp32"):
 if __name__ == "__main__":
     run(100, 200, 3)
     run(256, 256, 2)
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        for B, H, L in ((64, 256, 2), (128, 256, 2), (512, 256, 2), (1024, 256, 2), (256, 128, 2), (256, 256, 3)):
+            run(B, H, L, sampler=False)
+        sys.exit(0)
     run(8192, 256, 2, epochs=20)
     for B in (1024, 2048, 4096, 8192, 16384, 65536):
         run(B, 256, 2, epochs=20, sampler=False)
