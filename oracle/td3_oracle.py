@@ -124,16 +124,23 @@ class AdamState:
         self.t = 0
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(F32)
+
+
 def adam_step(p, g, st: AdamState, lr=1e-5, b1=0.9, b2=0.999, eps=1e-8):
-    """torch.optim.Adam defaults (robot.py:237-239): in-place on p."""
+    """torch.optim.Adam defaults (robot.py:237-239), in place on p, in the operation order of torch's CPU kernels (pinned bit for bit to
+    torch.optim.Adam by tests/test_oracle_td3.py): exp_avg.lerp_ is ONE fused multiply-add; exp_avg_sq.mul_(b2) is rounded, then
+    addcmul_ adds ((1-b2)*g)*g with the last product fused into the sum; addcdiv_ adds (value*exp_avg)/denom."""
     st.t += 1
-    st.m[...] = st.m + (g - st.m) * F32(1 - b1)                       # exp_avg.lerp_(grad, 1-beta1)
-    st.v[...] = st.v * F32(b2) + (g * g) * F32(1 - b2)                # exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    st.m[...] = _fma32(g - st.m, F32(1 - b1), st.m)                   # exp_avg.lerp_(grad, 1-beta1)
+    st.v[...] = _fma32(F32(1 - b2) * g, g, st.v * F32(b2))            # exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
     bc1 = 1 - b1 ** st.t
     bc2 = 1 - b2 ** st.t
     step_size = lr / bc1
     denom = np.sqrt(st.v) / F32(np.sqrt(bc2)) + F32(eps)
-    p[...] = p - F32(step_size) * (st.m / denom)
+    p[...] = p + (F32(-step_size) * st.m) / denom
 
 
 def soft_update(target, source, tau=0.001):                           # robot.py:307-310

@@ -11,8 +11,11 @@
 // cluster-wide barrier per layer (measured: barrier.cluster after a push costs 1 300-2 900 cycles, the products 1 500).  Two
 // mbarriers alternate by stage; consecutive stages write different tiles, and a CTA can only be one stage ahead of the slowest CTA
 // of its cluster (it needs that CTA's output to go on), which is what makes the reuse of tiles and barriers two stages later safe.
-// Network heads (1-2 outputs) are evaluated redundantly by every CTA.  The per-row layer inputs / pre-activation gradients go to the
-// same row scratch as before; wgrad_kernel (+ fused Adam) is unchanged.
+// What is NOT exchanged: the first layer (2-4 inputs) is evaluated for all H columns by every CTA, and the last hidden layer's
+// output stays with its CTA - only its contribution to the 1-2 head outputs (R x out partial sums) is pushed.  So a forward pass of
+// a 2-hidden-layer network costs one tiny exchange, a backward pass one full one.  A ninth warp does nothing but issue the weight
+// copies (an issue costs ~100 cycles per bulk copy, 16 per tile).  The per-row layer inputs / pre-activation gradients go to the same
+// row scratch as before; wgrad_kernel (+ fused Adam) consumes them.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -65,21 +68,29 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       : "memory");
 }
 
+
+constexpr int kCT = kThreads;            // compute threads; one more warp issues the weight copies
+constexpr int kClBlock = kCT + 32;
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }   // the compute threads only
+
 // Shared-memory plan of one CTA (offsets in floats into smem_f), its place in the cluster and the running stage state.
 struct Cl {
   int ring;          // [ns][Wc / 4][4 H + 4] weight slices: groups of 4 rows, row n = the H weights that feed own output column n
   int red;           // [KG][R][Wc] partial sums of the reduction groups
-  int small;         // per network: W0 slice [Wc][4] | biases [L][Wc] | head [2][H] | head bias [4]
+  int small;         // per network: W0 [H][4] | b0 [H] | b_l slices [L-1][Wc] | head [2][H] | head bias [4]
   int act0;          // kept activations, nkeep full-width [R][ld] tiles
-  int dz0, dz1;      // two more full-width tiles (forward of the target networks, backward)
-  int in0, out, dout, din, S, dinp;   // [R][4], [R][2], [R][2], [R][4], [R][8], [CS][R][2]
-  int bar;           // mbarriers (uint64): [0,1] stages, [2..4] weight ring slots, [5] small parameters
+  int xl;            // first-layer output of a network whose activations are not kept (written locally only)
+  int dz0, dz1;      // full-width tiles that receive pushed slices (they alternate; one tile when there is one push per pass)
+  int in0, out, dout, din, S;         // [R][4], [R][2], [R][2], [R][4], [R][8]
+  int hpart;         // [R][Wc / 4][2] head contributions of the column groups
+  int hp, dinp;      // [CS][R][2] each: head / input-gradient partial sums of the CTAs of the cluster
+  int bar;           // mbarriers (uint64): [0,1] stages, [2..4] ring slot full, [5..7] ring slot empty
   int ld, Wc, H, L, ns, tile_floats, small_stride;
   int ncg_sh;        // log2 of the column groups a reduction group spans (>= Wc / 4)
   int kgn, part;     // reduction groups and their length
   int rank, c_lo, ncols;
   int stg;           // stages completed so far (the same number in every thread of the cluster)
-  int dsel;          // which dz tile the next un-kept output goes to
+  int dsel;          // which dz tile the next pushed output goes to
   long long* prof;   // development: stage stamps of thread 0 of CTA 0 ((code << 48) | clock64), nullptr = off
   int pn;
 };
@@ -102,10 +113,11 @@ constexpr size_t kClSmemLimit = 226 * 1024;
 
 static ClPlan make_plan(int R, int CS, int H, int L, int nets, int nkeep) {
   const int Wc = cl_wc(H, CS), ld = H + 4;
-  const int kgn = kThreads / ((1 << cl_ncg_sh(Wc)) * (R / 4));
+  const int kgn = kCT / ((1 << cl_ncg_sh(Wc)) * (R / 4));
   const size_t tile = (size_t)(Wc / 4) * (4 * H + 4);
-  const size_t small_stride = (size_t)(4 + L) * Wc + 2 * H + 4;
-  const size_t fixed = (size_t)kgn * R * Wc + nets * small_stride + (size_t)(nkeep + 2) * R * ld + R * (4 + 2 + 2 + 4 + 8) + (size_t)CS * R * 2 + 16;
+  const size_t small_stride = (size_t)7 * H + (size_t)(L - 1) * Wc + 4;
+  const size_t fixed = (size_t)kgn * R * Wc + nets * small_stride + (size_t)(nkeep + (L >= 3 ? 3 : 2)) * R * ld + R * (4 + 2 + 2 + 4 + 8) +
+                       (size_t)R * (Wc / 4) * 2 + (size_t)2 * CS * R * 2 + 16;
   ClPlan p;
   p.ns = 3;
   p.bytes = (fixed + p.ns * tile) * sizeof(float);
@@ -121,22 +133,26 @@ __device__ __forceinline__ void cl_carve(Cl& c, int R, int CS, int H, int L, int
   c.Wc = cl_wc(H, CS);
   c.ld = H + 4;
   c.tile_floats = (c.Wc / 4) * (4 * H + 4);
-  c.small_stride = (4 + L) * c.Wc + 2 * H + 4;
+  c.small_stride = 7 * H + (L - 1) * c.Wc + 4;
   c.ncg_sh = cl_ncg_sh(c.Wc);
-  c.kgn = kThreads / ((1 << c.ncg_sh) * (R / 4));
+  c.kgn = kCT / ((1 << c.ncg_sh) * (R / 4));
   c.part = ((H + 4 * c.kgn - 1) / (4 * c.kgn)) * 4;
   int p = 0;
   c.ring = p; p += ns * c.tile_floats;
   c.red = p; p += c.kgn * R * c.Wc;
   c.small = p; p += nets * c.small_stride;
   c.act0 = p; p += nkeep * R * c.ld;
+  c.xl = p; p += R * c.ld;
   c.dz0 = p; p += R * c.ld;
-  c.dz1 = p; p += R * c.ld;
+  c.dz1 = c.dz0;
+  if (L >= 3) { c.dz1 = p; p += R * c.ld; }
   c.in0 = p; p += R * 4;
   c.out = p; p += R * 2;
   c.dout = p; p += R * 2;
   c.din = p; p += R * 4;
   c.S = p; p += R * 8;
+  c.hpart = p; p += R * (c.Wc / 4) * 2;
+  c.hp = p; p += CS * R * 2;
   c.dinp = p; p += CS * R * 2;
   c.bar = p;
   c.rank = (int)cluster_ctarank();
@@ -149,59 +165,91 @@ __device__ __forceinline__ void cl_carve(Cl& c, int R, int CS, int H, int L, int
 // ---- weight ring ------------------------------------------------------------------------------------------------------------------
 // tile = the rows of one H x H matrix that produce the own output columns: forward W_l[n][:] (torch layout, n = own column),
 // backward Wt_l[k][:] (the transposed copy, k = own column) - Wc contiguous rows of H floats, fetched in groups of 4 rows (one bulk
-// copy of 16 H bytes per group: per-row copies made the issue, ~65 cycles per copy, the longest part of a stage) into groups of
+// copy of 16 H bytes per group: per-row copies made the issue, ~100 cycles per copy, the longest part of a stage) into groups of
 // pitch 4 H + 4 floats: the product's lane cl reads the rows of group cl, and the skew keeps the lanes on different banks.
-// Warp 0 issues, the copies complete on the slot's mbarrier.
+// The producer warp (threads kCT..) issues tile after tile as the ring's slots are released.
 __device__ __forceinline__ uint64_t* cl_bar(const Cl& c, int i) { return reinterpret_cast<uint64_t*>(smem_f + c.bar) + i; }
-__device__ __forceinline__ void tile_issue(const Cl& c, const float* __restrict__ base, int slot) {
-  if (base && threadIdx.x < 32 && c.ncols > 0) {
-    uint64_t* bar = cl_bar(c, 2 + slot);
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)(c.ncols * c.H * 4));
-    __syncwarp();
-    const int g = threadIdx.x;
-    if (g < (c.ncols >> 2))
-      bulk_g2s(smem_f + c.ring + slot * c.tile_floats + g * (4 * c.H + 4), base + (int64_t)(c.c_lo + 4 * g) * c.H, (uint32_t)(16 * c.H), bar);
+__device__ __forceinline__ void cl_producer(const Cl& c, const float* const* tiles, int first, int ntiles) {
+  const int lane = threadIdx.x - kCT;
+  for (int i = first; i < ntiles; ++i) {
+    const int slot = i % c.ns;
+    if (i >= c.ns) mbar_wait(cl_bar(c, 5 + slot), (uint32_t)((i / c.ns - 1) & 1));
+    if (c.ncols > 0) {
+      uint64_t* bar = cl_bar(c, 2 + slot);
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(c.ncols * c.H * 4));
+      __syncwarp();
+      if (lane < (c.ncols >> 2))
+        bulk_g2s(smem_f + c.ring + slot * c.tile_floats + lane * (4 * c.H + 4), tiles[i] + (int64_t)(c.c_lo + 4 * lane) * c.H, (uint32_t)(16 * c.H),
+                 bar);
+    }
   }
 }
-// make tile i resident; the slot of tile i-1 (all threads have left its product) is refilled with tile i + ns - 1
-__device__ __forceinline__ int tile_acquire(const Cl& c, const float* __restrict__ next_base, int i) {
-  __syncthreads();          // the previous epilogue has left the partial sums (the stage waits in between are not CTA barriers)
-  tile_issue(c, next_base, (i + c.ns - 1) % c.ns);
+// make tile i resident (compute threads)
+__device__ __forceinline__ int tile_acquire(const Cl& c, int i) {
+  cta_sync();          // the previous epilogue has left the partial sums (the stage waits in between are not CTA barriers)
   if (c.ncols > 0) mbar_wait(cl_bar(c, 2 + i % c.ns), (uint32_t)((i / c.ns) & 1));
   return c.ring + (i % c.ns) * c.tile_floats;
 }
+// all compute threads have left the product of tile i: its slot may be refilled
+__device__ __forceinline__ void tile_release(const Cl& c, int i) {
+  if (threadIdx.x == 0) mbar_arrive(cl_bar(c, 5 + i % c.ns));
+}
 
-// small parameters of one network (own column slice) by bulk copies on mbarrier 5: W0 slice [ncols][in] | biases [L][Wc] | head
-// [2][H] | head bias [4].  One lane per copy; small_bytes() is what the arming thread expects.
-__device__ __forceinline__ uint32_t small_bytes(const Cl& c, const NetShape& s) {
-  return (uint32_t)((c.ncols * s.in + s.layers * c.ncols + s.out * c.H + 4) * 4);
-}
-__device__ __forceinline__ void small_issue(const Cl& c, int slot, const float* __restrict__ P, const NetShape& s, int item) {
-  float* sp = smem_f + c.small + slot * c.small_stride;
-  uint64_t* bar = cl_bar(c, 5);
-  if (item == 0) {
-    if (c.ncols > 0) bulk_g2s(sp, P + net_w_off(s, 0) + c.c_lo * s.in, (uint32_t)(c.ncols * s.in * 4), bar);
-  } else if (item <= s.layers) {
-    const int l = item - 1;
-    if (c.ncols > 0) bulk_g2s(sp + (4 + l) * c.Wc, P + net_b_off(s, l) + c.c_lo, (uint32_t)(c.ncols * 4), bar);
-  } else if (item == kMaxLayers + 1) {
-    bulk_g2s(sp + (4 + s.layers) * c.Wc, P + net_w_off(s, s.layers), (uint32_t)(s.out * c.H * 4), bar);
-  } else if (item == kMaxLayers + 2) {
-    bulk_g2s(sp + (4 + s.layers) * c.Wc + 2 * c.H, P + net_b_off(s, s.layers), 16u, bar);
+// small parameters of one network: W0 [H][in] | b0 [H] | b_l slices | head [out][H] + head bias.  Fetched as float4 by all compute
+// threads, loads first and stores after (LDGSTS was tried: ~40 cycles of issue per warp instruction, 7.8 k cycles for the five
+// networks of the critic step).  Element i of the network's list -> (source, destination offset); at most two per thread.
+__device__ __forceinline__ bool small_slot(const Cl& c, const float* __restrict__ P, const NetShape& s, int i, const float*& src, int& dst) {
+  const int H = c.H;
+  const int n0 = (H * s.in) >> 2, n1 = H >> 2, q = c.ncols >> 2, n2 = (s.layers - 1) * q, n3 = (s.out * H) >> 2;
+  if (i < n0) { src = P + net_w_off(s, 0) + 4 * i; dst = 4 * i; return true; }
+  i -= n0;
+  if (i < n1) { src = P + net_b_off(s, 0) + 4 * i; dst = 4 * H + 4 * i; return true; }
+  i -= n1;
+  if (i < n2) {
+    const int l = 1 + i / q, j = i - (l - 1) * q;
+    src = P + net_b_off(s, l) + c.c_lo + 4 * j; dst = 5 * H + (l - 1) * c.Wc + 4 * j;
+    return true;
   }
+  i -= n2;
+  const int head = 5 * H + (s.layers - 1) * c.Wc;
+  if (i < n3) { src = P + net_w_off(s, s.layers) + 4 * i; dst = head + 4 * i; return true; }
+  i -= n3;
+  if (i == 0) { src = P + net_b_off(s, s.layers); dst = head + 2 * H; return true; }     // (reads into the slot's padding)
+  return false;
 }
-// the second head row of a one-output network is read (times a zero gradient) by the backward pass: it must be finite
-__device__ __forceinline__ void small_zero(const Cl& c, int slot, const NetShape& s) {
-  if (s.out < 2) {
-    float* head = smem_f + c.small + slot * c.small_stride + (4 + s.layers) * c.Wc;
-    for (int i = threadIdx.x; i < c.H; i += kThreads) head[c.H + i] = 0.f;
+template <int NETS>
+__device__ __forceinline__ void small_load_all(const Cl& c, const float* const (&P)[NETS], const NetShape (&s)[NETS]) {
+  float4 v[NETS][2];
+  int d[NETS][2];
+#pragma unroll
+  for (int n = 0; n < NETS; ++n)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float* src = nullptr;
+      d[n][k] = -1;
+      int dst = 0;
+      if (small_slot(c, P[n], s[n], threadIdx.x + k * kCT, src, dst)) {
+        v[n][k] = __ldg(reinterpret_cast<const float4*>(src));
+        d[n][k] = c.small + n * c.small_stride + dst;
+      }
+    }
+#pragma unroll
+  for (int n = 0; n < NETS; ++n) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (d[n][k] >= 0) *reinterpret_cast<float4*>(smem_f + d[n][k]) = v[n][k];
+    if (s[n].out < 2) {                                       // read (times a zero gradient) by the backward pass: must be finite
+      float* head = smem_f + c.small + n * c.small_stride + 5 * c.H + (s[n].layers - 1) * c.Wc;
+      for (int i = threadIdx.x; i < c.H; i += kCT) head[c.H + i] = 0.f;
+    }
   }
 }
 __device__ __forceinline__ int sp_w0(const Cl& c, int slot) { return c.small + slot * c.small_stride; }
-__device__ __forceinline__ int sp_bias(const Cl& c, int slot, int l) { return c.small + slot * c.small_stride + (4 + l) * c.Wc; }
-__device__ __forceinline__ int sp_head(const Cl& c, int slot) { return c.small + slot * c.small_stride + (4 + c.L) * c.Wc; }
+__device__ __forceinline__ int sp_b0(const Cl& c, int slot) { return c.small + slot * c.small_stride + 4 * c.H; }
+__device__ __forceinline__ int sp_bias(const Cl& c, int slot, int l) { return c.small + slot * c.small_stride + 5 * c.H + (l - 1) * c.Wc; }   // l >= 1
+__device__ __forceinline__ int sp_head(const Cl& c, int slot) { return c.small + slot * c.small_stride + 5 * c.H + (c.L - 1) * c.Wc; }
 
-// the dz tile the next un-kept output goes to (they alternate: consecutive stages never write the same tile)
+// the dz tile the next pushed output goes to (they alternate: consecutive stages never write the same tile)
 __device__ __forceinline__ int next_dz(Cl& c) {
   const int r = c.dsel ? c.dz1 : c.dz0;
   c.dsel ^= 1;
@@ -217,6 +265,12 @@ __device__ __forceinline__ void push4(const Cl& c, int off, const float4& v) {
 #pragma unroll
   for (int k = 0; k < CS; ++k) st_async4(map_to_rank(own, (uint32_t)k), v, map_to_rank(bar, (uint32_t)k));
 }
+template <int CS>
+__device__ __forceinline__ void push2(const Cl& c, int off, float a, float b) {
+  const uint32_t own = smem_u32(smem_f + off), bar = stage_bar(c);
+#pragma unroll
+  for (int k = 0; k < CS; ++k) st_async2(map_to_rank(own, (uint32_t)k), a, b, map_to_rank(bar, (uint32_t)k));
+}
 // wait until the `bytes` all CTAs push to this one in the current stage have landed
 __device__ __forceinline__ void stage_wait(Cl& c, uint32_t bytes) {
   const uint32_t bar = stage_bar(c);
@@ -224,35 +278,48 @@ __device__ __forceinline__ void stage_wait(Cl& c, uint32_t bytes) {
   mbar_wait_cluster(bar, (uint32_t)((c.stg >> 1) & 1));
   c.stg += 1;
 }
-
-// ---- first layer, own columns: h[r][c] = relu(b[c] + sum_j in0[r][j] * W0[c][j]) ---------------------------------------------------
+// [R][2] partial sums of every CTA -> all CTAs (slot [rank]), summed in rank order into dst[r * dstride + {0,1}] (+ bias)
 template <int R, int CS>
-__device__ __forceinline__ void cl_first(Cl& c, int slot, int in_dim, int Y, float* __restrict__ gh /*nullable [B][H]*/, int r0, int B) {
-  const int q = c.ncols >> 2;
-  const int w0 = sp_w0(c, slot), bb = sp_bias(c, slot, 0);
-  for (int idx = threadIdx.x; idx < R * q; idx += kThreads) {
-    const int r = idx / q, cc = (idx - r * q) * 4;
-    const float4 x = lds4(c.in0 + r * 4);
-    const float4 b = lds4(bb + cc);
-    float v[4] = {b.x, b.y, b.z, b.w};
+__device__ __forceinline__ void exchange_pairs(Cl& c, int buf, float a, float b, int dst, int dstride, float bias0, float bias1) {
+  const int t = threadIdx.x;
+  if (t < R) push2<CS>(c, buf + (c.rank * R + t) * 2, a, b);
+  stage_wait(c, (uint32_t)(CS * R * 8));
+  if (t < R) {
+    float x = 0.f, y = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (in_dim == 4) {
-        const float4 w = lds4(w0 + (cc + e) * 4);
-        v[e] = fmaf(x.x, w.x, v[e]); v[e] = fmaf(x.y, w.y, v[e]); v[e] = fmaf(x.z, w.z, v[e]); v[e] = fmaf(x.w, w.w, v[e]);
-      } else {
-        const float2 w = *reinterpret_cast<const float2*>(smem_f + w0 + (cc + e) * 2);
-        v[e] = fmaf(x.x, w.x, v[e]); v[e] = fmaf(x.y, w.y, v[e]);
-      }
-      v[e] = fmaxf(v[e], 0.f);
+    for (int k = 0; k < CS; ++k) { x += smem_f[buf + (k * R + t) * 2]; y += smem_f[buf + (k * R + t) * 2 + 1]; }
+    smem_f[dst + t * dstride] = x + bias0;
+    smem_f[dst + t * dstride + 1] = y + bias1;
+  }
+  cta_sync();
+}
+
+// ---- first layer, ALL columns, every CTA: h[r][c] = relu(b[c] + sum_j in0[r][j] * W0[c][j]) -------------------------------------------
+template <int R>
+__device__ __forceinline__ void cl_first(Cl& c, int slot, int in_dim, int Y, float* __restrict__ gh /*nullable [B][H]*/, int r0, int B) {
+  const int w0 = sp_w0(c, slot), bb = sp_b0(c, slot);
+  for (int col = threadIdx.x; col < c.H; col += kCT) {
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (in_dim == 4) {
+      const float4 q = lds4(w0 + col * 4);
+      w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else {
+      const float2 q = *reinterpret_cast<const float2*>(smem_f + w0 + col * 2);
+      w[0] = q.x; w[1] = q.y;
     }
-    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-    push4<CS>(c, Y + r * c.ld + c.c_lo + cc, o);
-    if (gh && r0 + r < B) *reinterpret_cast<float4*>(gh + (int64_t)(r0 + r) * c.H + c.c_lo + cc) = o;
+    const float bias = smem_f[bb + col];
+    const bool own = gh && col >= c.c_lo && col < c.c_lo + c.ncols;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 x = lds4(c.in0 + r * 4);
+      float v = bias;
+      v = fmaf(x.x, w[0], v); v = fmaf(x.y, w[1], v); v = fmaf(x.z, w[2], v); v = fmaf(x.w, w[3], v);
+      v = fmaxf(v, 0.f);
+      smem_f[Y + r * c.ld + col] = v;
+      if (own && r0 + r < B) gh[(int64_t)(r0 + r) * c.H + col] = v;
+    }
   }
   stamp(c, 10);
-  stage_wait(c, (uint32_t)(R * c.H * 4));
-  stamp(c, 11);
 }
 
 // ---- hidden product, own columns: red[g][r][c] = sum_{j in group g} X[r][j] * T[c][j] ------------------------------------------------
@@ -290,7 +357,7 @@ __device__ __forceinline__ void cl_product(const Cl& c, int T, int X) {
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(smem_f + c.red + (kg * R + rg + i * RG) * c.Wc + 4 * cl) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
-  __syncthreads();
+  cta_sync();
 }
 
 // sum of the partials of the four values (r, cc..cc+3)
@@ -304,64 +371,89 @@ __device__ __forceinline__ float4 cl_reduce4(const Cl& c, int r, int cc) {
   return v;
 }
 
-// ---- hidden layer forward: Y[r][c] = relu(b[c] + sum_k X[r][k] * Wt[k][c]), own columns, pushed to the whole cluster ----------------
+// ---- hidden layer forward: Y[r][c] = relu(b[c] + sum_k X[r][k] * Wt[k][c]), own columns ------------------------------------------------
+// not the last hidden layer: the slice is pushed into tile Y of the whole cluster (the next product reduces over all columns).
+// The last one: kept locally when `Ykeep` >= 0 (the backward pass masks with it), and its contribution to the head goes out instead:
+// out[r][o] = b[o] + sum over the CTAs (in rank order) of sum_{c own} h[r][c] * Wout[o][c].
 template <int R, int CS>
-__device__ __forceinline__ void cl_fwd_hidden(Cl& c, int T, int slot, int l, int X, int Y, float* __restrict__ gh, int r0, int B) {
+__device__ __forceinline__ void cl_fwd_hidden(Cl& c, int ti, int T, int slot, int l, bool last, int X, int Y, int out_dim, float* __restrict__ gh, int r0,
+                                              int B) {
   stamp(c, 20);
   cl_product<R>(c, T, X);
+  tile_release(c, ti);
   stamp(c, 21);
-  const int q = c.ncols >> 2, bb = sp_bias(c, slot, l);
-  for (int idx = threadIdx.x; idx < R * q; idx += kThreads) {
-    const int r = idx / q, cc = (idx - r * q) * 4;
+  const int q = c.ncols >> 2, bb = sp_bias(c, slot, l), hd = sp_head(c, slot);
+  for (int idx = threadIdx.x; idx < R * q; idx += kCT) {
+    const int r = idx / q, cg = idx - r * q, cc = cg * 4;
     const float4 p = cl_reduce4<R>(c, r, cc);
     const float4 b = lds4(bb + cc);
     const float4 o = make_float4(fmaxf(b.x + p.x, 0.f), fmaxf(b.y + p.y, 0.f), fmaxf(b.z + p.z, 0.f), fmaxf(b.w + p.w, 0.f));
-    push4<CS>(c, Y + r * c.ld + c.c_lo + cc, o);
+    if (!last) push4<CS>(c, Y + r * c.ld + c.c_lo + cc, o);
+    else {
+      if (Y >= 0) *reinterpret_cast<float4*>(smem_f + Y + r * c.ld + c.c_lo + cc) = o;
+      const float4 wa = lds4(hd + c.c_lo + cc);
+      float h0 = o.x * wa.x;
+      h0 = fmaf(o.y, wa.y, h0); h0 = fmaf(o.z, wa.z, h0); h0 = fmaf(o.w, wa.w, h0);
+      float h1 = 0.f;
+      if (out_dim > 1) {
+        const float4 wb = lds4(hd + c.H + c.c_lo + cc);
+        h1 = o.x * wb.x;
+        h1 = fmaf(o.y, wb.y, h1); h1 = fmaf(o.z, wb.z, h1); h1 = fmaf(o.w, wb.w, h1);
+      }
+      *reinterpret_cast<float2*>(smem_f + c.hpart + idx * 2) = make_float2(h0, h1);
+    }
     if (gh && r0 + r < B) *reinterpret_cast<float4*>(gh + (int64_t)(r0 + r) * c.H + c.c_lo + cc) = o;
   }
   stamp(c, 22);
-  stage_wait(c, (uint32_t)(R * c.H * 4));
-  stamp(c, 23);
-}
-
-// ---- head, evaluated by every CTA for all R rows: out[r][o] = b[o] + sum_k X[r][k] * Wout[o][k]; 16 threads per dot product -----------
-template <int R>
-__device__ __forceinline__ void cl_head(Cl& c, int slot, int X, int out_dim) {
-  const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
-  const int hd = sp_head(c, slot);
-  const int np = R * out_dim;
-  for (int p0 = 0; p0 < np; p0 += kThreads / 16) {                  // the trip count is the same for all threads (full-warp shuffles)
-    const int p = min(p0 + grp, np - 1);
-    const int r = p / out_dim, o = p - r * out_dim;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-    for (int k = sub * 4; k < c.H; k += 64) {
-      const float4 x = lds4(X + r * c.ld + k), w = lds4(hd + o * c.H + k);
-      a0 = fmaf(x.x, w.x, a0); a1 = fmaf(x.y, w.y, a1); a2 = fmaf(x.z, w.z, a2); a3 = fmaf(x.w, w.w, a3);
+  if (!last) {
+    stage_wait(c, (uint32_t)(R * c.H * 4));
+    stamp(c, 23);
+  } else {
+    cta_sync();
+    float a = 0.f, b2 = 0.f;
+    if (threadIdx.x < R) {
+      for (int g = 0; g < q; ++g) {
+        const float2 v = *reinterpret_cast<const float2*>(smem_f + c.hpart + (threadIdx.x * q + g) * 2);
+        a += v.x; b2 += v.y;
+      }
     }
-    float v = (a0 + a1) + (a2 + a3);
-#pragma unroll
-    for (int s = 8; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (sub == 0 && p0 + grp < np) smem_f[c.out + r * 2 + o] = v + smem_f[hd + 2 * c.H + o];
+    exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + 2 * c.H], out_dim > 1 ? smem_f[hd + 2 * c.H + 1] : 0.f);
+    stamp(c, 30);
   }
-  __syncthreads();
-  stamp(c, 30);
 }
 
+// forward pass of one network.  keep: activations stay in act(keep0 + l) for the backward pass.
 template <int R, int CS>
-__device__ __forceinline__ void cl_forward(Cl& c, int slot, const NetShape& s, bool keep, int keep0, const RowScratch* rs, int r0,
-                                           const float* const* tiles, int& ti) {
+__device__ __forceinline__ void cl_forward(Cl& c, int slot, const NetShape& s, bool keep, int keep0, const RowScratch* rs, int r0, int& ti) {
   const int B = rs ? rs->B : 0;
-  int x = keep ? c.act0 + keep0 * R * c.ld : next_dz(c);
-  cl_first<R, CS>(c, slot, s.in, x, rs ? rs->h(0) : nullptr, r0, B);
+  int x = keep ? c.act0 + keep0 * R * c.ld : c.xl;
+  cl_first<R>(c, slot, s.in, x, rs ? rs->h(0) : nullptr, r0, B);
+  if (s.layers == 1) {
+    // the head straight from the first layer (every CTA holds all of it): own columns' contribution, exchanged like any other
+    cta_sync();
+    const int hd = sp_head(c, slot);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < R * 2; p += kCT / 32) {
+      const int r = p >> 1, o = p & 1;
+      float v = 0.f;
+      if (o < s.out)
+        for (int cc = lane; cc < c.ncols; cc += 32) v = fmaf(smem_f[x + r * c.ld + c.c_lo + cc], smem_f[hd + o * c.H + c.c_lo + cc], v);
+      v = warp_sum(v);
+      if (lane == 0) smem_f[c.din + r * 4 + o] = v;          // din doubles as scratch here (the backward pass writes it later)
+    }
+    cta_sync();
+    const float a = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4] : 0.f, b2 = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4 + 1] : 0.f;
+    exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + 2 * c.H], s.out > 1 ? smem_f[hd + 2 * c.H + 1] : 0.f);
+    return;
+  }
   for (int l = 1; l < s.layers; ++l) {
-    const int y = keep ? c.act0 + (keep0 + l) * R * c.ld : next_dz(c);
-    const int T = tile_acquire(c, tiles[ti + c.ns - 1], ti);
+    const bool last = l == s.layers - 1;
+    const int y = keep ? c.act0 + (keep0 + l) * R * c.ld : (last ? -1 : next_dz(c));
+    const int T = tile_acquire(c, ti);
+    cl_fwd_hidden<R, CS>(c, ti, T, slot, l, last, x, y, s.out, rs ? rs->h(l) : nullptr, r0, B);
     ++ti;
-    cl_fwd_hidden<R, CS>(c, T, slot, l, x, y, rs ? rs->h(l) : nullptr, r0, B);
     x = y;
   }
-  cl_head<R>(c, slot, x, s.out);
 }
 
 // ---- backward (pre-activation gradients; the parameter gradients are wgrad_kernel's) ---------------------------------------------
@@ -369,8 +461,7 @@ __device__ __forceinline__ void cl_forward(Cl& c, int slot, const NetShape& s, b
 // dz_{l-1}[r][k] = relu'(h_{l-1}[r][k]) * sum_n dz_l[r][n] * W_l[n][k]
 // want_din: din[r][j] = sum_c dz_0[r][c] * W0[c][j] (partials over own columns, summed over the cluster in rank order)
 template <int R, int CS>
-__device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, int keep0, const RowScratch* rs, int r0, bool want_din,
-                                            const float* const* tiles, int& ti) {
+__device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, int keep0, const RowScratch* rs, int r0, bool want_din, int& ti) {
   const int L = s.layers, B = rs ? rs->B : 0;
   const int t = threadIdx.x;
   if (rs && c.rank == 0 && t < R && r0 + t < B) {
@@ -378,12 +469,12 @@ __device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, 
     *reinterpret_cast<float2*>(rs->dout() + (int64_t)(r0 + t) * 2) = *reinterpret_cast<const float2*>(smem_f + c.dout + t * 2);
   }
   const int q = c.ncols >> 2;
-  int cur = next_dz(c);
+  int cur = L > 1 ? next_dz(c) : c.xl;                 // a single hidden layer: dz_0 is only read back by this CTA (want_din)
   {
     const bool push = L > 1;                          // a product reduces over it
     const int hd = sp_head(c, slot), Hl = c.act0 + (keep0 + L - 1) * R * c.ld;
     float* g = rs ? rs->dz(L - 1) : nullptr;
-    for (int idx = t; idx < R * q; idx += kThreads) {
+    for (int idx = t; idx < R * q; idx += kCT) {
       const int r = idx / q, cc = (idx - r * q) * 4, k = c.c_lo + cc;
       const float d0 = smem_f[c.dout + r * 2], d1 = smem_f[c.dout + r * 2 + 1];
       const float4 wa = lds4(hd + k), wb = lds4(hd + c.H + k), h = lds4(Hl + r * c.ld + k);
@@ -397,20 +488,21 @@ __device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, 
       if (g && r0 + r < B) *reinterpret_cast<float4*>(g + (int64_t)(r0 + r) * c.H + k) = o;
     }
     stamp(c, 40);
-    if (push) stage_wait(c, (uint32_t)(R * c.H * 4)); else __syncthreads();
+    if (push) stage_wait(c, (uint32_t)(R * c.H * 4)); else cta_sync();
     stamp(c, 41);
   }
   for (int l = L - 1; l >= 1; --l) {
-    const int T = tile_acquire(c, tiles[ti + c.ns - 1], ti);
-    ++ti;
+    const int T = tile_acquire(c, ti);
     stamp(c, 50);
     cl_product<R>(c, T, cur);
+    tile_release(c, ti);
+    ++ti;
     stamp(c, 51);
-    const int nxt = next_dz(c);
+    const bool push = l - 1 >= 1;                    // another product follows
+    const int nxt = push ? next_dz(c) : c.xl;
     const int Hp = c.act0 + (keep0 + l - 1) * R * c.ld;
     float* g = rs ? rs->dz(l - 1) : nullptr;
-    const bool push = l - 1 >= 1;                    // another product follows
-    for (int idx = t; idx < R * q; idx += kThreads) {
+    for (int idx = t; idx < R * q; idx += kCT) {
       const int r = idx / q, cc = (idx - r * q) * 4, k = c.c_lo + cc;
       const float4 p = cl_reduce4<R>(c, r, cc);
       const float4 h = lds4(Hp + r * c.ld + k);
@@ -420,75 +512,40 @@ __device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, 
       if (g && r0 + r < B) *reinterpret_cast<float4*>(g + (int64_t)(r0 + r) * c.H + k) = o;
     }
     stamp(c, 52);
-    if (push) stage_wait(c, (uint32_t)(R * c.H * 4)); else __syncthreads();
+    if (push) stage_wait(c, (uint32_t)(R * c.H * 4)); else cta_sync();
     stamp(c, 53);
     cur = nxt;
   }
   if (want_din) {
-    // partial over own columns: one warp per (r, j); the partials of the CS CTAs meet in dinp[rank][r][j] of every CTA
+    // partial over own columns: one warp per (r, j); only the action components j = 2, 3 are used (robot.py:386-391)
     const int warp = t >> 5, lane = t & 31;
     const int w0 = sp_w0(c, slot);
-    for (int p = warp; p < R * 2; p += kThreads / 32) {          // only the action components j = 2, 3 are used (robot.py:386-391)
+    for (int p = warp; p < R * 2; p += kCT / 32) {
       const int r = p >> 1, j = 2 + (p & 1);
       float v = 0.f;
-      for (int cc = lane; cc < c.ncols; cc += 32) v = fmaf(smem_f[cur + r * c.ld + c.c_lo + cc], smem_f[w0 + cc * 4 + j], v);
+      for (int cc = lane; cc < c.ncols; cc += 32) v = fmaf(smem_f[cur + r * c.ld + c.c_lo + cc], smem_f[w0 + (c.c_lo + cc) * 4 + j], v);
       v = warp_sum(v);
       if (lane == 0) smem_f[c.din + r * 4 + j] = v;
     }
-    __syncthreads();
-    if (t < R) {
-      const uint32_t own = smem_u32(smem_f + c.dinp + (c.rank * R + t) * 2), bar = stage_bar(c);
-      const float a = smem_f[c.din + t * 4 + 2], b = smem_f[c.din + t * 4 + 3];
-#pragma unroll
-      for (int k = 0; k < CS; ++k) st_async2(map_to_rank(own, (uint32_t)k), a, b, map_to_rank(bar, (uint32_t)k));
-    }
-    stage_wait(c, (uint32_t)(CS * R * 8));
-    if (t < R) {
-      float a = 0.f, b = 0.f;
-#pragma unroll
-      for (int k = 0; k < CS; ++k) { a += smem_f[c.dinp + (k * R + t) * 2]; b += smem_f[c.dinp + (k * R + t) * 2 + 1]; }
-      smem_f[c.din + t * 4 + 2] = a;
-      smem_f[c.din + t * 4 + 3] = b;
-    }
-    __syncthreads();
+    cta_sync();
+    const float a = t < R ? smem_f[c.din + t * 4 + 2] : 0.f, b2 = t < R ? smem_f[c.din + t * 4 + 3] : 0.f;
+    exchange_pairs<R, CS>(c, c.dinp, a, b2, c.din + 2, 4, 0.f, 0.f);
     stamp(c, 60);
   }
 }
 
-constexpr int kMaxTiles = 7 * (kMaxLayers - 1) + 4;      // critic step: 7 (L-1) tiles, + ns slack of nulls
+constexpr int kMaxTiles = 7 * (kMaxLayers - 1) + 4;      // critic step: 7 (L-1) tiles
 
-// common start: mbarriers, the small parameters of `nets` networks (warp 1 issues), the first weight tiles (warp 0)
-struct SmallNet { const float* P; NetShape s; };
-template <int NETS>
-__device__ __forceinline__ void cl_begin(Cl& c, const SmallNet (&nets)[NETS], const float* const* tiles) {
+// common start (all threads of the CTA): the mbarriers.  Ends with a CTA barrier.
+__device__ __forceinline__ void cl_begin(Cl& c) {
   if (threadIdx.x == 0) {
-    mbar_init(cl_bar(c, 0), 1);
-    mbar_init(cl_bar(c, 1), 1);
-    for (int i = 0; i < 3; ++i) mbar_init(cl_bar(c, 2 + i), 1);
-    mbar_init(cl_bar(c, 5), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(cl_bar(c, i), 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (threadIdx.x == 32) {
-    uint32_t bytes = 0;
-#pragma unroll
-    for (int n = 0; n < NETS; ++n) bytes += small_bytes(c, nets[n].s);
-    mbar_arrive_expect_tx(cl_bar(c, 5), bytes);
-  }
-  if (threadIdx.x >= 32 && threadIdx.x < 64) {
-    __syncwarp();
-    const int lane = threadIdx.x - 32;
-#pragma unroll
-    for (int n = 0; n < NETS; ++n)
-      if (lane < kMaxLayers + 3) small_issue(c, n, nets[n].P, nets[n].s, lane);
-  }
-#pragma unroll
-  for (int n = 0; n < NETS; ++n) small_zero(c, n, nets[n].s);
-  for (int i = 0; i < c.ns - 1; ++i) tile_issue(c, tiles[i], i);
 }
+// compute threads: the small parameters have landed; every CTA of the cluster runs and has its mbarriers set up
 __device__ __forceinline__ void cl_started(Cl& c) {
-  // the small parameters have landed; every CTA of the cluster runs and has its mbarriers set up
-  mbar_wait(cl_bar(c, 5), 0);
   stamp(c, 1);
   cluster_sync();
   stamp(c, 2);
@@ -496,7 +553,7 @@ __device__ __forceinline__ void cl_started(Cl& c) {
 
 // ---- critic phase (robot.py:312-366 up to the optimiser steps); see td3_critic_kernel for the arithmetic ---------------------------
 template <int R, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kClBlock, 1)
 td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp,
                           const int32_t* __restrict__ idx, const float* __restrict__ noise, int B, Td3Hyper hp, float* __restrict__ loss,
                           float* __restrict__ q_out, float* __restrict__ y_out, int32_t* __restrict__ steps, double* __restrict__ beta_pows, int ns,
@@ -508,7 +565,6 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
   stamp(c, 0);
   const int r0 = (int)cluster_id_x() * R;
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) advance_adam_clock(steps, beta_pows, 1);
 
   // weight tiles in the order of use: passes 0-2 forward, passes 3-4 forward then backward
   __shared__ const float* tiles[kMaxTiles];
@@ -531,9 +587,22 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
     }
     tiles[t] = p;
   }
-  const SmallNet nets[5] = {{params + ar.off(3), ar.actor}, {params + ar.off(4), ar.critic}, {params + ar.off(5), ar.critic},
-                            {params + ar.off(1), ar.critic}, {params + ar.off(2), ar.critic}};
-  cl_begin<5>(c, nets, tiles);
+  cl_begin(c);
+  stamp(c, 3);
+  if (t >= kCT) {                        // producer warp: weight tiles, in the order of use
+    cl_producer(c, tiles, 0, min(c.ns, 7 * (L - 1)));      // the first tiles need no free slot; then join the start barrier
+    if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 1);   // (read by the optimiser kernel that follows)
+    cluster_sync();
+    cl_producer(c, tiles, c.ns, 7 * (L - 1));
+    cluster_sync();
+    return;
+  }
+  {
+    const float* const Ps[5] = {params + ar.off(3), params + ar.off(4), params + ar.off(5), params + ar.off(1), params + ar.off(2)};
+    const NetShape ss[5] = {ar.actor, ar.critic, ar.critic, ar.critic, ar.critic};
+    small_load_all<5>(c, Ps, ss);
+  }
+  stamp(c, 4);
   float* S = smem_f + c.S;       // [R][8]: 0 s.x 1 s.y 2 a.x 3 a.y 4 reward 5 notdone 6 y 7 valid
   float* in0 = smem_f + c.in0;
   float* out = smem_f + c.out;
@@ -547,14 +616,16 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
     S[t * 8 + 4] = rp.r[j]; S[t * 8 + 5] = rp.notdone[j]; S[t * 8 + 7] = valid ? 1.f : 0.f;
     in0[t * 4 + 0] = s2.x; in0[t * 4 + 1] = s2.y; in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;
   }
+  stamp(c, 5);
   cl_started(c);
 
   int ti = 0;
+#pragma unroll 1
   for (int pass = 0; pass < 5; ++pass) {
     const NetShape shape = pass == 0 ? ar.actor : ar.critic;
     const bool train = pass >= 3;
     RowScratch rs{scratch + (train ? (pass - 3) : 0) * RowScratch::floats(B, ar.critic.hid, L), B, ar.critic.hid, L};
-    cl_forward<R, CS>(c, pass, shape, train, 0, train ? &rs : nullptr, r0, tiles, ti);
+    cl_forward<R, CS>(c, pass, shape, train, 0, train ? &rs : nullptr, r0, ti);
     if (t < R) {
       if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
         const int row = min(r0 + t, B - 1);
@@ -588,8 +659,8 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
         if (t == 0 && c.rank == 0) atomicAdd(loss + cr, l);
       }
     }
-    __syncthreads();
-    if (train) cl_backward<R, CS>(c, pass, shape, 0, &rs, r0, false, tiles, ti);
+    cta_sync();
+    if (train) cl_backward<R, CS>(c, pass, shape, 0, &rs, r0, false, ti);
   }
   stamp(c, 98);
   cluster_sync();        // no CTA leaves while stores of its peers may still be on their way to it
@@ -599,7 +670,7 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
 
 // ---- actor phase (robot.py:369-398 up to the optimiser step) ----------------------------------------------------------------------
 template <int R, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kClBlock, 1)
 td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float* __restrict__ params_t, float* __restrict__ scratch, ReplayView rp,
                          const int32_t* __restrict__ idx, int B, float* __restrict__ loss, int32_t* __restrict__ steps, double* __restrict__ beta_pows,
                          int ns, long long* prof) {
@@ -610,7 +681,6 @@ td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float
   stamp(c, 0);
   const int r0 = (int)cluster_id_x() * R;
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) advance_adam_clock(steps, beta_pows, 0);
   __shared__ const float* tiles[kMaxTiles];
   if (t < kMaxTiles) {
     const int n = L - 1;
@@ -623,8 +693,20 @@ td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float
     }
     tiles[t] = p;
   }
-  const SmallNet nets[2] = {{params + ar.off(0), ar.actor}, {params + ar.off(1), ar.critic}};
-  cl_begin<2>(c, nets, tiles);
+  cl_begin(c);
+  if (t >= kCT) {
+    cl_producer(c, tiles, 0, min(c.ns, 4 * (L - 1)));
+    if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 0);
+    cluster_sync();
+    cl_producer(c, tiles, c.ns, 4 * (L - 1));
+    cluster_sync();
+    return;
+  }
+  {
+    const float* const Ps[2] = {params + ar.off(0), params + ar.off(1)};
+    const NetShape ss[2] = {ar.actor, ar.critic};
+    small_load_all<2>(c, Ps, ss);
+  }
   float* S = smem_f + c.S;
   float* in0 = smem_f + c.in0;
   RowScratch rs{scratch, B, ar.actor.hid, ar.actor.layers};
@@ -638,34 +720,41 @@ td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float
   cl_started(c);
 
   int ti = 0;
-  // forward: a = pi(s) (fed the raw replay state, robot.py:386), then Q1(s, a)
-  cl_forward<R, CS>(c, 0, ar.actor, true, 0, &rs, r0, tiles, ti);
-  if (t < R) {
-    in0[t * 4 + 2] = smem_f[c.out + t * 2];
-    in0[t * 4 + 3] = smem_f[c.out + t * 2 + 1];
-  }
-  __syncthreads();
-  cl_forward<R, CS>(c, 1, ar.critic, true, L, nullptr, r0, tiles, ti);
-  if (t < R) {
-    const float valid = S[t * 8 + 7];
-    smem_f[c.dout + t * 2] = -valid / (float)B;
-    smem_f[c.dout + t * 2 + 1] = 0.f;
-    float l = -smem_f[c.out + t * 2] * valid / (float)B;
+  // forward: a = pi(s) (fed the raw replay state, robot.py:386), then Q1(s, a).  The two passes are iterations of ONE loop (and so are
+  // the two backward passes): every inlined copy of the layer code costs instruction-cache misses that a kernel of ~30 us does not amortise
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    cl_forward<R, CS>(c, pass, pass == 0 ? ar.actor : ar.critic, true, pass == 0 ? 0 : L, pass == 0 ? &rs : nullptr, r0, ti);
+    if (t < R) {
+      if (pass == 0) {
+        in0[t * 4 + 2] = smem_f[c.out + t * 2];
+        in0[t * 4 + 3] = smem_f[c.out + t * 2 + 1];
+      } else {
+        const float valid = S[t * 8 + 7];
+        smem_f[c.dout + t * 2] = -valid / (float)B;
+        smem_f[c.dout + t * 2 + 1] = 0.f;
+        float l = -smem_f[c.out + t * 2] * valid / (float)B;
 #pragma unroll
-    for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
-    if (t == 0 && c.rank == 0) atomicAdd(loss, l);
+        for (int o = R / 2; o > 0; o >>= 1) l += __shfl_xor_sync((R >= 32) ? 0xffffffffu : ((1u << R) - 1u), l, o);
+        if (t == 0 && c.rank == 0) atomicAdd(loss, l);
+      }
+    }
+    cta_sync();
   }
-  __syncthreads();
   // backward through critic 1 (only dQ/d(action) is needed), then through the actor
-  cl_backward<R, CS>(c, 1, ar.critic, L, nullptr, r0, true, tiles, ti);
-  if (t < R) {
-    smem_f[c.dout + t * 2] = smem_f[c.din + t * 4 + 2];
-    smem_f[c.dout + t * 2 + 1] = smem_f[c.din + t * 4 + 3];
-    // cl_backward stores in0 of the network it differentiates: the actor's input was (s, 0, 0)
-    in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    cl_backward<R, CS>(c, 1 - pass, pass == 0 ? ar.critic : ar.actor, pass == 0 ? L : 0, pass == 0 ? nullptr : &rs, r0, pass == 0, ti);
+    if (pass == 0) {
+      if (t < R) {
+        smem_f[c.dout + t * 2] = smem_f[c.din + t * 4 + 2];
+        smem_f[c.dout + t * 2 + 1] = smem_f[c.din + t * 4 + 3];
+        // cl_backward stores in0 of the network it differentiates: the actor's input was (s, 0, 0)
+        in0[t * 4 + 2] = 0.f; in0[t * 4 + 3] = 0.f;
+      }
+      cta_sync();
+    }
   }
-  __syncthreads();
-  cl_backward<R, CS>(c, 0, ar.actor, 0, &rs, r0, false, tiles, ti);
   stamp(c, 98);
   cluster_sync();
   stamp(c, 99);
@@ -729,7 +818,7 @@ int32_t rtd3::critic_cluster_launch(rtd3_td3* h, const float* params, const floa
   return dispatch(s, [&](auto r, auto cs) -> int32_t {
     auto* fn = td3_critic_cluster_kernel<decltype(r)::value, decltype(cs)::value>;
     RTD3_CUDA(ensure_dyn_smem((const void*)fn, p.bytes));
-    fn<<<grid, kThreads, p.bytes, st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, p.ns,
+    fn<<<grid, kClBlock, p.bytes, st>>>(h->ar, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, p.ns,
                                         g_prof[0]);
     RTD3_LAUNCHED();
     return 0;
@@ -745,7 +834,7 @@ int32_t rtd3::actor_cluster_launch(rtd3_td3* h, const float* params, const float
   return dispatch(s, [&](auto r, auto cs) -> int32_t {
     auto* fn = td3_actor_cluster_kernel<decltype(r)::value, decltype(cs)::value>;
     RTD3_CUDA(ensure_dyn_smem((const void*)fn, p.bytes));
-    fn<<<grid, kThreads, p.bytes, st>>>(h->ar, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows, p.ns, g_prof[1]);
+    fn<<<grid, kClBlock, p.bytes, st>>>(h->ar, params, params_t, scratch, rp, idx, batch, loss1, steps, beta_pows, p.ns, g_prof[1]);
     RTD3_LAUNCHED();
     return 0;
   });
@@ -765,7 +854,7 @@ int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch) {
     if (ensure_dyn_smem((const void*)fn, p.bytes) != cudaSuccess) return -2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ceil_div(batch, s.R) * s.CS), 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(kClBlock, 1, 1);
     cfg.dynamicSmemBytes = p.bytes;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;

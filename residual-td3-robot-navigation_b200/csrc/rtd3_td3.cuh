@@ -81,15 +81,18 @@ __host__ __device__ inline int64_t chunk_major_index_v(const NetShape& s, int64_
   return net_off + first + l * blk + ((n >> 2) * s.hid + k) * 4 + (n & 3);
 }
 
-// One element of torch.optim.Adam (defaults, robot.py:237-239): exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g,
-// 1 - beta2); param -= step_size * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps).  Every rounding is spelled out so that the three
-// kernels that apply it (td3_adam_polyak_kernel, the optimiser fused into wgrad_kernel, the cooperative kernel) agree bit for bit -
-// left to the compiler, the contraction of a*b + c*d differs from one kernel to the next.
+// One element of torch.optim.Adam (defaults, robot.py:237-239) in the operation order of torch's CPU kernels, measured against
+// torch.optim.Adam in the build container (oracle/td3_oracle.py: adam_step, pinned bit for bit by tests/test_oracle_td3.py):
+//   exp_avg.lerp_(grad, 1 - beta1)                       m = fma(g - m, 0.1f, m)
+//   exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)     v = fma(0.001f * g, g, v * 0.999f)         (both products rounded)
+//   denom = sqrt(v) / sqrt(bc2) + eps;  param.addcdiv_(exp_avg, denom, -step)      p = p + (-step * m) / denom
+// Every rounding is spelled out so that the three kernels that apply it (td3_adam_polyak_kernel, the optimiser fused into
+// wgrad_kernel, the cooperative kernel) agree bit for bit - left to the compiler, the contraction of a*b + c*d differs between them.
 __device__ __forceinline__ void adam_element(float g, float& m, float& v, float& p, float step, float sqrt_bc2) {
   m = __fmaf_rn(__fsub_rn(g, m), 0.1f, m);
-  v = __fmaf_rn(__fmul_rn(g, g), 0.001f, __fmul_rn(v, 0.999f));
+  v = __fmaf_rn(__fmul_rn(0.001f, g), g, __fmul_rn(v, 0.999f));
   const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), sqrt_bc2), 1e-8f);
-  p = __fsub_rn(p, __fmul_rn(step, __fdiv_rn(m, denom)));
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-step, m), denom));
 }
 
 // Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
