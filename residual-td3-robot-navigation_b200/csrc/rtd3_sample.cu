@@ -207,7 +207,7 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
 //    first: 2 000 of a round's 2 900 cycles);
 //  * smaller rounds only at the lowest mask levels, where the undecided band is wide.
 // The state written back is the un-tempered ring block the stream ended in.
-constexpr int kRing = 4;
+constexpr int kRing = 6;
 constexpr int kRingWords = kRing * RTD3_MT_N;
 
 __device__ __forceinline__ uint32_t mt_untemper(uint32_t y) {
@@ -241,15 +241,18 @@ __device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("b
 
 struct MaybeRec { int S; uint32_t rw; };
 
-__global__ void __launch_bounds__(512)
+// NW consumer warps (a round takes up to 32 NW draws) + 8 generator warps
+template <int NW>
+__global__ void __launch_bounds__(NW * 32 + 256)
 sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count, int32_t* __restrict__ J) {
+  constexpr int NC = NW * 32;
   __shared__ uint32_t mt[RTD3_MT_N], ring[kRingWords];
-  __shared__ int w_cnt[2][8];                        // per warp: sure draws | undecided draws << 16
-  __shared__ MaybeRec mb[2][8][32];
+  __shared__ int w_cnt[2][NW];                        // per warp: sure draws | undecided draws << 16
+  __shared__ MaybeRec mb[2][NW][32];
   __shared__ __align__(8) uint64_t full[kRing], empty[kRing];
   __shared__ volatile int s_done, s_last;
   const int tid = threadIdx.x;
-  for (int k = tid; k < RTD3_MT_N; k += 512) mt[k] = b.mt[(int64_t)k * b.n + stream_id];
+  for (int k = tid; k < RTD3_MT_N; k += NC + 256) mt[k] = b.mt[(int64_t)k * b.n + stream_id];
   const int pos0 = b.pos[stream_id];
   if (tid == 0) {
     for (int k = 0; k < kRing; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], 1); }
@@ -258,9 +261,9 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
   }
   __syncthreads();
 
-  if (tid >= 256) {
+  if (tid >= NC) {
     // ---- generator warps: block 0 is the state as it stands, block k its k-th twist
-    const int t = tid - 256;
+    const int t = tid - NC;
     constexpr int N = RTD3_MT_N, M = 397;
     for (int blk = 0;; ++blk) {
       const int slot = blk % kRing;
@@ -304,8 +307,11 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
       const int lvl = 31 - __clz(i);                 // mask(i) = 2^(lvl+1) - 1
       const int gap = i - (1 << lvl);                // bounds down to i - gap keep mask(i)
       // about sqrt(32 * 2^(lvl+1)) draws keep the expected number of undecided draws near 16
-      const int want = lvl >= 8 ? 256 : (lvl >= 6 ? 128 : 64);
-      const int g = min(max(gap + 1, 32), want);
+      const int want = lvl >= 10 ? NC : (lvl >= 8 ? 256 : (lvl >= 6 ? 128 : 64));
+      // close to the next power of two the round runs over it: about two raw draws per remaining index of this level cross the
+      // boundary (acceptance there is ~50 %), the draws behind it are undecided (their mask depends on how many were accepted) and are
+      // resolved exactly like the others - instead of five or six ever shorter rounds that stop at the boundary
+      const int g = min(2 * (gap + 1) + 32, want);
       // ring upkeep: blocks before the one holding draw gpos - 1 are finished with; blocks up to the one of draw gpos + g - 1 are needed
       if (t == 0)
         while (released_words + (uint32_t)RTD3_MT_N + 1u <= gpos) {
@@ -329,20 +335,20 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
       const int S_in = __popc(bs & lt), m_in = __popc(bm & lt);
       if (lane == 0) w_cnt[par][warp] = __popc(bs) | (__popc(bm) << 16);
       if (maybe) mb[par][warp][m_in] = MaybeRec{S_in, rw};
-      bar_named(1, 256);
+      bar_named(1, NC);
       // every WARP resolves the undecided draws of the whole round, 32 at a time in stream order (lane q: the q-th of them): bound_q =
       // i - (sure draws before q) - (accepted undecided draws before q); the last term by iterating the ballot to its fixed point
       // (lane L depends only on lanes < L).  Redundant in all eight warps - what it saves is compaction, a resolver warp, three barriers.
-      int sbef[8], mbef[8], sure_run = 0, maybe_run = 0;
+      int sbef[NW], mbef[NW], sure_run = 0, maybe_run = 0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < NW; ++w) {
         const int cnt = w_cnt[par][w];
         sbef[w] = sure_run; mbef[w] = maybe_run;
         sure_run += cnt & 0xffff; maybe_run += cnt >> 16;
       }
       int S_base = 0, nb = m_in;                     // sure draws before my warp; undecided draws before me
 #pragma unroll
-      for (int w = 0; w < 8; ++w)
+      for (int w = 0; w < NW; ++w)
         if (w == warp) { S_base = sbef[w]; nb += mbef[w]; }
       int extra = 0, my_before = 0;
       bool my_acc = false;
@@ -351,7 +357,7 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
         const bool on = q < maybe_run;
         int wq = 0, sb = sbef[0], mq = mbef[0];
 #pragma unroll
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < NW; ++w)
           if (q >= mbef[w]) { wq = w; sb = sbef[w]; mq = mbef[w]; }
         MaybeRec r = MaybeRec{0, 0u};
         if (on) r = mb[par][wq][q - mq];
@@ -378,11 +384,11 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
       const int total_acc = sure_run + extra;        // the same number in every thread
       par ^= 1;
       if (total_acc >= i) {
-        bar_named(1, 256);
+        bar_named(1, NC);
         gpos += (uint32_t)(s_last + 1);
         rpos += s_last + 1;
         i = 0;
-        bar_named(1, 256);                           // everybody has read s_last before the next sample's last round writes it
+        bar_named(1, NC);                           // everybody has read s_last before the next sample's last round writes it
       } else {
         gpos += (uint32_t)g;
         rpos += g;
@@ -397,9 +403,9 @@ sample_swaps_pipelined_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int3
   if (pos == 0 && gpos > 0u) { blk -= 1; pos = RTD3_MT_N; }
   // block blk is still in the ring (nothing at or after the block of draw gpos - 1 was released); make sure it has been produced
   while (avail <= blk) { mbar_wait(&full[avail % kRing], (uint32_t)((avail / kRing) & 1)); ++avail; }
-  bar_named(1, 256);
+  bar_named(1, NC);
   if (t == 0) s_done = 1;                              // the generator polls this word while it waits for a free slot
-  for (int k = t; k < RTD3_MT_N; k += 256) b.mt[(int64_t)k * b.n + stream_id] = mt_untemper(ring[(blk % kRing) * RTD3_MT_N + k]);
+  for (int k = t; k < RTD3_MT_N; k += NC) b.mt[(int64_t)k * b.n + stream_id] = mt_untemper(ring[(blk % kRing) * RTD3_MT_N + k]);
   if (t == 0) b.pos[stream_id] = pos;
 }
 
@@ -463,8 +469,10 @@ extern "C" int32_t rtd3_sample_indices_mt19937(const rtd3_mt_bank* bank, int64_t
   RTD3_CUDA(ensure_dyn_smem((const void*)sample_trace_kernel, 56000 * 4));
   cudaStream_t st = (cudaStream_t)stream;
   static const bool legacy = getenv("RTD3_SAMPLER_LEGACY") != nullptr;      // development: the block-per-round form above
+  static const bool wide = getenv("RTD3_SAMPLER_WIDE") != nullptr;          // 512-draw rounds: measured slower (12.2 against 8.75 ms)
   if (legacy) sample_swaps_kernel<<<1, kSampleThreads, 0, st>>>(*bank, stream_id, n, count, scratch);
-  else sample_swaps_pipelined_kernel<<<1, 512, 0, st>>>(*bank, stream_id, n, count, scratch);
+  else if (wide) sample_swaps_pipelined_kernel<16><<<1, 16 * 32 + 256, 0, st>>>(*bank, stream_id, n, count, scratch);
+  else sample_swaps_pipelined_kernel<8><<<1, 8 * 32 + 256, 0, st>>>(*bank, stream_id, n, count, scratch);
   RTD3_LAUNCHED();
   const size_t smem = (size_t)((n + 3) & ~3) * 4;
   sample_trace_kernel<<<count, 256, smem, st>>>(scratch, n, batch, out);
