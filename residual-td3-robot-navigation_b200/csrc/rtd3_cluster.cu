@@ -54,12 +54,15 @@ __device__ __forceinline__ void st_async2(uint32_t addr, float a, float b, uint3
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// (default semantics, acquire at CTA scope: the bytes counted on the barrier are visible to whoever observes the phase - the pattern
+// of every TMA / st.async consumer.  With .acquire.cluster ptxas adds CCTL.IVALL, an L1 invalidate, to EVERY wait of every warp:
+// 12 % of the kernel's stall samples.)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAITC_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONEC_%=;\n"
       "bra WAITC_%=;\n"
       "DONEC_%=:\n"
@@ -325,27 +328,29 @@ __device__ __forceinline__ void cl_first(Cl& c, int slot, int in_dim, int Y, flo
 // ---- hidden product, own columns: red[g][r][c] = sum_{j in group g} X[r][j] * T[c][j] ------------------------------------------------
 // thread = (reduction group, row group rg, column group cl); it owns rows rg, rg + RG, rg + 2 RG, rg + 3 RG (neighbouring row groups
 // read neighbouring rows: with ld = H + 4 their float4 fall into different banks) and the 4 columns of tile group cl
+// (inlined into the forward and the backward pass: one shared __noinline__ copy was measured - 15 % of the kernel's stall samples are
+// instruction fetches - and was slower, 2.9-3.5 k cycles per product against 2.5 k)
 template <int R>
-__device__ __forceinline__ void cl_product(const Cl& c, int T, int X) {
+__device__ __forceinline__ void cl_product_impl(int T, int X, int H, int ld, int Wc, int ncols, int ncg_sh, int part, int red) {
   constexpr int RG = R / 4;
   const int t = threadIdx.x;
-  const int cl = t & ((1 << c.ncg_sh) - 1);
-  const int rg = (t >> c.ncg_sh) % RG;
-  const int kg = (t >> c.ncg_sh) / RG;
-  const int jlo = kg * c.part, jhi = min(c.H, jlo + c.part);
+  const int cl = t & ((1 << ncg_sh) - 1);
+  const int rg = (t >> ncg_sh) % RG;
+  const int kg = (t >> ncg_sh) / RG;
+  const int jlo = kg * part, jhi = min(H, jlo + part);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-  if (4 * cl < c.ncols) {
-    const int tw = T + cl * (4 * c.H + 4), xr = X + rg * c.ld;
+  if (4 * cl < ncols) {
+    const int tw = T + cl * (4 * H + 4), xr = X + rg * ld;
 #pragma unroll 2
     for (int j = jlo; j < jhi; j += 4) {
       float4 w[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[e] = lds4(tw + e * c.H + j);
+      for (int e = 0; e < 4; ++e) w[e] = lds4(tw + e * H + j);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 x = lds4(xr + i * RG * c.ld + j);
+        const float4 x = lds4(xr + i * RG * ld + j);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           acc[i][e] = fmaf(x.x, w[e].x, acc[i][e]); acc[i][e] = fmaf(x.y, w[e].y, acc[i][e]);
@@ -355,9 +360,13 @@ __device__ __forceinline__ void cl_product(const Cl& c, int T, int X) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(smem_f + c.red + (kg * R + rg + i * RG) * c.Wc + 4 * cl) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(smem_f + red + (kg * R + rg + i * RG) * Wc + 4 * cl) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
   cta_sync();
+}
+template <int R>
+__device__ __forceinline__ void cl_product(const Cl& c, int T, int X) {
+  cl_product_impl<R>(T, X, c.H, c.ld, c.Wc, c.ncols, c.ncg_sh, c.part, c.red);
 }
 
 // sum of the partials of the four values (r, cc..cc+3)

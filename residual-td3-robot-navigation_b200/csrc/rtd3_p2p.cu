@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "rtd3_common.cuh"
+#include "rtd3_td3.cuh"
 
 namespace rtd3 {
 
@@ -51,10 +52,11 @@ __device__ __forceinline__ float4 ld_fresh(const float4* p) {   // written by a 
   return v;
 }
 
+// phases (1) and (2) of the header comment + the wait of phase (3); returns this step's number
 template <int kWorld>
-__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter, float* __restrict__ out,
-                                                            float* __restrict__ local_grads, int64_t count4, int64_t stride4,
-                                                            unsigned int* block_counter) {
+__device__ __forceinline__ unsigned long long p2p_push_and_wait(const P2pPeers& peers, int rank, unsigned long long* seq_counter,
+                                                                float* __restrict__ local_grads, int64_t count4, int64_t stride4,
+                                                                unsigned int* block_counter) {
   __shared__ bool s_last;
   __shared__ unsigned long long s_seq;
   const int tid = threadIdx.x;
@@ -89,18 +91,64 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int 
       *seq_counter = seq;                              // ... and has read the step number
     }
   }
-  // (3) all W gradients of this step have landed here: add them in rank order
+  // (3) all W gradients of this step have landed here
   if (tid < kWorld) wait_flag(peers.flags[rank] + tid, seq);
   __syncthreads();
+  return seq;
+}
+
+template <int kWorld>
+__device__ __forceinline__ float4 p2p_sum_slots(const float4* mine, int64_t stride4, int64_t i) {
+  float4 v[kWorld];
+#pragma unroll
+  for (int r = 0; r < kWorld; ++r) v[r] = ld_fresh(mine + (int64_t)r * stride4 + i);
+  float4 acc = v[0];
+#pragma unroll
+  for (int r = 1; r < kWorld; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }   // rank order on every rank
+  return acc;
+}
+
+template <int kWorld>
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter, float* __restrict__ out,
+                                                            float* __restrict__ local_grads, int64_t count4, int64_t stride4,
+                                                            unsigned int* block_counter) {
+  const unsigned long long seq = p2p_push_and_wait<kWorld>(peers, rank, seq_counter, local_grads, count4, stride4, block_counter);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * stride4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < count4; i += stride) {
-    float4 v[kWorld];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride)
+    reinterpret_cast<float4*>(out)[i] = p2p_sum_slots<kWorld>(mine, stride4, i);
+}
+
+// The same all-reduce with the optimiser applied to the sums: phase (3) walks the online arena like td3_adam_polyak_kernel - Adam on the
+// elements of the reduced slice (gradient = sum of the W slots x grad_scale), the Polyak blend where asked for - so the summed
+// gradients never go back to memory and the separate optimiser launch (one more pass over the arena, ~10 us) disappears.
+template <int kWorld>
+__global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter,
+                                                                 float* __restrict__ local_grads, int64_t count4, int64_t stride4,
+                                                                 unsigned int* block_counter, P2pAdamArgs o) {
+  __shared__ float s_step[2], s_bc2[2];
+  if (threadIdx.x < 2) {                                              // 0: actor optimiser, 1: both critic optimisers
+    const double bc1 = 1.0 - o.beta_pows[2 * threadIdx.x], bc2 = 1.0 - o.beta_pows[2 * threadIdx.x + 1];
+    const double lr = threadIdx.x == 0 ? (double)o.lr_actor : (double)o.lr_critic;
+    s_step[threadIdx.x] = (float)(lr / bc1);
+    s_bc2[threadIdx.x] = (float)sqrt(bc2);
+  }
+  const unsigned long long seq = p2p_push_and_wait<kWorld>(peers, rank, seq_counter, local_grads + o.off, count4, stride4, block_counter);
+  const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * stride4;
+  const int n4 = (int)(o.ar.online_total() >> 2), off4 = (int)(o.off >> 2);
+  const int off1 = (int)o.ar.off(1), off2 = (int)o.ar.off(2);
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const int i = i4 * 4;
+    const int net = i < off1 ? 0 : (i < off2 ? 1 : 2);               // slots are multiples of 4 floats: a group never straddles two
+    const bool do_adam = (o.nets >> net) & 1, do_polyak = (o.polyak >> net) & 1;
+    if (!do_adam && !do_polyak) continue;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (do_adam) g = p2p_sum_slots<kWorld>(mine, stride4, (int64_t)(i4 - off4));
+    const float gg[4] = {g.x * o.grad_scale, g.y * o.grad_scale, g.z * o.grad_scale, g.w * o.grad_scale};
+    const int k = net == 0 ? 0 : 1;
 #pragma unroll
-    for (int r = 0; r < kWorld; ++r) v[r] = ld_fresh(mine + (int64_t)r * stride4 + i);
-    float4 acc = v[0];
-#pragma unroll
-    for (int r = 1; r < kWorld; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    for (int e = 0; e < 4; ++e)
+      adam_polyak_apply(o.ar, i + e, net, gg[e], do_adam, do_polyak, o.params, o.params_t, o.params_uv, o.m, o.v, s_step[k], s_bc2[k], o.tau);
   }
 }
 
@@ -137,6 +185,40 @@ extern "C" int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* 
   const void* fn = nullptr;
   switch (world) {
 #define RTD3_P2P_CASE(W) case W: fn = (const void*)p2p_allreduce_kernel<W>; break;
+    RTD3_P2P_CASE(2) RTD3_P2P_CASE(3) RTD3_P2P_CASE(4) RTD3_P2P_CASE(5) RTD3_P2P_CASE(6) RTD3_P2P_CASE(7) RTD3_P2P_CASE(8)
+#undef RTD3_P2P_CASE
+  }
+  RTD3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), kargs, 0, st));
+  RTD3_LAUNCHED();
+  return 0;
+}
+
+
+int32_t rtd3::p2p_allreduce_adam_launch(const rtd3_p2p_state* ps, float* local_grads, int64_t count, const P2pAdamArgs& opt, cudaStream_t st) {
+  RTD3_CHECK_ARG(ps && ps->peer_recv && ps->peer_flags && local_grads && ps->block_counter && ps->seq_counter, "null argument");
+  const int world = ps->world, rank = ps->rank;
+  RTD3_CHECK_ARG(world >= 2 && world <= kP2pMaxWorld && rank >= 0 && rank < world, "bad rank / world");
+  RTD3_CHECK_ARG(count > 0 && count % 4 == 0 && opt.off % 4 == 0, "count / offset must be multiples of 4");
+  RTD3_CHECK_ARG(ps->slot_floats >= count && ps->slot_floats % 4 == 0, "slot_floats must be a multiple of 4 and at least count");
+  P2pPeers p{};
+  for (int r = 0; r < world; ++r) {
+    RTD3_CHECK_ARG(ps->peer_recv[r] && ps->peer_flags[r], "null peer pointer");
+    p.recv[r] = ps->peer_recv[r];
+    p.flags[r] = (unsigned long long*)ps->peer_flags[r];
+  }
+  // cooperative launch with at most one CTA per SM: see rtd3_p2p_allreduce
+  int64_t count4 = count / 4, stride4 = ps->slot_floats / 4;
+  int num_sms = 0;
+  RTD3_CUDA(current_num_sms(&num_sms));
+  const int grid = (int)std::min<int64_t>((int64_t)num_sms, ceil_div(opt.ar.online_total() / 4, 256));
+  unsigned long long* sc = (unsigned long long*)ps->seq_counter;
+  int rk = rank;
+  unsigned int* bc = ps->block_counter;
+  P2pAdamArgs o = opt;
+  void* kargs[] = {&p, &rk, &sc, &local_grads, &count4, &stride4, &bc, &o};
+  const void* fn = nullptr;
+  switch (world) {
+#define RTD3_P2P_CASE(W) case W: fn = (const void*)p2p_allreduce_adam_kernel<W>; break;
     RTD3_P2P_CASE(2) RTD3_P2P_CASE(3) RTD3_P2P_CASE(4) RTD3_P2P_CASE(5) RTD3_P2P_CASE(6) RTD3_P2P_CASE(7) RTD3_P2P_CASE(8)
 #undef RTD3_P2P_CASE
   }

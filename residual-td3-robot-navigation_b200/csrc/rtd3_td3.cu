@@ -152,28 +152,6 @@ td3_actor_kernel(Arena ar, const float* __restrict__ params, const float* __rest
   }
 }
 
-// Where arena element o (offset inside its network's slot) sits in the derived copies, decomposed ONCE per element in 32-bit
-// arithmetic: the 64-bit divisions of transposed_index / chunk_major_index (five calls per element) made this kernel ~13 us.
-struct CopyIndex {
-  int t, u, v;          // offsets inside the slot in the transposed / forward chunk-major / input-gradient chunk-major copies
-  bool hidden;          // a hidden-to-hidden weight (the only entries that move, and that are TF32-rounded in u / v)
-};
-__device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
-  CopyIndex c{o, o, o, false};
-  const int first = s.in * s.hid + s.hid, blk = s.hid * s.hid + s.hid;
-  if (o < first) return c;
-  const unsigned o2 = (unsigned)(o - first);
-  const unsigned l = o2 / (unsigned)blk, rem = o2 - l * (unsigned)blk;
-  if ((int)l >= s.layers - 1 || rem >= (unsigned)(s.hid * s.hid)) return c;
-  const unsigned n = rem / (unsigned)s.hid, k = rem - n * (unsigned)s.hid;
-  const int base = first + (int)l * blk;
-  c.hidden = true;
-  c.t = base + (int)(k * s.hid + n);
-  c.u = base + (int)((((k >> 2) * s.hid + n) << 2) + (k & 3u));
-  c.v = base + (int)((((n >> 2) * s.hid + k) << 2) + (n & 3u));
-  return c;
-}
-
 // Optional optimiser fused into the weight-gradient pass (single GPU, batch <= 512: every gradient element is final when its job
 // writes it): torch.optim.Adam on the element (the arithmetic of td3_adam_polyak_kernel, bit for bit) and, on request, the Polyak
 // blend of the matching target parameter - the two separate optimiser launches of an epoch (13 us at B = 256) disappear.
@@ -462,39 +440,14 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
     s_bc2[threadIdx.x] = (float)sqrt(bc2);
   }
   __syncthreads();
-  const int n_online = (int)ar.online_total(), total = (int)ar.total();
-  const int off1 = (int)ar.off(1), off2 = (int)ar.off(2);
+  const int n_online = (int)ar.online_total();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_online; i += gridDim.x * blockDim.x) {
-    const int net = i < off1 ? 0 : (i < off2 ? 1 : 2);
+    const int net = i < (int)ar.off(1) ? 0 : (i < (int)ar.off(2) ? 1 : 2);
     const bool do_adam = (nets >> net) & 1, do_polyak = (polyak >> net) & 1;
     if (!do_adam && !do_polyak) continue;
-    const int noff = net == 0 ? 0 : (net == 1 ? off1 : off2);
-    const CopyIndex ci = copy_index(net == 0 ? ar.actor : ar.critic, i - noff);
-    float p = params[i];
-    if (do_adam) {
-      const int o = net == 0 ? 0 : 1;
-      const float g = grads[i] * grad_scale;
-      grads[i] = 0.f;
-      float mi = m[i], vi = v[i];
-      adam_element(g, mi, vi, p, s_step[o], s_bc2[o]);
-      m[i] = mi;
-      v[i] = vi;
-      params[i] = p;
-      params_t[noff + ci.t] = p;
-      if (params_uv) {                                                  // tensor-core operand copies (see rtd3_td3.cuh)
-        const float pr = ci.hidden ? tf32_rn(p) : p;
-        params_uv[noff + ci.u] = pr;
-        params_uv[total + noff + ci.v] = pr;
-      }
-    }
-    if (do_polyak) {
-      const int ti = n_online + i;                                    // target slots mirror the online layout
-      // torch evaluates target*(1-tau) + source*tau as three separately rounded float32 ops (robot.py:309): no fma here
-      const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
-      params[ti] = tv;
-      params_t[n_online + noff + ci.t] = tv;
-      if (params_uv) params_uv[n_online + noff + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
-    }
+    float g = 0.f;
+    if (do_adam) { g = grads[i] * grad_scale; grads[i] = 0.f; }
+    adam_polyak_apply(ar, i, net, g, do_adam, do_polyak, params, params_t, params_uv, m, v, s_step[net == 0 ? 0 : 1], s_bc2[net == 0 ? 0 : 1], tau);
   }
 }
 
@@ -860,6 +813,17 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
     fz.tau = a->tau; fz.n_online = (int)n_online; fz.total = (int)h->ar.total(); fz.shape = actor ? h->ar.actor : h->ar.critic;
     return fz;
   };
+  // Data parallel over peer memory: the all-reduce kernel applies the optimiser to the sums it forms (one launch and one pass over the
+  // arena less per optimiser step); RTD3_P2P_FUSE=0 keeps the two-kernel form (development)
+  static const bool p2p_fuse_env = !(getenv("RTD3_P2P_FUSE") && atoi(getenv("RTD3_P2P_FUSE")) == 0);
+  const bool fuse_p2p = a->world > 1 && a->p2p && p2p_fuse_env;
+  auto p2p_opt = [&](int nets, int polyak, int64_t off) {
+    P2pAdamArgs o{};
+    o.ar = h->ar; o.params = a->params; o.params_t = a->params_t; o.params_uv = a->params_uv; o.m = a->adam_m; o.v = a->adam_v;
+    o.beta_pows = a->beta_pows; o.lr_actor = a->lr_actor; o.lr_critic = a->lr_critic; o.grad_scale = scale; o.tau = a->tau;
+    o.nets = nets; o.polyak = polyak; o.off = off;
+    return o;
+  };
   int64_t k = 0, ka = 0;
   int32_t rc = 0;
   for (int e = 0; e < E; ++e) {
@@ -874,7 +838,9 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
       rc = critic_step_fused(h, a->params, a->params_t, a->grads, a->scratch, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr,
                              a->steps, a->beta_pows, st, fuse ? fuse_for(false, e % delay == 0) : AdamFuse{});
     if (rc) return rc;
-    if (!fuse) {
+    if (fuse_p2p) {
+      if ((rc = p2p_allreduce_adam_launch(a->p2p, a->grads, n_online - off_c, p2p_opt(0b110, 0, off_c), st))) return rc;
+    } else if (!fuse) {
       if ((rc = update_allreduce(a, off_c, n_online - off_c, st))) return rc;
       if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b110, a->lr_actor,
                                      a->lr_critic, scale, 0, a->tau, st)))
@@ -890,7 +856,9 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
                               fuse ? fuse_for(true, true) : AdamFuse{});
       ++ka;
       if (rc) return rc;
-      if (!fuse) {
+      if (fuse_p2p) {
+        if ((rc = p2p_allreduce_adam_launch(a->p2p, a->grads, off_c, p2p_opt(0b001, 0b111, 0), st))) return rc;
+      } else if (!fuse) {
         if ((rc = update_allreduce(a, 0, off_c, st))) return rc;
         if ((rc = rtd3_td3_adam_polyak(h, a->params, a->params_t, a->params_uv, opt_grads, a->adam_m, a->adam_v, a->beta_pows, 0b001, a->lr_actor,
                                        a->lr_critic, scale, 0b111, a->tau, st)))

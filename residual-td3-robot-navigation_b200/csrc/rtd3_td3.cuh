@@ -2,6 +2,7 @@
 #pragma once
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
+#include "rtd3_tc.cuh"
 
 namespace rtd3 {
 
@@ -95,6 +96,63 @@ __device__ __forceinline__ void adam_element(float g, float& m, float& v, float&
   p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-step, m), denom));
 }
 
+// Where arena element o (offset inside its network's slot) sits in the derived copies, decomposed ONCE per element in 32-bit
+// arithmetic: the 64-bit divisions of transposed_index / chunk_major_index (five calls per element) made this kernel ~13 us.
+struct CopyIndex {
+  int t, u, v;          // offsets inside the slot in the transposed / forward chunk-major / input-gradient chunk-major copies
+  bool hidden;          // a hidden-to-hidden weight (the only entries that move, and that are TF32-rounded in u / v)
+};
+__device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
+  CopyIndex c{o, o, o, false};
+  const int first = s.in * s.hid + s.hid, blk = s.hid * s.hid + s.hid;
+  if (o < first) return c;
+  const unsigned o2 = (unsigned)(o - first);
+  const unsigned l = o2 / (unsigned)blk, rem = o2 - l * (unsigned)blk;
+  if ((int)l >= s.layers - 1 || rem >= (unsigned)(s.hid * s.hid)) return c;
+  const unsigned n = rem / (unsigned)s.hid, k = rem - n * (unsigned)s.hid;
+  const int base = first + (int)l * blk;
+  c.hidden = true;
+  c.t = base + (int)(k * s.hid + n);
+  c.u = base + (int)((((k >> 2) * s.hid + n) << 2) + (k & 3u));
+  c.v = base + (int)((((n >> 2) * s.hid + k) << 2) + (n & 3u));
+  return c;
+}
+
+
+// One arena element of the optimiser pass: Adam (when do_adam, with the already scaled gradient g) on parameter i of online network
+// `net`, then (when do_polyak) the blend of the matching target parameter: t = t*(1-tau) + p*tau; the transposed copy and the
+// tensor-core operand copies (params_uv, nullable) are kept in step.  Shared by td3_adam_polyak_kernel and the peer-memory
+// all-reduce that applies the optimiser to the sums it forms (rtd3_p2p.cu).
+__device__ __forceinline__ void adam_polyak_apply(const Arena& ar, int i, int net, float g, bool do_adam, bool do_polyak, float* __restrict__ params,
+                                                  float* __restrict__ params_t, float* __restrict__ params_uv, float* __restrict__ m,
+                                                  float* __restrict__ v, float step, float sqrt_bc2, float tau) {
+  const int n_online = (int)ar.online_total(), total = (int)ar.total();
+  const int noff = net == 0 ? 0 : (int)ar.off(net);
+  const CopyIndex ci = copy_index(net == 0 ? ar.actor : ar.critic, i - noff);
+  float p = params[i];
+  if (do_adam) {
+    float mi = m[i], vi = v[i];
+    adam_element(g, mi, vi, p, step, sqrt_bc2);
+    m[i] = mi;
+    v[i] = vi;
+    params[i] = p;
+    params_t[noff + ci.t] = p;
+    if (params_uv) {                                                  // tensor-core operand copies
+      const float pr = ci.hidden ? tf32_rn(p) : p;
+      params_uv[noff + ci.u] = pr;
+      params_uv[total + noff + ci.v] = pr;
+    }
+  }
+  if (do_polyak) {
+    const int ti = n_online + i;                                    // target slots mirror the online layout
+    // torch evaluates target*(1-tau) + source*tau as three separately rounded float32 ops (robot.py:309): no fma here
+    const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
+    params[ti] = tv;
+    params_t[n_online + noff + ci.t] = tv;
+    if (params_uv) params_uv[n_online + noff + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
+  }
+}
+
 // Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
 // beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
 __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {
@@ -122,6 +180,19 @@ int32_t critic_cluster_launch(rtd3_td3* h, const float* params, const float* par
                               double* beta_pows, cudaStream_t st);
 int32_t actor_cluster_launch(rtd3_td3* h, const float* params, const float* params_t, float* scratch, const ReplayView& rp, const int32_t* idx,
                              int32_t batch, float* loss1, int32_t* steps, double* beta_pows, cudaStream_t st);
+
+// The gradient all-reduce over peer memory with the optimiser applied to the sums (rtd3_p2p.cu): what update_allreduce +
+// rtd3_td3_adam_polyak do in two launches and two passes over the arena.  [off, off + count) = the slice of the gradient arena this
+// optimiser step reduces; nets / polyak as in rtd3_td3_adam_polyak.
+struct P2pAdamArgs {
+  Arena ar;
+  float* params; float* params_t; float* params_uv; float* m; float* v;
+  const double* beta_pows;
+  float lr_actor, lr_critic, grad_scale, tau;
+  int nets, polyak;
+  int64_t off;
+};
+int32_t p2p_allreduce_adam_launch(const rtd3_p2p_state* p, float* local_grads, int64_t count, const P2pAdamArgs& opt, cudaStream_t st);
 }  // namespace rtd3
 
 // the opaque learner handle of the C ABI
