@@ -51,6 +51,8 @@ __device__ __forceinline__ void st_async2(uint32_t addr, float a, float b, uint3
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a), "f"(b), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -80,14 +82,14 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n
 struct Cl {
   int ring;          // [ns][Wc / 4][4 H + 4] weight slices: groups of 4 rows, row n = the H weights that feed own output column n
   int red;           // [KG][R][Wc] partial sums of the reduction groups
-  int small;         // per network: W0 [H][4] | b0 [H] | b_l slices [L-1][Wc] | head [2][H] | head bias [4]
+  int small;         // per network: W0 [H][in] b0 [H] (one copy) | pad to 5 H | b_l [L-1][H] | head [out][H] + head bias (one copy)
   int act0;          // kept activations, nkeep full-width [R][ld] tiles
   int xl;            // first-layer output of a network whose activations are not kept (written locally only)
   int dz0, dz1;      // full-width tiles that receive pushed slices (they alternate; one tile when there is one push per pass)
   int in0, out, dout, din, S;         // [R][4], [R][2], [R][2], [R][4], [R][8]
   int hpart;         // [R][Wc / 4][2] head contributions of the column groups
   int hp, dinp;      // [CS][R][2] each: head / input-gradient partial sums of the CTAs of the cluster
-  int bar;           // mbarriers (uint64): [0,1] stages, [2..4] ring slot full, [5..7] ring slot empty
+  int bar;           // mbarriers (uint64): [0,1] stages, [2..4] ring slot full, [5..7] ring slot empty, [8] small parameters
   int ld, Wc, H, L, ns, tile_floats, small_stride;
   int ncg_sh;        // log2 of the column groups a reduction group spans (>= Wc / 4)
   int kgn, part;     // reduction groups and their length
@@ -118,9 +120,9 @@ static ClPlan make_plan(int R, int CS, int H, int L, int nets, int nkeep) {
   const int Wc = cl_wc(H, CS), ld = H + 4;
   const int kgn = kCT / ((1 << cl_ncg_sh(Wc)) * (R / 4));
   const size_t tile = (size_t)(Wc / 4) * (4 * H + 4);
-  const size_t small_stride = (size_t)7 * H + (size_t)(L - 1) * Wc + 4;
+  const size_t small_stride = (size_t)(6 + L) * H + 4;
   const size_t fixed = (size_t)kgn * R * Wc + nets * small_stride + (size_t)(nkeep + (L >= 3 ? 3 : 2)) * R * ld + R * (4 + 2 + 2 + 4 + 8) +
-                       (size_t)R * (Wc / 4) * 2 + (size_t)2 * CS * R * 2 + 16;
+                       (size_t)R * (Wc / 4) * 2 + (size_t)2 * CS * R * 2 + 24;
   ClPlan p;
   p.ns = 3;
   p.bytes = (fixed + p.ns * tile) * sizeof(float);
@@ -136,7 +138,7 @@ __device__ __forceinline__ void cl_carve(Cl& c, int R, int CS, int H, int L, int
   c.Wc = cl_wc(H, CS);
   c.ld = H + 4;
   c.tile_floats = (c.Wc / 4) * (4 * H + 4);
-  c.small_stride = 7 * H + (L - 1) * c.Wc + 4;
+  c.small_stride = (6 + L) * H + 4;
   c.ncg_sh = cl_ncg_sh(c.Wc);
   c.kgn = kCT / ((1 << c.ncg_sh) * (R / 4));
   c.part = ((H + 4 * c.kgn - 1) / (4 * c.kgn)) * 4;
@@ -198,59 +200,25 @@ __device__ __forceinline__ void tile_release(const Cl& c, int i) {
   if (threadIdx.x == 0) mbar_arrive(cl_bar(c, 5 + i % c.ns));
 }
 
-// small parameters of one network: W0 [H][in] | b0 [H] | b_l slices | head [out][H] + head bias.  Fetched as float4 by all compute
-// threads, loads first and stores after (LDGSTS was tried: ~40 cycles of issue per warp instruction, 7.8 k cycles for the five
-// networks of the critic step).  Element i of the network's list -> (source, destination offset); at most two per thread.
-__device__ __forceinline__ bool small_slot(const Cl& c, const float* __restrict__ P, const NetShape& s, int i, const float*& src, int& dst) {
-  const int H = c.H;
-  const int n0 = (H * s.in) >> 2, n1 = H >> 2, q = c.ncols >> 2, n2 = (s.layers - 1) * q, n3 = (s.out * H) >> 2;
-  if (i < n0) { src = P + net_w_off(s, 0) + 4 * i; dst = 4 * i; return true; }
-  i -= n0;
-  if (i < n1) { src = P + net_b_off(s, 0) + 4 * i; dst = 4 * H + 4 * i; return true; }
-  i -= n1;
-  if (i < n2) {
-    const int l = 1 + i / q, j = i - (l - 1) * q;
-    src = P + net_b_off(s, l) + c.c_lo + 4 * j; dst = 5 * H + (l - 1) * c.Wc + 4 * j;
-    return true;
-  }
-  i -= n2;
-  const int head = 5 * H + (s.layers - 1) * c.Wc;
-  if (i < n3) { src = P + net_w_off(s, s.layers) + 4 * i; dst = head + 4 * i; return true; }
-  i -= n3;
-  if (i == 0) { src = P + net_b_off(s, s.layers); dst = head + 2 * H; return true; }     // (reads into the slot's padding)
-  return false;
+// small parameters: per network three kinds of bulk copies, issued by the lanes of the producer warp at kernel start onto mbarrier 8 -
+// W0 and b0 (adjacent in the arena), every further bias vector, the head with its bias.  (Loads by the compute threads, LDGSTS or
+// LDG + STS, kept the prologue at 8-9 k cycles: ten loads per thread behind an index decode.)
+__device__ __forceinline__ uint32_t small_bytes(const Cl& c, const NetShape& s) {
+  return (uint32_t)((c.H * s.in + c.H + (s.layers - 1) * c.H + s.out * c.H + 4) * 4);
 }
-template <int NETS>
-__device__ __forceinline__ void small_load_all(const Cl& c, const float* const (&P)[NETS], const NetShape (&s)[NETS]) {
-  float4 v[NETS][2];
-  int d[NETS][2];
-#pragma unroll
-  for (int n = 0; n < NETS; ++n)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float* src = nullptr;
-      d[n][k] = -1;
-      int dst = 0;
-      if (small_slot(c, P[n], s[n], threadIdx.x + k * kCT, src, dst)) {
-        v[n][k] = __ldg(reinterpret_cast<const float4*>(src));
-        d[n][k] = c.small + n * c.small_stride + dst;
-      }
-    }
-#pragma unroll
-  for (int n = 0; n < NETS; ++n) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (d[n][k] >= 0) *reinterpret_cast<float4*>(smem_f + d[n][k]) = v[n][k];
-    if (s[n].out < 2) {                                       // read (times a zero gradient) by the backward pass: must be finite
-      float* head = smem_f + c.small + n * c.small_stride + 5 * c.H + (s[n].layers - 1) * c.Wc;
-      for (int i = threadIdx.x; i < c.H; i += kCT) head[c.H + i] = 0.f;
-    }
-  }
+__device__ __forceinline__ void small_issue(const Cl& c, int slot, const float* __restrict__ P, const NetShape& s, int item) {
+  float* sp = smem_f + c.small + slot * c.small_stride;
+  uint64_t* bar = cl_bar(c, 8);
+  if (item == 0) bulk_g2s(sp, P, (uint32_t)((c.H * s.in + c.H) * 4), bar);
+  else if (item < s.layers) bulk_g2s(sp + (4 + item) * c.H, P + net_b_off(s, item), (uint32_t)(c.H * 4), bar);
+  else if (item == s.layers) bulk_g2s(sp + (4 + s.layers) * c.H, P + net_w_off(s, s.layers), (uint32_t)((s.out * c.H + 4) * 4), bar);
 }
 __device__ __forceinline__ int sp_w0(const Cl& c, int slot) { return c.small + slot * c.small_stride; }
-__device__ __forceinline__ int sp_b0(const Cl& c, int slot) { return c.small + slot * c.small_stride + 4 * c.H; }
-__device__ __forceinline__ int sp_bias(const Cl& c, int slot, int l) { return c.small + slot * c.small_stride + 5 * c.H + (l - 1) * c.Wc; }   // l >= 1
-__device__ __forceinline__ int sp_head(const Cl& c, int slot) { return c.small + slot * c.small_stride + 5 * c.H + (c.L - 1) * c.Wc; }
+__device__ __forceinline__ int sp_b0(const Cl& c, int slot, int in_dim) { return c.small + slot * c.small_stride + in_dim * c.H; }
+// own slice of b_l, l >= 1
+__device__ __forceinline__ int sp_bias(const Cl& c, int slot, int l) { return c.small + slot * c.small_stride + (4 + l) * c.H + c.c_lo; }
+// head [out][H], its bias right behind it
+__device__ __forceinline__ int sp_head(const Cl& c, int slot) { return c.small + slot * c.small_stride + (4 + c.L) * c.H; }
 
 // the dz tile the next pushed output goes to (they alternate: consecutive stages never write the same tile)
 __device__ __forceinline__ int next_dz(Cl& c) {
@@ -281,11 +249,11 @@ __device__ __forceinline__ void stage_wait(Cl& c, uint32_t bytes) {
   mbar_wait_cluster(bar, (uint32_t)((c.stg >> 1) & 1));
   c.stg += 1;
 }
-// [R][2] partial sums of every CTA -> all CTAs (slot [rank]), summed in rank order into dst[r * dstride + {0,1}] (+ bias)
+// [R][2] partial sums of every CTA -> all CTAs (slot [rank]), summed in rank order into dst[r * dstride + {0,1}] (+ bias).
+// exchange_finish: the pushes of this CTA (push2 into buf + (rank * R + r) * 2) have been issued by whichever threads held the sums.
 template <int R, int CS>
-__device__ __forceinline__ void exchange_pairs(Cl& c, int buf, float a, float b, int dst, int dstride, float bias0, float bias1) {
+__device__ __forceinline__ void exchange_finish(Cl& c, int buf, int dst, int dstride, float bias0, float bias1) {
   const int t = threadIdx.x;
-  if (t < R) push2<CS>(c, buf + (c.rank * R + t) * 2, a, b);
   stage_wait(c, (uint32_t)(CS * R * 8));
   if (t < R) {
     float x = 0.f, y = 0.f;
@@ -296,11 +264,16 @@ __device__ __forceinline__ void exchange_pairs(Cl& c, int buf, float a, float b,
   }
   cta_sync();
 }
+template <int R, int CS>
+__device__ __forceinline__ void exchange_pairs(Cl& c, int buf, float a, float b, int dst, int dstride, float bias0, float bias1) {
+  if (threadIdx.x < R) push2<CS>(c, buf + (c.rank * R + threadIdx.x) * 2, a, b);
+  exchange_finish<R, CS>(c, buf, dst, dstride, bias0, bias1);
+}
 
 // ---- first layer, ALL columns, every CTA: h[r][c] = relu(b[c] + sum_j in0[r][j] * W0[c][j]) -------------------------------------------
 template <int R>
 __device__ __forceinline__ void cl_first(Cl& c, int slot, int in_dim, int Y, float* __restrict__ gh /*nullable [B][H]*/, int r0, int B) {
-  const int w0 = sp_w0(c, slot), bb = sp_b0(c, slot);
+  const int w0 = sp_w0(c, slot), bb = sp_b0(c, slot, in_dim);
   for (int col = threadIdx.x; col < c.H; col += kCT) {
     float w[4] = {0.f, 0.f, 0.f, 0.f};
     if (in_dim == 4) {
@@ -392,6 +365,8 @@ __device__ __forceinline__ void cl_fwd_hidden(Cl& c, int ti, int T, int slot, in
   tile_release(c, ti);
   stamp(c, 21);
   const int q = c.ncols >> 2, bb = sp_bias(c, slot, l), hd = sp_head(c, slot);
+  // 16 column groups and all rows in one sweep: the 16 threads of a row are half a warp and add their head contributions by shuffles
+  const bool fast = last && q == 16 && R * 16 <= kCT;
   for (int idx = threadIdx.x; idx < R * q; idx += kCT) {
     const int r = idx / q, cg = idx - r * q, cc = cg * 4;
     const float4 p = cl_reduce4<R>(c, r, cc);
@@ -409,7 +384,16 @@ __device__ __forceinline__ void cl_fwd_hidden(Cl& c, int ti, int T, int slot, in
         h1 = o.x * wb.x;
         h1 = fmaf(o.y, wb.y, h1); h1 = fmaf(o.z, wb.z, h1); h1 = fmaf(o.w, wb.w, h1);
       }
-      *reinterpret_cast<float2*>(smem_f + c.hpart + idx * 2) = make_float2(h0, h1);
+      if (fast) {                                            // (whole warps run this branch: idx < R * 16 is a multiple of 32)
+#pragma unroll
+        for (int sft = 8; sft > 0; sft >>= 1) {
+          h0 += __shfl_xor_sync(0xffffffffu, h0, sft);
+          h1 += __shfl_xor_sync(0xffffffffu, h1, sft);
+        }
+        if (cg == 0) push2<CS>(c, c.hp + (c.rank * R + r) * 2, h0, h1);
+      } else {
+        *reinterpret_cast<float2*>(smem_f + c.hpart + idx * 2) = make_float2(h0, h1);
+      }
     }
     if (gh && r0 + r < B) *reinterpret_cast<float4*>(gh + (int64_t)(r0 + r) * c.H + c.c_lo + cc) = o;
   }
@@ -418,15 +402,19 @@ __device__ __forceinline__ void cl_fwd_hidden(Cl& c, int ti, int T, int slot, in
     stage_wait(c, (uint32_t)(R * c.H * 4));
     stamp(c, 23);
   } else {
-    cta_sync();
-    float a = 0.f, b2 = 0.f;
-    if (threadIdx.x < R) {
-      for (int g = 0; g < q; ++g) {
-        const float2 v = *reinterpret_cast<const float2*>(smem_f + c.hpart + (threadIdx.x * q + g) * 2);
-        a += v.x; b2 += v.y;
+    const float bias0 = smem_f[hd + out_dim * c.H], bias1 = out_dim > 1 ? smem_f[hd + out_dim * c.H + 1] : 0.f;
+    if (!fast) {
+      cta_sync();
+      float a = 0.f, b2 = 0.f;
+      if (threadIdx.x < R) {
+        for (int g = 0; g < q; ++g) {
+          const float2 v = *reinterpret_cast<const float2*>(smem_f + c.hpart + (threadIdx.x * q + g) * 2);
+          a += v.x; b2 += v.y;
+        }
+        push2<CS>(c, c.hp + (c.rank * R + threadIdx.x) * 2, a, b2);
       }
     }
-    exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + 2 * c.H], out_dim > 1 ? smem_f[hd + 2 * c.H + 1] : 0.f);
+    exchange_finish<R, CS>(c, c.hp, c.out, 2, bias0, bias1);
     stamp(c, 30);
   }
 }
@@ -452,7 +440,7 @@ __device__ __forceinline__ void cl_forward(Cl& c, int slot, const NetShape& s, b
     }
     cta_sync();
     const float a = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4] : 0.f, b2 = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4 + 1] : 0.f;
-    exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + 2 * c.H], s.out > 1 ? smem_f[hd + 2 * c.H + 1] : 0.f);
+    exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + s.out * c.H], s.out > 1 ? smem_f[hd + s.out * c.H + 1] : 0.f);
     return;
   }
   for (int l = 1; l < s.layers; ++l) {
@@ -486,7 +474,8 @@ __device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, 
     for (int idx = t; idx < R * q; idx += kCT) {
       const int r = idx / q, cc = (idx - r * q) * 4, k = c.c_lo + cc;
       const float d0 = smem_f[c.dout + r * 2], d1 = smem_f[c.dout + r * 2 + 1];
-      const float4 wa = lds4(hd + k), wb = lds4(hd + c.H + k), h = lds4(Hl + r * c.ld + k);
+      const float4 wa = lds4(hd + k), h = lds4(Hl + r * c.ld + k);
+      const float4 wb = s.out > 1 ? lds4(hd + c.H + k) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 o;
       o.x = h.x > 0.f ? fmaf(d0, wa.x, d1 * wb.x) : 0.f;
       o.y = h.y > 0.f ? fmaf(d0, wa.y, d1 * wb.y) : 0.f;
@@ -548,13 +537,14 @@ constexpr int kMaxTiles = 7 * (kMaxLayers - 1) + 4;      // critic step: 7 (L-1)
 // common start (all threads of the CTA): the mbarriers.  Ends with a CTA barrier.
 __device__ __forceinline__ void cl_begin(Cl& c) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(cl_bar(c, i), 1);
+    for (int i = 0; i < 9; ++i) mbar_init(cl_bar(c, i), 1);
     fence_mbar_init();
   }
   __syncthreads();
 }
 // compute threads: the small parameters have landed; every CTA of the cluster runs and has its mbarriers set up
 __device__ __forceinline__ void cl_started(Cl& c) {
+  mbar_wait(cl_bar(c, 8), 0);
   stamp(c, 1);
   cluster_sync();
   stamp(c, 2);
@@ -575,6 +565,7 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
   const int r0 = (int)cluster_id_x() * R;
   const int t = threadIdx.x;
 
+  const int j_row = (t < R && r0 + t < B) ? idx[r0 + t] : 0;      // replay row of this thread's batch row (its loads follow below)
   // weight tiles in the order of use: passes 0-2 forward, passes 3-4 forward then backward
   __shared__ const float* tiles[kMaxTiles];
   if (t < kMaxTiles) {
@@ -599,27 +590,37 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
   cl_begin(c);
   stamp(c, 3);
   if (t >= kCT) {                        // producer warp: weight tiles, in the order of use
+    cluster_arrive();                                      // its share of the start barrier first: nobody waits for its copies to be issued
+    {                                                      // small parameters of the five passes: lane = (pass, item)
+      const int lane = t - kCT, per = L + 1;
+      if (lane == 0) {
+        uint32_t bytes = small_bytes(c, ar.actor) + 4u * small_bytes(c, ar.critic);
+        mbar_arrive_expect_tx(cl_bar(c, 8), bytes);
+      }
+      __syncwarp();
+      for (int w = lane; w < 5 * per; w += 32) {
+        const int pass = w / per, net = pass < 3 ? pass + 3 : pass - 2;
+        small_issue(c, pass, params + ar.off(net), pass == 0 ? ar.actor : ar.critic, w - pass * per);
+      }
+    }
     cl_producer(c, tiles, 0, min(c.ns, 7 * (L - 1)));      // the first tiles need no free slot; then join the start barrier
     if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 1);   // (read by the optimiser kernel that follows)
-    cluster_sync();
+    cluster_wait();
     cl_producer(c, tiles, c.ns, 7 * (L - 1));
     cluster_sync();
     return;
-  }
-  {
-    const float* const Ps[5] = {params + ar.off(3), params + ar.off(4), params + ar.off(5), params + ar.off(1), params + ar.off(2)};
-    const NetShape ss[5] = {ar.actor, ar.critic, ar.critic, ar.critic, ar.critic};
-    small_load_all<5>(c, Ps, ss);
   }
   stamp(c, 4);
   float* S = smem_f + c.S;       // [R][8]: 0 s.x 1 s.y 2 a.x 3 a.y 4 reward 5 notdone 6 y 7 valid
   float* in0 = smem_f + c.in0;
   float* out = smem_f + c.out;
   float* dout = smem_f + c.dout;
+  float2 zn = make_float2(0.f, 0.f);     // this row's smoothing noise (Philox + log + sincos: off the chain between the passes)
   if (t < R) {
+    zn = target_noise(noise, hp, min(r0 + t, B - 1));
     const int row = r0 + t;
     const bool valid = row < B;
-    const int j = valid ? idx[row] : 0;
+    const int j = j_row;
     const float2 s = rp.s[j], a = rp.a[j], s2 = rp.s2[j];
     S[t * 8 + 0] = s.x; S[t * 8 + 1] = s.y; S[t * 8 + 2] = a.x; S[t * 8 + 3] = a.y;
     S[t * 8 + 4] = rp.r[j]; S[t * 8 + 5] = rp.notdone[j]; S[t * 8 + 7] = valid ? 1.f : 0.f;
@@ -637,8 +638,6 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
     cl_forward<R, CS>(c, pass, shape, train, 0, train ? &rs : nullptr, r0, ti);
     if (t < R) {
       if (pass == 0) {                                   // smoothing noise and clips (robot.py:338-339)
-        const int row = min(r0 + t, B - 1);
-        const float2 zn = target_noise(noise, hp, row);
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           float e = (o == 0 ? zn.x : zn.y) * hp.policy_noise;
@@ -704,17 +703,22 @@ td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float
   }
   cl_begin(c);
   if (t >= kCT) {
+    cluster_arrive();
+    {
+      const int lane = t - kCT, per = L + 1;
+      if (lane == 0) mbar_arrive_expect_tx(cl_bar(c, 8), small_bytes(c, ar.actor) + small_bytes(c, ar.critic));
+      __syncwarp();
+      for (int w = lane; w < 2 * per; w += 32) {
+        const int pass = w / per;
+        small_issue(c, pass, params + ar.off(pass), pass == 0 ? ar.actor : ar.critic, w - pass * per);
+      }
+    }
     cl_producer(c, tiles, 0, min(c.ns, 4 * (L - 1)));
     if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 0);
-    cluster_sync();
+    cluster_wait();
     cl_producer(c, tiles, c.ns, 4 * (L - 1));
     cluster_sync();
     return;
-  }
-  {
-    const float* const Ps[2] = {params + ar.off(0), params + ar.off(1)};
-    const NetShape ss[2] = {ar.actor, ar.critic};
-    small_load_all<2>(c, Ps, ss);
   }
   float* S = smem_f + c.S;
   float* in0 = smem_f + c.in0;
