@@ -284,7 +284,9 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
         flops = td3_flops_per_epoch(B * world, H, L) * epochs
         row = {"shape": label, "global_batch": B * world, "epochs": epochs, "sampler": rb.sampler,
                "update_kernel": ("tcgen05 step kernels" if tf32 else ("persistent cooperative kernel (rtd3_td3_update_coop)" if agent._coop_ok(B)
-                                                                     else "per-step kernels (rtd3_td3_update)")),
+                                                                     else ("cluster step kernels (rtd3_td3_update: 4-CTA clusters, columns split, st.async hand-over)"
+                                                                           if rt._lib.lib().rtd3_td3_cluster_supported(agent._handle, B)
+                                                                           else "row-tile step kernels (rtd3_td3_update)"))),
                "dp_collective": getattr(agent, "dp_collective", None) if world > 1 else None,
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
                "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
