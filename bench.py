@@ -353,6 +353,53 @@ def bench_forward(rt, torch, dev):
     return rows
 
 
+def bench_single_env(rt, torch, dev):
+    """configs[0]: the reference's own run - robot-learning.py's update(dt) for ONE env, seeded, default demo budget - through the
+    drop-in classes (`trainer.DriverLoop`: Environment / Robot hooks one call per tick, host <-> device copies and a sync per hook).
+    Wall clock per tick by kind, beside the survey-time figures of the unmodified reference on CPU (not re-timed
+    here: the reference cannot travel to the GPU box)."""
+    import numpy as _np
+    from rtd3_b200.trainer import DriverLoop
+    speed, angle = rt.synthetic_maps(0)
+    torch.manual_seed(0)
+    t_build = time.perf_counter()
+    loop = DriverLoop.from_seed(1707366464, maps=(speed, angle))
+    build_s = time.perf_counter() - t_build
+    robot = loop.robot
+    upd = {"n": 0, "s": 0.0, "each": []}
+    real_update = robot.td3_agent.td3_update
+
+    def timed_update(*a, **kw):
+        t0 = time.perf_counter()
+        out = real_update(*a, **kw)
+        torch.cuda.synchronize(dev)
+        upd["n"] += 1
+        upd["s"] += time.perf_counter() - t0
+        upd["each"].append(time.perf_counter() - t0)
+        return out
+    robot.td3_agent.td3_update = timed_update
+    per_kind = {}
+    t_run = time.perf_counter()
+    ticks = 0
+    while not loop.finished and ticks < 5000:
+        u0 = upd["s"]
+        t0 = time.perf_counter()
+        kind = loop.update()
+        dt = time.perf_counter() - t0 - (upd["s"] - u0)              # the learner update of an episode end is reported separately
+        per_kind.setdefault(kind or "none", []).append(dt)
+        ticks += 1
+    total_s = time.perf_counter() - t_run
+    row = {"config": "configs[0]: reference robot-learning.py loop, single env, seed 1707366464, default demo budget, synthetic maps",
+           "ticks": ticks, "total_s": round(total_s, 3), "build_s": round(build_s, 3), "success": bool(loop.success), "td3_updates": upd["n"],
+           "ms_per_td3_update_100_epochs": {"median": round(1e3 * float(_np.median(upd["each"])), 3) if upd["each"] else None,
+                                            "first_call_with_graph_capture": round(1e3 * upd["each"][0], 3) if upd["each"] else None},
+           "ms_per_tick_by_kind": {k: {"n": len(v), "median_ms": round(1e3 * float(_np.median(v)), 4), "mean_ms": round(1e3 * float(_np.mean(v)), 4)}
+                                   for k, v in per_kind.items()},
+           "reference_cpu_survey": {"training_tick_ms": 4.4, "td3_update_100_epochs_ms": "720-1270", "get_demonstration_s": 3.5,
+                                    "source": "BASELINE.md section 2 (unmodified reference, survey container, 8 vCPU); not re-timed on this box"}}
+    return row
+
+
 def bench_full_loop(rt, torch, dev, world, rank):
     """configs[3]: the act -> step -> transition -> (episodes ended: TD3 update) loop, gradients all-reduced across ranks.
     8192 envs per GPU (65536 over 8 GPUs) and, for the per-GPU ceiling, 65536 envs per GPU.  Every row states its mode:
@@ -600,6 +647,7 @@ def run_b200(args):
     td3_rows = None if args.no_td3 else bench_td3(rt, torch, dev, world, rank, cpu=not args.no_cpu)
     fwd_rows = None if (args.no_td3 or rank != 0 or world > 1) else bench_forward(rt, torch, dev)
     loop_row = None if args.no_loop else bench_full_loop(rt, torch, dev, world, rank)
+    single_row = bench_single_env(rt, torch, dev) if (world == 1 and not args.no_loop) else None
     sampler.in_region = False
     sampler.stop()
 
@@ -638,6 +686,8 @@ def run_b200(args):
             line["actor_forward"] = fwd_rows
         if loop_row is not None:
             line["full_loop"] = loop_row
+        if single_row is not None:
+            line["single_env_loop"] = single_row
         if world > 1:
             flags = [r.get("replicas_identical") for r in (td3_rows or []) + (loop_row or []) if "replicas_identical" in r]
             line["replicas_identical"] = bool(flags) and all(flags)
