@@ -330,7 +330,10 @@ int32_t rtd3_trainer_tally(const int8_t* type, int64_t* steps, int64_t* resets, 
 int32_t rtd3_p2p_allreduce(float* const* peer_recv, uint64_t* const* peer_flags, int32_t rank, int32_t world, uint64_t* seq_counter,
                            float* out, float* local_grads, int64_t count, int64_t slot_floats, uint32_t* block_counter, void* stream);
 
-/* The same arguments as a HOST struct (what rtd3_td3_update takes). `sum`: private buffer the optimiser reads (same indexing as grads). */
+/* The same arguments as a HOST struct (what rtd3_td3_update takes). `sum`: private buffer the optimiser reads (same indexing as grads).
+ * rtd3_td3_update fuses the optimiser into its all-reduce launches and hands the data over per thread block: for that form every
+ * flag array must hold 16 + RTD3_P2P_MAX_WORLD * 256 uint64 (zero-initialised once): [0, 16) as above, then one flag per
+ * (rank, block). */
 typedef struct rtd3_p2p_state {
   float* const* peer_recv;
   uint64_t* const* peer_flags;

@@ -119,25 +119,60 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int 
     reinterpret_cast<float4*>(out)[i] = p2p_sum_slots<kWorld>(mine, stride4, i);
 }
 
-// The same all-reduce with the optimiser applied to the sums: phase (3) walks the online arena like td3_adam_polyak_kernel - Adam on the
-// elements of the reduced slice (gradient = sum of the W slots x grad_scale), the Polyak blend where asked for - so the summed
-// gradients never go back to memory and the separate optimiser launch (one more pass over the arena, ~10 us) disappears.
+// The same all-reduce with the optimiser applied to the sums, and with the hand-over made BLOCK-LOCAL: block b of every rank owns the
+// same arena elements in the push and in the reduction, so it raises its own flag (flag area [16 + rank * 256 + block]) right after
+// its own pushes and waits only for block b of its peers - no block counter and no last-block hop on the way to the flags, and a
+// slow block delays only its own elements.  Phase (3) walks the online arena like td3_adam_polyak_kernel - Adam on the elements of
+// the reduced slice (gradient = sum of the W slots x grad_scale), the Polyak blend where asked for - so the summed gradients never
+// go back to memory and the separate optimiser launch (one more pass over the arena) disappears.
+constexpr int kP2pBlockFlags = 256;          // per rank; the grid never has more blocks (one per SM)
+constexpr int kP2pBlockFlagBase = 16;
+
 template <int kWorld>
 __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter,
                                                                  float* __restrict__ local_grads, int64_t count4, int64_t stride4,
                                                                  unsigned int* block_counter, P2pAdamArgs o) {
   __shared__ float s_step[2], s_bc2[2];
-  if (threadIdx.x < 2) {                                              // 0: actor optimiser, 1: both critic optimisers
-    const double bc1 = 1.0 - o.beta_pows[2 * threadIdx.x], bc2 = 1.0 - o.beta_pows[2 * threadIdx.x + 1];
-    const double lr = threadIdx.x == 0 ? (double)o.lr_actor : (double)o.lr_critic;
-    s_step[threadIdx.x] = (float)(lr / bc1);
-    s_bc2[threadIdx.x] = (float)sqrt(bc2);
+  __shared__ unsigned long long s_seq;
+  const int tid = threadIdx.x;
+  if (tid < 2) {                                                      // 0: actor optimiser, 1: both critic optimisers
+    const double bc1 = 1.0 - o.beta_pows[2 * tid], bc2 = 1.0 - o.beta_pows[2 * tid + 1];
+    const double lr = tid == 0 ? (double)o.lr_actor : (double)o.lr_critic;
+    s_step[tid] = (float)(lr / bc1);
+    s_bc2[tid] = (float)sqrt(bc2);
   }
-  const unsigned long long seq = p2p_push_and_wait<kWorld>(peers, rank, seq_counter, local_grads + o.off, count4, stride4, block_counter);
+  if (tid == 0) s_seq = *reinterpret_cast<volatile unsigned long long*>(seq_counter) + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int n4 = (int)(o.ar.online_total() >> 2), off4 = (int)(o.off >> 2), end4 = off4 + (int)count4;
+  const int gstride = gridDim.x * blockDim.x;
+  const int64_t slot = ((int64_t)(seq & 1ull) * kWorld + rank) * stride4;
+  // (1) push this block's elements of the slice into slot [step parity][rank] of every rank, clear them locally
+  for (int i4 = blockIdx.x * blockDim.x + tid; i4 < n4; i4 += gstride) {
+    if (i4 < off4 || i4 >= end4) continue;
+    const float4 v = reinterpret_cast<const float4*>(local_grads)[i4];
+#pragma unroll
+    for (int q = 0; q < kWorld; ++q) reinterpret_cast<float4*>(peers.recv[q])[slot + (i4 - off4)] = v;
+    reinterpret_cast<float4*>(local_grads)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // (2) this block's flag at every rank (the fence of each storing thread covers the block's pushes: they precede the barrier)
+  __syncthreads();
+  if (tid < kWorld) {
+    __threadfence_system();
+    st_release_sys(peers.flags[tid] + kP2pBlockFlagBase + rank * kP2pBlockFlags + blockIdx.x, seq);
+  }
+  if (tid == 32) {                                                    // bookkeeping off the critical path: the step number
+    if (atomicAdd(block_counter, 1u) == gridDim.x - 1) {              // every block of this launch has read it
+      *block_counter = 0u;
+      *seq_counter = seq;
+    }
+  }
+  // (3) block b of every rank has pushed: reduce in rank order, apply the optimiser
+  if (tid < kWorld) wait_flag(peers.flags[rank] + kP2pBlockFlagBase + tid * kP2pBlockFlags + blockIdx.x, seq);
+  __syncthreads();
   const float4* mine = reinterpret_cast<const float4*>(peers.recv[rank]) + (int64_t)(seq & 1ull) * kWorld * stride4;
-  const int n4 = (int)(o.ar.online_total() >> 2), off4 = (int)(o.off >> 2);
   const int off1 = (int)o.ar.off(1), off2 = (int)o.ar.off(2);
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+  for (int i4 = blockIdx.x * blockDim.x + tid; i4 < n4; i4 += gstride) {
     const int i = i4 * 4;
     const int net = i < off1 ? 0 : (i < off2 ? 1 : 2);               // slots are multiples of 4 floats: a group never straddles two
     const bool do_adam = (o.nets >> net) & 1, do_polyak = (o.polyak >> net) & 1;
@@ -146,9 +181,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(P2pPeers peers,
     if (do_adam) g = p2p_sum_slots<kWorld>(mine, stride4, (int64_t)(i4 - off4));
     const float gg[4] = {g.x * o.grad_scale, g.y * o.grad_scale, g.z * o.grad_scale, g.w * o.grad_scale};
     const int k = net == 0 ? 0 : 1;
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      adam_polyak_apply(o.ar, i + e, net, gg[e], do_adam, do_polyak, o.params, o.params_t, o.params_uv, o.m, o.v, s_step[k], s_bc2[k], o.tau);
+    adam_polyak_apply4(o.ar, i, net, gg, do_adam, do_polyak, o.params, o.params_t, o.params_uv, o.m, o.v, s_step[k], s_bc2[k], o.tau);
   }
 }
 
@@ -210,11 +243,12 @@ int32_t rtd3::p2p_allreduce_adam_launch(const rtd3_p2p_state* ps, float* local_g
   int64_t count4 = count / 4, stride4 = ps->slot_floats / 4;
   int num_sms = 0;
   RTD3_CUDA(current_num_sms(&num_sms));
-  const int grid = (int)std::min<int64_t>((int64_t)num_sms, ceil_div(opt.ar.online_total() / 4, 256));
+  const int grid = (int)std::min<int64_t>(std::min<int64_t>((int64_t)num_sms, kP2pBlockFlags), ceil_div(opt.ar.online_total() / 4, 256));
   unsigned long long* sc = (unsigned long long*)ps->seq_counter;
   int rk = rank;
   unsigned int* bc = ps->block_counter;
   P2pAdamArgs o = opt;
+  // every element of a reduced slice must have an optimiser bit: the pushes and the reduction use the same element -> block map
   void* kargs[] = {&p, &rk, &sc, &local_grads, &count4, &stride4, &bc, &o};
   const void* fn = nullptr;
   switch (world) {

@@ -440,14 +440,19 @@ __global__ void td3_adam_polyak_kernel(Arena ar, float* __restrict__ params, flo
     s_bc2[threadIdx.x] = (float)sqrt(bc2);
   }
   __syncthreads();
-  const int n_online = (int)ar.online_total();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_online; i += gridDim.x * blockDim.x) {
+  const int n4 = (int)(ar.online_total() >> 2);                     // slots are multiples of 4 floats: a group of 4 never straddles two networks
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const int i = i4 * 4;
     const int net = i < (int)ar.off(1) ? 0 : (i < (int)ar.off(2) ? 1 : 2);
     const bool do_adam = (nets >> net) & 1, do_polyak = (polyak >> net) & 1;
     if (!do_adam && !do_polyak) continue;
-    float g = 0.f;
-    if (do_adam) { g = grads[i] * grad_scale; grads[i] = 0.f; }
-    adam_polyak_apply(ar, i, net, g, do_adam, do_polyak, params, params_t, params_uv, m, v, s_step[net == 0 ? 0 : 1], s_bc2[net == 0 ? 0 : 1], tau);
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (do_adam) {
+      const float4 g4 = *reinterpret_cast<const float4*>(grads + i);
+      g[0] = g4.x * grad_scale; g[1] = g4.y * grad_scale; g[2] = g4.z * grad_scale; g[3] = g4.w * grad_scale;
+      *reinterpret_cast<float4*>(grads + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    adam_polyak_apply4(ar, i, net, g, do_adam, do_polyak, params, params_t, params_uv, m, v, s_step[net == 0 ? 0 : 1], s_bc2[net == 0 ? 0 : 1], tau);
   }
 }
 
@@ -690,7 +695,7 @@ int32_t rtd3_td3_adam_polyak(rtd3_td3* h, float* params, float* params_t, float*
   RTD3_CHECK_ARG(h && params && params_t && grads && adam_m && adam_v && beta_pows, "null argument");
   const int64_t n = h->ar.online_total();
   const int block = 256;
-  const int grid = (int)std::min<int64_t>(ceil_div(n, block), (int64_t)h->num_sms * 8);
+  const int grid = (int)std::min<int64_t>(ceil_div(n / 4, block), (int64_t)h->num_sms * 8);
   td3_adam_polyak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(h->ar, params, params_t, params_uv, grads, adam_m, adam_v, beta_pows, nets, lr_actor,
                                                                     lr_critic, grad_scale, polyak, tau);
   RTD3_LAUNCHED();

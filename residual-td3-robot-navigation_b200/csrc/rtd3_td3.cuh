@@ -153,6 +153,56 @@ __device__ __forceinline__ void adam_polyak_apply(const Arena& ar, int i, int ne
   }
 }
 
+// The same for four consecutive arena elements i .. i+3 (i a multiple of 4: network slots, weight matrices and bias vectors all start
+// at multiples of 4, so the four are either four neighbours of one row of a hidden weight matrix or four elements that keep their
+// place in the derived copies).  One round of 16-byte loads instead of four dependent rounds of scalar ones; element arithmetic as
+// in adam_polyak_apply, bit for bit.
+__device__ __forceinline__ void adam_polyak_apply4(const Arena& ar, int i, int net, const float (&g)[4], bool do_adam, bool do_polyak,
+                                                   float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ params_uv,
+                                                   float* __restrict__ m, float* __restrict__ v, float step, float sqrt_bc2, float tau) {
+  const int n_online = (int)ar.online_total(), total = (int)ar.total();
+  const int noff = net == 0 ? 0 : (int)ar.off(net);
+  const CopyIndex ci = copy_index(net == 0 ? ar.actor : ar.critic, i - noff);      // of element i; hidden: .t stride H, .u contiguous, .v stride 4
+  const int H = (net == 0 ? ar.actor : ar.critic).hid;
+  const int st = ci.hidden ? H : 1, sv = ci.hidden ? 4 : 1;
+  float4 p4 = *reinterpret_cast<const float4*>(params + i);
+  float p[4] = {p4.x, p4.y, p4.z, p4.w};
+  float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (do_polyak) t4 = *reinterpret_cast<const float4*>(params + n_online + i);
+  if (do_adam) {
+    const float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) adam_element(g[e], mm[e], vv[e], p[e], step, sqrt_bc2);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(params + i) = make_float4(p[0], p[1], p[2], p[3]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) params_t[noff + ci.t + e * st] = p[e];
+    if (params_uv) {
+      float pr[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pr[e] = ci.hidden ? tf32_rn(p[e]) : p[e];
+      *reinterpret_cast<float4*>(params_uv + noff + ci.u) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) params_uv[total + noff + ci.v + e * sv] = pr[e];
+    }
+  }
+  if (do_polyak) {
+    const float to[4] = {t4.x, t4.y, t4.z, t4.w};
+    float tv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tv[e] = __fadd_rn(__fmul_rn(to[e], 1.0f - tau), __fmul_rn(p[e], tau));   // robot.py:309, three roundings
+    *reinterpret_cast<float4*>(params + n_online + i) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) params_t[n_online + noff + ci.t + e * st] = tv[e];
+    if (params_uv)
+      *reinterpret_cast<float4*>(params_uv + n_online + noff + ci.u) =
+          make_float4(ci.hidden ? tf32_rn(tv[0]) : tv[0], ci.hidden ? tf32_rn(tv[1]) : tv[1], ci.hidden ? tf32_rn(tv[2]) : tv[2],
+                      ci.hidden ? tf32_rn(tv[3]) : tv[3]);
+  }
+}
+
 // Adam bookkeeping advanced by the first thread of a step kernel: the step counter and the running powers
 // beta1^t, beta2^t (float64, as torch computes the bias corrections in Python floats).  o: 0 actor, 1 critics.
 __device__ __forceinline__ void advance_adam_clock(int32_t* steps, double* beta_pows, int o) {

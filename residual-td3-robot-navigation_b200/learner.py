@@ -426,7 +426,9 @@ class TD3:
         if world > 8:
             raise ValueError("the peer-memory all-reduce serves up to 8 ranks (one NVSwitch box)")
         G = self.grads.numel()
-        buf = torch.zeros((2 * world * G + 32,), dtype=torch.float32, device=self.device)   # receive slots [2][world][G] | flags
+        # receive slots [2][world][G] | flags: uint64 [16] per rank (rtd3_p2p_allreduce) + [8][256] per (rank, block) (the fused all-reduce
+        # + optimiser of rtd3_td3_update)
+        buf = torch.zeros((2 * world * G + 2 * (16 + 8 * 256),), dtype=torch.float32, device=self.device)
         torch.cuda.synchronize(self.device)
         handles = [None] * world
         dist.all_gather_object(handles, reduce_tensor(buf), group=pg)
