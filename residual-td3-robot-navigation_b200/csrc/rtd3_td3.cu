@@ -195,8 +195,19 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     s_step = (float)((double)fz.lr / (1.0 - bp1));
     s_bc2 = (float)sqrt(1.0 - bp2);
   };
-  // one gradient element: stored (or accumulated), or consumed by the fused optimiser.  o = offset inside the net's slot
-  auto emit = [&](int64_t net_off, int64_t o, float g, bool atomic_acc) {
+  // the optimiser's operands of one element, fetched BEFORE the batch reduction (the small jobs' five emits were five dependent
+  // chains of two L2 round trips each - the longest blocks of the launch)
+  struct OptPre { float m, v, p, t; };
+  auto pre_load = [&](int64_t net_off, int64_t o) {
+    OptPre q{0.f, 0.f, 0.f, 0.f};
+    if (fz.params) {
+      const int64_t i = net_off + o;
+      q.m = fz.m[i]; q.v = fz.v[i]; q.p = fz.params[i];
+      if (fz.polyak) q.t = fz.params[fz.n_online + i];
+    }
+    return q;
+  };
+  auto emit_pre = [&](int64_t net_off, int64_t o, float g, bool atomic_acc, const OptPre& q) {
     if (!fz.params) {
       float* dst = grads + net_off + o;
       if (atomic_acc) atomicAdd(dst, g); else *dst = g;
@@ -204,7 +215,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     const int64_t i = net_off + o;
     const CopyIndex ci = copy_index(fz.shape, (int)o);
-    float mi = fz.m[i], vi = fz.v[i], p = fz.params[i];
+    float mi = q.m, vi = q.v, p = q.p;
     adam_element(g, mi, vi, p, s_step, s_bc2);
     fz.m[i] = mi;
     fz.v[i] = vi;
@@ -217,7 +228,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     if (fz.polyak) {
       const int64_t ti = fz.n_online + i;
-      const float tv = __fadd_rn(__fmul_rn(fz.params[ti], 1.0f - fz.tau), __fmul_rn(p, fz.tau));   // robot.py:309, three roundings
+      const float tv = __fadd_rn(__fmul_rn(q.t, 1.0f - fz.tau), __fmul_rn(p, fz.tau));   // robot.py:309, three roundings
       fz.params[ti] = tv;
       fz.params_t[fz.n_online + net_off + ci.t] = tv;
       if (fz.params_uv) fz.params_uv[fz.n_online + net_off + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
@@ -307,7 +318,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
         if (!atomic) *reinterpret_cast<float4*>(grads + G0 + off) = v;
         else { atomicAdd(grads + G0 + off, v.x); atomicAdd(grads + G0 + off + 1, v.y); atomicAdd(grads + G0 + off + 2, v.z); atomicAdd(grads + G0 + off + 3, v.w); }
       } else {
-        // torch.optim.Adam on 4 consecutive elements of a hidden weight W_l[gn][gk..gk+3] (the arithmetic of emit(), element by element)
+        // torch.optim.Adam on 4 consecutive elements of a hidden weight W_l[gn][gk..gk+3] (the arithmetic of emit_pre(), element by element)
         bias_corrections();
         const float g4[4] = {v.x, v.y, v.z, v.w};
         const float mo[4] = {m4.x, m4.y, m4.z, m4.w}, vo[4] = {v4.x, v4.y, v4.z, v4.w}, po[4] = {p4.x, p4.y, p4.z, p4.w};
@@ -349,6 +360,13 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     const float* dz = rs.dz(l);
     const float* in0 = rs.in0();
     float ab = 0.f, aw[4] = {0.f, 0.f, 0.f, 0.f};
+    OptPre pre[5];
+    if (warp == 0 && n < H) {
+      pre[0] = pre_load(G0, net_b_off(s, l) + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (l == 0 && j < s.in) pre[1 + j] = pre_load(G0, net_w_off(s, 0) + n * s.in + j);
+    }
     if (n < H) {
 #pragma unroll 8
       for (int b = b_lo + warp; b < b_hi; b += 8) {
@@ -368,9 +386,11 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
       float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 5; ++q) v[q] += red_small[w][lane * 5 + q];
-      emit(G0, net_b_off(s, l) + n, v[0], atomic);
+      emit_pre(G0, net_b_off(s, l) + n, v[0], atomic, pre[0]);
       if (l == 0) {
-        for (int j = 0; j < s.in; ++j) emit(G0, net_w_off(s, 0) + n * s.in + j, v[1 + j], atomic);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < s.in) emit_pre(G0, net_w_off(s, 0) + n * s.in + j, v[1 + j], atomic, pre[1 + j]);
       }
     }
   } else {
@@ -378,6 +398,13 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     const float* hl = rs.h(L - 1);
     const float* dout = rs.dout();
     float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+    OptPre pre[3];
+    if (warp == 0) {
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+        if (k < H && o < s.out) pre[o] = pre_load(G0, net_w_off(s, L) + (int64_t)o * H + k);
+      if (chunk == 0 && lane < s.out) pre[2] = pre_load(G0, net_b_off(s, L) + lane);
+    }
 #pragma unroll 8
     for (int b = b_lo + warp; b < b_hi; b += 8) {
       const float2 d = __ldg(reinterpret_cast<const float2*>(dout + (int64_t)b * 2));
@@ -394,9 +421,11 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 4; ++q) v[q] += red_small[w][lane * 4 + q];
       if (k < H) {
-        for (int o = 0; o < s.out; ++o) emit(G0, net_w_off(s, L) + (int64_t)o * H + k, v[o], atomic);
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+          if (o < s.out) emit_pre(G0, net_w_off(s, L) + (int64_t)o * H + k, v[o], atomic, pre[o]);
       }
-      if (chunk == 0 && lane < s.out) emit(G0, net_b_off(s, L) + lane, v[2 + lane], atomic);
+      if (chunk == 0 && lane < s.out) emit_pre(G0, net_b_off(s, L) + lane, v[2 + lane], atomic, pre[2]);
     }
   }
 }
