@@ -430,6 +430,9 @@ int32_t rtd3_debug_coop_prof(long long* device_buf);
  * device can hold at once (cudaOccupancyMaxActiveClusters of the critic kernel; negative: CUDA error). */
 int32_t rtd3_td3_cluster_supported(const rtd3_td3* h, int32_t batch);
 int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch);
+/* Development / test aid: 0 = the step entry points use the row-tile kernels, 2 = the cluster kernels wherever their plan fits (the
+ * default); returns the previous mode (1 = a shape forced through RTD3_CLUSTER=R,CS).  Not thread-safe against running launches. */
+int32_t rtd3_debug_cluster_mode(int32_t mode);
 /* Development aid: DEVICE buffers of 256 int64 each that the following cluster critic / actor kernels fill with clock64 stamps of
  * CTA 0 at every stage boundary ([0] = number of stamps); NULL switches it off. */
 int32_t rtd3_debug_cluster_prof(long long* critic_buf, long long* actor_buf);

@@ -881,6 +881,13 @@ int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch) {
   });
 }
 
+int32_t rtd3_debug_cluster_mode(int32_t mode) {
+  read_mode();
+  const int prev = g_mode;
+  if (mode == 0 || mode == 2) g_mode = mode;
+  return prev;
+}
+
 int32_t rtd3_debug_cluster_prof(long long* critic_buf, long long* actor_buf) {
   g_prof[0] = critic_buf;
   g_prof[1] = actor_buf;

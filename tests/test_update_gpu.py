@@ -236,3 +236,38 @@ def test_cooperative_update_kernel_vs_step_kernels_and_oracle(pkg, H, L, B, E):
     c1b, _ = a_coop.td3_update(rb, idx=idx, noise=noise)
     c2b, _ = a_steps.td3_update(rb, idx=idx, noise=noise)
     torch.testing.assert_close(c1b, c2b, rtol=5e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("H,L,B", [(256, 2, 256), (200, 3, 100), (256, 2, 37), (64, 2, 513), (128, 1, 64)])
+def test_cluster_step_kernels_vs_row_tile_kernels(pkg, H, L, B):
+    """The cluster step kernels (csrc/rtd3_cluster.cu: 4 CTAs share 8 batch rows and split every layer's columns) against the row-tile
+    kernels on the same minibatch: gradients of all three networks, losses, Q-values and targets.  The two differ in summation order
+    only - a different split of every reduction - so the bar is float32 round-off of chained 256-term sums over O(100) inputs (1e-4;
+    measured <= 8e-5 on the three-layer shape), not the 1e-3 of the parity bar.
+    Ragged batches (37, 513 rows: a last cluster with 5 / 1 valid rows), 13 column groups per CTA (H = 200) and a single hidden layer
+    (the head straight from the first layer) are the cluster plan's edge cases."""
+    L_ = pkg._lib.lib()
+    rb = synthetic_replay(pkg)
+    idx = torch.randint(0, len(rb), (B,), device="cuda", dtype=torch.int32)
+    noise = torch.randn((B, 2), device="cuda")
+    out = {}
+    prev = L_.rtd3_debug_cluster_mode(2)
+    try:
+        for mode in (2, 0):
+            L_.rtd3_debug_cluster_mode(mode)
+            ag = make_agent(pkg, H, L, B, 1, seed=5)
+            assert L_.rtd3_td3_cluster_supported(ag._handle, B) == (1 if mode == 2 else 0)
+            ag.sync_transposed()
+            loss2 = torch.zeros(2, device="cuda"); loss1 = torch.zeros(1, device="cuda")
+            q = torch.zeros((2, B), device="cuda"); y = torch.zeros(B, device="cuda")
+            ag._critic_step(rb, idx, noise, loss2, q, y, apply=False)          # critic gradients stay in ag.grads
+            ag._actor_step(rb, idx, loss1)                                     # + the actor's (no optimiser step in between)
+            out[mode] = (ag.grads.clone(), torch.cat([loss2, loss1]), q.clone(), y.clone())
+    finally:
+        L_.rtd3_debug_cluster_mode(prev)
+    (g1, l1, q1, y1), (g0, l0, q0, y0) = out[2], out[0]
+    torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(q1, q0, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(l1, l0, rtol=1e-4, atol=0)
+    scale = float(g0.abs().max())
+    assert float((g1 - g0).abs().max()) <= 1e-4 * scale
