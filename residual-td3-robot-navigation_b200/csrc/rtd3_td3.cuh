@@ -119,44 +119,12 @@ __device__ __forceinline__ CopyIndex copy_index(const NetShape& s, int o) {
 }
 
 
-// One arena element of the optimiser pass: Adam (when do_adam, with the already scaled gradient g) on parameter i of online network
-// `net`, then (when do_polyak) the blend of the matching target parameter: t = t*(1-tau) + p*tau; the transposed copy and the
-// tensor-core operand copies (params_uv, nullable) are kept in step.  Shared by td3_adam_polyak_kernel and the peer-memory
-// all-reduce that applies the optimiser to the sums it forms (rtd3_p2p.cu).
-__device__ __forceinline__ void adam_polyak_apply(const Arena& ar, int i, int net, float g, bool do_adam, bool do_polyak, float* __restrict__ params,
-                                                  float* __restrict__ params_t, float* __restrict__ params_uv, float* __restrict__ m,
-                                                  float* __restrict__ v, float step, float sqrt_bc2, float tau) {
-  const int n_online = (int)ar.online_total(), total = (int)ar.total();
-  const int noff = net == 0 ? 0 : (int)ar.off(net);
-  const CopyIndex ci = copy_index(net == 0 ? ar.actor : ar.critic, i - noff);
-  float p = params[i];
-  if (do_adam) {
-    float mi = m[i], vi = v[i];
-    adam_element(g, mi, vi, p, step, sqrt_bc2);
-    m[i] = mi;
-    v[i] = vi;
-    params[i] = p;
-    params_t[noff + ci.t] = p;
-    if (params_uv) {                                                  // tensor-core operand copies
-      const float pr = ci.hidden ? tf32_rn(p) : p;
-      params_uv[noff + ci.u] = pr;
-      params_uv[total + noff + ci.v] = pr;
-    }
-  }
-  if (do_polyak) {
-    const int ti = n_online + i;                                    // target slots mirror the online layout
-    // torch evaluates target*(1-tau) + source*tau as three separately rounded float32 ops (robot.py:309): no fma here
-    const float tv = __fadd_rn(__fmul_rn(params[ti], 1.0f - tau), __fmul_rn(p, tau));
-    params[ti] = tv;
-    params_t[n_online + noff + ci.t] = tv;
-    if (params_uv) params_uv[n_online + noff + ci.u] = ci.hidden ? tf32_rn(tv) : tv;
-  }
-}
-
-// The same for four consecutive arena elements i .. i+3 (i a multiple of 4: network slots, weight matrices and bias vectors all start
-// at multiples of 4, so the four are either four neighbours of one row of a hidden weight matrix or four elements that keep their
-// place in the derived copies).  One round of 16-byte loads instead of four dependent rounds of scalar ones; element arithmetic as
-// in adam_polyak_apply, bit for bit.
+// Four consecutive arena elements i .. i+3 of the optimiser pass (i a multiple of 4: network slots, weight matrices and bias vectors all
+// start at multiples of 4, so the four are either four neighbours of one row of a hidden weight matrix or four elements that keep
+// their place in the derived copies): Adam (when do_adam, with the already scaled gradients g) on the parameters of online network
+// `net`, then (when do_polyak) the blend of the matching target parameters, t = t*(1-tau) + p*tau; the transposed copy and the
+// tensor-core operand copies (params_uv, nullable) are kept in step.  One round of 16-byte loads per group.  Shared by
+// td3_adam_polyak_kernel and the peer-memory all-reduce that applies the optimiser to the sums it forms (rtd3_p2p.cu).
 __device__ __forceinline__ void adam_polyak_apply4(const Arena& ar, int i, int net, const float (&g)[4], bool do_adam, bool do_polyak,
                                                    float* __restrict__ params, float* __restrict__ params_t, float* __restrict__ params_uv,
                                                    float* __restrict__ m, float* __restrict__ v, float step, float sqrt_bc2, float tau) {
