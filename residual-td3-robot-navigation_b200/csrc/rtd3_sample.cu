@@ -206,6 +206,11 @@ sample_swaps_kernel(rtd3_mt_bank b, int64_t stream_id, int32_t n, int32_t count,
 //    redundantly - instead of compaction, a resolver warp and three more barriers (a per-thread serial walk over them was tried
 //    first: 2 000 of a round's 2 900 cycles);
 //  * smaller rounds only at the lowest mask levels, where the undecided band is wide.
+// Also tried, both bit-exact and both slower or equal: (a) ONE consumer warp with eight consecutive draws per lane, every prefix from
+// per-slot ballots, rounds cut at the mask level, no block barrier at all - 27 ms: ~600 dependent instructions per lane and round on a
+// single warp run at 4-6 cycles each, where eight warps with one draw per lane and one barrier need 1 650 cycles; (b) undecided draws
+// that decide themselves from their exact interval [i - S - M, i - S] plus a second barrier for the counts, the walk only for a
+// truly undecided draw - 8.9 ms against 8.75: the walk was not what a round waits for.
 // The state written back is the un-tempered ring block the stream ended in.
 constexpr int kRing = 6;
 constexpr int kRingWords = kRing * RTD3_MT_N;
