@@ -811,14 +811,18 @@ int32_t dispatch(const ClShape& s, F&& f) {
 }
 }  // namespace
 
+// The cluster kernels win while the batch is ONE wave of clusters (B = 256: 32 of the 33 clusters a B200 holds; 47.9 against 77.5 us
+// per epoch); from the second wave on the row-tile kernels are faster again (B = 512: 88.4 against 83.9, B = 1024: 171.8 against
+// 120.7 us per epoch), so larger batches keep them.
 bool rtd3::cluster_path_ok(const rtd3_td3* h, int batch) {
   read_mode();
   if (g_mode == 0) return false;
-  if (g_mode == 2 && batch > 1024) return false;
   const ClShape s = cluster_shape(batch);
   const int H = h->ar.critic.hid, L = h->ar.critic.layers;
   if (H % 4 != 0 || H < 4) return false;
-  return make_plan(s.R, s.CS, H, L, 5, L).bytes <= kClSmemLimit && make_plan(s.R, s.CS, H, L, 2, 2 * L).bytes <= kClSmemLimit;
+  if (make_plan(s.R, s.CS, H, L, 5, L).bytes > kClSmemLimit || make_plan(s.R, s.CS, H, L, 2, 2 * L).bytes > kClSmemLimit) return false;
+  if (g_mode == 2 && ceil_div(batch, s.R) > h->cluster_cap) return false;
+  return true;
 }
 
 int32_t rtd3::critic_cluster_launch(rtd3_td3* h, const float* params, const float* params_t, float* scratch, const ReplayView& rp, const int32_t* idx,

@@ -607,6 +607,7 @@ int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t 
   RTD3_CUDA(set_smem(mlp_forward_kernel<8>, h->smem_fwd[2]));
   RTD3_CUDA(set_smem(mlp_forward_kernel<16>, h->smem_fwd[3]));
   if (const char* e = getenv("RTD3_TILE")) g_tile_override = atoi(e);
+  h->cluster_cap = std::max(0, rtd3_td3_cluster_occupancy(h, 256));     // (queried here, never inside a stream capture)
   RTD3_CUDA(cudaSetDevice(prev));
   *out = h;
   return 0;

@@ -222,5 +222,6 @@ struct rtd3_td3 {
   int device;
   int num_sms;
   size_t smem_critic[kNumTiles], smem_actor[kNumTiles], smem_fwd[kNumTiles];
+  int cluster_cap;      // clusters of the cluster step kernels the device holds at once (set by rtd3_td3_create; 0: path unavailable)
 };
 

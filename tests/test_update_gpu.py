@@ -238,13 +238,14 @@ def test_cooperative_update_kernel_vs_step_kernels_and_oracle(pkg, H, L, B, E):
     torch.testing.assert_close(c1b, c2b, rtol=5e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("H,L,B", [(256, 2, 256), (200, 3, 100), (256, 2, 37), (64, 2, 513), (128, 1, 64)])
+@pytest.mark.parametrize("H,L,B", [(256, 2, 256), (200, 3, 100), (256, 2, 37), (64, 2, 261), (128, 1, 64)])
 def test_cluster_step_kernels_vs_row_tile_kernels(pkg, H, L, B):
     """The cluster step kernels (csrc/rtd3_cluster.cu: 4 CTAs share 8 batch rows and split every layer's columns) against the row-tile
     kernels on the same minibatch: gradients of all three networks, losses, Q-values and targets.  The two differ in summation order
     only - a different split of every reduction - so the bar is float32 round-off of chained 256-term sums over O(100) inputs (1e-4;
     measured <= 8e-5 on the three-layer shape), not the 1e-3 of the parity bar.
-    Ragged batches (37, 513 rows: a last cluster with 5 / 1 valid rows), 13 column groups per CTA (H = 200) and a single hidden layer
+    Ragged batches (37, 261 rows: a last cluster with 5 valid rows; 261 rows = 33 clusters, all the device holds at once - larger
+    batches stay on the row tiles), 13 column groups per CTA (H = 200) and a single hidden layer
     (the head straight from the first layer) are the cluster plan's edge cases."""
     L_ = pkg._lib.lib()
     rb = synthetic_replay(pkg)
