@@ -866,9 +866,10 @@ int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch) {
   const ClShape s = cluster_shape(batch);
   const int H = h->ar.critic.hid, L = h->ar.critic.layers;
   const ClPlan p = make_plan(s.R, s.CS, H, L, 5, L);
+  if (H % 4 != 0 || H < 4 || p.bytes > kClSmemLimit || make_plan(s.R, s.CS, H, L, 2, 2 * L).bytes > kClSmemLimit) return 0;   // no plan: no clusters
   return dispatch(s, [&](auto r, auto cs) -> int32_t {
     auto* fn = td3_critic_cluster_kernel<decltype(r)::value, decltype(cs)::value>;
-    if (ensure_dyn_smem((const void*)fn, p.bytes) != cudaSuccess) return -2;
+    if (ensure_dyn_smem((const void*)fn, p.bytes) != cudaSuccess) { (void)cudaGetLastError(); return -2; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(ceil_div(batch, s.R) * s.CS), 1, 1);
     cfg.blockDim = dim3(kClBlock, 1, 1);
@@ -880,7 +881,7 @@ int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch) {
     cfg.numAttrs = 1;
     int n = 0;
     const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
-    if (e != cudaSuccess) { rtd3::set_error("cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e)); return -3; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); rtd3::set_error("cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e)); return -3; }
     return n;
   });
 }
