@@ -426,7 +426,7 @@ int32_t rtd3_td3_update_coop(rtd3_td3* h, const rtd3_td3_update_args* args, floa
 int32_t rtd3_debug_coop_prof(long long* device_buf);
 
 /* Small-batch step kernels on thread-block clusters (csrc/rtd3_cluster.cu; the default of rtd3_td3_critic_step / rtd3_td3_actor_step /
- * rtd3_td3_update for fp32 batches that are ONE wave of clusters: 8 rows per cluster, 33 clusters on a B200 = up to 264 rows): 1 if the step of `batch` rows runs on that path, and how many of its 8-CTA clusters the
+ * rtd3_td3_update for fp32 batches that are ONE wave of clusters: 8 rows per cluster, 33 clusters on a B200 = up to 264 rows): 1 if the step of `batch` rows runs on that path, and how many of its 4-CTA clusters the
  * device can hold at once (cudaOccupancyMaxActiveClusters of the critic kernel; negative: CUDA error). */
 int32_t rtd3_td3_cluster_supported(const rtd3_td3* h, int32_t batch);
 int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch);

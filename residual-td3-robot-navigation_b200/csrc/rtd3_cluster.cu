@@ -534,10 +534,24 @@ __device__ __forceinline__ void cl_backward(Cl& c, int slot, const NetShape& s, 
 
 constexpr int kMaxTiles = 7 * (kMaxLayers - 1) + 4;      // critic step: 7 (L-1) tiles
 
+// producer warp, first thing in the kernel: its own barrier and the small-parameter copies (their latency runs under the set-up of
+// the other threads; the compute threads meet barrier 8 only after the CTA barrier of cl_begin)
+template <typename IssueFn>
+__device__ __forceinline__ void small_begin(const Cl& c, uint32_t bytes, int items, IssueFn&& issue) {
+  const int lane = threadIdx.x - kCT;
+  if (lane == 0) {
+    mbar_init(cl_bar(c, 8), 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(cl_bar(c, 8), bytes);
+  }
+  __syncwarp();
+  for (int w = lane; w < items; w += 32) issue(w);
+}
+
 // common start (all threads of the CTA): the mbarriers.  Ends with a CTA barrier.
 __device__ __forceinline__ void cl_begin(Cl& c) {
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(cl_bar(c, i), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(cl_bar(c, i), 1);     // (barrier 8 is the producer warp's: see small_begin)
     fence_mbar_init();
   }
   __syncthreads();
@@ -587,22 +601,15 @@ td3_critic_cluster_kernel(Arena ar, const float* __restrict__ params, const floa
     }
     tiles[t] = p;
   }
+  if (t >= kCT)                          // small parameters of the five passes: work item = (pass, copy)
+    small_begin(c, small_bytes(c, ar.actor) + 4u * small_bytes(c, ar.critic), 5 * (L + 1), [&](int w) {
+      const int pass = w / (L + 1), net = pass < 3 ? pass + 3 : pass - 2;
+      small_issue(c, pass, params + ar.off(net), pass == 0 ? ar.actor : ar.critic, w - pass * (L + 1));
+    });
   cl_begin(c);
   stamp(c, 3);
   if (t >= kCT) {                        // producer warp: weight tiles, in the order of use
     cluster_arrive();                                      // its share of the start barrier first: nobody waits for its copies to be issued
-    {                                                      // small parameters of the five passes: lane = (pass, item)
-      const int lane = t - kCT, per = L + 1;
-      if (lane == 0) {
-        uint32_t bytes = small_bytes(c, ar.actor) + 4u * small_bytes(c, ar.critic);
-        mbar_arrive_expect_tx(cl_bar(c, 8), bytes);
-      }
-      __syncwarp();
-      for (int w = lane; w < 5 * per; w += 32) {
-        const int pass = w / per, net = pass < 3 ? pass + 3 : pass - 2;
-        small_issue(c, pass, params + ar.off(net), pass == 0 ? ar.actor : ar.critic, w - pass * per);
-      }
-    }
     cl_producer(c, tiles, 0, min(c.ns, 7 * (L - 1)));      // the first tiles need no free slot; then join the start barrier
     if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 1);   // (read by the optimiser kernel that follows)
     cluster_wait();
@@ -701,18 +708,14 @@ td3_actor_cluster_kernel(Arena ar, const float* __restrict__ params, const float
     }
     tiles[t] = p;
   }
+  if (t >= kCT)
+    small_begin(c, small_bytes(c, ar.actor) + small_bytes(c, ar.critic), 2 * (L + 1), [&](int w) {
+      const int pass = w / (L + 1);
+      small_issue(c, pass, params + ar.off(pass), pass == 0 ? ar.actor : ar.critic, w - pass * (L + 1));
+    });
   cl_begin(c);
   if (t >= kCT) {
     cluster_arrive();
-    {
-      const int lane = t - kCT, per = L + 1;
-      if (lane == 0) mbar_arrive_expect_tx(cl_bar(c, 8), small_bytes(c, ar.actor) + small_bytes(c, ar.critic));
-      __syncwarp();
-      for (int w = lane; w < 2 * per; w += 32) {
-        const int pass = w / per;
-        small_issue(c, pass, params + ar.off(pass), pass == 0 ? ar.actor : ar.critic, w - pass * per);
-      }
-    }
     cl_producer(c, tiles, 0, min(c.ns, 4 * (L - 1)));
     if (blockIdx.x == 0 && t == kCT) advance_adam_clock(steps, beta_pows, 0);
     cluster_wait();
