@@ -94,6 +94,7 @@ struct Cl {
   int ncg_sh;        // log2 of the column groups a reduction group spans (>= Wc / 4)
   int kgn, part;     // reduction groups and their length
   int rank, c_lo, ncols;
+  int started;       // 0 until this thread has waited for the start barrier (it does so right before the cluster's first push)
   int stg;           // stages completed so far (the same number in every thread of the cluster)
   int dsel;          // which dz tile the next pushed output goes to
   long long* prof;   // development: stage stamps of thread 0 of CTA 0 ((code << 48) | clock64), nullptr = off
@@ -163,7 +164,7 @@ __device__ __forceinline__ void cl_carve(Cl& c, int R, int CS, int H, int L, int
   c.rank = (int)cluster_ctarank();
   c.c_lo = c.rank * c.Wc;
   c.ncols = max(0, min(c.Wc, H - c.c_lo));
-  c.stg = 0; c.dsel = 0;
+  c.stg = 0; c.dsel = 0; c.started = 0;
   c.prof = nullptr; c.pn = 0;
 }
 
@@ -225,6 +226,15 @@ __device__ __forceinline__ int next_dz(Cl& c) {
   const int r = c.dsel ? c.dz1 : c.dz0;
   c.dsel ^= 1;
   return r;
+}
+
+// The start barrier (every CTA of the cluster runs and has initialised its mbarriers) is only needed before the first store into a
+// peer's shared memory: the threads arrive at kernel start and wait here, a first layer and a product later.
+__device__ __forceinline__ void ensure_started(Cl& c) {
+  if (!c.started) {
+    cluster_wait();
+    c.started = 1;
+  }
 }
 
 // ---- stages ------------------------------------------------------------------------------------------------------------------------
@@ -364,6 +374,7 @@ __device__ __forceinline__ void cl_fwd_hidden(Cl& c, int ti, int T, int slot, in
   cl_product<R>(c, T, X);
   tile_release(c, ti);
   stamp(c, 21);
+  ensure_started(c);
   const int q = c.ncols >> 2, bb = sp_bias(c, slot, l), hd = sp_head(c, slot);
   // 16 column groups and all rows in one sweep: the 16 threads of a row are half a warp and add their head contributions by shuffles
   const bool fast = last && q == 16 && R * 16 <= kCT;
@@ -439,6 +450,7 @@ __device__ __forceinline__ void cl_forward(Cl& c, int slot, const NetShape& s, b
       if (lane == 0) smem_f[c.din + r * 4 + o] = v;          // din doubles as scratch here (the backward pass writes it later)
     }
     cta_sync();
+    ensure_started(c);
     const float a = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4] : 0.f, b2 = threadIdx.x < R ? smem_f[c.din + threadIdx.x * 4 + 1] : 0.f;
     exchange_pairs<R, CS>(c, c.hp, a, b2, c.out, 2, smem_f[hd + s.out * c.H], s.out > 1 ? smem_f[hd + s.out * c.H + 1] : 0.f);
     return;
@@ -558,9 +570,10 @@ __device__ __forceinline__ void cl_begin(Cl& c) {
 }
 // compute threads: the small parameters have landed; every CTA of the cluster runs and has its mbarriers set up
 __device__ __forceinline__ void cl_started(Cl& c) {
+  cluster_arrive();                  // waited for in ensure_started()
   mbar_wait(cl_bar(c, 8), 0);
   stamp(c, 1);
-  cluster_sync();
+  cta_sync();                        // the replay rows gathered by the first R threads
   stamp(c, 2);
 }
 
