@@ -673,9 +673,10 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s",
                     "h2d_bytes_per_step": per_buf * EPS, "d2h_bytes_per_step": per_buf * EPS, "calls_per_step": EPS,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "path": "Environment.rollout_host on pinned host buffers: one launch, the rollout kernel's TMA tiles read the actions from / "
-                            "write the trajectory to host memory over PCIe (UVA zero-copy, no staging copies); raw cudaMemcpy of both "
-                            "directions run concurrently takes 0.66 ms for these bytes"},
+                    "path": "Environment.rollout_host on pinned host buffers (rtd3_env_rollout_host): 8 time slices, the copy engine stages "
+                            "the actions of slice c+1 in HBM while the rollout kernel runs slice c and writes its trajectory tiles to host "
+                            "memory over PCIe (TMA stores), the pipeline replayed as one CUDA graph per call; raw cudaMemcpy of both "
+                            "directions run concurrently takes 0.70 ms for these bytes"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }

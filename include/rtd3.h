@@ -84,6 +84,15 @@ int32_t rtd3_env_rollout(rtd3_env* h, float* x, float* y, const float* actions, 
  * warp-pair TMA kernel used for latency-bound batches), 0 restores the automatic choice. */
 void rtd3_env_force_plain_rollout(int32_t on);
 
+/* rtd3_env_rollout for HOST buffers: actions_host / traj_host are page-locked host memory [T][2][n] (same loop, robot-learning.py:97-100).
+ * mode is a bit set - 1: the copy engine stages the actions in HBM, 2: the trajectory goes back through the copy engine; an
+ * unstaged direction is read / written by the kernel's TMA tiles across PCIe (0 = both: one plain launch).  With a staged direction
+ * the T steps run as `chunks` time slices: copy of slice c+1, kernel of slice c and copy-back of slice c-1 overlap, and the whole
+ * pipeline is ONE CUDA graph per (buffers, shape), cached in the handle (staging buffers and up to 16 graphs, freed by
+ * rtd3_env_destroy).  Asynchronous on `stream` like every other call; x, y end at the final state. */
+int32_t rtd3_env_rollout_host(rtd3_env* h, float* x, float* y, const float* actions_host, float* traj_host, int64_t n,
+                              int64_t T, int32_t chunks, int32_t mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * numpy-legacy MT19937 streams, one per env      (robot-learning.py:19; numpy RandomState)
  * ---------------------------------------------------------------------------------------------- */

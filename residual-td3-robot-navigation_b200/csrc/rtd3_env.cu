@@ -629,6 +629,7 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
   h->device = device;
   h->has_map = false;
   h->table = nullptr;
+  h->host_pipe = nullptr;
   RTD3_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   RTD3_CUDA(cudaMalloc(&h->table, kTableBytes));
   if (!g_encode_tiled) load_encode_tiled();
@@ -653,6 +654,7 @@ int32_t rtd3_env_create(rtd3_env** out, int32_t device) {
 
 int32_t rtd3_env_destroy(rtd3_env* h) {
   if (!h) return 0;
+  rtd3::host_pipe_destroy(h);
   if (h->table) cudaFree(h->table);
   delete h;
   return 0;

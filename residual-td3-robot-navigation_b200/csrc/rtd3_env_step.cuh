@@ -9,9 +9,12 @@ struct rtd3_env {
   int num_sms;
   float2* table;   // [100*100] (speed*cos(rot), speed*sin(rot)), indexed x*100+y
   bool has_map;
+  void* host_pipe;   // rtd3::HostPipe of rtd3_env_rollout_host (rtd3_env_host.cu), created on first use
 };
 
 namespace rtd3 {
+
+void host_pipe_destroy(rtd3_env* h);   // rtd3_env_host.cu: streams, staging buffers and cached graphs of the host-buffer rollout
 
 // One env-step, the rotation form of environment.py:100-117 (no atan2):
 //   s' = clip(s + speed*(ax*cos(rot) - ay*sin(rot), ax*sin(rot) + ay*cos(rot)), 0, 98.9999)

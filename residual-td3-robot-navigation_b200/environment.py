@@ -270,19 +270,26 @@ class Environment:
         self._state_np = None
         return traj.permute(0, 2, 1) if record else None
 
-    def rollout_host(self, actions_host, out_host=None, chunks=8, mode=None):
+    def rollout_host(self, actions_host, out_host=None, chunks=None, mode=None):
         """`rollout` for HOST buffers: `actions_host` float32 `[T,2,N]` (planes), `out_host` `[T,2,N]` or None.  Pinned buffers
-        are mapped into the device's address space (UVA), so the rollout kernel's TMA tiles can cross PCIe themselves:
+        are mapped into the device's address space (UVA), so the copy engines and the rollout kernel's TMA tiles reach them:
 
-        mode "zero_copy" (default for pinned buffers): ONE launch; the kernel's TMA tile loads read the actions from host memory
-            and its tile stores write the trajectory back, both overlapped with the recurrence, nothing staged in HBM
-            (0.91-0.93 ms per synchronous call for 4096 x 1000);
-        mode "hybrid": the T steps are cut into `chunks` time slices; the copy engine brings the actions of slice c+1 to HBM
-            while the kernel runs slice c and writes its trajectory tiles straight to the host buffer (0.95 ms per synchronous
-            call; 0.85 ms when calls are issued back to back without a host sync in between);
-        mode "staged" (any buffers; the default when one is pageable): H2D copy of slice c+1, kernel of slice c and D2H copy of
-            slice c-1 on three streams (0.92 ms).
-        For reference, the two raw copies run concurrently take 0.66 ms for these bytes: every mode is PCIe-bound.
+        mode "graph_in" (default for pinned buffers): `rtd3_env_rollout_host` - the T steps in `chunks` (8) time slices, the
+            copy engine brings the actions of slice c+1 to HBM while the kernel runs slice c and writes its trajectory tiles
+            straight to the host buffer (TMA stores across PCIe); the whole pipeline is ONE CUDA graph cached in the library per
+            (buffers, shape), so a call is one graph launch: 0.834 ms per synchronous call for 4096 x 1000 (16 slices 0.846,
+            32 slices 0.971: a slice costs ~7 us of hand-over, the first one's copy is exposed);
+        mode "graph": both directions through the copy engines (H2D of slice c+1, kernel of slice c, D2H of slice c-1): 0.920 ms
+            with 4 slices, 0.943 with 8, 1.07 with 16 - every memcpy node adds ~8 us to the chain;
+        mode "graph_out": the kernel reads the host actions itself, the trajectory goes back through the copy engine: 1.22 ms
+            (TMA tile reads across PCIe are the slow direction);
+        mode "zero_copy": ONE launch; the kernel's TMA tile loads read the actions from host memory and its tile stores write
+            the trajectory back, both overlapped with the recurrence, nothing staged in HBM (0.926 ms);
+        mode "hybrid": the "graph_in" pipeline issued eagerly from Python on torch streams (0.95 ms);
+        mode "staged" (any buffers; the default when one is pageable): the "graph" pipeline issued eagerly from Python on three
+            torch streams (0.934 ms).
+        For reference, the two raw copies run concurrently take 0.70 ms for these bytes: every mode is PCIe-bound
+        (`tools/e2e_graph.py`).
 
         Returns `out_host` (a fresh pinned tensor if None was given); the call returns once the result is on the host."""
         n = self.num_envs
@@ -295,13 +302,22 @@ class Environment:
             raise ValueError("out_host must be a contiguous float32 [T,2,%d] like actions_host" % n)
         pinned = actions_host.is_pinned() and out_host.is_pinned()
         if mode is None:
-            mode = "zero_copy" if pinned else "staged"
-        if mode not in ("hybrid", "zero_copy", "staged"):
-            raise ValueError("mode must be 'hybrid', 'zero_copy' or 'staged'")
+            mode = "graph_in" if pinned else "staged"
+        graph_modes = {"graph": 3, "graph_in": 1, "graph_out": 2}
+        if mode not in ("hybrid", "zero_copy", "staged") and mode not in graph_modes:
+            raise ValueError("mode must be 'graph', 'graph_in', 'graph_out', 'zero_copy', 'hybrid' or 'staged'")
         if mode != "staged" and not pinned:
             raise ValueError("mode %r needs pinned host buffers" % mode)
         main = torch.cuda.current_stream(self.device)
         self._state_np = None
+        if mode in graph_modes:
+            _lib.check(_lib.lib().rtd3_env_rollout_host(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
+                                                        _lib.ptr(actions_host), _lib.ptr(out_host), n, T,
+                                                        8 if chunks is None else int(chunks), graph_modes[mode],
+                                                        _lib.stream_ptr(self.device)), "env_rollout_host")
+            main.synchronize()
+            return out_host
+        chunks = 8 if chunks is None else int(chunks)
         if mode == "zero_copy":
             _lib.check(_lib.lib().rtd3_env_rollout(self._handle, _lib.ptr(self._state[0]), _lib.ptr(self._state[1]),
                                                    _lib.ptr(actions_host), _lib.ptr(out_host), n, T,

@@ -260,11 +260,23 @@ def test_rollout_host_equals_device_rollout(pkg, env_golden):
     assert torch.equal(out2.cuda().permute(0, 2, 1), ref2)
     out3 = torch.empty((T, 2, n)).pin_memory()
     before = pkg._lib.launch_count()
-    assert env_a.rollout_host(h_act, out3) is out3                       # pinned default: one launch, the kernel itself crosses PCIe both ways
+    assert env_a.rollout_host(h_act, out3, mode="zero_copy") is out3     # one launch, the kernel itself crosses PCIe both ways
     assert pkg._lib.launch_count() - before == 1
     ref3 = env_b.rollout(h_act.cuda())
     assert torch.equal(out3.cuda().permute(0, 2, 1), ref3)
     assert torch.equal(env_a.robot_state, env_b.robot_state)
+    # pinned default: rtd3_env_rollout_host - the copy-engine pipeline as one cached CUDA graph; replayed, and with ragged slices
+    for kw in ({}, {}, {"chunks": 7}, {"chunks": 1}, {"chunks": 1000}, {"mode": "graph", "chunks": 5}, {"mode": "graph_out", "chunks": 3}):
+        out6 = torch.empty((T, 2, n)).pin_memory() if kw else out3
+        out6.zero_()
+        assert env_a.rollout_host(h_act, out6, **kw) is out6
+        ref6 = env_b.rollout(h_act.cuda())
+        assert torch.equal(out6.cuda().permute(0, 2, 1), ref6), kw
+        assert torch.equal(env_a.robot_state, env_b.robot_state)
+    small = pkg.Environment(num_envs=6, seed=3, maps=(g["speed"], g["angle"]))      # n % 4 != 0: the cp.async rollout kernel in the graph
+    small_b = pkg.Environment(num_envs=6, seed=3, maps=(g["speed"], g["angle"]))
+    h_small = (torch.rand((33, 2, 6)) * 15 - 7.5).pin_memory()
+    assert torch.equal(small.rollout_host(h_small, chunks=4).cuda().permute(0, 2, 1), small_b.rollout(h_small.cuda()))
     out5 = torch.empty((T, 2, n)).pin_memory()
     assert env_a.rollout_host(h_act, out5, chunks=6, mode="hybrid") is out5   # H2D slices by the copy engine, trajectory written to the host by the kernel
     ref5 = env_b.rollout(h_act.cuda())
