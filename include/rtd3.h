@@ -442,6 +442,10 @@ int32_t rtd3_td3_cluster_occupancy(const rtd3_td3* h, int32_t batch);
 /* Development / test aid: 0 = the step entry points use the row-tile kernels, 2 = the cluster kernels wherever their plan fits (the
  * default); returns the previous mode (1 = a shape forced through RTD3_CLUSTER=R,CS).  Not thread-safe against running launches. */
 int32_t rtd3_debug_cluster_mode(int32_t mode);
+/* Development: stage stamps (%globaltimer, ns) of the last weight-gradient launch that exchanged its tiles with the peers
+ * (rtd3_td3_update at world > 1 over peer memory, RTD3_P2P_PROF=1): out_host [256 blocks][2 threads][8 stages] uint64.  Returns 1 if
+ * the stamps were copied, 0 if profiling is off. */
+int32_t rtd3_debug_p2p_prof(uint64_t* out_host);
 /* Development aid: DEVICE buffers of 256 int64 each that the following cluster critic / actor kernels fill with clock64 stamps of
  * CTA 0 at every stage boundary ([0] = number of stamps); NULL switches it off. */
 int32_t rtd3_debug_cluster_prof(long long* critic_buf, long long* actor_buf);

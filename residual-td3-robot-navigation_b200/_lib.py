@@ -128,6 +128,7 @@ _SIGNATURES = {
     "rtd3_td3_cluster_occupancy": (c_int32, [_P, c_int32]),
     "rtd3_debug_cluster_prof": (c_int32, [_P, _P]),
     "rtd3_debug_cluster_mode": (c_int32, [c_int32]),
+    "rtd3_debug_p2p_prof": (c_int32, [_P]),
     "rtd3_td3_target_noise": (c_int32, [c_uint64, c_uint64, _P, c_int64, _P]),
     "rtd3_tick_pre": (c_int32, [POINTER(TickStateStruct), _P]),
     "rtd3_tick_post": (c_int32, [_P, POINTER(TickStateStruct), _P, _P, c_int32, _P]),

@@ -15,42 +15,10 @@
 #include <algorithm>
 
 #include "rtd3_common.cuh"
+#include "rtd3_p2p.cuh"
 #include "rtd3_td3.cuh"
 
 namespace rtd3 {
-
-constexpr int kP2pMaxWorld = RTD3_P2P_MAX_WORLD;
-constexpr unsigned long long kSpinLimitNs = 20ull * 1000 * 1000 * 1000;
-
-struct P2pPeers {
-  float* recv[kP2pMaxWorld];                 // rank q's receive area as mapped here: [2][W][count] floats
-  unsigned long long* flags[kP2pMaxWorld];   // rank q's flag array: flags[r] = last step rank r has pushed completely
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long seq) {
-  if (ld_acquire_sys(p) >= seq) return;
-  const unsigned long long t0 = global_ns();
-  while (ld_acquire_sys(p) < seq)
-    if (global_ns() - t0 > kSpinLimitNs) asm volatile("trap;");
-}
-__device__ __forceinline__ float4 ld_fresh(const float4* p) {   // written by a peer during this launch: not from a stale line
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
 
 // phases (1) and (2) of the header comment + the wait of phase (3); returns this step's number
 template <int kWorld>
@@ -125,9 +93,6 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pPeers peers, int 
 // slow block delays only its own elements.  Phase (3) walks the online arena like td3_adam_polyak_kernel - Adam on the elements of
 // the reduced slice (gradient = sum of the W slots x grad_scale), the Polyak blend where asked for - so the summed gradients never
 // go back to memory and the separate optimiser launch (one more pass over the arena) disappears.
-constexpr int kP2pBlockFlags = 256;          // per rank; the grid never has more blocks (one per SM)
-constexpr int kP2pBlockFlagBase = 16;
-
 template <int kWorld>
 __global__ void __launch_bounds__(256) p2p_allreduce_adam_kernel(P2pPeers peers, int rank, unsigned long long* seq_counter,
                                                                  float* __restrict__ local_grads, int64_t count4, int64_t stride4,

@@ -5,6 +5,7 @@
 #include "rtd3_common.cuh"
 #include "rtd3_mlp.cuh"
 #include "rtd3_tc.cuh"
+#include "rtd3_p2p.cuh"
 #include "rtd3_td3.cuh"
 
 namespace rtd3 {
@@ -170,6 +171,131 @@ struct AdamFuse {
   NetShape shape;
 };
 
+// Optional peer-memory exchange fused into the same pass (data parallel, world > 1, with AdamFuse): a job PUSHES the gradient elements
+// it has just formed into slot [step parity][rank] of every peer's receive area (remote stores over NVLink, fire and forget), reads the
+// peers' contributions to the same elements from its own receive area, adds the W contributions in rank order - the same order on
+// every rank, so the replicas stay bit-identical - and applies the optimiser to the sum.  The gradients never go to memory on their
+// own rank, and the all-reduce launch of an optimiser step disappears.
+// Hand-over WITHOUT a fence: the first version raised a flag per block after a system-scope fence, and the stage stamps
+// (RTD3_P2P_PROF, tools/dp_perf.py) showed the fence alone taking 4-17 us per block (MEMBAR.SYS waits for the acknowledgement of
+// every remote store in flight) - 10 of the 26 us the kernel then took.  Now every value travels WITH its flag, as in NCCL's LL
+// protocol: a 16-byte line is {value, step, value, step}, each 8-byte half is single-copy atomic, and the reader polls its own lines
+// until both halves carry this step's number.  Twice the bytes on the link (1 MB per peer and critic step), no fence, no flag hop: the
+// hand-over costs one NVLink one-way trip.  A slot is `stride` floats = room for a slice in line form (2 floats per element).
+// Why the two parity slots suffice: the steps of a rank are kernel launches in stream order; rank A's step s + 1 kernel starts after its
+// step s kernel has ended, i.e. after every block of A has seen B's step s lines, which B pushes only after its step s - 1 kernel has
+// ended - so when A overwrites slot [(s + 1) & 1], B has finished reading it.  A reader that sees no line within 20 s traps.
+struct P2pFuse {
+  float* recv[kP2pMaxWorld];
+  int world;                          // 0: no exchange
+  int rank;
+  unsigned long long* seq_counter;    // last completed step (device memory: a replayed graph counts on by itself)
+  unsigned int* block_counter;
+  int64_t stride;                     // floats between the [parity][rank] slots of a receive area (>= 2 x the largest slice)
+  int64_t slice_off;                  // arena offset of the slice this optimiser step reduces
+  float grad_scale;                   // 1 / world
+  unsigned long long* prof;           // development (RTD3_P2P_PROF=1): %globaltimer stamps [block][2 threads][8 stages], else nullptr
+};
+__device__ __forceinline__ void p2p_stamp(const P2pFuse& px, int cta, int k) {
+  if (px.prof && threadIdx.x < 2) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    px.prof[(cta * 2 + threadIdx.x) * 8 + k] = t;
+  }
+}
+// float offset of element `arena_idx` (line form) in slot [parity][r]
+__device__ __forceinline__ int64_t p2p_slot(const P2pFuse& px, unsigned int seq, int r, int64_t arena_idx) {
+  return ((int64_t)(seq & 1u) * px.world + r) * px.stride + 2 * (arena_idx - px.slice_off);
+}
+__device__ __forceinline__ void st_line(float* p, float a, float b, unsigned int f) {
+  asm volatile("st.volatile.global.v4.b32 [%0], {%1, %2, %3, %2};" ::"l"(p), "r"(__float_as_uint(a)), "r"(f), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ uint4 ld_line(const float* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_half(float* p, float a, unsigned int f) {
+  asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(a)), "r"(f) : "memory");
+}
+__device__ __forceinline__ uint2 ld_half(const float* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_push4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float4 v) {
+  const int64_t at = p2p_slot(px, seq, px.rank, arena_idx);
+#pragma unroll
+  for (int q = 0; q < kP2pMaxWorld; ++q)
+    if (q < px.world && q != px.rank) {
+      st_line(px.recv[q] + at, v.x, v.y, seq);
+      st_line(px.recv[q] + at + 4, v.z, v.w, seq);
+    }
+}
+__device__ __forceinline__ void p2p_push1(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float v) {
+  const int64_t at = p2p_slot(px, seq, px.rank, arena_idx);
+#pragma unroll
+  for (int q = 0; q < kP2pMaxWorld; ++q)
+    if (q < px.world && q != px.rank) st_half(px.recv[q] + at, v, seq);
+}
+__device__ __forceinline__ void p2p_spin_check(unsigned long long& t0) {
+  const unsigned long long now = global_ns();
+  if (t0 == 0ull) t0 = now;
+  else if (now - t0 > kSpinLimitNs) asm volatile("trap;");
+}
+// sum over the ranks in rank order (own contribution from registers), times grad_scale; polls until every peer's lines carry `seq`
+__device__ __forceinline__ float4 p2p_sum4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float4 own) {
+  float4 v[kP2pMaxWorld];
+  const float* mine = px.recv[px.rank];
+  unsigned long long t0 = 0ull;
+#pragma unroll
+  for (int r = 0; r < kP2pMaxWorld; ++r) {
+    if (r >= px.world) continue;
+    if (r == px.rank) { v[r] = own; continue; }
+    const float* at = mine + p2p_slot(px, seq, r, arena_idx);
+    uint4 a = ld_line(at), b = ld_line(at + 4);
+    while (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
+      p2p_spin_check(t0);
+      a = ld_line(at); b = ld_line(at + 4);
+    }
+    v[r] = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+  }
+  float4 acc = v[0];
+#pragma unroll
+  for (int r = 1; r < kP2pMaxWorld; ++r)
+    if (r < px.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+  return make_float4(acc.x * px.grad_scale, acc.y * px.grad_scale, acc.z * px.grad_scale, acc.w * px.grad_scale);
+}
+__device__ __forceinline__ float p2p_sum1(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float own) {
+  float v[kP2pMaxWorld];
+  const float* mine = px.recv[px.rank];
+  unsigned long long t0 = 0ull;
+#pragma unroll
+  for (int r = 0; r < kP2pMaxWorld; ++r) {
+    if (r >= px.world) continue;
+    if (r == px.rank) { v[r] = own; continue; }
+    const float* at = mine + p2p_slot(px, seq, r, arena_idx);
+    uint2 a = ld_half(at);
+    while (a.y != seq) {
+      p2p_spin_check(t0);
+      a = ld_half(at);
+    }
+    v[r] = __uint_as_float(a.x);
+  }
+  float acc = v[0];
+#pragma unroll
+  for (int r = 1; r < kP2pMaxWorld; ++r)
+    if (r < px.world) acc += v[r];
+  return acc * px.grad_scale;
+}
+// bookkeeping of a step, by one thread per block: the last block to come by (every block has read the step number) advances it
+__device__ __forceinline__ void p2p_step_done(const P2pFuse& px, unsigned long long seq64, int ncta) {
+  if (atomicAdd(px.block_counter, 1u) == (unsigned)ncta - 1u) {
+    *px.block_counter = 0u;
+    *px.seq_counter = seq64;
+  }
+}
+
 // ---- weight gradients from the row scratch, reduced over the batch without atomics -----------------------------------
 //   hidden layer l (1..L-1):  gW_l[n][k] = sum_b dz_l[b][n] * h_{l-1}[b][k]      32x32 output tiles
 //   every hidden layer l:     gb_l[n]    = sum_b dz_l[b][n];   l = 0 also gW_0[n][j] = sum_b dz_0[b][n] * in0[b][j]
@@ -185,8 +311,18 @@ constexpr int kWgradRows = 256;                                   // batch rows 
 constexpr size_t kWgradSmem = 2 * kWgradRows * 32 * sizeof(float);  // dz slab + layer-input slab (the partial tiles alias them)
 
 __global__ void __launch_bounds__(kThreads)
-wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split, AdamFuse fz) {
+wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split, AdamFuse fz,
+             P2pFuse px) {
   __shared__ __align__(16) float red_small[8][32 * 5];
+  // peer exchange: this step's number (the last block whose threads have all read it advances it)
+  const unsigned long long seq64 = px.world ? *reinterpret_cast<volatile unsigned long long*>(px.seq_counter) + 1ull : 0ull;
+  const unsigned int seq = (unsigned int)seq64;                      // the number the lines of this step carry
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x, ncta = gridDim.x * gridDim.y;
+  p2p_stamp(px, cta, 0);
+  if (px.world) {
+    __syncthreads();                                                 // every thread of the block has read the step number
+    if (threadIdx.x == 32) p2p_step_done(px, seq64, ncta);
+  }
   // fused optimiser: bias corrections from the Adam clocks (loaded now, used after the batch reduction)
   double bp1 = 0.0, bp2 = 0.0;
   if (fz.params) { bp1 = fz.beta_pows[2 * fz.opt]; bp2 = fz.beta_pows[2 * fz.opt + 1]; }
@@ -313,6 +449,13 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
       const float4 p = *reinterpret_cast<const float4*>(red + w * 1024 + o);
       v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
     }
+    if (px.world) {
+      p2p_stamp(px, cta, 1);
+      if (out_ok) p2p_push4(px, seq, G0 + off, v);
+      p2p_stamp(px, cta, 2);
+      if (out_ok) v = p2p_sum4(px, seq, G0 + off, v);
+      p2p_stamp(px, cta, 5);
+    }
     if (out_ok) {
       if (!fz.params) {
         if (!atomic) *reinterpret_cast<float4*>(grads + G0 + off) = v;
@@ -355,6 +498,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
         }
       }
     }
+    p2p_stamp(px, cta, 6);
   } else if (job < nT + nS) {
     const int l = (job - nT) / nch, n = ((job - nT) % nch) * 32 + lane;
     const float* dz = rs.dz(l);
@@ -381,11 +525,27 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     float* r = &red_small[warp][lane * 5];
     r[0] = ab; r[1] = aw[0]; r[2] = aw[1]; r[3] = aw[2]; r[4] = aw[3];
     __syncthreads();
-    if (warp == 0 && n < H) {
-      if (fz.params) bias_corrections();
-      float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool own = warp == 0 && n < H;
+    if (own)
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 5; ++q) v[q] += red_small[w][lane * 5 + q];
+    if (px.world) {
+      if (own) {
+        p2p_push1(px, seq, G0 + net_b_off(s, l) + n, v[0]);
+        if (l == 0)
+          for (int j = 0; j < 4; ++j)
+            if (j < s.in) p2p_push1(px, seq, G0 + net_w_off(s, 0) + n * s.in + j, v[1 + j]);
+      }
+      if (own) {
+        v[0] = p2p_sum1(px, seq, G0 + net_b_off(s, l) + n, v[0]);
+        if (l == 0)
+          for (int j = 0; j < 4; ++j)
+            if (j < s.in) v[1 + j] = p2p_sum1(px, seq, G0 + net_w_off(s, 0) + n * s.in + j, v[1 + j]);
+      }
+    }
+    if (own) {
+      if (fz.params) bias_corrections();
       emit_pre(G0, net_b_off(s, l) + n, v[0], atomic, pre[0]);
       if (l == 0) {
 #pragma unroll
@@ -415,11 +575,27 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     float* r = &red_small[warp][lane * 4];
     r[0] = a0; r[1] = a1; r[2] = s0; r[3] = s1;
     __syncthreads();
-    if (warp == 0) {
-      if (fz.params) bias_corrections();
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp == 0)
       for (int w = 0; w < 8; ++w)
         for (int q = 0; q < 4; ++q) v[q] += red_small[w][lane * 4 + q];
+    if (px.world) {
+      const bool own_w = warp == 0 && k < H, own_b = warp == 0 && chunk == 0 && lane < s.out;
+      if (own_w)
+        for (int o = 0; o < 2; ++o)
+          if (o < s.out) p2p_push1(px, seq, G0 + net_w_off(s, L) + (int64_t)o * H + k, v[o]);
+      const float vb = lane == 0 ? v[2] : v[3];                        // v[2 + lane] of the bias lanes (s.out <= 2)
+      if (own_b) p2p_push1(px, seq, G0 + net_b_off(s, L) + lane, vb);
+      if (own_w)
+        for (int o = 0; o < 2; ++o)
+          if (o < s.out) v[o] = p2p_sum1(px, seq, G0 + net_w_off(s, L) + (int64_t)o * H + k, v[o]);
+      if (own_b) {
+        const float sb = p2p_sum1(px, seq, G0 + net_b_off(s, L) + lane, vb);
+        if (lane == 0) v[2] = sb; else v[3] = sb;
+      }
+    }
+    if (warp == 0) {
+      if (fz.params) bias_corrections();
       if (k < H) {
 #pragma unroll
         for (int o = 0; o < 2; ++o)
@@ -558,15 +734,31 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static int32_t launch_wgrad(rtd3_td3* h, const NetShape& s, const float* scratch, float* grads, const WgradSlots& slots, int nslots, int B,
-                            cudaStream_t st, const AdamFuse& fz = AdamFuse{}) {
+static unsigned long long* g_p2p_prof = nullptr;   // development: stage stamps of the last fused weight-gradient launch
+
+static int wgrad_jobs(const NetShape& s) {
   const int nch = (s.hid + 31) / 32;
-  const int jobs = (s.layers - 1) * nch * nch + s.layers * nch + nch;
+  return (s.layers - 1) * nch * nch + s.layers * nch + nch;
+}
+
+static int32_t launch_wgrad(rtd3_td3* h, const NetShape& s, const float* scratch, float* grads, const WgradSlots& slots, int nslots, int B,
+                            cudaStream_t st, const AdamFuse& fz = AdamFuse{}, const P2pFuse& px = P2pFuse{}) {
+  const int jobs = wgrad_jobs(s);
   const int rows_per_split = 512;
   const int bsplit = (B + rows_per_split - 1) / rows_per_split;
   RTD3_CHECK_ARG(!fz.params || bsplit == 1, "the fused optimiser needs batch <= 512");
+  RTD3_CHECK_ARG(!px.world || (fz.params && jobs * nslots <= kP2pBlockFlags), "the fused peer exchange needs the fused optimiser and at most 256 blocks");
   RTD3_CUDA(ensure_dyn_smem((const void*)wgrad_kernel, kWgradSmem));
-  wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, kWgradSmem, st>>>(s, scratch, grads, slots, B, rows_per_split, fz);
+  static const bool coop_env = !(getenv("RTD3_P2P_COOP") && atoi(getenv("RTD3_P2P_COOP")) == 0);
+  if (px.world && coop_env) {
+    // every block waits for the same block of its peers: placed as a whole or not at all (see rtd3_p2p_allreduce)
+    NetShape s_ = s; WgradSlots sl = slots; AdamFuse fz_ = fz; P2pFuse px_ = px;
+    int B_ = B, rps = rows_per_split;
+    void* kargs[] = {&s_, &scratch, &grads, &sl, &B_, &rps, &fz_, &px_};
+    RTD3_CUDA(cudaLaunchCooperativeKernel((const void*)wgrad_kernel, dim3(jobs, nslots, bsplit), dim3(kThreads), kargs, kWgradSmem, st));
+  } else {
+    wgrad_kernel<<<dim3(jobs, nslots, bsplit), kThreads, kWgradSmem, st>>>(s, scratch, grads, slots, B, rows_per_split, fz, px);
+  }
   RTD3_LAUNCHED();
   return 0;
 }
@@ -609,6 +801,10 @@ int32_t rtd3_td3_create(rtd3_td3** out, int32_t device, int32_t hidden, int32_t 
   if (const char* e = getenv("RTD3_TILE")) g_tile_override = atoi(e);
   h->cluster_cap = std::max(0, rtd3_td3_cluster_occupancy(h, 256));     // (queried here, never inside a stream capture)
   RTD3_CUDA(cudaSetDevice(prev));
+  if (!g_p2p_prof && getenv("RTD3_P2P_PROF") && atoi(getenv("RTD3_P2P_PROF")) == 1) {      // development: stage stamps of the fused exchange
+    RTD3_CUDA(cudaMalloc(&g_p2p_prof, kP2pBlockFlags * 16 * sizeof(unsigned long long)));
+    RTD3_CUDA(cudaMemset(g_p2p_prof, 0, kP2pBlockFlags * 16 * sizeof(unsigned long long)));
+  }
   *out = h;
   return 0;
 }
@@ -651,7 +847,7 @@ int32_t rtd3_td3_critic_step(rtd3_td3* h, const float* params, const float* para
 
 static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
                                  const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
-                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz);
+                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz, const P2pFuse& px = P2pFuse{});
 
 int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
                                  const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
@@ -661,7 +857,7 @@ int32_t rtd3::critic_step_launch(rtd3_td3* h, const float* params, const float* 
 
 static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const ReplayView& rp,
                                  const int32_t* idx, const float* noise, int32_t batch, const Td3Hyper& hp, float* loss2, float* q_out, float* y_out,
-                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz) {
+                                 int32_t* steps, double* beta_pows, cudaStream_t st, const AdamFuse& fz, const P2pFuse& px) {
   if (cluster_path_ok(h, batch)) {
     const int32_t rc = critic_cluster_launch(h, params, params_t, scratch, rp, idx, noise, batch, hp, loss2, q_out, y_out, steps, beta_pows, st);
     if (rc) return rc;
@@ -679,13 +875,14 @@ static int32_t critic_step_fused(rtd3_td3* h, const float* params, const float* 
   const int64_t per = RowScratch::floats(batch, h->ar.critic.hid, h->ar.critic.layers);
   slots.grad_off[0] = h->ar.off(1); slots.grad_off[1] = h->ar.off(2);
   slots.scratch_off[0] = 0; slots.scratch_off[1] = per;
-  return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st, fz);
+  return launch_wgrad(h, h->ar.critic, scratch, grads, slots, 2, batch, st, fz, px);
 }
 
 extern "C" {
 
 static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
-                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz);
+                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz,
+                                const P2pFuse& px = P2pFuse{});
 
 int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s, const int32_t* idx,
                             int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream) {
@@ -695,7 +892,8 @@ int32_t rtd3_td3_actor_step(rtd3_td3* h, const float* params, const float* param
 }  // extern "C"
 
 static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* params_t, float* grads, float* scratch, const float* rp_s,
-                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz) {
+                                const int32_t* idx, int32_t batch, float* loss1, int32_t* steps, double* beta_pows, void* stream, const AdamFuse& fz,
+                                const P2pFuse& px) {
   RTD3_CHECK_ARG(h && params && params_t && grads && scratch && rp_s && idx && loss1 && steps && beta_pows, "null argument");
   RTD3_CHECK_ARG(batch > 0, "batch must be positive");
   ReplayView rp{(const float2*)rp_s, nullptr, nullptr, nullptr, nullptr};
@@ -715,7 +913,7 @@ static int32_t actor_step_fused(rtd3_td3* h, const float* params, const float* p
   WgradSlots slots;
   slots.grad_off[0] = h->ar.off(0); slots.grad_off[1] = 0;
   slots.scratch_off[0] = 0; slots.scratch_off[1] = 0;
-  return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st, fz);
+  return launch_wgrad(h, h->ar.actor, scratch, grads, slots, 1, batch, st, fz, px);
 }
 
 extern "C" {
@@ -840,7 +1038,25 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
   // Single GPU, fp32 step kernels, batch <= 512 (no split weight-gradient pass): the optimiser - and on actor epochs the Polyak
   // blends - run inside the weight-gradient kernels; the critics' targets are blended right after the critics' Adam step of the
   // same epoch (the actor step in between reads neither the targets nor changes the critics: robot.py:278-285 gives the same values)
-  const bool fuse = a->world == 1 && !tc && B <= 512;
+  // Data parallel over peer memory, same conditions: the weight-gradient kernels also exchange their gradient tiles with the peers
+  // before they apply the optimiser (P2pFuse) - no all-reduce launch at all.  RTD3_P2P_FUSE: 2 (default) this form, 1 the all-reduce
+  // kernel that applies the optimiser (p2p_allreduce_adam_kernel), 0 all-reduce and optimiser as two kernels (development)
+  static const int p2p_fuse_env = getenv("RTD3_P2P_FUSE") ? atoi(getenv("RTD3_P2P_FUSE")) : 2;
+  const bool fuse_wg = a->world > 1 && a->p2p && p2p_fuse_env >= 2 && !tc && B <= 512 && 2 * wgrad_jobs(h->ar.critic) <= kP2pBlockFlags &&
+                       wgrad_jobs(h->ar.actor) <= kP2pBlockFlags && a->p2p->slot_floats >= 2 * std::max(off_c, n_online - off_c);
+  const bool fuse = (a->world == 1 || fuse_wg) && !tc && B <= 512;
+  auto px_for = [&](bool actor) {
+    P2pFuse px{};
+    if (!fuse_wg) return px;
+    px.prof = g_p2p_prof;
+    for (int r = 0; r < a->world; ++r) {
+      px.recv[r] = a->p2p->peer_recv[r];
+    }
+    px.world = a->world; px.rank = a->p2p->rank;
+    px.seq_counter = (unsigned long long*)a->p2p->seq_counter; px.block_counter = a->p2p->block_counter;
+    px.stride = a->p2p->slot_floats; px.slice_off = actor ? 0 : off_c; px.grad_scale = scale;
+    return px;
+  };
   auto fuse_for = [&](bool actor, bool polyak) {
     AdamFuse fz{};
     fz.params = a->params; fz.params_t = a->params_t; fz.params_uv = a->params_uv; fz.m = a->adam_m; fz.v = a->adam_v;
@@ -850,8 +1066,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
   };
   // Data parallel over peer memory: the all-reduce kernel applies the optimiser to the sums it forms (one launch and one pass over the
   // arena less per optimiser step); RTD3_P2P_FUSE=0 keeps the two-kernel form (development)
-  static const bool p2p_fuse_env = !(getenv("RTD3_P2P_FUSE") && atoi(getenv("RTD3_P2P_FUSE")) == 0);
-  const bool fuse_p2p = a->world > 1 && a->p2p && p2p_fuse_env;
+  const bool fuse_p2p = a->world > 1 && a->p2p && p2p_fuse_env >= 1 && !fuse_wg;
   auto p2p_opt = [&](int nets, int polyak, int64_t off) {
     P2pAdamArgs o{};
     o.ar = h->ar; o.params = a->params; o.params_t = a->params_t; o.params_uv = a->params_uv; o.m = a->adam_m; o.v = a->adam_v;
@@ -871,7 +1086,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
                                  a->beta_pows, st);
     else
       rc = critic_step_fused(h, a->params, a->params_t, a->grads, a->scratch, rp, ix, nz, B, hp, a->critic_losses + 2 * e, nullptr, nullptr,
-                             a->steps, a->beta_pows, st, fuse ? fuse_for(false, e % delay == 0) : AdamFuse{});
+                             a->steps, a->beta_pows, st, fuse ? fuse_for(false, e % delay == 0) : AdamFuse{}, px_for(false));
     if (rc) return rc;
     if (fuse_p2p) {
       if ((rc = p2p_allreduce_adam_launch(a->p2p, a->grads, n_online - off_c, p2p_opt(0b110, 0, off_c), st))) return rc;
@@ -888,7 +1103,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
         rc = rtd3_td3_actor_step_tf32(h, a->params, a->params_uv, a->grads, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st);
       else
         rc = actor_step_fused(h, a->params, a->params_t, a->grads, a->scratch, a->rp_s, ixa, B, a->actor_losses + ka, a->steps, a->beta_pows, st,
-                              fuse ? fuse_for(true, true) : AdamFuse{});
+                              fuse ? fuse_for(true, true) : AdamFuse{}, px_for(true));
       ++ka;
       if (rc) return rc;
       if (fuse_p2p) {
@@ -904,6 +1119,14 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
   (void)rp_actor;
   if (!a->noise) return advance_noise_counter(a->noise_counter, (uint64_t)E, st);
   return 0;
+}
+
+/* development: copies the stage stamps of the last fused weight-gradient + peer-exchange launch ([256 blocks][2 threads][8 stages]
+ * uint64 nanoseconds) to the host; returns 0 when RTD3_P2P_PROF=1 was not set */
+int32_t rtd3_debug_p2p_prof(uint64_t* out_host) {
+  if (!g_p2p_prof || !out_host) return 0;
+  RTD3_CUDA(cudaMemcpy(out_host, g_p2p_prof, kP2pBlockFlags * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 1;
 }
 
 }  // extern "C"

@@ -426,9 +426,10 @@ class TD3:
         if world > 8:
             raise ValueError("the peer-memory all-reduce serves up to 8 ranks (one NVSwitch box)")
         G = self.grads.numel()
-        # receive slots [2][world][G] | flags: uint64 [16] per rank (rtd3_p2p_allreduce) + [8][256] per (rank, block) (the fused all-reduce
+        S = 2 * G           # floats per slot: a gradient slice in the line form of the fused weight-gradient exchange ({value, step} pairs)
+        # receive slots [2][world][S] | flags: uint64 [16] per rank (rtd3_p2p_allreduce) + [8][256] per (rank, block) (the fused all-reduce
         # + optimiser of rtd3_td3_update)
-        buf = torch.zeros((2 * world * G + 2 * (16 + 8 * 256),), dtype=torch.float32, device=self.device)
+        buf = torch.zeros((2 * world * S + 2 * (16 + 8 * 256),), dtype=torch.float32, device=self.device)
         torch.cuda.synchronize(self.device)
         handles = [None] * world
         dist.all_gather_object(handles, reduce_tensor(buf), group=pg)
@@ -443,12 +444,12 @@ class TD3:
             peers.append(fn(*args))
         self._grads_sum = torch.zeros((G,), dtype=torch.float32, device=self.device)
         c = ctypes.c_void_p * world
-        self._p2p = {"peers": peers, "rank": rank, "seq": torch.zeros((1,), dtype=torch.int64, device=self.device), "count": G,
-                     "recv": c(*[t.data_ptr() for t in peers]), "flags": c(*[t.data_ptr() + 4 * 2 * world * G for t in peers]),
+        self._p2p = {"peers": peers, "rank": rank, "seq": torch.zeros((1,), dtype=torch.int64, device=self.device), "count": G, "slot": S,
+                     "recv": c(*[t.data_ptr() for t in peers]), "flags": c(*[t.data_ptr() + 4 * 2 * world * S for t in peers]),
                      "counter": torch.zeros((1,), dtype=torch.int32, device=self.device)}
         p = self._p2p
         p["struct"] = _lib.P2pStateStruct(ctypes.cast(p["recv"], ctypes.c_void_p), ctypes.cast(p["flags"], ctypes.c_void_p), rank, world,
-                                          p["seq"].data_ptr(), self._grads_sum.data_ptr(), G, p["counter"].data_ptr())
+                                          p["seq"].data_ptr(), self._grads_sum.data_ptr(), S, p["counter"].data_ptr())
         torch.cuda.synchronize(self.device)
         dist.barrier(group=pg)                          # every rank has mapped every buffer before the first launch
 
@@ -565,7 +566,7 @@ class TD3:
         if self._p2p is not None:
             p = self._p2p
             _lib.check(_lib.lib().rtd3_p2p_allreduce(p["recv"], p["flags"], p["rank"], self.world, _lib.ptr(p["seq"]), _lib.ptr(self._grads_sum[off:]),
-                                                     _lib.ptr(self.grads[off:]), count, p["count"], _lib.ptr(p["counter"]), _lib.stream_ptr(self.device)),
+                                                     _lib.ptr(self.grads[off:]), count, p["slot"], _lib.ptr(p["counter"]), _lib.stream_ptr(self.device)),
                        "p2p_allreduce")
         else:
             _lib.check(_lib.lib().rtd3_allreduce_grads(self._comm, _lib.ptr(self.grads[off:]), count, _lib.stream_ptr(self.device)), "allreduce_grads")
