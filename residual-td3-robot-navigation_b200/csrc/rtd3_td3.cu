@@ -186,7 +186,9 @@ struct AdamFuse {
 // step s kernel has ended, i.e. after every block of A has seen B's step s lines, which B pushes only after its step s - 1 kernel has
 // ended - so when A overwrites slot [(s + 1) & 1], B has finished reading it.  A reader that sees no line within 20 s traps.
 struct P2pFuse {
-  float* recv[kP2pMaxWorld];
+  float* recv[kP2pMaxWorld];          // rank q's receive area as mapped here
+  float* mine;                        // = recv[rank] (a field of its own: indexing the kernel parameter with a run-time rank would
+                                      // send the whole struct through local memory)
   int world;                          // 0: no exchange
   int rank;
   unsigned long long* seq_counter;    // last completed step (device memory: a replayed graph counts on by itself)
@@ -194,6 +196,7 @@ struct P2pFuse {
   int64_t stride;                     // floats between the [parity][rank] slots of a receive area (>= 2 x the largest slice)
   int64_t slice_off;                  // arena offset of the slice this optimiser step reduces
   float grad_scale;                   // 1 / world
+  int mode;                           // 0 all to all, 1 reduce-scatter + all-gather (p2p_exchange4)
   unsigned long long* prof;           // development (RTD3_P2P_PROF=1): %globaltimer stamps [block][2 threads][8 stages], else nullptr
 };
 __device__ __forceinline__ void p2p_stamp(const P2pFuse& px, int cta, int k) {
@@ -223,70 +226,152 @@ __device__ __forceinline__ uint2 ld_half(const float* p) {
   asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void p2p_push4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float4 v) {
+// `only` = -1: to every peer; else to that rank alone
+__device__ __forceinline__ void p2p_push4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float4 v, int only) {
   const int64_t at = p2p_slot(px, seq, px.rank, arena_idx);
 #pragma unroll
   for (int q = 0; q < kP2pMaxWorld; ++q)
-    if (q < px.world && q != px.rank) {
+    if (q < px.world && q != px.rank && (only < 0 || q == only)) {
       st_line(px.recv[q] + at, v.x, v.y, seq);
       st_line(px.recv[q] + at + 4, v.z, v.w, seq);
     }
 }
-__device__ __forceinline__ void p2p_push1(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float v) {
+__device__ __forceinline__ void p2p_push1(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float v, int only) {
   const int64_t at = p2p_slot(px, seq, px.rank, arena_idx);
 #pragma unroll
   for (int q = 0; q < kP2pMaxWorld; ++q)
-    if (q < px.world && q != px.rank) st_half(px.recv[q] + at, v, seq);
+    if (q < px.world && q != px.rank && (only < 0 || q == only)) st_half(px.recv[q] + at, v, seq);
 }
 __device__ __forceinline__ void p2p_spin_check(unsigned long long& t0) {
   const unsigned long long now = global_ns();
   if (t0 == 0ull) t0 = now;
   else if (now - t0 > kSpinLimitNs) asm volatile("trap;");
 }
-// sum over the ranks in rank order (own contribution from registers), times grad_scale; polls until every peer's lines carry `seq`
+// sum over the ranks in rank order (own contribution from registers), times grad_scale.  The lines of ALL peers are requested before
+// the first one is examined (one round trip for W - 1 peers when they have arrived, instead of W - 1 dependent ones); a line that does
+// not carry `seq` yet is polled.
 __device__ __forceinline__ float4 p2p_sum4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float4 own) {
-  float4 v[kP2pMaxWorld];
-  const float* mine = px.recv[px.rank];
+  const float* mine = px.mine;
+  uint4 a[kP2pMaxWorld], b[kP2pMaxWorld];
+#pragma unroll
+  for (int r = 0; r < kP2pMaxWorld; ++r)
+    if (r < px.world && r != px.rank) {
+      const float* at = mine + p2p_slot(px, seq, r, arena_idx);
+      a[r] = ld_line(at); b[r] = ld_line(at + 4);
+    }
   unsigned long long t0 = 0ull;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < kP2pMaxWorld; ++r) {
     if (r >= px.world) continue;
-    if (r == px.rank) { v[r] = own; continue; }
-    const float* at = mine + p2p_slot(px, seq, r, arena_idx);
-    uint4 a = ld_line(at), b = ld_line(at + 4);
-    while (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
-      p2p_spin_check(t0);
-      a = ld_line(at); b = ld_line(at + 4);
+    float4 v = own;
+    if (r != px.rank) {
+      const float* at = mine + p2p_slot(px, seq, r, arena_idx);
+      while (a[r].y != seq || a[r].w != seq || b[r].y != seq || b[r].w != seq) {
+        p2p_spin_check(t0);
+        a[r] = ld_line(at); b[r] = ld_line(at + 4);
+      }
+      v = make_float4(__uint_as_float(a[r].x), __uint_as_float(a[r].z), __uint_as_float(b[r].x), __uint_as_float(b[r].z));
     }
-    v[r] = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+    if (r == 0) acc = v;
+    else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
   }
-  float4 acc = v[0];
-#pragma unroll
-  for (int r = 1; r < kP2pMaxWorld; ++r)
-    if (r < px.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
   return make_float4(acc.x * px.grad_scale, acc.y * px.grad_scale, acc.z * px.grad_scale, acc.w * px.grad_scale);
 }
-__device__ __forceinline__ float p2p_sum1(const P2pFuse& px, unsigned int seq, int64_t arena_idx, float own) {
-  float v[kP2pMaxWorld];
-  const float* mine = px.recv[px.rank];
+// the same for kN scalars of one thread (slot elements idx[i], live[i] = the thread owns element i): all kN x (W - 1) halves are requested first
+template <int kN>
+__device__ __forceinline__ void p2p_sum_n(const P2pFuse& px, unsigned int seq, const int64_t (&idx)[kN], const bool (&live)[kN], float (&val)[kN]) {
+  const float* mine = px.mine;
+  uint2 h[kN][kP2pMaxWorld];
+#pragma unroll
+  for (int i = 0; i < kN; ++i)
+#pragma unroll
+    for (int r = 0; r < kP2pMaxWorld; ++r)
+      if (live[i] && r < px.world && r != px.rank) h[i][r] = ld_half(mine + p2p_slot(px, seq, r, idx[i]));
   unsigned long long t0 = 0ull;
 #pragma unroll
-  for (int r = 0; r < kP2pMaxWorld; ++r) {
-    if (r >= px.world) continue;
-    if (r == px.rank) { v[r] = own; continue; }
-    const float* at = mine + p2p_slot(px, seq, r, arena_idx);
-    uint2 a = ld_half(at);
-    while (a.y != seq) {
-      p2p_spin_check(t0);
-      a = ld_half(at);
-    }
-    v[r] = __uint_as_float(a.x);
-  }
-  float acc = v[0];
+  for (int i = 0; i < kN; ++i) {
+    if (!live[i]) continue;
+    float acc = 0.f;
 #pragma unroll
-  for (int r = 1; r < kP2pMaxWorld; ++r)
-    if (r < px.world) acc += v[r];
-  return acc * px.grad_scale;
+    for (int r = 0; r < kP2pMaxWorld; ++r) {
+      if (r >= px.world) continue;
+      float v = val[i];
+      if (r != px.rank) {
+        const float* at = mine + p2p_slot(px, seq, r, idx[i]);
+        while (h[i][r].y != seq) {
+          p2p_spin_check(t0);
+          h[i][r] = ld_half(at);
+        }
+        v = __uint_as_float(h[i][r].x);
+      }
+      acc = r == 0 ? v : acc + v;
+    }
+    val[i] = acc * px.grad_scale;
+  }
+}
+// the lines rank `from` pushed for this element, as they are
+__device__ __forceinline__ float4 p2p_take4(const P2pFuse& px, unsigned int seq, int64_t arena_idx, int from) {
+  const float* at = px.mine + p2p_slot(px, seq, from, arena_idx);
+  unsigned long long t0 = 0ull;
+  uint4 a = ld_line(at), b = ld_line(at + 4);
+  while (a.y != seq || a.w != seq || b.y != seq || b.w != seq) {
+    p2p_spin_check(t0);
+    a = ld_line(at); b = ld_line(at + 4);
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+template <int kN>
+__device__ __forceinline__ void p2p_take_n(const P2pFuse& px, unsigned int seq, const int64_t (&idx)[kN], const bool (&live)[kN], float (&val)[kN], int from) {
+  const float* mine = px.mine;
+  uint2 h[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i)
+    if (live[i]) h[i] = ld_half(mine + p2p_slot(px, seq, from, idx[i]));
+  unsigned long long t0 = 0ull;
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    if (!live[i]) continue;
+    while (h[i].y != seq) {
+      p2p_spin_check(t0);
+      h[i] = ld_half(mine + p2p_slot(px, seq, from, idx[i]));
+    }
+    val[i] = __uint_as_float(h[i].x);
+  }
+}
+// The exchange of a block's elements.  mode 0 (all to all): push to every peer, add all W contributions - one hop, (W - 1) x the bytes.
+// mode 1 (reduce-scatter + all-gather, for W > 2): the block's OWNER rank (block % W) receives the W - 1 partial values, adds them in
+// rank order and pushes the finished, scaled sum to every peer; the other ranks push to the owner alone and take the owner's sum as it
+// is (bit-identical replicas) - two hops, 2 (W - 1) / W x the bytes per rank instead of (W - 1) x.  The owner's sums travel in slot
+// [parity][owner] of the receivers' areas: at those positions nothing else arrives there (partial values only go to the owner's area).
+__device__ __forceinline__ float4 p2p_exchange4(const P2pFuse& px, unsigned int seq, int owner, int64_t arena_idx, float4 v) {
+  if (px.mode == 0) {
+    p2p_push4(px, seq, arena_idx, v, -1);
+    return p2p_sum4(px, seq, arena_idx, v);
+  }
+  if (px.rank == owner) {
+    v = p2p_sum4(px, seq, arena_idx, v);
+    p2p_push4(px, seq, arena_idx, v, -1);
+    return v;
+  }
+  p2p_push4(px, seq, arena_idx, v, owner);
+  return p2p_take4(px, seq, arena_idx, owner);
+}
+template <int kN>
+__device__ __forceinline__ void p2p_exchange_n(const P2pFuse& px, unsigned int seq, int owner, const int64_t (&idx)[kN], const bool (&live)[kN], float (&val)[kN]) {
+  const bool reduce_here = px.mode == 0 || px.rank == owner;
+  if (px.mode == 0 || !reduce_here) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i)
+      if (live[i]) p2p_push1(px, seq, idx[i], val[i], px.mode == 0 ? -1 : owner);
+  }
+  if (reduce_here) p2p_sum_n<kN>(px, seq, idx, live, val);
+  else p2p_take_n<kN>(px, seq, idx, live, val, owner);
+  if (px.mode != 0 && reduce_here) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i)
+      if (live[i]) p2p_push1(px, seq, idx[i], val[i], -1);
+  }
 }
 // bookkeeping of a step, by one thread per block: the last block to come by (every block has read the step number) advances it
 __device__ __forceinline__ void p2p_step_done(const P2pFuse& px, unsigned long long seq64, int ncta) {
@@ -310,7 +395,7 @@ struct WgradSlots {
 constexpr int kWgradRows = 256;                                   // batch rows staged per pass
 constexpr size_t kWgradSmem = 2 * kWgradRows * 32 * sizeof(float);  // dz slab + layer-input slab (the partial tiles alias them)
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)     // two blocks per SM: the whole grid is resident at once (the peer exchange needs it)
 wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ grads, WgradSlots slots, int B, int rows_per_split, AdamFuse fz,
              P2pFuse px) {
   __shared__ __align__(16) float red_small[8][32 * 5];
@@ -451,9 +536,7 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     if (px.world) {
       p2p_stamp(px, cta, 1);
-      if (out_ok) p2p_push4(px, seq, G0 + off, v);
-      p2p_stamp(px, cta, 2);
-      if (out_ok) v = p2p_sum4(px, seq, G0 + off, v);
+      if (out_ok) v = p2p_exchange4(px, seq, cta % px.world, G0 + off, v);
       p2p_stamp(px, cta, 5);
     }
     if (out_ok) {
@@ -500,17 +583,17 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     }
     p2p_stamp(px, cta, 6);
   } else if (job < nT + nS) {
+    // bias gradients of hidden layer l for 32 units (and, l = 0, the first-layer weights).  After the batch reduction warp q finishes
+    // value q of unit n = lane (q = 0 the bias, 1 + j the weight of input j): one optimiser element - and one peer exchange - per
+    // thread instead of five dependent ones in warp 0.
     const int l = (job - nT) / nch, n = ((job - nT) % nch) * 32 + lane;
     const float* dz = rs.dz(l);
     const float* in0 = rs.in0();
     float ab = 0.f, aw[4] = {0.f, 0.f, 0.f, 0.f};
-    OptPre pre[5];
-    if (warp == 0 && n < H) {
-      pre[0] = pre_load(G0, net_b_off(s, l) + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (l == 0 && j < s.in) pre[1 + j] = pre_load(G0, net_w_off(s, 0) + n * s.in + j);
-    }
+    const bool own = warp < 5 && n < H && (warp == 0 || (l == 0 && warp - 1 < s.in));
+    const int64_t o = warp == 0 ? net_b_off(s, l) + n : net_w_off(s, 0) + (int64_t)n * s.in + (warp - 1);
+    OptPre pre{0.f, 0.f, 0.f, 0.f};
+    if (own) pre = pre_load(G0, o);
     if (n < H) {
 #pragma unroll 8
       for (int b = b_lo + warp; b < b_hi; b += 8) {
@@ -525,46 +608,29 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     float* r = &red_small[warp][lane * 5];
     r[0] = ab; r[1] = aw[0]; r[2] = aw[1]; r[3] = aw[2]; r[4] = aw[3];
     __syncthreads();
-    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    const bool own = warp == 0 && n < H;
+    float v[1] = {0.f};
     if (own)
-      for (int w = 0; w < 8; ++w)
-        for (int q = 0; q < 5; ++q) v[q] += red_small[w][lane * 5 + q];
+      for (int w = 0; w < 8; ++w) v[0] += red_small[w][lane * 5 + warp];
     if (px.world) {
-      if (own) {
-        p2p_push1(px, seq, G0 + net_b_off(s, l) + n, v[0]);
-        if (l == 0)
-          for (int j = 0; j < 4; ++j)
-            if (j < s.in) p2p_push1(px, seq, G0 + net_w_off(s, 0) + n * s.in + j, v[1 + j]);
-      }
-      if (own) {
-        v[0] = p2p_sum1(px, seq, G0 + net_b_off(s, l) + n, v[0]);
-        if (l == 0)
-          for (int j = 0; j < 4; ++j)
-            if (j < s.in) v[1 + j] = p2p_sum1(px, seq, G0 + net_w_off(s, 0) + n * s.in + j, v[1 + j]);
-      }
+      const int64_t ix[1] = {G0 + o};
+      const bool lv[1] = {own};
+      p2p_exchange_n<1>(px, seq, cta % px.world, ix, lv, v);
     }
     if (own) {
       if (fz.params) bias_corrections();
-      emit_pre(G0, net_b_off(s, l) + n, v[0], atomic, pre[0]);
-      if (l == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < s.in) emit_pre(G0, net_w_off(s, 0) + n * s.in + j, v[1 + j], atomic, pre[1 + j]);
-      }
+      emit_pre(G0, o, v[0], atomic, pre);
     }
   } else {
+    // output layer: warp o < 2 finishes W_L[o][k] for k = lane of this chunk, warp 2 of chunk 0 the biases
     const int chunk = job - nT - nS, k = chunk * 32 + lane;
     const float* hl = rs.h(L - 1);
     const float* dout = rs.dout();
     float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
-    OptPre pre[3];
-    if (warp == 0) {
-#pragma unroll
-      for (int o = 0; o < 2; ++o)
-        if (k < H && o < s.out) pre[o] = pre_load(G0, net_w_off(s, L) + (int64_t)o * H + k);
-      if (chunk == 0 && lane < s.out) pre[2] = pre_load(G0, net_b_off(s, L) + lane);
-    }
+    const bool own = (warp < 2 && warp < s.out && k < H) || (warp == 2 && chunk == 0 && lane < s.out);
+    const int64_t o = warp < 2 ? net_w_off(s, L) + (int64_t)warp * H + k : net_b_off(s, L) + lane;
+    const int q = warp < 2 ? warp : 2 + lane;                           // which of the four reduced values
+    OptPre pre{0.f, 0.f, 0.f, 0.f};
+    if (own) pre = pre_load(G0, o);
 #pragma unroll 8
     for (int b = b_lo + warp; b < b_hi; b += 8) {
       const float2 d = __ldg(reinterpret_cast<const float2*>(dout + (int64_t)b * 2));
@@ -575,33 +641,17 @@ wgrad_kernel(NetShape s, const float* __restrict__ scratch, float* __restrict__ 
     float* r = &red_small[warp][lane * 4];
     r[0] = a0; r[1] = a1; r[2] = s0; r[3] = s1;
     __syncthreads();
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (warp == 0)
-      for (int w = 0; w < 8; ++w)
-        for (int q = 0; q < 4; ++q) v[q] += red_small[w][lane * 4 + q];
+    float v[1] = {0.f};
+    if (own)
+      for (int w = 0; w < 8; ++w) v[0] += red_small[w][lane * 4 + q];
     if (px.world) {
-      const bool own_w = warp == 0 && k < H, own_b = warp == 0 && chunk == 0 && lane < s.out;
-      if (own_w)
-        for (int o = 0; o < 2; ++o)
-          if (o < s.out) p2p_push1(px, seq, G0 + net_w_off(s, L) + (int64_t)o * H + k, v[o]);
-      const float vb = lane == 0 ? v[2] : v[3];                        // v[2 + lane] of the bias lanes (s.out <= 2)
-      if (own_b) p2p_push1(px, seq, G0 + net_b_off(s, L) + lane, vb);
-      if (own_w)
-        for (int o = 0; o < 2; ++o)
-          if (o < s.out) v[o] = p2p_sum1(px, seq, G0 + net_w_off(s, L) + (int64_t)o * H + k, v[o]);
-      if (own_b) {
-        const float sb = p2p_sum1(px, seq, G0 + net_b_off(s, L) + lane, vb);
-        if (lane == 0) v[2] = sb; else v[3] = sb;
-      }
+      const int64_t ix[1] = {G0 + o};
+      const bool lv[1] = {own};
+      p2p_exchange_n<1>(px, seq, cta % px.world, ix, lv, v);
     }
-    if (warp == 0) {
+    if (own) {
       if (fz.params) bias_corrections();
-      if (k < H) {
-#pragma unroll
-        for (int o = 0; o < 2; ++o)
-          if (o < s.out) emit_pre(G0, net_w_off(s, L) + (int64_t)o * H + k, v[o], atomic, pre[o]);
-      }
-      if (chunk == 0 && lane < s.out) emit_pre(G0, net_b_off(s, L) + lane, v[2 + lane], atomic, pre[2]);
+      emit_pre(G0, o, v[0], atomic, pre);
     }
   }
 }
@@ -1042,6 +1092,7 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
   // before they apply the optimiser (P2pFuse) - no all-reduce launch at all.  RTD3_P2P_FUSE: 2 (default) this form, 1 the all-reduce
   // kernel that applies the optimiser (p2p_allreduce_adam_kernel), 0 all-reduce and optimiser as two kernels (development)
   static const int p2p_fuse_env = getenv("RTD3_P2P_FUSE") ? atoi(getenv("RTD3_P2P_FUSE")) : 2;
+  static const int p2p_mode_env = getenv("RTD3_P2P_MODE") ? atoi(getenv("RTD3_P2P_MODE")) : -1;   // development: force the exchange pattern
   const bool fuse_wg = a->world > 1 && a->p2p && p2p_fuse_env >= 2 && !tc && B <= 512 && 2 * wgrad_jobs(h->ar.critic) <= kP2pBlockFlags &&
                        wgrad_jobs(h->ar.actor) <= kP2pBlockFlags && a->p2p->slot_floats >= 2 * std::max(off_c, n_online - off_c);
   const bool fuse = (a->world == 1 || fuse_wg) && !tc && B <= 512;
@@ -1052,9 +1103,11 @@ int32_t rtd3_td3_update(rtd3_td3* h, const rtd3_td3_update_args* a, void* stream
     for (int r = 0; r < a->world; ++r) {
       px.recv[r] = a->p2p->peer_recv[r];
     }
+    px.mine = a->p2p->peer_recv[a->p2p->rank];
     px.world = a->world; px.rank = a->p2p->rank;
     px.seq_counter = (unsigned long long*)a->p2p->seq_counter; px.block_counter = a->p2p->block_counter;
     px.stride = a->p2p->slot_floats; px.slice_off = actor ? 0 : off_c; px.grad_scale = scale;
+    px.mode = p2p_mode_env >= 0 ? p2p_mode_env : (a->world > 2 ? 1 : 0);
     return px;
   };
   auto fuse_for = [&](bool actor, bool polyak) {
