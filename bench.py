@@ -238,6 +238,18 @@ def cpu_td3_epochs_per_sec(B, H, L, epochs):
     return epochs / (time.perf_counter() - t0)
 
 
+def dp_step_form(agent, B, tf32, world):
+    """Which form the optimiser step of the data-parallel learner takes (decided inside rtd3_td3_update, csrc/rtd3_td3.cu)."""
+    if world == 1:
+        return None
+    if getattr(agent, "dp_collective", None) != "p2p":
+        return "rtd3_allreduce_grads (NCCL, in the update graph) + optimiser kernel"
+    if not tf32 and B <= 512 and int(os.environ.get("RTD3_P2P_FUSE", "2")) >= 2:
+        return ("weight-gradient kernels exchange their own gradient tiles over peer memory ({value, step} lines, no fence, no all-reduce launch; %s) "
+                "and apply Adam / Polyak to the sums" % ("all to all" if world <= 2 else "reduce-scatter + all-gather by block owner"))
+    return "p2p_allreduce_adam_kernel: peer-memory all-reduce that applies Adam / Polyak to the sums (one cooperative launch per optimiser step)"
+
+
 def bench_td3(rt, torch, dev, world, rank, cpu):
     import torch.distributed as dist
     out = []
@@ -288,6 +300,7 @@ def bench_td3(rt, torch, dev, world, rank, cpu):
                                                                            if rt._lib.lib().rtd3_td3_cluster_supported(agent._handle, B)
                                                                            else "row-tile step kernels (rtd3_td3_update)"))),
                "dp_collective": getattr(agent, "dp_collective", None) if world > 1 else None,
+               "dp_step": dp_step_form(agent, B, tf32, world),
                "update_ms": round(ms_update, 3), "sampler_ms": round(ms_sample, 3), "us_per_epoch": round(1e3 * ms_update / epochs, 2),
                "td3_update_call_ms": round(ms_call, 3), "updates_per_sec": epochs / (ms_call * 1e-3),
                "updates_per_sec_update_only": epochs / (ms_update * 1e-3),
