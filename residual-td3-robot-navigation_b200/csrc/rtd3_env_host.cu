@@ -19,8 +19,9 @@ struct HostGraph {
   cudaGraphExec_t exec;
 };
 
+static std::mutex g_pipe_mu;         // one host-buffer call at a time per process: creation, capture and the graph cache are not re-entrant
+
 struct HostPipe {
-  std::mutex mu;
   cudaStream_t cap = nullptr, s_in = nullptr, s_out = nullptr;
   float *d_act = nullptr, *d_traj = nullptr;
   size_t floats = 0;                 // capacity of each staging buffer
@@ -154,11 +155,11 @@ extern "C" int32_t rtd3_env_rollout_host(rtd3_env* h, float* x, float* y, const 
   int prev = 0;
   RTD3_CUDA(cudaGetDevice(&prev));
   if (prev != h->device) RTD3_CUDA(cudaSetDevice(h->device));
+  std::lock_guard<std::mutex> lock(g_pipe_mu);
   HostPipe* p = nullptr;
   int32_t rc = pipe_prepare(h, &p, (size_t)(2 * n * T), 2 * chunks + 2);
   cudaGraphExec_t exec = nullptr;
   if (rc == 0) {
-    std::lock_guard<std::mutex> lock(p->mu);
     for (auto& g : p->graphs)
       if (g.x == x && g.y == y && g.act == actions_host && g.traj == traj_host && g.n == n && g.T == T && g.chunks == chunks && g.mode == mode)
         exec = g.exec;
