@@ -185,6 +185,10 @@ struct AdamFuse {
 // Why the two parity slots suffice: the steps of a rank are kernel launches in stream order; rank A's step s + 1 kernel starts after its
 // step s kernel has ended, i.e. after every block of A has seen B's step s lines, which B pushes only after its step s - 1 kernel has
 // ended - so when A overwrites slot [(s + 1) & 1], B has finished reading it.  A reader that sees no line within 20 s traps.
+// Stale words: a slot position that a line step last wrote carries an OLDER step number (never this one: the counter only grows, and the
+// area starts zeroed while steps start at 1).  The all-reduce kernels of rtd3_p2p.cu (larger batches) share the area and leave raw
+// gradient floats there; one of those would have to equal the current step number bit for bit - a denormal of the order of 1e-39 for
+// the first billion steps - to be mistaken for a line.
 struct P2pFuse {
   float* recv[kP2pMaxWorld];          // rank q's receive area as mapped here
   float* mine;                        // = recv[rank] (a field of its own: indexing the kernel parameter with a run-time rank would
